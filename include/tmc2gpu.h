@@ -226,6 +226,9 @@ TMC2_API tmc2_status tmc2gpu_last_launch_info(tmc2gpu_ctx* ctx, uint32_t* kernel
 /* Device time of the unpack kernel alone over the last reconstruct_resident, measured with CUDA
  * events recorded on the launching stream (synchronises). */
 TMC2_API tmc2_status tmc2gpu_last_unpack_ms(tmc2gpu_ctx* ctx, float* ms);
+/* All stage times of the last launch: ms[0] block_to_patch, [1] unpack, [2] geometry smoothing, [3] colour
+ * smoothing, [4] final YUV->RGB pass (0 when the stage did not run). */
+TMC2_API tmc2_status tmc2gpu_last_stage_ms(tmc2gpu_ctx* ctx, float* ms5);
 
 /* ---- stage entry points: one frame, host buffers in and out, synchronous ------------------------
  * These mirror the reference's own function boundaries so parity tests read like the reference.

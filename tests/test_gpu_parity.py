@@ -1,0 +1,255 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run on a B200: pytest -m gpu."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import util
+from oracle import oracle
+from tmc2rs_b200 import abi, codec, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def both(ctx, gof, frame=0):
+    view = abi.GofView(gof)
+    return ctx.generate_point_cloud(view, frame), oracle.reconstruct_frame(view, frame)
+
+
+def test_appendix_c_known_answer(gpu_ctx):
+    g = synth.kat_appendix_c()
+    got, want = both(gpu_ctx, g)
+    util.assert_same(got, want, what="appendix C")
+    assert got["block_to_patch"].tolist() == [1, 2] and got["point_count"] == 48
+    assert got["positions"][24].tolist() == [20, 940, 14] and got["positions"][29].tolist() == [21, 938, 14]
+    b2p = gpu_ctx.generate_block_to_patch_from_occupancy_map_video(abi.GofView(g), 0)
+    assert b2p.tolist() == [1, 2]
+
+
+CASES = [
+    dict(seed=1, orientations=(0, 1)),
+    dict(seed=2, orientations=(0, 1), absolute_d1=False),
+    dict(seed=3, orientations=(0, 1, 8), extreme=True),
+    dict(seed=4, orientations=tuple(range(9)), spec=True),
+    dict(seed=5, orientations=tuple(range(9)), spec=False, n_patches=6),
+    dict(seed=6, orientations=(0, 1), prec=2),
+    dict(seed=7, orientations=(0, 1), prec=1, W=48, H=32),
+    dict(seed=8, orientations=(0, 1, 3, 5), spec=True, res=8, prec=4, W=40, H=32),
+    dict(seed=9, orientations=(0, 1), attr=False),
+    dict(seed=10, orientations=tuple(range(9)), spec=True, absolute_d1=False, extreme=True),
+    dict(seed=11, orientations=(0, 1), W=208, H=112, n_patches=14),
+    dict(seed=12, orientations=tuple(range(9)), spec=True, W=208, H=112, n_patches=14, extreme=True),
+    dict(seed=13, orientations=(0, 1), prec=3, W=48, H=48),
+    dict(seed=14, orientations=(0, 1, 2, 4, 6), spec=False, res=32, W=128, H=96, prec=4),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items() if k != "orientations"))
+def test_random_small_atlases_bit_exact(gpu_ctx, case):
+    g = util.random_small_gof(**case)
+    got, want = both(gpu_ctx, g)
+    keys = [k for k in util.STREAMS if g.params.attribute_count or k not in ("colors", "colors16bit")]
+    util.assert_same(got, want, keys=keys, what=str(case))
+
+
+def test_config1_full_frame_bit_exact(gpu_ctx):
+    """BASELINE config 1: 1024x1024, 2 maps, precision 4, no smoothing, ~800k points."""
+    g = synth.make_gof(synth.config("c1"))
+    got, want = both(gpu_ctx, g)
+    assert 700_000 < want["point_count"] < 900_000
+    util.assert_same(got, want, what="c1")
+
+
+def test_two_pass_scan_equals_single_pass(gpu_ctx):
+    g = synth.make_gof(synth.config("small"))
+    view = abi.GofView(g)
+    ctx2 = codec.Context(two_pass_scan=True)
+    try:
+        for f in range(g.frame_count):
+            a = gpu_ctx.generate_point_cloud(view, f)
+            b = ctx2.generate_point_cloud(view, f)
+            util.assert_same(a, b, what=f"two-pass frame {f}")
+            util.assert_same(a, oracle.reconstruct_frame(view, f), what=f"frame {f}")
+    finally:
+        ctx2.close()
+
+
+def test_streaming_gof_in_order_and_deterministic(gpu_ctx):
+    """submit_gof / next_frame: frames come back in order (src/lib.rs:81), identical on every run."""
+    g = synth.make_gof(synth.config("small", frames=5))
+    view = abi.GofView(g)
+    first = gpu_ctx.decode_gof(view)
+    second = gpu_ctx.decode_gof(view)
+    assert gpu_ctx.next_frame() is None
+    for f, (a, b) in enumerate(zip(first, second)):
+        want = oracle.reconstruct_frame(view, f)
+        assert len(a) == want["point_count"]
+        assert np.array_equal(a.positions, want["positions"]) and np.array_equal(a.colors, want["colors"])
+        assert np.array_equal(a.positions, b.positions) and np.array_equal(a.colors, b.colors)
+        assert a.with_colors
+
+
+def test_streaming_pinned_zero_staging_and_two_gofs_in_flight(gpu_ctx):
+    g = synth.make_gof(synth.config("small", frames=4))
+    gp = codec.pinned_copy_of(g)
+    v, vp = abi.GofView(g), abi.GofView(gp)
+    gpu_ctx.submit_gof(vp)
+    gpu_ctx.submit_gof(v)                      # second GOF while the first is still in flight
+    with pytest.raises(abi.Tmc2Error) as e:    # third one would need a third slot
+        gpu_ctx.submit_gof(v)
+    assert e.value.status == abi.ERR_STATE
+    frames = [gpu_ctx.next_frame() for _ in range(8)]
+    assert gpu_ctx.next_frame() is None
+    for k, fr in enumerate(frames):
+        want = oracle.reconstruct_frame(v, k % 4)
+        assert np.array_equal(fr.positions, want["positions"]) and np.array_equal(fr.colors, want["colors"])
+
+
+def test_resident_path_matches(gpu_ctx):
+    g = synth.make_gof(synth.config("small", frames=3))
+    view = abi.GofView(g)
+    r = gpu_ctx.upload_gof(view)
+    try:
+        r.reconstruct()
+        r.reconstruct()                       # relaunch on resident planes: same answer
+        counts = r.counts()
+        for f in range(3):
+            want = oracle.reconstruct_frame(view, f)
+            assert int(counts[f]) == want["point_count"]
+            pos, col = r.fetch(f, int(counts[f]))
+            assert np.array_equal(pos, want["positions"]) and np.array_equal(col, want["colors"])
+        k, nbytes, total = gpu_ctx.last_launch_info()
+        assert k >= 2 and total == int(counts.sum()) and nbytes > 0
+    finally:
+        r.free()
+
+
+def test_color_conversion_bit_exact(gpu_ctx):
+    rng = np.random.RandomState(3)
+    yuv = np.concatenate([rng.randint(0, 1024, (200000, 3)), rng.randint(0, 65536, (50000, 3)),
+                          [[512, 512, 512], [1023, 512, 512], [0, 512, 512], [512, 512, 1023], [0, 0, 0],
+                           [1023, 1023, 1023], [65535, 0, 65535]]]).astype(np.uint16)
+    got = gpu_ctx.convert_yuv16_to_rgb8(yuv)
+    want = oracle.convert_yuv10_to_rgb8(yuv)
+    assert np.array_equal(got, want)
+    assert got[-7:].tolist() == [[127, 127, 127], [255, 255, 255], [0, 0, 0], [255, 67, 127], [0, 83, 0],
+                                 [255, 171, 255], [255, 255, 255]]
+
+
+def test_exhaustive_10bit_luma_chroma_slices(gpu_ctx):
+    """Every (Y, V) pair at U=512 and every (Y, U) pair at V=512 for 10-bit input: 2 M colours, bit-exact."""
+    y, c = np.meshgrid(np.arange(1024), np.arange(1024), indexing="ij")
+    a = np.stack([y.ravel(), np.full(y.size, 512), c.ravel()], 1)
+    b = np.stack([y.ravel(), c.ravel(), np.full(y.size, 512)], 1)
+    yuv = np.concatenate([a, b]).astype(np.uint16)
+    got = gpu_ctx.convert_yuv16_to_rgb8(yuv)
+    # the oracle's scalar loop through ctypes is slow: check a strided sample exactly, and the full set by checksum of
+    # a vectorised float64 numpy evaluation (numpy does not fuse multiply-add either)
+    yy, uu, vv = (yuv[:, i].astype(np.float64) for i in range(3))
+    r = yy + 1.57480 * (vv - 512.0)
+    gg = yy - 0.18733 * (uu - 512.0) - (0.46813 * (vv - 512.0))
+    bb = yy + 1.85563 * (uu - 512.0)
+    want = np.stack([np.clip(np.floor(ch / 1023.0 * 255.0), 0, 255) for ch in (r, gg, bb)], 1).astype(np.uint8)
+    assert np.array_equal(got, want)
+    idx = np.arange(0, len(yuv), 997)
+    assert np.array_equal(got[idx], oracle.convert_yuv10_to_rgb8(yuv[idx]))
+
+
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_smoothing_matches_own_spec_oracle(gpu_ctx, name):
+    """Boundary detection + grid geometry smoothing + grid colour smoothing: the reference has only stubs for these
+    (parity unpinned upstream); the CUDA kernels must equal the repository's integer spec exactly.  The +-1 report that
+    north_star asks for is printed as well (expected: 0 differing points)."""
+    g = synth.make_gof(synth.config(name))
+    g.params.geometry_smoothing = True
+    g.params.color_smoothing = True
+    got, want = both(gpu_ctx, g)
+    util.assert_same(got, want, keys=("positions_presmooth", "colors16bit_presmooth", "partition", "boundary_type"),
+                     what=name + " pre-smoothing")
+    dpos = np.abs(got["positions"].astype(int) - want["positions"].astype(int)).max(axis=1)
+    dcol = np.abs(got["colors"].astype(int) - want["colors"].astype(int)).max(axis=1)
+    print(f"{name}: points {want['point_count']}, moved gpu/oracle {got['smoothed_positions']}/{want['smoothed_positions']}, "
+          f"recoloured {got['smoothed_colors']}/{want['smoothed_colors']}, |dpos|>0: {(dpos > 0).sum()}, "
+          f"|dpos|>1: {(dpos > 1).sum()}, |dcol|>0: {(dcol > 0).sum()}, |dcol|>1: {(dcol > 1).sum()}")
+    assert (dpos <= 1).all() and (dcol <= 1).all()        # north_star tolerance
+    util.assert_same(got, want, keys=("positions", "colors16bit", "colors"), what=name + " smoothed")   # own spec: exact
+    assert got["smoothed_positions"] == want["smoothed_positions"]
+    assert got["smoothed_colors"] == want["smoothed_colors"]
+
+
+def test_smoothing_dense_overlap_case(gpu_ctx):
+    """Patches forced into the same 3D region so that many cells hold several patches (lots of smoothing work)."""
+    g = synth.make_gof(synth.config("small"))
+    for p in g.patches:
+        p["u1"] = 100 + (np.arange(len(p)) % 3)
+        p["v1"] = 100 + (np.arange(len(p)) % 2)
+        p["d1"] = np.where(p["projection_mode"] == 0, 64, 1024 - 64 - 300)
+        p["normal_axis"], p["tangent_axis"], p["bitangent_axis"] = 0, 2, 1
+    g.params.geometry_smoothing = True
+    g.params.color_smoothing = True
+    got, want = both(gpu_ctx, g, 1)
+    assert want["smoothed_positions"] > 100 and want["smoothed_colors"] > 100
+    util.assert_same(got, want, keys=("positions", "colors16bit", "colors", "boundary_type"), what="dense overlap")
+    # streaming path with smoothing gives the same frames
+    frames = gpu_ctx.decode_gof(abi.GofView(g))
+    assert np.array_equal(frames[1].positions, want["positions"]) and np.array_equal(frames[1].colors, want["colors"])
+    assert frames[1].smoothed_positions == want["smoothed_positions"]
+
+
+def test_error_codes_where_the_reference_panics(gpu_ctx):
+    g = util.random_small_gof(seed=11)
+    mk = lambda **kw: abi.GofView(abi.Gof(g.width, g.height, kw.get("occ", g.occ), g.geo, g.attr_y, g.attr_u, g.attr_v,
+                                          kw.get("patches", g.patches), kw.get("params", g.params),
+                                          kw.get("geo_video_frames"), kw.get("attr_video_frames")))
+    bad = g.patches[0].copy(); bad["u0"][0] = 1000
+    cases = [(mk(patches=[bad]), abi.ERR_PATCH_OUT_OF_CANVAS), (mk(geo_video_frames=1), abi.ERR_SHORT_VIDEO),
+             (mk(attr_video_frames=1), abi.ERR_SHORT_VIDEO),
+             (mk(params=abi.Params(**{**g.params.__dict__, "map_count_minus1": 0})), abi.ERR_MAP_COUNT),
+             (mk(params=abi.Params(**{**g.params.__dict__, "enhanced_occupancy_map": True})), abi.ERR_UNSUPPORTED),
+             (mk(params=abi.Params(**{**g.params.__dict__, "occupancy_precision": 8})), abi.ERR_INVALID_ARG)]
+    for view, code in cases:
+        with pytest.raises(abi.Tmc2Error) as e:
+            gpu_ctx.generate_point_cloud(view, 0)
+        assert e.value.status == code
+        with pytest.raises(abi.Tmc2Error) as e:
+            gpu_ctx.submit_gof(view)
+        assert e.value.status == code
+    # the context is still usable afterwards
+    got, want = both(gpu_ctx, g)
+    util.assert_same(got, want, what="after errors")
+
+
+def test_empty_and_blank_frames(gpu_ctx):
+    g = util.random_small_gof(seed=12, frames=3)
+    patches = [g.patches[0][:0], g.patches[1], g.patches[2]]
+    occ = g.occ.copy(); occ[1] = 0
+    g2 = abi.Gof(g.width, g.height, occ, g.geo, g.attr_y, g.attr_u, g.attr_v, patches, g.params)
+    view = abi.GofView(g2)
+    frames = gpu_ctx.decode_gof(view)
+    assert len(frames[0]) == 0 and len(frames[1]) == 0
+    want = oracle.reconstruct_frame(view, 2)
+    assert np.array_equal(frames[2].positions, want["positions"]) and np.array_equal(frames[2].colors, want["colors"])
+
+
+def test_config2_gof_properties_at_full_size(gpu_ctx):
+    """BASELINE config 2 (32 frames, 1024x1024, smoothing on) through the resident path: size-independent properties
+    (determinism, per-frame independence, counts) + exact oracle parity on a sample of frames."""
+    cfg = synth.config("c2", frames=8)
+    base = synth.make_gof(cfg)
+    g = synth.replicate_gof(base, 32)          # 32 frames cycling 8 distinct ones
+    view = abi.GofView(g)
+    r = gpu_ctx.upload_gof(view)
+    try:
+        r.reconstruct()
+        counts = r.counts()
+        assert (counts.reshape(4, 8) == counts[:8]).all()          # replicated frames -> identical counts
+        sha = lambda f: hashlib.sha256(b"".join(a.tobytes() for a in r.fetch(f, int(counts[f])))).hexdigest()
+        assert sha(3) == sha(11) == sha(27)                        # frame independence inside the batch
+        r.reconstruct()
+        assert (r.counts() == counts).all() and sha(5) == sha(13)  # deterministic relaunch
+        for f in (0, 7, 30):
+            want = oracle.reconstruct_frame(view, f)
+            pos, col = r.fetch(f, int(counts[f]))
+            assert np.array_equal(pos, want["positions"]) and np.array_equal(col, want["colors"])
+    finally:
+        r.free()

@@ -1,0 +1,131 @@
+// device_types.h -- PODs shared by the host runtime (tmc2gpu.cu) and the sm_100a kernels (kernels.cu).
+//
+// HBM layout of one batch (a GOF, or the slice of a GOF given to one GPU); F frames, M = 2 maps:
+//   occ    [F][occ_h][occ_pitch]       u8   low-resolution occupancy video     (reference atlas.occ_frames)
+//   geo    [F][2][H][geo_pitch]        u16  geometry video, channel 0 only     (reference atlas.geo_frames[0], frame f*2+m)
+//   attr_y [F][2][H][attr_pitch_y]     u16  attribute video, channel 0         (reference atlas.attr_frames[0])
+//   attr_u [F][2][H/2][attr_pitch_c]   u16  channel 1 (4:2:0)      attr_v likewise
+//   patches[total]  DevPatch ; slot_patch[n_tiles*kWarpsPerTile] ; tile_frame[n_tiles] ; frame_tile_begin[F+1]
+//   block_to_patch [F][bw*bh] u32
+// Pitches are multiples of 64 elements so every 16x16 canvas block row starts on a 32-byte boundary.
+// Outputs are per-frame slabs of `cap` points:  pos [F][cap][3] u16, rgb [F][cap][3] u8, yuv [F][cap][3] u16,
+// partition [F][cap] u16, pixel [F][cap] u32 (x | y<<15 | map<<30), btype [F][cap] u8, count [F] u32.
+#pragma once
+#include <cstdint>
+
+namespace tmc2 {
+
+constexpr int kWarpsPerTile = 8;            // one warp per 16x16 patch block ("slot"); one CTA per tile of 8 slots
+constexpr uint32_t kNoPatch = 0xFFFFFFFFu;  // padding slot
+constexpr int kSlotPoints = 512;            // max points of a 16x16 block (2 maps)
+
+struct DevPatch {            // reference Patch (src/decoder.rs:711-783), pre-digested on the host
+  int32_t  x0, y0;           // uv0 * occupancy_resolution  (pixels)
+  uint32_t u0, v0;           // uv0 (blocks)
+  uint32_t size_u0, size_v0; // size_uv0 (blocks)
+  uint32_t u1, v1, d1;       // 3D shifts
+  uint16_t lod_x, lod_y;
+  uint8_t  normal, tangent, bitangent, mode;
+  uint8_t  orient, _pad[3];
+  uint32_t slot_base;        // index of this patch's first slot in slot_patch[]
+  uint32_t local_index;      // patch index inside its frame (partition value; block_to_patch holds local_index+1)
+  uint32_t frame;            // frame inside the batch
+};
+
+struct Planes {
+  const uint8_t*  occ;
+  const uint16_t* geo;
+  const uint16_t* attr_y;
+  const uint16_t* attr_u;
+  const uint16_t* attr_v;
+  uint32_t occ_pitch, occ_w, occ_h;
+  uint32_t geo_pitch, attr_pitch_y, attr_pitch_c;
+  uint64_t occ_frame_stride;     // elements between frames
+  uint64_t geo_map_stride;       // elements between maps (frame stride = 2x)
+  uint64_t attr_y_map_stride;
+  uint64_t attr_c_map_stride;
+};
+
+struct Outputs {                // any pointer may be null = stream not wanted
+  uint16_t* pos;
+  uint8_t*  rgb;
+  uint16_t* yuv;
+  uint16_t* part;
+  uint32_t* pix;
+  uint8_t*  btype;
+  uint64_t  cap;                // points per frame slab
+};
+
+struct UnpackArgs {
+  Planes   in;
+  Outputs  out;
+  uint32_t W, H, res, prec;
+  int32_t  prec_shift;          // log2(prec) or -1 when prec is not a power of two
+  uint32_t bw, bh;              // block grid (W/res, H/res)
+  uint32_t n_frames, n_tiles;
+  uint8_t  absolute_d1, spec_orientation, has_attr, want_btype;
+  const DevPatch* patches;
+  const uint32_t* slot_patch;
+  const uint32_t* tile_frame;
+  const uint32_t* frame_tile_begin;   // [F+1]
+  const uint32_t* block_to_patch;     // [F][bw*bh]
+  uint64_t*       tile_status;        // chained-scan state, one word per tile
+  uint32_t        epoch;              // launch tag inside the status words (no memset between launches)
+  uint32_t*       tile_total;         // two-pass mode: per-tile totals (count kernel) / exclusive bases (emit kernel)
+  uint32_t*       frame_count;        // [F] points per frame
+  int*            err;                // device error flag (0 ok)
+  // byte offsets of each staged stream inside a warp's shared-memory region, and the region size
+  uint32_t off_pos, off_rgb, off_yuv, off_part, off_pix, off_bt, warp_bytes;
+};
+
+// ---- sparse voxel-cell table used by grid geometry / colour smoothing (own spec) ----------------------
+struct GeoCell {     // 32 B = one DRAM sector
+  uint32_t key;      // cx | cy<<10 | cz<<20 ; 0xFFFFFFFF = empty
+  uint32_t count;
+  uint32_t pmin, pmax;          // smallest / largest patch index seen
+  uint32_t sx, sy, sz;          // sums of (coordinate - cell origin)  (< grid size each)
+  uint32_t _pad;
+};
+struct ColCell {     // 64 B
+  uint32_t key, count, pmin, pmax;
+  unsigned long long sy, su, sv;   // sums of Y, U, V
+  unsigned long long sy2;          // sum of Y*Y
+  unsigned long long _pad[2];
+};
+constexpr uint32_t kCellEmpty = 0xFFFFFFFFu;
+
+struct GridArgs {
+  uint32_t g, w, disth, th;     // cell edge, cells per axis, border margin, g*w
+  uint32_t n_frames;
+  uint64_t cap;                 // points per frame slab
+  uint64_t table_slots;         // per frame, power of two
+  uint32_t identity_hash;       // 1: slot = dense cell index (table covers the whole grid)
+  const uint32_t* frame_count;
+  uint16_t* pos;                // in/out (geometry filter writes)
+  uint16_t* yuv;                // in/out (colour filter writes)
+  const uint16_t* part;
+  const uint8_t*  btype;
+  void*     table;              // GeoCell[F][slots] or ColCell[F][slots]
+  uint32_t* touched;            // [F][touched_cap] slots claimed during accumulate
+  uint32_t* touched_count;      // [F]
+  uint64_t  touched_cap;
+  uint32_t  thr_a, thr_b, thr_c; // geometry: threshold_smoothing ; colour: smoothing, difference, variation (scaled)
+  unsigned long long* changed;  // [F] moved / recoloured points
+  int*      err;
+};
+
+// launch wrappers (kernels.cu); every one enqueues on `stream` and returns the cudaGetLastError() code
+int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream);
+int launch_unpack(const UnpackArgs& a, int mode /*0 fused, 1 count, 2 emit*/, void* stream);
+int launch_tile_scan(const UnpackArgs& a, void* stream);
+int launch_upsample(const UnpackArgs& a, uint8_t* occ_full /*[F][H][W]*/, void* stream);
+int launch_geo_smoothing(const GridArgs& g, void* stream);     // accumulate + filter + clear
+int launch_color_smoothing(const GridArgs& g, void* stream);   // accumulate + filter + clear
+int launch_yuv_to_rgb(const uint16_t* yuv, uint8_t* rgb, const uint32_t* frame_count, uint32_t n_frames, uint64_t cap,
+                      void* stream);
+int launch_yuv_to_rgb_flat(const uint16_t* yuv, uint8_t* rgb, uint64_t n, void* stream);
+int launch_table_init(void* table, uint64_t total_slots, int is_color, void* stream);
+size_t unpack_smem_bytes(const UnpackArgs& a);
+int kernel_launch_count_reset();   // returns launches since the last reset
+
+}  // namespace tmc2

@@ -1,0 +1,1002 @@
+// kernels.cu -- hand-written sm_100a kernels of the V-PCC rec0 reconstruction path.
+//
+//   K2  block_to_patch_kernel     src/codec.rs:205-250   (atomicMax == "later patch overwrites", :242-244)
+//   K1  upsample_kernel           src/codec.rs:288-300   (materialised only for the stage API; fused otherwise)
+//   K3+K4 unpack_kernel           src/codec.rs:352-480 (unpack loop, order, dedup), :517-565 (generate_points),
+//                                 :569-658 (attribute fetch), :661-687 (YUV->RGB), src/decoder.rs:827-888 (patch maths)
+//       + K5 boundary type per point (own spec)
+//   K6  geo_accumulate / geo_filter      grid geometry smoothing (own integer spec; reference stubs
+//   K7  col_accumulate / col_filter      decoder.rs:291-299)
+//       yuv_to_rgb_kernel         src/codec.rs:88-94 + :661-687
+//
+// Ordering.  The reference emits points in (patch, v0, u0, v1, u1, map) order.  A 16x16 patch block ("slot") that
+// owns its canvas block emits one contiguous run, so the output position of a run is an exclusive prefix sum of
+// per-slot counts in slot order.  unpack_kernel is ONE pass: a warp owns a slot, a CTA owns a tile of 8 consecutive
+// slots, and tiles publish / look back their prefix through `tile_status` (single-pass chained scan with decoupled
+// look-back, tile id == blockIdx.x, one scan domain per frame).  Nothing is read twice from HBM.
+//
+// All arithmetic on the bit-exact path is integer except the colour conversion, which is IEEE f64 with every operation
+// rounded separately (__dmul_rn/__dadd_rn/__ddiv_rn: no FMA contraction), exactly like the reference's Rust code.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "device_types.h"
+
+namespace tmc2 {
+
+static int g_launches = 0;
+int kernel_launch_count_reset() { int n = g_launches; g_launches = 0; return n; }
+
+// ----------------------------------------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ uint32_t div_prec(uint32_t x, uint32_t prec, int shift) {
+  return shift >= 0 ? (x >> shift) : (x / prec);
+}
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {   // streaming 16-byte load, no L1 allocation
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t u16_of(const uint4& v, int j) {   // j-th u16 of a 16-byte vector (j constant)
+  const uint32_t w = (j >> 1) == 0 ? v.x : (j >> 1) == 1 ? v.y : (j >> 1) == 2 ? v.z : v.w;
+  return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+__device__ __forceinline__ uint32_t u16_of(const uint2& v, int j) {
+  const uint32_t w = (j >> 1) == 0 ? v.x : v.y;
+  return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+
+// ---- Patch maths, src/decoder.rs:853-888 --------------------------------------------------------------------------
+// Forward map patch (u,v) -> canvas (x,y), decoder.rs:853-867.  `sscale` multiplies size_uv0: 1 reproduces the
+// reference (sizes stay in blocks even at pixel level), `res` is the spec-correct form.  Signed 64-bit arithmetic: the
+// host has verified that every pixel of the patch lands inside the canvas, where wrapping usize and i64 agree.
+__device__ __forceinline__ void patch_to_canvas(const DevPatch& P, int64_t u, int64_t v, int64_t res, int64_t sscale,
+                                                int64_t& x, int64_t& y) {
+  const int64_t u0 = (int64_t)P.u0 * res, v0 = (int64_t)P.v0 * res;
+  const int64_t su = (int64_t)P.size_u0 * sscale, sv = (int64_t)P.size_v0 * sscale;
+  switch (P.orient) {
+    case 0:  x = u + u0;           y = v + v0;           break;   // Default
+    case 2:  x = sv - 1 - v + u0;  y = u + v0;           break;   // Rot90
+    case 3:  x = su - 1 - u + u0;  y = sv - 1 - v + v0;  break;   // Rot180
+    case 4:  x = v + u0;           y = su - 1 - u + v0;  break;   // Rot270
+    case 5:  x = su - 1 - u + u0;  y = v + v0;           break;   // Mirror
+    case 6:  x = sv - 1 - v + u0;  y = su - 1 - u + v0;  break;   // MRot90
+    case 7:  x = u + u0;           y = sv - 1 - v + v0;  break;   // MRot180
+    default: x = v + u0;           y = u + v0;           break;   // Swap (1) and MRot270 (8)
+  }
+}
+// Inverse map canvas (x,y) -> patch (u,v) for block-aligned orientations (sizes scaled by res).
+__device__ __forceinline__ void canvas_to_patch(const DevPatch& P, int32_t x, int32_t y, int32_t res, int32_t& u,
+                                                int32_t& v) {
+  const int32_t dx = x - P.x0, dy = y - P.y0;
+  const int32_t su = (int32_t)P.size_u0 * res, sv = (int32_t)P.size_v0 * res;
+  switch (P.orient) {
+    case 0:  u = dx;          v = dy;          break;
+    case 2:  u = dy;          v = sv - 1 - dx; break;
+    case 3:  u = su - 1 - dx; v = sv - 1 - dy; break;
+    case 4:  u = su - 1 - dy; v = dx;          break;
+    case 5:  u = su - 1 - dx; v = dy;          break;
+    case 6:  u = su - 1 - dy; v = sv - 1 - dx; break;
+    case 7:  u = dx;          v = sv - 1 - dy; break;
+    default: u = dy;          v = dx;          break;
+  }
+}
+
+// generate_normal_coordinate (decoder.rs:881-888), truncated to u16 like the `as u16` cast at :874
+__device__ __forceinline__ uint32_t normal_coord(const DevPatch& P, uint32_t depth) {
+  const uint32_t n = P.mode == 0 ? depth + P.d1 : (P.d1 > depth ? P.d1 : depth) - depth;
+  return n & 0xFFFFu;
+}
+// generate_point (decoder.rs:871-878): sequential writes, later axes overwrite earlier ones if they coincide
+__device__ __forceinline__ void make_point(const DevPatch& P, uint32_t n, uint32_t t, uint32_t b, uint32_t out[3]) {
+  out[0] = out[1] = out[2] = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (P.normal == a) out[a] = n;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (P.tangent == a) out[a] = t;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (P.bitangent == a) out[a] = b;
+  }
+}
+
+// convert_yuv10_to_rgb8, src/codec.rs:661-687.  One channel: clamp(floor(c / 1023 * 255)).
+__device__ __forceinline__ uint32_t quant_channel(double c) {
+  const double q = floor(__dmul_rn(__ddiv_rn(c, 1023.0), 255.0));
+  if (q < 0.0) return 0u;
+  if (q > 255.0) return 255u;
+  return (uint32_t)q;
+}
+__device__ __forceinline__ uint32_t yuv_to_rgb_packed(uint32_t Y, uint32_t U, uint32_t V) {
+  const double y = (double)Y, u = __dsub_rn((double)U, 512.0), v = __dsub_rn((double)V, 512.0);
+  const double r = __dadd_rn(y, __dmul_rn(1.57480, v));
+  const double g = __dsub_rn(__dsub_rn(y, __dmul_rn(0.18733, u)), __dmul_rn(0.46813, v));
+  const double b = __dadd_rn(y, __dmul_rn(1.85563, u));
+  return quant_channel(r) | (quant_channel(g) << 8) | (quant_channel(b) << 16);
+}
+
+// occupancy of the full-resolution pixel (x,y) straight from the low-resolution video (codec.rs:294-298)
+__device__ __forceinline__ uint32_t occ_at(const UnpackArgs& a, const uint8_t* occ_f, uint32_t x, uint32_t y) {
+  return occ_f[(uint64_t)div_prec(y, a.prec, a.prec_shift) * a.in.occ_pitch + div_prec(x, a.prec, a.prec_shift)];
+}
+
+// K5: boundary type of an occupied pixel (own spec): 1 = image border or an unoccupied 4-neighbour, 2 = an unoccupied
+// pixel inside the 5x5 window (clipped to the image), 0 = interior.  Evaluated per low-resolution cell.
+__device__ uint32_t boundary_type(const UnpackArgs& a, const uint8_t* occ_f, int32_t x, int32_t y) {
+  const int32_t W = (int32_t)a.W, H = (int32_t)a.H;
+  if (x == 0 || y == 0 || x == W - 1 || y == H - 1) return 1;
+  if (!occ_at(a, occ_f, x - 1, y) || !occ_at(a, occ_f, x + 1, y) || !occ_at(a, occ_f, x, y - 1) ||
+      !occ_at(a, occ_f, x, y + 1))
+    return 1;
+  const int32_t xa = max(x - 2, 0), xb = min(x + 2, W - 1), ya = max(y - 2, 0), yb = min(y + 2, H - 1);
+  const uint32_t cxa = div_prec(xa, a.prec, a.prec_shift), cxb = div_prec(xb, a.prec, a.prec_shift);
+  const uint32_t cya = div_prec(ya, a.prec, a.prec_shift), cyb = div_prec(yb, a.prec, a.prec_shift);
+  for (uint32_t cy = cya; cy <= cyb; ++cy)
+    for (uint32_t cx = cxa; cx <= cxb; ++cx)
+      if (occ_f[(uint64_t)cy * a.in.occ_pitch + cx] == 0) return 2;
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// K2: block-to-patch map.  One warp per slot (= one 16x16 block of one patch).
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) block_to_patch_kernel(const UnpackArgs a, uint32_t n_slots,
+                                                             uint32_t* __restrict__ b2p) {
+  const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slot >= n_slots) return;
+  const uint32_t pid = a.slot_patch[slot];
+  if (pid == kNoPatch) return;
+  const DevPatch P = a.patches[pid];
+  const uint32_t s = slot - P.slot_base;
+  const uint32_t v0 = s / P.size_u0, u0 = s - v0 * P.size_u0;
+  int64_t bx, by;
+  patch_to_canvas(P, u0, v0, 1, 1, bx, by);                       // codec.rs:220-225 (block variant, resolution 1)
+  const uint8_t* occ_f = a.in.occ + (uint64_t)P.frame * a.in.occ_frame_stride;
+  const uint32_t lane = lane_id();
+  const uint32_t res = a.res;
+  bool nz = false;
+  const bool aligned = a.spec_orientation || P.orient <= 1 || P.orient == 8;
+  if (aligned) {
+    // the 16x16 patch pixels are exactly the canvas block: test the low-resolution samples that cover it
+    const uint32_t x0 = (uint32_t)bx * res, y0 = (uint32_t)by * res;
+    const uint32_t cxa = div_prec(x0, a.prec, a.prec_shift), cxb = div_prec(x0 + res - 1, a.prec, a.prec_shift);
+    const uint32_t cya = div_prec(y0, a.prec, a.prec_shift), cyb = div_prec(y0 + res - 1, a.prec, a.prec_shift);
+    const uint32_t nx = cxb - cxa + 1, n = nx * (cyb - cya + 1);
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint32_t cy = cya + i / nx, cx = cxa + i % nx;
+      nz |= occ_f[(uint64_t)cy * a.in.occ_pitch + cx] != 0;
+    }
+  } else {
+    // reference-literal pixel mapping for the rotated / mirrored orientations (codec.rs:227-241)
+    const int64_t sscale = a.spec_orientation ? res : 1;
+    for (uint32_t i = lane; i < res * res; i += 32) {
+      const uint32_t v1 = i / res, u1 = i - v1 * res;
+      int64_t x, y;
+      patch_to_canvas(P, (int64_t)u0 * res + u1, (int64_t)v0 * res + v1, res, sscale, x, y);
+      nz |= occ_at(a, occ_f, (uint32_t)x, (uint32_t)y) != 0;
+    }
+  }
+  if (__any_sync(0xFFFFFFFFu, nz) && lane == 0)
+    atomicMax(&b2p[(uint64_t)P.frame * a.bw * a.bh + (uint64_t)by * a.bw + (uint64_t)bx], P.local_index + 1);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// K1: occupancy upsample (codec.rs:288-300), materialised only when the caller asks for tile.occupancy_map.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample_kernel(const UnpackArgs a, uint8_t* __restrict__ occ_full) {
+  const uint64_t total = (uint64_t)a.n_frames * a.W * a.H;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t f = i / ((uint64_t)a.W * a.H);
+    const uint32_t r = (uint32_t)(i - f * a.W * a.H);
+    const uint32_t y = r / a.W, x = r - y * a.W;
+    occ_full[i] = (uint8_t)occ_at(a, a.in.occ + f * a.in.occ_frame_stride, x, y);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// K3+K4(+K5): fused unpack.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr unsigned long long kFlagAggregate = 1ull, kFlagInclusive = 2ull;
+__device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, unsigned long long flag, uint32_t value) {
+  return ((unsigned long long)epoch << 34) | (flag << 32) | value;
+}
+
+// copy `nbytes` staged at shared `sm` (which has the same 16-byte phase as global `g`) to global memory
+__device__ __forceinline__ void warp_copy_out(uint8_t* __restrict__ g, const uint8_t* sm, uint32_t nbytes, uint32_t lane) {
+  const uint32_t head = min(nbytes, (uint32_t)((16u - (uint32_t)((uintptr_t)g & 15u)) & 15u));
+  if (lane < head) g[lane] = sm[lane];
+  const uint32_t nvec = (nbytes - head) >> 4;
+  const uint4* s4 = reinterpret_cast<const uint4*>(sm + head);
+  uint4* g4 = reinterpret_cast<uint4*>(g + head);
+  for (uint32_t i = lane; i < nvec; i += 32) g4[i] = s4[i];
+  const uint32_t done = head + (nvec << 4);
+  if (done + lane < nbytes) g[done + lane] = sm[done + lane];
+}
+
+template <int kMode>   // 0: fused single pass (chained scan) ; 1: count only ; 2: emit with precomputed tile bases
+__global__ void __launch_bounds__(kWarpsPerTile * 32) unpack_kernel(const UnpackArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ uint32_t s_tot[kWarpsPerTile];
+  __shared__ uint32_t s_base;
+
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t tile = blockIdx.x;
+  const uint32_t slot = tile * kWarpsPerTile + warp;
+  const uint32_t frame = a.tile_frame[tile];
+  const uint32_t pid = a.slot_patch[slot];
+  const uint32_t res = a.res;
+
+  DevPatch P;
+  bool owned = false;
+  int32_t bx = 0, by = 0;
+  uint32_t u0b = 0, v0b = 0;
+  if (pid != kNoPatch) {
+    P = a.patches[pid];
+    const uint32_t s = slot - P.slot_base;
+    v0b = s / P.size_u0; u0b = s - v0b * P.size_u0;
+    int64_t bxx, byy;
+    patch_to_canvas(P, u0b, v0b, 1, 1, bxx, byy);                 // codec.rs:373-378
+    bx = (int32_t)bxx; by = (int32_t)byy;
+    owned = a.block_to_patch[(uint64_t)frame * a.bw * a.bh + (uint64_t)by * a.bw + bx] == P.local_index + 1;  // :379
+  }
+  const bool fast = owned && res == 16 && (a.spec_orientation || P.orient <= 1 || P.orient == 8);
+  const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
+  const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
+  const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
+
+  // ---- phase 1: load the block, decide which pixels emit 1 or 2 points ------------------------------------------
+  uint4 g0 = {0, 0, 0, 0}, g1 = {0, 0, 0, 0}, ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
+  uint2 ua = {0, 0}, va = {0, 0}, ub = {0, 0}, vb = {0, 0};
+  uint32_t m1 = 0, m2 = 0;     // fast path: bit j set = pixel j of this lane emits >=1 / 2 points
+  uint32_t total = 0;
+  const int32_t px = bx * 16 + (int32_t)(lane & 1) * 8;   // fast path: this lane's 8 canvas pixels (px..px+7, py)
+  const int32_t py = by * 16 + (int32_t)(lane >> 1);
+
+  if (fast) {
+    const uint64_t goff = (uint64_t)py * a.in.geo_pitch + px;
+    g0 = ldg_nc_v4(geo0 + goff);
+    g1 = ldg_nc_v4(geo1 + goff);
+    if (kMode != 1 && a.has_attr) {
+      const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride;
+      const uint64_t yoff = (uint64_t)py * a.in.attr_pitch_y + px;
+      ya = ldg_nc_v4(ay0 + yoff);
+      yb = ldg_nc_v4(ay0 + a.in.attr_y_map_stride + yoff);
+      const uint64_t coff = (uint64_t)(py >> 1) * a.in.attr_pitch_c + (px >> 1);
+      const uint64_t cf = (uint64_t)frame * 2 * a.in.attr_c_map_stride;
+      ua = ldg_nc_v2(a.in.attr_u + cf + coff);
+      va = ldg_nc_v2(a.in.attr_v + cf + coff);
+      ub = ldg_nc_v2(a.in.attr_u + cf + a.in.attr_c_map_stride + coff);
+      vb = ldg_nc_v2(a.in.attr_v + cf + a.in.attr_c_map_stride + coff);
+    }
+    // occupancy bits of the 8 pixels (codec.rs:393-396: any non-zero sample counts)
+    uint32_t occ_bits = 0;
+    {
+      const uint8_t* row = occ_f + (uint64_t)div_prec((uint32_t)py, a.prec, a.prec_shift) * a.in.occ_pitch;
+      uint32_t prev_c = 0xFFFFFFFFu, prev_v = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t c = div_prec((uint32_t)px + j, a.prec, a.prec_shift);
+        if (c != prev_c) { prev_c = c; prev_v = row[c]; }
+        occ_bits |= (prev_v != 0 ? 1u : 0u) << j;
+      }
+    }
+    m1 = occ_bits;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t d0 = u16_of(g0, j) >> 2, d1 = u16_of(g1, j) >> 2;          // codec.rs:534,548
+      const uint32_t n0 = normal_coord(P, d0);
+      uint32_t n1;
+      if (a.absolute_d1) n1 = normal_coord(P, d1);                               // :549-550
+      else n1 = (P.mode == 0 ? n0 + d1 : n0 - d1) & 0xFFFFu;                     // :551-558 (u16 wrap)
+      if (n1 != n0) m2 |= (occ_bits & (1u << j));                                // :422-428 duplicate skip
+    }
+    total = __reduce_add_sync(0xFFFFFFFFu, __popc(m1) + __popc(m2));
+  } else if (owned) {
+    // generic path (any resolution, reference-literal rotated orientations): lane = pixel, chunks of 32 in raster order
+    const int64_t sscale = a.spec_orientation ? res : 1;
+    for (uint32_t base = 0; base < res * res; base += 32) {
+      const uint32_t i = base + lane;
+      uint32_t c = 0;
+      if (i < res * res) {
+        const uint32_t v1 = i / res, u1 = i - v1 * res;
+        int64_t x, y;
+        patch_to_canvas(P, (int64_t)u0b * res + u1, (int64_t)v0b * res + v1, res, sscale, x, y);
+        if (occ_at(a, occ_f, (uint32_t)x, (uint32_t)y)) {
+          const uint64_t off = (uint64_t)y * a.in.geo_pitch + (uint64_t)x;
+          const uint32_t d0 = geo0[off] >> 2, d1 = geo1[off] >> 2;
+          const uint32_t n0 = normal_coord(P, d0);
+          const uint32_t n1 = a.absolute_d1 ? normal_coord(P, d1) : ((P.mode == 0 ? n0 + d1 : n0 - d1) & 0xFFFFu);
+          c = n1 != n0 ? 2u : 1u;
+        }
+      }
+      total += __reduce_add_sync(0xFFFFFFFFu, c);
+    }
+  }
+
+  if (lane == 0) s_tot[warp] = total;
+  __syncthreads();
+
+  // ---- tile prefix: chained scan over tiles of the same frame ----------------------------------------------------
+  if (kMode == 1) {
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+#pragma unroll
+      for (int w = 0; w < kWarpsPerTile; ++w) t += s_tot[w];
+      a.tile_total[tile] = t;
+    }
+    return;
+  }
+  if (warp == 0) {
+    uint32_t tile_sum = 0;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerTile; ++w) tile_sum += s_tot[w];
+    uint32_t excl = 0;
+    const uint32_t first_tile = a.frame_tile_begin[frame];
+    if (kMode == 2) {
+      excl = a.tile_total[tile];
+    } else {
+      unsigned long long* status = reinterpret_cast<unsigned long long*>(a.tile_status);
+      if (tile == first_tile) {
+        if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagInclusive, tile_sum));
+      } else {
+        if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagAggregate, tile_sum));
+        int64_t look = (int64_t)tile - 1;
+        uint32_t spins = 0;
+        bool dead = false;
+        while (true) {
+          const int64_t idx = look - (int64_t)lane;
+          const bool valid = idx >= (int64_t)first_tile;
+          unsigned long long st = pack_status(a.epoch, kFlagInclusive, 0);       // before the frame: prefix 0
+          if (valid) st = ld_relaxed_u64(status + idx);
+          // wait until every predecessor in the window has published something for this launch
+          while (__any_sync(0xFFFFFFFFu, valid && ((st >> 34) != a.epoch || ((st >> 32) & 3ull) == 0))) {
+            if (++spins > (1u << 22)) { dead = true; break; }                    // watchdog: never hang the GPU
+            __nanosleep(40);
+            if (valid) st = ld_relaxed_u64(status + idx);
+          }
+          if (dead) { if (lane == 0) atomicExch(a.err, 11); break; }
+          const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, ((st >> 32) & 3ull) == kFlagInclusive);
+          const uint32_t upto = incl_mask ? (uint32_t)(__ffs(incl_mask) - 1) : 31u;   // nearest inclusive predecessor
+          const uint32_t v = lane <= upto ? (uint32_t)(st & 0xFFFFFFFFull) : 0u;
+          excl += __reduce_add_sync(0xFFFFFFFFu, v);
+          if (incl_mask) break;
+          look -= 32;
+        }
+        if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagInclusive, excl + tile_sum));
+      }
+    }
+    if (lane == 0) {
+      s_base = excl;
+      if (tile + 1 == a.frame_tile_begin[frame + 1]) a.frame_count[frame] = excl + tile_sum;  // codec.rs:482
+    }
+  }
+  __syncthreads();
+  if (!owned || total == 0) return;
+
+  uint32_t run_base = s_base;
+  for (uint32_t w = 0; w < warp; ++w) run_base += s_tot[w];
+  if ((uint64_t)run_base + total > a.out.cap) {                   // cannot happen for footprints inside the canvas
+    if (lane == 0) atomicExch(a.err, 7);
+    return;
+  }
+  const uint64_t gidx = (uint64_t)frame * a.out.cap + run_base;   // first point of this run
+
+  // ---- phase 2 ----------------------------------------------------------------------------------------------------
+  if (fast) {
+    uint8_t* wsm = smem + (size_t)warp * a.warp_bytes;
+    // (a) exclusive prefix of the per-pixel counts in PATCH-LOCAL raster order (v1 major, u1 minor; codec.rs:382-385)
+    uint8_t* cnt_sm = wsm;                                          // [256] counts by rank
+    uint16_t* pre_sm = reinterpret_cast<uint16_t*>(wsm + 256);      // [256] exclusive prefix by rank
+    uint32_t rank[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int32_t u, v;
+      canvas_to_patch(P, px + j, py, 16, u, v);
+      rank[j] = (uint32_t)((v & 15) * 16 + (u & 15));
+      cnt_sm[rank[j]] = (uint8_t)(((m1 >> j) & 1u) + ((m2 >> j) & 1u));
+    }
+    __syncwarp();
+    {
+      const uint2 c8 = *reinterpret_cast<const uint2*>(cnt_sm + lane * 8);
+      uint32_t c[8] = {c8.x & 255u, (c8.x >> 8) & 255u, (c8.x >> 16) & 255u, c8.x >> 24,
+                       c8.y & 255u, (c8.y >> 8) & 255u, (c8.y >> 16) & 255u, c8.y >> 24};
+      uint32_t sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += c[j];
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+      }
+      uint32_t run = incl - sum;
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o[j] = run; run += c[j]; }
+      uint4 packed;
+      packed.x = o[0] | (o[1] << 16); packed.y = o[2] | (o[3] << 16);
+      packed.z = o[4] | (o[5] << 16); packed.w = o[6] | (o[7] << 16);
+      *reinterpret_cast<uint4*>(pre_sm + lane * 8) = packed;
+    }
+    __syncwarp();
+    uint32_t off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) off[j] = pre_sm[rank[j]];
+    __syncwarp();                                                   // the scratch is reused as staging below
+
+    // (b) stage every output stream in shared memory at the same 16-byte phase as its global destination
+    uint8_t* g_pos = a.out.pos ? reinterpret_cast<uint8_t*>(a.out.pos) + gidx * 6 : nullptr;
+    uint8_t* g_rgb = a.out.rgb ? a.out.rgb + gidx * 3 : nullptr;
+    uint8_t* g_yuv = a.out.yuv ? reinterpret_cast<uint8_t*>(a.out.yuv) + gidx * 6 : nullptr;
+    uint8_t* g_part = a.out.part ? reinterpret_cast<uint8_t*>(a.out.part) + gidx * 2 : nullptr;
+    uint8_t* g_pix = a.out.pix ? reinterpret_cast<uint8_t*>(a.out.pix) + gidx * 4 : nullptr;
+    uint8_t* g_bt = a.out.btype ? a.out.btype + gidx : nullptr;
+    uint8_t* s_pos = wsm + a.off_pos + ((uintptr_t)g_pos & 15u);
+    uint8_t* s_rgb = wsm + a.off_rgb + ((uintptr_t)g_rgb & 15u);
+    uint8_t* s_yuv = wsm + a.off_yuv + ((uintptr_t)g_yuv & 15u);
+    uint8_t* s_part = wsm + a.off_part + ((uintptr_t)g_part & 15u);
+    uint8_t* s_pix = wsm + a.off_pix + ((uintptr_t)g_pix & 15u);
+    uint8_t* s_bt = wsm + a.off_bt + ((uintptr_t)g_bt & 15u);
+
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!((m1 >> j) & 1u)) continue;
+      int32_t u, v;
+      canvas_to_patch(P, px + j, py, 16, u, v);
+      const uint32_t t = ((uint32_t)u * P.lod_x + P.u1) & 0xFFFFu;             // decoder.rs:875
+      const uint32_t b = ((uint32_t)v * P.lod_y + P.v1) & 0xFFFFu;             // decoder.rs:876
+      const uint32_t d0 = u16_of(g0, j) >> 2, d1 = u16_of(g1, j) >> 2;
+      const uint32_t n0 = normal_coord(P, d0);
+      const uint32_t n1 = a.absolute_d1 ? normal_coord(P, d1) : ((P.mode == 0 ? n0 + d1 : n0 - d1) & 0xFFFFu);
+      const uint32_t npts = 1u + ((m2 >> j) & 1u);
+      uint32_t bt = 0;
+      if (g_bt) bt = boundary_type(a, occ_f, px + j, py);
+      for (uint32_t i = 0; i < npts; ++i) {                                     // map0 then map1 (codec.rs:421)
+        const uint32_t k = off[j] + i;
+        uint32_t pt[3];
+        make_point(P, i == 0 ? n0 : n1, t, b, pt);
+        if (g_pos) {
+          uint16_t* d = reinterpret_cast<uint16_t*>(s_pos + k * 6);
+          d[0] = (uint16_t)pt[0]; d[1] = (uint16_t)pt[1]; d[2] = (uint16_t)pt[2];
+        }
+        if (a.has_attr) {
+          const uint32_t Y = i == 0 ? u16_of(ya, j) : u16_of(yb, j);             // codec.rs:637-640, decoder.rs:976-977
+          const uint32_t U = i == 0 ? u16_of(ua, j >> 1) : u16_of(ub, j >> 1);
+          const uint32_t V = i == 0 ? u16_of(va, j >> 1) : u16_of(vb, j >> 1);
+          if (g_yuv) {
+            uint16_t* d = reinterpret_cast<uint16_t*>(s_yuv + k * 6);
+            d[0] = (uint16_t)Y; d[1] = (uint16_t)U; d[2] = (uint16_t)V;
+          }
+          if (g_rgb) {
+            const uint32_t c = yuv_to_rgb_packed(Y, U, V);
+            uint8_t* d = s_rgb + k * 3;
+            d[0] = (uint8_t)c; d[1] = (uint8_t)(c >> 8); d[2] = (uint8_t)(c >> 16);
+          }
+        }
+        if (g_part) *reinterpret_cast<uint16_t*>(s_part + k * 2) = (uint16_t)P.local_index;   // codec.rs:452
+        if (g_pix) *reinterpret_cast<uint32_t*>(s_pix + k * 4) = (uint32_t)(px + j) | ((uint32_t)py << 15) | (i << 30);
+        if (g_bt) s_bt[k] = (uint8_t)bt;
+      }
+    }
+    __syncwarp();
+    // (c) coalesced 16-byte stores of the contiguous run
+    if (g_pos) warp_copy_out(g_pos, s_pos, total * 6, lane);
+    if (g_rgb) warp_copy_out(g_rgb, s_rgb, total * 3, lane);
+    if (g_yuv) warp_copy_out(g_yuv, s_yuv, total * 6, lane);
+    if (g_part) warp_copy_out(g_part, s_part, total * 2, lane);
+    if (g_pix) warp_copy_out(g_pix, s_pix, total * 4, lane);
+    if (g_bt) warp_copy_out(g_bt, s_bt, total, lane);
+  } else {
+    // generic path: recompute and write straight to global memory
+    const int64_t sscale = a.spec_orientation ? res : 1;
+    uint64_t run = gidx;
+    for (uint32_t base = 0; base < res * res; base += 32) {
+      const uint32_t i = base + lane;
+      uint32_t c = 0, n0 = 0, n1 = 0, t = 0, b = 0;
+      int64_t x = 0, y = 0;
+      if (i < res * res) {
+        const uint32_t v1 = i / res, u1 = i - v1 * res;
+        const uint32_t u = u0b * res + u1, v = v0b * res + v1;
+        patch_to_canvas(P, u, v, res, sscale, x, y);
+        if (occ_at(a, occ_f, (uint32_t)x, (uint32_t)y)) {
+          const uint64_t off = (uint64_t)y * a.in.geo_pitch + (uint64_t)x;
+          const uint32_t d0 = geo0[off] >> 2, d1 = geo1[off] >> 2;
+          n0 = normal_coord(P, d0);
+          n1 = a.absolute_d1 ? normal_coord(P, d1) : ((P.mode == 0 ? n0 + d1 : n0 - d1) & 0xFFFFu);
+          c = n1 != n0 ? 2u : 1u;
+          t = (u * P.lod_x + P.u1) & 0xFFFFu;
+          b = (v * P.lod_y + P.v1) & 0xFFFFu;
+        }
+      }
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t tt = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (uint32_t)d) incl += tt;
+      }
+      const uint32_t chunk_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      uint64_t k = run + (incl - c);
+      uint32_t bt = 0;
+      if (c && a.out.btype) bt = boundary_type(a, occ_f, (int32_t)x, (int32_t)y);
+      for (uint32_t m = 0; m < c; ++m, ++k) {
+        uint32_t pt[3];
+        make_point(P, m == 0 ? n0 : n1, t, b, pt);
+        if (a.out.pos) { uint16_t* d = a.out.pos + k * 3; d[0] = (uint16_t)pt[0]; d[1] = (uint16_t)pt[1]; d[2] = (uint16_t)pt[2]; }
+        if (a.has_attr) {
+          const uint64_t fm = (uint64_t)frame * 2 + m;
+          const uint32_t Y = a.in.attr_y[fm * a.in.attr_y_map_stride + (uint64_t)y * a.in.attr_pitch_y + (uint64_t)x];
+          const uint64_t co = fm * a.in.attr_c_map_stride + (uint64_t)(y >> 1) * a.in.attr_pitch_c + (uint64_t)(x >> 1);
+          const uint32_t U = a.in.attr_u[co], V = a.in.attr_v[co];
+          if (a.out.yuv) { uint16_t* d = a.out.yuv + k * 3; d[0] = (uint16_t)Y; d[1] = (uint16_t)U; d[2] = (uint16_t)V; }
+          if (a.out.rgb) {
+            const uint32_t cc = yuv_to_rgb_packed(Y, U, V);
+            uint8_t* d = a.out.rgb + k * 3; d[0] = (uint8_t)cc; d[1] = (uint8_t)(cc >> 8); d[2] = (uint8_t)(cc >> 16);
+          }
+        }
+        if (a.out.part) a.out.part[k] = (uint16_t)P.local_index;
+        if (a.out.pix) a.out.pix[k] = (uint32_t)x | ((uint32_t)y << 15) | (m << 30);
+        if (a.out.btype) a.out.btype[k] = (uint8_t)bt;
+      }
+      run += chunk_total;
+    }
+  }
+}
+
+// two-pass mode: exclusive scan of tile totals inside each frame (one CTA per frame)
+__global__ void __launch_bounds__(256) tile_scan_kernel(const UnpackArgs a) {
+  const uint32_t f = blockIdx.x;
+  const uint32_t t0 = a.frame_tile_begin[f], t1 = a.frame_tile_begin[f + 1];
+  __shared__ uint32_t s_w[8];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t b = t0; b < t1; b += 256) {
+    const uint32_t i = b + threadIdx.x;
+    const uint32_t v = i < t1 ? a.tile_total[i] : 0;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane_id() >= (uint32_t)d) incl += t;
+    }
+    if (lane_id() == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t wbase = s_carry;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) wbase += s_w[w];
+    if (i < t1) a.tile_total[i] = wbase + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 255) s_carry = wbase + incl;
+    __syncthreads();
+  }
+  // frame_count is written by the emit kernel (last tile of the frame)
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// yuv -> rgb over finished point streams (codec.rs:88-94)
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) yuv_to_rgb_kernel(const uint16_t* __restrict__ yuv, uint8_t* __restrict__ rgb,
+                                                         const uint32_t* __restrict__ frame_count, uint64_t cap) {
+  const uint32_t f = blockIdx.y;
+  const uint32_t n = frame_count[f];
+  const uint16_t* src = yuv + (uint64_t)f * cap * 3;
+  uint8_t* dst = rgb + (uint64_t)f * cap * 3;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t c = yuv_to_rgb_packed(src[3 * (uint64_t)i], src[3 * (uint64_t)i + 1], src[3 * (uint64_t)i + 2]);
+    dst[3 * (uint64_t)i] = (uint8_t)c; dst[3 * (uint64_t)i + 1] = (uint8_t)(c >> 8); dst[3 * (uint64_t)i + 2] = (uint8_t)(c >> 16);
+  }
+}
+__global__ void __launch_bounds__(256) yuv_to_rgb_flat_kernel(const uint16_t* __restrict__ yuv, uint8_t* __restrict__ rgb,
+                                                              uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = yuv_to_rgb_packed(yuv[3 * i], yuv[3 * i + 1], yuv[3 * i + 2]);
+    rgb[3 * i] = (uint8_t)c; rgb[3 * i + 1] = (uint8_t)(c >> 8); rgb[3 * i + 2] = (uint8_t)(c >> 16);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// K6 / K7: sparse voxel-cell tables (own integer spec; see DESIGN.md "Smoothing specification")
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t cell_slot0(uint32_t key, const GridArgs& G) {
+  if (G.identity_hash) {
+    const uint64_t cx = key & 1023u, cy = (key >> 10) & 1023u, cz = key >> 20;
+    return cx + (uint64_t)G.w * (cy + (uint64_t)G.w * cz);
+  }
+  return (((uint64_t)key * 0x9E3779B97F4A7C15ull) >> 24) & (G.table_slots - 1);
+}
+
+template <typename Cell>
+__device__ __forceinline__ Cell* cell_insert(Cell* tab, uint32_t key, const GridArgs& G, uint32_t frame) {
+  uint64_t i = cell_slot0(key, G);
+  for (uint64_t probe = 0; probe < G.table_slots; ++probe) {
+    const uint32_t prev = atomicCAS(&tab[i].key, kCellEmpty, key);
+    if (prev == kCellEmpty) {
+      const uint32_t t = atomicAdd(&G.touched_count[frame], 1u);
+      if (t < G.touched_cap) G.touched[(uint64_t)frame * G.touched_cap + t] = (uint32_t)i;
+      else atomicExch(G.err, 11);
+      return &tab[i];
+    }
+    if (prev == key) return &tab[i];
+    i = (i + 1) & (G.table_slots - 1);
+  }
+  atomicExch(G.err, 11);
+  return nullptr;
+}
+template <typename Cell>
+__device__ __forceinline__ const Cell* cell_find(const Cell* tab, uint32_t key, const GridArgs& G) {
+  uint64_t i = cell_slot0(key, G);
+  for (uint64_t probe = 0; probe < G.table_slots; ++probe) {
+    const uint32_t k = tab[i].key;
+    if (k == key) return &tab[i];
+    if (k == kCellEmpty) return nullptr;
+    i = (i + 1) & (G.table_slots - 1);
+  }
+  return nullptr;
+}
+
+__device__ __forceinline__ bool in_grid(const GridArgs& G, uint32_t x, uint32_t y, uint32_t z) {
+  return x < G.th && y < G.th && z < G.th;
+}
+
+template <bool kColor>
+__global__ void __launch_bounds__(256) grid_accumulate_kernel(const GridArgs G) {
+  const uint32_t f = blockIdx.y;
+  const uint32_t n = G.frame_count[f];
+  const uint16_t* pos = G.pos + (uint64_t)f * G.cap * 3;
+  const uint16_t* yuv = kColor ? G.yuv + (uint64_t)f * G.cap * 3 : nullptr;
+  const uint16_t* part = G.part + (uint64_t)f * G.cap;
+  const uint32_t lane = lane_id();
+  const uint32_t n_round = (n + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    uint32_t key = kCellEmpty, rx = 0, ry = 0, rz = 0, pa = 0, Y = 0, U = 0, V = 0;
+    if (i < n) {
+      const uint32_t x = pos[3 * (uint64_t)i], y = pos[3 * (uint64_t)i + 1], z = pos[3 * (uint64_t)i + 2];
+      if (in_grid(G, x, y, z)) {
+        const uint32_t cx = x / G.g, cy = y / G.g, cz = z / G.g;
+        key = cx | (cy << 10) | (cz << 20);
+        rx = x - cx * G.g; ry = y - cy * G.g; rz = z - cz * G.g;
+        pa = part[i];
+        if (kColor) { Y = yuv[3 * (uint64_t)i]; U = yuv[3 * (uint64_t)i + 1]; V = yuv[3 * (uint64_t)i + 2]; }
+      }
+    }
+    // warp aggregation: one set of atomics per distinct cell in the warp (points arrive in patch-raster order, so
+    // neighbouring lanes mostly share a cell)
+    uint32_t remaining = __ballot_sync(0xFFFFFFFFu, key != kCellEmpty);
+    while (remaining) {
+      const uint32_t leader = __ffs(remaining) - 1;
+      const uint32_t k = __shfl_sync(0xFFFFFFFFu, key, leader);
+      const bool in = key == k;
+      const uint32_t grp = __ballot_sync(0xFFFFFFFFu, in);
+      const uint32_t cnt = __popc(grp);
+      const uint32_t pmin = __reduce_min_sync(0xFFFFFFFFu, in ? pa : 0xFFFFFFFFu);
+      const uint32_t pmax = __reduce_max_sync(0xFFFFFFFFu, in ? pa : 0u);
+      if (!kColor) {
+        const uint32_t sx = __reduce_add_sync(0xFFFFFFFFu, in ? rx : 0u);
+        const uint32_t sy = __reduce_add_sync(0xFFFFFFFFu, in ? ry : 0u);
+        const uint32_t sz = __reduce_add_sync(0xFFFFFFFFu, in ? rz : 0u);
+        if (lane == leader) {
+          GeoCell* c = cell_insert(reinterpret_cast<GeoCell*>(G.table) + (uint64_t)f * G.table_slots, k, G, f);
+          if (c) {
+            atomicAdd(&c->count, cnt); atomicMin(&c->pmin, pmin); atomicMax(&c->pmax, pmax);
+            atomicAdd(&c->sx, sx); atomicAdd(&c->sy, sy); atomicAdd(&c->sz, sz);
+          }
+        }
+      } else {
+        const uint32_t sY = __reduce_add_sync(0xFFFFFFFFu, in ? Y : 0u);
+        const uint32_t sU = __reduce_add_sync(0xFFFFFFFFu, in ? U : 0u);
+        const uint32_t sV = __reduce_add_sync(0xFFFFFFFFu, in ? V : 0u);
+        const uint32_t y2 = Y * Y;                                           // < 2^32
+        const uint32_t s2lo = __reduce_add_sync(0xFFFFFFFFu, in ? (y2 & 0xFFFFu) : 0u);
+        const uint32_t s2hi = __reduce_add_sync(0xFFFFFFFFu, in ? (y2 >> 16) : 0u);
+        if (lane == leader) {
+          ColCell* c = cell_insert(reinterpret_cast<ColCell*>(G.table) + (uint64_t)f * G.table_slots, k, G, f);
+          if (c) {
+            atomicAdd(&c->count, cnt); atomicMin(&c->pmin, pmin); atomicMax(&c->pmax, pmax);
+            atomicAdd(&c->sy, (unsigned long long)sY); atomicAdd(&c->su, (unsigned long long)sU);
+            atomicAdd(&c->sv, (unsigned long long)sV);
+            atomicAdd(&c->sy2, (unsigned long long)s2lo + ((unsigned long long)s2hi << 16));
+          }
+        }
+      }
+      remaining &= ~grp;
+    }
+  }
+}
+
+struct Nbhd { uint32_t key[8]; bool valid[8]; unsigned long long wgt[8]; unsigned long long w3; };
+__device__ __forceinline__ bool neighbourhood(const GridArgs& G, const uint32_t p[3], Nbhd& N) {
+  if (!in_grid(G, p[0], p[1], p[2])) return false;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    if (p[a] < G.disth || p[a] + G.disth >= G.th) return false;
+  int32_t s[3]; unsigned long long wa[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const uint32_t c = p[a] / G.g, rem = p[a] - c * G.g;
+    s[a] = (int32_t)c + (rem < G.g / 2 ? -1 : 0);
+    wa[a] = 2ull * (unsigned long long)((long long)p[a] - (long long)s[a] * (long long)G.g - (long long)(G.g / 2)) + 1ull;
+  }
+  const unsigned long long g2 = 2ull * G.g;
+  N.w3 = g2 * g2 * g2;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
+    const int32_t cx = s[0] + dx, cy = s[1] + dy, cz = s[2] + dz;
+    N.valid[k] = cx >= 0 && cy >= 0 && cz >= 0 && (uint32_t)cx < G.w && (uint32_t)cy < G.w && (uint32_t)cz < G.w;
+    N.key[k] = N.valid[k] ? ((uint32_t)cx | ((uint32_t)cy << 10) | ((uint32_t)cz << 20)) : kCellEmpty;
+    N.wgt[k] = (dx ? wa[0] : g2 - wa[0]) * (dy ? wa[1] : g2 - wa[1]) * (dz ? wa[2] : g2 - wa[2]);
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(256) geo_filter_kernel(const GridArgs G) {
+  const uint32_t f = blockIdx.y;
+  const uint32_t n = G.frame_count[f];
+  uint16_t* pos = G.pos + (uint64_t)f * G.cap * 3;
+  const uint8_t* bt = G.btype + (uint64_t)f * G.cap;
+  const GeoCell* tab = reinterpret_cast<const GeoCell*>(G.table) + (uint64_t)f * G.table_slots;
+  uint32_t moved = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (bt[i] != 1) continue;
+    uint32_t p[3] = {pos[3 * (uint64_t)i], pos[3 * (uint64_t)i + 1], pos[3 * (uint64_t)i + 2]};
+    Nbhd N;
+    if (!neighbourhood(G, p, N)) continue;
+    unsigned long long C[3] = {0, 0, 0}, cntw = 0;
+    bool other = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const GeoCell* c = N.valid[j] ? cell_find(tab, N.key[j], G) : nullptr;
+      uint32_t cnt = 0, s[3] = {0, 0, 0}, o[3] = {0, 0, 0};
+      if (c) {
+        cnt = c->count; s[0] = c->sx; s[1] = c->sy; s[2] = c->sz;
+        if (cnt > 0 && c->pmin != c->pmax) other = true;
+        o[0] = (N.key[j] & 1023u) * G.g; o[1] = ((N.key[j] >> 10) & 1023u) * G.g; o[2] = (N.key[j] >> 20) * G.g;
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        unsigned long long m = 256ull * p[a];
+        if (cnt > 0) m = 256ull * o[a] + (256ull * s[a] + cnt / 2) / cnt;      // cell mean, Q8
+        C[a] += N.wgt[j] * m;
+      }
+      cntw += N.wgt[j] * cnt;
+    }
+    if (!other) continue;
+    const unsigned long long count = cntw / N.w3;
+    if (count == 0) continue;
+    unsigned long long c4[3], D2 = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      c4[a] = (C[a] + N.w3 / 2) / N.w3;
+      const long long d = (long long)(256ull * p[a]) - (long long)c4[a];
+      D2 += (unsigned long long)(d * d);
+    }
+    const unsigned long long m = G.thr_a > count ? G.thr_a : count;
+    const unsigned __int128 lhs = (unsigned __int128)2 * count * D2 + 65536u;
+    const unsigned __int128 rhs = (unsigned __int128)262144u * m;
+    if (lhs >= rhs) {
+      bool changed = false;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        unsigned long long r = (c4[a] + 128) >> 8;
+        if (r > 65535) r = 65535;
+        changed |= (uint32_t)r != p[a];
+        pos[3 * (uint64_t)i + a] = (uint16_t)r;
+      }
+      moved += changed ? 1u : 0u;
+    }
+  }
+  moved = __reduce_add_sync(0xFFFFFFFFu, moved);
+  if (lane_id() == 0 && moved) atomicAdd(&G.changed[f], (unsigned long long)moved);
+}
+
+__global__ void __launch_bounds__(256) col_filter_kernel(const GridArgs G) {
+  const uint32_t f = blockIdx.y;
+  const uint32_t n = G.frame_count[f];
+  const uint16_t* pos = G.pos + (uint64_t)f * G.cap * 3;
+  uint16_t* yuv = G.yuv + (uint64_t)f * G.cap * 3;
+  const uint8_t* bt = G.btype + (uint64_t)f * G.cap;
+  const ColCell* tab = reinterpret_cast<const ColCell*>(G.table) + (uint64_t)f * G.table_slots;
+  uint32_t recol = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (bt[i] != 1) continue;
+    const uint32_t p[3] = {pos[3 * (uint64_t)i], pos[3 * (uint64_t)i + 1], pos[3 * (uint64_t)i + 2]};
+    Nbhd N;
+    if (!neighbourhood(G, p, N)) continue;
+    const uint32_t col[3] = {yuv[3 * (uint64_t)i], yuv[3 * (uint64_t)i + 1], yuv[3 * (uint64_t)i + 2]};
+    unsigned long long C[3] = {0, 0, 0};
+    bool other = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const ColCell* c = N.valid[j] ? cell_find(tab, N.key[j], G) : nullptr;
+      bool usable = false;
+      unsigned long long mean[3] = {0, 0, 0};
+      if (c && c->count > 0) {
+        const unsigned long long cnt = c->count;
+        if (c->pmin != c->pmax) other = true;
+        usable = true;
+        const unsigned long long s[3] = {c->sy, c->su, c->sv};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) mean[a] = (256ull * s[a] + cnt / 2) / cnt;
+        const unsigned __int128 num = (unsigned __int128)cnt * c->sy2 - (unsigned __int128)s[0] * s[0];
+        const unsigned long long tv = (unsigned long long)G.thr_c * cnt;
+        const unsigned __int128 lim = (unsigned __int128)tv * tv;
+        if (num > lim) usable = false;
+        const long long dy = (long long)mean[0] - (long long)(256ull * col[0]);
+        if ((unsigned long long)(dy < 0 ? -dy : dy) > 256ull * G.thr_b) usable = false;
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) C[a] += N.wgt[j] * (usable ? mean[a] : 256ull * col[a]);
+    }
+    if (!other) continue;
+    uint32_t q[3]; unsigned long long dist = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const unsigned long long c4 = (C[a] + N.w3 / 2) / N.w3;
+      unsigned long long r = (c4 + 128) >> 8;
+      if (r > 65535) r = 65535;
+      q[a] = (uint32_t)r;
+      const long long d = (long long)q[a] - (long long)col[a];
+      dist += (unsigned long long)(d < 0 ? -d : d) * (a == 0 ? 10u : 1u);
+    }
+    if (dist >= G.thr_a && dist > 0) {
+      yuv[3 * (uint64_t)i] = (uint16_t)q[0]; yuv[3 * (uint64_t)i + 1] = (uint16_t)q[1]; yuv[3 * (uint64_t)i + 2] = (uint16_t)q[2];
+      recol += 1;
+    }
+  }
+  recol = __reduce_add_sync(0xFFFFFFFFu, recol);
+  if (lane_id() == 0 && recol) atomicAdd(&G.changed[f], (unsigned long long)recol);
+}
+
+template <typename Cell>
+__global__ void __launch_bounds__(256) grid_clear_kernel(const GridArgs G) {
+  const uint32_t f = blockIdx.y;
+  const uint32_t n = min((uint64_t)G.touched_count[f], G.touched_cap);
+  Cell* tab = reinterpret_cast<Cell*>(G.table) + (uint64_t)f * G.table_slots;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Cell z;
+    memset(&z, 0, sizeof z);
+    z.key = kCellEmpty; z.pmin = 0xFFFFFFFFu;
+    tab[G.touched[(uint64_t)f * G.touched_cap + i]] = z;
+  }
+}
+__global__ void grid_reset_counts_kernel(const GridArgs G) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < G.n_frames) G.touched_count[f] = 0;
+}
+template <typename Cell>
+__global__ void __launch_bounds__(256) table_init_kernel(Cell* tab, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    Cell z;
+    memset(&z, 0, sizeof z);
+    z.key = kCellEmpty; z.pmin = 0xFFFFFFFFu;
+    tab[i] = z;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// launch wrappers
+// ----------------------------------------------------------------------------------------------------------------
+static inline int after_launch() { ++g_launches; return (int)cudaGetLastError(); }
+
+size_t unpack_smem_bytes(const UnpackArgs& a) { return (size_t)a.warp_bytes * kWarpsPerTile; }
+
+int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream) {
+  if (n_slots == 0) return 0;
+  const uint32_t blocks = (n_slots * 32 + 255) / 256;
+  block_to_patch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, n_slots, const_cast<uint32_t*>(a.block_to_patch));
+  return after_launch();
+}
+
+int launch_unpack(const UnpackArgs& a, int mode, void* stream) {
+  if (a.n_tiles == 0) return 0;
+  const size_t smem = unpack_smem_bytes(a);
+  static bool attr_set[3] = {false, false, false};
+  cudaError_t e = cudaSuccess;
+  auto set = [&](const void* fn) {
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  };
+  if (!attr_set[mode]) {
+    if (mode == 0) e = set((const void*)unpack_kernel<0>);
+    else if (mode == 1) e = set((const void*)unpack_kernel<1>);
+    else e = set((const void*)unpack_kernel<2>);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[mode] = true;
+  }
+  const cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 0) unpack_kernel<0><<<a.n_tiles, kWarpsPerTile * 32, smem, s>>>(a);
+  else if (mode == 1) unpack_kernel<1><<<a.n_tiles, kWarpsPerTile * 32, 0, s>>>(a);
+  else unpack_kernel<2><<<a.n_tiles, kWarpsPerTile * 32, smem, s>>>(a);
+  return after_launch();
+}
+
+int launch_tile_scan(const UnpackArgs& a, void* stream) {
+  if (a.n_frames == 0) return 0;
+  tile_scan_kernel<<<a.n_frames, 256, 0, (cudaStream_t)stream>>>(a);
+  return after_launch();
+}
+
+int launch_upsample(const UnpackArgs& a, uint8_t* occ_full, void* stream) {
+  upsample_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(a, occ_full);
+  return after_launch();
+}
+
+static inline dim3 per_frame_grid(uint64_t cap, uint32_t n_frames) {
+  uint64_t bx = (cap + 255) / 256;
+  const uint64_t lim = (148ull * 8 + n_frames - 1) / (n_frames ? n_frames : 1) + 1;   // ~8 CTAs per SM over all frames
+  if (bx > lim) bx = lim;
+  if (bx < 1) bx = 1;
+  return dim3((unsigned)bx, n_frames, 1);
+}
+
+int launch_geo_smoothing(const GridArgs& G, void* stream) {
+  const cudaStream_t s = (cudaStream_t)stream;
+  const dim3 grid = per_frame_grid(G.cap, G.n_frames);
+  int e;
+  grid_reset_counts_kernel<<<(G.n_frames + 63) / 64, 64, 0, s>>>(G);
+  if ((e = after_launch())) return e;
+  grid_accumulate_kernel<false><<<grid, 256, 0, s>>>(G);
+  if ((e = after_launch())) return e;
+  geo_filter_kernel<<<grid, 256, 0, s>>>(G);
+  if ((e = after_launch())) return e;
+  grid_clear_kernel<GeoCell><<<grid, 256, 0, s>>>(G);
+  return after_launch();
+}
+
+int launch_color_smoothing(const GridArgs& G, void* stream) {
+  const cudaStream_t s = (cudaStream_t)stream;
+  const dim3 grid = per_frame_grid(G.cap, G.n_frames);
+  int e;
+  grid_reset_counts_kernel<<<(G.n_frames + 63) / 64, 64, 0, s>>>(G);
+  if ((e = after_launch())) return e;
+  grid_accumulate_kernel<true><<<grid, 256, 0, s>>>(G);
+  if ((e = after_launch())) return e;
+  col_filter_kernel<<<grid, 256, 0, s>>>(G);
+  if ((e = after_launch())) return e;
+  grid_clear_kernel<ColCell><<<grid, 256, 0, s>>>(G);
+  return after_launch();
+}
+
+int launch_yuv_to_rgb(const uint16_t* yuv, uint8_t* rgb, const uint32_t* frame_count, uint32_t n_frames, uint64_t cap,
+                      void* stream) {
+  if (n_frames == 0) return 0;
+  yuv_to_rgb_kernel<<<per_frame_grid(cap, n_frames), 256, 0, (cudaStream_t)stream>>>(yuv, rgb, frame_count, cap);
+  return after_launch();
+}
+int launch_yuv_to_rgb_flat(const uint16_t* yuv, uint8_t* rgb, uint64_t n, void* stream) {
+  if (n == 0) return 0;
+  uint64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  yuv_to_rgb_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(yuv, rgb, n);
+  return after_launch();
+}
+int launch_table_init(void* table, uint64_t total_slots, int is_color, void* stream) {
+  if (total_slots == 0) return 0;
+  if (is_color) table_init_kernel<ColCell><<<148 * 8, 256, 0, (cudaStream_t)stream>>>((ColCell*)table, total_slots);
+  else table_init_kernel<GeoCell><<<148 * 8, 256, 0, (cudaStream_t)stream>>>((GeoCell*)table, total_slots);
+  return after_launch();
+}
+
+}  // namespace tmc2

@@ -1,0 +1,1105 @@
+// tmc2gpu.cu -- host runtime behind include/tmc2gpu.h: validation (everything the reference asserts), HBM layout,
+// pinned staging, stream/event plumbing, frame-wise multi-GPU sharding, and the C ABI entry points.
+//
+// This file replaces the per-frame driver of the reference, src/decoder.rs:188-314, with a GOF-batched one:
+//   submit_gof  = validate + stage + H2D + [K2 block_to_patch] + [fused unpack] + [smoothing] + counts D2H
+//   next_frame  = in-order hand-out of PointSet3-compatible buffers (src/lib.rs:81, src/codec.rs:20-36)
+// There is no CPU fallback anywhere: without a CUDA device every entry point returns TMC2_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tmc2gpu.h"
+#include "device_types.h"
+
+using namespace tmc2;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// utilities
+// ---------------------------------------------------------------------------------------------------------------
+struct Err {
+  tmc2_status st = TMC2_OK;
+  std::string msg;
+};
+
+static std::string fmt(const char* f, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof buf, f, ap);
+  va_end(ap);
+  return buf;
+}
+
+#define CU(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t _e = (call);                                                                          \
+    if (_e != cudaSuccess) {                                                                          \
+      err.st = TMC2_ERR_CUDA;                                                                         \
+      err.msg = fmt("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__);      \
+      return err.st;                                                                                  \
+    }                                                                                                 \
+  } while (0)
+#define KL(call)                                                                                      \
+  do {                                                                                                \
+    int _e = (call);                                                                                  \
+    if (_e != 0) {                                                                                    \
+      err.st = TMC2_ERR_CUDA;                                                                         \
+      err.msg = fmt("%s failed: %s", #call, cudaGetErrorString((cudaError_t)_e));                     \
+      return err.st;                                                                                  \
+    }                                                                                                 \
+  } while (0)
+#define FAIL(code, ...)            \
+  do {                             \
+    err.st = (code);               \
+    err.msg = fmt(__VA_ARGS__);    \
+    return err.st;                 \
+  } while (0)
+
+static inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+static inline uint64_t round_up64(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+static inline uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    bytes = bytes + bytes / 4;   // head room: later GOFs of the same stream rarely need a re-pin
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// registry of memory handed out by tmc2gpu_alloc_pinned: planes inside it are DMA'd without staging
+std::mutex g_pin_mu;
+std::vector<std::pair<const uint8_t*, size_t>> g_pinned;
+static bool is_pinned(const void* p, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  const uint8_t* q = static_cast<const uint8_t*>(p);
+  for (auto& r : g_pinned)
+    if (q >= r.first && q + bytes <= r.first + r.second) return true;
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// validation: everything the reference asserts / unwraps / leaves unimplemented on this path
+// ---------------------------------------------------------------------------------------------------------------
+static void helper_i64(const tmc2_patch& p, int64_t u, int64_t v, int64_t res, int64_t sscale, int64_t& x, int64_t& y) {
+  // src/decoder.rs:853-867 in signed arithmetic (agrees with wrapping usize whenever the result is in range)
+  const int64_t u0 = (int64_t)p.u0 * res, v0 = (int64_t)p.v0 * res;
+  const int64_t su = (int64_t)p.size_u0 * sscale, sv = (int64_t)p.size_v0 * sscale;
+  switch (p.patch_orientation) {
+    case TMC2_ORIENT_DEFAULT: x = u + u0; y = v + v0; break;
+    case TMC2_ORIENT_ROT90:   x = sv - 1 - v + u0; y = u + v0; break;
+    case TMC2_ORIENT_ROT180:  x = su - 1 - u + u0; y = sv - 1 - v + v0; break;
+    case TMC2_ORIENT_ROT270:  x = v + u0; y = su - 1 - u + v0; break;
+    case TMC2_ORIENT_MIRROR:  x = su - 1 - u + u0; y = v + v0; break;
+    case TMC2_ORIENT_MROT90:  x = sv - 1 - v + u0; y = su - 1 - u + v0; break;
+    case TMC2_ORIENT_MROT180: x = u + u0; y = sv - 1 - v + v0; break;
+    default:                  x = v + u0; y = u + v0; break;  // Swap, MRot270
+  }
+}
+
+static tmc2_status validate_params(const tmc2_gof* g, Err& err) {
+  if (!g) FAIL(TMC2_ERR_INVALID_ARG, "gof is NULL");
+  const tmc2_params& P = g->params;
+  if (g->frame_count && !g->frames) FAIL(TMC2_ERR_INVALID_ARG, "frames is NULL");
+  if (g->width == 0 || g->height == 0 || g->occ_width == 0 || g->occ_height == 0)
+    FAIL(TMC2_ERR_INVALID_ARG, "zero-sized frame");
+  if (g->width >= 32768 || g->height >= 32768) FAIL(TMC2_ERR_CAPACITY, "frame larger than 32767 pixels");
+  if (P.occupancy_resolution == 0 || P.occupancy_precision == 0)
+    FAIL(TMC2_ERR_INVALID_ARG, "occupancy resolution / precision must be non-zero");
+  if (P.occupancy_resolution > 64) FAIL(TMC2_ERR_CAPACITY, "occupancy resolution > 64");
+  if (P.enable_size_quantization || P.multiple_streams || P.pbf_enabled || P.enhanced_occupancy_map ||
+      P.point_local_reconstruction || P.single_map_pixel_interleaving || P.use_additional_points_patch)
+    FAIL(TMC2_ERR_UNSUPPORTED, "reference branch is unimplemented!() (codec.rs:285,303,314,399,402,454,494)");
+  if (P.map_count_minus1 != 1) FAIL(TMC2_ERR_MAP_COUNT, "map_count must be 2 (codec.rs:415-432)");
+  if (P.attribute_count > 1) FAIL(TMC2_ERR_UNSUPPORTED, "attribute_count > 1 (decoder.rs:133)");
+  if (P.orientation_mode > 1) FAIL(TMC2_ERR_INVALID_ARG, "orientation_mode");
+  // Image::get asserts (decoder.rs:974): the upsample touches every pixel of the tile
+  if ((g->width - 1) / P.occupancy_precision >= g->occ_width || (g->height - 1) / P.occupancy_precision >= g->occ_height)
+    FAIL(TMC2_ERR_INVALID_ARG, "occupancy video smaller than frame / precision (decoder.rs:974 assert)");
+  if (P.geometry_smoothing || P.color_smoothing) {
+    if (P.geometry_bitdepth_3d == 0 || P.geometry_bitdepth_3d > 16) FAIL(TMC2_ERR_INVALID_ARG, "geometry_bitdepth_3d");
+    const uint32_t maxs = 1u << P.geometry_bitdepth_3d;
+    if (P.geometry_smoothing) {
+      if (P.grid_size < 1) FAIL(TMC2_ERR_INVALID_ARG, "grid_size");
+      if ((maxs + P.grid_size - 1) / P.grid_size > 1024) FAIL(TMC2_ERR_UNSUPPORTED, "geometry grid wider than 1024 cells");
+    }
+    if (P.color_smoothing && P.attribute_count) {
+      if (P.cgrid_size < 1) FAIL(TMC2_ERR_INVALID_ARG, "cgrid_size");
+      if ((maxs + P.cgrid_size - 1) / P.cgrid_size > 1024) FAIL(TMC2_ERR_UNSUPPORTED, "colour grid wider than 1024 cells");
+    }
+  }
+  return TMC2_OK;
+}
+
+static tmc2_status validate_frame(const tmc2_gof* g, uint32_t f, Err& err) {
+  const tmc2_params& P = g->params;
+  const tmc2_frame& fr = g->frames[f];
+  // codec.rs:318-320: geometry video must hold frames f*M .. f*M+M-1
+  if ((uint64_t)g->geo_video_frames < (uint64_t)f * 2 + 2)
+    FAIL(TMC2_ERR_SHORT_VIDEO, "geometry video has %u frames, frame %u needs %llu (codec.rs:318)", g->geo_video_frames, f,
+         (unsigned long long)f * 2 + 2);
+  if (P.attribute_count && (uint64_t)g->attr_video_frames < (uint64_t)f * 2 + 2)
+    FAIL(TMC2_ERR_SHORT_VIDEO, "attribute video has %u frames, frame %u needs %llu (codec.rs:589,637)",
+         g->attr_video_frames, f, (unsigned long long)f * 2 + 2);
+  if (!fr.occ || !fr.geo[0] || !fr.geo[1]) FAIL(TMC2_ERR_INVALID_ARG, "frame %u: NULL occupancy / geometry plane", f);
+  if (P.attribute_count && (!fr.attr_y[0] || !fr.attr_y[1] || !fr.attr_u[0] || !fr.attr_u[1] || !fr.attr_v[0] || !fr.attr_v[1]))
+    FAIL(TMC2_ERR_INVALID_ARG, "frame %u: NULL attribute plane", f);
+  if (fr.occ_stride < g->occ_width || fr.geo_stride < g->width ||
+      (P.attribute_count && (fr.attr_stride_y < g->width || fr.attr_stride_c < g->width / 2)))
+    FAIL(TMC2_ERR_INVALID_ARG, "frame %u: stride smaller than width", f);
+  if (fr.patch_count && !fr.patches) FAIL(TMC2_ERR_INVALID_ARG, "frame %u: NULL patch list", f);
+  if (fr.patch_count > 65535) FAIL(TMC2_ERR_CAPACITY, "frame %u: more than 65535 patches", f);
+  const int64_t res = P.occupancy_resolution;
+  const int64_t sscale = P.orientation_mode == TMC2_ORIENTATION_SPEC ? res : 1;
+  const int64_t bw = g->width / res, bh = g->height / res;
+  for (uint32_t i = 0; i < fr.patch_count; ++i) {
+    const tmc2_patch& p = fr.patches[i];
+    if (p.patch_orientation > 8) FAIL(TMC2_ERR_INVALID_ARG, "frame %u patch %u: orientation %u", f, i, p.patch_orientation);
+    if (p.normal_axis > 2 || p.tangent_axis > 2 || p.bitangent_axis > 2 || p.projection_mode > 1)
+      FAIL(TMC2_ERR_INVALID_ARG, "frame %u patch %u: axes / projection mode out of range", f, i);
+    if (p.axis_of_additional_plane != 0)
+      FAIL(TMC2_ERR_UNSUPPORTED, "frame %u patch %u: axis_of_additional_plane (codec.rs:437)", f, i);
+    if (p.size_u0 == 0 || p.size_v0 == 0) continue;
+    if (p.size_u0 > 4096 || p.size_v0 > 4096) FAIL(TMC2_ERR_PATCH_OUT_OF_CANVAS, "frame %u patch %u: size", f, i);
+    for (int c = 0; c < 4; ++c) {
+      int64_t x, y;
+      const int64_t ub = (c & 1) ? p.size_u0 - 1 : 0, vb = (c & 2) ? p.size_v0 - 1 : 0;
+      helper_i64(p, ub, vb, 1, 1, x, y);                         // decoder.rs:834-835
+      if (x < 0 || y < 0 || x >= bw || y >= bh)
+        FAIL(TMC2_ERR_PATCH_OUT_OF_CANVAS, "frame %u patch %u: block (%lld,%lld) outside %lldx%lld (decoder.rs:835)", f, i,
+             (long long)x, (long long)y, (long long)bw, (long long)bh);
+      const int64_t u = (c & 1) ? (int64_t)p.size_u0 * res - 1 : 0, v = (c & 2) ? (int64_t)p.size_v0 * res - 1 : 0;
+      helper_i64(p, u, v, res, sscale, x, y);                    // decoder.rs:847-848
+      if (x < 0 || y < 0 || x >= (int64_t)g->width || y >= (int64_t)g->height)
+        FAIL(TMC2_ERR_PATCH_OUT_OF_CANVAS, "frame %u patch %u: pixel (%lld,%lld) outside the canvas (decoder.rs:848)", f, i,
+             (long long)x, (long long)y);
+    }
+  }
+  return TMC2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Batch: the frames of one GOF (or GOF slice) on one device
+// ---------------------------------------------------------------------------------------------------------------
+enum : uint32_t {
+  WANT_DEBUG = 1u,       // partition, point_to_pixel, colors16bit, boundary type, pre-smoothing copies
+  WANT_OCC_FULL = 2u,    // materialise tile.occupancy_map (K1)
+};
+
+struct StageTimes { float b2p = 0, unpack = 0, geo = 0, col = 0, rgb = 0; };
+
+struct Batch {
+  int device = 0;
+  cudaStream_t stream = nullptr;      // compute + H2D
+  cudaStream_t d2h_stream = nullptr;  // result copies
+  bool two_pass = false;
+
+  // description of the loaded GOF slice
+  uint32_t W = 0, H = 0, occ_w = 0, occ_h = 0, F = 0, res = 16, prec = 4;
+  uint32_t geo_pitch = 0, attr_pitch_y = 0, attr_pitch_c = 0, occ_pitch = 0, Hc = 0;
+  tmc2_params params{};
+  uint32_t want = 0;
+  uint64_t cap = 0;                   // points per frame slab
+  uint32_t n_tiles = 0, n_slots = 0, bw = 0, bh = 0;
+  uint32_t epoch = 0;
+  bool smoothing_geo = false, smoothing_col = false;
+
+  std::vector<DevPatch> h_patches;
+  std::vector<uint32_t> h_slot_patch, h_tile_frame, h_ftb;
+
+  DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_status, d_tile_total, d_count, d_err;
+  DevBuf d_pos, d_rgb, d_yuv, d_part, d_pix, d_bt, d_occ_full, d_pos_pre, d_yuv_pre;
+  DevBuf d_geotab, d_coltab, d_touched, d_touched_count, d_changed;
+  uint64_t geotab_slots = 0, coltab_slots = 0, geotab_frames = 0, coltab_frames = 0, touched_cap = 0;
+  PinBuf h_in, h_meta, h_small, h_out;
+  size_t meta_patch_off = 0, meta_slot_off = 0, meta_tf_off = 0, meta_ftb_off = 0, meta_bytes = 0;
+
+  cudaEvent_t ev[8] = {};             // stage boundaries: 0 start,1 after b2p,2 after unpack,3 geo,4 col,5 rgb
+  cudaEvent_t ev_counts = nullptr, ev_inputs_free = nullptr;
+  std::vector<cudaEvent_t> ev_frame;  // per-frame D2H completion
+
+  // results on the host after fetch
+  std::vector<uint32_t> counts;
+  std::vector<uint64_t> moved, recoloured;
+  std::vector<size_t> out_pos_off, out_rgb_off;
+  bool counts_ready = false, outputs_enqueued = false;
+  uint32_t launches = 0;
+  uint64_t unpack_alg_bytes = 0;
+  uint32_t frames_released = 0;
+  bool busy = false;
+
+  ~Batch() { destroy(); }
+  void destroy() {
+    cudaSetDevice(device);
+    for (DevBuf* b : {&d_occ, &d_geo, &d_ay, &d_au, &d_av, &d_meta, &d_b2p, &d_status, &d_tile_total, &d_count, &d_err, &d_pos,
+                      &d_rgb, &d_yuv, &d_part, &d_pix, &d_bt, &d_occ_full, &d_pos_pre, &d_yuv_pre, &d_geotab, &d_coltab,
+                      &d_touched, &d_touched_count, &d_changed})
+      b->release();
+    for (PinBuf* b : {&h_in, &h_meta, &h_small, &h_out}) b->release();
+    for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    if (ev_counts) cudaEventDestroy(ev_counts), ev_counts = nullptr;
+    if (ev_inputs_free) cudaEventDestroy(ev_inputs_free), ev_inputs_free = nullptr;
+    for (auto e : ev_frame) cudaEventDestroy(e);
+    ev_frame.clear();
+    if (stream) cudaStreamDestroy(stream), stream = nullptr;
+    if (d2h_stream) cudaStreamDestroy(d2h_stream), d2h_stream = nullptr;
+  }
+
+  tmc2_status init(int dev, bool two_pass_scan, Err& err) {
+    device = dev; two_pass = two_pass_scan;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
+    for (auto& e : ev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&ev_counts, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev_inputs_free, cudaEventDisableTiming));
+    CU(d_err.ensure(sizeof(int)));
+    CU(cudaMemset(d_err.p, 0, sizeof(int)));
+    return TMC2_OK;
+  }
+
+  // ---- host-side digest of the patch lists: DevPatch array, slot list, tile -> frame map ------------------------
+  tmc2_status prepare(const tmc2_gof* g, uint32_t first, uint32_t count, uint32_t want_flags, Err& err) {
+    CU(cudaSetDevice(device));
+    params = g->params;
+    W = g->width; H = g->height; occ_w = g->occ_width; occ_h = g->occ_height; F = count;
+    res = params.occupancy_resolution; prec = params.occupancy_precision;
+    bw = W / res; bh = H / res;
+    want = want_flags;
+    Hc = H / 2;
+    geo_pitch = round_up(W, 64); attr_pitch_y = round_up(W, 64); attr_pitch_c = round_up(std::max(W / 2, 1u), 64);
+    occ_pitch = round_up(occ_w, 16);
+    cap = 2ull * W * H;
+    smoothing_geo = params.geometry_smoothing != 0;
+    smoothing_col = params.color_smoothing != 0 && params.attribute_count != 0;
+
+    h_patches.clear(); h_slot_patch.clear(); h_tile_frame.clear(); h_ftb.assign(1, 0);
+    uint64_t total_points_bound = 0;
+    for (uint32_t k = 0; k < count; ++k) {
+      const tmc2_frame& fr = g->frames[first + k];
+      for (uint32_t i = 0; i < fr.patch_count; ++i) {
+        const tmc2_patch& p = fr.patches[i];
+        DevPatch d{};
+        d.x0 = (int32_t)(p.u0 * res); d.y0 = (int32_t)(p.v0 * res);
+        d.u0 = p.u0; d.v0 = p.v0; d.size_u0 = p.size_u0; d.size_v0 = p.size_v0;
+        d.u1 = p.u1; d.v1 = p.v1; d.d1 = p.d1; d.lod_x = p.lod_x; d.lod_y = p.lod_y;
+        d.normal = p.normal_axis; d.tangent = p.tangent_axis; d.bitangent = p.bitangent_axis; d.mode = p.projection_mode;
+        d.orient = p.patch_orientation;
+        d.slot_base = (uint32_t)h_slot_patch.size();
+        d.local_index = i; d.frame = k;
+        const uint64_t ns = (uint64_t)p.size_u0 * p.size_v0;
+        if (h_slot_patch.size() + ns > (1ull << 30)) FAIL(TMC2_ERR_CAPACITY, "too many patch blocks in one GOF");
+        const uint32_t pid = (uint32_t)h_patches.size();
+        h_patches.push_back(d);
+        h_slot_patch.insert(h_slot_patch.end(), (size_t)ns, pid);
+        total_points_bound += ns * res * res * 2;
+      }
+      // pad the frame's slot list to whole tiles: a tile never straddles two frames (one scan domain per frame)
+      while (h_slot_patch.size() % kWarpsPerTile) h_slot_patch.push_back(kNoPatch);
+      const uint32_t tiles_now = (uint32_t)(h_slot_patch.size() / kWarpsPerTile);
+      h_tile_frame.resize(tiles_now, k);
+      h_ftb.push_back(tiles_now);
+    }
+    n_slots = (uint32_t)h_slot_patch.size();
+    n_tiles = n_slots / kWarpsPerTile;
+    (void)total_points_bound;
+
+    // device buffers
+    const bool attr = params.attribute_count != 0;
+    CU(d_occ.ensure((size_t)F * occ_h * occ_pitch));
+    CU(d_geo.ensure((size_t)F * 2 * H * geo_pitch * 2));
+    if (attr) {
+      CU(d_ay.ensure((size_t)F * 2 * H * attr_pitch_y * 2));
+      CU(d_au.ensure((size_t)F * 2 * std::max(Hc, 1u) * attr_pitch_c * 2));
+      CU(d_av.ensure((size_t)F * 2 * std::max(Hc, 1u) * attr_pitch_c * 2));
+    }
+    meta_patch_off = 0;
+    meta_slot_off = round_up64(h_patches.size() * sizeof(DevPatch), 256);
+    meta_tf_off = meta_slot_off + round_up64((uint64_t)n_slots * 4, 256);
+    meta_ftb_off = meta_tf_off + round_up64((uint64_t)n_tiles * 4, 256);
+    meta_bytes = meta_ftb_off + round_up64((uint64_t)(F + 1) * 4, 256);
+    CU(d_meta.ensure(meta_bytes));
+    CU(h_meta.ensure(meta_bytes));
+    CU(d_b2p.ensure(std::max<size_t>((size_t)F * bw * bh * 4, 4)));
+    const size_t old_status_cap = d_status.cap;
+    CU(d_status.ensure(std::max<size_t>((size_t)n_tiles * 8, 8)));
+    if (d_status.cap != old_status_cap) { CU(cudaMemsetAsync(d_status.p, 0, d_status.cap, stream)); epoch = 0; }
+    CU(d_tile_total.ensure(std::max<size_t>((size_t)n_tiles * 4, 4)));
+    CU(d_count.ensure(std::max<size_t>((size_t)F * 4, 4)));
+    CU(d_changed.ensure(std::max<size_t>((size_t)F * 16, 16)));
+    CU(d_pos.ensure((size_t)F * cap * 6));
+    const bool dbg = (want & WANT_DEBUG) != 0;
+    if (attr) CU(d_rgb.ensure((size_t)F * cap * 3));
+    if (attr && (smoothing_col || dbg)) CU(d_yuv.ensure((size_t)F * cap * 6));
+    if (smoothing_geo || smoothing_col || dbg) {
+      CU(d_part.ensure((size_t)F * cap * 2));
+      CU(d_bt.ensure((size_t)F * cap));
+    }
+    if (dbg) {
+      CU(d_pix.ensure((size_t)F * cap * 4));
+      CU(d_pos_pre.ensure((size_t)F * cap * 6));
+      if (attr) CU(d_yuv_pre.ensure((size_t)F * cap * 6));
+    }
+    if (want & WANT_OCC_FULL) CU(d_occ_full.ensure((size_t)F * W * H));
+    if (smoothing_geo || smoothing_col) {
+      const uint32_t maxs = 1u << params.geometry_bitdepth_3d;
+      touched_cap = cap;
+      CU(d_touched.ensure((size_t)F * touched_cap * 4));
+      CU(d_touched_count.ensure((size_t)F * 4));
+      if (smoothing_geo) {
+        const uint64_t w = (maxs + params.grid_size - 1) / params.grid_size;
+        const uint64_t cells = w * w * w;
+        const uint64_t slots = cells <= 2 * cap ? cells : pow2_at_least(2 * cap);
+        if (slots != geotab_slots || F > geotab_frames) {
+          CU(d_geotab.ensure((size_t)F * slots * sizeof(GeoCell)));
+          geotab_slots = slots; geotab_frames = F;
+          KL(launch_table_init(d_geotab.p, (uint64_t)F * slots, 0, stream));
+        }
+      }
+      if (smoothing_col) {
+        const uint64_t w = (maxs + params.cgrid_size - 1) / params.cgrid_size;
+        const uint64_t cells = w * w * w;
+        const uint64_t slots = cells <= 2 * cap ? cells : pow2_at_least(2 * cap);
+        if (slots != coltab_slots || F > coltab_frames) {
+          CU(d_coltab.ensure((size_t)F * slots * sizeof(ColCell)));
+          coltab_slots = slots; coltab_frames = F;
+          KL(launch_table_init(d_coltab.p, (uint64_t)F * slots, 1, stream));
+        }
+      }
+    }
+    return TMC2_OK;
+  }
+
+  // ---- H2D: planes (through pinned staging unless the caller's memory is already pinned) + metadata -------------
+  tmc2_status copy_plane_set(const tmc2_gof* g, uint32_t first, int kind, Err& err, size_t& stage_off) {
+    // kind: 0 occ, 1 geo, 2 attr_y, 3 attr_u, 4 attr_v.  One row-pitched copy per (frame, map), merged when the source
+    // planes are contiguous in memory and tight.
+    const int maps = kind == 0 ? 1 : 2;
+    const uint32_t esz = kind == 0 ? 1 : 2;
+    const uint32_t w = kind == 0 ? occ_w : (kind >= 3 ? W / 2 : W);
+    const uint32_t h = kind == 0 ? occ_h : (kind >= 3 ? Hc : H);
+    const uint32_t dpitch = kind == 0 ? occ_pitch : kind == 1 ? geo_pitch : kind == 2 ? attr_pitch_y : attr_pitch_c;
+    uint8_t* dbase = kind == 0 ? d_occ.as<uint8_t>() : kind == 1 ? d_geo.as<uint8_t>() : kind == 2 ? d_ay.as<uint8_t>()
+                   : kind == 3 ? d_au.as<uint8_t>() : d_av.as<uint8_t>();
+    if (w == 0 || h == 0) return TMC2_OK;
+    const size_t plane_dev = (size_t)h * dpitch * esz;
+    struct Seg { const uint8_t* src; size_t spitch; uint8_t* dst; uint32_t rows; };
+    std::vector<Seg> segs;
+    for (uint32_t k = 0; k < F; ++k) {
+      const tmc2_frame& fr = g->frames[first + k];
+      for (int m = 0; m < maps; ++m) {
+        const void* src = kind == 0 ? (const void*)fr.occ : kind == 1 ? (const void*)fr.geo[m]
+                        : kind == 2 ? (const void*)fr.attr_y[m] : kind == 3 ? (const void*)fr.attr_u[m] : (const void*)fr.attr_v[m];
+        const uint32_t sstride = kind == 0 ? fr.occ_stride : kind == 1 ? fr.geo_stride : kind == 2 ? fr.attr_stride_y : fr.attr_stride_c;
+        segs.push_back({(const uint8_t*)src, (size_t)sstride * esz, dbase + ((size_t)k * maps + m) * plane_dev, h});
+      }
+    }
+    const size_t row_bytes = (size_t)w * esz;
+    const size_t dpb = (size_t)dpitch * esz;
+    // current run of planes that are contiguous on both sides -> one cudaMemcpyAsync
+    const uint8_t* run_src = nullptr; uint8_t* run_dst = nullptr; size_t run_bytes = 0;
+    auto flush = [&]() -> cudaError_t {
+      cudaError_t e = cudaSuccess;
+      if (run_bytes) e = cudaMemcpyAsync(run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, stream);
+      run_bytes = 0;
+      return e;
+    };
+    for (const Seg& s : segs) {
+      const size_t src_bytes = (size_t)(s.rows - 1) * s.spitch + row_bytes;
+      const uint8_t* src = s.src;
+      size_t spitch = s.spitch;
+      if (!is_pinned(s.src, src_bytes)) {
+        // stage: repack into pinned memory with the device pitch
+        uint8_t* st = h_in.as<uint8_t>() + stage_off;
+        if (spitch == dpb && row_bytes == dpb) memcpy(st, s.src, plane_dev);
+        else for (uint32_t r = 0; r < s.rows; ++r) memcpy(st + (size_t)r * dpb, s.src + (size_t)r * s.spitch, row_bytes);
+        stage_off += plane_dev;
+        src = st; spitch = dpb;
+      }
+      if (spitch == dpb) {
+        if (run_bytes && src == run_src + run_bytes && s.dst == run_dst + run_bytes) {
+          run_bytes += plane_dev;
+        } else {
+          CU(flush());
+          run_src = src; run_dst = s.dst; run_bytes = plane_dev;
+        }
+        // the last row of a plane may be shorter than the pitch in the SOURCE allocation: never read past it
+        if (row_bytes != dpb && src == s.src) { run_bytes -= plane_dev; CU(flush());
+          CU(cudaMemcpy2DAsync(s.dst, dpb, src, spitch, row_bytes, s.rows, cudaMemcpyHostToDevice, stream)); }
+      } else {
+        CU(flush());
+        CU(cudaMemcpy2DAsync(s.dst, dpb, src, spitch, row_bytes, s.rows, cudaMemcpyHostToDevice, stream));
+      }
+    }
+    CU(flush());
+    return TMC2_OK;
+  }
+
+  tmc2_status upload(const tmc2_gof* g, uint32_t first, Err& err) {
+    CU(cudaSetDevice(device));
+    const bool attr = params.attribute_count != 0;
+    // worst-case staging need (nothing pinned)
+    size_t need = (size_t)F * occ_h * occ_pitch + (size_t)F * 2 * H * geo_pitch * 2;
+    if (attr) need += (size_t)F * 2 * H * attr_pitch_y * 2 + 2 * (size_t)F * 2 * std::max(Hc, 1u) * attr_pitch_c * 2;
+    bool any_unpinned = false;
+    for (uint32_t k = 0; k < F && !any_unpinned; ++k) {
+      const tmc2_frame& fr = g->frames[first + k];
+      any_unpinned |= !is_pinned(fr.geo[0], 2) || !is_pinned(fr.occ, 1) || (attr && !is_pinned(fr.attr_y[0], 2));
+    }
+    if (any_unpinned) {
+      // the previous batch using this staging area must have finished its H2D copies
+      CU(cudaEventSynchronize(ev_inputs_free));
+      CU(h_in.ensure(need));
+    }
+    size_t off = 0;
+    for (int kind = 0; kind < (attr ? 5 : 2); ++kind) {
+      tmc2_status s = copy_plane_set(g, first, kind, err, off);
+      if (s) return s;
+    }
+    // metadata
+    CU(cudaEventSynchronize(ev_inputs_free));
+    uint8_t* m = h_meta.as<uint8_t>();
+    if (!h_patches.empty()) memcpy(m + meta_patch_off, h_patches.data(), h_patches.size() * sizeof(DevPatch));
+    if (n_slots) memcpy(m + meta_slot_off, h_slot_patch.data(), (size_t)n_slots * 4);
+    if (n_tiles) memcpy(m + meta_tf_off, h_tile_frame.data(), (size_t)n_tiles * 4);
+    memcpy(m + meta_ftb_off, h_ftb.data(), (size_t)(F + 1) * 4);
+    CU(cudaMemcpyAsync(d_meta.p, m, meta_bytes, cudaMemcpyHostToDevice, stream));
+    CU(cudaEventRecord(ev_inputs_free, stream));
+    return TMC2_OK;
+  }
+
+  UnpackArgs make_args() const {
+    UnpackArgs a{};
+    a.in.occ = d_occ.as<uint8_t>(); a.in.geo = d_geo.as<uint16_t>();
+    a.in.attr_y = d_ay.as<uint16_t>(); a.in.attr_u = d_au.as<uint16_t>(); a.in.attr_v = d_av.as<uint16_t>();
+    a.in.occ_pitch = occ_pitch; a.in.occ_w = occ_w; a.in.occ_h = occ_h;
+    a.in.geo_pitch = geo_pitch; a.in.attr_pitch_y = attr_pitch_y; a.in.attr_pitch_c = attr_pitch_c;
+    a.in.occ_frame_stride = (uint64_t)occ_h * occ_pitch;
+    a.in.geo_map_stride = (uint64_t)H * geo_pitch;
+    a.in.attr_y_map_stride = (uint64_t)H * attr_pitch_y;
+    a.in.attr_c_map_stride = (uint64_t)std::max(Hc, 1u) * attr_pitch_c;
+    a.W = W; a.H = H; a.res = res; a.prec = prec;
+    a.prec_shift = -1;
+    for (int s = 0; s < 16; ++s) if ((1u << s) == prec) a.prec_shift = s;
+    a.bw = bw; a.bh = bh; a.n_frames = F; a.n_tiles = n_tiles;
+    a.absolute_d1 = params.absolute_d1 ? 1 : 0;
+    a.spec_orientation = params.orientation_mode == TMC2_ORIENTATION_SPEC ? 1 : 0;
+    a.has_attr = params.attribute_count ? 1 : 0;
+    const uint8_t* m = d_meta.as<uint8_t>();
+    a.patches = reinterpret_cast<const DevPatch*>(m + meta_patch_off);
+    a.slot_patch = reinterpret_cast<const uint32_t*>(m + meta_slot_off);
+    a.tile_frame = reinterpret_cast<const uint32_t*>(m + meta_tf_off);
+    a.frame_tile_begin = reinterpret_cast<const uint32_t*>(m + meta_ftb_off);
+    a.block_to_patch = d_b2p.as<uint32_t>();
+    a.tile_status = d_status.as<uint64_t>();
+    a.tile_total = d_tile_total.as<uint32_t>();
+    a.frame_count = d_count.as<uint32_t>();
+    a.err = d_err.as<int>();
+    const bool dbg = (want & WANT_DEBUG) != 0;
+    const bool smooth = smoothing_geo || smoothing_col;
+    a.out.cap = cap;
+    a.out.pos = d_pos.as<uint16_t>();
+    a.out.rgb = (a.has_attr && !smoothing_col) ? d_rgb.as<uint8_t>() : nullptr;   // with colour smoothing RGB comes last
+    a.out.yuv = (a.has_attr && (smoothing_col || dbg)) ? d_yuv.as<uint16_t>() : nullptr;
+    a.out.part = (smooth || dbg) ? d_part.as<uint16_t>() : nullptr;
+    a.out.btype = (smooth || dbg) ? d_bt.as<uint8_t>() : nullptr;
+    a.out.pix = dbg ? d_pix.as<uint32_t>() : nullptr;
+    a.want_btype = a.out.btype != nullptr;
+    // shared-memory staging layout of one warp (each stream gets 16 bytes of phase slack)
+    uint32_t off = 0;
+    auto place = [&](bool on, uint32_t bytes_per_point) {
+      const uint32_t o = off;
+      if (on) off += round_up(kSlotPoints * bytes_per_point + 16, 16);
+      return o;
+    };
+    a.off_pos = place(true, 6);
+    a.off_rgb = place(a.out.rgb != nullptr, 3);
+    a.off_yuv = place(a.out.yuv != nullptr, 6);
+    a.off_part = place(a.out.part != nullptr, 2);
+    a.off_pix = place(a.out.pix != nullptr, 4);
+    a.off_bt = place(a.out.btype != nullptr, 1);
+    a.warp_bytes = std::max(off, 768u);
+    return a;
+  }
+
+  uint64_t algorithmic_bytes_core(uint64_t total_points) const {
+    // occ + geometry Y (2 maps) + attribute YUV 4:2:0 (2 maps) + per-point output streams
+    uint64_t b = (uint64_t)F * ((uint64_t)occ_w * occ_h + 2ull * W * H * 2);
+    if (params.attribute_count) b += (uint64_t)F * 2ull * ((uint64_t)W * H + 2ull * (W / 2) * (H / 2)) * 2;
+    uint64_t per_point = 6;
+    const bool dbg = (want & WANT_DEBUG) != 0;
+    if (params.attribute_count && !smoothing_col) per_point += 3;
+    if (params.attribute_count && (smoothing_col || dbg)) per_point += 6;
+    if (smoothing_geo || smoothing_col || dbg) per_point += 3;
+    if (dbg) per_point += 4;
+    return b + per_point * total_points;
+  }
+
+  // ---- kernels ---------------------------------------------------------------------------------------------------
+  tmc2_status launch(cudaStream_t s, Err& err) {
+    CU(cudaSetDevice(device));
+    kernel_launch_count_reset();
+    UnpackArgs a = make_args();
+    if (++epoch >= (1u << 30)) { CU(cudaMemsetAsync(d_status.p, 0, d_status.cap, s)); epoch = 1; }
+    a.epoch = epoch;
+    CU(cudaEventRecord(ev[0], s));
+    CU(cudaMemsetAsync(d_b2p.p, 0, std::max<size_t>((size_t)F * bw * bh * 4, 4), s));
+    CU(cudaMemsetAsync(d_count.p, 0, std::max<size_t>((size_t)F * 4, 4), s));
+    KL(launch_block_to_patch(a, n_slots, s));
+    CU(cudaEventRecord(ev[1], s));
+    if (two_pass) {
+      KL(launch_unpack(a, 1, s));
+      KL(launch_tile_scan(a, s));
+      KL(launch_unpack(a, 2, s));
+    } else {
+      KL(launch_unpack(a, 0, s));
+    }
+    CU(cudaEventRecord(ev[2], s));
+    if (want & WANT_OCC_FULL) KL(launch_upsample(a, d_occ_full.as<uint8_t>(), s));
+    const bool dbg = (want & WANT_DEBUG) != 0;
+    if (dbg) {
+      CU(cudaMemcpyAsync(d_pos_pre.p, d_pos.p, (size_t)F * cap * 6, cudaMemcpyDeviceToDevice, s));
+      if (a.out.yuv) CU(cudaMemcpyAsync(d_yuv_pre.p, d_yuv.p, (size_t)F * cap * 6, cudaMemcpyDeviceToDevice, s));
+    }
+    CU(cudaMemsetAsync(d_changed.p, 0, std::max<size_t>((size_t)F * 16, 16), s));
+    if (smoothing_geo || smoothing_col) {
+      const uint32_t maxs = 1u << params.geometry_bitdepth_3d;
+      GridArgs G{};
+      G.n_frames = F; G.cap = cap; G.frame_count = d_count.as<uint32_t>();
+      G.pos = d_pos.as<uint16_t>(); G.yuv = d_yuv.as<uint16_t>(); G.part = d_part.as<uint16_t>(); G.btype = d_bt.as<uint8_t>();
+      G.touched = d_touched.as<uint32_t>(); G.touched_count = d_touched_count.as<uint32_t>(); G.touched_cap = touched_cap;
+      G.err = d_err.as<int>();
+      if (smoothing_geo) {
+        G.g = params.grid_size; G.w = (maxs + G.g - 1) / G.g; G.disth = std::max(G.g / 2, 1u); G.th = G.g * G.w;
+        G.table = d_geotab.p; G.table_slots = geotab_slots;
+        G.identity_hash = (uint64_t)G.w * G.w * G.w <= geotab_slots ? 1 : 0;
+        G.thr_a = params.threshold_smoothing;
+        G.changed = d_changed.as<unsigned long long>();
+        KL(launch_geo_smoothing(G, s));
+      }
+      CU(cudaEventRecord(ev[3], s));
+      if (smoothing_col) {
+        const uint32_t sc = params.attribute_bitdepth > 8 ? (1u << (params.attribute_bitdepth - 8)) : 1u;
+        G.g = params.cgrid_size; G.w = (maxs + G.g - 1) / G.g; G.disth = std::max(G.g / 2, 1u); G.th = G.g * G.w;
+        G.table = d_coltab.p; G.table_slots = coltab_slots;
+        G.identity_hash = (uint64_t)G.w * G.w * G.w <= coltab_slots ? 1 : 0;
+        G.thr_a = params.threshold_color_smoothing * sc; G.thr_b = params.threshold_color_difference * sc;
+        G.thr_c = params.threshold_color_variation * sc;
+        G.changed = d_changed.as<unsigned long long>() + F;
+        KL(launch_color_smoothing(G, s));
+      }
+      CU(cudaEventRecord(ev[4], s));
+      if (smoothing_col)
+        KL(launch_yuv_to_rgb(d_yuv.as<uint16_t>(), d_rgb.as<uint8_t>(), d_count.as<uint32_t>(), F, cap, s));
+      CU(cudaEventRecord(ev[5], s));
+    } else {
+      CU(cudaEventRecord(ev[3], s)); CU(cudaEventRecord(ev[4], s)); CU(cudaEventRecord(ev[5], s));
+    }
+    launches = (uint32_t)kernel_launch_count_reset();
+    counts_ready = false; outputs_enqueued = false;
+    return TMC2_OK;
+  }
+
+  // counts (+ error flag, + smoothing statistics) to the host; synchronises with `s`
+  tmc2_status fetch_counts(cudaStream_t s, Err& err) {
+    CU(cudaSetDevice(device));
+    const size_t bytes = (size_t)F * 4 + (size_t)F * 16 + 16;
+    CU(h_small.ensure(bytes));
+    uint8_t* hs = h_small.as<uint8_t>();
+    CU(cudaMemcpyAsync(hs, d_count.p, (size_t)F * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hs + (size_t)F * 4, d_changed.p, (size_t)F * 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hs + (size_t)F * 20, d_err.p, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(ev_counts, s));
+    CU(cudaEventSynchronize(ev_counts));
+    int dev_err = 0;
+    memcpy(&dev_err, hs + (size_t)F * 20, 4);
+    if (dev_err) {
+      CU(cudaMemsetAsync(d_err.p, 0, 4, s));
+      FAIL((tmc2_status)dev_err, "device-side failure flag %d (7 = output capacity, 11 = watchdog / table)", dev_err);
+    }
+    counts.assign(F, 0); moved.assign(F, 0); recoloured.assign(F, 0);
+    if (F) {
+      memcpy(counts.data(), hs, (size_t)F * 4);
+      memcpy(moved.data(), hs + (size_t)F * 4, (size_t)F * 8);
+      memcpy(recoloured.data(), hs + (size_t)F * 12, (size_t)F * 8);
+    }
+    uint64_t total = 0;
+    for (auto c : counts) total += c;
+    unpack_alg_bytes = algorithmic_bytes_core(total);
+    counts_ready = true;
+    return TMC2_OK;
+  }
+
+  // enqueue the per-frame result copies into one pinned slab; per-frame events signal completion
+  tmc2_status enqueue_outputs(Err& err) {
+    CU(cudaSetDevice(device));
+    const bool attr = params.attribute_count != 0;
+    out_pos_off.assign(F, 0); out_rgb_off.assign(F, 0);
+    size_t off = 0;
+    for (uint32_t k = 0; k < F; ++k) {
+      out_pos_off[k] = off; off += round_up64((uint64_t)counts[k] * 6, 64);
+      out_rgb_off[k] = off; if (attr) off += round_up64((uint64_t)counts[k] * 3, 64);
+    }
+    CU(h_out.ensure(std::max<size_t>(off, 64)));
+    while (ev_frame.size() < F) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ev_frame.push_back(e);
+    }
+    CU(cudaStreamWaitEvent(d2h_stream, ev_counts, 0));
+    uint8_t* ho = h_out.as<uint8_t>();
+    for (uint32_t k = 0; k < F; ++k) {
+      if (counts[k]) {
+        CU(cudaMemcpyAsync(ho + out_pos_off[k], d_pos.as<uint8_t>() + (size_t)k * cap * 6, (size_t)counts[k] * 6,
+                           cudaMemcpyDeviceToHost, d2h_stream));
+        if (attr)
+          CU(cudaMemcpyAsync(ho + out_rgb_off[k], d_rgb.as<uint8_t>() + (size_t)k * cap * 3, (size_t)counts[k] * 3,
+                             cudaMemcpyDeviceToHost, d2h_stream));
+      }
+      CU(cudaEventRecord(ev_frame[k], d2h_stream));
+    }
+    outputs_enqueued = true;
+    return TMC2_OK;
+  }
+
+  tmc2_status stage_times(StageTimes& t, Err& err) {
+    CU(cudaSetDevice(device));
+    CU(cudaEventSynchronize(ev[5]));
+    CU(cudaEventElapsedTime(&t.b2p, ev[0], ev[1]));
+    CU(cudaEventElapsedTime(&t.unpack, ev[1], ev[2]));
+    CU(cudaEventElapsedTime(&t.geo, ev[2], ev[3]));
+    CU(cudaEventElapsedTime(&t.col, ev[3], ev[4]));
+    CU(cudaEventElapsedTime(&t.rgb, ev[4], ev[5]));
+    return TMC2_OK;
+  }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------------
+struct PendingFrame {
+  Batch* batch;
+  uint32_t local;
+  uint64_t global_index;
+};
+
+struct tmc2gpu_ctx {
+  std::vector<int> devices;
+  tmc2_limits limits{};
+  std::vector<std::vector<std::unique_ptr<Batch>>> slots;   // [device][gofs_in_flight]
+  std::unique_ptr<Batch> stage_batch;                        // single-frame stage API
+  std::deque<PendingFrame> pending;
+  uint64_t next_global = 0;
+  Err err;
+  std::string last_error;
+  Batch* last_batch = nullptr;                               // for launch info / stage times
+  bool two_pass = false;
+
+  tmc2_status fail() { last_error = err.msg; return err.st; }
+};
+
+struct tmc2_resident {
+  std::unique_ptr<Batch> batch;
+};
+
+extern "C" {
+
+uint32_t tmc2gpu_abi_version(void) { return TMC2GPU_ABI_VERSION; }
+
+int tmc2gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* tmc2gpu_status_string(tmc2_status s) {
+  static const char* names[] = {"TMC2_OK", "TMC2_END", "TMC2_ERR_INVALID_ARG", "TMC2_ERR_PATCH_OUT_OF_CANVAS",
+                                "TMC2_ERR_SHORT_VIDEO", "TMC2_ERR_MAP_COUNT", "TMC2_ERR_UNSUPPORTED", "TMC2_ERR_CAPACITY",
+                                "TMC2_ERR_STATE", "TMC2_ERR_NO_DEVICE", "TMC2_ERR_CUDA", "TMC2_ERR_INTERNAL"};
+  return (int)s >= 0 && (int)s < 12 ? names[s] : "TMC2_ERR_?";
+}
+
+tmc2_status tmc2gpu_create(const int* device_ids, int device_count, const tmc2_limits* limits, tmc2gpu_ctx** out_ctx) {
+  if (!out_ctx) return TMC2_ERR_INVALID_ARG;
+  *out_ctx = nullptr;
+  const int n_dev = tmc2gpu_device_count();
+  if (n_dev <= 0) return TMC2_ERR_NO_DEVICE;      // no CPU fallback
+  std::unique_ptr<tmc2gpu_ctx> ctx(new tmc2gpu_ctx());
+  if (device_ids && device_count > 0) {
+    for (int i = 0; i < device_count; ++i) {
+      if (device_ids[i] < 0 || device_ids[i] >= n_dev) return TMC2_ERR_NO_DEVICE;
+      ctx->devices.push_back(device_ids[i]);
+    }
+  } else {
+    ctx->devices.push_back(0);
+  }
+  if (limits) ctx->limits = *limits;
+  if (ctx->limits.gofs_in_flight == 0) ctx->limits.gofs_in_flight = 2;
+  if (ctx->limits.gofs_in_flight > 8) ctx->limits.gofs_in_flight = 8;
+  ctx->two_pass = (ctx->limits.flags & TMC2_CTX_TWO_PASS_SCAN) != 0;
+  ctx->slots.resize(ctx->devices.size());
+  for (size_t d = 0; d < ctx->devices.size(); ++d) {
+    for (uint32_t k = 0; k < ctx->limits.gofs_in_flight; ++k) {
+      std::unique_ptr<Batch> b(new Batch());
+      if (b->init(ctx->devices[d], ctx->two_pass, ctx->err)) return ctx->err.st;
+      ctx->slots[d].push_back(std::move(b));
+    }
+  }
+  ctx->stage_batch.reset(new Batch());
+  if (ctx->stage_batch->init(ctx->devices[0], ctx->two_pass, ctx->err)) return ctx->err.st;
+  *out_ctx = ctx.release();
+  return TMC2_OK;
+}
+
+void tmc2gpu_destroy(tmc2gpu_ctx* ctx) {
+  if (!ctx) return;
+  for (int d : ctx->devices) { cudaSetDevice(d); cudaDeviceSynchronize(); }
+  delete ctx;
+}
+
+const char* tmc2gpu_last_error(const tmc2gpu_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "ctx is NULL"; }
+
+void* tmc2gpu_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) return nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  g_pinned.emplace_back((const uint8_t*)p, bytes);
+  return p;
+}
+void tmc2gpu_free_pinned(void* p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (size_t i = 0; i < g_pinned.size(); ++i)
+      if (g_pinned[i].first == p) { g_pinned.erase(g_pinned.begin() + i); break; }
+  }
+  cudaFreeHost(p);
+}
+
+// ---- streaming -----------------------------------------------------------------------------------------------
+tmc2_status tmc2gpu_submit_gof(tmc2gpu_ctx* ctx, const tmc2_gof* gof) {
+  if (!ctx) return TMC2_ERR_INVALID_ARG;
+  Err& err = ctx->err;
+  err = Err();
+  if (validate_params(gof, err)) return ctx->fail();
+  if (ctx->limits.max_frames && gof->frame_count > ctx->limits.max_frames) {
+    err.st = TMC2_ERR_CAPACITY; err.msg = "GOF has more frames than limits.max_frames"; return ctx->fail();
+  }
+  if ((ctx->limits.max_width && gof->width > ctx->limits.max_width) ||
+      (ctx->limits.max_height && gof->height > ctx->limits.max_height)) {
+    err.st = TMC2_ERR_CAPACITY; err.msg = "frame larger than limits.max_width/height"; return ctx->fail();
+  }
+  for (uint32_t f = 0; f < gof->frame_count; ++f)
+    if (validate_frame(gof, f, err)) return ctx->fail();
+  if (gof->frame_count == 0) return TMC2_OK;
+
+  // frame-wise sharding: contiguous chunks of the GOF, one per device; no collective
+  const uint32_t D = (uint32_t)ctx->devices.size();
+  const uint32_t F = gof->frame_count;
+  std::vector<Batch*> chosen(D, nullptr);
+  for (uint32_t d = 0; d < D; ++d) {
+    const uint32_t lo = (uint32_t)((uint64_t)F * d / D), hi = (uint32_t)((uint64_t)F * (d + 1) / D);
+    if (hi == lo) continue;
+    for (auto& b : ctx->slots[d]) if (!b->busy) { chosen[d] = b.get(); break; }
+    if (!chosen[d]) {
+      err.st = TMC2_ERR_STATE;
+      err.msg = "all GOF slots in flight: drain frames with tmc2gpu_next_frame / release_frame first";
+      return ctx->fail();
+    }
+  }
+  for (uint32_t d = 0; d < D; ++d) {
+    const uint32_t lo = (uint32_t)((uint64_t)F * d / D), hi = (uint32_t)((uint64_t)F * (d + 1) / D);
+    if (hi == lo) continue;
+    Batch* b = chosen[d];
+    if (b->prepare(gof, lo, hi - lo, 0, err) || b->upload(gof, lo, err) || b->launch(b->stream, err)) return ctx->fail();
+    // counts travel right behind the kernels; result copies are enqueued when the first frame is asked for
+    b->busy = true; b->frames_released = 0;
+    ctx->last_batch = b;
+    for (uint32_t k = 0; k < hi - lo; ++k) ctx->pending.push_back({b, k, ctx->next_global++});
+  }
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_next_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out) {
+  if (!ctx || !out) return TMC2_ERR_INVALID_ARG;
+  Err& err = ctx->err;
+  err = Err();
+  if (ctx->pending.empty()) return TMC2_END;
+  PendingFrame pf = ctx->pending.front();
+  Batch* b = pf.batch;
+  if (!b->counts_ready && b->fetch_counts(b->stream, err)) return ctx->fail();
+  if (!b->outputs_enqueued && b->enqueue_outputs(err)) return ctx->fail();
+  if (cudaSetDevice(b->device) != cudaSuccess || cudaEventSynchronize(b->ev_frame[pf.local]) != cudaSuccess) {
+    err.st = TMC2_ERR_CUDA; err.msg = std::string("waiting for frame: ") + cudaGetErrorString(cudaGetLastError());
+    return ctx->fail();
+  }
+  ctx->pending.pop_front();
+  memset(out, 0, sizeof *out);
+  out->frame_index = pf.global_index;
+  out->point_count = b->counts[pf.local];
+  out->positions = reinterpret_cast<const uint16_t*>(b->h_out.as<uint8_t>() + b->out_pos_off[pf.local]);
+  out->with_colors = b->params.attribute_count ? 1 : 0;
+  out->colors = out->with_colors ? b->h_out.as<uint8_t>() + b->out_rgb_off[pf.local] : nullptr;
+  out->smoothed_positions = b->moved[pf.local];
+  out->smoothed_colors = b->recoloured[pf.local];
+  out->_handle = b;
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_release_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out) {
+  if (!ctx || !out || !out->_handle) return TMC2_ERR_INVALID_ARG;
+  Batch* b = static_cast<Batch*>(out->_handle);
+  bool known = false;
+  for (auto& v : ctx->slots) for (auto& s : v) known |= s.get() == b;
+  if (!known || !b->busy) { ctx->last_error = "release_frame: frame was not handed out by this context"; return TMC2_ERR_STATE; }
+  out->_handle = nullptr; out->positions = nullptr; out->colors = nullptr;
+  if (++b->frames_released >= b->F) b->busy = false;
+  return TMC2_OK;
+}
+
+// ---- resident path -------------------------------------------------------------------------------------------
+tmc2_status tmc2gpu_upload_gof(tmc2gpu_ctx* ctx, const tmc2_gof* gof, tmc2_resident** out) {
+  if (!ctx || !out) return TMC2_ERR_INVALID_ARG;
+  *out = nullptr;
+  Err& err = ctx->err;
+  err = Err();
+  if (validate_params(gof, err)) return ctx->fail();
+  for (uint32_t f = 0; f < gof->frame_count; ++f)
+    if (validate_frame(gof, f, err)) return ctx->fail();
+  std::unique_ptr<tmc2_resident> r(new tmc2_resident());
+  r->batch.reset(new Batch());
+  Batch* b = r->batch.get();
+  if (b->init(ctx->devices[0], ctx->two_pass, err) || b->prepare(gof, 0, gof->frame_count, 0, err) || b->upload(gof, 0, err))
+    return ctx->fail();
+  if (cudaStreamSynchronize(b->stream) != cudaSuccess) { err.st = TMC2_ERR_CUDA; err.msg = "upload sync"; return ctx->fail(); }
+  b->h_in.release();   // planes now live in HBM; the staging area is not needed again
+  *out = r.release();
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_reconstruct_resident(tmc2gpu_ctx* ctx, tmc2_resident* r, void* cuda_stream) {
+  if (!ctx || !r) return TMC2_ERR_INVALID_ARG;
+  Err& err = ctx->err;
+  err = Err();
+  Batch* b = r->batch.get();
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
+  if (b->launch(s, err)) return ctx->fail();
+  ctx->last_batch = b;
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_resident_counts(tmc2gpu_ctx* ctx, tmc2_resident* r, uint64_t* point_counts) {
+  if (!ctx || !r || !point_counts) return TMC2_ERR_INVALID_ARG;
+  Err& err = ctx->err;
+  err = Err();
+  Batch* b = r->batch.get();
+  if (cudaSetDevice(b->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    err.st = TMC2_ERR_CUDA; err.msg = std::string("device sync: ") + cudaGetErrorString(cudaGetLastError()); return ctx->fail();
+  }
+  if (b->fetch_counts(b->stream, err)) return ctx->fail();
+  for (uint32_t k = 0; k < b->F; ++k) point_counts[k] = b->counts[k];
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_resident_fetch(tmc2gpu_ctx* ctx, tmc2_resident* r, uint32_t frame, uint16_t* positions, uint8_t* colors,
+                                   uint64_t capacity_points) {
+  if (!ctx || !r) return TMC2_ERR_INVALID_ARG;
+  Err& err = ctx->err;
+  err = Err();
+  Batch* b = r->batch.get();
+  if (frame >= b->F) return TMC2_ERR_INVALID_ARG;
+  if (cudaSetDevice(b->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    err.st = TMC2_ERR_CUDA; err.msg = "device sync"; return ctx->fail();
+  }
+  if (!b->counts_ready && b->fetch_counts(b->stream, err)) return ctx->fail();
+  const uint64_t n = b->counts[frame];
+  if (n > capacity_points) { err.st = TMC2_ERR_CAPACITY; err.msg = "resident_fetch: capacity_points too small"; return ctx->fail(); }
+  auto body = [&]() -> tmc2_status {
+    if (positions && n)
+      CU(cudaMemcpy(positions, b->d_pos.as<uint8_t>() + (size_t)frame * b->cap * 6, n * 6, cudaMemcpyDeviceToHost));
+    if (colors && n && b->params.attribute_count)
+      CU(cudaMemcpy(colors, b->d_rgb.as<uint8_t>() + (size_t)frame * b->cap * 3, n * 3, cudaMemcpyDeviceToHost));
+    return TMC2_OK;
+  };
+  if (body()) return ctx->fail();
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_free_resident(tmc2gpu_ctx* ctx, tmc2_resident* r) {
+  if (!ctx || !r) return TMC2_ERR_INVALID_ARG;
+  if (ctx->last_batch == r->batch.get()) ctx->last_batch = nullptr;
+  cudaSetDevice(r->batch->device);
+  cudaDeviceSynchronize();
+  delete r;
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_last_launch_info(tmc2gpu_ctx* ctx, uint32_t* kernel_launches, uint64_t* unpack_algorithmic_bytes,
+                                     uint64_t* total_points) {
+  if (!ctx || !ctx->last_batch) return TMC2_ERR_STATE;
+  Batch* b = ctx->last_batch;
+  Err& err = ctx->err;
+  err = Err();
+  if (!b->counts_ready) {
+    if (cudaSetDevice(b->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return TMC2_ERR_CUDA;
+    if (b->fetch_counts(b->stream, err)) return ctx->fail();
+  }
+  uint64_t total = 0;
+  for (auto c : b->counts) total += c;
+  if (kernel_launches) *kernel_launches = b->launches;
+  if (unpack_algorithmic_bytes) *unpack_algorithmic_bytes = b->unpack_alg_bytes;
+  if (total_points) *total_points = total;
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_last_unpack_ms(tmc2gpu_ctx* ctx, float* ms) {
+  if (!ctx || !ctx->last_batch || !ms) return TMC2_ERR_STATE;
+  StageTimes t;
+  ctx->err = Err();
+  if (ctx->last_batch->stage_times(t, ctx->err)) return ctx->fail();
+  *ms = t.unpack;
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_last_stage_ms(tmc2gpu_ctx* ctx, float* ms5) {
+  if (!ctx || !ctx->last_batch || !ms5) return TMC2_ERR_STATE;
+  StageTimes t;
+  ctx->err = Err();
+  if (ctx->last_batch->stage_times(t, ctx->err)) return ctx->fail();
+  ms5[0] = t.b2p; ms5[1] = t.unpack; ms5[2] = t.geo; ms5[3] = t.col; ms5[4] = t.rgb;
+  return TMC2_OK;
+}
+
+// ---- stage entry points -----------------------------------------------------------------------------------------
+static tmc2_status run_single(tmc2gpu_ctx* ctx, const tmc2_gof* gof, uint32_t frame_index, uint32_t want) {
+  Err& err = ctx->err;
+  err = Err();
+  if (validate_params(gof, err)) return err.st;
+  if (frame_index >= gof->frame_count) FAIL(TMC2_ERR_INVALID_ARG, "frame_index %u >= frame_count %u", frame_index, gof->frame_count);
+  if (validate_frame(gof, frame_index, err)) return err.st;
+  Batch* b = ctx->stage_batch.get();
+  if (b->prepare(gof, frame_index, 1, want, err) || b->upload(gof, frame_index, err) || b->launch(b->stream, err)) return err.st;
+  if (b->fetch_counts(b->stream, err)) return err.st;
+  ctx->last_batch = b;
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_generate_block_to_patch_from_occupancy_map_video(tmc2gpu_ctx* ctx, const tmc2_gof* gof,
+                                                                      uint32_t frame_index, uint32_t* block_to_patch) {
+  if (!ctx || !block_to_patch) return TMC2_ERR_INVALID_ARG;
+  if (run_single(ctx, gof, frame_index, 0)) return ctx->fail();
+  Batch* b = ctx->stage_batch.get();
+  Err& err = ctx->err;
+  if (cudaMemcpy(block_to_patch, b->d_b2p.p, (size_t)b->bw * b->bh * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    err.st = TMC2_ERR_CUDA; err.msg = "block_to_patch D2H"; return ctx->fail();
+  }
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_generate_point_cloud(tmc2gpu_ctx* ctx, const tmc2_gof* gof, uint32_t frame_index,
+                                         tmc2_point_cloud_out* out) {
+  if (!ctx || !out) return TMC2_ERR_INVALID_ARG;
+  const bool dbg = out->colors16bit || out->partition || out->point_to_pixel || out->boundary_type ||
+                   out->positions_presmooth || out->colors16bit_presmooth;
+  const uint32_t want = (dbg ? WANT_DEBUG : 0u) | (out->occupancy_map ? WANT_OCC_FULL : 0u);
+  if (run_single(ctx, gof, frame_index, want)) return ctx->fail();
+  Batch* b = ctx->stage_batch.get();
+  Err& err = ctx->err;
+  const uint64_t n = b->counts[0];
+  out->point_count = n;
+  out->smoothed_positions = b->moved[0];
+  out->smoothed_colors = b->recoloured[0];
+  if (n > out->capacity_points) { err.st = TMC2_ERR_CAPACITY; err.msg = "capacity_points too small"; return ctx->fail(); }
+  const bool attr = b->params.attribute_count != 0;
+  auto d2h = [&](void* dst, const void* src, size_t bytes) -> bool {
+    if (!dst || !bytes || !src) return true;
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
+  };
+  bool ok = true;
+  ok &= d2h(out->positions, b->d_pos.p, n * 6);
+  if (attr) ok &= d2h(out->colors, b->d_rgb.p, n * 3);
+  if (attr && dbg) ok &= d2h(out->colors16bit, b->d_yuv.p, n * 6);
+  if (dbg) {
+    ok &= d2h(out->boundary_type, b->d_bt.p, n);
+    ok &= d2h(out->positions_presmooth, b->d_pos_pre.p, n * 6);
+    if (attr) ok &= d2h(out->colors16bit_presmooth, b->d_yuv_pre.p, n * 6);
+    if (out->partition && n) {
+      std::vector<uint16_t> tmp(n);
+      ok &= d2h(tmp.data(), b->d_part.p, n * 2);
+      for (uint64_t i = 0; i < n; ++i) out->partition[i] = tmp[i];
+    }
+    if (out->point_to_pixel && n) {
+      std::vector<uint32_t> tmp(n);
+      ok &= d2h(tmp.data(), b->d_pix.p, n * 4);
+      for (uint64_t i = 0; i < n; ++i) {
+        out->point_to_pixel[3 * i] = tmp[i] & 0x7FFFu;
+        out->point_to_pixel[3 * i + 1] = (tmp[i] >> 15) & 0x7FFFu;
+        out->point_to_pixel[3 * i + 2] = tmp[i] >> 30;
+      }
+    }
+  }
+  if (out->occupancy_map) ok &= d2h(out->occupancy_map, b->d_occ_full.p, (size_t)b->W * b->H);
+  if (out->block_to_patch) ok &= d2h(out->block_to_patch, b->d_b2p.p, (size_t)b->bw * b->bh * 4);
+  if (!ok) { err.st = TMC2_ERR_CUDA; err.msg = std::string("D2H: ") + cudaGetErrorString(cudaGetLastError()); return ctx->fail(); }
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_convert_yuv16_to_rgb8(tmc2gpu_ctx* ctx, const uint16_t* yuv16, uint64_t n, uint8_t* rgb8) {
+  if (!ctx || (n && (!yuv16 || !rgb8))) return TMC2_ERR_INVALID_ARG;
+  if (n == 0) return TMC2_OK;
+  Err& err = ctx->err;
+  err = Err();
+  Batch* b = ctx->stage_batch.get();
+  auto body = [&]() -> tmc2_status {
+    CU(cudaSetDevice(b->device));
+    DevBuf din, dout;
+    CU(din.ensure(n * 6));
+    CU(dout.ensure(n * 3));
+    CU(cudaMemcpyAsync(din.p, yuv16, n * 6, cudaMemcpyHostToDevice, b->stream));
+    KL(launch_yuv_to_rgb_flat(din.as<uint16_t>(), dout.as<uint8_t>(), n, b->stream));
+    CU(cudaMemcpyAsync(rgb8, dout.p, n * 3, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    din.release(); dout.release();
+    return TMC2_OK;
+  };
+  if (body()) return ctx->fail();
+  return TMC2_OK;
+}
+
+}  // extern "C"
