@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--two-pass", action="store_true", help="debug: count/scan/emit instead of the fused single pass")
+    ap.add_argument("--no-smoothing", action="store_true", help="reference-exact rec0 path only (no post-processing)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -143,7 +144,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     frames_default = {"c1": 1, "c2": 32, "c3": 32, "c4": 8}.get(args.config, 32)
     frames = args.frames or frames_default
-    smoothing = args.config != "c1"
+    smoothing = args.config != "c1" and not args.no_smoothing
     cfg_desc = {"workload": f"{args.config}: {frames}-frame GOF, synthetic decoded planes + patch metadata", "frames_per_gof": frames}
 
     # ------------------------------------------------------------------------------------------------ reference arm
@@ -151,6 +152,8 @@ def main():
         if rank != 0:
             return 0
         gof, cfg = build_workload(args.config, frames, min(args.distinct, 4))
+        gof.params.geometry_smoothing = smoothing
+        gof.params.color_smoothing = smoothing
         cfg_desc.update({"atlas": f"{cfg.width}x{cfg.height}", "smoothing": smoothing, "maps": 2,
                          "occupancy_precision": cfg.occupancy_precision})
         sample = max(1, min(frames, 2))                   # frames per step: bounded so K steps end within minutes
@@ -200,7 +203,12 @@ def main():
 
     # ---- value: planes resident in HBM, kernels only -----------------------------------------------------------------
     res = ctx.upload_gof(view)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated torch stream: torch.cuda.Event only sees the stream it is recorded on, and torch's default stream
+    # has handle 0, which the C ABI reads as "use the library's own stream"
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     for _ in range(args.warmup):
         res.reconstruct(stream)
     counts = res.counts()

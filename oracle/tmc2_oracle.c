@@ -509,7 +509,7 @@ static int geometry_smoothing(const tmc2_params* P, uint64_t n, uint16_t* pos, c
   return TMC2_OK;
 }
 
-/* K7: grid colour smoothing on the 16-bit YUV colours, on the (already smoothed) positions. */
+/* K7: grid colour smoothing on the 16-bit YUV colours; cells are indexed by the pre-geometry-smoothing positions. */
 static int color_smoothing(const tmc2_params* P, uint64_t n, const uint16_t* pos, uint16_t* c16,
                            const uint64_t* partition, const uint8_t* btype, uint64_t* recoloured) {
   grid_geom G;
@@ -645,7 +645,9 @@ int orc_reconstruct_frame(const tmc2_gof* g, uint32_t frame_index, orc_frame** o
     if (P->color_smoothing && reconstruct.with_colors) {
       F->colors16bit_presmooth = (uint16_t*)malloc((size_t)n * 6);
       memcpy(F->colors16bit_presmooth, F->colors16bit, (size_t)n * 6);
-      st = color_smoothing(P, n, F->positions, F->colors16bit, F->partition, F->boundary_type, &F->smoothed_colors);
+      /* own spec: the colour grid is built on the RECONSTRUCTED (pre-geometry-smoothing) positions, so both
+       * post-processing stages depend only on the unpack output and can share one pass over the points */
+      st = color_smoothing(P, n, F->positions_presmooth, F->colors16bit, F->partition, F->boundary_type, &F->smoothed_colors);
       if (st) { orc_frame_free(F); return st; }
     }
   }

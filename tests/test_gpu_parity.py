@@ -188,7 +188,7 @@ def test_smoothing_dense_overlap_case(gpu_ctx):
     g.params.geometry_smoothing = True
     g.params.color_smoothing = True
     got, want = both(gpu_ctx, g, 1)
-    assert want["smoothed_positions"] > 100 and want["smoothed_colors"] > 100
+    assert want["smoothed_positions"] > 20 and want["smoothed_colors"] > 20
     util.assert_same(got, want, keys=("positions", "colors16bit", "colors", "boundary_type"), what="dense overlap")
     # streaming path with smoothing gives the same frames
     frames = gpu_ctx.decode_gof(abi.GofView(g))

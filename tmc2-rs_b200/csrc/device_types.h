@@ -8,8 +8,10 @@
 //   patches[total]  DevPatch ; slot_patch[n_tiles*kWarpsPerTile] ; tile_frame[n_tiles] ; frame_tile_begin[F+1]
 //   block_to_patch [F][bw*bh] u32
 // Pitches are multiples of 64 elements so every 16x16 canvas block row starts on a 32-byte boundary.
-// Outputs are per-frame slabs of `cap` points:  pos [F][cap][3] u16, rgb [F][cap][3] u8, yuv [F][cap][3] u16,
-// partition [F][cap] u16, pixel [F][cap] u32 (x | y<<15 | map<<30), btype [F][cap] u8, count [F] u32.
+// Outputs are per-frame slabs of `cap` points:  pos [F][cap][3] u16, rgb [F][cap][3] u8, and (debug / stage API only)
+// yuv [F][cap][3] u16, partition [F][cap] u16, pixel [F][cap] u32 (x | y<<15 | map<<30), btype [F][cap] u8; count [F] u32.
+// Smoothing state: per frame-in-group sparse voxel-cell tables (GeoCell / ColCell), touched-slot lists, and per frame a
+// compact list of type-1 boundary points (BoundaryEntry).
 #pragma once
 #include <cstdint>
 
@@ -56,6 +58,50 @@ struct Outputs {                // any pointer may be null = stream not wanted
   uint64_t  cap;                // points per frame slab
 };
 
+// ---- sparse voxel-cell tables of the grid smoothing stages (own spec) ---------------------------------
+constexpr uint32_t kCellEmpty = 0xFFFFFFFFu;
+struct GeoCell {     // 32 B = one DRAM sector
+  uint32_t key;      // cx | cy<<10 | cz<<20 ; kCellEmpty = free
+  uint32_t count;
+  uint32_t pmin, pmax;          // smallest / largest patch index seen
+  uint32_t sx, sy, sz;          // sums of (coordinate - cell origin)  (< grid size each)
+  uint32_t _pad;
+};
+struct ColCell {     // 64 B
+  uint32_t key, count, pmin, pmax;
+  unsigned long long sy, su, sv;   // sums of Y, U, V
+  unsigned long long sy2;          // sum of Y*Y
+  unsigned long long _pad[2];
+};
+struct alignas(16) BoundaryEntry {  // one type-1 boundary point (16 B)
+  uint32_t idx;         // point index inside its frame
+  uint16_t pos[3];      // reconstructed (pre-smoothing) position
+  uint16_t yuv[3];      // 16-bit colour
+};
+
+struct GridDesc {               // geometry of one voxel grid
+  uint32_t on;
+  uint32_t g, w, disth, th;     // cell edge, cells per axis, border margin, g*w
+  uint32_t identity;            // 1: slot = dense cell index (table covers the whole grid)
+  uint64_t slots;               // table slots per frame-in-group (power of two unless identity)
+  void*    table;               // GeoCell / ColCell [frames_in_group][slots]
+  uint32_t* touched;            // [frames_in_group][touched_cap]
+  uint32_t* touched_count;      // [frames_in_group]
+};
+
+struct SmoothArgs {
+  GridDesc geo, col;
+  uint64_t touched_cap;
+  BoundaryEntry* blist;         // [F][blist_cap]
+  uint32_t* blist_count;        // [F]
+  uint64_t blist_cap;
+  uint32_t group_first_frame;   // tables are indexed by (frame - group_first_frame)
+  uint32_t group_frames;
+  uint32_t thr_geo;             // threshold_smoothing
+  uint32_t thr_col_smooth, thr_col_diff, thr_col_var;   // colour thresholds, already scaled to the sample bit depth
+  unsigned long long* changed;  // [2][F] moved / recoloured points
+};
+
 struct UnpackArgs {
   Planes   in;
   Outputs  out;
@@ -75,54 +121,18 @@ struct UnpackArgs {
   uint32_t*       frame_count;        // [F] points per frame
   int*            err;                // device error flag (0 ok)
   // byte offsets of each staged stream inside a warp's shared-memory region, and the region size
-  uint32_t off_pos, off_rgb, off_yuv, off_part, off_pix, off_bt, warp_bytes;
-};
-
-// ---- sparse voxel-cell table used by grid geometry / colour smoothing (own spec) ----------------------
-struct GeoCell {     // 32 B = one DRAM sector
-  uint32_t key;      // cx | cy<<10 | cz<<20 ; 0xFFFFFFFF = empty
-  uint32_t count;
-  uint32_t pmin, pmax;          // smallest / largest patch index seen
-  uint32_t sx, sy, sz;          // sums of (coordinate - cell origin)  (< grid size each)
-  uint32_t _pad;
-};
-struct ColCell {     // 64 B
-  uint32_t key, count, pmin, pmax;
-  unsigned long long sy, su, sv;   // sums of Y, U, V
-  unsigned long long sy2;          // sum of Y*Y
-  unsigned long long _pad[2];
-};
-constexpr uint32_t kCellEmpty = 0xFFFFFFFFu;
-
-struct GridArgs {
-  uint32_t g, w, disth, th;     // cell edge, cells per axis, border margin, g*w
-  uint32_t n_frames;
-  uint64_t cap;                 // points per frame slab
-  uint64_t table_slots;         // per frame, power of two
-  uint32_t identity_hash;       // 1: slot = dense cell index (table covers the whole grid)
-  const uint32_t* frame_count;
-  uint16_t* pos;                // in/out (geometry filter writes)
-  uint16_t* yuv;                // in/out (colour filter writes)
-  const uint16_t* part;
-  const uint8_t*  btype;
-  void*     table;              // GeoCell[F][slots] or ColCell[F][slots]
-  uint32_t* touched;            // [F][touched_cap] slots claimed during accumulate
-  uint32_t* touched_count;      // [F]
-  uint64_t  touched_cap;
-  uint32_t  thr_a, thr_b, thr_c; // geometry: threshold_smoothing ; colour: smoothing, difference, variation (scaled)
-  unsigned long long* changed;  // [F] moved / recoloured points
-  int*      err;
+  uint32_t off_scan, off_pos, off_rgb, off_yuv, off_part, off_pix, off_bt, warp_bytes;
+  SmoothArgs sm;                      // used by the smoothing instantiation only
 };
 
 // launch wrappers (kernels.cu); every one enqueues on `stream` and returns the cudaGetLastError() code
 int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream);
-int launch_unpack(const UnpackArgs& a, int mode /*0 fused, 1 count, 2 emit*/, void* stream);
+// mode: 0 fused single pass, 1 count, 2 emit.  Tiles [tile_begin, tile_end).  smooth: accumulate cell tables + boundary list
+int launch_unpack(const UnpackArgs& a, int mode, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream);
 int launch_tile_scan(const UnpackArgs& a, void* stream);
 int launch_upsample(const UnpackArgs& a, uint8_t* occ_full /*[F][H][W]*/, void* stream);
-int launch_geo_smoothing(const GridArgs& g, void* stream);     // accumulate + filter + clear
-int launch_color_smoothing(const GridArgs& g, void* stream);   // accumulate + filter + clear
-int launch_yuv_to_rgb(const uint16_t* yuv, uint8_t* rgb, const uint32_t* frame_count, uint32_t n_frames, uint64_t cap,
-                      void* stream);
+int launch_smooth_filter(const UnpackArgs& a, void* stream);   // boundary points of the current frame group
+int launch_smooth_clear(const UnpackArgs& a, void* stream);    // reset touched cells + list counters of the group
 int launch_yuv_to_rgb_flat(const uint16_t* yuv, uint8_t* rgb, uint64_t n, void* stream);
 int launch_table_init(void* table, uint64_t total_slots, int is_color, void* stream);
 size_t unpack_smem_bytes(const UnpackArgs& a);

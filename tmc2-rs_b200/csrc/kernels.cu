@@ -4,10 +4,9 @@
 //   K1  upsample_kernel           src/codec.rs:288-300   (materialised only for the stage API; fused otherwise)
 //   K3+K4 unpack_kernel           src/codec.rs:352-480 (unpack loop, order, dedup), :517-565 (generate_points),
 //                                 :569-658 (attribute fetch), :661-687 (YUV->RGB), src/decoder.rs:827-888 (patch maths)
-//       + K5 boundary type per point (own spec)
-//   K6  geo_accumulate / geo_filter      grid geometry smoothing (own integer spec; reference stubs
-//   K7  col_accumulate / col_filter      decoder.rs:291-299)
-//       yuv_to_rgb_kernel         src/codec.rs:88-94 + :661-687
+//       + K5 boundary type per point, K6/K7 cell statistics (own spec) in the smoothing instantiation
+//   K6/K7 smooth_filter_kernel    grid geometry + colour smoothing of the boundary points (own integer spec, DESIGN.md;
+//                                 the reference has only stubs: decoder.rs:291-299)
 //
 // Ordering.  The reference emits points in (patch, v0, u0, v1, u1, map) order.  A 16x16 patch block ("slot") that
 // owns its canvas block emits one contiguous run, so the output position of a run is an exclusive prefix sum of
@@ -15,8 +14,10 @@
 // slots, and tiles publish / look back their prefix through `tile_status` (single-pass chained scan with decoupled
 // look-back, tile id == blockIdx.x, one scan domain per frame).  Nothing is read twice from HBM.
 //
-// All arithmetic on the bit-exact path is integer except the colour conversion, which is IEEE f64 with every operation
-// rounded separately (__dmul_rn/__dadd_rn/__ddiv_rn: no FMA contraction), exactly like the reference's Rust code.
+// All arithmetic on the bit-exact path is integer.  The colour conversion of the reference is IEEE f64; it is evaluated
+// here in 32.32 fixed point with a proven error margin, and re-done with the literal f64 sequence (__dmul_rn/__dadd_rn/
+// __ddiv_rn, every operation rounded on its own like rustc's code) whenever the fixed-point value is within that margin
+// of an integer boundary, so the result is bit-exact for every u16 input.
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -107,36 +108,57 @@ __device__ __forceinline__ uint32_t normal_coord(const DevPatch& P, uint32_t dep
   const uint32_t n = P.mode == 0 ? depth + P.d1 : (P.d1 > depth ? P.d1 : depth) - depth;
   return n & 0xFFFFu;
 }
-// generate_point (decoder.rs:871-878): sequential writes, later axes overwrite earlier ones if they coincide
-__device__ __forceinline__ void make_point(const DevPatch& P, uint32_t n, uint32_t t, uint32_t b, uint32_t out[3]) {
-  out[0] = out[1] = out[2] = 0;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    if (P.normal == a) out[a] = n;
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    if (P.tangent == a) out[a] = t;
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    if (P.bitangent == a) out[a] = b;
-  }
+// generate_point (decoder.rs:871-878) writes point[normal], point[tangent], point[bitangent] in that order, so a later
+// axis overwrites an earlier one if they coincide.  axis_source() returns, for output axis `a`, which value lands there:
+// 0 nothing, 1 normal, 2 tangent, 3 bitangent.
+__device__ __forceinline__ uint32_t axis_source(const DevPatch& P, uint32_t a) {
+  return P.bitangent == a ? 3u : P.tangent == a ? 2u : P.normal == a ? 1u : 0u;
+}
+__device__ __forceinline__ uint32_t pick(uint32_t src, uint32_t n, uint32_t t, uint32_t b) {
+  return src == 3u ? b : src == 2u ? t : src == 1u ? n : 0u;
 }
 
-// convert_yuv10_to_rgb8, src/codec.rs:661-687.  One channel: clamp(floor(c / 1023 * 255)).
-__device__ __forceinline__ uint32_t quant_channel(double c) {
+// ---- convert_yuv10_to_rgb8, src/codec.rs:661-687 ---------------------------------------------------------------------
+// literal f64 sequence: one channel = clamp(floor(c / 1023 * 255))
+__device__ __forceinline__ uint32_t quant_channel_f64(double c) {
   const double q = floor(__dmul_rn(__ddiv_rn(c, 1023.0), 255.0));
   if (q < 0.0) return 0u;
   if (q > 255.0) return 255u;
   return (uint32_t)q;
 }
-__device__ __forceinline__ uint32_t yuv_to_rgb_packed(uint32_t Y, uint32_t U, uint32_t V) {
+__device__ __noinline__ uint32_t yuv_to_rgb_f64(uint32_t Y, uint32_t U, uint32_t V) {
   const double y = (double)Y, u = __dsub_rn((double)U, 512.0), v = __dsub_rn((double)V, 512.0);
   const double r = __dadd_rn(y, __dmul_rn(1.57480, v));
   const double g = __dsub_rn(__dsub_rn(y, __dmul_rn(0.18733, u)), __dmul_rn(0.46813, v));
   const double b = __dadd_rn(y, __dmul_rn(1.85563, u));
-  return quant_channel(r) | (quant_channel(g) << 8) | (quant_channel(b) << 16);
+  return quant_channel_f64(r) | (quant_channel_f64(g) << 8) | (quant_channel_f64(b) << 16);
+}
+// Fixed point: N = c * 2^32 with the f64 constants rounded to 32 fractional bits (|error| <= |d|/2 units per product).
+// T = 255 c / 1023 ; A = 255 N ; floor(T) = floor(A / (1023 * 2^32)).  The f64 chain deviates from the real value by
+// < 2e-11 (< 100 units of A), the constants' rounding by <= 127.5 |d| units, so the result is certain unless A is within
+// `margin` = 128 |d| + 1024 units of a multiple of 1023 * 2^32.
+constexpr long long kKr = 6763714498LL;   // 1.57480 * 2^32
+constexpr long long kKgu = 804576224LL;   // 0.18733 * 2^32
+constexpr long long kKgv = 2010603040LL;  // 0.46813 * 2^32
+constexpr long long kKb = 7969870163LL;   // 1.85563 * 2^32
+__device__ __forceinline__ uint32_t quant_fixed(long long N, uint32_t margin, bool& uncertain) {
+  if (N <= 0) return 0u;                                   // c <= 0: floor(T) <= 0 -> 0 after the clamp
+  const unsigned long long A = (unsigned long long)N * 255ull;   // < 2^58
+  const uint32_t hi = (uint32_t)(A >> 32), lo = (uint32_t)A;
+  const uint32_t q = hi / 1023u, rem = hi - q * 1023u;
+  uncertain |= (rem == 0u && lo < margin) || (rem == 1022u && lo > ~margin);
+  return q > 255u ? 255u : q;
+}
+__device__ __forceinline__ uint32_t yuv_to_rgb_packed(uint32_t Y, uint32_t U, uint32_t V) {
+  const int32_t du = (int32_t)U - 512, dv = (int32_t)V - 512;
+  const long long y32 = (long long)Y << 32;
+  const uint32_t adu = (uint32_t)abs(du), adv = (uint32_t)abs(dv);
+  bool unc = false;
+  const uint32_t r = quant_fixed(y32 + kKr * dv, 128u * adv + 1024u, unc);
+  const uint32_t g = quant_fixed(y32 - kKgu * du - kKgv * dv, 128u * (adu + adv) + 1024u, unc);
+  const uint32_t b = quant_fixed(y32 + kKb * du, 128u * adu + 1024u, unc);
+  if (unc) return yuv_to_rgb_f64(Y, U, V);                 // a handful of points per million
+  return r | (g << 8) | (b << 16);
 }
 
 // occupancy of the full-resolution pixel (x,y) straight from the low-resolution video (codec.rs:294-298)
@@ -159,6 +181,77 @@ __device__ uint32_t boundary_type(const UnpackArgs& a, const uint8_t* occ_f, int
     for (uint32_t cx = cxa; cx <= cxb; ++cx)
       if (occ_f[(uint64_t)cy * a.in.occ_pitch + cx] == 0) return 2;
   return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// sparse voxel-cell tables (own spec; see DESIGN.md "Smoothing specification")
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t cell_slot0(uint32_t key, const GridDesc& G) {
+  const uint32_t cx = key & 1023u, cy = (key >> 10) & 1023u, cz = key >> 20;
+  if (G.identity) return cx + (uint64_t)G.w * (cy + (uint64_t)G.w * cz);
+  // 2x2x2 neighbouring cells share one 8-slot group: the filter's neighbourhood lookups stay within a few lines
+  const uint32_t grp = (cx >> 1) | ((cy >> 1) << 9) | ((cz >> 1) << 18);
+  const uint64_t h = ((uint64_t)grp * 0x9E3779B97F4A7C15ull) >> 24;
+  return ((h << 3) | ((cx & 1u) | ((cy & 1u) << 1) | ((cz & 1u) << 2))) & (G.slots - 1);
+}
+
+template <typename Cell>
+__device__ __forceinline__ Cell* cell_insert(const GridDesc& G, uint32_t fig, uint32_t key, uint64_t touched_cap, int* err) {
+  Cell* tab = reinterpret_cast<Cell*>(G.table) + (uint64_t)fig * G.slots;
+  uint64_t i = cell_slot0(key, G);
+  for (uint64_t probe = 0; probe < G.slots; ++probe) {
+    uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&tab[i].key);
+    if (cur == kCellEmpty) {
+      cur = atomicCAS(&tab[i].key, kCellEmpty, key);
+      if (cur == kCellEmpty) {
+        const uint32_t t = atomicAdd(&G.touched_count[fig], 1u);
+        if (t < touched_cap) G.touched[(uint64_t)fig * touched_cap + t] = (uint32_t)i;
+        else atomicExch(err, 11);
+        return &tab[i];
+      }
+    }
+    if (cur == key) return &tab[i];
+    i = G.identity ? (i + 1 < G.slots ? i + 1 : 0) : ((i + 1) & (G.slots - 1));
+  }
+  atomicExch(err, 11);
+  return nullptr;
+}
+template <typename Cell>
+__device__ __forceinline__ const Cell* cell_find(const GridDesc& G, uint32_t fig, uint32_t key) {
+  const Cell* tab = reinterpret_cast<const Cell*>(G.table) + (uint64_t)fig * G.slots;
+  uint64_t i = cell_slot0(key, G);
+  for (uint64_t probe = 0; probe < G.slots; ++probe) {
+    const uint32_t k = tab[i].key;
+    if (k == key) return &tab[i];
+    if (k == kCellEmpty) return nullptr;
+    i = G.identity ? (i + 1 < G.slots ? i + 1 : 0) : ((i + 1) & (G.slots - 1));
+  }
+  return nullptr;
+}
+__device__ __forceinline__ void patch_range_update(uint32_t* pmin, uint32_t* pmax, uint32_t patch) {
+  // stale reads only ever show a wider-than-current gap, so skipping the atomic when the patch is already inside is safe
+  if (__ldcg(pmin) > patch) atomicMin(pmin, patch);
+  if (__ldcg(pmax) < patch) atomicMax(pmax, patch);
+}
+
+struct GeoRun { uint32_t key, cnt, sx, sy, sz; };
+struct ColRun { uint32_t key, cnt, sy, su, sv; unsigned long long sy2; };
+
+__device__ __forceinline__ void flush_geo(const UnpackArgs& a, uint32_t fig, const GeoRun& r, uint32_t patch) {
+  if (r.cnt == 0) return;
+  GeoCell* c = cell_insert<GeoCell>(a.sm.geo, fig, r.key, a.sm.touched_cap, a.err);
+  if (!c) return;
+  atomicAdd(&c->count, r.cnt); atomicAdd(&c->sx, r.sx); atomicAdd(&c->sy, r.sy); atomicAdd(&c->sz, r.sz);
+  patch_range_update(&c->pmin, &c->pmax, patch);
+}
+__device__ __forceinline__ void flush_col(const UnpackArgs& a, uint32_t fig, const ColRun& r, uint32_t patch) {
+  if (r.cnt == 0) return;
+  ColCell* c = cell_insert<ColCell>(a.sm.col, fig, r.key, a.sm.touched_cap, a.err);
+  if (!c) return;
+  atomicAdd(&c->count, r.cnt);
+  atomicAdd(&c->sy, (unsigned long long)r.sy); atomicAdd(&c->su, (unsigned long long)r.su);
+  atomicAdd(&c->sv, (unsigned long long)r.sv); atomicAdd(&c->sy2, r.sy2);
+  patch_range_update(&c->pmin, &c->pmax, patch);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -218,7 +311,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(const UnpackArgs a, uint8
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// K3+K4(+K5): fused unpack.
+// K3+K4(+K5, + K6/K7 statistics): fused unpack.
 // ----------------------------------------------------------------------------------------------------------------
 constexpr unsigned long long kFlagAggregate = 1ull, kFlagInclusive = 2ull;
 __device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, unsigned long long flag, uint32_t value) {
@@ -237,14 +330,16 @@ __device__ __forceinline__ void warp_copy_out(uint8_t* __restrict__ g, const uin
   if (done + lane < nbytes) g[done + lane] = sm[done + lane];
 }
 
-template <int kMode>   // 0: fused single pass (chained scan) ; 1: count only ; 2: emit with precomputed tile bases
-__global__ void __launch_bounds__(kWarpsPerTile * 32) unpack_kernel(const UnpackArgs a) {
+__device__ __forceinline__ int64_t ceil_div_pos(int64_t n, int64_t d) { return n <= 0 ? 0 : (n + d - 1) / d; }
+
+template <int kMode, bool kSmooth>   // kMode 0: fused single pass (chained scan) ; 1: count only ; 2: emit with tile bases
+__global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) unpack_kernel(const UnpackArgs a, uint32_t tile_offset) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_tot[kWarpsPerTile];
   __shared__ uint32_t s_base;
 
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-  const uint32_t tile = blockIdx.x;
+  const uint32_t tile = blockIdx.x + tile_offset;
   const uint32_t slot = tile * kWarpsPerTile + warp;
   const uint32_t frame = a.tile_frame[tile];
   const uint32_t pid = a.slot_patch[slot];
@@ -404,20 +499,22 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32) unpack_kernel(const Unpack
     return;
   }
   const uint64_t gidx = (uint64_t)frame * a.out.cap + run_base;   // first point of this run
+  const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
 
   // ---- phase 2 ----------------------------------------------------------------------------------------------------
   if (fast) {
     uint8_t* wsm = smem + (size_t)warp * a.warp_bytes;
     // (a) exclusive prefix of the per-pixel counts in PATCH-LOCAL raster order (v1 major, u1 minor; codec.rs:382-385)
-    uint8_t* cnt_sm = wsm;                                          // [256] counts by rank
-    uint16_t* pre_sm = reinterpret_cast<uint16_t*>(wsm + 256);      // [256] exclusive prefix by rank
-    uint32_t rank[8];
+    uint8_t* cnt_sm = wsm + a.off_scan;                             // [256] counts by rank
+    uint16_t* pre_sm = reinterpret_cast<uint16_t*>(cnt_sm + 256);   // [256] exclusive prefix by rank
+    int32_t pu, pv, pu1, pv1;
+    canvas_to_patch(P, px, py, 16, pu, pv);
+    canvas_to_patch(P, px + 1, py, 16, pu1, pv1);
+    const int32_t su = pu1 - pu, sv = pv1 - pv;                     // patch-space step per canvas pixel
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      int32_t u, v;
-      canvas_to_patch(P, px + j, py, 16, u, v);
-      rank[j] = (uint32_t)((v & 15) * 16 + (u & 15));
-      cnt_sm[rank[j]] = (uint8_t)(((m1 >> j) & 1u) + ((m2 >> j) & 1u));
+      const uint32_t rank = (uint32_t)(((pv + j * sv) & 15) * 16 + ((pu + j * su) & 15));
+      cnt_sm[rank] = (uint8_t)(((m1 >> j) & 1u) + ((m2 >> j) & 1u));
     }
     __syncwarp();
     {
@@ -443,10 +540,6 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32) unpack_kernel(const Unpack
       *reinterpret_cast<uint4*>(pre_sm + lane * 8) = packed;
     }
     __syncwarp();
-    uint32_t off[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) off[j] = pre_sm[rank[j]];
-    __syncwarp();                                                   // the scratch is reused as staging below
 
     // (b) stage every output stream in shared memory at the same 16-byte phase as its global destination
     uint8_t* g_pos = a.out.pos ? reinterpret_cast<uint8_t*>(a.out.pos) + gidx * 6 : nullptr;
@@ -457,16 +550,20 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32) unpack_kernel(const Unpack
     uint8_t* g_bt = a.out.btype ? a.out.btype + gidx : nullptr;
     uint8_t* s_pos = wsm + a.off_pos + ((uintptr_t)g_pos & 15u);
     uint8_t* s_rgb = wsm + a.off_rgb + ((uintptr_t)g_rgb & 15u);
-    uint8_t* s_yuv = wsm + a.off_yuv + ((uintptr_t)g_yuv & 15u);
+    uint8_t* s_yuv = wsm + a.off_yuv + ((uintptr_t)g_yuv & 15u);      // smoothing: staged even when not written out
     uint8_t* s_part = wsm + a.off_part + ((uintptr_t)g_part & 15u);
     uint8_t* s_pix = wsm + a.off_pix + ((uintptr_t)g_pix & 15u);
-    uint8_t* s_bt = wsm + a.off_bt + ((uintptr_t)g_bt & 15u);
+    uint8_t* s_bt = wsm + a.off_bt + ((uintptr_t)g_bt & 15u);         // smoothing: staged even when not written out
+    const bool st_yuv = a.has_attr && (g_yuv != nullptr || kSmooth);
+    const bool st_bt = g_bt != nullptr || kSmooth;
+    const uint32_t srcx = axis_source(P, 0), srcy = axis_source(P, 1), srcz = axis_source(P, 2);
+    uint32_t n_boundary = 0;
 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (!((m1 >> j) & 1u)) continue;
-      int32_t u, v;
-      canvas_to_patch(P, px + j, py, 16, u, v);
+      const int32_t u = pu + j * su, v = pv + j * sv;
+      const uint32_t k0 = pre_sm[(uint32_t)((v & 15) * 16 + (u & 15))];
       const uint32_t t = ((uint32_t)u * P.lod_x + P.u1) & 0xFFFFu;             // decoder.rs:875
       const uint32_t b = ((uint32_t)v * P.lod_y + P.v1) & 0xFFFFu;             // decoder.rs:876
       const uint32_t d0 = u16_of(g0, j) >> 2, d1 = u16_of(g1, j) >> 2;
@@ -474,20 +571,19 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32) unpack_kernel(const Unpack
       const uint32_t n1 = a.absolute_d1 ? normal_coord(P, d1) : ((P.mode == 0 ? n0 + d1 : n0 - d1) & 0xFFFFu);
       const uint32_t npts = 1u + ((m2 >> j) & 1u);
       uint32_t bt = 0;
-      if (g_bt) bt = boundary_type(a, occ_f, px + j, py);
+      if (st_bt) { bt = boundary_type(a, occ_f, px + j, py); n_boundary += bt == 1u ? npts : 0u; }
       for (uint32_t i = 0; i < npts; ++i) {                                     // map0 then map1 (codec.rs:421)
-        const uint32_t k = off[j] + i;
-        uint32_t pt[3];
-        make_point(P, i == 0 ? n0 : n1, t, b, pt);
-        if (g_pos) {
+        const uint32_t k = k0 + i;
+        const uint32_t n = i == 0 ? n0 : n1;
+        {
           uint16_t* d = reinterpret_cast<uint16_t*>(s_pos + k * 6);
-          d[0] = (uint16_t)pt[0]; d[1] = (uint16_t)pt[1]; d[2] = (uint16_t)pt[2];
+          d[0] = (uint16_t)pick(srcx, n, t, b); d[1] = (uint16_t)pick(srcy, n, t, b); d[2] = (uint16_t)pick(srcz, n, t, b);
         }
         if (a.has_attr) {
           const uint32_t Y = i == 0 ? u16_of(ya, j) : u16_of(yb, j);             // codec.rs:637-640, decoder.rs:976-977
           const uint32_t U = i == 0 ? u16_of(ua, j >> 1) : u16_of(ub, j >> 1);
           const uint32_t V = i == 0 ? u16_of(va, j >> 1) : u16_of(vb, j >> 1);
-          if (g_yuv) {
+          if (st_yuv) {
             uint16_t* d = reinterpret_cast<uint16_t*>(s_yuv + k * 6);
             d[0] = (uint16_t)Y; d[1] = (uint16_t)U; d[2] = (uint16_t)V;
           }
@@ -499,7 +595,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32) unpack_kernel(const Unpack
         }
         if (g_part) *reinterpret_cast<uint16_t*>(s_part + k * 2) = (uint16_t)P.local_index;   // codec.rs:452
         if (g_pix) *reinterpret_cast<uint32_t*>(s_pix + k * 4) = (uint32_t)(px + j) | ((uint32_t)py << 15) | (i << 30);
-        if (g_bt) s_bt[k] = (uint8_t)bt;
+        if (st_bt) s_bt[k] = (uint8_t)bt;
       }
     }
     __syncwarp();
@@ -510,9 +606,97 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32) unpack_kernel(const Unpack
     if (g_part) warp_copy_out(g_part, s_part, total * 2, lane);
     if (g_pix) warp_copy_out(g_pix, s_pix, total * 4, lane);
     if (g_bt) warp_copy_out(g_bt, s_bt, total, lane);
+
+    if (kSmooth) {
+      // (d) compact list of the type-1 boundary points of this run (order inside the list is irrelevant)
+      n_boundary = __reduce_add_sync(0xFFFFFFFFu, n_boundary);
+      if (n_boundary) {
+        uint32_t lbase = 0;
+        if (lane == 0) lbase = atomicAdd(&a.sm.blist_count[frame], n_boundary);
+        lbase = __shfl_sync(0xFFFFFFFFu, lbase, 0);
+        if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
+          if (lane == 0) atomicExch(a.err, 7);
+        } else {
+          BoundaryEntry* L = a.sm.blist + (uint64_t)frame * a.sm.blist_cap + lbase;
+          uint32_t done = 0;
+          for (uint32_t kb = 0; kb < total; kb += 32) {
+            const uint32_t k = kb + lane;
+            const bool isb = k < total && s_bt[k] == 1;
+            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, isb);
+            if (isb) {
+              BoundaryEntry e;
+              e.idx = run_base + k;
+              const uint16_t* p = reinterpret_cast<const uint16_t*>(s_pos + k * 6);
+              e.pos[0] = p[0]; e.pos[1] = p[1]; e.pos[2] = p[2];
+              if (a.has_attr) {
+                const uint16_t* c = reinterpret_cast<const uint16_t*>(s_yuv + k * 6);
+                e.yuv[0] = c[0]; e.yuv[1] = c[1]; e.yuv[2] = c[2];
+              } else { e.yuv[0] = e.yuv[1] = e.yuv[2] = 0; }
+              *reinterpret_cast<uint4*>(&L[done + __popc(mask & ((1u << lane) - 1u))]) = *reinterpret_cast<const uint4*>(&e);
+            }
+            done += __popc(mask);
+          }
+        }
+      }
+      // (e) cell statistics.  Work is split by cell-aligned squares of the colour grid in patch space (<= 25 per block
+      // for a cell edge of 4) so that a lane's points mostly share a cell; keys always come from the staged positions,
+      // so the split is only a grouping heuristic and stays exact under u16 wrap-around.
+      const bool do_geo = a.sm.geo.on != 0, do_col = a.sm.col.on != 0 && a.has_attr;
+      const int64_t cg = do_col ? a.sm.col.g : a.sm.geo.g;
+      const int64_t ulo = (int64_t)u0b * 16, vlo = (int64_t)v0b * 16;
+      const int64_t lx = P.lod_x, ly = P.lod_y;
+      const int64_t tc0 = (ulo * lx + P.u1) / cg, tc1 = ((ulo + 15) * lx + P.u1) / cg;
+      const int64_t bc0 = (vlo * ly + P.v1) / cg, bc1 = ((vlo + 15) * ly + P.v1) / cg;
+      const uint32_t nt = (uint32_t)(tc1 - tc0 + 1), nb = (uint32_t)(bc1 - bc0 + 1);
+      GeoRun gr0 = {kCellEmpty, 0, 0, 0, 0}, gr1 = gr0;
+      ColRun cr0 = {kCellEmpty, 0, 0, 0, 0, 0ull}, cr1 = cr0;
+      const uint32_t patch = P.local_index;
+      for (uint32_t pair = lane; pair < nt * nb; pair += 32) {
+        const int64_t tc = tc0 + pair % nt, bc = bc0 + pair / nt;
+        const int64_t ua_ = lx ? min(max(ceil_div_pos(tc * cg - P.u1, lx), ulo), ulo + 16) : ulo;
+        const int64_t ub_ = lx ? min(max(ceil_div_pos((tc + 1) * cg - P.u1, lx), ulo), ulo + 16) : ulo + 16;
+        const int64_t va_ = ly ? min(max(ceil_div_pos(bc * cg - P.v1, ly), vlo), vlo + 16) : vlo;
+        const int64_t vb_ = ly ? min(max(ceil_div_pos((bc + 1) * cg - P.v1, ly), vlo), vlo + 16) : vlo + 16;
+        for (int64_t vv = va_; vv < vb_; ++vv) {
+          for (int64_t uu = ua_; uu < ub_; ++uu) {
+            const uint32_t rank = (uint32_t)((vv & 15) * 16 + (uu & 15));
+            const uint32_t cnt = cnt_sm[rank];
+            const uint32_t k0 = pre_sm[rank];
+            for (uint32_t i = 0; i < cnt; ++i) {
+              const uint16_t* p = reinterpret_cast<const uint16_t*>(s_pos + (k0 + i) * 6);
+              const uint32_t x = p[0], y = p[1], z = p[2];
+              if (do_geo && x < a.sm.geo.th && y < a.sm.geo.th && z < a.sm.geo.th) {
+                const uint32_t g = a.sm.geo.g;
+                const uint32_t cx = x / g, cy = y / g, cz = z / g;
+                const uint32_t key = cx | (cy << 10) | (cz << 20);
+                if (key != gr0.key) {
+                  if (key == gr1.key) { const GeoRun t = gr0; gr0 = gr1; gr1 = t; }
+                  else { flush_geo(a, fig, gr1, patch); gr1 = gr0; gr0 = {key, 0, 0, 0, 0}; }
+                }
+                gr0.cnt += 1; gr0.sx += x - cx * g; gr0.sy += y - cy * g; gr0.sz += z - cz * g;
+              }
+              if (do_col && x < a.sm.col.th && y < a.sm.col.th && z < a.sm.col.th) {
+                const uint32_t g = a.sm.col.g;
+                const uint32_t key = (x / g) | ((y / g) << 10) | ((z / g) << 20);
+                if (key != cr0.key) {
+                  if (key == cr1.key) { const ColRun t = cr0; cr0 = cr1; cr1 = t; }
+                  else { flush_col(a, fig, cr1, patch); cr1 = cr0; cr0 = {key, 0, 0, 0, 0, 0ull}; }
+                }
+                const uint16_t* c = reinterpret_cast<const uint16_t*>(s_yuv + (k0 + i) * 6);
+                const uint32_t Y = c[0];
+                cr0.cnt += 1; cr0.sy += Y; cr0.su += c[1]; cr0.sv += c[2]; cr0.sy2 += (unsigned long long)Y * Y;
+              }
+            }
+          }
+        }
+      }
+      if (do_geo) { flush_geo(a, fig, gr0, patch); flush_geo(a, fig, gr1, patch); }
+      if (do_col) { flush_col(a, fig, cr0, patch); flush_col(a, fig, cr1, patch); }
+    }
   } else {
-    // generic path: recompute and write straight to global memory
+    // generic path: recompute and write straight to global memory (no staging, no run aggregation)
     const int64_t sscale = a.spec_orientation ? res : 1;
+    const uint32_t srcx = axis_source(P, 0), srcy = axis_source(P, 1), srcz = axis_source(P, 2);
     uint64_t run = gidx;
     for (uint32_t base = 0; base < res * res; base += 32) {
       const uint32_t i = base + lane;
@@ -541,16 +725,17 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32) unpack_kernel(const Unpack
       const uint32_t chunk_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
       uint64_t k = run + (incl - c);
       uint32_t bt = 0;
-      if (c && a.out.btype) bt = boundary_type(a, occ_f, (int32_t)x, (int32_t)y);
+      if (c && (a.out.btype || kSmooth)) bt = boundary_type(a, occ_f, (int32_t)x, (int32_t)y);
       for (uint32_t m = 0; m < c; ++m, ++k) {
-        uint32_t pt[3];
-        make_point(P, m == 0 ? n0 : n1, t, b, pt);
-        if (a.out.pos) { uint16_t* d = a.out.pos + k * 3; d[0] = (uint16_t)pt[0]; d[1] = (uint16_t)pt[1]; d[2] = (uint16_t)pt[2]; }
+        const uint32_t n = m == 0 ? n0 : n1;
+        const uint32_t X = pick(srcx, n, t, b), Yc = pick(srcy, n, t, b), Z = pick(srcz, n, t, b);
+        if (a.out.pos) { uint16_t* d = a.out.pos + k * 3; d[0] = (uint16_t)X; d[1] = (uint16_t)Yc; d[2] = (uint16_t)Z; }
+        uint32_t Y = 0, U = 0, V = 0;
         if (a.has_attr) {
           const uint64_t fm = (uint64_t)frame * 2 + m;
-          const uint32_t Y = a.in.attr_y[fm * a.in.attr_y_map_stride + (uint64_t)y * a.in.attr_pitch_y + (uint64_t)x];
+          Y = a.in.attr_y[fm * a.in.attr_y_map_stride + (uint64_t)y * a.in.attr_pitch_y + (uint64_t)x];
           const uint64_t co = fm * a.in.attr_c_map_stride + (uint64_t)(y >> 1) * a.in.attr_pitch_c + (uint64_t)(x >> 1);
-          const uint32_t U = a.in.attr_u[co], V = a.in.attr_v[co];
+          U = a.in.attr_u[co]; V = a.in.attr_v[co];
           if (a.out.yuv) { uint16_t* d = a.out.yuv + k * 3; d[0] = (uint16_t)Y; d[1] = (uint16_t)U; d[2] = (uint16_t)V; }
           if (a.out.rgb) {
             const uint32_t cc = yuv_to_rgb_packed(Y, U, V);
@@ -560,6 +745,28 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32) unpack_kernel(const Unpack
         if (a.out.part) a.out.part[k] = (uint16_t)P.local_index;
         if (a.out.pix) a.out.pix[k] = (uint32_t)x | ((uint32_t)y << 15) | (m << 30);
         if (a.out.btype) a.out.btype[k] = (uint8_t)bt;
+        if (kSmooth) {
+          if (a.sm.geo.on && X < a.sm.geo.th && Yc < a.sm.geo.th && Z < a.sm.geo.th) {
+            const uint32_t g = a.sm.geo.g, cx = X / g, cy = Yc / g, cz = Z / g;
+            const GeoRun r = {cx | (cy << 10) | (cz << 20), 1, X - cx * g, Yc - cy * g, Z - cz * g};
+            flush_geo(a, fig, r, P.local_index);
+          }
+          if (a.sm.col.on && a.has_attr && X < a.sm.col.th && Yc < a.sm.col.th && Z < a.sm.col.th) {
+            const uint32_t g = a.sm.col.g;
+            const ColRun r = {(X / g) | ((Yc / g) << 10) | ((Z / g) << 20), 1, Y, U, V, (unsigned long long)Y * Y};
+            flush_col(a, fig, r, P.local_index);
+          }
+          if (bt == 1) {
+            const uint32_t li = atomicAdd(&a.sm.blist_count[frame], 1u);
+            if (li < a.sm.blist_cap) {
+              BoundaryEntry e;
+              e.idx = (uint32_t)(k - (uint64_t)frame * a.out.cap);
+              e.pos[0] = (uint16_t)X; e.pos[1] = (uint16_t)Yc; e.pos[2] = (uint16_t)Z;
+              e.yuv[0] = (uint16_t)Y; e.yuv[1] = (uint16_t)U; e.yuv[2] = (uint16_t)V;
+              a.sm.blist[(uint64_t)frame * a.sm.blist_cap + li] = e;
+            } else atomicExch(a.err, 7);
+          }
+        }
       }
       run += chunk_total;
     }
@@ -592,23 +799,11 @@ __global__ void __launch_bounds__(256) tile_scan_kernel(const UnpackArgs a) {
     if (threadIdx.x == 255) s_carry = wbase + incl;
     __syncthreads();
   }
-  // frame_count is written by the emit kernel (last tile of the frame)
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// yuv -> rgb over finished point streams (codec.rs:88-94)
+// yuv -> rgb over a flat colour array (codec.rs:88-94)
 // ----------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) yuv_to_rgb_kernel(const uint16_t* __restrict__ yuv, uint8_t* __restrict__ rgb,
-                                                         const uint32_t* __restrict__ frame_count, uint64_t cap) {
-  const uint32_t f = blockIdx.y;
-  const uint32_t n = frame_count[f];
-  const uint16_t* src = yuv + (uint64_t)f * cap * 3;
-  uint8_t* dst = rgb + (uint64_t)f * cap * 3;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t c = yuv_to_rgb_packed(src[3 * (uint64_t)i], src[3 * (uint64_t)i + 1], src[3 * (uint64_t)i + 2]);
-    dst[3 * (uint64_t)i] = (uint8_t)c; dst[3 * (uint64_t)i + 1] = (uint8_t)(c >> 8); dst[3 * (uint64_t)i + 2] = (uint8_t)(c >> 16);
-  }
-}
 __global__ void __launch_bounds__(256) yuv_to_rgb_flat_kernel(const uint16_t* __restrict__ yuv, uint8_t* __restrict__ rgb,
                                                               uint64_t n) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -618,117 +813,11 @@ __global__ void __launch_bounds__(256) yuv_to_rgb_flat_kernel(const uint16_t* __
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// K6 / K7: sparse voxel-cell tables (own integer spec; see DESIGN.md "Smoothing specification")
+// K6 / K7: filter the type-1 boundary points against the trilinear blend of the 8 surrounding cell means
 // ----------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t cell_slot0(uint32_t key, const GridArgs& G) {
-  if (G.identity_hash) {
-    const uint64_t cx = key & 1023u, cy = (key >> 10) & 1023u, cz = key >> 20;
-    return cx + (uint64_t)G.w * (cy + (uint64_t)G.w * cz);
-  }
-  return (((uint64_t)key * 0x9E3779B97F4A7C15ull) >> 24) & (G.table_slots - 1);
-}
-
-template <typename Cell>
-__device__ __forceinline__ Cell* cell_insert(Cell* tab, uint32_t key, const GridArgs& G, uint32_t frame) {
-  uint64_t i = cell_slot0(key, G);
-  for (uint64_t probe = 0; probe < G.table_slots; ++probe) {
-    const uint32_t prev = atomicCAS(&tab[i].key, kCellEmpty, key);
-    if (prev == kCellEmpty) {
-      const uint32_t t = atomicAdd(&G.touched_count[frame], 1u);
-      if (t < G.touched_cap) G.touched[(uint64_t)frame * G.touched_cap + t] = (uint32_t)i;
-      else atomicExch(G.err, 11);
-      return &tab[i];
-    }
-    if (prev == key) return &tab[i];
-    i = (i + 1) & (G.table_slots - 1);
-  }
-  atomicExch(G.err, 11);
-  return nullptr;
-}
-template <typename Cell>
-__device__ __forceinline__ const Cell* cell_find(const Cell* tab, uint32_t key, const GridArgs& G) {
-  uint64_t i = cell_slot0(key, G);
-  for (uint64_t probe = 0; probe < G.table_slots; ++probe) {
-    const uint32_t k = tab[i].key;
-    if (k == key) return &tab[i];
-    if (k == kCellEmpty) return nullptr;
-    i = (i + 1) & (G.table_slots - 1);
-  }
-  return nullptr;
-}
-
-__device__ __forceinline__ bool in_grid(const GridArgs& G, uint32_t x, uint32_t y, uint32_t z) {
-  return x < G.th && y < G.th && z < G.th;
-}
-
-template <bool kColor>
-__global__ void __launch_bounds__(256) grid_accumulate_kernel(const GridArgs G) {
-  const uint32_t f = blockIdx.y;
-  const uint32_t n = G.frame_count[f];
-  const uint16_t* pos = G.pos + (uint64_t)f * G.cap * 3;
-  const uint16_t* yuv = kColor ? G.yuv + (uint64_t)f * G.cap * 3 : nullptr;
-  const uint16_t* part = G.part + (uint64_t)f * G.cap;
-  const uint32_t lane = lane_id();
-  const uint32_t n_round = (n + 31u) & ~31u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-    uint32_t key = kCellEmpty, rx = 0, ry = 0, rz = 0, pa = 0, Y = 0, U = 0, V = 0;
-    if (i < n) {
-      const uint32_t x = pos[3 * (uint64_t)i], y = pos[3 * (uint64_t)i + 1], z = pos[3 * (uint64_t)i + 2];
-      if (in_grid(G, x, y, z)) {
-        const uint32_t cx = x / G.g, cy = y / G.g, cz = z / G.g;
-        key = cx | (cy << 10) | (cz << 20);
-        rx = x - cx * G.g; ry = y - cy * G.g; rz = z - cz * G.g;
-        pa = part[i];
-        if (kColor) { Y = yuv[3 * (uint64_t)i]; U = yuv[3 * (uint64_t)i + 1]; V = yuv[3 * (uint64_t)i + 2]; }
-      }
-    }
-    // warp aggregation: one set of atomics per distinct cell in the warp (points arrive in patch-raster order, so
-    // neighbouring lanes mostly share a cell)
-    uint32_t remaining = __ballot_sync(0xFFFFFFFFu, key != kCellEmpty);
-    while (remaining) {
-      const uint32_t leader = __ffs(remaining) - 1;
-      const uint32_t k = __shfl_sync(0xFFFFFFFFu, key, leader);
-      const bool in = key == k;
-      const uint32_t grp = __ballot_sync(0xFFFFFFFFu, in);
-      const uint32_t cnt = __popc(grp);
-      const uint32_t pmin = __reduce_min_sync(0xFFFFFFFFu, in ? pa : 0xFFFFFFFFu);
-      const uint32_t pmax = __reduce_max_sync(0xFFFFFFFFu, in ? pa : 0u);
-      if (!kColor) {
-        const uint32_t sx = __reduce_add_sync(0xFFFFFFFFu, in ? rx : 0u);
-        const uint32_t sy = __reduce_add_sync(0xFFFFFFFFu, in ? ry : 0u);
-        const uint32_t sz = __reduce_add_sync(0xFFFFFFFFu, in ? rz : 0u);
-        if (lane == leader) {
-          GeoCell* c = cell_insert(reinterpret_cast<GeoCell*>(G.table) + (uint64_t)f * G.table_slots, k, G, f);
-          if (c) {
-            atomicAdd(&c->count, cnt); atomicMin(&c->pmin, pmin); atomicMax(&c->pmax, pmax);
-            atomicAdd(&c->sx, sx); atomicAdd(&c->sy, sy); atomicAdd(&c->sz, sz);
-          }
-        }
-      } else {
-        const uint32_t sY = __reduce_add_sync(0xFFFFFFFFu, in ? Y : 0u);
-        const uint32_t sU = __reduce_add_sync(0xFFFFFFFFu, in ? U : 0u);
-        const uint32_t sV = __reduce_add_sync(0xFFFFFFFFu, in ? V : 0u);
-        const uint32_t y2 = Y * Y;                                           // < 2^32
-        const uint32_t s2lo = __reduce_add_sync(0xFFFFFFFFu, in ? (y2 & 0xFFFFu) : 0u);
-        const uint32_t s2hi = __reduce_add_sync(0xFFFFFFFFu, in ? (y2 >> 16) : 0u);
-        if (lane == leader) {
-          ColCell* c = cell_insert(reinterpret_cast<ColCell*>(G.table) + (uint64_t)f * G.table_slots, k, G, f);
-          if (c) {
-            atomicAdd(&c->count, cnt); atomicMin(&c->pmin, pmin); atomicMax(&c->pmax, pmax);
-            atomicAdd(&c->sy, (unsigned long long)sY); atomicAdd(&c->su, (unsigned long long)sU);
-            atomicAdd(&c->sv, (unsigned long long)sV);
-            atomicAdd(&c->sy2, (unsigned long long)s2lo + ((unsigned long long)s2hi << 16));
-          }
-        }
-      }
-      remaining &= ~grp;
-    }
-  }
-}
-
-struct Nbhd { uint32_t key[8]; bool valid[8]; unsigned long long wgt[8]; unsigned long long w3; };
-__device__ __forceinline__ bool neighbourhood(const GridArgs& G, const uint32_t p[3], Nbhd& N) {
-  if (!in_grid(G, p[0], p[1], p[2])) return false;
+struct Nbhd { uint32_t key[8]; unsigned long long wgt[8]; unsigned long long w3; };
+__device__ __forceinline__ bool neighbourhood(const GridDesc& G, const uint32_t p[3], Nbhd& N) {
+  if (!(p[0] < G.th && p[1] < G.th && p[2] < G.th)) return false;
 #pragma unroll
   for (int a = 0; a < 3; ++a)
     if (p[a] < G.disth || p[a] + G.disth >= G.th) return false;
@@ -745,146 +834,158 @@ __device__ __forceinline__ bool neighbourhood(const GridArgs& G, const uint32_t 
   for (int k = 0; k < 8; ++k) {
     const int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
     const int32_t cx = s[0] + dx, cy = s[1] + dy, cz = s[2] + dz;
-    N.valid[k] = cx >= 0 && cy >= 0 && cz >= 0 && (uint32_t)cx < G.w && (uint32_t)cy < G.w && (uint32_t)cz < G.w;
-    N.key[k] = N.valid[k] ? ((uint32_t)cx | ((uint32_t)cy << 10) | ((uint32_t)cz << 20)) : kCellEmpty;
+    const bool valid = cx >= 0 && cy >= 0 && cz >= 0 && (uint32_t)cx < G.w && (uint32_t)cy < G.w && (uint32_t)cz < G.w;
+    N.key[k] = valid ? ((uint32_t)cx | ((uint32_t)cy << 10) | ((uint32_t)cz << 20)) : kCellEmpty;
     N.wgt[k] = (dx ? wa[0] : g2 - wa[0]) * (dy ? wa[1] : g2 - wa[1]) * (dz ? wa[2] : g2 - wa[2]);
   }
   return true;
 }
 
-__global__ void __launch_bounds__(256) geo_filter_kernel(const GridArgs G) {
-  const uint32_t f = blockIdx.y;
-  const uint32_t n = G.frame_count[f];
-  uint16_t* pos = G.pos + (uint64_t)f * G.cap * 3;
-  const uint8_t* bt = G.btype + (uint64_t)f * G.cap;
-  const GeoCell* tab = reinterpret_cast<const GeoCell*>(G.table) + (uint64_t)f * G.table_slots;
-  uint32_t moved = 0;
+__global__ void __launch_bounds__(256) smooth_filter_kernel(const UnpackArgs a) {
+  const uint32_t fig = blockIdx.y;
+  const uint32_t f = a.sm.group_first_frame + fig;
+  const uint32_t n = min((uint64_t)a.sm.blist_count[f], a.sm.blist_cap);
+  const BoundaryEntry* L = a.sm.blist + (uint64_t)f * a.sm.blist_cap;
+  uint32_t moved = 0, recol = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (bt[i] != 1) continue;
-    uint32_t p[3] = {pos[3 * (uint64_t)i], pos[3 * (uint64_t)i + 1], pos[3 * (uint64_t)i + 2]};
+    const uint4 raw = *reinterpret_cast<const uint4*>(&L[i]);
+    const BoundaryEntry e = *reinterpret_cast<const BoundaryEntry*>(&raw);
+    const uint32_t p[3] = {e.pos[0], e.pos[1], e.pos[2]};
+    const uint64_t gi = (uint64_t)f * a.out.cap + e.idx;
     Nbhd N;
-    if (!neighbourhood(G, p, N)) continue;
-    unsigned long long C[3] = {0, 0, 0}, cntw = 0;
-    bool other = false;
+    // ---- geometry (K6) ----
+    if (a.sm.geo.on && neighbourhood(a.sm.geo, p, N)) {
+      const GridDesc& G = a.sm.geo;
+      unsigned long long C[3] = {0, 0, 0}, cntw = 0;
+      bool other = false;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const GeoCell* c = N.valid[j] ? cell_find(tab, N.key[j], G) : nullptr;
-      uint32_t cnt = 0, s[3] = {0, 0, 0}, o[3] = {0, 0, 0};
-      if (c) {
-        cnt = c->count; s[0] = c->sx; s[1] = c->sy; s[2] = c->sz;
-        if (cnt > 0 && c->pmin != c->pmax) other = true;
-        o[0] = (N.key[j] & 1023u) * G.g; o[1] = ((N.key[j] >> 10) & 1023u) * G.g; o[2] = (N.key[j] >> 20) * G.g;
-      }
+      for (int j = 0; j < 8; ++j) {
+        const GeoCell* c = N.key[j] != kCellEmpty ? cell_find<GeoCell>(G, fig, N.key[j]) : nullptr;
+        uint32_t cnt = 0, s[3] = {0, 0, 0}, o[3] = {0, 0, 0};
+        if (c) {
+          cnt = c->count; s[0] = c->sx; s[1] = c->sy; s[2] = c->sz;
+          if (cnt > 0 && c->pmin != c->pmax) other = true;
+          o[0] = (N.key[j] & 1023u) * G.g; o[1] = ((N.key[j] >> 10) & 1023u) * G.g; o[2] = (N.key[j] >> 20) * G.g;
+        }
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        unsigned long long m = 256ull * p[a];
-        if (cnt > 0) m = 256ull * o[a] + (256ull * s[a] + cnt / 2) / cnt;      // cell mean, Q8
-        C[a] += N.wgt[j] * m;
+        for (int ax = 0; ax < 3; ++ax) {
+          unsigned long long m = 256ull * p[ax];
+          if (cnt > 0) m = 256ull * o[ax] + (256ull * s[ax] + cnt / 2) / cnt;      // cell mean, Q8
+          C[ax] += N.wgt[j] * m;
+        }
+        cntw += N.wgt[j] * cnt;
       }
-      cntw += N.wgt[j] * cnt;
+      const unsigned long long count = cntw / N.w3;
+      if (other && count > 0) {
+        unsigned long long c4[3], D2 = 0;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+          c4[ax] = (C[ax] + N.w3 / 2) / N.w3;
+          const long long d = (long long)(256ull * p[ax]) - (long long)c4[ax];
+          D2 += (unsigned long long)(d * d);
+        }
+        const unsigned long long m = a.sm.thr_geo > count ? a.sm.thr_geo : count;
+        const unsigned __int128 lhs = (unsigned __int128)2 * count * D2 + 65536u;
+        const unsigned __int128 rhs = (unsigned __int128)262144u * m;
+        if (lhs >= rhs) {
+          bool changed = false;
+          uint16_t q[3];
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            unsigned long long r = (c4[ax] + 128) >> 8;
+            if (r > 65535) r = 65535;
+            q[ax] = (uint16_t)r;
+            changed |= q[ax] != p[ax];
+          }
+          if (changed) {
+            uint16_t* d = a.out.pos + gi * 3;
+            d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
+            moved += 1;
+          }
+        }
+      }
     }
-    if (!other) continue;
-    const unsigned long long count = cntw / N.w3;
-    if (count == 0) continue;
-    unsigned long long c4[3], D2 = 0;
+    // ---- colour (K7), on the same pre-smoothing position ----
+    if (a.sm.col.on && a.has_attr && neighbourhood(a.sm.col, p, N)) {
+      const GridDesc& G = a.sm.col;
+      const uint32_t col[3] = {e.yuv[0], e.yuv[1], e.yuv[2]};
+      unsigned long long C[3] = {0, 0, 0};
+      bool other = false;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      c4[a] = (C[a] + N.w3 / 2) / N.w3;
-      const long long d = (long long)(256ull * p[a]) - (long long)c4[a];
-      D2 += (unsigned long long)(d * d);
-    }
-    const unsigned long long m = G.thr_a > count ? G.thr_a : count;
-    const unsigned __int128 lhs = (unsigned __int128)2 * count * D2 + 65536u;
-    const unsigned __int128 rhs = (unsigned __int128)262144u * m;
-    if (lhs >= rhs) {
-      bool changed = false;
+      for (int j = 0; j < 8; ++j) {
+        const ColCell* c = N.key[j] != kCellEmpty ? cell_find<ColCell>(G, fig, N.key[j]) : nullptr;
+        bool usable = false;
+        unsigned long long mean[3] = {0, 0, 0};
+        if (c && c->count > 0) {
+          const unsigned long long cnt = c->count;
+          if (c->pmin != c->pmax) other = true;
+          usable = true;
+          const unsigned long long s[3] = {c->sy, c->su, c->sv};
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        unsigned long long r = (c4[a] + 128) >> 8;
-        if (r > 65535) r = 65535;
-        changed |= (uint32_t)r != p[a];
-        pos[3 * (uint64_t)i + a] = (uint16_t)r;
+          for (int ax = 0; ax < 3; ++ax) mean[ax] = (256ull * s[ax] + cnt / 2) / cnt;
+          const unsigned __int128 num = (unsigned __int128)cnt * c->sy2 - (unsigned __int128)s[0] * s[0];
+          const unsigned long long tv = (unsigned long long)a.sm.thr_col_var * cnt;
+          const unsigned __int128 lim = (unsigned __int128)tv * tv;
+          if (num > lim) usable = false;
+          const long long dy = (long long)mean[0] - (long long)(256ull * col[0]);
+          if ((unsigned long long)(dy < 0 ? -dy : dy) > 256ull * a.sm.thr_col_diff) usable = false;
+        }
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) C[ax] += N.wgt[j] * (usable ? mean[ax] : 256ull * col[ax]);
       }
-      moved += changed ? 1u : 0u;
+      if (other) {
+        uint32_t q[3]; unsigned long long dist = 0;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+          const unsigned long long c4 = (C[ax] + N.w3 / 2) / N.w3;
+          unsigned long long r = (c4 + 128) >> 8;
+          if (r > 65535) r = 65535;
+          q[ax] = (uint32_t)r;
+          const long long d = (long long)q[ax] - (long long)col[ax];
+          dist += (unsigned long long)(d < 0 ? -d : d) * (ax == 0 ? 10u : 1u);
+        }
+        if (dist >= a.sm.thr_col_smooth && dist > 0) {
+          const uint32_t c = yuv_to_rgb_packed(q[0], q[1], q[2]);
+          uint8_t* d = a.out.rgb + gi * 3;
+          d[0] = (uint8_t)c; d[1] = (uint8_t)(c >> 8); d[2] = (uint8_t)(c >> 16);
+          if (a.out.yuv) { uint16_t* y = a.out.yuv + gi * 3; y[0] = (uint16_t)q[0]; y[1] = (uint16_t)q[1]; y[2] = (uint16_t)q[2]; }
+          recol += 1;
+        }
+      }
     }
   }
   moved = __reduce_add_sync(0xFFFFFFFFu, moved);
-  if (lane_id() == 0 && moved) atomicAdd(&G.changed[f], (unsigned long long)moved);
-}
-
-__global__ void __launch_bounds__(256) col_filter_kernel(const GridArgs G) {
-  const uint32_t f = blockIdx.y;
-  const uint32_t n = G.frame_count[f];
-  const uint16_t* pos = G.pos + (uint64_t)f * G.cap * 3;
-  uint16_t* yuv = G.yuv + (uint64_t)f * G.cap * 3;
-  const uint8_t* bt = G.btype + (uint64_t)f * G.cap;
-  const ColCell* tab = reinterpret_cast<const ColCell*>(G.table) + (uint64_t)f * G.table_slots;
-  uint32_t recol = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (bt[i] != 1) continue;
-    const uint32_t p[3] = {pos[3 * (uint64_t)i], pos[3 * (uint64_t)i + 1], pos[3 * (uint64_t)i + 2]};
-    Nbhd N;
-    if (!neighbourhood(G, p, N)) continue;
-    const uint32_t col[3] = {yuv[3 * (uint64_t)i], yuv[3 * (uint64_t)i + 1], yuv[3 * (uint64_t)i + 2]};
-    unsigned long long C[3] = {0, 0, 0};
-    bool other = false;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const ColCell* c = N.valid[j] ? cell_find(tab, N.key[j], G) : nullptr;
-      bool usable = false;
-      unsigned long long mean[3] = {0, 0, 0};
-      if (c && c->count > 0) {
-        const unsigned long long cnt = c->count;
-        if (c->pmin != c->pmax) other = true;
-        usable = true;
-        const unsigned long long s[3] = {c->sy, c->su, c->sv};
-#pragma unroll
-        for (int a = 0; a < 3; ++a) mean[a] = (256ull * s[a] + cnt / 2) / cnt;
-        const unsigned __int128 num = (unsigned __int128)cnt * c->sy2 - (unsigned __int128)s[0] * s[0];
-        const unsigned long long tv = (unsigned long long)G.thr_c * cnt;
-        const unsigned __int128 lim = (unsigned __int128)tv * tv;
-        if (num > lim) usable = false;
-        const long long dy = (long long)mean[0] - (long long)(256ull * col[0]);
-        if ((unsigned long long)(dy < 0 ? -dy : dy) > 256ull * G.thr_b) usable = false;
-      }
-#pragma unroll
-      for (int a = 0; a < 3; ++a) C[a] += N.wgt[j] * (usable ? mean[a] : 256ull * col[a]);
-    }
-    if (!other) continue;
-    uint32_t q[3]; unsigned long long dist = 0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const unsigned long long c4 = (C[a] + N.w3 / 2) / N.w3;
-      unsigned long long r = (c4 + 128) >> 8;
-      if (r > 65535) r = 65535;
-      q[a] = (uint32_t)r;
-      const long long d = (long long)q[a] - (long long)col[a];
-      dist += (unsigned long long)(d < 0 ? -d : d) * (a == 0 ? 10u : 1u);
-    }
-    if (dist >= G.thr_a && dist > 0) {
-      yuv[3 * (uint64_t)i] = (uint16_t)q[0]; yuv[3 * (uint64_t)i + 1] = (uint16_t)q[1]; yuv[3 * (uint64_t)i + 2] = (uint16_t)q[2];
-      recol += 1;
-    }
-  }
   recol = __reduce_add_sync(0xFFFFFFFFu, recol);
-  if (lane_id() == 0 && recol) atomicAdd(&G.changed[f], (unsigned long long)recol);
+  if (lane_id() == 0) {
+    if (moved) atomicAdd(&a.sm.changed[f], (unsigned long long)moved);
+    if (recol) atomicAdd(&a.sm.changed[a.n_frames + f], (unsigned long long)recol);
+  }
 }
 
 template <typename Cell>
-__global__ void __launch_bounds__(256) grid_clear_kernel(const GridArgs G) {
-  const uint32_t f = blockIdx.y;
-  const uint32_t n = min((uint64_t)G.touched_count[f], G.touched_cap);
-  Cell* tab = reinterpret_cast<Cell*>(G.table) + (uint64_t)f * G.table_slots;
+__device__ __forceinline__ void clear_cells(const GridDesc& G, uint32_t fig, uint64_t touched_cap) {
+  if (!G.on) return;
+  const uint32_t n = min((uint64_t)G.touched_count[fig], touched_cap);
+  Cell* tab = reinterpret_cast<Cell*>(G.table) + (uint64_t)fig * G.slots;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     Cell z;
     memset(&z, 0, sizeof z);
     z.key = kCellEmpty; z.pmin = 0xFFFFFFFFu;
-    tab[G.touched[(uint64_t)f * G.touched_cap + i]] = z;
+    tab[G.touched[(uint64_t)fig * touched_cap + i]] = z;
   }
 }
-__global__ void grid_reset_counts_kernel(const GridArgs G) {
-  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f < G.n_frames) G.touched_count[f] = 0;
+__global__ void __launch_bounds__(256) smooth_clear_kernel(const UnpackArgs a) {
+  const uint32_t fig = blockIdx.y;
+  clear_cells<GeoCell>(a.sm.geo, fig, a.sm.touched_cap);
+  clear_cells<ColCell>(a.sm.col, fig, a.sm.touched_cap);
+}
+__global__ void smooth_reset_kernel(const UnpackArgs a) {   // after the clear: counters back to zero for the next group
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.sm.group_frames) {
+    if (a.sm.geo.on) a.sm.geo.touched_count[i] = 0;
+    if (a.sm.col.on) a.sm.col.touched_count[i] = 0;
+    a.sm.blist_count[a.sm.group_first_frame + i] = 0;
+  }
 }
 template <typename Cell>
 __global__ void __launch_bounds__(256) table_init_kernel(Cell* tab, uint64_t n) {
@@ -910,26 +1011,24 @@ int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream) {
   return after_launch();
 }
 
-int launch_unpack(const UnpackArgs& a, int mode, void* stream) {
-  if (a.n_tiles == 0) return 0;
-  const size_t smem = unpack_smem_bytes(a);
-  static bool attr_set[3] = {false, false, false};
-  cudaError_t e = cudaSuccess;
-  auto set = [&](const void* fn) {
-    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  };
-  if (!attr_set[mode]) {
-    if (mode == 0) e = set((const void*)unpack_kernel<0>);
-    else if (mode == 1) e = set((const void*)unpack_kernel<1>);
-    else e = set((const void*)unpack_kernel<2>);
-    if (e != cudaSuccess) return (int)e;
-    attr_set[mode] = true;
-  }
-  const cudaStream_t s = (cudaStream_t)stream;
-  if (mode == 0) unpack_kernel<0><<<a.n_tiles, kWarpsPerTile * 32, smem, s>>>(a);
-  else if (mode == 1) unpack_kernel<1><<<a.n_tiles, kWarpsPerTile * 32, 0, s>>>(a);
-  else unpack_kernel<2><<<a.n_tiles, kWarpsPerTile * 32, smem, s>>>(a);
+template <int kMode, bool kSmooth>
+static int launch_unpack_t(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute((const void*)unpack_kernel<kMode, kSmooth>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  unpack_kernel<kMode, kSmooth><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin);
   return after_launch();
+}
+
+int launch_unpack(const UnpackArgs& a, int mode, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream) {
+  if (tile_end <= tile_begin) return 0;
+  const size_t smem = mode == 1 ? 0 : unpack_smem_bytes(a);
+  const cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 1) return launch_unpack_t<1, false>(a, tile_begin, tile_end, smem, s);
+  if (smooth) return mode == 0 ? launch_unpack_t<0, true>(a, tile_begin, tile_end, smem, s)
+                               : launch_unpack_t<2, true>(a, tile_begin, tile_end, smem, s);
+  return mode == 0 ? launch_unpack_t<0, false>(a, tile_begin, tile_end, smem, s)
+                   : launch_unpack_t<2, false>(a, tile_begin, tile_end, smem, s);
 }
 
 int launch_tile_scan(const UnpackArgs& a, void* stream) {
@@ -943,48 +1042,23 @@ int launch_upsample(const UnpackArgs& a, uint8_t* occ_full, void* stream) {
   return after_launch();
 }
 
-static inline dim3 per_frame_grid(uint64_t cap, uint32_t n_frames) {
-  uint64_t bx = (cap + 255) / 256;
-  const uint64_t lim = (148ull * 8 + n_frames - 1) / (n_frames ? n_frames : 1) + 1;   // ~8 CTAs per SM over all frames
-  if (bx > lim) bx = lim;
-  if (bx < 1) bx = 1;
-  return dim3((unsigned)bx, n_frames, 1);
-}
-
-int launch_geo_smoothing(const GridArgs& G, void* stream) {
-  const cudaStream_t s = (cudaStream_t)stream;
-  const dim3 grid = per_frame_grid(G.cap, G.n_frames);
-  int e;
-  grid_reset_counts_kernel<<<(G.n_frames + 63) / 64, 64, 0, s>>>(G);
-  if ((e = after_launch())) return e;
-  grid_accumulate_kernel<false><<<grid, 256, 0, s>>>(G);
-  if ((e = after_launch())) return e;
-  geo_filter_kernel<<<grid, 256, 0, s>>>(G);
-  if ((e = after_launch())) return e;
-  grid_clear_kernel<GeoCell><<<grid, 256, 0, s>>>(G);
+int launch_smooth_filter(const UnpackArgs& a, void* stream) {
+  if (a.sm.group_frames == 0) return 0;
+  const unsigned bx = (148u * 8u + a.sm.group_frames - 1) / a.sm.group_frames;
+  smooth_filter_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
 }
 
-int launch_color_smoothing(const GridArgs& G, void* stream) {
-  const cudaStream_t s = (cudaStream_t)stream;
-  const dim3 grid = per_frame_grid(G.cap, G.n_frames);
-  int e;
-  grid_reset_counts_kernel<<<(G.n_frames + 63) / 64, 64, 0, s>>>(G);
-  if ((e = after_launch())) return e;
-  grid_accumulate_kernel<true><<<grid, 256, 0, s>>>(G);
-  if ((e = after_launch())) return e;
-  col_filter_kernel<<<grid, 256, 0, s>>>(G);
-  if ((e = after_launch())) return e;
-  grid_clear_kernel<ColCell><<<grid, 256, 0, s>>>(G);
+int launch_smooth_clear(const UnpackArgs& a, void* stream) {
+  if (a.sm.group_frames == 0) return 0;
+  const unsigned bx = (148u * 4u + a.sm.group_frames - 1) / a.sm.group_frames;
+  smooth_clear_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
+  int e = after_launch();
+  if (e) return e;
+  smooth_reset_kernel<<<(a.sm.group_frames + 63) / 64, 64, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
 }
 
-int launch_yuv_to_rgb(const uint16_t* yuv, uint8_t* rgb, const uint32_t* frame_count, uint32_t n_frames, uint64_t cap,
-                      void* stream) {
-  if (n_frames == 0) return 0;
-  yuv_to_rgb_kernel<<<per_frame_grid(cap, n_frames), 256, 0, (cudaStream_t)stream>>>(yuv, rgb, frame_count, cap);
-  return after_launch();
-}
 int launch_yuv_to_rgb_flat(const uint16_t* yuv, uint8_t* rgb, uint64_t n, void* stream) {
   if (n == 0) return 0;
   uint64_t blocks = (n + 255) / 256;

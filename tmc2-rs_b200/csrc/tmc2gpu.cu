@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -242,8 +243,10 @@ struct Batch {
 
   DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_status, d_tile_total, d_count, d_err;
   DevBuf d_pos, d_rgb, d_yuv, d_part, d_pix, d_bt, d_occ_full, d_pos_pre, d_yuv_pre;
-  DevBuf d_geotab, d_coltab, d_touched, d_touched_count, d_changed;
-  uint64_t geotab_slots = 0, coltab_slots = 0, geotab_frames = 0, coltab_frames = 0, touched_cap = 0;
+  DevBuf d_geotab, d_coltab, d_touched_geo, d_touched_col, d_touched_count, d_changed, d_blist, d_blist_count;
+  uint64_t geotab_slots = 0, coltab_slots = 0, geotab_frames = 0, coltab_frames = 0, touched_cap = 0, blist_cap = 0;
+  uint32_t group_frames = 8;          // frames per smoothing group (cell tables stay L2-resident inside a group)
+  std::vector<cudaEvent_t> ev_grp;    // 2 per group: around the unpack launch
   PinBuf h_in, h_meta, h_small, h_out;
   size_t meta_patch_off = 0, meta_slot_off = 0, meta_tf_off = 0, meta_ftb_off = 0, meta_bytes = 0;
 
@@ -256,7 +259,7 @@ struct Batch {
   std::vector<uint64_t> moved, recoloured;
   std::vector<size_t> out_pos_off, out_rgb_off;
   bool counts_ready = false, outputs_enqueued = false;
-  uint32_t launches = 0;
+  uint32_t launches = 0, n_groups = 1;
   uint64_t unpack_alg_bytes = 0;
   uint32_t frames_released = 0;
   bool busy = false;
@@ -266,7 +269,7 @@ struct Batch {
     cudaSetDevice(device);
     for (DevBuf* b : {&d_occ, &d_geo, &d_ay, &d_au, &d_av, &d_meta, &d_b2p, &d_status, &d_tile_total, &d_count, &d_err, &d_pos,
                       &d_rgb, &d_yuv, &d_part, &d_pix, &d_bt, &d_occ_full, &d_pos_pre, &d_yuv_pre, &d_geotab, &d_coltab,
-                      &d_touched, &d_touched_count, &d_changed})
+                      &d_touched_geo, &d_touched_col, &d_touched_count, &d_changed, &d_blist, &d_blist_count})
       b->release();
     for (PinBuf* b : {&h_in, &h_meta, &h_small, &h_out}) b->release();
     for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -274,6 +277,8 @@ struct Batch {
     if (ev_inputs_free) cudaEventDestroy(ev_inputs_free), ev_inputs_free = nullptr;
     for (auto e : ev_frame) cudaEventDestroy(e);
     ev_frame.clear();
+    for (auto e : ev_grp) cudaEventDestroy(e);
+    ev_grp.clear();
     if (stream) cudaStreamDestroy(stream), stream = nullptr;
     if (d2h_stream) cudaStreamDestroy(d2h_stream), d2h_stream = nullptr;
   }
@@ -363,40 +368,53 @@ struct Batch {
     CU(d_pos.ensure((size_t)F * cap * 6));
     const bool dbg = (want & WANT_DEBUG) != 0;
     if (attr) CU(d_rgb.ensure((size_t)F * cap * 3));
-    if (attr && (smoothing_col || dbg)) CU(d_yuv.ensure((size_t)F * cap * 6));
-    if (smoothing_geo || smoothing_col || dbg) {
+    if (dbg) {
+      if (attr) CU(d_yuv.ensure((size_t)F * cap * 6));
       CU(d_part.ensure((size_t)F * cap * 2));
       CU(d_bt.ensure((size_t)F * cap));
-    }
-    if (dbg) {
       CU(d_pix.ensure((size_t)F * cap * 4));
       CU(d_pos_pre.ensure((size_t)F * cap * 6));
       if (attr) CU(d_yuv_pre.ensure((size_t)F * cap * 6));
     }
     if (want & WANT_OCC_FULL) CU(d_occ_full.ensure((size_t)F * W * H));
     if (smoothing_geo || smoothing_col) {
+      if (const char* e = getenv("TMC2_SMOOTH_GROUP")) group_frames = std::max(1, atoi(e));
+      const uint32_t GF = std::min(group_frames, std::max(F, 1u));
       const uint32_t maxs = 1u << params.geometry_bitdepth_3d;
+      // boundary-point lists (one per frame) and their counters
+      if (blist_cap != cap || d_blist.cap < (size_t)F * cap * sizeof(BoundaryEntry)) {
+        CU(d_blist.ensure((size_t)F * cap * sizeof(BoundaryEntry)));
+        blist_cap = cap;
+      }
+      if (d_blist_count.cap < (size_t)F * 4) {
+        CU(d_blist_count.ensure((size_t)F * 4));
+        CU(cudaMemsetAsync(d_blist_count.p, 0, d_blist_count.cap, stream));
+      }
+      auto table_slots = [&](uint32_t g) -> uint64_t {
+        const uint64_t w = (maxs + g - 1) / g, cells = w * w * w;
+        return cells <= 2 * cap ? cells : pow2_at_least(2 * cap);   // dense (identity) when the whole grid fits
+      };
       touched_cap = cap;
-      CU(d_touched.ensure((size_t)F * touched_cap * 4));
-      CU(d_touched_count.ensure((size_t)F * 4));
+      if (d_touched_count.cap < (size_t)GF * 8) {
+        CU(d_touched_count.ensure((size_t)GF * 8));
+        CU(cudaMemsetAsync(d_touched_count.p, 0, d_touched_count.cap, stream));
+      }
       if (smoothing_geo) {
-        const uint64_t w = (maxs + params.grid_size - 1) / params.grid_size;
-        const uint64_t cells = w * w * w;
-        const uint64_t slots = cells <= 2 * cap ? cells : pow2_at_least(2 * cap);
-        if (slots != geotab_slots || F > geotab_frames) {
-          CU(d_geotab.ensure((size_t)F * slots * sizeof(GeoCell)));
-          geotab_slots = slots; geotab_frames = F;
-          KL(launch_table_init(d_geotab.p, (uint64_t)F * slots, 0, stream));
+        const uint64_t slots = table_slots(params.grid_size);
+        if (slots != geotab_slots || GF > geotab_frames) {
+          CU(d_geotab.ensure((size_t)GF * slots * sizeof(GeoCell)));
+          CU(d_touched_geo.ensure((size_t)GF * touched_cap * 4));
+          geotab_slots = slots; geotab_frames = GF;
+          KL(launch_table_init(d_geotab.p, (uint64_t)GF * slots, 0, stream));
         }
       }
       if (smoothing_col) {
-        const uint64_t w = (maxs + params.cgrid_size - 1) / params.cgrid_size;
-        const uint64_t cells = w * w * w;
-        const uint64_t slots = cells <= 2 * cap ? cells : pow2_at_least(2 * cap);
-        if (slots != coltab_slots || F > coltab_frames) {
-          CU(d_coltab.ensure((size_t)F * slots * sizeof(ColCell)));
-          coltab_slots = slots; coltab_frames = F;
-          KL(launch_table_init(d_coltab.p, (uint64_t)F * slots, 1, stream));
+        const uint64_t slots = table_slots(params.cgrid_size);
+        if (slots != coltab_slots || GF > coltab_frames) {
+          CU(d_coltab.ensure((size_t)GF * slots * sizeof(ColCell)));
+          CU(d_touched_col.ensure((size_t)GF * touched_cap * 4));
+          coltab_slots = slots; coltab_frames = GF;
+          KL(launch_table_init(d_coltab.p, (uint64_t)GF * slots, 1, stream));
         }
       }
     }
@@ -532,26 +550,51 @@ struct Batch {
     const bool smooth = smoothing_geo || smoothing_col;
     a.out.cap = cap;
     a.out.pos = d_pos.as<uint16_t>();
-    a.out.rgb = (a.has_attr && !smoothing_col) ? d_rgb.as<uint8_t>() : nullptr;   // with colour smoothing RGB comes last
-    a.out.yuv = (a.has_attr && (smoothing_col || dbg)) ? d_yuv.as<uint16_t>() : nullptr;
-    a.out.part = (smooth || dbg) ? d_part.as<uint16_t>() : nullptr;
-    a.out.btype = (smooth || dbg) ? d_bt.as<uint8_t>() : nullptr;
+    a.out.rgb = a.has_attr ? d_rgb.as<uint8_t>() : nullptr;     // pre-smoothing colours; the filter patches recoloured points
+    a.out.yuv = (a.has_attr && dbg) ? d_yuv.as<uint16_t>() : nullptr;
+    a.out.part = dbg ? d_part.as<uint16_t>() : nullptr;
+    a.out.btype = dbg ? d_bt.as<uint8_t>() : nullptr;
     a.out.pix = dbg ? d_pix.as<uint32_t>() : nullptr;
-    a.want_btype = a.out.btype != nullptr;
-    // shared-memory staging layout of one warp (each stream gets 16 bytes of phase slack)
+    a.want_btype = a.out.btype != nullptr || smooth;
+    // shared-memory layout of one warp: scan scratch, then one staging area per stream (16 bytes of phase slack each)
     uint32_t off = 0;
-    auto place = [&](bool on, uint32_t bytes_per_point) {
+    auto place = [&](bool on, uint32_t bytes) {
       const uint32_t o = off;
-      if (on) off += round_up(kSlotPoints * bytes_per_point + 16, 16);
+      if (on) off += round_up(bytes, 16);
       return o;
     };
-    a.off_pos = place(true, 6);
-    a.off_rgb = place(a.out.rgb != nullptr, 3);
-    a.off_yuv = place(a.out.yuv != nullptr, 6);
-    a.off_part = place(a.out.part != nullptr, 2);
-    a.off_pix = place(a.out.pix != nullptr, 4);
-    a.off_bt = place(a.out.btype != nullptr, 1);
-    a.warp_bytes = std::max(off, 768u);
+    a.off_scan = place(true, 768);
+    a.off_pos = place(true, kSlotPoints * 6 + 16);
+    a.off_rgb = place(a.out.rgb != nullptr, kSlotPoints * 3 + 16);
+    a.off_yuv = place(a.has_attr && (a.out.yuv != nullptr || smooth), kSlotPoints * 6 + 16);
+    a.off_part = place(a.out.part != nullptr, kSlotPoints * 2 + 16);
+    a.off_pix = place(a.out.pix != nullptr, kSlotPoints * 4 + 16);
+    a.off_bt = place(a.out.btype != nullptr || smooth, kSlotPoints + 16);
+    a.warp_bytes = off;
+    if (smooth) {
+      const uint32_t maxs = 1u << params.geometry_bitdepth_3d;
+      auto grid = [&](GridDesc& G, bool on, uint32_t g, void* table, uint64_t slots, uint32_t* touched, uint32_t* tcount) {
+        G.on = on ? 1 : 0;
+        if (!on) return;
+        G.g = g; G.w = (maxs + g - 1) / g; G.disth = std::max(g / 2, 1u); G.th = g * G.w;
+        G.slots = slots; G.table = table;
+        G.identity = (uint64_t)G.w * G.w * G.w <= slots ? 1 : 0;
+        G.touched = touched; G.touched_count = tcount;
+      };
+      const uint32_t GF = std::min(group_frames, std::max(F, 1u));
+      grid(a.sm.geo, smoothing_geo, params.grid_size, d_geotab.p, geotab_slots, d_touched_geo.as<uint32_t>(),
+           d_touched_count.as<uint32_t>());
+      grid(a.sm.col, smoothing_col, params.cgrid_size, d_coltab.p, coltab_slots, d_touched_col.as<uint32_t>(),
+           d_touched_count.as<uint32_t>() + GF);
+      a.sm.touched_cap = touched_cap;
+      a.sm.blist = d_blist.as<BoundaryEntry>(); a.sm.blist_count = d_blist_count.as<uint32_t>(); a.sm.blist_cap = blist_cap;
+      const uint32_t sc = params.attribute_bitdepth > 8 ? (1u << (params.attribute_bitdepth - 8)) : 1u;
+      a.sm.thr_geo = params.threshold_smoothing;
+      a.sm.thr_col_smooth = params.threshold_color_smoothing * sc;
+      a.sm.thr_col_diff = params.threshold_color_difference * sc;
+      a.sm.thr_col_var = params.threshold_color_variation * sc;
+      a.sm.changed = d_changed.as<unsigned long long>();
+    }
     return a;
   }
 
@@ -561,10 +604,8 @@ struct Batch {
     if (params.attribute_count) b += (uint64_t)F * 2ull * ((uint64_t)W * H + 2ull * (W / 2) * (H / 2)) * 2;
     uint64_t per_point = 6;
     const bool dbg = (want & WANT_DEBUG) != 0;
-    if (params.attribute_count && !smoothing_col) per_point += 3;
-    if (params.attribute_count && (smoothing_col || dbg)) per_point += 6;
-    if (smoothing_geo || smoothing_col || dbg) per_point += 3;
-    if (dbg) per_point += 4;
+    if (params.attribute_count) per_point += 3;
+    if (dbg) per_point += (params.attribute_count ? 6 : 0) + 2 + 1 + 4;
     return b + per_point * total_points;
   }
 
@@ -580,54 +621,49 @@ struct Batch {
     CU(cudaMemsetAsync(d_count.p, 0, std::max<size_t>((size_t)F * 4, 4), s));
     KL(launch_block_to_patch(a, n_slots, s));
     CU(cudaEventRecord(ev[1], s));
-    if (two_pass) {
-      KL(launch_unpack(a, 1, s));
+    const bool smooth = smoothing_geo || smoothing_col;
+    const bool dbg = (want & WANT_DEBUG) != 0;
+    CU(cudaMemsetAsync(d_changed.p, 0, std::max<size_t>((size_t)F * 16, 16), s));
+    if (two_pass) {   // debug: the counts of every frame first, one scan, then the emit launches
+      KL(launch_unpack(a, 1, false, 0, n_tiles, s));
       KL(launch_tile_scan(a, s));
-      KL(launch_unpack(a, 2, s));
+    }
+    const int emit_mode = two_pass ? 2 : 0;
+    if (!smooth) {
+      while (ev_grp.size() < 2) { cudaEvent_t e; CU(cudaEventCreate(&e)); ev_grp.push_back(e); }
+      n_groups = 1;
+      CU(cudaEventRecord(ev_grp[0], s));
+      KL(launch_unpack(a, emit_mode, false, 0, n_tiles, s));
+      CU(cudaEventRecord(ev_grp[1], s));
     } else {
-      KL(launch_unpack(a, 0, s));
+      // frame groups: unpack (+ cell statistics + boundary lists) -> filter -> clear, tables stay hot in L2
+      const uint32_t GF = std::min(group_frames, std::max(F, 1u));
+      n_groups = (F + GF - 1) / GF;
+      while (ev_grp.size() < 2 * (size_t)n_groups) { cudaEvent_t e; CU(cudaEventCreate(&e)); ev_grp.push_back(e); }
+      for (uint32_t gi = 0; gi < n_groups; ++gi) {
+        const uint32_t f0 = gi * GF, f1 = std::min(F, f0 + GF);
+        a.sm.group_first_frame = f0; a.sm.group_frames = f1 - f0;
+        CU(cudaEventRecord(ev_grp[2 * gi], s));
+        KL(launch_unpack(a, emit_mode, true, h_ftb[f0], h_ftb[f1], s));
+        CU(cudaEventRecord(ev_grp[2 * gi + 1], s));
+        if (dbg) {
+          CU(cudaMemcpyAsync(d_pos_pre.as<uint8_t>() + (size_t)f0 * cap * 6, d_pos.as<uint8_t>() + (size_t)f0 * cap * 6,
+                             (size_t)(f1 - f0) * cap * 6, cudaMemcpyDeviceToDevice, s));
+          if (a.out.yuv)
+            CU(cudaMemcpyAsync(d_yuv_pre.as<uint8_t>() + (size_t)f0 * cap * 6, d_yuv.as<uint8_t>() + (size_t)f0 * cap * 6,
+                               (size_t)(f1 - f0) * cap * 6, cudaMemcpyDeviceToDevice, s));
+        }
+        KL(launch_smooth_filter(a, s));
+        KL(launch_smooth_clear(a, s));
+      }
     }
     CU(cudaEventRecord(ev[2], s));
     if (want & WANT_OCC_FULL) KL(launch_upsample(a, d_occ_full.as<uint8_t>(), s));
-    const bool dbg = (want & WANT_DEBUG) != 0;
-    if (dbg) {
+    if (dbg && !smooth) {
       CU(cudaMemcpyAsync(d_pos_pre.p, d_pos.p, (size_t)F * cap * 6, cudaMemcpyDeviceToDevice, s));
       if (a.out.yuv) CU(cudaMemcpyAsync(d_yuv_pre.p, d_yuv.p, (size_t)F * cap * 6, cudaMemcpyDeviceToDevice, s));
     }
-    CU(cudaMemsetAsync(d_changed.p, 0, std::max<size_t>((size_t)F * 16, 16), s));
-    if (smoothing_geo || smoothing_col) {
-      const uint32_t maxs = 1u << params.geometry_bitdepth_3d;
-      GridArgs G{};
-      G.n_frames = F; G.cap = cap; G.frame_count = d_count.as<uint32_t>();
-      G.pos = d_pos.as<uint16_t>(); G.yuv = d_yuv.as<uint16_t>(); G.part = d_part.as<uint16_t>(); G.btype = d_bt.as<uint8_t>();
-      G.touched = d_touched.as<uint32_t>(); G.touched_count = d_touched_count.as<uint32_t>(); G.touched_cap = touched_cap;
-      G.err = d_err.as<int>();
-      if (smoothing_geo) {
-        G.g = params.grid_size; G.w = (maxs + G.g - 1) / G.g; G.disth = std::max(G.g / 2, 1u); G.th = G.g * G.w;
-        G.table = d_geotab.p; G.table_slots = geotab_slots;
-        G.identity_hash = (uint64_t)G.w * G.w * G.w <= geotab_slots ? 1 : 0;
-        G.thr_a = params.threshold_smoothing;
-        G.changed = d_changed.as<unsigned long long>();
-        KL(launch_geo_smoothing(G, s));
-      }
-      CU(cudaEventRecord(ev[3], s));
-      if (smoothing_col) {
-        const uint32_t sc = params.attribute_bitdepth > 8 ? (1u << (params.attribute_bitdepth - 8)) : 1u;
-        G.g = params.cgrid_size; G.w = (maxs + G.g - 1) / G.g; G.disth = std::max(G.g / 2, 1u); G.th = G.g * G.w;
-        G.table = d_coltab.p; G.table_slots = coltab_slots;
-        G.identity_hash = (uint64_t)G.w * G.w * G.w <= coltab_slots ? 1 : 0;
-        G.thr_a = params.threshold_color_smoothing * sc; G.thr_b = params.threshold_color_difference * sc;
-        G.thr_c = params.threshold_color_variation * sc;
-        G.changed = d_changed.as<unsigned long long>() + F;
-        KL(launch_color_smoothing(G, s));
-      }
-      CU(cudaEventRecord(ev[4], s));
-      if (smoothing_col)
-        KL(launch_yuv_to_rgb(d_yuv.as<uint16_t>(), d_rgb.as<uint8_t>(), d_count.as<uint32_t>(), F, cap, s));
-      CU(cudaEventRecord(ev[5], s));
-    } else {
-      CU(cudaEventRecord(ev[3], s)); CU(cudaEventRecord(ev[4], s)); CU(cudaEventRecord(ev[5], s));
-    }
+    CU(cudaEventRecord(ev[3], s)); CU(cudaEventRecord(ev[4], s)); CU(cudaEventRecord(ev[5], s));
     launches = (uint32_t)kernel_launch_count_reset();
     counts_ready = false; outputs_enqueued = false;
     return TMC2_OK;
@@ -699,10 +735,16 @@ struct Batch {
     CU(cudaSetDevice(device));
     CU(cudaEventSynchronize(ev[5]));
     CU(cudaEventElapsedTime(&t.b2p, ev[0], ev[1]));
-    CU(cudaEventElapsedTime(&t.unpack, ev[1], ev[2]));
-    CU(cudaEventElapsedTime(&t.geo, ev[2], ev[3]));
-    CU(cudaEventElapsedTime(&t.col, ev[3], ev[4]));
-    CU(cudaEventElapsedTime(&t.rgb, ev[4], ev[5]));
+    float whole = 0;
+    CU(cudaEventElapsedTime(&whole, ev[1], ev[2]));
+    t.unpack = 0;
+    for (uint32_t gi = 0; gi < n_groups; ++gi) {
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, ev_grp[2 * gi], ev_grp[2 * gi + 1]));
+      t.unpack += ms;
+    }
+    t.geo = std::max(0.f, whole - t.unpack);   // filter + clear launches of all groups (both smoothing stages)
+    t.col = 0; t.rgb = 0;
     return TMC2_OK;
   }
 };
