@@ -206,7 +206,7 @@ def test_error_codes_where_the_reference_panics(gpu_ctx):
              (mk(attr_video_frames=1), abi.ERR_SHORT_VIDEO),
              (mk(params=abi.Params(**{**g.params.__dict__, "map_count_minus1": 0})), abi.ERR_MAP_COUNT),
              (mk(params=abi.Params(**{**g.params.__dict__, "enhanced_occupancy_map": True})), abi.ERR_UNSUPPORTED),
-             (mk(params=abi.Params(**{**g.params.__dict__, "occupancy_precision": 8})), abi.ERR_INVALID_ARG)]
+             (mk(params=abi.Params(**{**g.params.__dict__, "occupancy_precision": 2})), abi.ERR_INVALID_ARG)]
     for view, code in cases:
         with pytest.raises(abi.Tmc2Error) as e:
             gpu_ctx.generate_point_cloud(view, 0)

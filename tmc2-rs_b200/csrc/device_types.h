@@ -82,6 +82,7 @@ struct alignas(16) BoundaryEntry {  // one type-1 boundary point (16 B)
 struct GridDesc {               // geometry of one voxel grid
   uint32_t on;
   uint32_t g, w, disth, th;     // cell edge, cells per axis, border margin, g*w
+  uint32_t magic;               // ceil(2^32 / g): x / g == umulhi(x, magic) for x < 65536
   uint32_t identity;            // 1: slot = dense cell index (table covers the whole grid)
   uint64_t slots;               // table slots per frame-in-group (power of two unless identity)
   void*    table;               // GeoCell / ColCell [frames_in_group][slots]

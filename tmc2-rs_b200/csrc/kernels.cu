@@ -133,32 +133,57 @@ __device__ __noinline__ uint32_t yuv_to_rgb_f64(uint32_t Y, uint32_t U, uint32_t
   const double b = __dadd_rn(y, __dmul_rn(1.85563, u));
   return quant_channel_f64(r) | (quant_channel_f64(g) << 8) | (quant_channel_f64(b) << 16);
 }
-// Fixed point: N = c * 2^32 with the f64 constants rounded to 32 fractional bits (|error| <= |d|/2 units per product).
-// T = 255 c / 1023 ; A = 255 N ; floor(T) = floor(A / (1023 * 2^32)).  The f64 chain deviates from the real value by
-// < 2e-11 (< 100 units of A), the constants' rounding by <= 127.5 |d| units, so the result is certain unless A is within
-// `margin` = 128 |d| + 1024 units of a multiple of 1023 * 2^32.
+// Exact integer evaluation.  With d = chroma - 512 and t = k*d, a channel is floor(T), T = 255*(Y + t)/1023.
+// Write 255*t = I + f with I integer and 0 <= f < 1: then floor((255*Y + I + f)/1023) == floor((255*Y + I)/1023), because
+// (255*Y + I)/1023 has a fractional part <= 1022/1023 and f/1023 < 1/1023.  So the chroma-dependent work is done ONCE per
+// chroma sample (ChromaTerm: three integers), and a point costs three 32-bit multiply-shift divisions.
+// Exactness versus the reference's f64 chain: the chain deviates from the real value by < 2e-11, and I, f are computed
+// from the f64 constants rounded to 32 fractional bits (error <= 255*|d|/2^33), so floor() can only differ when f is
+// within `eps` = 255*|d|/2^33 + 2^-24 of 0 or 1 AND 255*Y + I is congruent to 0 / 1022 mod 1023.  Such chroma samples are
+// flagged (a few per million for 10-bit content) and their points take the literal f64 path.
 constexpr long long kKr = 6763714498LL;   // 1.57480 * 2^32
 constexpr long long kKgu = 804576224LL;   // 0.18733 * 2^32
 constexpr long long kKgv = 2010603040LL;  // 0.46813 * 2^32
 constexpr long long kKb = 7969870163LL;   // 1.85563 * 2^32
-__device__ __forceinline__ uint32_t quant_fixed(long long N, uint32_t margin, bool& uncertain) {
-  if (N <= 0) return 0u;                                   // c <= 0: floor(T) <= 0 -> 0 after the clamp
-  const unsigned long long A = (unsigned long long)N * 255ull;   // < 2^58
-  const uint32_t hi = (uint32_t)(A >> 32), lo = (uint32_t)A;
-  const uint32_t q = hi / 1023u, rem = hi - q * 1023u;
-  uncertain |= (rem == 0u && lo < margin) || (rem == 1022u && lo > ~margin);
+struct ChromaTerm { int32_t ir, ig, ib; uint32_t flags; };   // flags: 2 bits per channel (f ~ 0, f ~ 1), r g b
+__device__ __forceinline__ int32_t chroma_floor(long long p32 /* 255*k*d in 32.32 */, uint32_t eps, uint32_t shift,
+                                                uint32_t& flags) {
+  const uint32_t f = (uint32_t)p32;                         // fractional part, units of 2^-32
+  flags |= ((f < eps ? 1u : 0u) | (f > ~eps ? 2u : 0u)) << shift;
+  return (int32_t)(p32 >> 32);                              // floor (arithmetic shift)
+}
+__device__ __forceinline__ ChromaTerm chroma_term(uint32_t U, uint32_t V) {
+  const int32_t du = (int32_t)U - 512, dv = (int32_t)V - 512;
+  const uint32_t adu = (uint32_t)abs(du), adv = (uint32_t)abs(dv);
+  ChromaTerm c;
+  c.flags = 0;
+  c.ir = chroma_floor(255LL * (kKr * dv), 128u * adv + 256u, 0, c.flags);
+  c.ig = chroma_floor(-255LL * (kKgu * du + kKgv * dv), 128u * (adu + adv) + 256u, 2, c.flags);
+  c.ib = chroma_floor(255LL * (kKb * du), 128u * adu + 256u, 4, c.flags);
+  return c;
+}
+__device__ __forceinline__ uint32_t quant_int(int32_t m) {   // clamp(floor(m / 1023), 0, 255)
+  if (m <= 0) return 0u;
+  const uint32_t q = (uint32_t)m / 1023u;
   return q > 255u ? 255u : q;
 }
+// true when floor() of this channel depends on rounding details of the f64 chain
+__device__ __forceinline__ bool channel_uncertain(int32_t m, uint32_t fl) {
+  if (m <= 0) return false;
+  const uint32_t rem = (uint32_t)m % 1023u;
+  return ((fl & 1u) && rem == 0u) || ((fl & 2u) && rem == 1022u);
+}
+__device__ __forceinline__ uint32_t yuv_to_rgb_term(uint32_t Y, uint32_t U, uint32_t V, const ChromaTerm& c) {
+  const int32_t y255 = (int32_t)(255u * Y);
+  if (c.flags) {   // rare unless the chroma is exactly neutral; then only Y = 0 mod 341 reaches the f64 path
+    if (channel_uncertain(y255 + c.ir, c.flags) || channel_uncertain(y255 + c.ig, c.flags >> 2) ||
+        channel_uncertain(y255 + c.ib, c.flags >> 4))
+      return yuv_to_rgb_f64(Y, U, V);
+  }
+  return quant_int(y255 + c.ir) | (quant_int(y255 + c.ig) << 8) | (quant_int(y255 + c.ib) << 16);
+}
 __device__ __forceinline__ uint32_t yuv_to_rgb_packed(uint32_t Y, uint32_t U, uint32_t V) {
-  const int32_t du = (int32_t)U - 512, dv = (int32_t)V - 512;
-  const long long y32 = (long long)Y << 32;
-  const uint32_t adu = (uint32_t)abs(du), adv = (uint32_t)abs(dv);
-  bool unc = false;
-  const uint32_t r = quant_fixed(y32 + kKr * dv, 128u * adv + 1024u, unc);
-  const uint32_t g = quant_fixed(y32 - kKgu * du - kKgv * dv, 128u * (adu + adv) + 1024u, unc);
-  const uint32_t b = quant_fixed(y32 + kKb * du, 128u * adu + 1024u, unc);
-  if (unc) return yuv_to_rgb_f64(Y, U, V);                 // a handful of points per million
-  return r | (g << 8) | (b << 16);
+  return yuv_to_rgb_term(Y, U, V, chroma_term(U, V));
 }
 
 // occupancy of the full-resolution pixel (x,y) straight from the low-resolution video (codec.rs:294-298)
@@ -186,6 +211,9 @@ __device__ uint32_t boundary_type(const UnpackArgs& a, const uint8_t* occ_f, int
 // ----------------------------------------------------------------------------------------------------------------
 // sparse voxel-cell tables (own spec; see DESIGN.md "Smoothing specification")
 // ----------------------------------------------------------------------------------------------------------------
+// x / G.g for x < 65536 by multiply-high (magic = ceil(2^32 / g); exact while x * g < 2^32)
+__device__ __forceinline__ uint32_t cell_div(uint32_t x, const GridDesc& G) { return G.g == 1u ? x : __umulhi(x, G.magic); }
+
 __device__ __forceinline__ uint64_t cell_slot0(uint32_t key, const GridDesc& G) {
   const uint32_t cx = key & 1023u, cy = (key >> 10) & 1023u, cz = key >> 20;
   if (G.identity) return cx + (uint64_t)G.w * (cy + (uint64_t)G.w * cz);
@@ -332,8 +360,10 @@ __device__ __forceinline__ void warp_copy_out(uint8_t* __restrict__ g, const uin
 
 __device__ __forceinline__ int64_t ceil_div_pos(int64_t n, int64_t d) { return n <= 0 ? 0 : (n + d - 1) / d; }
 
-template <int kMode, bool kSmooth>   // kMode 0: fused single pass (chained scan) ; 1: count only ; 2: emit with tile bases
-__global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) unpack_kernel(const UnpackArgs a, uint32_t tile_offset) {
+// kMode 0: fused single pass (chained scan) ; 1: count only ; 2: emit with tile bases.  kDebug adds the streams the
+// reference materialises but nobody downstream needs (colors16bit, partition, point_to_pixel, boundary types).
+template <int kMode, bool kSmooth, bool kDebug>
+__global__ void __launch_bounds__(kWarpsPerTile * 32, (kSmooth || kDebug) ? 2 : 3) unpack_kernel(const UnpackArgs a, uint32_t tile_offset) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_tot[kWarpsPerTile];
   __shared__ uint32_t s_base;
@@ -544,10 +574,10 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) unpack_ke
     // (b) stage every output stream in shared memory at the same 16-byte phase as its global destination
     uint8_t* g_pos = a.out.pos ? reinterpret_cast<uint8_t*>(a.out.pos) + gidx * 6 : nullptr;
     uint8_t* g_rgb = a.out.rgb ? a.out.rgb + gidx * 3 : nullptr;
-    uint8_t* g_yuv = a.out.yuv ? reinterpret_cast<uint8_t*>(a.out.yuv) + gidx * 6 : nullptr;
-    uint8_t* g_part = a.out.part ? reinterpret_cast<uint8_t*>(a.out.part) + gidx * 2 : nullptr;
-    uint8_t* g_pix = a.out.pix ? reinterpret_cast<uint8_t*>(a.out.pix) + gidx * 4 : nullptr;
-    uint8_t* g_bt = a.out.btype ? a.out.btype + gidx : nullptr;
+    uint8_t* g_yuv = (kDebug && a.out.yuv) ? reinterpret_cast<uint8_t*>(a.out.yuv) + gidx * 6 : nullptr;
+    uint8_t* g_part = (kDebug && a.out.part) ? reinterpret_cast<uint8_t*>(a.out.part) + gidx * 2 : nullptr;
+    uint8_t* g_pix = (kDebug && a.out.pix) ? reinterpret_cast<uint8_t*>(a.out.pix) + gidx * 4 : nullptr;
+    uint8_t* g_bt = (kDebug && a.out.btype) ? a.out.btype + gidx : nullptr;
     uint8_t* s_pos = wsm + a.off_pos + ((uintptr_t)g_pos & 15u);
     uint8_t* s_rgb = wsm + a.off_rgb + ((uintptr_t)g_rgb & 15u);
     uint8_t* s_yuv = wsm + a.off_yuv + ((uintptr_t)g_yuv & 15u);      // smoothing: staged even when not written out
@@ -560,42 +590,59 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) unpack_ke
     uint32_t n_boundary = 0;
 
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (!((m1 >> j) & 1u)) continue;
-      const int32_t u = pu + j * su, v = pv + j * sv;
-      const uint32_t k0 = pre_sm[(uint32_t)((v & 15) * 16 + (u & 15))];
-      const uint32_t t = ((uint32_t)u * P.lod_x + P.u1) & 0xFFFFu;             // decoder.rs:875
-      const uint32_t b = ((uint32_t)v * P.lod_y + P.v1) & 0xFFFFu;             // decoder.rs:876
-      const uint32_t d0 = u16_of(g0, j) >> 2, d1 = u16_of(g1, j) >> 2;
-      const uint32_t n0 = normal_coord(P, d0);
-      const uint32_t n1 = a.absolute_d1 ? normal_coord(P, d1) : ((P.mode == 0 ? n0 + d1 : n0 - d1) & 0xFFFFu);
-      const uint32_t npts = 1u + ((m2 >> j) & 1u);
-      uint32_t bt = 0;
-      if (st_bt) { bt = boundary_type(a, occ_f, px + j, py); n_boundary += bt == 1u ? npts : 0u; }
-      for (uint32_t i = 0; i < npts; ++i) {                                     // map0 then map1 (codec.rs:421)
-        const uint32_t k = k0 + i;
-        const uint32_t n = i == 0 ? n0 : n1;
-        {
-          uint16_t* d = reinterpret_cast<uint16_t*>(s_pos + k * 6);
-          d[0] = (uint16_t)pick(srcx, n, t, b); d[1] = (uint16_t)pick(srcy, n, t, b); d[2] = (uint16_t)pick(srcz, n, t, b);
-        }
-        if (a.has_attr) {
-          const uint32_t Y = i == 0 ? u16_of(ya, j) : u16_of(yb, j);             // codec.rs:637-640, decoder.rs:976-977
-          const uint32_t U = i == 0 ? u16_of(ua, j >> 1) : u16_of(ub, j >> 1);
-          const uint32_t V = i == 0 ? u16_of(va, j >> 1) : u16_of(vb, j >> 1);
-          if (st_yuv) {
-            uint16_t* d = reinterpret_cast<uint16_t*>(s_yuv + k * 6);
-            d[0] = (uint16_t)Y; d[1] = (uint16_t)U; d[2] = (uint16_t)V;
+    for (int cc = 0; cc < 4; ++cc) {                                            // chroma column: pixels 2cc, 2cc+1
+      if (!((m1 >> (2 * cc)) & 3u)) continue;
+      ChromaTerm ta, tb;
+      uint32_t Ua = 0, Va = 0, Ub = 0, Vb = 0;
+      if (a.has_attr) {
+        Ua = u16_of(ua, cc); Va = u16_of(va, cc); Ub = u16_of(ub, cc); Vb = u16_of(vb, cc);   // decoder.rs:976-977
+        if (g_rgb) { ta = chroma_term(Ua, Va); tb = chroma_term(Ub, Vb); }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = 2 * cc + jj;
+        if (!((m1 >> j) & 1u)) continue;
+        const int32_t u = pu + j * su, v = pv + j * sv;
+        const uint32_t k0 = pre_sm[(uint32_t)((v & 15) * 16 + (u & 15))];
+        const uint32_t t = ((uint32_t)u * P.lod_x + P.u1) & 0xFFFFu;             // decoder.rs:875
+        const uint32_t b = ((uint32_t)v * P.lod_y + P.v1) & 0xFFFFu;             // decoder.rs:876
+        const uint32_t d0 = u16_of(g0, j) >> 2, d1 = u16_of(g1, j) >> 2;
+        const uint32_t n0 = normal_coord(P, d0);
+        const uint32_t n1 = a.absolute_d1 ? normal_coord(P, d1) : ((P.mode == 0 ? n0 + d1 : n0 - d1) & 0xFFFFu);
+        const bool two = (m2 >> j) & 1u;
+        uint32_t bt = 0;
+        if (st_bt) { bt = boundary_type(a, occ_f, px + j, py); n_boundary += bt == 1u ? (two ? 2u : 1u) : 0u; }
+        {                                                                         // map 0 (codec.rs:421, i == 0)
+          uint16_t* d = reinterpret_cast<uint16_t*>(s_pos + k0 * 6);
+          d[0] = (uint16_t)pick(srcx, n0, t, b); d[1] = (uint16_t)pick(srcy, n0, t, b); d[2] = (uint16_t)pick(srcz, n0, t, b);
+          if (a.has_attr) {
+            const uint32_t Y = u16_of(ya, j);                                     // codec.rs:637-640
+            if (st_yuv) { uint16_t* q = reinterpret_cast<uint16_t*>(s_yuv + k0 * 6); q[0] = (uint16_t)Y; q[1] = (uint16_t)Ua; q[2] = (uint16_t)Va; }
+            if (g_rgb) {
+              const uint32_t c = yuv_to_rgb_term(Y, Ua, Va, ta);
+              uint8_t* q = s_rgb + k0 * 3; q[0] = (uint8_t)c; q[1] = (uint8_t)(c >> 8); q[2] = (uint8_t)(c >> 16);
+            }
           }
-          if (g_rgb) {
-            const uint32_t c = yuv_to_rgb_packed(Y, U, V);
-            uint8_t* d = s_rgb + k * 3;
-            d[0] = (uint8_t)c; d[1] = (uint8_t)(c >> 8); d[2] = (uint8_t)(c >> 16);
-          }
+          if (g_part) *reinterpret_cast<uint16_t*>(s_part + k0 * 2) = (uint16_t)P.local_index;   // codec.rs:452
+          if (g_pix) *reinterpret_cast<uint32_t*>(s_pix + k0 * 4) = (uint32_t)(px + j) | ((uint32_t)py << 15);
+          if (st_bt) s_bt[k0] = (uint8_t)bt;
         }
-        if (g_part) *reinterpret_cast<uint16_t*>(s_part + k * 2) = (uint16_t)P.local_index;   // codec.rs:452
-        if (g_pix) *reinterpret_cast<uint32_t*>(s_pix + k * 4) = (uint32_t)(px + j) | ((uint32_t)py << 15) | (i << 30);
-        if (st_bt) s_bt[k] = (uint8_t)bt;
+        if (two) {                                                                // map 1 unless it duplicates map 0
+          const uint32_t k1 = k0 + 1;
+          uint16_t* d = reinterpret_cast<uint16_t*>(s_pos + k1 * 6);
+          d[0] = (uint16_t)pick(srcx, n1, t, b); d[1] = (uint16_t)pick(srcy, n1, t, b); d[2] = (uint16_t)pick(srcz, n1, t, b);
+          if (a.has_attr) {
+            const uint32_t Y = u16_of(yb, j);
+            if (st_yuv) { uint16_t* q = reinterpret_cast<uint16_t*>(s_yuv + k1 * 6); q[0] = (uint16_t)Y; q[1] = (uint16_t)Ub; q[2] = (uint16_t)Vb; }
+            if (g_rgb) {
+              const uint32_t c = yuv_to_rgb_term(Y, Ub, Vb, tb);
+              uint8_t* q = s_rgb + k1 * 3; q[0] = (uint8_t)c; q[1] = (uint8_t)(c >> 8); q[2] = (uint8_t)(c >> 16);
+            }
+          }
+          if (g_part) *reinterpret_cast<uint16_t*>(s_part + k1 * 2) = (uint16_t)P.local_index;
+          if (g_pix) *reinterpret_cast<uint32_t*>(s_pix + k1 * 4) = (uint32_t)(px + j) | ((uint32_t)py << 15) | (1u << 30);
+          if (st_bt) s_bt[k1] = (uint8_t)bt;
+        }
       }
     }
     __syncwarp();
@@ -667,7 +714,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) unpack_ke
               const uint32_t x = p[0], y = p[1], z = p[2];
               if (do_geo && x < a.sm.geo.th && y < a.sm.geo.th && z < a.sm.geo.th) {
                 const uint32_t g = a.sm.geo.g;
-                const uint32_t cx = x / g, cy = y / g, cz = z / g;
+                const uint32_t cx = cell_div(x, a.sm.geo), cy = cell_div(y, a.sm.geo), cz = cell_div(z, a.sm.geo);
                 const uint32_t key = cx | (cy << 10) | (cz << 20);
                 if (key != gr0.key) {
                   if (key == gr1.key) { const GeoRun t = gr0; gr0 = gr1; gr1 = t; }
@@ -676,8 +723,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) unpack_ke
                 gr0.cnt += 1; gr0.sx += x - cx * g; gr0.sy += y - cy * g; gr0.sz += z - cz * g;
               }
               if (do_col && x < a.sm.col.th && y < a.sm.col.th && z < a.sm.col.th) {
-                const uint32_t g = a.sm.col.g;
-                const uint32_t key = (x / g) | ((y / g) << 10) | ((z / g) << 20);
+                const uint32_t key = cell_div(x, a.sm.col) | (cell_div(y, a.sm.col) << 10) | (cell_div(z, a.sm.col) << 20);
                 if (key != cr0.key) {
                   if (key == cr1.key) { const ColRun t = cr0; cr0 = cr1; cr1 = t; }
                   else { flush_col(a, fig, cr1, patch); cr1 = cr0; cr0 = {key, 0, 0, 0, 0, 0ull}; }
@@ -725,7 +771,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) unpack_ke
       const uint32_t chunk_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
       uint64_t k = run + (incl - c);
       uint32_t bt = 0;
-      if (c && (a.out.btype || kSmooth)) bt = boundary_type(a, occ_f, (int32_t)x, (int32_t)y);
+      if (c && ((kDebug && a.out.btype) || kSmooth)) bt = boundary_type(a, occ_f, (int32_t)x, (int32_t)y);
       for (uint32_t m = 0; m < c; ++m, ++k) {
         const uint32_t n = m == 0 ? n0 : n1;
         const uint32_t X = pick(srcx, n, t, b), Yc = pick(srcy, n, t, b), Z = pick(srcz, n, t, b);
@@ -736,15 +782,15 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) unpack_ke
           Y = a.in.attr_y[fm * a.in.attr_y_map_stride + (uint64_t)y * a.in.attr_pitch_y + (uint64_t)x];
           const uint64_t co = fm * a.in.attr_c_map_stride + (uint64_t)(y >> 1) * a.in.attr_pitch_c + (uint64_t)(x >> 1);
           U = a.in.attr_u[co]; V = a.in.attr_v[co];
-          if (a.out.yuv) { uint16_t* d = a.out.yuv + k * 3; d[0] = (uint16_t)Y; d[1] = (uint16_t)U; d[2] = (uint16_t)V; }
+          if (kDebug && a.out.yuv) { uint16_t* d = a.out.yuv + k * 3; d[0] = (uint16_t)Y; d[1] = (uint16_t)U; d[2] = (uint16_t)V; }
           if (a.out.rgb) {
             const uint32_t cc = yuv_to_rgb_packed(Y, U, V);
             uint8_t* d = a.out.rgb + k * 3; d[0] = (uint8_t)cc; d[1] = (uint8_t)(cc >> 8); d[2] = (uint8_t)(cc >> 16);
           }
         }
-        if (a.out.part) a.out.part[k] = (uint16_t)P.local_index;
-        if (a.out.pix) a.out.pix[k] = (uint32_t)x | ((uint32_t)y << 15) | (m << 30);
-        if (a.out.btype) a.out.btype[k] = (uint8_t)bt;
+        if (kDebug && a.out.part) a.out.part[k] = (uint16_t)P.local_index;
+        if (kDebug && a.out.pix) a.out.pix[k] = (uint32_t)x | ((uint32_t)y << 15) | (m << 30);
+        if (kDebug && a.out.btype) a.out.btype[k] = (uint8_t)bt;
         if (kSmooth) {
           if (a.sm.geo.on && X < a.sm.geo.th && Yc < a.sm.geo.th && Z < a.sm.geo.th) {
             const uint32_t g = a.sm.geo.g, cx = X / g, cy = Yc / g, cz = Z / g;
@@ -824,7 +870,7 @@ __device__ __forceinline__ bool neighbourhood(const GridDesc& G, const uint32_t 
   int32_t s[3]; unsigned long long wa[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const uint32_t c = p[a] / G.g, rem = p[a] - c * G.g;
+    const uint32_t c = cell_div(p[a], G), rem = p[a] - c * G.g;
     s[a] = (int32_t)c + (rem < G.g / 2 ? -1 : 0);
     wa[a] = 2ull * (unsigned long long)((long long)p[a] - (long long)s[a] * (long long)G.g - (long long)(G.g / 2)) + 1ull;
   }
@@ -1011,24 +1057,28 @@ int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream) {
   return after_launch();
 }
 
-template <int kMode, bool kSmooth>
+template <int kMode, bool kSmooth, bool kDebug>
 static int launch_unpack_t(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute((const void*)unpack_kernel<kMode, kSmooth>,
+  cudaError_t e = cudaFuncSetAttribute((const void*)unpack_kernel<kMode, kSmooth, kDebug>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  unpack_kernel<kMode, kSmooth><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin);
+  unpack_kernel<kMode, kSmooth, kDebug><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin);
   return after_launch();
+}
+template <int kMode>
+static int launch_unpack_m(const UnpackArgs& a, bool smooth, bool debug, uint32_t t0, uint32_t t1, size_t smem, cudaStream_t s) {
+  if (smooth) return debug ? launch_unpack_t<kMode, true, true>(a, t0, t1, smem, s) : launch_unpack_t<kMode, true, false>(a, t0, t1, smem, s);
+  return debug ? launch_unpack_t<kMode, false, true>(a, t0, t1, smem, s) : launch_unpack_t<kMode, false, false>(a, t0, t1, smem, s);
 }
 
 int launch_unpack(const UnpackArgs& a, int mode, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream) {
   if (tile_end <= tile_begin) return 0;
   const size_t smem = mode == 1 ? 0 : unpack_smem_bytes(a);
   const cudaStream_t s = (cudaStream_t)stream;
-  if (mode == 1) return launch_unpack_t<1, false>(a, tile_begin, tile_end, smem, s);
-  if (smooth) return mode == 0 ? launch_unpack_t<0, true>(a, tile_begin, tile_end, smem, s)
-                               : launch_unpack_t<2, true>(a, tile_begin, tile_end, smem, s);
-  return mode == 0 ? launch_unpack_t<0, false>(a, tile_begin, tile_end, smem, s)
-                   : launch_unpack_t<2, false>(a, tile_begin, tile_end, smem, s);
+  const bool debug = a.out.yuv || a.out.part || a.out.pix || a.out.btype;
+  if (mode == 1) return launch_unpack_t<1, false, false>(a, tile_begin, tile_end, smem, s);
+  return mode == 0 ? launch_unpack_m<0>(a, smooth, debug, tile_begin, tile_end, smem, s)
+                   : launch_unpack_m<2>(a, smooth, debug, tile_begin, tile_end, smem, s);
 }
 
 int launch_tile_scan(const UnpackArgs& a, void* stream) {

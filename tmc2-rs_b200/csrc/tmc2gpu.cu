@@ -577,6 +577,7 @@ struct Batch {
         G.on = on ? 1 : 0;
         if (!on) return;
         G.g = g; G.w = (maxs + g - 1) / g; G.disth = std::max(g / 2, 1u); G.th = g * G.w;
+        G.magic = g > 1 ? (uint32_t)(((1ull << 32) + g - 1) / g) : 0u;
         G.slots = slots; G.table = table;
         G.identity = (uint64_t)G.w * G.w * G.w <= slots ? 1 : 0;
         G.touched = touched; G.touched_count = tcount;
