@@ -196,6 +196,32 @@ def test_smoothing_dense_overlap_case(gpu_ctx):
     assert frames[1].smoothed_positions == want["smoothed_positions"]
 
 
+def test_smoothing_hashed_tables_and_small_groups(monkeypatch):
+    """Same answers when the voxel-cell tables are hashed (grids too large for a dense table) and with 1-frame groups."""
+    monkeypatch.setenv("TMC2_FORCE_HASH", "1")
+    monkeypatch.setenv("TMC2_SMOOTH_GROUP", "2")
+    g = synth.make_gof(synth.config("small", frames=5))
+    for p in g.patches:
+        p["u1"] = 100 + (np.arange(len(p)) % 3)
+        p["v1"] = 100 + (np.arange(len(p)) % 2)
+        p["d1"] = np.where(p["projection_mode"] == 0, 64, 1024 - 64 - 300)
+        p["normal_axis"], p["tangent_axis"], p["bitangent_axis"] = 0, 2, 1
+    g.params.geometry_smoothing = True
+    g.params.color_smoothing = True
+    view = abi.GofView(g)
+    ctx = codec.Context()
+    try:
+        frames = ctx.decode_gof(view)
+        frames2 = ctx.decode_gof(view)          # tables must come back clean for the next GOF
+        for f in range(5):
+            want = oracle.reconstruct_frame(view, f)
+            for fr in (frames[f], frames2[f]):
+                assert np.array_equal(fr.positions, want["positions"]) and np.array_equal(fr.colors, want["colors"])
+                assert fr.smoothed_positions == want["smoothed_positions"] and fr.smoothed_colors == want["smoothed_colors"]
+    finally:
+        ctx.close()
+
+
 def test_error_codes_where_the_reference_panics(gpu_ctx):
     g = util.random_small_gof(seed=11)
     mk = lambda **kw: abi.GofView(abi.Gof(g.width, g.height, kw.get("occ", g.occ), g.geo, g.attr_y, g.attr_u, g.attr_v,

@@ -11,7 +11,7 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtmc2gpu.so")
+LIB_PATH = os.environ.get("TMC2_LIB") or os.path.join(_HERE, "libtmc2gpu.so")   # TMC2_LIB: tuning variants
 
 # every symbol include/tmc2gpu.h declares: (name, restype, argtypes)
 _P = C.c_void_p

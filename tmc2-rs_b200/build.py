@@ -31,17 +31,17 @@ def stale() -> bool:
     return any(os.path.exists(f) and os.path.getmtime(f) > t for f in files)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    if not force and not stale() and out == LIB:
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines] + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
         raise RuntimeError("nvcc failed building libtmc2gpu.so")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

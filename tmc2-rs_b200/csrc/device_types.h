@@ -17,11 +17,17 @@
 
 namespace tmc2 {
 
-constexpr int kWarpsPerTile = 8;            // one warp per 16x16 patch block ("slot"); one CTA per tile of 8 slots
+#ifndef TMC2_WARPS_PER_TILE
+#define TMC2_WARPS_PER_TILE 8
+#endif
+#ifndef TMC2_MIN_CTAS
+#define TMC2_MIN_CTAS 3
+#endif
+constexpr int kWarpsPerTile = TMC2_WARPS_PER_TILE;   // one warp per 16x16 patch block ("slot"); one CTA per tile of slots
 constexpr uint32_t kNoPatch = 0xFFFFFFFFu;  // padding slot
 constexpr int kSlotPoints = 512;            // max points of a 16x16 block (2 maps)
 
-struct DevPatch {            // reference Patch (src/decoder.rs:711-783), pre-digested on the host
+struct alignas(16) DevPatch { // reference Patch (src/decoder.rs:711-783), pre-digested on the host (64 B)
   int32_t  x0, y0;           // uv0 * occupancy_resolution  (pixels)
   uint32_t u0, v0;           // uv0 (blocks)
   uint32_t size_u0, size_v0; // size_uv0 (blocks)
@@ -60,18 +66,20 @@ struct Outputs {                // any pointer may be null = stream not wanted
 
 // ---- sparse voxel-cell tables of the grid smoothing stages (own spec) ---------------------------------
 constexpr uint32_t kCellEmpty = 0xFFFFFFFFu;
+// A cell is "multi-patch" (the smoothing trigger) when points of two different patches fell into it: the first
+// toucher CASes pfirst from 0 to patch+1, anybody who finds a different value there sets bit 31 of `count`.
+constexpr uint32_t kCellMulti = 0x80000000u;
 struct GeoCell {     // 32 B = one DRAM sector
-  uint32_t key;      // cx | cy<<10 | cz<<20 ; kCellEmpty = free
-  uint32_t count;
-  uint32_t pmin, pmax;          // smallest / largest patch index seen
+  uint32_t key;      // cx | cy<<10 | cz<<20 ; kCellEmpty = free (hashed tables only; dense tables ignore it)
+  uint32_t pfirst;   // patch index + 1 of the first point, 0 = untouched
+  uint32_t count;    // points in the cell | kCellMulti
   uint32_t sx, sy, sz;          // sums of (coordinate - cell origin)  (< grid size each)
-  uint32_t _pad;
+  uint32_t _pad[2];
 };
-struct ColCell {     // 64 B
-  uint32_t key, count, pmin, pmax;
-  unsigned long long sy, su, sv;   // sums of Y, U, V
+struct ColCell {     // 32 B
+  uint32_t key, pfirst, count;
+  uint32_t sy, su, sv;             // sums of Y, U, V (exact while count <= 65536; the filter checks)
   unsigned long long sy2;          // sum of Y*Y
-  unsigned long long _pad[2];
 };
 struct alignas(16) BoundaryEntry {  // one type-1 boundary point (16 B)
   uint32_t idx;         // point index inside its frame

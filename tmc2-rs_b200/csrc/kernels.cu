@@ -145,41 +145,44 @@ constexpr long long kKr = 6763714498LL;   // 1.57480 * 2^32
 constexpr long long kKgu = 804576224LL;   // 0.18733 * 2^32
 constexpr long long kKgv = 2010603040LL;  // 0.46813 * 2^32
 constexpr long long kKb = 7969870163LL;   // 1.85563 * 2^32
-struct ChromaTerm { int32_t ir, ig, ib; uint32_t flags; };   // flags: 2 bits per channel (f ~ 0, f ~ 1), r g b
-__device__ __forceinline__ int32_t chroma_floor(long long p32 /* 255*k*d in 32.32 */, uint32_t eps, uint32_t shift,
-                                                uint32_t& flags) {
+struct ChromaTerm { int32_t ir, ig, ib; uint32_t flagged; };   // flagged: some channel's f is within eps of 0 or 1
+__device__ __forceinline__ int32_t chroma_floor(long long p32 /* 255*k*d in 32.32 */, uint32_t eps, uint32_t& flagged) {
   const uint32_t f = (uint32_t)p32;                         // fractional part, units of 2^-32
-  flags |= ((f < eps ? 1u : 0u) | (f > ~eps ? 2u : 0u)) << shift;
+  flagged |= (f + eps <= 2u * eps) ? 1u : 0u;               // f < eps or f > 2^32 - 1 - eps (unsigned wrap)
   return (int32_t)(p32 >> 32);                              // floor (arithmetic shift)
 }
 __device__ __forceinline__ ChromaTerm chroma_term(uint32_t U, uint32_t V) {
   const int32_t du = (int32_t)U - 512, dv = (int32_t)V - 512;
   const uint32_t adu = (uint32_t)abs(du), adv = (uint32_t)abs(dv);
   ChromaTerm c;
-  c.flags = 0;
-  c.ir = chroma_floor(255LL * (kKr * dv), 128u * adv + 256u, 0, c.flags);
-  c.ig = chroma_floor(-255LL * (kKgu * du + kKgv * dv), 128u * (adu + adv) + 256u, 2, c.flags);
-  c.ib = chroma_floor(255LL * (kKb * du), 128u * adu + 256u, 4, c.flags);
+  c.flagged = 0;
+  c.ir = chroma_floor(255LL * kKr * dv, 128u * adv + 256u, c.flagged);
+  c.ig = chroma_floor(-(255LL * kKgu) * du - (255LL * kKgv) * dv, 128u * (adu + adv) + 256u, c.flagged);
+  c.ib = chroma_floor(255LL * kKb * du, 128u * adu + 256u, c.flagged);
   return c;
 }
-__device__ __forceinline__ uint32_t quant_int(int32_t m) {   // clamp(floor(m / 1023), 0, 255)
-  if (m <= 0) return 0u;
-  const uint32_t q = (uint32_t)m / 1023u;
-  return q > 255u ? 255u : q;
+// clamp(floor(m / 1023), 0, 255) for m < 7.1e7: floor(m / 1023) == umulhi(m, ceil(2^36 / 1023)) >> 4
+__device__ __forceinline__ uint32_t quant_int(int32_t m) {
+  const uint32_t q = __umulhi((uint32_t)max(m, 0), 67174465u) >> 4;
+  return min(q, 255u);
 }
-// true when floor() of this channel depends on rounding details of the f64 chain
-__device__ __forceinline__ bool channel_uncertain(int32_t m, uint32_t fl) {
-  if (m <= 0) return false;
-  const uint32_t rem = (uint32_t)m % 1023u;
-  return ((fl & 1u) && rem == 0u) || ((fl & 2u) && rem == 1022u);
+// A flagged chroma sample only matters when 255*Y + I sits right at a multiple of 1023: then the f64 chain decides.
+__device__ __noinline__ uint32_t yuv_to_rgb_flagged(uint32_t Y, uint32_t U, uint32_t V, int32_t ir, int32_t ig, int32_t ib) {
+  const int32_t y255 = (int32_t)(255u * Y);
+  const int32_t m[3] = {y255 + ir, y255 + ig, y255 + ib};
+  bool unc = false;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (m[i] <= 0) continue;
+    const uint32_t rem = (uint32_t)m[i] % 1023u;
+    unc |= rem == 0u || rem == 1022u;
+  }
+  if (unc) return yuv_to_rgb_f64(Y, U, V);
+  return quant_int(m[0]) | (quant_int(m[1]) << 8) | (quant_int(m[2]) << 16);
 }
 __device__ __forceinline__ uint32_t yuv_to_rgb_term(uint32_t Y, uint32_t U, uint32_t V, const ChromaTerm& c) {
+  if (c.flagged) return yuv_to_rgb_flagged(Y, U, V, c.ir, c.ig, c.ib);   // rare unless the chroma is exactly neutral
   const int32_t y255 = (int32_t)(255u * Y);
-  if (c.flags) {   // rare unless the chroma is exactly neutral; then only Y = 0 mod 341 reaches the f64 path
-    if (channel_uncertain(y255 + c.ir, c.flags) || channel_uncertain(y255 + c.ig, c.flags >> 2) ||
-        channel_uncertain(y255 + c.ib, c.flags >> 4))
-      return yuv_to_rgb_f64(Y, U, V);
-  }
   return quant_int(y255 + c.ir) | (quant_int(y255 + c.ig) << 8) | (quant_int(y255 + c.ib) << 16);
 }
 __device__ __forceinline__ uint32_t yuv_to_rgb_packed(uint32_t Y, uint32_t U, uint32_t V) {
@@ -223,23 +226,17 @@ __device__ __forceinline__ uint64_t cell_slot0(uint32_t key, const GridDesc& G) 
   return ((h << 3) | ((cx & 1u) | ((cy & 1u) << 1) | ((cz & 1u) << 2))) & (G.slots - 1);
 }
 
+// slot of `key` in the table of frame-in-group `fig`: direct index for dense tables, find-or-claim for hashed ones
 template <typename Cell>
-__device__ __forceinline__ Cell* cell_insert(const GridDesc& G, uint32_t fig, uint32_t key, uint64_t touched_cap, int* err) {
+__device__ __forceinline__ Cell* cell_slot(const GridDesc& G, uint32_t fig, uint32_t key, int* err) {
   Cell* tab = reinterpret_cast<Cell*>(G.table) + (uint64_t)fig * G.slots;
   uint64_t i = cell_slot0(key, G);
+  if (G.identity) return &tab[i];
   for (uint64_t probe = 0; probe < G.slots; ++probe) {
     uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&tab[i].key);
-    if (cur == kCellEmpty) {
-      cur = atomicCAS(&tab[i].key, kCellEmpty, key);
-      if (cur == kCellEmpty) {
-        const uint32_t t = atomicAdd(&G.touched_count[fig], 1u);
-        if (t < touched_cap) G.touched[(uint64_t)fig * touched_cap + t] = (uint32_t)i;
-        else atomicExch(err, 11);
-        return &tab[i];
-      }
-    }
-    if (cur == key) return &tab[i];
-    i = G.identity ? (i + 1 < G.slots ? i + 1 : 0) : ((i + 1) & (G.slots - 1));
+    if (cur == kCellEmpty) cur = atomicCAS(&tab[i].key, kCellEmpty, key);
+    if (cur == kCellEmpty || cur == key) return &tab[i];
+    i = (i + 1) & (G.slots - 1);
   }
   atomicExch(err, 11);
   return nullptr;
@@ -248,18 +245,27 @@ template <typename Cell>
 __device__ __forceinline__ const Cell* cell_find(const GridDesc& G, uint32_t fig, uint32_t key) {
   const Cell* tab = reinterpret_cast<const Cell*>(G.table) + (uint64_t)fig * G.slots;
   uint64_t i = cell_slot0(key, G);
+  if (G.identity) return tab[i].pfirst ? &tab[i] : nullptr;
   for (uint64_t probe = 0; probe < G.slots; ++probe) {
     const uint32_t k = tab[i].key;
     if (k == key) return &tab[i];
     if (k == kCellEmpty) return nullptr;
-    i = G.identity ? (i + 1 < G.slots ? i + 1 : 0) : ((i + 1) & (G.slots - 1));
+    i = (i + 1) & (G.slots - 1);
   }
   return nullptr;
 }
-__device__ __forceinline__ void patch_range_update(uint32_t* pmin, uint32_t* pmax, uint32_t patch) {
-  // stale reads only ever show a wider-than-current gap, so skipping the atomic when the patch is already inside is safe
-  if (__ldcg(pmin) > patch) atomicMin(pmin, patch);
-  if (__ldcg(pmax) < patch) atomicMax(pmax, patch);
+// first-toucher / multi-patch bookkeeping; the only operation of a flush that needs an answer from L2
+template <typename Cell>
+__device__ __forceinline__ void cell_claim(const GridDesc& G, uint32_t fig, Cell* c, uint32_t patch, uint64_t touched_cap, int* err) {
+  const uint32_t old = atomicCAS(&c->pfirst, 0u, patch + 1u);
+  if (old == 0u) {
+    const uint32_t t = atomicAdd(&G.touched_count[fig], 1u);
+    if (t < touched_cap) G.touched[(uint64_t)fig * touched_cap + t] =
+        (uint32_t)(c - (reinterpret_cast<Cell*>(G.table) + (uint64_t)fig * G.slots));
+    else atomicExch(err, 11);
+  } else if (old != patch + 1u) {
+    atomicOr(&c->count, kCellMulti);
+  }
 }
 
 struct GeoRun { uint32_t key, cnt, sx, sy, sz; };
@@ -267,19 +273,18 @@ struct ColRun { uint32_t key, cnt, sy, su, sv; unsigned long long sy2; };
 
 __device__ __forceinline__ void flush_geo(const UnpackArgs& a, uint32_t fig, const GeoRun& r, uint32_t patch) {
   if (r.cnt == 0) return;
-  GeoCell* c = cell_insert<GeoCell>(a.sm.geo, fig, r.key, a.sm.touched_cap, a.err);
+  GeoCell* c = cell_slot<GeoCell>(a.sm.geo, fig, r.key, a.err);
   if (!c) return;
-  atomicAdd(&c->count, r.cnt); atomicAdd(&c->sx, r.sx); atomicAdd(&c->sy, r.sy); atomicAdd(&c->sz, r.sz);
-  patch_range_update(&c->pmin, &c->pmax, patch);
+  atomicAdd(&c->count, r.cnt); atomicAdd(&c->sx, r.sx); atomicAdd(&c->sy, r.sy); atomicAdd(&c->sz, r.sz);   // REDs
+  cell_claim(a.sm.geo, fig, c, patch, a.sm.touched_cap, a.err);
 }
 __device__ __forceinline__ void flush_col(const UnpackArgs& a, uint32_t fig, const ColRun& r, uint32_t patch) {
   if (r.cnt == 0) return;
-  ColCell* c = cell_insert<ColCell>(a.sm.col, fig, r.key, a.sm.touched_cap, a.err);
+  ColCell* c = cell_slot<ColCell>(a.sm.col, fig, r.key, a.err);
   if (!c) return;
-  atomicAdd(&c->count, r.cnt);
-  atomicAdd(&c->sy, (unsigned long long)r.sy); atomicAdd(&c->su, (unsigned long long)r.su);
-  atomicAdd(&c->sv, (unsigned long long)r.sv); atomicAdd(&c->sy2, r.sy2);
-  patch_range_update(&c->pmin, &c->pmax, patch);
+  atomicAdd(&c->count, r.cnt); atomicAdd(&c->sy, r.sy); atomicAdd(&c->su, r.su); atomicAdd(&c->sv, r.sv);
+  atomicAdd(&c->sy2, r.sy2);
+  cell_claim(a.sm.col, fig, c, patch, a.sm.touched_cap, a.err);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -346,39 +351,246 @@ __device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, unsign
   return ((unsigned long long)epoch << 34) | (flag << 32) | value;
 }
 
-// copy `nbytes` staged at shared `sm` (which has the same 16-byte phase as global `g`) to global memory
+// Copy `nbytes` staged at shared `sm` (16-byte aligned, staged before the global position was known) to global `g`
+// (any alignment).  Global stores are aligned 16-byte vectors; the source words are re-aligned with a funnel shift.
 __device__ __forceinline__ void warp_copy_out(uint8_t* __restrict__ g, const uint8_t* sm, uint32_t nbytes, uint32_t lane) {
   const uint32_t head = min(nbytes, (uint32_t)((16u - (uint32_t)((uintptr_t)g & 15u)) & 15u));
   if (lane < head) g[lane] = sm[lane];
   const uint32_t nvec = (nbytes - head) >> 4;
-  const uint4* s4 = reinterpret_cast<const uint4*>(sm + head);
   uint4* g4 = reinterpret_cast<uint4*>(g + head);
-  for (uint32_t i = lane; i < nvec; i += 32) g4[i] = s4[i];
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(sm) + (head >> 2);   // first source word (4-byte aligned)
+  const uint32_t sh = (head & 3u) * 8u;                                          // byte phase inside a word, as bits
+  for (uint32_t i = lane; i < nvec; i += 32) {
+    const uint32_t* w = sw + i * 4;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
+    uint4 v;
+    v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
+    v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+    g4[i] = v;
+  }
   const uint32_t done = head + (nvec << 4);
   if (done + lane < nbytes) g[done + lane] = sm[done + lane];
 }
 
 __device__ __forceinline__ int64_t ceil_div_pos(int64_t n, int64_t d) { return n <= 0 ? 0 : (n + d - 1) / d; }
 
+// normal coordinates (n0 | n1 << 16) of one pixel from its two geometry samples (codec.rs:534-558)
+__device__ __forceinline__ uint32_t normals_of(const DevPatch& P, uint32_t s0, uint32_t s1, bool absolute_d1) {
+  const uint32_t d0 = s0 >> 2, d1 = s1 >> 2;                                     // depth = sample / 4
+  const uint32_t n0 = normal_coord(P, d0);
+  const uint32_t n1 = absolute_d1 ? normal_coord(P, d1) : ((P.mode == 0 ? n0 + d1 : n0 - d1) & 0xFFFFu);
+  return n0 | (n1 << 16);
+}
+
+// Generic slot path (any occupancy resolution; reference-literal rotated / mirrored orientations): lane = pixel, 32 at
+// a time in patch raster order, everything straight to global memory.  Rare, kept out of line to keep the fast path lean.
+template <bool kSmooth, bool kDebug>
+__device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, const DevPatch& P, uint32_t frame, uint32_t fig,
+                                               uint32_t u0b, uint32_t v0b, uint64_t gidx) {
+  const uint32_t lane = lane_id(), res = a.res;
+  const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
+  const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
+  const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
+  const int64_t sscale = a.spec_orientation ? res : 1;
+  const uint32_t srcx = axis_source(P, 0), srcy = axis_source(P, 1), srcz = axis_source(P, 2);
+  uint64_t run = gidx;
+  for (uint32_t base = 0; base < res * res; base += 32) {
+    const uint32_t i = base + lane;
+    uint32_t c = 0, n0 = 0, n1 = 0, t = 0, b = 0;
+    int64_t x = 0, y = 0;
+    if (i < res * res) {
+      const uint32_t v1 = i / res, u1 = i - v1 * res;
+      const uint32_t u = u0b * res + u1, v = v0b * res + v1;
+      patch_to_canvas(P, u, v, res, sscale, x, y);
+      if (occ_at(a, occ_f, (uint32_t)x, (uint32_t)y)) {
+        const uint64_t off = (uint64_t)y * a.in.geo_pitch + (uint64_t)x;
+        const uint32_t nn = normals_of(P, geo0[off], geo1[off], a.absolute_d1);
+        n0 = nn & 0xFFFFu; n1 = nn >> 16;
+        c = n1 != n0 ? 2u : 1u;
+        t = (u * P.lod_x + P.u1) & 0xFFFFu;
+        b = (v * P.lod_y + P.v1) & 0xFFFFu;
+      }
+    }
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t tt = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= (uint32_t)d) incl += tt;
+    }
+    const uint32_t chunk_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    uint64_t k = run + (incl - c);
+    uint32_t bt = 0;
+    if (c && ((kDebug && a.out.btype) || kSmooth)) bt = boundary_type(a, occ_f, (int32_t)x, (int32_t)y);
+    for (uint32_t m = 0; m < c; ++m, ++k) {
+      const uint32_t n = m == 0 ? n0 : n1;
+      const uint32_t X = pick(srcx, n, t, b), Yc = pick(srcy, n, t, b), Z = pick(srcz, n, t, b);
+      if (a.out.pos) { uint16_t* d = a.out.pos + k * 3; d[0] = (uint16_t)X; d[1] = (uint16_t)Yc; d[2] = (uint16_t)Z; }
+      uint32_t Y = 0, U = 0, V = 0;
+      if (a.has_attr) {
+        const uint64_t fm = (uint64_t)frame * 2 + m;
+        Y = a.in.attr_y[fm * a.in.attr_y_map_stride + (uint64_t)y * a.in.attr_pitch_y + (uint64_t)x];
+        const uint64_t co = fm * a.in.attr_c_map_stride + (uint64_t)(y >> 1) * a.in.attr_pitch_c + (uint64_t)(x >> 1);
+        U = a.in.attr_u[co]; V = a.in.attr_v[co];
+        if (kDebug && a.out.yuv) { uint16_t* d = a.out.yuv + k * 3; d[0] = (uint16_t)Y; d[1] = (uint16_t)U; d[2] = (uint16_t)V; }
+        if (a.out.rgb) {
+          const uint32_t cc = yuv_to_rgb_packed(Y, U, V);
+          uint8_t* d = a.out.rgb + k * 3; d[0] = (uint8_t)cc; d[1] = (uint8_t)(cc >> 8); d[2] = (uint8_t)(cc >> 16);
+        }
+      }
+      if (kDebug && a.out.part) a.out.part[k] = (uint16_t)P.local_index;
+      if (kDebug && a.out.pix) a.out.pix[k] = (uint32_t)x | ((uint32_t)y << 15) | (m << 30);
+      if (kDebug && a.out.btype) a.out.btype[k] = (uint8_t)bt;
+      if (kSmooth) {
+        if (a.sm.geo.on && X < a.sm.geo.th && Yc < a.sm.geo.th && Z < a.sm.geo.th) {
+          const uint32_t g = a.sm.geo.g, cx = cell_div(X, a.sm.geo), cy = cell_div(Yc, a.sm.geo), cz = cell_div(Z, a.sm.geo);
+          const GeoRun r = {cx | (cy << 10) | (cz << 20), 1, X - cx * g, Yc - cy * g, Z - cz * g};
+          flush_geo(a, fig, r, P.local_index);
+        }
+        if (a.sm.col.on && a.has_attr && X < a.sm.col.th && Yc < a.sm.col.th && Z < a.sm.col.th) {
+          const ColRun r = {cell_div(X, a.sm.col) | (cell_div(Yc, a.sm.col) << 10) | (cell_div(Z, a.sm.col) << 20), 1, Y, U, V,
+                            (unsigned long long)Y * Y};
+          flush_col(a, fig, r, P.local_index);
+        }
+        if (bt == 1) {
+          const uint32_t li = atomicAdd(&a.sm.blist_count[frame], 1u);
+          if (li < a.sm.blist_cap) {
+            BoundaryEntry e;
+            e.idx = (uint32_t)(k - (uint64_t)frame * a.out.cap);
+            e.pos[0] = (uint16_t)X; e.pos[1] = (uint16_t)Yc; e.pos[2] = (uint16_t)Z;
+            e.yuv[0] = (uint16_t)Y; e.yuv[1] = (uint16_t)U; e.yuv[2] = (uint16_t)V;
+            a.sm.blist[(uint64_t)frame * a.sm.blist_cap + li] = e;
+          } else atomicExch(a.err, 7);
+        }
+      }
+    }
+    run += chunk_total;
+  }
+}
+
+// Cell statistics of one staged run (smoothing instantiation).  Work is split by cell-aligned squares of the colour
+// grid in patch space (<= 25 per block for a cell edge of 4) so that a lane's points mostly share a cell; keys always
+// come from the staged positions, so the split is only a grouping heuristic and stays exact under u16 wrap-around.
+__device__ __noinline__ void accumulate_cells(const UnpackArgs& a, const DevPatch& P, uint32_t fig, uint32_t u0b, uint32_t v0b,
+                                              const uint8_t* cnt_sm, const uint16_t* pre_sm, const uint8_t* s_pos,
+                                              const uint8_t* s_yuv) {
+  const uint32_t lane = lane_id();
+  const bool do_geo = a.sm.geo.on != 0, do_col = a.sm.col.on != 0 && a.has_attr;
+  const int64_t cg = do_col ? a.sm.col.g : a.sm.geo.g;
+  const int64_t ulo = (int64_t)u0b * 16, vlo = (int64_t)v0b * 16;
+  const int64_t lx = P.lod_x, ly = P.lod_y;
+  const int64_t tc0 = (ulo * lx + P.u1) / cg, tc1 = ((ulo + 15) * lx + P.u1) / cg;
+  const int64_t bc0 = (vlo * ly + P.v1) / cg, bc1 = ((vlo + 15) * ly + P.v1) / cg;
+  const uint32_t nt = (uint32_t)(tc1 - tc0 + 1), nb = (uint32_t)(bc1 - bc0 + 1);
+  GeoRun gr0 = {kCellEmpty, 0, 0, 0, 0}, gr1 = gr0;
+  ColRun cr0 = {kCellEmpty, 0, 0, 0, 0, 0ull}, cr1 = cr0;
+  const uint32_t patch = P.local_index;
+  for (uint32_t pair = lane; pair < nt * nb; pair += 32) {
+    const int64_t tc = tc0 + pair % nt, bc = bc0 + pair / nt;
+    const int32_t ua_ = (int32_t)(lx ? min(max(ceil_div_pos(tc * cg - P.u1, lx), ulo), ulo + 16) : ulo);
+    const int32_t ub_ = (int32_t)(lx ? min(max(ceil_div_pos((tc + 1) * cg - P.u1, lx), ulo), ulo + 16) : ulo + 16);
+    const int32_t va_ = (int32_t)(ly ? min(max(ceil_div_pos(bc * cg - P.v1, ly), vlo), vlo + 16) : vlo);
+    const int32_t vb_ = (int32_t)(ly ? min(max(ceil_div_pos((bc + 1) * cg - P.v1, ly), vlo), vlo + 16) : vlo + 16);
+    for (int32_t vv = va_; vv < vb_; ++vv) {
+      for (int32_t uu = ua_; uu < ub_; ++uu) {
+        const uint32_t rank = (uint32_t)((vv & 15) * 16 + (uu & 15));
+        const uint32_t cnt = cnt_sm[rank];
+        const uint32_t k0 = pre_sm[rank];
+        for (uint32_t i = 0; i < cnt; ++i) {
+          const uint16_t* p = reinterpret_cast<const uint16_t*>(s_pos + (k0 + i) * 6);
+          const uint32_t x = p[0], y = p[1], z = p[2];
+          if (do_geo && x < a.sm.geo.th && y < a.sm.geo.th && z < a.sm.geo.th) {
+            const uint32_t g = a.sm.geo.g;
+            const uint32_t cx = cell_div(x, a.sm.geo), cy = cell_div(y, a.sm.geo), cz = cell_div(z, a.sm.geo);
+            const uint32_t key = cx | (cy << 10) | (cz << 20);
+            if (key != gr0.key) {
+              if (key == gr1.key) { const GeoRun t = gr0; gr0 = gr1; gr1 = t; }
+              else { flush_geo(a, fig, gr1, patch); gr1 = gr0; gr0 = {key, 0, 0, 0, 0}; }
+            }
+            gr0.cnt += 1; gr0.sx += x - cx * g; gr0.sy += y - cy * g; gr0.sz += z - cz * g;
+          }
+          if (do_col && x < a.sm.col.th && y < a.sm.col.th && z < a.sm.col.th) {
+            const uint32_t key = cell_div(x, a.sm.col) | (cell_div(y, a.sm.col) << 10) | (cell_div(z, a.sm.col) << 20);
+            if (key != cr0.key) {
+              if (key == cr1.key) { const ColRun t = cr0; cr0 = cr1; cr1 = t; }
+              else { flush_col(a, fig, cr1, patch); cr1 = cr0; cr0 = {key, 0, 0, 0, 0, 0ull}; }
+            }
+            const uint16_t* c = reinterpret_cast<const uint16_t*>(s_yuv + (k0 + i) * 6);
+            const uint32_t Y = c[0];
+            cr0.cnt += 1; cr0.sy += Y; cr0.su += c[1]; cr0.sv += c[2]; cr0.sy2 += (unsigned long long)Y * Y;
+          }
+        }
+      }
+    }
+  }
+  if (do_geo) { flush_geo(a, fig, gr0, patch); flush_geo(a, fig, gr1, patch); }
+  if (do_col) { flush_col(a, fig, cr0, patch); flush_col(a, fig, cr1, patch); }
+}
+
 // kMode 0: fused single pass (chained scan) ; 1: count only ; 2: emit with tile bases.  kDebug adds the streams the
 // reference materialises but nobody downstream needs (colors16bit, partition, point_to_pixel, boundary types).
+// Exclusive prefix of this tile inside its frame by decoupled look-back over the tile status words (one warp).
+__device__ __forceinline__ uint32_t tile_lookback(const UnpackArgs& a, uint32_t tile, uint32_t first_tile, uint32_t tile_sum,
+                                                  uint32_t lane) {
+  unsigned long long* status = reinterpret_cast<unsigned long long*>(a.tile_status);
+  if (tile == first_tile) {
+    if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagInclusive, tile_sum));
+    return 0;
+  }
+  if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagAggregate, tile_sum));
+  uint32_t excl = 0, spins = 0;
+  int64_t look = (int64_t)tile - 1;
+  while (true) {
+    const int64_t idx = look - (int64_t)lane;
+    const bool valid = idx >= (int64_t)first_tile;
+    unsigned long long st = pack_status(a.epoch, kFlagInclusive, 0);       // before the frame: prefix 0
+    if (valid) st = ld_relaxed_u64(status + idx);
+    const bool ready = (st >> 34) == a.epoch && ((st >> 32) & 3ull) != 0;
+    const uint32_t ready_mask = __ballot_sync(0xFFFFFFFFu, ready);
+    const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, ready && ((st >> 32) & 3ull) == kFlagInclusive);
+    // usable as soon as every predecessor up to the nearest inclusive one (or the whole window) has published
+    const uint32_t upto = incl_mask ? (uint32_t)(__ffs(incl_mask) - 1) : 31u;
+    const uint32_t need = upto == 31u ? 0xFFFFFFFFu : ((2u << upto) - 1u);
+    if ((ready_mask & need) != need) {
+      if (++spins > (1u << 22)) { if (lane == 0) atomicExch(a.err, 11); break; }   // watchdog: never hang the GPU
+      __nanosleep(20);
+      continue;
+    }
+    const uint32_t v = lane <= upto ? (uint32_t)(st & 0xFFFFFFFFull) : 0u;
+    excl += __reduce_add_sync(0xFFFFFFFFu, v);
+    if (incl_mask) break;
+    look -= 32;
+  }
+  if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagInclusive, excl + tile_sum));
+  return excl;
+}
+
+// kMode 0: fused single pass (chained scan) ; 1: count only ; 2: emit with tile bases.  kDebug adds the streams the
+// reference materialises but nobody downstream needs (colors16bit, partition, point_to_pixel, boundary types).
+//
+// CTA protocol (no __syncthreads after the prologue): every warp posts its slot's point count, then stages its output
+// in shared memory BEFORE the tile's base is known; the first warp that gets that far claims the look-back, publishes the
+// base, and everybody copies out.  Look-back latency therefore overlaps the other warps' staging work.
 template <int kMode, bool kSmooth, bool kDebug>
-__global__ void __launch_bounds__(kWarpsPerTile * 32, (kSmooth || kDebug) ? 2 : 3) unpack_kernel(const UnpackArgs a, uint32_t tile_offset) {
+__global__ void __launch_bounds__(kWarpsPerTile * 32, (kSmooth || kDebug) ? (TMC2_MIN_CTAS * 8 / kWarpsPerTile * 2 / 3) : (TMC2_MIN_CTAS * 8 / kWarpsPerTile))
+unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_tot[kWarpsPerTile];
-  __shared__ uint32_t s_base;
+  __shared__ uint32_t s_posted, s_claim, s_ready, s_base;
 
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t tile = blockIdx.x + tile_offset;
   const uint32_t slot = tile * kWarpsPerTile + warp;
+  if (threadIdx.x == 0) { s_posted = 0; s_claim = 0; s_ready = 0; }
   const uint32_t frame = a.tile_frame[tile];
   const uint32_t pid = a.slot_patch[slot];
   const uint32_t res = a.res;
+  __syncthreads();                                               // the only block-wide barrier
 
   DevPatch P;
-  bool owned = false;
+  bool owned = false, cand = false;
   int32_t bx = 0, by = 0;
   uint32_t u0b = 0, v0b = 0;
+  const uint32_t* b2p_ptr = nullptr;
   if (pid != kNoPatch) {
     P = a.patches[pid];
     const uint32_t s = slot - P.slot_base;
@@ -386,25 +598,29 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, (kSmooth || kDebug) ? 2 : 
     int64_t bxx, byy;
     patch_to_canvas(P, u0b, v0b, 1, 1, bxx, byy);                 // codec.rs:373-378
     bx = (int32_t)bxx; by = (int32_t)byy;
-    owned = a.block_to_patch[(uint64_t)frame * a.bw * a.bh + (uint64_t)by * a.bw + bx] == P.local_index + 1;  // :379
+    b2p_ptr = a.block_to_patch + (uint64_t)frame * a.bw * a.bh + (uint64_t)by * a.bw + bx;
+    cand = res == 16 && (a.spec_orientation || P.orient <= 1 || P.orient == 8);
   }
-  const bool fast = owned && res == 16 && (a.spec_orientation || P.orient <= 1 || P.orient == 8);
   const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
-  const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
-  const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
 
   // ---- phase 1: load the block, decide which pixels emit 1 or 2 points ------------------------------------------
-  uint4 g0 = {0, 0, 0, 0}, g1 = {0, 0, 0, 0}, ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
+  uint32_t nn[8];                                          // fast path: n0 | n1 << 16 of this lane's 8 pixels
+  uint4 ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
   uint2 ua = {0, 0}, va = {0, 0}, ub = {0, 0}, vb = {0, 0};
   uint32_t m1 = 0, m2 = 0;     // fast path: bit j set = pixel j of this lane emits >=1 / 2 points
   uint32_t total = 0;
   const int32_t px = bx * 16 + (int32_t)(lane & 1) * 8;   // fast path: this lane's 8 canvas pixels (px..px+7, py)
   const int32_t py = by * 16 + (int32_t)(lane >> 1);
+  bool fast = false;
 
-  if (fast) {
+  if (cand) {
+    // plane loads are issued before the ownership answer arrives (one less dependent round trip); an unowned block
+    // (a later patch took the canvas block, codec.rs:379) just drops them
+    const uint32_t owner = __ldg(b2p_ptr);
+    const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
     const uint64_t goff = (uint64_t)py * a.in.geo_pitch + px;
-    g0 = ldg_nc_v4(geo0 + goff);
-    g1 = ldg_nc_v4(geo1 + goff);
+    const uint4 g0 = ldg_nc_v4(geo0 + goff);
+    const uint4 g1 = ldg_nc_v4(geo0 + a.in.geo_map_stride + goff);
     if (kMode != 1 && a.has_attr) {
       const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride;
       const uint64_t yoff = (uint64_t)py * a.in.attr_pitch_y + px;
@@ -429,123 +645,81 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, (kSmooth || kDebug) ? 2 : 
         occ_bits |= (prev_v != 0 ? 1u : 0u) << j;
       }
     }
-    m1 = occ_bits;
+    owned = owner == P.local_index + 1;                           // codec.rs:379
+    fast = owned;
+    if (owned) {
+      m1 = occ_bits;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t d0 = u16_of(g0, j) >> 2, d1 = u16_of(g1, j) >> 2;          // codec.rs:534,548
-      const uint32_t n0 = normal_coord(P, d0);
-      uint32_t n1;
-      if (a.absolute_d1) n1 = normal_coord(P, d1);                               // :549-550
-      else n1 = (P.mode == 0 ? n0 + d1 : n0 - d1) & 0xFFFFu;                     // :551-558 (u16 wrap)
-      if (n1 != n0) m2 |= (occ_bits & (1u << j));                                // :422-428 duplicate skip
+      for (int j = 0; j < 8; ++j) {
+        nn[j] = normals_of(P, u16_of(g0, j), u16_of(g1, j), a.absolute_d1);
+        if ((nn[j] >> 16) != (nn[j] & 0xFFFFu)) m2 |= (occ_bits & (1u << j));   // codec.rs:422-428 duplicate skip
+      }
     }
     total = __reduce_add_sync(0xFFFFFFFFu, __popc(m1) + __popc(m2));
-  } else if (owned) {
-    // generic path (any resolution, reference-literal rotated orientations): lane = pixel, chunks of 32 in raster order
-    const int64_t sscale = a.spec_orientation ? res : 1;
-    for (uint32_t base = 0; base < res * res; base += 32) {
-      const uint32_t i = base + lane;
-      uint32_t c = 0;
-      if (i < res * res) {
-        const uint32_t v1 = i / res, u1 = i - v1 * res;
-        int64_t x, y;
-        patch_to_canvas(P, (int64_t)u0b * res + u1, (int64_t)v0b * res + v1, res, sscale, x, y);
-        if (occ_at(a, occ_f, (uint32_t)x, (uint32_t)y)) {
-          const uint64_t off = (uint64_t)y * a.in.geo_pitch + (uint64_t)x;
-          const uint32_t d0 = geo0[off] >> 2, d1 = geo1[off] >> 2;
-          const uint32_t n0 = normal_coord(P, d0);
-          const uint32_t n1 = a.absolute_d1 ? normal_coord(P, d1) : ((P.mode == 0 ? n0 + d1 : n0 - d1) & 0xFFFFu);
-          c = n1 != n0 ? 2u : 1u;
+  } else if (pid != kNoPatch) {
+    owned = __ldg(b2p_ptr) == P.local_index + 1;
+    if (owned) {
+      // generic path (any resolution, reference-literal rotated orientations): lane = pixel, 32 at a time
+      const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
+      const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
+      const int64_t sscale = a.spec_orientation ? res : 1;
+      for (uint32_t base = 0; base < res * res; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t c = 0;
+        if (i < res * res) {
+          const uint32_t v1 = i / res, u1 = i - v1 * res;
+          int64_t x, y;
+          patch_to_canvas(P, (int64_t)u0b * res + u1, (int64_t)v0b * res + v1, res, sscale, x, y);
+          if (occ_at(a, occ_f, (uint32_t)x, (uint32_t)y)) {
+            const uint64_t off = (uint64_t)y * a.in.geo_pitch + (uint64_t)x;
+            const uint32_t n = normals_of(P, geo0[off], geo1[off], a.absolute_d1);
+            c = (n >> 16) != (n & 0xFFFFu) ? 2u : 1u;
+          }
         }
+        total += __reduce_add_sync(0xFFFFFFFFu, c);
       }
-      total += __reduce_add_sync(0xFFFFFFFFu, c);
     }
   }
 
-  if (lane == 0) s_tot[warp] = total;
-  __syncthreads();
-
-  // ---- tile prefix: chained scan over tiles of the same frame ----------------------------------------------------
-  if (kMode == 1) {
-    if (threadIdx.x == 0) {
+  // post this slot's count
+  if (lane == 0) {
+    s_tot[warp] = total;
+    __threadfence_block();
+    const uint32_t prev = atomicAdd(&s_posted, 1u);
+    if (kMode == 1 && prev == kWarpsPerTile - 1) {               // count-only launch: the last poster sums the tile
       uint32_t t = 0;
 #pragma unroll
-      for (int w = 0; w < kWarpsPerTile; ++w) t += s_tot[w];
+      for (int w = 0; w < kWarpsPerTile; ++w) t += reinterpret_cast<volatile uint32_t*>(s_tot)[w];
       a.tile_total[tile] = t;
     }
-    return;
   }
-  if (warp == 0) {
-    uint32_t tile_sum = 0;
-#pragma unroll
-    for (int w = 0; w < kWarpsPerTile; ++w) tile_sum += s_tot[w];
-    uint32_t excl = 0;
-    const uint32_t first_tile = a.frame_tile_begin[frame];
-    if (kMode == 2) {
-      excl = a.tile_total[tile];
-    } else {
-      unsigned long long* status = reinterpret_cast<unsigned long long*>(a.tile_status);
-      if (tile == first_tile) {
-        if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagInclusive, tile_sum));
-      } else {
-        if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagAggregate, tile_sum));
-        int64_t look = (int64_t)tile - 1;
-        uint32_t spins = 0;
-        bool dead = false;
-        while (true) {
-          const int64_t idx = look - (int64_t)lane;
-          const bool valid = idx >= (int64_t)first_tile;
-          unsigned long long st = pack_status(a.epoch, kFlagInclusive, 0);       // before the frame: prefix 0
-          if (valid) st = ld_relaxed_u64(status + idx);
-          // wait until every predecessor in the window has published something for this launch
-          while (__any_sync(0xFFFFFFFFu, valid && ((st >> 34) != a.epoch || ((st >> 32) & 3ull) == 0))) {
-            if (++spins > (1u << 22)) { dead = true; break; }                    // watchdog: never hang the GPU
-            __nanosleep(40);
-            if (valid) st = ld_relaxed_u64(status + idx);
-          }
-          if (dead) { if (lane == 0) atomicExch(a.err, 11); break; }
-          const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, ((st >> 32) & 3ull) == kFlagInclusive);
-          const uint32_t upto = incl_mask ? (uint32_t)(__ffs(incl_mask) - 1) : 31u;   // nearest inclusive predecessor
-          const uint32_t v = lane <= upto ? (uint32_t)(st & 0xFFFFFFFFull) : 0u;
-          excl += __reduce_add_sync(0xFFFFFFFFu, v);
-          if (incl_mask) break;
-          look -= 32;
-        }
-        if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagInclusive, excl + tile_sum));
-      }
-    }
-    if (lane == 0) {
-      s_base = excl;
-      if (tile + 1 == a.frame_tile_begin[frame + 1]) a.frame_count[frame] = excl + tile_sum;  // codec.rs:482
-    }
-  }
-  __syncthreads();
-  if (!owned || total == 0) return;
+  if (kMode == 1) return;
 
-  uint32_t run_base = s_base;
-  for (uint32_t w = 0; w < warp; ++w) run_base += s_tot[w];
-  if ((uint64_t)run_base + total > a.out.cap) {                   // cannot happen for footprints inside the canvas
-    if (lane == 0) atomicExch(a.err, 7);
-    return;
-  }
-  const uint64_t gidx = (uint64_t)frame * a.out.cap + run_base;   // first point of this run
-  const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
-
-  // ---- phase 2 ----------------------------------------------------------------------------------------------------
-  if (fast) {
-    uint8_t* wsm = smem + (size_t)warp * a.warp_bytes;
-    // (a) exclusive prefix of the per-pixel counts in PATCH-LOCAL raster order (v1 major, u1 minor; codec.rs:382-385)
-    uint8_t* cnt_sm = wsm + a.off_scan;                             // [256] counts by rank
-    uint16_t* pre_sm = reinterpret_cast<uint16_t*>(cnt_sm + 256);   // [256] exclusive prefix by rank
+  // ---- phase 2a: stage the run in shared memory (needs only warp-local offsets) -----------------------------------
+  uint8_t* wsm = smem + (size_t)warp * a.warp_bytes;
+  uint8_t* cnt_sm = wsm + a.off_scan;                             // [256] counts by rank
+  uint16_t* pre_sm = reinterpret_cast<uint16_t*>(cnt_sm + 256);   // [256] exclusive prefix by rank
+  uint8_t* s_pos = wsm + a.off_pos;
+  uint8_t* s_rgb = wsm + a.off_rgb;
+  uint8_t* s_yuv = wsm + a.off_yuv;      // smoothing: staged even when not written out
+  uint8_t* s_part = wsm + a.off_part;
+  uint8_t* s_pix = wsm + a.off_pix;
+  uint8_t* s_bt = wsm + a.off_bt;        // smoothing: staged even when not written out
+  const bool w_rgb = a.out.rgb != nullptr;
+  const bool w_yuv = kDebug && a.out.yuv != nullptr, w_part = kDebug && a.out.part != nullptr;
+  const bool w_pix = kDebug && a.out.pix != nullptr, w_bt = kDebug && a.out.btype != nullptr;
+  uint32_t n_boundary = 0;
+  if (fast && total) {
+    // exclusive prefix of the per-pixel counts in PATCH-LOCAL raster order (v1 major, u1 minor; codec.rs:382-385)
     int32_t pu, pv, pu1, pv1;
     canvas_to_patch(P, px, py, 16, pu, pv);
     canvas_to_patch(P, px + 1, py, 16, pu1, pv1);
     const int32_t su = pu1 - pu, sv = pv1 - pv;                     // patch-space step per canvas pixel
+    const uint32_t rank0 = (uint32_t)((pv & 15) * 16 + (pu & 15));
+    const int32_t rstep = sv * 16 + su;                             // rank step per canvas pixel (no wrap inside a block)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t rank = (uint32_t)(((pv + j * sv) & 15) * 16 + ((pu + j * su) & 15));
-      cnt_sm[rank] = (uint8_t)(((m1 >> j) & 1u) + ((m2 >> j) & 1u));
-    }
+    for (int j = 0; j < 8; ++j)
+      cnt_sm[rank0 + j * rstep] = (uint8_t)(((m1 >> j) & 1u) + ((m2 >> j) & 1u));
     __syncwarp();
     {
       const uint2 c8 = *reinterpret_cast<const uint2*>(cnt_sm + lane * 8);
@@ -571,23 +745,12 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, (kSmooth || kDebug) ? 2 : 
     }
     __syncwarp();
 
-    // (b) stage every output stream in shared memory at the same 16-byte phase as its global destination
-    uint8_t* g_pos = a.out.pos ? reinterpret_cast<uint8_t*>(a.out.pos) + gidx * 6 : nullptr;
-    uint8_t* g_rgb = a.out.rgb ? a.out.rgb + gidx * 3 : nullptr;
-    uint8_t* g_yuv = (kDebug && a.out.yuv) ? reinterpret_cast<uint8_t*>(a.out.yuv) + gidx * 6 : nullptr;
-    uint8_t* g_part = (kDebug && a.out.part) ? reinterpret_cast<uint8_t*>(a.out.part) + gidx * 2 : nullptr;
-    uint8_t* g_pix = (kDebug && a.out.pix) ? reinterpret_cast<uint8_t*>(a.out.pix) + gidx * 4 : nullptr;
-    uint8_t* g_bt = (kDebug && a.out.btype) ? a.out.btype + gidx : nullptr;
-    uint8_t* s_pos = wsm + a.off_pos + ((uintptr_t)g_pos & 15u);
-    uint8_t* s_rgb = wsm + a.off_rgb + ((uintptr_t)g_rgb & 15u);
-    uint8_t* s_yuv = wsm + a.off_yuv + ((uintptr_t)g_yuv & 15u);      // smoothing: staged even when not written out
-    uint8_t* s_part = wsm + a.off_part + ((uintptr_t)g_part & 15u);
-    uint8_t* s_pix = wsm + a.off_pix + ((uintptr_t)g_pix & 15u);
-    uint8_t* s_bt = wsm + a.off_bt + ((uintptr_t)g_bt & 15u);         // smoothing: staged even when not written out
-    const bool st_yuv = a.has_attr && (g_yuv != nullptr || kSmooth);
-    const bool st_bt = g_bt != nullptr || kSmooth;
-    const uint32_t srcx = axis_source(P, 0), srcy = axis_source(P, 1), srcz = axis_source(P, 2);
-    uint32_t n_boundary = 0;
+    const bool st_yuv = a.has_attr && (w_yuv || kSmooth);
+    const bool st_bt = w_bt || kSmooth;
+    // generate_point (decoder.rs:871-878) stores normal, tangent, bitangent in that order: byte offsets inside a point.
+    // Axes that are not a permutation leave a coordinate at 0 (and let later stores overwrite earlier ones).
+    const uint32_t o_n = 2u * P.normal, o_t = 2u * P.tangent, o_b = 2u * P.bitangent;
+    const bool perm = ((1u << P.normal) | (1u << P.tangent) | (1u << P.bitangent)) == 7u;
 
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {                                            // chroma column: pixels 2cc, 2cc+1
@@ -596,226 +759,140 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, (kSmooth || kDebug) ? 2 : 
       uint32_t Ua = 0, Va = 0, Ub = 0, Vb = 0;
       if (a.has_attr) {
         Ua = u16_of(ua, cc); Va = u16_of(va, cc); Ub = u16_of(ub, cc); Vb = u16_of(vb, cc);   // decoder.rs:976-977
-        if (g_rgb) { ta = chroma_term(Ua, Va); tb = chroma_term(Ub, Vb); }
+        if (w_rgb) { ta = chroma_term(Ua, Va); tb = chroma_term(Ub, Vb); }
       }
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
         const int j = 2 * cc + jj;
         if (!((m1 >> j) & 1u)) continue;
         const int32_t u = pu + j * su, v = pv + j * sv;
-        const uint32_t k0 = pre_sm[(uint32_t)((v & 15) * 16 + (u & 15))];
-        const uint32_t t = ((uint32_t)u * P.lod_x + P.u1) & 0xFFFFu;             // decoder.rs:875
-        const uint32_t b = ((uint32_t)v * P.lod_y + P.v1) & 0xFFFFu;             // decoder.rs:876
-        const uint32_t d0 = u16_of(g0, j) >> 2, d1 = u16_of(g1, j) >> 2;
-        const uint32_t n0 = normal_coord(P, d0);
-        const uint32_t n1 = a.absolute_d1 ? normal_coord(P, d1) : ((P.mode == 0 ? n0 + d1 : n0 - d1) & 0xFFFFu);
+        const uint32_t k0 = pre_sm[rank0 + j * rstep];
+        const uint32_t t = (uint32_t)u * P.lod_x + P.u1;                          // decoder.rs:875 (stored as u16)
+        const uint32_t b = (uint32_t)v * P.lod_y + P.v1;                          // decoder.rs:876
         const bool two = (m2 >> j) & 1u;
         uint32_t bt = 0;
         if (st_bt) { bt = boundary_type(a, occ_f, px + j, py); n_boundary += bt == 1u ? (two ? 2u : 1u) : 0u; }
         {                                                                         // map 0 (codec.rs:421, i == 0)
-          uint16_t* d = reinterpret_cast<uint16_t*>(s_pos + k0 * 6);
-          d[0] = (uint16_t)pick(srcx, n0, t, b); d[1] = (uint16_t)pick(srcy, n0, t, b); d[2] = (uint16_t)pick(srcz, n0, t, b);
+          uint8_t* d = s_pos + k0 * 6;
+          if (!perm) { reinterpret_cast<uint16_t*>(d)[0] = 0; reinterpret_cast<uint16_t*>(d)[1] = 0; reinterpret_cast<uint16_t*>(d)[2] = 0; }
+          *reinterpret_cast<uint16_t*>(d + o_n) = (uint16_t)nn[j];
+          *reinterpret_cast<uint16_t*>(d + o_t) = (uint16_t)t;
+          *reinterpret_cast<uint16_t*>(d + o_b) = (uint16_t)b;
           if (a.has_attr) {
             const uint32_t Y = u16_of(ya, j);                                     // codec.rs:637-640
             if (st_yuv) { uint16_t* q = reinterpret_cast<uint16_t*>(s_yuv + k0 * 6); q[0] = (uint16_t)Y; q[1] = (uint16_t)Ua; q[2] = (uint16_t)Va; }
-            if (g_rgb) {
+            if (w_rgb) {
               const uint32_t c = yuv_to_rgb_term(Y, Ua, Va, ta);
               uint8_t* q = s_rgb + k0 * 3; q[0] = (uint8_t)c; q[1] = (uint8_t)(c >> 8); q[2] = (uint8_t)(c >> 16);
             }
           }
-          if (g_part) *reinterpret_cast<uint16_t*>(s_part + k0 * 2) = (uint16_t)P.local_index;   // codec.rs:452
-          if (g_pix) *reinterpret_cast<uint32_t*>(s_pix + k0 * 4) = (uint32_t)(px + j) | ((uint32_t)py << 15);
+          if (w_part) *reinterpret_cast<uint16_t*>(s_part + k0 * 2) = (uint16_t)P.local_index;   // codec.rs:452
+          if (w_pix) *reinterpret_cast<uint32_t*>(s_pix + k0 * 4) = (uint32_t)(px + j) | ((uint32_t)py << 15);
           if (st_bt) s_bt[k0] = (uint8_t)bt;
         }
         if (two) {                                                                // map 1 unless it duplicates map 0
           const uint32_t k1 = k0 + 1;
-          uint16_t* d = reinterpret_cast<uint16_t*>(s_pos + k1 * 6);
-          d[0] = (uint16_t)pick(srcx, n1, t, b); d[1] = (uint16_t)pick(srcy, n1, t, b); d[2] = (uint16_t)pick(srcz, n1, t, b);
+          uint8_t* d = s_pos + k1 * 6;
+          if (!perm) { reinterpret_cast<uint16_t*>(d)[0] = 0; reinterpret_cast<uint16_t*>(d)[1] = 0; reinterpret_cast<uint16_t*>(d)[2] = 0; }
+          *reinterpret_cast<uint16_t*>(d + o_n) = (uint16_t)(nn[j] >> 16);
+          *reinterpret_cast<uint16_t*>(d + o_t) = (uint16_t)t;
+          *reinterpret_cast<uint16_t*>(d + o_b) = (uint16_t)b;
           if (a.has_attr) {
             const uint32_t Y = u16_of(yb, j);
             if (st_yuv) { uint16_t* q = reinterpret_cast<uint16_t*>(s_yuv + k1 * 6); q[0] = (uint16_t)Y; q[1] = (uint16_t)Ub; q[2] = (uint16_t)Vb; }
-            if (g_rgb) {
+            if (w_rgb) {
               const uint32_t c = yuv_to_rgb_term(Y, Ub, Vb, tb);
               uint8_t* q = s_rgb + k1 * 3; q[0] = (uint8_t)c; q[1] = (uint8_t)(c >> 8); q[2] = (uint8_t)(c >> 16);
             }
           }
-          if (g_part) *reinterpret_cast<uint16_t*>(s_part + k1 * 2) = (uint16_t)P.local_index;
-          if (g_pix) *reinterpret_cast<uint32_t*>(s_pix + k1 * 4) = (uint32_t)(px + j) | ((uint32_t)py << 15) | (1u << 30);
+          if (w_part) *reinterpret_cast<uint16_t*>(s_part + k1 * 2) = (uint16_t)P.local_index;
+          if (w_pix) *reinterpret_cast<uint32_t*>(s_pix + k1 * 4) = (uint32_t)(px + j) | ((uint32_t)py << 15) | (1u << 30);
           if (st_bt) s_bt[k1] = (uint8_t)bt;
         }
       }
     }
     __syncwarp();
-    // (c) coalesced 16-byte stores of the contiguous run
-    if (g_pos) warp_copy_out(g_pos, s_pos, total * 6, lane);
-    if (g_rgb) warp_copy_out(g_rgb, s_rgb, total * 3, lane);
-    if (g_yuv) warp_copy_out(g_yuv, s_yuv, total * 6, lane);
-    if (g_part) warp_copy_out(g_part, s_part, total * 2, lane);
-    if (g_pix) warp_copy_out(g_pix, s_pix, total * 4, lane);
-    if (g_bt) warp_copy_out(g_bt, s_bt, total, lane);
+  }
 
-    if (kSmooth) {
-      // (d) compact list of the type-1 boundary points of this run (order inside the list is irrelevant)
-      n_boundary = __reduce_add_sync(0xFFFFFFFFu, n_boundary);
-      if (n_boundary) {
-        uint32_t lbase = 0;
-        if (lane == 0) lbase = atomicAdd(&a.sm.blist_count[frame], n_boundary);
-        lbase = __shfl_sync(0xFFFFFFFFu, lbase, 0);
-        if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
-          if (lane == 0) atomicExch(a.err, 7);
-        } else {
-          BoundaryEntry* L = a.sm.blist + (uint64_t)frame * a.sm.blist_cap + lbase;
-          uint32_t done = 0;
-          for (uint32_t kb = 0; kb < total; kb += 32) {
-            const uint32_t k = kb + lane;
-            const bool isb = k < total && s_bt[k] == 1;
-            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, isb);
-            if (isb) {
-              BoundaryEntry e;
-              e.idx = run_base + k;
-              const uint16_t* p = reinterpret_cast<const uint16_t*>(s_pos + k * 6);
-              e.pos[0] = p[0]; e.pos[1] = p[1]; e.pos[2] = p[2];
-              if (a.has_attr) {
-                const uint16_t* c = reinterpret_cast<const uint16_t*>(s_yuv + k * 6);
-                e.yuv[0] = c[0]; e.yuv[1] = c[1]; e.yuv[2] = c[2];
-              } else { e.yuv[0] = e.yuv[1] = e.yuv[2] = 0; }
-              *reinterpret_cast<uint4*>(&L[done + __popc(mask & ((1u << lane) - 1u))]) = *reinterpret_cast<const uint4*>(&e);
-            }
-            done += __popc(mask);
-          }
-        }
-      }
-      // (e) cell statistics.  Work is split by cell-aligned squares of the colour grid in patch space (<= 25 per block
-      // for a cell edge of 4) so that a lane's points mostly share a cell; keys always come from the staged positions,
-      // so the split is only a grouping heuristic and stays exact under u16 wrap-around.
-      const bool do_geo = a.sm.geo.on != 0, do_col = a.sm.col.on != 0 && a.has_attr;
-      const int64_t cg = do_col ? a.sm.col.g : a.sm.geo.g;
-      const int64_t ulo = (int64_t)u0b * 16, vlo = (int64_t)v0b * 16;
-      const int64_t lx = P.lod_x, ly = P.lod_y;
-      const int64_t tc0 = (ulo * lx + P.u1) / cg, tc1 = ((ulo + 15) * lx + P.u1) / cg;
-      const int64_t bc0 = (vlo * ly + P.v1) / cg, bc1 = ((vlo + 15) * ly + P.v1) / cg;
-      const uint32_t nt = (uint32_t)(tc1 - tc0 + 1), nb = (uint32_t)(bc1 - bc0 + 1);
-      GeoRun gr0 = {kCellEmpty, 0, 0, 0, 0}, gr1 = gr0;
-      ColRun cr0 = {kCellEmpty, 0, 0, 0, 0, 0ull}, cr1 = cr0;
-      const uint32_t patch = P.local_index;
-      for (uint32_t pair = lane; pair < nt * nb; pair += 32) {
-        const int64_t tc = tc0 + pair % nt, bc = bc0 + pair / nt;
-        const int64_t ua_ = lx ? min(max(ceil_div_pos(tc * cg - P.u1, lx), ulo), ulo + 16) : ulo;
-        const int64_t ub_ = lx ? min(max(ceil_div_pos((tc + 1) * cg - P.u1, lx), ulo), ulo + 16) : ulo + 16;
-        const int64_t va_ = ly ? min(max(ceil_div_pos(bc * cg - P.v1, ly), vlo), vlo + 16) : vlo;
-        const int64_t vb_ = ly ? min(max(ceil_div_pos((bc + 1) * cg - P.v1, ly), vlo), vlo + 16) : vlo + 16;
-        for (int64_t vv = va_; vv < vb_; ++vv) {
-          for (int64_t uu = ua_; uu < ub_; ++uu) {
-            const uint32_t rank = (uint32_t)((vv & 15) * 16 + (uu & 15));
-            const uint32_t cnt = cnt_sm[rank];
-            const uint32_t k0 = pre_sm[rank];
-            for (uint32_t i = 0; i < cnt; ++i) {
-              const uint16_t* p = reinterpret_cast<const uint16_t*>(s_pos + (k0 + i) * 6);
-              const uint32_t x = p[0], y = p[1], z = p[2];
-              if (do_geo && x < a.sm.geo.th && y < a.sm.geo.th && z < a.sm.geo.th) {
-                const uint32_t g = a.sm.geo.g;
-                const uint32_t cx = cell_div(x, a.sm.geo), cy = cell_div(y, a.sm.geo), cz = cell_div(z, a.sm.geo);
-                const uint32_t key = cx | (cy << 10) | (cz << 20);
-                if (key != gr0.key) {
-                  if (key == gr1.key) { const GeoRun t = gr0; gr0 = gr1; gr1 = t; }
-                  else { flush_geo(a, fig, gr1, patch); gr1 = gr0; gr0 = {key, 0, 0, 0, 0}; }
-                }
-                gr0.cnt += 1; gr0.sx += x - cx * g; gr0.sy += y - cy * g; gr0.sz += z - cz * g;
-              }
-              if (do_col && x < a.sm.col.th && y < a.sm.col.th && z < a.sm.col.th) {
-                const uint32_t key = cell_div(x, a.sm.col) | (cell_div(y, a.sm.col) << 10) | (cell_div(z, a.sm.col) << 20);
-                if (key != cr0.key) {
-                  if (key == cr1.key) { const ColRun t = cr0; cr0 = cr1; cr1 = t; }
-                  else { flush_col(a, fig, cr1, patch); cr1 = cr0; cr0 = {key, 0, 0, 0, 0, 0ull}; }
-                }
-                const uint16_t* c = reinterpret_cast<const uint16_t*>(s_yuv + (k0 + i) * 6);
-                const uint32_t Y = c[0];
-                cr0.cnt += 1; cr0.sy += Y; cr0.su += c[1]; cr0.sv += c[2]; cr0.sy2 += (unsigned long long)Y * Y;
-              }
-            }
-          }
-        }
-      }
-      if (do_geo) { flush_geo(a, fig, gr0, patch); flush_geo(a, fig, gr1, patch); }
-      if (do_col) { flush_col(a, fig, cr0, patch); flush_col(a, fig, cr1, patch); }
-    }
-  } else {
-    // generic path: recompute and write straight to global memory (no staging, no run aggregation)
-    const int64_t sscale = a.spec_orientation ? res : 1;
-    const uint32_t srcx = axis_source(P, 0), srcy = axis_source(P, 1), srcz = axis_source(P, 2);
-    uint64_t run = gidx;
-    for (uint32_t base = 0; base < res * res; base += 32) {
-      const uint32_t i = base + lane;
-      uint32_t c = 0, n0 = 0, n1 = 0, t = 0, b = 0;
-      int64_t x = 0, y = 0;
-      if (i < res * res) {
-        const uint32_t v1 = i / res, u1 = i - v1 * res;
-        const uint32_t u = u0b * res + u1, v = v0b * res + v1;
-        patch_to_canvas(P, u, v, res, sscale, x, y);
-        if (occ_at(a, occ_f, (uint32_t)x, (uint32_t)y)) {
-          const uint64_t off = (uint64_t)y * a.in.geo_pitch + (uint64_t)x;
-          const uint32_t d0 = geo0[off] >> 2, d1 = geo1[off] >> 2;
-          n0 = normal_coord(P, d0);
-          n1 = a.absolute_d1 ? normal_coord(P, d1) : ((P.mode == 0 ? n0 + d1 : n0 - d1) & 0xFFFFu);
-          c = n1 != n0 ? 2u : 1u;
-          t = (u * P.lod_x + P.u1) & 0xFFFFu;
-          b = (v * P.lod_y + P.v1) & 0xFFFFu;
-        }
-      }
-      uint32_t incl = c;
+  // ---- tile base: the first warp to get here does the look-back for the whole tile --------------------------------
+  uint32_t claim = 0;
+  if (lane == 0) claim = atomicAdd(&s_claim, 1u);
+  claim = __shfl_sync(0xFFFFFFFFu, claim, 0);
+  if (claim == 0) {
+    while (*reinterpret_cast<volatile uint32_t*>(&s_posted) < (uint32_t)kWarpsPerTile) { }
+    __threadfence_block();
+    uint32_t tile_sum = 0;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t tt = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= (uint32_t)d) incl += tt;
-      }
-      const uint32_t chunk_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-      uint64_t k = run + (incl - c);
-      uint32_t bt = 0;
-      if (c && ((kDebug && a.out.btype) || kSmooth)) bt = boundary_type(a, occ_f, (int32_t)x, (int32_t)y);
-      for (uint32_t m = 0; m < c; ++m, ++k) {
-        const uint32_t n = m == 0 ? n0 : n1;
-        const uint32_t X = pick(srcx, n, t, b), Yc = pick(srcy, n, t, b), Z = pick(srcz, n, t, b);
-        if (a.out.pos) { uint16_t* d = a.out.pos + k * 3; d[0] = (uint16_t)X; d[1] = (uint16_t)Yc; d[2] = (uint16_t)Z; }
-        uint32_t Y = 0, U = 0, V = 0;
-        if (a.has_attr) {
-          const uint64_t fm = (uint64_t)frame * 2 + m;
-          Y = a.in.attr_y[fm * a.in.attr_y_map_stride + (uint64_t)y * a.in.attr_pitch_y + (uint64_t)x];
-          const uint64_t co = fm * a.in.attr_c_map_stride + (uint64_t)(y >> 1) * a.in.attr_pitch_c + (uint64_t)(x >> 1);
-          U = a.in.attr_u[co]; V = a.in.attr_v[co];
-          if (kDebug && a.out.yuv) { uint16_t* d = a.out.yuv + k * 3; d[0] = (uint16_t)Y; d[1] = (uint16_t)U; d[2] = (uint16_t)V; }
-          if (a.out.rgb) {
-            const uint32_t cc = yuv_to_rgb_packed(Y, U, V);
-            uint8_t* d = a.out.rgb + k * 3; d[0] = (uint8_t)cc; d[1] = (uint8_t)(cc >> 8); d[2] = (uint8_t)(cc >> 16);
-          }
-        }
-        if (kDebug && a.out.part) a.out.part[k] = (uint16_t)P.local_index;
-        if (kDebug && a.out.pix) a.out.pix[k] = (uint32_t)x | ((uint32_t)y << 15) | (m << 30);
-        if (kDebug && a.out.btype) a.out.btype[k] = (uint8_t)bt;
-        if (kSmooth) {
-          if (a.sm.geo.on && X < a.sm.geo.th && Yc < a.sm.geo.th && Z < a.sm.geo.th) {
-            const uint32_t g = a.sm.geo.g, cx = X / g, cy = Yc / g, cz = Z / g;
-            const GeoRun r = {cx | (cy << 10) | (cz << 20), 1, X - cx * g, Yc - cy * g, Z - cz * g};
-            flush_geo(a, fig, r, P.local_index);
-          }
-          if (a.sm.col.on && a.has_attr && X < a.sm.col.th && Yc < a.sm.col.th && Z < a.sm.col.th) {
-            const uint32_t g = a.sm.col.g;
-            const ColRun r = {(X / g) | ((Yc / g) << 10) | ((Z / g) << 20), 1, Y, U, V, (unsigned long long)Y * Y};
-            flush_col(a, fig, r, P.local_index);
-          }
-          if (bt == 1) {
-            const uint32_t li = atomicAdd(&a.sm.blist_count[frame], 1u);
-            if (li < a.sm.blist_cap) {
-              BoundaryEntry e;
-              e.idx = (uint32_t)(k - (uint64_t)frame * a.out.cap);
-              e.pos[0] = (uint16_t)X; e.pos[1] = (uint16_t)Yc; e.pos[2] = (uint16_t)Z;
-              e.yuv[0] = (uint16_t)Y; e.yuv[1] = (uint16_t)U; e.yuv[2] = (uint16_t)V;
-              a.sm.blist[(uint64_t)frame * a.sm.blist_cap + li] = e;
-            } else atomicExch(a.err, 7);
-          }
-        }
-      }
-      run += chunk_total;
+    for (int w = 0; w < kWarpsPerTile; ++w) tile_sum += reinterpret_cast<volatile uint32_t*>(s_tot)[w];
+    const uint32_t first_tile = a.frame_tile_begin[frame];
+    const uint32_t excl = kMode == 2 ? a.tile_total[tile] : tile_lookback(a, tile, first_tile, tile_sum, lane);
+    if (lane == 0) {
+      if (tile + 1 == a.frame_tile_begin[frame + 1]) a.frame_count[frame] = excl + tile_sum;  // codec.rs:482
+      s_base = excl;
+      __threadfence_block();
+      *reinterpret_cast<volatile uint32_t*>(&s_ready) = 1u;
     }
+  }
+  if (!owned || total == 0) return;
+  while (*reinterpret_cast<volatile uint32_t*>(&s_ready) == 0u) { }
+  __threadfence_block();
+  uint32_t run_base = *reinterpret_cast<volatile uint32_t*>(&s_base);
+  for (uint32_t w = 0; w < warp; ++w) run_base += reinterpret_cast<volatile uint32_t*>(s_tot)[w];
+  if ((uint64_t)run_base + total > a.out.cap) {                   // cannot happen for footprints inside the canvas
+    if (lane == 0) atomicExch(a.err, 7);
+    return;
+  }
+  const uint64_t gidx = (uint64_t)frame * a.out.cap + run_base;   // first point of this run
+  const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
+
+  // ---- phase 2b: copy-out ---------------------------------------------------------------------------------------------
+  if (!fast) {
+    generic_slot_emit<kSmooth, kDebug>(a, P, frame, fig, u0b, v0b, gidx);
+    return;
+  }
+  warp_copy_out(reinterpret_cast<uint8_t*>(a.out.pos) + gidx * 6, s_pos, total * 6, lane);
+  if (w_rgb) warp_copy_out(a.out.rgb + gidx * 3, s_rgb, total * 3, lane);
+  if (w_yuv) warp_copy_out(reinterpret_cast<uint8_t*>(a.out.yuv) + gidx * 6, s_yuv, total * 6, lane);
+  if (w_part) warp_copy_out(reinterpret_cast<uint8_t*>(a.out.part) + gidx * 2, s_part, total * 2, lane);
+  if (w_pix) warp_copy_out(reinterpret_cast<uint8_t*>(a.out.pix) + gidx * 4, s_pix, total * 4, lane);
+  if (w_bt) warp_copy_out(a.out.btype + gidx, s_bt, total, lane);
+
+  if (kSmooth) {
+    // compact list of the type-1 boundary points of this run (order inside the list is irrelevant)
+    n_boundary = __reduce_add_sync(0xFFFFFFFFu, n_boundary);
+    if (n_boundary) {
+      uint32_t lbase = 0;
+      if (lane == 0) lbase = atomicAdd(&a.sm.blist_count[frame], n_boundary);
+      lbase = __shfl_sync(0xFFFFFFFFu, lbase, 0);
+      if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
+        if (lane == 0) atomicExch(a.err, 7);
+      } else {
+        BoundaryEntry* L = a.sm.blist + (uint64_t)frame * a.sm.blist_cap + lbase;
+        uint32_t done = 0;
+        for (uint32_t kb = 0; kb < total; kb += 32) {
+          const uint32_t k = kb + lane;
+          const bool isb = k < total && s_bt[k] == 1;
+          const uint32_t mask = __ballot_sync(0xFFFFFFFFu, isb);
+          if (isb) {
+            const uint16_t* p = reinterpret_cast<const uint16_t*>(s_pos + k * 6);
+            uint4 e;
+            e.x = run_base + k;
+            e.y = p[0] | ((uint32_t)p[1] << 16);
+            e.z = p[2];
+            e.w = 0;
+            if (a.has_attr) {
+              const uint16_t* c = reinterpret_cast<const uint16_t*>(s_yuv + k * 6);
+              e.z |= (uint32_t)c[0] << 16;
+              e.w = c[1] | ((uint32_t)c[2] << 16);
+            }
+            reinterpret_cast<uint4*>(L)[done + __popc(mask & ((1u << lane) - 1u))] = e;
+          }
+          done += __popc(mask);
+        }
+      }
+    }
+    // cell statistics of the staged points
+    accumulate_cells(a, P, fig, u0b, v0b, cnt_sm, pre_sm, s_pos, s_yuv);
   }
 }
 
@@ -887,7 +964,7 @@ __device__ __forceinline__ bool neighbourhood(const GridDesc& G, const uint32_t 
   return true;
 }
 
-__global__ void __launch_bounds__(256) smooth_filter_kernel(const UnpackArgs a) {
+__global__ void __launch_bounds__(256) smooth_filter_kernel(const __grid_constant__ UnpackArgs a) {
   const uint32_t fig = blockIdx.y;
   const uint32_t f = a.sm.group_first_frame + fig;
   const uint32_t n = min((uint64_t)a.sm.blist_count[f], a.sm.blist_cap);
@@ -909,8 +986,9 @@ __global__ void __launch_bounds__(256) smooth_filter_kernel(const UnpackArgs a) 
         const GeoCell* c = N.key[j] != kCellEmpty ? cell_find<GeoCell>(G, fig, N.key[j]) : nullptr;
         uint32_t cnt = 0, s[3] = {0, 0, 0}, o[3] = {0, 0, 0};
         if (c) {
-          cnt = c->count; s[0] = c->sx; s[1] = c->sy; s[2] = c->sz;
-          if (cnt > 0 && c->pmin != c->pmax) other = true;
+          const uint32_t cw = c->count;
+          cnt = cw & ~kCellMulti; s[0] = c->sx; s[1] = c->sy; s[2] = c->sz;
+          if (cnt > 0 && (cw & kCellMulti)) other = true;
           o[0] = (N.key[j] & 1023u) * G.g; o[1] = ((N.key[j] >> 10) & 1023u) * G.g; o[2] = (N.key[j] >> 20) * G.g;
         }
 #pragma unroll
@@ -962,9 +1040,10 @@ __global__ void __launch_bounds__(256) smooth_filter_kernel(const UnpackArgs a) 
         const ColCell* c = N.key[j] != kCellEmpty ? cell_find<ColCell>(G, fig, N.key[j]) : nullptr;
         bool usable = false;
         unsigned long long mean[3] = {0, 0, 0};
-        if (c && c->count > 0) {
-          const unsigned long long cnt = c->count;
-          if (c->pmin != c->pmax) other = true;
+        if (c && (c->count & ~kCellMulti) > 0) {
+          const unsigned long long cnt = c->count & ~kCellMulti;
+          if (c->count & kCellMulti) other = true;
+          if (cnt > 65536ull) atomicExch(a.err, 6);     // u32 colour sums are only exact up to 65536 points per cell
           usable = true;
           const unsigned long long s[3] = {c->sy, c->su, c->sv};
 #pragma unroll
@@ -1016,7 +1095,7 @@ __device__ __forceinline__ void clear_cells(const GridDesc& G, uint32_t fig, uin
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     Cell z;
     memset(&z, 0, sizeof z);
-    z.key = kCellEmpty; z.pmin = 0xFFFFFFFFu;
+    z.key = kCellEmpty;
     tab[G.touched[(uint64_t)fig * touched_cap + i]] = z;
   }
 }
@@ -1038,7 +1117,7 @@ __global__ void __launch_bounds__(256) table_init_kernel(Cell* tab, uint64_t n) 
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     Cell z;
     memset(&z, 0, sizeof z);
-    z.key = kCellEmpty; z.pmin = 0xFFFFFFFFu;
+    z.key = kCellEmpty;
     tab[i] = z;
   }
 }

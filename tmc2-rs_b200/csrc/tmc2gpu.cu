@@ -153,6 +153,9 @@ static tmc2_status validate_params(const tmc2_gof* g, Err& err) {
   if (P.geometry_smoothing || P.color_smoothing) {
     if (P.geometry_bitdepth_3d == 0 || P.geometry_bitdepth_3d > 16) FAIL(TMC2_ERR_INVALID_ARG, "geometry_bitdepth_3d");
     const uint32_t maxs = 1u << P.geometry_bitdepth_3d;
+    if (2ull * g->width * g->height >= (1ull << 24))
+      FAIL(TMC2_ERR_UNSUPPORTED, "smoothing supports atlases up to 8.3 M pixels (per-cell sums are 32-bit)");
+    if (P.grid_size > 256 || P.cgrid_size > 256) FAIL(TMC2_ERR_UNSUPPORTED, "grid sizes above 256");
     if (P.geometry_smoothing) {
       if (P.grid_size < 1) FAIL(TMC2_ERR_INVALID_ARG, "grid_size");
       if ((maxs + P.grid_size - 1) / P.grid_size > 1024) FAIL(TMC2_ERR_UNSUPPORTED, "geometry grid wider than 1024 cells");
@@ -246,6 +249,7 @@ struct Batch {
   DevBuf d_geotab, d_coltab, d_touched_geo, d_touched_col, d_touched_count, d_changed, d_blist, d_blist_count;
   uint64_t geotab_slots = 0, coltab_slots = 0, geotab_frames = 0, coltab_frames = 0, touched_cap = 0, blist_cap = 0;
   uint32_t group_frames = 8;          // frames per smoothing group (cell tables stay L2-resident inside a group)
+  uint32_t group_frames_eff = 8;      // after fitting the dense tables into the memory budget
   std::vector<cudaEvent_t> ev_grp;    // 2 per group: around the unpack launch
   PinBuf h_in, h_meta, h_small, h_out;
   size_t meta_patch_off = 0, meta_slot_off = 0, meta_tf_off = 0, meta_ftb_off = 0, meta_bytes = 0;
@@ -379,7 +383,6 @@ struct Batch {
     if (want & WANT_OCC_FULL) CU(d_occ_full.ensure((size_t)F * W * H));
     if (smoothing_geo || smoothing_col) {
       if (const char* e = getenv("TMC2_SMOOTH_GROUP")) group_frames = std::max(1, atoi(e));
-      const uint32_t GF = std::min(group_frames, std::max(F, 1u));
       const uint32_t maxs = 1u << params.geometry_bitdepth_3d;
       // boundary-point lists (one per frame) and their counters
       if (blist_cap != cap || d_blist.cap < (size_t)F * cap * sizeof(BoundaryEntry)) {
@@ -390,9 +393,20 @@ struct Batch {
         CU(d_blist_count.ensure((size_t)F * 4));
         CU(cudaMemsetAsync(d_blist_count.p, 0, d_blist_count.cap, stream));
       }
-      auto table_slots = [&](uint32_t g) -> uint64_t {
-        const uint64_t w = (maxs + g - 1) / g, cells = w * w * w;
-        return cells <= 2 * cap ? cells : pow2_at_least(2 * cap);   // dense (identity) when the whole grid fits
+      // Cell tables: dense (direct-indexed, no probing, no key) when the whole grid fits the per-table budget for at
+      // least one frame, hashed otherwise.  The group size shrinks until the dense colour table fits.
+      const uint64_t kTableBudget = 16ull << 30;
+      auto cells_of = [&](uint32_t g) -> uint64_t { const uint64_t w = (maxs + g - 1) / g; return w * w * w; };
+      uint32_t GF = std::min(group_frames, std::max(F, 1u));
+      if (smoothing_col) {
+        const uint64_t per_frame = cells_of(params.cgrid_size) * sizeof(ColCell);
+        if (per_frame <= kTableBudget) GF = (uint32_t)std::min<uint64_t>(GF, std::max<uint64_t>(1, kTableBudget / per_frame));
+      }
+      group_frames_eff = GF;
+      auto table_slots = [&](uint32_t g, size_t cell_bytes) -> uint64_t {
+        const uint64_t cells = cells_of(g);
+        const bool force_hash = getenv("TMC2_FORCE_HASH") != nullptr;      // test hook for the hashed-table path
+        return (!force_hash && cells * cell_bytes <= kTableBudget) ? cells : pow2_at_least(2 * cap);
       };
       touched_cap = cap;
       if (d_touched_count.cap < (size_t)GF * 8) {
@@ -400,7 +414,7 @@ struct Batch {
         CU(cudaMemsetAsync(d_touched_count.p, 0, d_touched_count.cap, stream));
       }
       if (smoothing_geo) {
-        const uint64_t slots = table_slots(params.grid_size);
+        const uint64_t slots = table_slots(params.grid_size, sizeof(GeoCell));
         if (slots != geotab_slots || GF > geotab_frames) {
           CU(d_geotab.ensure((size_t)GF * slots * sizeof(GeoCell)));
           CU(d_touched_geo.ensure((size_t)GF * touched_cap * 4));
@@ -409,7 +423,7 @@ struct Batch {
         }
       }
       if (smoothing_col) {
-        const uint64_t slots = table_slots(params.cgrid_size);
+        const uint64_t slots = table_slots(params.cgrid_size, sizeof(ColCell));
         if (slots != coltab_slots || GF > coltab_frames) {
           CU(d_coltab.ensure((size_t)GF * slots * sizeof(ColCell)));
           CU(d_touched_col.ensure((size_t)GF * touched_cap * 4));
@@ -582,7 +596,7 @@ struct Batch {
         G.identity = (uint64_t)G.w * G.w * G.w <= slots ? 1 : 0;
         G.touched = touched; G.touched_count = tcount;
       };
-      const uint32_t GF = std::min(group_frames, std::max(F, 1u));
+      const uint32_t GF = group_frames_eff;
       grid(a.sm.geo, smoothing_geo, params.grid_size, d_geotab.p, geotab_slots, d_touched_geo.as<uint32_t>(),
            d_touched_count.as<uint32_t>());
       grid(a.sm.col, smoothing_col, params.cgrid_size, d_coltab.p, coltab_slots, d_touched_col.as<uint32_t>(),
@@ -638,7 +652,7 @@ struct Batch {
       CU(cudaEventRecord(ev_grp[1], s));
     } else {
       // frame groups: unpack (+ cell statistics + boundary lists) -> filter -> clear, tables stay hot in L2
-      const uint32_t GF = std::min(group_frames, std::max(F, 1u));
+      const uint32_t GF = group_frames_eff;
       n_groups = (F + GF - 1) / GF;
       while (ev_grp.size() < 2 * (size_t)n_groups) { cudaEvent_t e; CU(cudaEventCreate(&e)); ev_grp.push_back(e); }
       for (uint32_t gi = 0; gi < n_groups; ++gi) {

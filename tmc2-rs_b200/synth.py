@@ -208,8 +208,10 @@ def make_frame(cfg: SynthConfig, frame: int):
     # ---- geometry: smooth depth per rectangle ----------------------------------------------------------------------
     Y, X = np.mgrid[0:H, 0:W]
     rid_full = np.clip(np.repeat(np.repeat(rect_id, prec, axis=0), prec, axis=1)[:H, :W], 0, None)
-    fx = (0.004 + 0.02 * rng.uniform(nrect))[rid_full]
-    fy = (0.004 + 0.02 * rng.uniform(nrect))[rid_full]
+    # depth slope stays around <= 1.5 units / pixel: steeper surfaces are projected onto another plane by a V-PCC
+    # encoder (max gradient = 2*pi*f*amp)
+    fx = (0.0008 + 0.0027 * rng.uniform(nrect))[rid_full]
+    fy = (0.0008 + 0.0027 * rng.uniform(nrect))[rid_full]
     ph = (2 * np.pi * rng.uniform(nrect))[rid_full]
     mid = (0.3 + 0.4 * rng.uniform(nrect))[rid_full] * cfg.depth_max
     amp = 0.28 * cfg.depth_max
