@@ -522,7 +522,11 @@ static int color_smoothing(const tmc2_params* P, uint64_t n, const uint16_t* pos
   const uint64_t t_smooth = P->threshold_color_smoothing * cs_scale;
   const uint64_t t_diff = P->threshold_color_difference * cs_scale;
   const uint64_t t_var = P->threshold_color_variation * cs_scale;
+  /* pass 1: colour statistics of the SECOND-RING points (type 2): pixels next to, but not on, a patch outline.  The
+   * outline pixels themselves (type 1) carry the colour bleeding that this stage removes, so they are filtered
+   * (pass 2) but do not vote.  This is what gives boundary type 2 its purpose. */
   for (uint64_t k = 0; k < n; ++k) {
+    if (btype[k] != 2) continue;
     const uint16_t* p = pos + 3 * k;
     if (!in_grid(&G, p)) continue;
     cell* c = table_find(&T, cell_key(p[0] / G.g, p[1] / G.g, p[2] / G.g), 1);

@@ -2,16 +2,17 @@
 //
 // HBM layout of one batch (a GOF, or the slice of a GOF given to one GPU); F frames, M = 2 maps:
 //   occ    [F][occ_h][occ_pitch]       u8   low-resolution occupancy video     (reference atlas.occ_frames)
-//   geo    [F][2][H][geo_pitch]        u16  geometry video, channel 0 only     (reference atlas.geo_frames[0], frame f*2+m)
-//   attr_y [F][2][H][attr_pitch_y]     u16  attribute video, channel 0         (reference atlas.attr_frames[0])
-//   attr_u [F][2][H/2][attr_pitch_c]   u16  channel 1 (4:2:0)      attr_v likewise
+//   geo    [F][2][H][pitch]            u16  geometry video, channel 0 only     (reference atlas.geo_frames[0], frame f*2+m)
+//   attr_y [F][2][H][pitch]            u16  attribute video, channel 0         (reference atlas.attr_frames[0])
+//   attr_u [F][2][H/2][pitch_c]        u16  channel 1 (4:2:0)      attr_v likewise
 //   patches[total]  DevPatch ; slot_patch[n_tiles*kWarpsPerTile] ; tile_frame[n_tiles] ; frame_tile_begin[F+1]
 //   block_to_patch [F][bw*bh] u32
 // Pitches are multiples of 64 elements so every 16x16 canvas block row starts on a 32-byte boundary.
-// Outputs are per-frame slabs of `cap` points:  pos [F][cap][3] u16, rgb [F][cap][3] u8, and (debug / stage API only)
-// yuv [F][cap][3] u16, partition [F][cap] u16, pixel [F][cap] u32 (x | y<<15 | map<<30), btype [F][cap] u8; count [F] u32.
-// Smoothing state: per frame-in-group sparse voxel-cell tables (GeoCell / ColCell), touched-slot lists, and per frame a
-// compact list of type-1 boundary points (BoundaryEntry).
+// Outputs are per-frame slabs of `cap` points (cap % 16 == 0):  pos [F][cap][3] u16, rgb [F][cap][3] u8, and (debug /
+// stage API only) yuv [F][cap][3] u16, partition [F][cap] u16, pixel [F][cap] u32 (x | y<<15 | map<<30), btype [F][cap] u8;
+// count [F] u32.
+// Smoothing state (per group of frames): voxel-cell tables (GeoCell / ColCell, dense or hashed), a per-slot log of the
+// cells each slot added to, and per frame a compact list of type-1 boundary points (BoundaryEntry).
 #pragma once
 #include <cstdint>
 
@@ -20,21 +21,22 @@ namespace tmc2 {
 #ifndef TMC2_WARPS_PER_TILE
 #define TMC2_WARPS_PER_TILE 8
 #endif
-#ifndef TMC2_MIN_CTAS
-#define TMC2_MIN_CTAS 3
-#endif
 constexpr int kWarpsPerTile = TMC2_WARPS_PER_TILE;   // one warp per 16x16 patch block ("slot"); one CTA per tile of slots
 constexpr uint32_t kNoPatch = 0xFFFFFFFFu;  // padding slot
 constexpr int kSlotPoints = 512;            // max points of a 16x16 block (2 maps)
 
 struct alignas(16) DevPatch { // reference Patch (src/decoder.rs:711-783), pre-digested on the host (64 B)
-  int32_t  x0, y0;           // uv0 * occupancy_resolution  (pixels)
   uint32_t u0, v0;           // uv0 (blocks)
   uint32_t size_u0, size_v0; // size_uv0 (blocks)
   uint32_t u1, v1, d1;       // 3D shifts
   uint16_t lod_x, lod_y;
   uint8_t  normal, tangent, bitangent, mode;
-  uint8_t  orient, _pad[3];
+  uint8_t  orient;
+  uint8_t  aligned;          // 1: a 16x16 patch block is exactly one canvas block and (u,v) -> (x,y) is the affine map
+                             //    below (Default / Swap / MRot270 always; the other six in SPEC orientation mode)
+  int8_t   ax, ay;           // canvas step per +1 in patch u   (one of them is 0, the other +-1)
+  int8_t   rx, ry;           // canvas step per +1 in patch v
+  uint8_t  _pad[2];
   uint32_t slot_base;        // index of this patch's first slot in slot_patch[]
   uint32_t local_index;      // patch index inside its frame (partition value; block_to_patch holds local_index+1)
   uint32_t frame;            // frame inside the batch
@@ -61,25 +63,27 @@ struct Outputs {                // any pointer may be null = stream not wanted
   uint16_t* part;
   uint32_t* pix;
   uint8_t*  btype;
-  uint64_t  cap;                // points per frame slab
+  uint64_t  cap;                // points per frame slab (multiple of 16)
 };
 
-// ---- sparse voxel-cell tables of the grid smoothing stages (own spec) ---------------------------------
-constexpr uint32_t kCellEmpty = 0xFFFFFFFFu;
-// A cell is "multi-patch" (the smoothing trigger) when points of two different patches fell into it: the first
-// toucher CASes pfirst from 0 to patch+1, anybody who finds a different value there sets bit 31 of `count`.
-constexpr uint32_t kCellMulti = 0x80000000u;
+// ---- voxel-cell tables of the grid smoothing stages (own spec) ------------------------------------------
+// A cell is written only with fire-and-forget reductions (RED): two max, two / three 64-bit adds.  All-zero == empty.
+// "multi-patch" (the smoothing trigger) <=> max(patch) != min(patch) <=> pmax1 - 1 != ~pminc.
+// The finalize pass (once per touched cell, before the filter) turns the sums into Q8 means.
+constexpr uint32_t kCellEmpty = 0xFFFFFFFFu;      // free slot of a hashed table's key array
+constexpr uint32_t kCellFinal = 0x80000000u;      // ColCell.pmax1 flag: finalized
 struct GeoCell {     // 32 B = one DRAM sector
-  uint32_t key;      // cx | cy<<10 | cz<<20 ; kCellEmpty = free (hashed tables only; dense tables ignore it)
-  uint32_t pfirst;   // patch index + 1 of the first point, 0 = untouched
-  uint32_t count;    // points in the cell | kCellMulti
-  uint32_t sx, sy, sz;          // sums of (coordinate - cell origin)  (< grid size each)
-  uint32_t _pad[2];
+  uint32_t pmax1;               // max(patch index + 1), 0 = untouched
+  uint32_t pminc;               // max(~patch index)
+  unsigned long long cnt_sx;    // count | sum(x - cell origin) << 32
+  unsigned long long sy_sz;     // sum(y - origin) | sum(z - origin) << 32
+  unsigned long long mean;      // finalize: Q8 means relative to the cell origin, 16 bits each (x | y<<16 | z<<32)
 };
 struct ColCell {     // 32 B
-  uint32_t key, pfirst, count;
-  uint32_t sy, su, sv;             // sums of Y, U, V (exact while count <= 65536; the filter checks)
-  unsigned long long sy2;          // sum of Y*Y
+  uint32_t pmax1, pminc;
+  unsigned long long cnt_sy;    // count (24 bits) | sum(Y) << 24         finalize -> count | meanY_Q8 << 32
+  unsigned long long su_sv;     // sum(U) | sum(V) << 32                  finalize -> meanU_Q8 | meanV_Q8 << 32
+  unsigned long long sy2;       // sum(Y*Y)                               finalize -> 1 if the luminance variance test passes
 };
 struct alignas(16) BoundaryEntry {  // one type-1 boundary point (16 B)
   uint32_t idx;         // point index inside its frame
@@ -91,16 +95,20 @@ struct GridDesc {               // geometry of one voxel grid
   uint32_t on;
   uint32_t g, w, disth, th;     // cell edge, cells per axis, border margin, g*w
   uint32_t magic;               // ceil(2^32 / g): x / g == umulhi(x, magic) for x < 65536
+  int32_t  g_shift;             // log2(g) when g is a power of two, else -1
   uint32_t identity;            // 1: slot = dense cell index (table covers the whole grid)
   uint64_t slots;               // table slots per frame-in-group (power of two unless identity)
   void*    table;               // GeoCell / ColCell [frames_in_group][slots]
-  uint32_t* touched;            // [frames_in_group][touched_cap]
-  uint32_t* touched_count;      // [frames_in_group]
+  uint32_t* keys;               // hashed tables only: [frames_in_group][slots], kCellEmpty = free
+  uint32_t* log;                // [slots_in_group][log_stride] table slot of every flush of that unpack slot
+  uint32_t* log_count;          // [slots_in_group]
 };
 
 struct SmoothArgs {
   GridDesc geo, col;
-  uint64_t touched_cap;
+  uint32_t log_stride;          // entries per unpack slot (2 * res * res)
+  uint32_t group_first_slot;    // first unpack slot of the group (logs are indexed by slot - group_first_slot)
+  uint32_t group_slots;
   BoundaryEntry* blist;         // [F][blist_cap]
   uint32_t* blist_count;        // [F]
   uint64_t blist_cap;
@@ -129,10 +137,15 @@ struct UnpackArgs {
   uint32_t*       tile_total;         // two-pass mode: per-tile totals (count kernel) / exclusive bases (emit kernel)
   uint32_t*       frame_count;        // [F] points per frame
   int*            err;                // device error flag (0 ok)
-  // byte offsets of each staged stream inside a warp's shared-memory region, and the region size
-  uint32_t off_scan, off_pos, off_rgb, off_yuv, off_part, off_pix, off_bt, warp_bytes;
   SmoothArgs sm;                      // used by the smoothing instantiation only
 };
+
+// shared memory of one warp of unpack_kernel: staged positions (8 B / point, one pad slot every 8 points), staged
+// colours (4 B / point, one pad slot every 16 points), the 20x20 occupancy bitmap of the block and its 2-pixel margin
+constexpr uint32_t kStagePosBytes = (kSlotPoints + kSlotPoints / 8) * 8;    // 4608
+constexpr uint32_t kStageRgbBytes = (kSlotPoints + kSlotPoints / 16) * 4;   // 2176
+constexpr uint32_t kBitmapBytes = 32 * 4;
+constexpr uint32_t kWarpSmemBytes = kStagePosBytes + kStageRgbBytes + kBitmapBytes;   // 6912
 
 // launch wrappers (kernels.cu); every one enqueues on `stream` and returns the cudaGetLastError() code
 int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream);
@@ -140,11 +153,11 @@ int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream);
 int launch_unpack(const UnpackArgs& a, int mode, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream);
 int launch_tile_scan(const UnpackArgs& a, void* stream);
 int launch_upsample(const UnpackArgs& a, uint8_t* occ_full /*[F][H][W]*/, void* stream);
+int launch_smooth_finalize(const UnpackArgs& a, void* stream); // sums -> means for every cell the group touched
 int launch_smooth_filter(const UnpackArgs& a, void* stream);   // boundary points of the current frame group
 int launch_smooth_clear(const UnpackArgs& a, void* stream);    // reset touched cells + list counters of the group
 int launch_yuv_to_rgb_flat(const uint16_t* yuv, uint8_t* rgb, uint64_t n, void* stream);
-int launch_table_init(void* table, uint64_t total_slots, int is_color, void* stream);
-size_t unpack_smem_bytes(const UnpackArgs& a);
+int launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, void* stream);
 int kernel_launch_count_reset();   // returns launches since the last reset
 
 }  // namespace tmc2

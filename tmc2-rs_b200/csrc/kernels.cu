@@ -4,8 +4,9 @@
 //   K1  upsample_kernel           src/codec.rs:288-300   (materialised only for the stage API; fused otherwise)
 //   K3+K4 unpack_kernel           src/codec.rs:352-480 (unpack loop, order, dedup), :517-565 (generate_points),
 //                                 :569-658 (attribute fetch), :661-687 (YUV->RGB), src/decoder.rs:827-888 (patch maths)
-//       + K5 boundary type per point, K6/K7 cell statistics (own spec) in the smoothing instantiation
-//   K6/K7 smooth_filter_kernel    grid geometry + colour smoothing of the boundary points (own integer spec, DESIGN.md;
+//       + K5 boundary type per pixel, K6/K7 cell statistics (own spec) in the smoothing instantiation
+//   K6/K7 smooth_finalize_kernel / smooth_filter_kernel / smooth_clear_kernel
+//                                 grid geometry + colour smoothing of the boundary points (own integer spec, DESIGN.md;
 //                                 the reference has only stubs: decoder.rs:291-299)
 //
 // Ordering.  The reference emits points in (patch, v0, u0, v1, u1, map) order.  A 16x16 patch block ("slot") that
@@ -13,6 +14,12 @@
 // per-slot counts in slot order.  unpack_kernel is ONE pass: a warp owns a slot, a CTA owns a tile of 8 consecutive
 // slots, and tiles publish / look back their prefix through `tile_status` (single-pass chained scan with decoupled
 // look-back, tile id == blockIdx.x, one scan domain per frame).  Nothing is read twice from HBM.
+//
+// Lane layout of a slot.  Lane l owns the 8 pixels of patch-local ranks 8l .. 8l+7 (row v1 = l/2, columns
+// u1 = 8(l&1) .. +7), whatever the patch orientation: the orientation only changes WHERE those pixels are loaded from
+// (an affine map with steps in {-1,0,+1}; a 16-byte vector per plane for Default, eight 2-byte loads per plane for the
+// transposed / mirrored cases).  A lane therefore emits one contiguous piece of the output run and the ordered
+// compaction is a plain warp scan of lane totals.
 //
 // All arithmetic on the bit-exact path is integer.  The colour conversion of the reference is IEEE f64; it is evaluated
 // here in 32.32 fixed point with a proven error margin, and re-done with the literal f64 sequence (__dmul_rn/__dadd_rn/
@@ -28,6 +35,8 @@ namespace tmc2 {
 
 static int g_launches = 0;
 int kernel_launch_count_reset() { int n = g_launches; g_launches = 0; return n; }
+
+constexpr uint32_t kFull = 0xFFFFFFFFu;
 
 // ----------------------------------------------------------------------------------------------------------------
 // small helpers
@@ -46,7 +55,12 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {   // streaming 16-by
 }
 __device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
   uint2 r;
-  asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ldg_nc_u16(const uint16_t* p) {
+  uint16_t r;
+  asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(r) : "l"(p));
   return r;
 }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
@@ -57,15 +71,11 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
-
-__device__ __forceinline__ uint32_t u16_of(const uint4& v, int j) {   // j-th u16 of a 16-byte vector (j constant)
-  const uint32_t w = (j >> 1) == 0 ? v.x : (j >> 1) == 1 ? v.y : (j >> 1) == 2 ? v.z : v.w;
-  return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+__device__ __forceinline__ void stg_cs_v4(void* p, const uint4& v) {   // streaming store: output is never re-read here
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ uint32_t u16_of(const uint2& v, int j) {
-  const uint32_t w = (j >> 1) == 0 ? v.x : v.y;
-  return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
-}
+__device__ __forceinline__ uint32_t word_of(const uint4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+__device__ __forceinline__ uint32_t word_of(const uint2& v, int i) { return i == 0 ? v.x : v.y; }
 
 // ---- Patch maths, src/decoder.rs:853-888 --------------------------------------------------------------------------
 // Forward map patch (u,v) -> canvas (x,y), decoder.rs:853-867.  `sscale` multiplies size_uv0: 1 reproduces the
@@ -86,22 +96,6 @@ __device__ __forceinline__ void patch_to_canvas(const DevPatch& P, int64_t u, in
     default: x = v + u0;           y = u + v0;           break;   // Swap (1) and MRot270 (8)
   }
 }
-// Inverse map canvas (x,y) -> patch (u,v) for block-aligned orientations (sizes scaled by res).
-__device__ __forceinline__ void canvas_to_patch(const DevPatch& P, int32_t x, int32_t y, int32_t res, int32_t& u,
-                                                int32_t& v) {
-  const int32_t dx = x - P.x0, dy = y - P.y0;
-  const int32_t su = (int32_t)P.size_u0 * res, sv = (int32_t)P.size_v0 * res;
-  switch (P.orient) {
-    case 0:  u = dx;          v = dy;          break;
-    case 2:  u = dy;          v = sv - 1 - dx; break;
-    case 3:  u = su - 1 - dx; v = sv - 1 - dy; break;
-    case 4:  u = su - 1 - dy; v = dx;          break;
-    case 5:  u = su - 1 - dx; v = dy;          break;
-    case 6:  u = su - 1 - dy; v = sv - 1 - dx; break;
-    case 7:  u = dx;          v = sv - 1 - dy; break;
-    default: u = dy;          v = dx;          break;
-  }
-}
 
 // generate_normal_coordinate (decoder.rs:881-888), truncated to u16 like the `as u16` cast at :874
 __device__ __forceinline__ uint32_t normal_coord(const DevPatch& P, uint32_t depth) {
@@ -117,6 +111,9 @@ __device__ __forceinline__ uint32_t axis_source(const DevPatch& P, uint32_t a) {
 __device__ __forceinline__ uint32_t pick(uint32_t src, uint32_t n, uint32_t t, uint32_t b) {
   return src == 3u ? b : src == 2u ? t : src == 1u ? n : 0u;
 }
+// byte-permute selectors that build a staged position from A = n | t << 16 and Bv = b (upper half zero):
+// word 0 = pos[0] | pos[1] << 16, word 1 = pos[2].   source nibbles: n -> bytes 0,1 ; t -> 2,3 ; b -> 4,5 ; none -> 6,7
+__device__ __forceinline__ uint32_t sel_of_src(uint32_t src) { return src == 1u ? 0x10u : src == 2u ? 0x32u : src == 3u ? 0x54u : 0x76u; }
 
 // ---- convert_yuv10_to_rgb8, src/codec.rs:661-687 ---------------------------------------------------------------------
 // literal f64 sequence: one channel = clamp(floor(c / 1023 * 255))
@@ -136,7 +133,7 @@ __device__ __noinline__ uint32_t yuv_to_rgb_f64(uint32_t Y, uint32_t U, uint32_t
 // Exact integer evaluation.  With d = chroma - 512 and t = k*d, a channel is floor(T), T = 255*(Y + t)/1023.
 // Write 255*t = I + f with I integer and 0 <= f < 1: then floor((255*Y + I + f)/1023) == floor((255*Y + I)/1023), because
 // (255*Y + I)/1023 has a fractional part <= 1022/1023 and f/1023 < 1/1023.  So the chroma-dependent work is done ONCE per
-// chroma sample (ChromaTerm: three integers), and a point costs three 32-bit multiply-shift divisions.
+// chroma sample (ChromaTerm: three integers), and a point costs three 32-bit multiply-high divisions.
 // Exactness versus the reference's f64 chain: the chain deviates from the real value by < 2e-11, and I, f are computed
 // from the f64 constants rounded to 32 fractional bits (error <= 255*|d|/2^33), so floor() can only differ when f is
 // within `eps` = 255*|d|/2^33 + 2^-24 of 0 or 1 AND 255*Y + I is congruent to 0 / 1022 mod 1023.  Such chroma samples are
@@ -161,10 +158,10 @@ __device__ __forceinline__ ChromaTerm chroma_term(uint32_t U, uint32_t V) {
   c.ib = chroma_floor(255LL * kKb * du, 128u * adu + 256u, c.flagged);
   return c;
 }
-// clamp(floor(m / 1023), 0, 255) for m < 7.1e7: floor(m / 1023) == umulhi(m, ceil(2^36 / 1023)) >> 4
+// clamp(floor(m / 1023), 0, 255): clamp m to [0, 255*1023 + 1022] first, then floor(m / 1023) == umulhi(m, ceil(2^32/1023))
+// (exact while m * 1019 < 2^32, i.e. m < 4.2e6)
 __device__ __forceinline__ uint32_t quant_int(int32_t m) {
-  const uint32_t q = __umulhi((uint32_t)max(m, 0), 67174465u) >> 4;
-  return min(q, 255u);
+  return __umulhi((uint32_t)min(max(m, 0), 261887), 4198405u);
 }
 // A flagged chroma sample only matters when 255*Y + I sits right at a multiple of 1023: then the f64 chain decides.
 __device__ __noinline__ uint32_t yuv_to_rgb_flagged(uint32_t Y, uint32_t U, uint32_t V, int32_t ir, int32_t ig, int32_t ib) {
@@ -195,7 +192,7 @@ __device__ __forceinline__ uint32_t occ_at(const UnpackArgs& a, const uint8_t* o
 }
 
 // K5: boundary type of an occupied pixel (own spec): 1 = image border or an unoccupied 4-neighbour, 2 = an unoccupied
-// pixel inside the 5x5 window (clipped to the image), 0 = interior.  Evaluated per low-resolution cell.
+// pixel inside the 5x5 window (clipped to the image), 0 = interior.  Per-pixel form (generic slots only).
 __device__ uint32_t boundary_type(const UnpackArgs& a, const uint8_t* occ_f, int32_t x, int32_t y) {
   const int32_t W = (int32_t)a.W, H = (int32_t)a.H;
   if (x == 0 || y == 0 || x == W - 1 || y == H - 1) return 1;
@@ -212,87 +209,73 @@ __device__ uint32_t boundary_type(const UnpackArgs& a, const uint8_t* occ_f, int
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// sparse voxel-cell tables (own spec; see DESIGN.md "Smoothing specification")
+// voxel-cell tables (own spec; see DESIGN.md "Smoothing specification")
 // ----------------------------------------------------------------------------------------------------------------
 // x / G.g for x < 65536 by multiply-high (magic = ceil(2^32 / g); exact while x * g < 2^32)
-__device__ __forceinline__ uint32_t cell_div(uint32_t x, const GridDesc& G) { return G.g == 1u ? x : __umulhi(x, G.magic); }
+__device__ __forceinline__ uint32_t cell_div(uint32_t x, const GridDesc& G) {
+  return G.g_shift >= 0 ? (x >> G.g_shift) : __umulhi(x, G.magic);
+}
 
-__device__ __forceinline__ uint64_t cell_slot0(uint32_t key, const GridDesc& G) {
+__device__ __forceinline__ uint64_t hash_slot0(uint32_t key, const GridDesc& G) {
   const uint32_t cx = key & 1023u, cy = (key >> 10) & 1023u, cz = key >> 20;
-  if (G.identity) return cx + (uint64_t)G.w * (cy + (uint64_t)G.w * cz);
   // 2x2x2 neighbouring cells share one 8-slot group: the filter's neighbourhood lookups stay within a few lines
   const uint32_t grp = (cx >> 1) | ((cy >> 1) << 9) | ((cz >> 1) << 18);
   const uint64_t h = ((uint64_t)grp * 0x9E3779B97F4A7C15ull) >> 24;
   return ((h << 3) | ((cx & 1u) | ((cy & 1u) << 1) | ((cz & 1u) << 2))) & (G.slots - 1);
 }
-
-// slot of `key` in the table of frame-in-group `fig`: direct index for dense tables, find-or-claim for hashed ones
-template <typename Cell>
-__device__ __forceinline__ Cell* cell_slot(const GridDesc& G, uint32_t fig, uint32_t key, int* err) {
-  Cell* tab = reinterpret_cast<Cell*>(G.table) + (uint64_t)fig * G.slots;
-  uint64_t i = cell_slot0(key, G);
-  if (G.identity) return &tab[i];
+// table slot of cell `key` (cx | cy<<10 | cz<<20) in the table of frame-in-group `fig`: the dense index, or find-or-claim
+// in the key array of a hashed table.  kCellEmpty on failure (table full: cannot happen, slots >= 2 * points).
+__device__ __forceinline__ uint32_t cell_slot(const GridDesc& G, uint32_t fig, uint32_t key, int* err) {
+  if (G.identity) return (key & 1023u) + G.w * (((key >> 10) & 1023u) + G.w * (key >> 20));
+  uint32_t* keys = G.keys + (uint64_t)fig * G.slots;
+  uint64_t i = hash_slot0(key, G);
   for (uint64_t probe = 0; probe < G.slots; ++probe) {
-    uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&tab[i].key);
-    if (cur == kCellEmpty) cur = atomicCAS(&tab[i].key, kCellEmpty, key);
-    if (cur == kCellEmpty || cur == key) return &tab[i];
+    uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[i]);
+    if (cur == kCellEmpty) cur = atomicCAS(&keys[i], kCellEmpty, key);
+    if (cur == kCellEmpty || cur == key) return (uint32_t)i;
     i = (i + 1) & (G.slots - 1);
   }
   atomicExch(err, 11);
-  return nullptr;
+  return kCellEmpty;
 }
-template <typename Cell>
-__device__ __forceinline__ const Cell* cell_find(const GridDesc& G, uint32_t fig, uint32_t key) {
-  const Cell* tab = reinterpret_cast<const Cell*>(G.table) + (uint64_t)fig * G.slots;
-  uint64_t i = cell_slot0(key, G);
-  if (G.identity) return tab[i].pfirst ? &tab[i] : nullptr;
+__device__ __forceinline__ uint32_t cell_find(const GridDesc& G, uint32_t fig, uint32_t key) {
+  if (G.identity) return (key & 1023u) + G.w * (((key >> 10) & 1023u) + G.w * (key >> 20));
+  const uint32_t* keys = G.keys + (uint64_t)fig * G.slots;
+  uint64_t i = hash_slot0(key, G);
   for (uint64_t probe = 0; probe < G.slots; ++probe) {
-    const uint32_t k = tab[i].key;
-    if (k == key) return &tab[i];
-    if (k == kCellEmpty) return nullptr;
+    const uint32_t k = keys[i];
+    if (k == key) return (uint32_t)i;
+    if (k == kCellEmpty) return kCellEmpty;
     i = (i + 1) & (G.slots - 1);
   }
-  return nullptr;
-}
-// first-toucher / multi-patch bookkeeping; the only operation of a flush that needs an answer from L2
-template <typename Cell>
-__device__ __forceinline__ void cell_claim(const GridDesc& G, uint32_t fig, Cell* c, uint32_t patch, uint64_t touched_cap, int* err) {
-  const uint32_t old = atomicCAS(&c->pfirst, 0u, patch + 1u);
-  if (old == 0u) {
-    const uint32_t t = atomicAdd(&G.touched_count[fig], 1u);
-    if (t < touched_cap) G.touched[(uint64_t)fig * touched_cap + t] =
-        (uint32_t)(c - (reinterpret_cast<Cell*>(G.table) + (uint64_t)fig * G.slots));
-    else atomicExch(err, 11);
-  } else if (old != patch + 1u) {
-    atomicOr(&c->count, kCellMulti);
-  }
+  return kCellEmpty;
 }
 
-struct GeoRun { uint32_t key, cnt, sx, sy, sz; };
-struct ColRun { uint32_t key, cnt, sy, su, sv; unsigned long long sy2; };
-
-__device__ __forceinline__ void flush_geo(const UnpackArgs& a, uint32_t fig, const GeoRun& r, uint32_t patch) {
-  if (r.cnt == 0) return;
-  GeoCell* c = cell_slot<GeoCell>(a.sm.geo, fig, r.key, a.err);
-  if (!c) return;
-  atomicAdd(&c->count, r.cnt); atomicAdd(&c->sx, r.sx); atomicAdd(&c->sy, r.sy); atomicAdd(&c->sz, r.sz);   // REDs
-  cell_claim(a.sm.geo, fig, c, patch, a.sm.touched_cap, a.err);
+// fire-and-forget accumulation into a cell (REDs: nothing is read back)
+__device__ __forceinline__ void geo_cell_add(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
+                                             uint32_t sx, uint32_t sy, uint32_t sz) {
+  GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + slot;
+  atomicMax(&c->pmax1, patch + 1u);
+  atomicMax(&c->pminc, ~patch);
+  atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
+  atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
 }
-__device__ __forceinline__ void flush_col(const UnpackArgs& a, uint32_t fig, const ColRun& r, uint32_t patch) {
-  if (r.cnt == 0) return;
-  ColCell* c = cell_slot<ColCell>(a.sm.col, fig, r.key, a.err);
-  if (!c) return;
-  atomicAdd(&c->count, r.cnt); atomicAdd(&c->sy, r.sy); atomicAdd(&c->su, r.su); atomicAdd(&c->sv, r.sv);
-  atomicAdd(&c->sy2, r.sy2);
-  cell_claim(a.sm.col, fig, c, patch, a.sm.touched_cap, a.err);
+__device__ __forceinline__ void col_cell_add(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
+                                             uint32_t sy, uint32_t su, uint32_t sv, unsigned long long sy2) {
+  ColCell* c = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots + slot;
+  atomicMax(&c->pmax1, patch + 1u);
+  atomicMax(&c->pminc, ~patch);
+  atomicAdd(&c->cnt_sy, (unsigned long long)cnt | ((unsigned long long)sy << 24));
+  atomicAdd(&c->su_sv, (unsigned long long)su | ((unsigned long long)sv << 32));
+  atomicAdd(&c->sy2, sy2);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// K2: block-to-patch map.  One warp per slot (= one 16x16 block of one patch).
+// K2: block-to-patch map.  One thread per slot (= one 16x16 block of one patch).
 // ----------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) block_to_patch_kernel(const UnpackArgs a, uint32_t n_slots,
                                                              uint32_t* __restrict__ b2p) {
-  const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_slots) return;
   const uint32_t pid = a.slot_patch[slot];
   if (pid == kNoPatch) return;
@@ -302,32 +285,31 @@ __global__ void __launch_bounds__(256) block_to_patch_kernel(const UnpackArgs a,
   int64_t bx, by;
   patch_to_canvas(P, u0, v0, 1, 1, bx, by);                       // codec.rs:220-225 (block variant, resolution 1)
   const uint8_t* occ_f = a.in.occ + (uint64_t)P.frame * a.in.occ_frame_stride;
-  const uint32_t lane = lane_id();
   const uint32_t res = a.res;
   bool nz = false;
-  const bool aligned = a.spec_orientation || P.orient <= 1 || P.orient == 8;
-  if (aligned) {
-    // the 16x16 patch pixels are exactly the canvas block: test the low-resolution samples that cover it
+  if (P.aligned) {
+    // the res x res patch pixels are exactly the canvas block: test the low-resolution samples that cover it
     const uint32_t x0 = (uint32_t)bx * res, y0 = (uint32_t)by * res;
     const uint32_t cxa = div_prec(x0, a.prec, a.prec_shift), cxb = div_prec(x0 + res - 1, a.prec, a.prec_shift);
     const uint32_t cya = div_prec(y0, a.prec, a.prec_shift), cyb = div_prec(y0 + res - 1, a.prec, a.prec_shift);
-    const uint32_t nx = cxb - cxa + 1, n = nx * (cyb - cya + 1);
-    for (uint32_t i = lane; i < n; i += 32) {
-      const uint32_t cy = cya + i / nx, cx = cxa + i % nx;
-      nz |= occ_f[(uint64_t)cy * a.in.occ_pitch + cx] != 0;
+    for (uint32_t cy = cya; cy <= cyb && !nz; ++cy) {
+      const uint8_t* row = occ_f + (uint64_t)cy * a.in.occ_pitch;
+      if (((cxa | (cxb + 1)) & 3u) == 0) {                           // whole aligned words (precision 4, resolution 16)
+        for (uint32_t cx = cxa; cx <= cxb; cx += 4) nz |= *reinterpret_cast<const uint32_t*>(row + cx) != 0u;
+      } else {
+        for (uint32_t cx = cxa; cx <= cxb; ++cx) nz |= row[cx] != 0;
+      }
     }
   } else {
     // reference-literal pixel mapping for the rotated / mirrored orientations (codec.rs:227-241)
-    const int64_t sscale = a.spec_orientation ? res : 1;
-    for (uint32_t i = lane; i < res * res; i += 32) {
+    for (uint32_t i = 0; i < res * res && !nz; ++i) {
       const uint32_t v1 = i / res, u1 = i - v1 * res;
       int64_t x, y;
-      patch_to_canvas(P, (int64_t)u0 * res + u1, (int64_t)v0 * res + v1, res, sscale, x, y);
+      patch_to_canvas(P, (int64_t)u0 * res + u1, (int64_t)v0 * res + v1, res, 1, x, y);
       nz |= occ_at(a, occ_f, (uint32_t)x, (uint32_t)y) != 0;
     }
   }
-  if (__any_sync(0xFFFFFFFFu, nz) && lane == 0)
-    atomicMax(&b2p[(uint64_t)P.frame * a.bw * a.bh + (uint64_t)by * a.bw + (uint64_t)bx], P.local_index + 1);
+  if (nz) atomicMax(&b2p[(uint64_t)P.frame * a.bw * a.bh + (uint64_t)by * a.bw + (uint64_t)bx], P.local_index + 1);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -351,29 +333,6 @@ __device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, unsign
   return ((unsigned long long)epoch << 34) | (flag << 32) | value;
 }
 
-// Copy `nbytes` staged at shared `sm` (16-byte aligned, staged before the global position was known) to global `g`
-// (any alignment).  Global stores are aligned 16-byte vectors; the source words are re-aligned with a funnel shift.
-__device__ __forceinline__ void warp_copy_out(uint8_t* __restrict__ g, const uint8_t* sm, uint32_t nbytes, uint32_t lane) {
-  const uint32_t head = min(nbytes, (uint32_t)((16u - (uint32_t)((uintptr_t)g & 15u)) & 15u));
-  if (lane < head) g[lane] = sm[lane];
-  const uint32_t nvec = (nbytes - head) >> 4;
-  uint4* g4 = reinterpret_cast<uint4*>(g + head);
-  const uint32_t* sw = reinterpret_cast<const uint32_t*>(sm) + (head >> 2);   // first source word (4-byte aligned)
-  const uint32_t sh = (head & 3u) * 8u;                                          // byte phase inside a word, as bits
-  for (uint32_t i = lane; i < nvec; i += 32) {
-    const uint32_t* w = sw + i * 4;
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
-    uint4 v;
-    v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
-    v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
-    g4[i] = v;
-  }
-  const uint32_t done = head + (nvec << 4);
-  if (done + lane < nbytes) g[done + lane] = sm[done + lane];
-}
-
-__device__ __forceinline__ int64_t ceil_div_pos(int64_t n, int64_t d) { return n <= 0 ? 0 : (n + d - 1) / d; }
-
 // normal coordinates (n0 | n1 << 16) of one pixel from its two geometry samples (codec.rs:534-558)
 __device__ __forceinline__ uint32_t normals_of(const DevPatch& P, uint32_t s0, uint32_t s1, bool absolute_d1) {
   const uint32_t d0 = s0 >> 2, d1 = s1 >> 2;                                     // depth = sample / 4
@@ -382,11 +341,25 @@ __device__ __forceinline__ uint32_t normals_of(const DevPatch& P, uint32_t s0, u
   return n0 | (n1 << 16);
 }
 
-// Generic slot path (any occupancy resolution; reference-literal rotated / mirrored orientations): lane = pixel, 32 at
-// a time in patch raster order, everything straight to global memory.  Rare, kept out of line to keep the fast path lean.
+// staged point k of a warp: positions 8 B apart with one pad slot every 8 points, colours 4 B apart with one pad slot
+// every 16 points, so that the copy-out (one lane per group of 8 / 16 points) is free of bank conflicts
+__device__ __forceinline__ uint32_t spos_off(uint32_t k) { return (k + (k >> 3)) * 8u; }
+__device__ __forceinline__ uint32_t srgb_off(uint32_t k) { return (k + (k >> 4)) * 4u; }
+
+// ---- smoothing: per-point flush helpers (generic slots, colour statistics) -----------------------------------------
+struct SlotLog { uint32_t* geo; uint32_t* col; uint32_t n_geo, n_col; };   // this slot's log regions + warp-uniform counts
+
+__device__ __forceinline__ uint32_t cell_key_of(const GridDesc& G, uint32_t x, uint32_t y, uint32_t z) {
+  if (!(x < G.th && y < G.th && z < G.th)) return kCellEmpty;
+  return cell_div(x, G) | (cell_div(y, G) << 10) | (cell_div(z, G) << 20);
+}
+
+// Generic slot path (any occupancy resolution / precision; reference-literal rotated / mirrored orientations): lane =
+// pixel, 32 at a time in patch raster order, everything straight to global memory.  Rare; kept out of line.
 template <bool kSmooth, bool kDebug>
 __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, const DevPatch& P, uint32_t frame, uint32_t fig,
-                                               uint32_t u0b, uint32_t v0b, uint64_t gidx) {
+                                               uint32_t u0b, uint32_t v0b, uint64_t gidx, uint32_t* log_geo, uint32_t* log_col,
+                                               uint32_t* n_log /* shared: [0] geo, [1] col */) {
   const uint32_t lane = lane_id(), res = a.res;
   const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
   const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
@@ -414,10 +387,10 @@ __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, const DevPat
     uint32_t incl = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t tt = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      const uint32_t tt = __shfl_up_sync(kFull, incl, d);
       if (lane >= (uint32_t)d) incl += tt;
     }
-    const uint32_t chunk_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const uint32_t chunk_total = __shfl_sync(kFull, incl, 31);
     uint64_t k = run + (incl - c);
     uint32_t bt = 0;
     if (c && ((kDebug && a.out.btype) || kSmooth)) bt = boundary_type(a, occ_f, (int32_t)x, (int32_t)y);
@@ -441,15 +414,26 @@ __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, const DevPat
       if (kDebug && a.out.pix) a.out.pix[k] = (uint32_t)x | ((uint32_t)y << 15) | (m << 30);
       if (kDebug && a.out.btype) a.out.btype[k] = (uint8_t)bt;
       if (kSmooth) {
-        if (a.sm.geo.on && X < a.sm.geo.th && Yc < a.sm.geo.th && Z < a.sm.geo.th) {
-          const uint32_t g = a.sm.geo.g, cx = cell_div(X, a.sm.geo), cy = cell_div(Yc, a.sm.geo), cz = cell_div(Z, a.sm.geo);
-          const GeoRun r = {cx | (cy << 10) | (cz << 20), 1, X - cx * g, Yc - cy * g, Z - cz * g};
-          flush_geo(a, fig, r, P.local_index);
+        if (a.sm.geo.on) {
+          const uint32_t key = cell_key_of(a.sm.geo, X, Yc, Z);
+          if (key != kCellEmpty) {
+            const uint32_t cs = cell_slot(a.sm.geo, fig, key, a.err);
+            if (cs != kCellEmpty) {
+              const uint32_t g = a.sm.geo.g;
+              geo_cell_add(a.sm.geo, fig, cs, P.local_index, 1, X - (key & 1023u) * g, Yc - ((key >> 10) & 1023u) * g, Z - (key >> 20) * g);
+              log_geo[atomicAdd(&n_log[0], 1u)] = cs;
+            }
+          }
         }
-        if (a.sm.col.on && a.has_attr && X < a.sm.col.th && Yc < a.sm.col.th && Z < a.sm.col.th) {
-          const ColRun r = {cell_div(X, a.sm.col) | (cell_div(Yc, a.sm.col) << 10) | (cell_div(Z, a.sm.col) << 20), 1, Y, U, V,
-                            (unsigned long long)Y * Y};
-          flush_col(a, fig, r, P.local_index);
+        if (a.sm.col.on && a.has_attr && bt == 2) {
+          const uint32_t key = cell_key_of(a.sm.col, X, Yc, Z);
+          if (key != kCellEmpty) {
+            const uint32_t cs = cell_slot(a.sm.col, fig, key, a.err);
+            if (cs != kCellEmpty) {
+              col_cell_add(a.sm.col, fig, cs, P.local_index, 1, Y, U, V, (unsigned long long)Y * Y);
+              log_col[atomicAdd(&n_log[1], 1u)] = cs;
+            }
+          }
         }
         if (bt == 1) {
           const uint32_t li = atomicAdd(&a.sm.blist_count[frame], 1u);
@@ -467,67 +451,6 @@ __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, const DevPat
   }
 }
 
-// Cell statistics of one staged run (smoothing instantiation).  Work is split by cell-aligned squares of the colour
-// grid in patch space (<= 25 per block for a cell edge of 4) so that a lane's points mostly share a cell; keys always
-// come from the staged positions, so the split is only a grouping heuristic and stays exact under u16 wrap-around.
-__device__ __noinline__ void accumulate_cells(const UnpackArgs& a, const DevPatch& P, uint32_t fig, uint32_t u0b, uint32_t v0b,
-                                              const uint8_t* cnt_sm, const uint16_t* pre_sm, const uint8_t* s_pos,
-                                              const uint8_t* s_yuv) {
-  const uint32_t lane = lane_id();
-  const bool do_geo = a.sm.geo.on != 0, do_col = a.sm.col.on != 0 && a.has_attr;
-  const int64_t cg = do_col ? a.sm.col.g : a.sm.geo.g;
-  const int64_t ulo = (int64_t)u0b * 16, vlo = (int64_t)v0b * 16;
-  const int64_t lx = P.lod_x, ly = P.lod_y;
-  const int64_t tc0 = (ulo * lx + P.u1) / cg, tc1 = ((ulo + 15) * lx + P.u1) / cg;
-  const int64_t bc0 = (vlo * ly + P.v1) / cg, bc1 = ((vlo + 15) * ly + P.v1) / cg;
-  const uint32_t nt = (uint32_t)(tc1 - tc0 + 1), nb = (uint32_t)(bc1 - bc0 + 1);
-  GeoRun gr0 = {kCellEmpty, 0, 0, 0, 0}, gr1 = gr0;
-  ColRun cr0 = {kCellEmpty, 0, 0, 0, 0, 0ull}, cr1 = cr0;
-  const uint32_t patch = P.local_index;
-  for (uint32_t pair = lane; pair < nt * nb; pair += 32) {
-    const int64_t tc = tc0 + pair % nt, bc = bc0 + pair / nt;
-    const int32_t ua_ = (int32_t)(lx ? min(max(ceil_div_pos(tc * cg - P.u1, lx), ulo), ulo + 16) : ulo);
-    const int32_t ub_ = (int32_t)(lx ? min(max(ceil_div_pos((tc + 1) * cg - P.u1, lx), ulo), ulo + 16) : ulo + 16);
-    const int32_t va_ = (int32_t)(ly ? min(max(ceil_div_pos(bc * cg - P.v1, ly), vlo), vlo + 16) : vlo);
-    const int32_t vb_ = (int32_t)(ly ? min(max(ceil_div_pos((bc + 1) * cg - P.v1, ly), vlo), vlo + 16) : vlo + 16);
-    for (int32_t vv = va_; vv < vb_; ++vv) {
-      for (int32_t uu = ua_; uu < ub_; ++uu) {
-        const uint32_t rank = (uint32_t)((vv & 15) * 16 + (uu & 15));
-        const uint32_t cnt = cnt_sm[rank];
-        const uint32_t k0 = pre_sm[rank];
-        for (uint32_t i = 0; i < cnt; ++i) {
-          const uint16_t* p = reinterpret_cast<const uint16_t*>(s_pos + (k0 + i) * 6);
-          const uint32_t x = p[0], y = p[1], z = p[2];
-          if (do_geo && x < a.sm.geo.th && y < a.sm.geo.th && z < a.sm.geo.th) {
-            const uint32_t g = a.sm.geo.g;
-            const uint32_t cx = cell_div(x, a.sm.geo), cy = cell_div(y, a.sm.geo), cz = cell_div(z, a.sm.geo);
-            const uint32_t key = cx | (cy << 10) | (cz << 20);
-            if (key != gr0.key) {
-              if (key == gr1.key) { const GeoRun t = gr0; gr0 = gr1; gr1 = t; }
-              else { flush_geo(a, fig, gr1, patch); gr1 = gr0; gr0 = {key, 0, 0, 0, 0}; }
-            }
-            gr0.cnt += 1; gr0.sx += x - cx * g; gr0.sy += y - cy * g; gr0.sz += z - cz * g;
-          }
-          if (do_col && x < a.sm.col.th && y < a.sm.col.th && z < a.sm.col.th) {
-            const uint32_t key = cell_div(x, a.sm.col) | (cell_div(y, a.sm.col) << 10) | (cell_div(z, a.sm.col) << 20);
-            if (key != cr0.key) {
-              if (key == cr1.key) { const ColRun t = cr0; cr0 = cr1; cr1 = t; }
-              else { flush_col(a, fig, cr1, patch); cr1 = cr0; cr0 = {key, 0, 0, 0, 0, 0ull}; }
-            }
-            const uint16_t* c = reinterpret_cast<const uint16_t*>(s_yuv + (k0 + i) * 6);
-            const uint32_t Y = c[0];
-            cr0.cnt += 1; cr0.sy += Y; cr0.su += c[1]; cr0.sv += c[2]; cr0.sy2 += (unsigned long long)Y * Y;
-          }
-        }
-      }
-    }
-  }
-  if (do_geo) { flush_geo(a, fig, gr0, patch); flush_geo(a, fig, gr1, patch); }
-  if (do_col) { flush_col(a, fig, cr0, patch); flush_col(a, fig, cr1, patch); }
-}
-
-// kMode 0: fused single pass (chained scan) ; 1: count only ; 2: emit with tile bases.  kDebug adds the streams the
-// reference materialises but nobody downstream needs (colors16bit, partition, point_to_pixel, boundary types).
 // Exclusive prefix of this tile inside its frame by decoupled look-back over the tile status words (one warp).
 __device__ __forceinline__ uint32_t tile_lookback(const UnpackArgs& a, uint32_t tile, uint32_t first_tile, uint32_t tile_sum,
                                                   uint32_t lane) {
@@ -545,24 +468,107 @@ __device__ __forceinline__ uint32_t tile_lookback(const UnpackArgs& a, uint32_t 
     unsigned long long st = pack_status(a.epoch, kFlagInclusive, 0);       // before the frame: prefix 0
     if (valid) st = ld_relaxed_u64(status + idx);
     const bool ready = (st >> 34) == a.epoch && ((st >> 32) & 3ull) != 0;
-    const uint32_t ready_mask = __ballot_sync(0xFFFFFFFFu, ready);
-    const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, ready && ((st >> 32) & 3ull) == kFlagInclusive);
+    const uint32_t ready_mask = __ballot_sync(kFull, ready);
+    const uint32_t incl_mask = __ballot_sync(kFull, ready && ((st >> 32) & 3ull) == kFlagInclusive);
     // usable as soon as every predecessor up to the nearest inclusive one (or the whole window) has published
     const uint32_t upto = incl_mask ? (uint32_t)(__ffs(incl_mask) - 1) : 31u;
-    const uint32_t need = upto == 31u ? 0xFFFFFFFFu : ((2u << upto) - 1u);
+    const uint32_t need = upto == 31u ? kFull : ((2u << upto) - 1u);
     if ((ready_mask & need) != need) {
       if (++spins > (1u << 22)) { if (lane == 0) atomicExch(a.err, 11); break; }   // watchdog: never hang the GPU
       __nanosleep(20);
       continue;
     }
     const uint32_t v = lane <= upto ? (uint32_t)(st & 0xFFFFFFFFull) : 0u;
-    excl += __reduce_add_sync(0xFFFFFFFFu, v);
+    excl += __reduce_add_sync(kFull, v);
     if (incl_mask) break;
     look -= 32;
   }
   if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagInclusive, excl + tile_sum));
   return excl;
 }
+
+// ---- copy-out of one warp's staged run ---------------------------------------------------------------------------------
+// The run starts at point `run_base` of its frame slab (slabs are 16-byte aligned and hold a multiple of 16 points).
+// Packed output is written in aligned groups: 8 points = 48 B = three 16-byte vectors for positions (a group starts at a
+// point index that is a multiple of 8), 16 points = 48 B for colours (multiple of 16).  One lane assembles one group
+// from the padded staging with byte permutes; the few points before the first / after the last full group go out as
+// 2-byte / 1-byte stores.
+__device__ __forceinline__ void copy_out_pos(uint16_t* __restrict__ gpos /* frame slab */, uint32_t run_base, uint32_t total,
+                                             const uint8_t* s_pos, uint32_t lane) {
+  const uint32_t head = min(total, (0u - run_base) & 7u);
+  const uint32_t groups = (total - head) >> 3;
+  const uint32_t tail0 = head + (groups << 3);                  // first point of the tail
+  for (uint32_t g = lane; g < groups; g += 32) {
+    const uint32_t k0 = head + (g << 3);
+    // staged points k0 .. k0+7: slots are consecutive except for one pad slot after every 8th staged point
+    const uint32_t base = spos_off(k0);
+    const uint32_t brk = 8u - (k0 & 7u);                          // points at local index >= brk sit one slot further
+    uint2 p[8];
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i)
+      p[i] = *reinterpret_cast<const uint2*>(s_pos + base + i * 8u + (i >= brk ? 8u : 0u));
+    // stream words: A(P) = x|y<<16 ; B(P,Pn) = z | Pn.x << 16 ; C(P) = y | z << 16   (two points = three words)
+    uint4 v0, v1, v2;
+    v0.x = p[0].x;                                    v0.y = __byte_perm(p[0].y, p[1].x, 0x5410);
+    v0.z = __byte_perm(p[1].x, p[1].y, 0x5432);      v0.w = p[2].x;
+    v1.x = __byte_perm(p[2].y, p[3].x, 0x5410);      v1.y = __byte_perm(p[3].x, p[3].y, 0x5432);
+    v1.z = p[4].x;                                    v1.w = __byte_perm(p[4].y, p[5].x, 0x5410);
+    v2.x = __byte_perm(p[5].x, p[5].y, 0x5432);      v2.y = p[6].x;
+    v2.z = __byte_perm(p[6].y, p[7].x, 0x5410);      v2.w = __byte_perm(p[7].x, p[7].y, 0x5432);
+    uint4* dst = reinterpret_cast<uint4*>(gpos + (uint64_t)(run_base + k0) * 3);
+    stg_cs_v4(dst, v0); stg_cs_v4(dst + 1, v1); stg_cs_v4(dst + 2, v2);
+  }
+  const uint32_t n16 = 3u * (head + (total - tail0));           // u16 elements outside full groups (<= 42)
+  for (uint32_t i = lane; i < n16; i += 32) {
+    const uint32_t pt = i / 3u, c = i - pt * 3u;
+    const uint32_t k = pt < head ? pt : tail0 + (pt - head);
+    gpos[(uint64_t)(run_base + k) * 3 + c] = *reinterpret_cast<const uint16_t*>(s_pos + spos_off(k) + c * 2u);
+  }
+}
+__device__ __forceinline__ void copy_out_rgb(uint8_t* __restrict__ grgb /* frame slab */, uint32_t run_base, uint32_t total,
+                                             const uint8_t* s_rgb, uint32_t lane) {
+  const uint32_t head = min(total, (0u - run_base) & 15u);
+  const uint32_t groups = (total - head) >> 4;
+  const uint32_t tail0 = head + (groups << 4);
+  for (uint32_t g = lane; g < groups; g += 32) {
+    const uint32_t k0 = head + (g << 4);
+    const uint32_t base = srgb_off(k0);
+    const uint32_t brk = 16u - (k0 & 15u);
+    uint32_t p[16];
+#pragma unroll
+    for (uint32_t i = 0; i < 16; ++i)
+      p[i] = *reinterpret_cast<const uint32_t*>(s_rgb + base + i * 4u + (i >= brk ? 4u : 0u));
+    // four points (r,g,b,0 each) = three stream words
+    uint32_t w[12];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      w[3 * q + 0] = __byte_perm(p[4 * q + 0], p[4 * q + 1], 0x4210);
+      w[3 * q + 1] = __byte_perm(p[4 * q + 1], p[4 * q + 2], 0x5421);
+      w[3 * q + 2] = __byte_perm(p[4 * q + 2], p[4 * q + 3], 0x6542);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(grgb + (uint64_t)(run_base + k0) * 3);
+    stg_cs_v4(dst, make_uint4(w[0], w[1], w[2], w[3]));
+    stg_cs_v4(dst + 1, make_uint4(w[4], w[5], w[6], w[7]));
+    stg_cs_v4(dst + 2, make_uint4(w[8], w[9], w[10], w[11]));
+  }
+  const uint32_t n8 = 3u * (head + (total - tail0));            // bytes outside full groups (<= 90)
+  for (uint32_t i = lane; i < n8; i += 32) {
+    const uint32_t pt = i / 3u, c = i - pt * 3u;
+    const uint32_t k = pt < head ? pt : tail0 + (pt - head);
+    grgb[(uint64_t)(run_base + k) * 3 + c] = s_rgb[srgb_off(k) + c];
+  }
+}
+
+// ---- smoothing: geometry cell statistics of one slot, aggregated in registers ------------------------------------------
+// Every lane holds up to 16 points (8 pixels x 2 maps) as (key, packed contribution).  Rounds: each lane takes its
+// smallest remaining cell key, sums its own matching points, then lanes that hold the same key merge along a butterfly
+// (rows of a cell are neighbouring lanes), and whoever still holds a non-zero count issues the reductions.  Exact for
+// any input: a failed merge only means two reductions instead of one.
+struct GeoLaneCtx {
+  uint32_t shN, shT, shB;      // bit position (0, 10, 20) of the normal / tangent / bitangent cell index inside a key
+};
+
+template <bool kSmooth, bool kDebug> struct UnpackTraits { static constexpr int kMinCtas = (kSmooth || kDebug) ? 2 : 3; };
 
 // kMode 0: fused single pass (chained scan) ; 1: count only ; 2: emit with tile bases.  kDebug adds the streams the
 // reference materialises but nobody downstream needs (colors16bit, partition, point_to_pixel, boundary types).
@@ -571,10 +577,11 @@ __device__ __forceinline__ uint32_t tile_lookback(const UnpackArgs& a, uint32_t 
 // in shared memory BEFORE the tile's base is known; the first warp that gets that far claims the look-back, publishes the
 // base, and everybody copies out.  Look-back latency therefore overlaps the other warps' staging work.
 template <int kMode, bool kSmooth, bool kDebug>
-__global__ void __launch_bounds__(kWarpsPerTile * 32, (kSmooth || kDebug) ? (TMC2_MIN_CTAS * 8 / kWarpsPerTile * 2 / 3) : (TMC2_MIN_CTAS * 8 / kWarpsPerTile))
+__global__ void __launch_bounds__(kWarpsPerTile * 32, UnpackTraits<kSmooth, kDebug>::kMinCtas)
 unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_tot[kWarpsPerTile];
+  __shared__ uint32_t s_nlog[kWarpsPerTile][2];
   __shared__ uint32_t s_posted, s_claim, s_ready, s_base;
 
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
@@ -586,11 +593,15 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   const uint32_t res = a.res;
   __syncthreads();                                               // the only block-wide barrier
 
+  uint8_t* wsm = smem + (size_t)warp * kWarpSmemBytes;
+  uint8_t* s_pos = wsm;
+  uint8_t* s_rgb = wsm + kStagePosBytes;
+  uint32_t* s_bmp = reinterpret_cast<uint32_t*>(wsm + kStagePosBytes + kStageRgbBytes);
+
   DevPatch P;
-  bool owned = false, cand = false;
+  bool owned = false, fast = false;
   int32_t bx = 0, by = 0;
   uint32_t u0b = 0, v0b = 0;
-  const uint32_t* b2p_ptr = nullptr;
   if (pid != kNoPatch) {
     P = a.patches[pid];
     const uint32_t s = slot - P.slot_base;
@@ -598,92 +609,154 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
     int64_t bxx, byy;
     patch_to_canvas(P, u0b, v0b, 1, 1, bxx, byy);                 // codec.rs:373-378
     bx = (int32_t)bxx; by = (int32_t)byy;
-    b2p_ptr = a.block_to_patch + (uint64_t)frame * a.bw * a.bh + (uint64_t)by * a.bw + bx;
-    cand = res == 16 && (a.spec_orientation || P.orient <= 1 || P.orient == 8);
+    owned = __ldg(a.block_to_patch + (uint64_t)frame * a.bw * a.bh + (uint64_t)by * a.bw + bx) == P.local_index + 1;   // codec.rs:379
+    fast = owned && res == 16 && a.prec_shift >= 0 && P.aligned;
   }
   const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
 
-  // ---- phase 1: load the block, decide which pixels emit 1 or 2 points ------------------------------------------
-  uint32_t nn[8];                                          // fast path: n0 | n1 << 16 of this lane's 8 pixels
-  uint4 ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
-  uint2 ua = {0, 0}, va = {0, 0}, ub = {0, 0}, vb = {0, 0};
-  uint32_t m1 = 0, m2 = 0;     // fast path: bit j set = pixel j of this lane emits >=1 / 2 points
-  uint32_t total = 0;
-  const int32_t px = bx * 16 + (int32_t)(lane & 1) * 8;   // fast path: this lane's 8 canvas pixels (px..px+7, py)
-  const int32_t py = by * 16 + (int32_t)(lane >> 1);
-  bool fast = false;
+  // smoothing: this slot's log regions (table slots it added to); every slot of the group writes its counts
+  const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
+  uint32_t* log_geo = nullptr; uint32_t* log_col = nullptr;
+  uint32_t n_log_geo = 0, n_log_col = 0;
+  if (kSmooth) {
+    const uint64_t ls = (uint64_t)(slot - a.sm.group_first_slot) * a.sm.log_stride;
+    if (a.sm.geo.on) log_geo = a.sm.geo.log + ls;
+    if (a.sm.col.on) log_col = a.sm.col.log + ls;
+  }
 
-  if (cand) {
-    // plane loads are issued before the ownership answer arrives (one less dependent round trip); an unowned block
-    // (a later patch took the canvas block, codec.rs:379) just drops them
-    const uint32_t owner = __ldg(b2p_ptr);
+  // ---- phase 1: load the block, decide which pixels emit 1 or 2 points ------------------------------------------
+  const int32_t h = (int32_t)(lane & 1u), r = (int32_t)(lane >> 1);
+  uint32_t nn[8];                        // n0 | n1 << 16 per pixel
+  uint32_t yy[8];                        // attribute Y of map 0 | map 1 << 16 per pixel
+  uint32_t cA[4], cB[4];                 // chroma of map 0 / map 1 per pixel pair: U | V << 16
+  uint32_t m1 = 0, m2 = 0;               // bit j set = pixel j of this lane emits >= 1 / 2 points
+  uint32_t total = 0, lane_excl = 0;
+  int32_t xs = 0, ys = 0;                // canvas position of this lane's pixel 0; pixel j is (xs + ax*j, ys + ay*j)
+  const int32_t ax = pid != kNoPatch ? P.ax : 0, ay = pid != kNoPatch ? P.ay : 0;
+
+  if (fast) {
+    const int32_t cx0 = bx * 16 + ((P.ax < 0 || P.rx < 0) ? 15 : 0);
+    const int32_t cy0 = by * 16 + ((P.ay < 0 || P.ry < 0) ? 15 : 0);
+    xs = cx0 + P.ax * 8 * h + P.rx * r;
+    ys = cy0 + P.ay * 8 * h + P.ry * r;
     const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
-    const uint64_t goff = (uint64_t)py * a.in.geo_pitch + px;
-    const uint4 g0 = ldg_nc_v4(geo0 + goff);
-    const uint4 g1 = ldg_nc_v4(geo0 + a.in.geo_map_stride + goff);
-    if (kMode != 1 && a.has_attr) {
-      const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride;
-      const uint64_t yoff = (uint64_t)py * a.in.attr_pitch_y + px;
-      ya = ldg_nc_v4(ay0 + yoff);
-      yb = ldg_nc_v4(ay0 + a.in.attr_y_map_stride + yoff);
-      const uint64_t coff = (uint64_t)(py >> 1) * a.in.attr_pitch_c + (px >> 1);
-      const uint64_t cf = (uint64_t)frame * 2 * a.in.attr_c_map_stride;
-      ua = ldg_nc_v2(a.in.attr_u + cf + coff);
-      va = ldg_nc_v2(a.in.attr_v + cf + coff);
-      ub = ldg_nc_v2(a.in.attr_u + cf + a.in.attr_c_map_stride + coff);
-      vb = ldg_nc_v2(a.in.attr_v + cf + a.in.attr_c_map_stride + coff);
-    }
-    // occupancy bits of the 8 pixels (codec.rs:393-396: any non-zero sample counts)
-    uint32_t occ_bits = 0;
-    {
-      const uint8_t* row = occ_f + (uint64_t)div_prec((uint32_t)py, a.prec, a.prec_shift) * a.in.occ_pitch;
-      uint32_t prev_c = 0xFFFFFFFFu, prev_v = 0;
+    const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
+    const bool attr = kMode != 1 && a.has_attr;
+    const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride;
+    const uint16_t* ay1 = ay0 + a.in.attr_y_map_stride;
+    const uint64_t cf = (uint64_t)frame * 2 * a.in.attr_c_map_stride;
+    const uint16_t* au0 = a.in.attr_u + cf; const uint16_t* au1 = au0 + a.in.attr_c_map_stride;
+    const uint16_t* av0 = a.in.attr_v + cf; const uint16_t* av1 = av0 + a.in.attr_c_map_stride;
+    if (ax == 1) {
+      // Default-like rows: the 8 pixels are 16 contiguous bytes of every plane
+      const uint32_t goff = (uint32_t)ys * a.in.geo_pitch + (uint32_t)xs;
+      const uint4 g0 = ldg_nc_v4(geo0 + goff);
+      const uint4 g1 = ldg_nc_v4(geo1 + goff);
+      uint4 ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
+      uint2 ua = {0, 0}, va = {0, 0}, ub = {0, 0}, vb = {0, 0};
+      if (attr) {
+        const uint32_t yoff = (uint32_t)ys * a.in.attr_pitch_y + (uint32_t)xs;
+        ya = ldg_nc_v4(ay0 + yoff); yb = ldg_nc_v4(ay1 + yoff);
+        const uint32_t coff = (uint32_t)(ys >> 1) * a.in.attr_pitch_c + (uint32_t)(xs >> 1);
+        ua = ldg_nc_v2(au0 + coff); va = ldg_nc_v2(av0 + coff);
+        ub = ldg_nc_v2(au1 + coff); vb = ldg_nc_v2(av1 + coff);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint32_t c = div_prec((uint32_t)px + j, a.prec, a.prec_shift);
-        if (c != prev_c) { prev_c = c; prev_v = row[c]; }
-        occ_bits |= (prev_v != 0 ? 1u : 0u) << j;
+        const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+        nn[j] = __byte_perm(word_of(g0, j >> 1), word_of(g1, j >> 1), sel);      // raw samples, converted below
+        yy[j] = __byte_perm(word_of(ya, j >> 1), word_of(yb, j >> 1), sel);
       }
-    }
-    owned = owner == P.local_index + 1;                           // codec.rs:379
-    fast = owned;
-    if (owned) {
-      m1 = occ_bits;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t sel = (c & 1) ? 0x7632u : 0x5410u;
+        cA[c] = __byte_perm(word_of(ua, c >> 1), word_of(va, c >> 1), sel);
+        cB[c] = __byte_perm(word_of(ub, c >> 1), word_of(vb, c >> 1), sel);
+      }
+    } else {
+      // transposed / mirrored: eight 2-byte loads per plane; across the warp every load still covers whole 32-byte sectors
+      const int32_t dstep = ay * (int32_t)a.in.geo_pitch + ax;
+      const int32_t goff = ys * (int32_t)a.in.geo_pitch + xs;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        nn[j] = normals_of(P, u16_of(g0, j), u16_of(g1, j), a.absolute_d1);
-        if ((nn[j] >> 16) != (nn[j] & 0xFFFFu)) m2 |= (occ_bits & (1u << j));   // codec.rs:422-428 duplicate skip
+        const int32_t o = goff + j * dstep;
+        nn[j] = ldg_nc_u16(geo0 + o) | (ldg_nc_u16(geo1 + o) << 16);
       }
-    }
-    total = __reduce_add_sync(0xFFFFFFFFu, __popc(m1) + __popc(m2));
-  } else if (pid != kNoPatch) {
-    owned = __ldg(b2p_ptr) == P.local_index + 1;
-    if (owned) {
-      // generic path (any resolution, reference-literal rotated orientations): lane = pixel, 32 at a time
-      const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
-      const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
-      const int64_t sscale = a.spec_orientation ? res : 1;
-      for (uint32_t base = 0; base < res * res; base += 32) {
-        const uint32_t i = base + lane;
-        uint32_t c = 0;
-        if (i < res * res) {
-          const uint32_t v1 = i / res, u1 = i - v1 * res;
-          int64_t x, y;
-          patch_to_canvas(P, (int64_t)u0b * res + u1, (int64_t)v0b * res + v1, res, sscale, x, y);
-          if (occ_at(a, occ_f, (uint32_t)x, (uint32_t)y)) {
-            const uint64_t off = (uint64_t)y * a.in.geo_pitch + (uint64_t)x;
-            const uint32_t n = normals_of(P, geo0[off], geo1[off], a.absolute_d1);
-            c = (n >> 16) != (n & 0xFFFFu) ? 2u : 1u;
-          }
+      if (attr) {
+        const int32_t ystep = ay * (int32_t)a.in.attr_pitch_y + ax;
+        const int32_t yoff = ys * (int32_t)a.in.attr_pitch_y + xs;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int32_t o = yoff + j * ystep;
+          yy[j] = ldg_nc_u16(ay0 + o) | (ldg_nc_u16(ay1 + o) << 16);
         }
-        total += __reduce_add_sync(0xFFFFFFFFu, c);
+        const int32_t cstep = ay * (int32_t)a.in.attr_pitch_c + ax;
+        const int32_t coff = (ys >> 1) * (int32_t)a.in.attr_pitch_c + (xs >> 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int32_t o = coff + c * cstep;
+          cA[c] = ldg_nc_u16(au0 + o) | (ldg_nc_u16(av0 + o) << 16);
+          cB[c] = ldg_nc_u16(au1 + o) | (ldg_nc_u16(av1 + o) << 16);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yy[j] = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { cA[c] = 0; cB[c] = 0; }
       }
+    }
+    // occupancy of the 8 pixels (codec.rs:393-396: any non-zero sample counts).  Pixels j*p .. j*p+p-1 share a sample.
+    {
+      const int32_t lp = a.prec_shift;
+      const int32_t p = 1 << lp;
+      const int32_t nb = lp >= 3 ? 1 : (8 >> lp);
+      const uint32_t ones = lp >= 3 ? 0xFFu : ((1u << p) - 1u);
+      for (int32_t k = 0; k < nb; ++k) {
+        const int32_t j = k << lp;
+        const uint32_t ox = (uint32_t)(xs + ax * j) >> lp, oy = (uint32_t)(ys + ay * j) >> lp;
+        if (occ_f[(uint64_t)oy * a.in.occ_pitch + ox] != 0) m1 |= ones << j;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      nn[j] = normals_of(P, nn[j] & 0xFFFFu, nn[j] >> 16, a.absolute_d1);
+      if ((nn[j] >> 16) != (nn[j] & 0xFFFFu)) m2 |= (m1 & (1u << j));            // codec.rs:422-428 duplicate skip
+    }
+    const uint32_t c = __popc(m1) + __popc(m2);
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    total = __shfl_sync(kFull, incl, 31);
+    lane_excl = incl - c;
+  } else if (owned) {
+    // generic path (any resolution, reference-literal rotated orientations): lane = pixel, 32 at a time
+    const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
+    const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
+    const int64_t sscale = a.spec_orientation ? res : 1;
+    for (uint32_t base = 0; base < res * res; base += 32) {
+      const uint32_t i = base + lane;
+      uint32_t c = 0;
+      if (i < res * res) {
+        const uint32_t v1 = i / res, u1 = i - v1 * res;
+        int64_t x, y;
+        patch_to_canvas(P, (int64_t)u0b * res + u1, (int64_t)v0b * res + v1, res, sscale, x, y);
+        if (occ_at(a, occ_f, (uint32_t)x, (uint32_t)y)) {
+          const uint64_t off = (uint64_t)y * a.in.geo_pitch + (uint64_t)x;
+          const uint32_t n = normals_of(P, geo0[off], geo1[off], a.absolute_d1);
+          c = (n >> 16) != (n & 0xFFFFu) ? 2u : 1u;
+        }
+      }
+      total += __reduce_add_sync(kFull, c);
     }
   }
 
   // post this slot's count
   if (lane == 0) {
     s_tot[warp] = total;
+    s_nlog[warp][0] = 0; s_nlog[warp][1] = 0;
     __threadfence_block();
     const uint32_t prev = atomicAdd(&s_posted, 1u);
     if (kMode == 1 && prev == kWarpsPerTile - 1) {               // count-only launch: the last poster sums the tile
@@ -696,128 +769,225 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   if (kMode == 1) return;
 
   // ---- phase 2a: stage the run in shared memory (needs only warp-local offsets) -----------------------------------
-  uint8_t* wsm = smem + (size_t)warp * a.warp_bytes;
-  uint8_t* cnt_sm = wsm + a.off_scan;                             // [256] counts by rank
-  uint16_t* pre_sm = reinterpret_cast<uint16_t*>(cnt_sm + 256);   // [256] exclusive prefix by rank
-  uint8_t* s_pos = wsm + a.off_pos;
-  uint8_t* s_rgb = wsm + a.off_rgb;
-  uint8_t* s_yuv = wsm + a.off_yuv;      // smoothing: staged even when not written out
-  uint8_t* s_part = wsm + a.off_part;
-  uint8_t* s_pix = wsm + a.off_pix;
-  uint8_t* s_bt = wsm + a.off_bt;        // smoothing: staged even when not written out
   const bool w_rgb = a.out.rgb != nullptr;
-  const bool w_yuv = kDebug && a.out.yuv != nullptr, w_part = kDebug && a.out.part != nullptr;
-  const bool w_pix = kDebug && a.out.pix != nullptr, w_bt = kDebug && a.out.btype != nullptr;
-  uint32_t n_boundary = 0;
+  const bool want_bt = kSmooth || (kDebug && a.out.btype != nullptr);
+  uint32_t bt1 = 0, bt2 = 0;             // bit j: pixel j is a type-1 / type-2 boundary pixel (meaningful where m1 is set)
+  const uint32_t T0 = ((u0b * 16u + 8u * (uint32_t)h) * P.lod_x + P.u1);                  // decoder.rs:875 at j = 0
+  const uint32_t Bc = ((v0b * 16u + (uint32_t)r) * P.lod_y + P.v1) & 0xFFFFu;            // decoder.rs:876
+
   if (fast && total) {
-    // exclusive prefix of the per-pixel counts in PATCH-LOCAL raster order (v1 major, u1 minor; codec.rs:382-385)
-    int32_t pu, pv, pu1, pv1;
-    canvas_to_patch(P, px, py, 16, pu, pv);
-    canvas_to_patch(P, px + 1, py, 16, pu1, pv1);
-    const int32_t su = pu1 - pu, sv = pv1 - pv;                     // patch-space step per canvas pixel
-    const uint32_t rank0 = (uint32_t)((pv & 15) * 16 + (pu & 15));
-    const int32_t rstep = sv * 16 + su;                             // rank step per canvas pixel (no wrap inside a block)
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      cnt_sm[rank0 + j * rstep] = (uint8_t)(((m1 >> j) & 1u) + ((m2 >> j) & 1u));
-    __syncwarp();
-    {
-      const uint2 c8 = *reinterpret_cast<const uint2*>(cnt_sm + lane * 8);
-      uint32_t c[8] = {c8.x & 255u, (c8.x >> 8) & 255u, (c8.x >> 16) & 255u, c8.x >> 24,
-                       c8.y & 255u, (c8.y >> 8) & 255u, (c8.y >> 16) & 255u, c8.y >> 24};
-      uint32_t sum = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sum += c[j];
-      uint32_t incl = sum;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= (uint32_t)d) incl += t;
-      }
-      uint32_t run = incl - sum;
-      uint32_t o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { o[j] = run; run += c[j]; }
-      uint4 packed;
-      packed.x = o[0] | (o[1] << 16); packed.y = o[2] | (o[3] << 16);
-      packed.z = o[4] | (o[5] << 16); packed.w = o[6] | (o[7] << 16);
-      *reinterpret_cast<uint4*>(pre_sm + lane * 8) = packed;
-    }
-    __syncwarp();
-
-    const bool st_yuv = a.has_attr && (w_yuv || kSmooth);
-    const bool st_bt = w_bt || kSmooth;
-    // generate_point (decoder.rs:871-878) stores normal, tangent, bitangent in that order: byte offsets inside a point.
-    // Axes that are not a permutation leave a coordinate at 0 (and let later stores overwrite earlier ones).
-    const uint32_t o_n = 2u * P.normal, o_t = 2u * P.tangent, o_b = 2u * P.bitangent;
-    const bool perm = ((1u << P.normal) | (1u << P.tangent) | (1u << P.bitangent)) == 7u;
-
+    // generate_point (decoder.rs:871-878) stores normal, tangent, bitangent in that order; the selectors reproduce
+    // "later stores overwrite earlier ones" and leave unset coordinates at 0
+    const uint32_t s0 = sel_of_src(axis_source(P, 0)), s1 = sel_of_src(axis_source(P, 1)), s2 = sel_of_src(axis_source(P, 2));
+    const uint32_t selA = s0 | (s1 << 8), selB = s2 | 0x7600u;
+    uint32_t k = lane_excl;
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {                                            // chroma column: pixels 2cc, 2cc+1
       if (!((m1 >> (2 * cc)) & 3u)) continue;
       ChromaTerm ta, tb;
-      uint32_t Ua = 0, Va = 0, Ub = 0, Vb = 0;
-      if (a.has_attr) {
-        Ua = u16_of(ua, cc); Va = u16_of(va, cc); Ub = u16_of(ub, cc); Vb = u16_of(vb, cc);   // decoder.rs:976-977
-        if (w_rgb) { ta = chroma_term(Ua, Va); tb = chroma_term(Ub, Vb); }
-      }
+      const uint32_t Ua = cA[cc] & 0xFFFFu, Va = cA[cc] >> 16, Ub = cB[cc] & 0xFFFFu, Vb = cB[cc] >> 16;   // decoder.rs:976-977
+      if (w_rgb) { ta = chroma_term(Ua, Va); tb = chroma_term(Ub, Vb); }
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
         const int j = 2 * cc + jj;
         if (!((m1 >> j) & 1u)) continue;
-        const int32_t u = pu + j * su, v = pv + j * sv;
-        const uint32_t k0 = pre_sm[rank0 + j * rstep];
-        const uint32_t t = (uint32_t)u * P.lod_x + P.u1;                          // decoder.rs:875 (stored as u16)
-        const uint32_t b = (uint32_t)v * P.lod_y + P.v1;                          // decoder.rs:876
-        const bool two = (m2 >> j) & 1u;
-        uint32_t bt = 0;
-        if (st_bt) { bt = boundary_type(a, occ_f, px + j, py); n_boundary += bt == 1u ? (two ? 2u : 1u) : 0u; }
+        const uint32_t t = (T0 + (uint32_t)j * P.lod_x) & 0xFFFFu;
         {                                                                         // map 0 (codec.rs:421, i == 0)
-          uint8_t* d = s_pos + k0 * 6;
-          if (!perm) { reinterpret_cast<uint16_t*>(d)[0] = 0; reinterpret_cast<uint16_t*>(d)[1] = 0; reinterpret_cast<uint16_t*>(d)[2] = 0; }
-          *reinterpret_cast<uint16_t*>(d + o_n) = (uint16_t)nn[j];
-          *reinterpret_cast<uint16_t*>(d + o_t) = (uint16_t)t;
-          *reinterpret_cast<uint16_t*>(d + o_b) = (uint16_t)b;
-          if (a.has_attr) {
-            const uint32_t Y = u16_of(ya, j);                                     // codec.rs:637-640
-            if (st_yuv) { uint16_t* q = reinterpret_cast<uint16_t*>(s_yuv + k0 * 6); q[0] = (uint16_t)Y; q[1] = (uint16_t)Ua; q[2] = (uint16_t)Va; }
-            if (w_rgb) {
-              const uint32_t c = yuv_to_rgb_term(Y, Ua, Va, ta);
-              uint8_t* q = s_rgb + k0 * 3; q[0] = (uint8_t)c; q[1] = (uint8_t)(c >> 8); q[2] = (uint8_t)(c >> 16);
-            }
-          }
-          if (w_part) *reinterpret_cast<uint16_t*>(s_part + k0 * 2) = (uint16_t)P.local_index;   // codec.rs:452
-          if (w_pix) *reinterpret_cast<uint32_t*>(s_pix + k0 * 4) = (uint32_t)(px + j) | ((uint32_t)py << 15);
-          if (st_bt) s_bt[k0] = (uint8_t)bt;
+          const uint32_t A = (nn[j] & 0xFFFFu) | (t << 16);
+          *reinterpret_cast<uint2*>(s_pos + spos_off(k)) = make_uint2(__byte_perm(A, Bc, selA), __byte_perm(A, Bc, selB));
+          if (w_rgb) *reinterpret_cast<uint32_t*>(s_rgb + srgb_off(k)) = yuv_to_rgb_term(yy[j] & 0xFFFFu, Ua, Va, ta);   // codec.rs:637-640
+          ++k;
         }
-        if (two) {                                                                // map 1 unless it duplicates map 0
-          const uint32_t k1 = k0 + 1;
-          uint8_t* d = s_pos + k1 * 6;
-          if (!perm) { reinterpret_cast<uint16_t*>(d)[0] = 0; reinterpret_cast<uint16_t*>(d)[1] = 0; reinterpret_cast<uint16_t*>(d)[2] = 0; }
-          *reinterpret_cast<uint16_t*>(d + o_n) = (uint16_t)(nn[j] >> 16);
-          *reinterpret_cast<uint16_t*>(d + o_t) = (uint16_t)t;
-          *reinterpret_cast<uint16_t*>(d + o_b) = (uint16_t)b;
-          if (a.has_attr) {
-            const uint32_t Y = u16_of(yb, j);
-            if (st_yuv) { uint16_t* q = reinterpret_cast<uint16_t*>(s_yuv + k1 * 6); q[0] = (uint16_t)Y; q[1] = (uint16_t)Ub; q[2] = (uint16_t)Vb; }
-            if (w_rgb) {
-              const uint32_t c = yuv_to_rgb_term(Y, Ub, Vb, tb);
-              uint8_t* q = s_rgb + k1 * 3; q[0] = (uint8_t)c; q[1] = (uint8_t)(c >> 8); q[2] = (uint8_t)(c >> 16);
-            }
-          }
-          if (w_part) *reinterpret_cast<uint16_t*>(s_part + k1 * 2) = (uint16_t)P.local_index;
-          if (w_pix) *reinterpret_cast<uint32_t*>(s_pix + k1 * 4) = (uint32_t)(px + j) | ((uint32_t)py << 15) | (1u << 30);
-          if (st_bt) s_bt[k1] = (uint8_t)bt;
+        if ((m2 >> j) & 1u) {                                                     // map 1 unless it duplicates map 0
+          const uint32_t A = (nn[j] >> 16) | (t << 16);
+          *reinterpret_cast<uint2*>(s_pos + spos_off(k)) = make_uint2(__byte_perm(A, Bc, selA), __byte_perm(A, Bc, selB));
+          if (w_rgb) *reinterpret_cast<uint32_t*>(s_rgb + srgb_off(k)) = yuv_to_rgb_term(yy[j] >> 16, Ub, Vb, tb);
+          ++k;
         }
       }
     }
+
+    // ---- K5: boundary types from a 20x20 occupancy bitmap of the block and its 2-pixel margin (patch-local axes) ----
+    if (want_bt) {
+      const int32_t W = (int32_t)a.W, H = (int32_t)a.H, lp = a.prec_shift;
+      const int32_t cx0 = xs - P.ax * 8 * h - P.rx * r, cy0 = ys - P.ay * 8 * h - P.ry * r;   // canvas of patch-local (0,0)
+      if (lane < 20) {
+        const int32_t rr = (int32_t)lane - 2;
+        uint32_t bits = 0;
+        int32_t pox = -1, poy = -1; uint32_t pv = 0;
+        for (int32_t cc = 0; cc < 20; ++cc) {
+          const int32_t aa = cc - 2;
+          const int32_t x = cx0 + P.ax * aa + P.rx * rr, y = cy0 + P.ay * aa + P.ry * rr;
+          uint32_t o = 1;                                        // outside the image: ignored by the 5x5 test
+          if (x >= 0 && y >= 0 && x < W && y < H) {
+            const int32_t ox = x >> lp, oy = y >> lp;
+            if (ox != pox || oy != poy) { pox = ox; poy = oy; pv = occ_f[(uint64_t)oy * a.in.occ_pitch + ox]; }
+            o = pv != 0;
+          }
+          bits |= o << cc;
+        }
+        s_bmp[lane] = bits;
+      }
+      __syncwarp();
+      const uint32_t r0 = s_bmp[r], r1 = s_bmp[r + 1], r2 = s_bmp[r + 2], r3 = s_bmp[r + 3], r4 = s_bmp[r + 4];
+      const uint32_t cross = r1 & r3 & (r2 >> 1) & (r2 << 1);    // bit c: the four neighbours of column c are occupied
+      const uint32_t all5 = r0 & r1 & r2 & r3 & r4;
+      const uint32_t full = all5 & (all5 >> 1) & (all5 >> 2) & (all5 << 1) & (all5 << 2);
+      const uint32_t sh = 8u * (uint32_t)h + 2u;
+      uint32_t border = 0;
+      if (bx == 0 || by == 0 || (bx + 1) * 16 >= W || (by + 1) * 16 >= H) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int32_t x = xs + ax * j, y = ys + ay * j;
+          if (x == 0 || y == 0 || x == W - 1 || y == H - 1) border |= 1u << j;
+        }
+      }
+      bt1 = ((~(cross >> sh)) & 0xFFu) | border;
+      bt2 = (~(full >> sh)) & 0xFFu & ~bt1;
+    }
     __syncwarp();
+
+    // ---- K6 statistics: geometry cells over ALL points of the slot ---------------------------------------------------
+    if (kSmooth && a.sm.geo.on) {
+      const GridDesc& G = a.sm.geo;
+      const bool perm = ((1u << P.normal) | (1u << P.tangent) | (1u << P.bitangent)) == 7u;
+      if (perm) {
+        const uint32_t shN = 10u * P.normal, shT = 10u * P.tangent, shB = 10u * P.bitangent;
+        const uint32_t g = G.g;
+        const uint32_t cBc = cell_div(Bc, G), relB = Bc - cBc * g;
+        const bool okB = Bc < G.th;
+        uint32_t key[16], val[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t t = (T0 + (uint32_t)j * P.lod_x) & 0xFFFFu;
+          const uint32_t cT = cell_div(t, G), relT = t - cT * g;
+          const uint32_t kTB = (cT << shT) | (cBc << shB);
+          const bool okTB = okB && t < G.th && ((m1 >> j) & 1u);
+          const uint32_t n0 = nn[j] & 0xFFFFu, n1 = nn[j] >> 16;
+          const uint32_t c0 = cell_div(n0, G), c1 = cell_div(n1, G);
+          key[2 * j] = (okTB && n0 < G.th) ? (kTB | (c0 << shN)) : kCellEmpty;
+          val[2 * j] = 1u | ((n0 - c0 * g) << 5) | (relT << 17);
+          key[2 * j + 1] = (okTB && ((m2 >> j) & 1u) && n1 < G.th) ? (kTB | (c1 << shN)) : kCellEmpty;
+          val[2 * j + 1] = 1u | ((n1 - c1 * g) << 5) | (relT << 17);
+        }
+        uint32_t cur = kCellEmpty;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cur = min(cur, key[i]);
+        while (__any_sync(kFull, cur != kCellEmpty)) {
+          uint32_t acc = 0, nxt = kCellEmpty;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (key[i] == cur) acc += val[i];
+            else if (key[i] > cur) nxt = min(nxt, key[i]);
+          }
+          uint32_t cnt = cur != kCellEmpty ? (acc & 31u) : 0u;
+          uint32_t sN = cnt ? ((acc >> 5) & 0xFFFu) : 0u, sT = cnt ? (acc >> 17) : 0u, sB = cnt * relB;
+          // merge lanes holding the same cell: the other half-row (xor 1) and the neighbouring rows (xor 2..16)
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t ok = __shfl_xor_sync(kFull, cur, d);
+            const uint32_t oc = __shfl_xor_sync(kFull, cnt, d);
+            const uint32_t oN = __shfl_xor_sync(kFull, sN, d);
+            const uint32_t oT = __shfl_xor_sync(kFull, sT, d);
+            const uint32_t oB = __shfl_xor_sync(kFull, sB, d);
+            if (ok == cur && cur != kCellEmpty) {
+              if (lane & (uint32_t)d) { cnt = 0; sN = 0; sT = 0; sB = 0; }
+              else { cnt += oc; sN += oN; sT += oT; sB += oB; }
+            }
+          }
+          const bool fl = cnt != 0;
+          uint32_t cs = kCellEmpty;
+          if (fl) {
+            cs = cell_slot(G, fig, cur, a.err);
+            if (cs != kCellEmpty) {
+              const uint32_t sx = P.normal == 0 ? sN : P.tangent == 0 ? sT : sB;
+              const uint32_t sy = P.normal == 1 ? sN : P.tangent == 1 ? sT : sB;
+              const uint32_t sz = P.normal == 2 ? sN : P.tangent == 2 ? sT : sB;
+              geo_cell_add(G, fig, cs, P.local_index, cnt, sx, sy, sz);
+            }
+          }
+          const uint32_t fm = __ballot_sync(kFull, fl && cs != kCellEmpty);
+          if (fl && cs != kCellEmpty) log_geo[n_log_geo + __popc(fm & ((1u << lane) - 1u))] = cs;
+          n_log_geo += __popc(fm);
+          cur = nxt;
+        }
+      } else {
+        // axes that are not a permutation (never produced by the reference's set_view_id): per-point reductions on the
+        // staged positions
+        for (uint32_t kb = 0; kb < total; kb += 32) {
+          const uint32_t kk = kb + lane;
+          uint32_t cs = kCellEmpty;
+          if (kk < total) {
+            const uint2 pw = *reinterpret_cast<const uint2*>(s_pos + spos_off(kk));
+            const uint32_t X = pw.x & 0xFFFFu, Yc = pw.x >> 16, Z = pw.y & 0xFFFFu;
+            const uint32_t key = cell_key_of(G, X, Yc, Z);
+            if (key != kCellEmpty) {
+              cs = cell_slot(G, fig, key, a.err);
+              if (cs != kCellEmpty)
+                geo_cell_add(G, fig, cs, P.local_index, 1, X - (key & 1023u) * G.g, Yc - ((key >> 10) & 1023u) * G.g, Z - (key >> 20) * G.g);
+            }
+          }
+          const uint32_t fm = __ballot_sync(kFull, cs != kCellEmpty);
+          if (cs != kCellEmpty) log_geo[n_log_geo + __popc(fm & ((1u << lane) - 1u))] = cs;
+          n_log_geo += __popc(fm);
+        }
+      }
+    }
+
+    // ---- K7 statistics: colour cells over the type-2 (second ring) points ----------------------------------------------
+    if (kSmooth && a.sm.col.on && a.has_attr) {
+      const GridDesc& G = a.sm.col;
+      const uint32_t sel_mask = m1 & bt2;
+      if (__any_sync(kFull, sel_mask != 0)) {
+        uint32_t k = lane_excl;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          const bool on = (m1 >> j) & 1u, two = (m2 >> j) & 1u;
+          const bool sel = (sel_mask >> j) & 1u;
+          uint32_t cs0 = kCellEmpty, cs1 = kCellEmpty;
+          if (sel) {
+            const uint32_t U0 = cA[j >> 1] & 0xFFFFu, V0 = cA[j >> 1] >> 16, U1 = cB[j >> 1] & 0xFFFFu, V1 = cB[j >> 1] >> 16;
+            const uint32_t Y0 = yy[j] & 0xFFFFu, Y1 = yy[j] >> 16;
+            const uint2 p0 = *reinterpret_cast<const uint2*>(s_pos + spos_off(k));
+            const uint32_t key0 = cell_key_of(G, p0.x & 0xFFFFu, p0.x >> 16, p0.y & 0xFFFFu);
+            uint32_t key1 = kCellEmpty;
+            if (two) {
+              const uint2 p1 = *reinterpret_cast<const uint2*>(s_pos + spos_off(k + 1));
+              key1 = cell_key_of(G, p1.x & 0xFFFFu, p1.x >> 16, p1.y & 0xFFFFu);
+            }
+            if (key0 != kCellEmpty) {
+              cs0 = cell_slot(G, fig, key0, a.err);
+              if (cs0 != kCellEmpty) {
+                if (key1 == key0) {
+                  col_cell_add(G, fig, cs0, P.local_index, 2, Y0 + Y1, U0 + U1, V0 + V1,
+                               (unsigned long long)Y0 * Y0 + (unsigned long long)Y1 * Y1);
+                  key1 = kCellEmpty;
+                } else {
+                  col_cell_add(G, fig, cs0, P.local_index, 1, Y0, U0, V0, (unsigned long long)Y0 * Y0);
+                }
+              }
+            }
+            if (key1 != kCellEmpty) {
+              cs1 = cell_slot(G, fig, key1, a.err);
+              if (cs1 != kCellEmpty) col_cell_add(G, fig, cs1, P.local_index, 1, Y1, U1, V1, (unsigned long long)Y1 * Y1);
+            }
+          }
+          const uint32_t f0 = __ballot_sync(kFull, cs0 != kCellEmpty);
+          if (cs0 != kCellEmpty) log_col[n_log_col + __popc(f0 & ((1u << lane) - 1u))] = cs0;
+          n_log_col += __popc(f0);
+          const uint32_t f1 = __ballot_sync(kFull, cs1 != kCellEmpty);
+          if (cs1 != kCellEmpty) log_col[n_log_col + __popc(f1 & ((1u << lane) - 1u))] = cs1;
+          n_log_col += __popc(f1);
+          k += (on ? 1u : 0u) + (two ? 1u : 0u);
+        }
+      }
+    }
   }
 
   // ---- tile base: the first warp to get here does the look-back for the whole tile --------------------------------
   uint32_t claim = 0;
   if (lane == 0) claim = atomicAdd(&s_claim, 1u);
-  claim = __shfl_sync(0xFFFFFFFFu, claim, 0);
+  claim = __shfl_sync(kFull, claim, 0);
   if (claim == 0) {
     while (*reinterpret_cast<volatile uint32_t*>(&s_posted) < (uint32_t)kWarpsPerTile) { }
     __threadfence_block();
@@ -833,7 +1003,13 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
       *reinterpret_cast<volatile uint32_t*>(&s_ready) = 1u;
     }
   }
-  if (!owned || total == 0) return;
+  if (!owned || total == 0) {
+    if (kSmooth && lane == 0) {
+      if (a.sm.geo.on) a.sm.geo.log_count[slot - a.sm.group_first_slot] = 0;
+      if (a.sm.col.on) a.sm.col.log_count[slot - a.sm.group_first_slot] = 0;
+    }
+    return;
+  }
   while (*reinterpret_cast<volatile uint32_t*>(&s_ready) == 0u) { }
   __threadfence_block();
   uint32_t run_base = *reinterpret_cast<volatile uint32_t*>(&s_base);
@@ -843,56 +1019,86 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
     return;
   }
   const uint64_t gidx = (uint64_t)frame * a.out.cap + run_base;   // first point of this run
-  const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
 
   // ---- phase 2b: copy-out ---------------------------------------------------------------------------------------------
   if (!fast) {
-    generic_slot_emit<kSmooth, kDebug>(a, P, frame, fig, u0b, v0b, gidx);
+    __syncwarp();
+    generic_slot_emit<kSmooth, kDebug>(a, P, frame, fig, u0b, v0b, gidx, log_geo, log_col, &s_nlog[warp][0]);
+    __syncwarp();
+    if (kSmooth && lane == 0) {
+      if (a.sm.geo.on) a.sm.geo.log_count[slot - a.sm.group_first_slot] = reinterpret_cast<volatile uint32_t*>(&s_nlog[warp][0])[0];
+      if (a.sm.col.on) a.sm.col.log_count[slot - a.sm.group_first_slot] = reinterpret_cast<volatile uint32_t*>(&s_nlog[warp][0])[1];
+    }
     return;
   }
-  warp_copy_out(reinterpret_cast<uint8_t*>(a.out.pos) + gidx * 6, s_pos, total * 6, lane);
-  if (w_rgb) warp_copy_out(a.out.rgb + gidx * 3, s_rgb, total * 3, lane);
-  if (w_yuv) warp_copy_out(reinterpret_cast<uint8_t*>(a.out.yuv) + gidx * 6, s_yuv, total * 6, lane);
-  if (w_part) warp_copy_out(reinterpret_cast<uint8_t*>(a.out.part) + gidx * 2, s_part, total * 2, lane);
-  if (w_pix) warp_copy_out(reinterpret_cast<uint8_t*>(a.out.pix) + gidx * 4, s_pix, total * 4, lane);
-  if (w_bt) warp_copy_out(a.out.btype + gidx, s_bt, total, lane);
+  copy_out_pos(a.out.pos + (uint64_t)frame * a.out.cap * 3, run_base, total, s_pos, lane);
+  if (w_rgb) copy_out_rgb(a.out.rgb + (uint64_t)frame * a.out.cap * 3, run_base, total, s_rgb, lane);
+
+  if (kDebug) {                                                    // streams only the stage API / tests ask for
+    uint64_t k = gidx + lane_excl;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      if (!((m1 >> j) & 1u)) continue;
+      const uint32_t np = 1u + ((m2 >> j) & 1u);
+      const uint32_t x = (uint32_t)(xs + ax * j), y = (uint32_t)(ys + ay * j);
+      const uint32_t bt = ((bt1 >> j) & 1u) ? 1u : ((bt2 >> j) & 1u) ? 2u : 0u;
+      for (uint32_t m = 0; m < np; ++m, ++k) {
+        if (a.out.yuv && a.has_attr) {
+          uint16_t* q = a.out.yuv + k * 3;
+          q[0] = (uint16_t)(m ? yy[j] >> 16 : yy[j] & 0xFFFFu);
+          q[1] = (uint16_t)(m ? cB[j >> 1] & 0xFFFFu : cA[j >> 1] & 0xFFFFu);
+          q[2] = (uint16_t)(m ? cB[j >> 1] >> 16 : cA[j >> 1] >> 16);
+        }
+        if (a.out.part) a.out.part[k] = (uint16_t)P.local_index;                    // codec.rs:452
+        if (a.out.pix) a.out.pix[k] = x | (y << 15) | (m << 30);                     // codec.rs:463-472
+        if (a.out.btype) a.out.btype[k] = (uint8_t)bt;
+      }
+    }
+  }
 
   if (kSmooth) {
     // compact list of the type-1 boundary points of this run (order inside the list is irrelevant)
-    n_boundary = __reduce_add_sync(0xFFFFFFFFu, n_boundary);
+    const uint32_t b1 = m1 & bt1;
+    const uint32_t nb_lane = __popc(b1) + __popc(b1 & m2);
+    uint32_t incl = nb_lane;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    const uint32_t n_boundary = __shfl_sync(kFull, incl, 31);
     if (n_boundary) {
       uint32_t lbase = 0;
       if (lane == 0) lbase = atomicAdd(&a.sm.blist_count[frame], n_boundary);
-      lbase = __shfl_sync(0xFFFFFFFFu, lbase, 0);
+      lbase = __shfl_sync(kFull, lbase, 0);
       if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
         if (lane == 0) atomicExch(a.err, 7);
       } else {
-        BoundaryEntry* L = a.sm.blist + (uint64_t)frame * a.sm.blist_cap + lbase;
-        uint32_t done = 0;
-        for (uint32_t kb = 0; kb < total; kb += 32) {
-          const uint32_t k = kb + lane;
-          const bool isb = k < total && s_bt[k] == 1;
-          const uint32_t mask = __ballot_sync(0xFFFFFFFFu, isb);
-          if (isb) {
-            const uint16_t* p = reinterpret_cast<const uint16_t*>(s_pos + k * 6);
-            uint4 e;
-            e.x = run_base + k;
-            e.y = p[0] | ((uint32_t)p[1] << 16);
-            e.z = p[2];
-            e.w = 0;
-            if (a.has_attr) {
-              const uint16_t* c = reinterpret_cast<const uint16_t*>(s_yuv + k * 6);
-              e.z |= (uint32_t)c[0] << 16;
-              e.w = c[1] | ((uint32_t)c[2] << 16);
+        uint4* L = reinterpret_cast<uint4*>(a.sm.blist + (uint64_t)frame * a.sm.blist_cap + lbase + (incl - nb_lane));
+        uint32_t k = lane_excl;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          if (!((m1 >> j) & 1u)) continue;
+          const uint32_t np = 1u + ((m2 >> j) & 1u);
+          if ((b1 >> j) & 1u) {
+            for (uint32_t m = 0; m < np; ++m) {
+              const uint2 pw = *reinterpret_cast<const uint2*>(s_pos + spos_off(k + m));
+              uint4 e;
+              e.x = run_base + k + m;
+              e.y = pw.x;                                                  // pos[0] | pos[1] << 16
+              e.z = (pw.y & 0xFFFFu) | ((m ? yy[j] >> 16 : yy[j] & 0xFFFFu) << 16);   // pos[2] | Y << 16
+              e.w = m ? cB[j >> 1] : cA[j >> 1];                           // U | V << 16
+              *L++ = e;
             }
-            reinterpret_cast<uint4*>(L)[done + __popc(mask & ((1u << lane) - 1u))] = e;
           }
-          done += __popc(mask);
+          k += np;
         }
       }
     }
-    // cell statistics of the staged points
-    accumulate_cells(a, P, fig, u0b, v0b, cnt_sm, pre_sm, s_pos, s_yuv);
+    if (lane == 0) {
+      if (a.sm.geo.on) a.sm.geo.log_count[slot - a.sm.group_first_slot] = n_log_geo;
+      if (a.sm.col.on) a.sm.col.log_count[slot - a.sm.group_first_slot] = n_log_col;
+    }
   }
 }
 
@@ -910,7 +1116,7 @@ __global__ void __launch_bounds__(256) tile_scan_kernel(const UnpackArgs a) {
     uint32_t incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      const uint32_t t = __shfl_up_sync(kFull, incl, d);
       if (lane_id() >= (uint32_t)d) incl += t;
     }
     if (lane_id() == 31) s_w[threadIdx.x >> 5] = incl;
@@ -936,22 +1142,78 @@ __global__ void __launch_bounds__(256) yuv_to_rgb_flat_kernel(const uint16_t* __
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// K6 / K7 finalize: once per touched cell, sums -> Q8 means (and the colour cell's luminance-variance verdict), so that
+// the filter (8 cells per boundary point per grid) does no division.  One warp per unpack slot of the group walks that
+// slot's log; a cell logged by several slots is finalized more than once (geometry: idempotent, means live in their own
+// field; colour: claimed with an atomic flag because the means replace the sums).
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mean_q8_u32(uint32_t s, uint32_t cnt) {       // (256*s + cnt/2) / cnt
+  const unsigned long long num = 256ull * s + (cnt >> 1);
+  return num < (1ull << 32) ? (uint32_t)num / cnt : (uint32_t)(num / cnt);
+}
+__global__ void __launch_bounds__(256) smooth_finalize_kernel(const __grid_constant__ UnpackArgs a) {
+  const uint32_t ls = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // slot inside the group
+  if (ls >= a.sm.group_slots) return;
+  const uint32_t lane = lane_id();
+  const uint32_t frame = a.tile_frame[(a.sm.group_first_slot + ls) / kWarpsPerTile];
+  const uint32_t fig = frame - a.sm.group_first_frame;
+  if (a.sm.geo.on) {
+    const GridDesc& G = a.sm.geo;
+    const uint32_t n = min(G.log_count[ls], a.sm.log_stride);
+    const uint32_t* log = G.log + (uint64_t)ls * a.sm.log_stride;
+    GeoCell* tab = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots;
+    for (uint32_t i = lane; i < n; i += 32) {
+      GeoCell* c = tab + log[i];
+      const unsigned long long w0 = c->cnt_sx, w1 = c->sy_sz;
+      const uint32_t cnt = (uint32_t)w0;
+      if (cnt == 0) continue;
+      const unsigned long long mx = mean_q8_u32((uint32_t)(w0 >> 32), cnt), my = mean_q8_u32((uint32_t)w1, cnt),
+                               mz = mean_q8_u32((uint32_t)(w1 >> 32), cnt);
+      c->mean = mx | (my << 16) | (mz << 32);
+    }
+  }
+  if (a.sm.col.on) {
+    const GridDesc& G = a.sm.col;
+    const uint32_t n = min(G.log_count[ls], a.sm.log_stride);
+    const uint32_t* log = G.log + (uint64_t)ls * a.sm.log_stride;
+    ColCell* tab = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots;
+    for (uint32_t i = lane; i < n; i += 32) {
+      ColCell* c = tab + log[i];
+      if (atomicOr(&c->pmax1, kCellFinal) & kCellFinal) continue;          // somebody else finalizes / finalized it
+      const unsigned long long w0 = c->cnt_sy, w1 = c->su_sv, sy2 = c->sy2;
+      const unsigned long long cnt = w0 & 0xFFFFFFull, sy = w0 >> 24, su = w1 & 0xFFFFFFFFull, sv = w1 >> 32;
+      if (cnt > 65536ull) atomicExch(a.err, 6);     // the packed U / V sums are only exact up to 65536 points per cell
+      const unsigned long long my = (256ull * sy + cnt / 2) / cnt, mu = (256ull * su + cnt / 2) / cnt,
+                               mv = (256ull * sv + cnt / 2) / cnt;
+      // luminance variation: var(Y) = (cnt*sumY2 - sumY^2)/cnt^2 must not exceed t_var^2
+      const unsigned __int128 num = (unsigned __int128)cnt * sy2 - (unsigned __int128)sy * sy;
+      const unsigned long long tv = (unsigned long long)a.sm.thr_col_var * cnt;
+      const unsigned __int128 lim = (unsigned __int128)tv * tv;
+      c->cnt_sy = cnt | (my << 32);
+      c->su_sv = mu | (mv << 32);
+      c->sy2 = num > lim ? 0ull : 1ull;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
 // K6 / K7: filter the type-1 boundary points against the trilinear blend of the 8 surrounding cell means
 // ----------------------------------------------------------------------------------------------------------------
-struct Nbhd { uint32_t key[8]; unsigned long long wgt[8]; unsigned long long w3; };
+struct Nbhd { uint32_t key[8]; uint32_t wgt[8]; uint32_t w3; };
+// weights fit 32 bits: (2g)^3 <= 2^27 for g <= 256
 __device__ __forceinline__ bool neighbourhood(const GridDesc& G, const uint32_t p[3], Nbhd& N) {
   if (!(p[0] < G.th && p[1] < G.th && p[2] < G.th)) return false;
 #pragma unroll
   for (int a = 0; a < 3; ++a)
     if (p[a] < G.disth || p[a] + G.disth >= G.th) return false;
-  int32_t s[3]; unsigned long long wa[3];
+  int32_t s[3]; uint32_t wa[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const uint32_t c = cell_div(p[a], G), rem = p[a] - c * G.g;
     s[a] = (int32_t)c + (rem < G.g / 2 ? -1 : 0);
-    wa[a] = 2ull * (unsigned long long)((long long)p[a] - (long long)s[a] * (long long)G.g - (long long)(G.g / 2)) + 1ull;
+    wa[a] = 2u * (uint32_t)((int32_t)p[a] - s[a] * (int32_t)G.g - (int32_t)(G.g / 2)) + 1u;
   }
-  const unsigned long long g2 = 2ull * G.g;
+  const uint32_t g2 = 2u * G.g;
   N.w3 = g2 * g2 * g2;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -963,6 +1225,10 @@ __device__ __forceinline__ bool neighbourhood(const GridDesc& G, const uint32_t 
   }
   return true;
 }
+// x / w3 where w3 = (2g)^3: a shift when g is a power of two
+__device__ __forceinline__ unsigned long long div_w3(unsigned long long x, const GridDesc& G, uint32_t w3) {
+  return G.g_shift >= 0 ? (x >> (3 * (G.g_shift + 1))) : (x / w3);
+}
 
 __global__ void __launch_bounds__(256) smooth_filter_kernel(const __grid_constant__ UnpackArgs a) {
   const uint32_t fig = blockIdx.y;
@@ -972,59 +1238,70 @@ __global__ void __launch_bounds__(256) smooth_filter_kernel(const __grid_constan
   uint32_t moved = 0, recol = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint4 raw = *reinterpret_cast<const uint4*>(&L[i]);
-    const BoundaryEntry e = *reinterpret_cast<const BoundaryEntry*>(&raw);
-    const uint32_t p[3] = {e.pos[0], e.pos[1], e.pos[2]};
-    const uint64_t gi = (uint64_t)f * a.out.cap + e.idx;
+    const uint32_t p[3] = {raw.y & 0xFFFFu, raw.y >> 16, raw.z & 0xFFFFu};
+    const uint32_t col[3] = {raw.z >> 16, raw.w & 0xFFFFu, raw.w >> 16};
+    const uint64_t gi = (uint64_t)f * a.out.cap + raw.x;
     Nbhd N;
     // ---- geometry (K6) ----
     if (a.sm.geo.on && neighbourhood(a.sm.geo, p, N)) {
       const GridDesc& G = a.sm.geo;
-      unsigned long long C[3] = {0, 0, 0}, cntw = 0;
+      const GeoCell* tab = reinterpret_cast<const GeoCell*>(G.table) + (uint64_t)fig * G.slots;
+      uint4 c0[8]; uint2 cm[8];
       bool other = false;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const GeoCell* c = N.key[j] != kCellEmpty ? cell_find<GeoCell>(G, fig, N.key[j]) : nullptr;
-        uint32_t cnt = 0, s[3] = {0, 0, 0}, o[3] = {0, 0, 0};
-        if (c) {
-          const uint32_t cw = c->count;
-          cnt = cw & ~kCellMulti; s[0] = c->sx; s[1] = c->sy; s[2] = c->sz;
-          if (cnt > 0 && (cw & kCellMulti)) other = true;
-          o[0] = (N.key[j] & 1023u) * G.g; o[1] = ((N.key[j] >> 10) & 1023u) * G.g; o[2] = (N.key[j] >> 20) * G.g;
+        c0[j] = make_uint4(0, 0, 0, 0); cm[j] = make_uint2(0, 0);
+        const uint32_t cs = N.key[j] != kCellEmpty ? cell_find(G, fig, N.key[j]) : kCellEmpty;
+        if (cs != kCellEmpty) {
+          c0[j] = *reinterpret_cast<const uint4*>(tab + cs);                       // pmax1, pminc, count, sx
+          if (c0[j].z != 0) {
+            cm[j] = *reinterpret_cast<const uint2*>(&(tab + cs)->mean);
+            other |= (c0[j].x - 1u) != ~c0[j].y;
+          }
         }
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {
-          unsigned long long m = 256ull * p[ax];
-          if (cnt > 0) m = 256ull * o[ax] + (256ull * s[ax] + cnt / 2) / cnt;      // cell mean, Q8
-          C[ax] += N.wgt[j] * m;
-        }
-        cntw += N.wgt[j] * cnt;
       }
-      const unsigned long long count = cntw / N.w3;
-      if (other && count > 0) {
-        unsigned long long c4[3], D2 = 0;
+      if (other) {
+        unsigned long long C[3] = {0, 0, 0}, cntw = 0;
 #pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {
-          c4[ax] = (C[ax] + N.w3 / 2) / N.w3;
-          const long long d = (long long)(256ull * p[ax]) - (long long)c4[ax];
-          D2 += (unsigned long long)(d * d);
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t cnt = c0[j].z;
+          uint32_t m[3] = {256u * p[0], 256u * p[1], 256u * p[2]};                  // empty cell -> the point itself
+          if (cnt > 0) {
+            m[0] = 256u * ((N.key[j] & 1023u) * G.g) + (cm[j].x & 0xFFFFu);
+            m[1] = 256u * (((N.key[j] >> 10) & 1023u) * G.g) + (cm[j].x >> 16);
+            m[2] = 256u * ((N.key[j] >> 20) * G.g) + (cm[j].y & 0xFFFFu);
+          }
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) C[ax] += (unsigned long long)N.wgt[j] * m[ax];
+          cntw += (unsigned long long)N.wgt[j] * cnt;
         }
-        const unsigned long long m = a.sm.thr_geo > count ? a.sm.thr_geo : count;
-        const unsigned __int128 lhs = (unsigned __int128)2 * count * D2 + 65536u;
-        const unsigned __int128 rhs = (unsigned __int128)262144u * m;
-        if (lhs >= rhs) {
-          bool changed = false;
-          uint16_t q[3];
+        const unsigned long long count = div_w3(cntw, G, N.w3);
+        if (count > 0) {
+          unsigned long long c4[3], D2 = 0;
 #pragma unroll
           for (int ax = 0; ax < 3; ++ax) {
-            unsigned long long r = (c4[ax] + 128) >> 8;
-            if (r > 65535) r = 65535;
-            q[ax] = (uint16_t)r;
-            changed |= q[ax] != p[ax];
+            c4[ax] = div_w3(C[ax] + N.w3 / 2, G, N.w3);
+            const long long d = (long long)(256ull * p[ax]) - (long long)c4[ax];
+            D2 += (unsigned long long)(d * d);
           }
-          if (changed) {
-            uint16_t* d = a.out.pos + gi * 3;
-            d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
-            moved += 1;
+          const unsigned long long m = a.sm.thr_geo > count ? a.sm.thr_geo : count;
+          const unsigned __int128 lhs = (unsigned __int128)2 * count * D2 + 65536u;
+          const unsigned __int128 rhs = (unsigned __int128)262144u * m;
+          if (lhs >= rhs) {
+            bool changed = false;
+            uint16_t q[3];
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+              unsigned long long rr = (c4[ax] + 128) >> 8;
+              if (rr > 65535) rr = 65535;
+              q[ax] = (uint16_t)rr;
+              changed |= q[ax] != p[ax];
+            }
+            if (changed) {
+              uint16_t* d = a.out.pos + gi * 3;
+              d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
+              moved += 1;
+            }
           }
         }
       }
@@ -1032,40 +1309,41 @@ __global__ void __launch_bounds__(256) smooth_filter_kernel(const __grid_constan
     // ---- colour (K7), on the same pre-smoothing position ----
     if (a.sm.col.on && a.has_attr && neighbourhood(a.sm.col, p, N)) {
       const GridDesc& G = a.sm.col;
-      const uint32_t col[3] = {e.yuv[0], e.yuv[1], e.yuv[2]};
-      unsigned long long C[3] = {0, 0, 0};
+      const ColCell* tab = reinterpret_cast<const ColCell*>(G.table) + (uint64_t)fig * G.slots;
+      uint4 c0[8]; uint4 c1[8];
       bool other = false;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const ColCell* c = N.key[j] != kCellEmpty ? cell_find<ColCell>(G, fig, N.key[j]) : nullptr;
-        bool usable = false;
-        unsigned long long mean[3] = {0, 0, 0};
-        if (c && (c->count & ~kCellMulti) > 0) {
-          const unsigned long long cnt = c->count & ~kCellMulti;
-          if (c->count & kCellMulti) other = true;
-          if (cnt > 65536ull) atomicExch(a.err, 6);     // u32 colour sums are only exact up to 65536 points per cell
-          usable = true;
-          const unsigned long long s[3] = {c->sy, c->su, c->sv};
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax) mean[ax] = (256ull * s[ax] + cnt / 2) / cnt;
-          const unsigned __int128 num = (unsigned __int128)cnt * c->sy2 - (unsigned __int128)s[0] * s[0];
-          const unsigned long long tv = (unsigned long long)a.sm.thr_col_var * cnt;
-          const unsigned __int128 lim = (unsigned __int128)tv * tv;
-          if (num > lim) usable = false;
-          const long long dy = (long long)mean[0] - (long long)(256ull * col[0]);
-          if ((unsigned long long)(dy < 0 ? -dy : dy) > 256ull * a.sm.thr_col_diff) usable = false;
+        c0[j] = make_uint4(0, 0, 0, 0); c1[j] = make_uint4(0, 0, 0, 0);
+        const uint32_t cs = N.key[j] != kCellEmpty ? cell_find(G, fig, N.key[j]) : kCellEmpty;
+        if (cs != kCellEmpty) {
+          c0[j] = *reinterpret_cast<const uint4*>(tab + cs);                       // pmax1 | final, pminc, count, meanY
+          if (c0[j].z != 0) {
+            c1[j] = *(reinterpret_cast<const uint4*>(tab + cs) + 1);               // meanU, meanV, variance verdict
+            other |= ((c0[j].x & ~kCellFinal) - 1u) != ~c0[j].y;
+          }
         }
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) C[ax] += N.wgt[j] * (usable ? mean[ax] : 256ull * col[ax]);
       }
       if (other) {
+        unsigned long long C[3] = {0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          bool usable = c0[j].z != 0 && c1[j].z != 0;
+          const uint32_t mean[3] = {c0[j].w, c1[j].x, c1[j].y};
+          if (usable) {
+            const long long dy = (long long)mean[0] - (long long)(256u * col[0]);
+            if ((unsigned long long)(dy < 0 ? -dy : dy) > 256ull * a.sm.thr_col_diff) usable = false;
+          }
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) C[ax] += (unsigned long long)N.wgt[j] * (usable ? mean[ax] : 256u * col[ax]);
+        }
         uint32_t q[3]; unsigned long long dist = 0;
 #pragma unroll
         for (int ax = 0; ax < 3; ++ax) {
-          const unsigned long long c4 = (C[ax] + N.w3 / 2) / N.w3;
-          unsigned long long r = (c4 + 128) >> 8;
-          if (r > 65535) r = 65535;
-          q[ax] = (uint32_t)r;
+          const unsigned long long c4 = div_w3(C[ax] + N.w3 / 2, G, N.w3);
+          unsigned long long rr = (c4 + 128) >> 8;
+          if (rr > 65535) rr = 65535;
+          q[ax] = (uint32_t)rr;
           const long long d = (long long)q[ax] - (long long)col[ax];
           dist += (unsigned long long)(d < 0 ? -d : d) * (ax == 0 ? 10u : 1u);
         }
@@ -1079,47 +1357,39 @@ __global__ void __launch_bounds__(256) smooth_filter_kernel(const __grid_constan
       }
     }
   }
-  moved = __reduce_add_sync(0xFFFFFFFFu, moved);
-  recol = __reduce_add_sync(0xFFFFFFFFu, recol);
+  moved = __reduce_add_sync(kFull, moved);
+  recol = __reduce_add_sync(kFull, recol);
   if (lane_id() == 0) {
     if (moved) atomicAdd(&a.sm.changed[f], (unsigned long long)moved);
     if (recol) atomicAdd(&a.sm.changed[a.n_frames + f], (unsigned long long)recol);
   }
 }
 
-template <typename Cell>
-__device__ __forceinline__ void clear_cells(const GridDesc& G, uint32_t fig, uint64_t touched_cap) {
-  if (!G.on) return;
-  const uint32_t n = min((uint64_t)G.touched_count[fig], touched_cap);
-  Cell* tab = reinterpret_cast<Cell*>(G.table) + (uint64_t)fig * G.slots;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    Cell z;
-    memset(&z, 0, sizeof z);
-    z.key = kCellEmpty;
-    tab[G.touched[(uint64_t)fig * touched_cap + i]] = z;
+// back to all-zero cells (and free keys) for the next group: walk the same per-slot logs
+__global__ void __launch_bounds__(256) smooth_clear_kernel(const __grid_constant__ UnpackArgs a) {
+  const uint32_t ls = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ls >= a.sm.group_slots) return;
+  const uint32_t lane = lane_id();
+  const uint32_t frame = a.tile_frame[(a.sm.group_first_slot + ls) / kWarpsPerTile];
+  const uint32_t fig = frame - a.sm.group_first_frame;
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const GridDesc& G = which ? a.sm.col : a.sm.geo;
+    if (!G.on) continue;
+    const uint32_t n = min(G.log_count[ls], a.sm.log_stride);
+    const uint32_t* log = G.log + (uint64_t)ls * a.sm.log_stride;
+    uint4* tab = reinterpret_cast<uint4*>(G.table) + ((uint64_t)fig * G.slots) * 2;      // 32-byte cells
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint32_t cs = log[i];
+      tab[(uint64_t)cs * 2] = make_uint4(0, 0, 0, 0);
+      tab[(uint64_t)cs * 2 + 1] = make_uint4(0, 0, 0, 0);
+      if (!G.identity) G.keys[(uint64_t)fig * G.slots + cs] = kCellEmpty;
+    }
   }
 }
-__global__ void __launch_bounds__(256) smooth_clear_kernel(const UnpackArgs a) {
-  const uint32_t fig = blockIdx.y;
-  clear_cells<GeoCell>(a.sm.geo, fig, a.sm.touched_cap);
-  clear_cells<ColCell>(a.sm.col, fig, a.sm.touched_cap);
-}
-__global__ void smooth_reset_kernel(const UnpackArgs a) {   // after the clear: counters back to zero for the next group
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < a.sm.group_frames) {
-    if (a.sm.geo.on) a.sm.geo.touched_count[i] = 0;
-    if (a.sm.col.on) a.sm.col.touched_count[i] = 0;
-    a.sm.blist_count[a.sm.group_first_frame + i] = 0;
-  }
-}
-template <typename Cell>
-__global__ void __launch_bounds__(256) table_init_kernel(Cell* tab, uint64_t n) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    Cell z;
-    memset(&z, 0, sizeof z);
-    z.key = kCellEmpty;
-    tab[i] = z;
-  }
+
+__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t* p, uint64_t n, uint32_t v) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1127,11 +1397,9 @@ __global__ void __launch_bounds__(256) table_init_kernel(Cell* tab, uint64_t n) 
 // ----------------------------------------------------------------------------------------------------------------
 static inline int after_launch() { ++g_launches; return (int)cudaGetLastError(); }
 
-size_t unpack_smem_bytes(const UnpackArgs& a) { return (size_t)a.warp_bytes * kWarpsPerTile; }
-
 int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream) {
   if (n_slots == 0) return 0;
-  const uint32_t blocks = (n_slots * 32 + 255) / 256;
+  const uint32_t blocks = (n_slots + 255) / 256;
   block_to_patch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, n_slots, const_cast<uint32_t*>(a.block_to_patch));
   return after_launch();
 }
@@ -1152,7 +1420,7 @@ static int launch_unpack_m(const UnpackArgs& a, bool smooth, bool debug, uint32_
 
 int launch_unpack(const UnpackArgs& a, int mode, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream) {
   if (tile_end <= tile_begin) return 0;
-  const size_t smem = mode == 1 ? 0 : unpack_smem_bytes(a);
+  const size_t smem = mode == 1 ? 0 : (size_t)kWarpSmemBytes * kWarpsPerTile;
   const cudaStream_t s = (cudaStream_t)stream;
   const bool debug = a.out.yuv || a.out.part || a.out.pix || a.out.btype;
   if (mode == 1) return launch_unpack_t<1, false, false>(a, tile_begin, tile_end, smem, s);
@@ -1171,6 +1439,12 @@ int launch_upsample(const UnpackArgs& a, uint8_t* occ_full, void* stream) {
   return after_launch();
 }
 
+int launch_smooth_finalize(const UnpackArgs& a, void* stream) {
+  if (a.sm.group_slots == 0) return 0;
+  smooth_finalize_kernel<<<(a.sm.group_slots * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+  return after_launch();
+}
+
 int launch_smooth_filter(const UnpackArgs& a, void* stream) {
   if (a.sm.group_frames == 0) return 0;
   const unsigned bx = (148u * 8u + a.sm.group_frames - 1) / a.sm.group_frames;
@@ -1179,12 +1453,8 @@ int launch_smooth_filter(const UnpackArgs& a, void* stream) {
 }
 
 int launch_smooth_clear(const UnpackArgs& a, void* stream) {
-  if (a.sm.group_frames == 0) return 0;
-  const unsigned bx = (148u * 4u + a.sm.group_frames - 1) / a.sm.group_frames;
-  smooth_clear_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
-  int e = after_launch();
-  if (e) return e;
-  smooth_reset_kernel<<<(a.sm.group_frames + 63) / 64, 64, 0, (cudaStream_t)stream>>>(a);
+  if (a.sm.group_slots == 0) return 0;
+  smooth_clear_kernel<<<(a.sm.group_slots * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
 }
 
@@ -1195,10 +1465,9 @@ int launch_yuv_to_rgb_flat(const uint16_t* yuv, uint8_t* rgb, uint64_t n, void* 
   yuv_to_rgb_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(yuv, rgb, n);
   return after_launch();
 }
-int launch_table_init(void* table, uint64_t total_slots, int is_color, void* stream) {
-  if (total_slots == 0) return 0;
-  if (is_color) table_init_kernel<ColCell><<<148 * 8, 256, 0, (cudaStream_t)stream>>>((ColCell*)table, total_slots);
-  else table_init_kernel<GeoCell><<<148 * 8, 256, 0, (cudaStream_t)stream>>>((GeoCell*)table, total_slots);
+int launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, void* stream) {
+  if (n == 0) return 0;
+  fill_u32_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(p, n, v);
   return after_launch();
 }
 

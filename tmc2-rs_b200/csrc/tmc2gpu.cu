@@ -246,8 +246,11 @@ struct Batch {
 
   DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_status, d_tile_total, d_count, d_err;
   DevBuf d_pos, d_rgb, d_yuv, d_part, d_pix, d_bt, d_occ_full, d_pos_pre, d_yuv_pre;
-  DevBuf d_geotab, d_coltab, d_touched_geo, d_touched_col, d_touched_count, d_changed, d_blist, d_blist_count;
-  uint64_t geotab_slots = 0, coltab_slots = 0, geotab_frames = 0, coltab_frames = 0, touched_cap = 0, blist_cap = 0;
+  DevBuf d_geotab, d_coltab, d_geokeys, d_colkeys, d_geolog, d_collog, d_geolog_count, d_collog_count, d_changed, d_blist,
+      d_blist_count;
+  uint64_t geotab_slots = 0, coltab_slots = 0, geotab_frames = 0, coltab_frames = 0, blist_cap = 0;
+  bool geotab_hashed = false, coltab_hashed = false;
+  uint32_t max_group_slots = 0, log_stride = 0;
   uint32_t group_frames = 8;          // frames per smoothing group (cell tables stay L2-resident inside a group)
   uint32_t group_frames_eff = 8;      // after fitting the dense tables into the memory budget
   std::vector<cudaEvent_t> ev_grp;    // 2 per group: around the unpack launch
@@ -273,7 +276,8 @@ struct Batch {
     cudaSetDevice(device);
     for (DevBuf* b : {&d_occ, &d_geo, &d_ay, &d_au, &d_av, &d_meta, &d_b2p, &d_status, &d_tile_total, &d_count, &d_err, &d_pos,
                       &d_rgb, &d_yuv, &d_part, &d_pix, &d_bt, &d_occ_full, &d_pos_pre, &d_yuv_pre, &d_geotab, &d_coltab,
-                      &d_touched_geo, &d_touched_col, &d_touched_count, &d_changed, &d_blist, &d_blist_count})
+                      &d_geokeys, &d_colkeys, &d_geolog, &d_collog, &d_geolog_count, &d_collog_count, &d_changed, &d_blist,
+                      &d_blist_count})
       b->release();
     for (PinBuf* b : {&h_in, &h_meta, &h_small, &h_out}) b->release();
     for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -311,7 +315,7 @@ struct Batch {
     Hc = H / 2;
     geo_pitch = round_up(W, 64); attr_pitch_y = round_up(W, 64); attr_pitch_c = round_up(std::max(W / 2, 1u), 64);
     occ_pitch = round_up(occ_w, 16);
-    cap = 2ull * W * H;
+    cap = round_up64(2ull * W * H, 16);   // slabs stay 16-byte aligned for both output streams
     smoothing_geo = params.geometry_smoothing != 0;
     smoothing_col = params.color_smoothing != 0 && params.attribute_count != 0;
 
@@ -322,11 +326,18 @@ struct Batch {
       for (uint32_t i = 0; i < fr.patch_count; ++i) {
         const tmc2_patch& p = fr.patches[i];
         DevPatch d{};
-        d.x0 = (int32_t)(p.u0 * res); d.y0 = (int32_t)(p.v0 * res);
         d.u0 = p.u0; d.v0 = p.v0; d.size_u0 = p.size_u0; d.size_v0 = p.size_v0;
         d.u1 = p.u1; d.v1 = p.v1; d.d1 = p.d1; d.lod_x = p.lod_x; d.lod_y = p.lod_y;
         d.normal = p.normal_axis; d.tangent = p.tangent_axis; d.bitangent = p.bitangent_axis; d.mode = p.projection_mode;
         d.orient = p.patch_orientation;
+        {
+          // block-aligned affine form of decoder.rs:853-867: canvas step per +1 in patch u (ax, ay) and per +1 in v (rx, ry)
+          static const int8_t kAx[9] = {1, 0, 0, -1, 0, -1, 0, 1, 0}, kAy[9] = {0, 1, 1, 0, -1, 0, -1, 0, 1};
+          static const int8_t kRx[9] = {0, 1, -1, 0, 1, 0, -1, 0, 1}, kRy[9] = {1, 0, 0, -1, 0, 1, 0, -1, 0};
+          const uint32_t o = p.patch_orientation;
+          d.ax = kAx[o]; d.ay = kAy[o]; d.rx = kRx[o]; d.ry = kRy[o];
+          d.aligned = (params.orientation_mode == TMC2_ORIENTATION_SPEC || o <= 1 || o == 8) ? 1 : 0;
+        }
         d.slot_base = (uint32_t)h_slot_patch.size();
         d.local_index = i; d.frame = k;
         const uint64_t ns = (uint64_t)p.size_u0 * p.size_v0;
@@ -389,48 +400,53 @@ struct Batch {
         CU(d_blist.ensure((size_t)F * cap * sizeof(BoundaryEntry)));
         blist_cap = cap;
       }
-      if (d_blist_count.cap < (size_t)F * 4) {
-        CU(d_blist_count.ensure((size_t)F * 4));
-        CU(cudaMemsetAsync(d_blist_count.p, 0, d_blist_count.cap, stream));
-      }
-      // Cell tables: dense (direct-indexed, no probing, no key) when the whole grid fits the per-table budget for at
-      // least one frame, hashed otherwise.  The group size shrinks until the dense colour table fits.
+      CU(d_blist_count.ensure(std::max<size_t>((size_t)F * 4, 4)));
+      // Cell tables: dense (direct-indexed, no probing) when the whole grid fits the per-table budget for at least one
+      // frame, hashed (separate key array) otherwise.  The group size shrinks until the dense tables fit.
       const uint64_t kTableBudget = 16ull << 30;
+      const bool force_hash = getenv("TMC2_FORCE_HASH") != nullptr;        // test hook for the hashed-table path
       auto cells_of = [&](uint32_t g) -> uint64_t { const uint64_t w = (maxs + g - 1) / g; return w * w * w; };
       uint32_t GF = std::min(group_frames, std::max(F, 1u));
-      if (smoothing_col) {
-        const uint64_t per_frame = cells_of(params.cgrid_size) * sizeof(ColCell);
+      auto fit = [&](bool on, uint32_t g, size_t cell_bytes) {
+        if (!on || force_hash) return;
+        const uint64_t per_frame = cells_of(g) * cell_bytes;
         if (per_frame <= kTableBudget) GF = (uint32_t)std::min<uint64_t>(GF, std::max<uint64_t>(1, kTableBudget / per_frame));
-      }
-      group_frames_eff = GF;
-      auto table_slots = [&](uint32_t g, size_t cell_bytes) -> uint64_t {
-        const uint64_t cells = cells_of(g);
-        const bool force_hash = getenv("TMC2_FORCE_HASH") != nullptr;      // test hook for the hashed-table path
-        return (!force_hash && cells * cell_bytes <= kTableBudget) ? cells : pow2_at_least(2 * cap);
       };
-      touched_cap = cap;
-      if (d_touched_count.cap < (size_t)GF * 8) {
-        CU(d_touched_count.ensure((size_t)GF * 8));
-        CU(cudaMemsetAsync(d_touched_count.p, 0, d_touched_count.cap, stream));
-      }
-      if (smoothing_geo) {
-        const uint64_t slots = table_slots(params.grid_size, sizeof(GeoCell));
-        if (slots != geotab_slots || GF > geotab_frames) {
-          CU(d_geotab.ensure((size_t)GF * slots * sizeof(GeoCell)));
-          CU(d_touched_geo.ensure((size_t)GF * touched_cap * 4));
-          geotab_slots = slots; geotab_frames = GF;
-          KL(launch_table_init(d_geotab.p, (uint64_t)GF * slots, 0, stream));
+      fit(smoothing_geo, params.grid_size, sizeof(GeoCell));
+      fit(smoothing_col, params.cgrid_size, sizeof(ColCell));
+      group_frames_eff = GF;
+      auto table_slots = [&](uint32_t g, size_t cell_bytes, bool& hashed) -> uint64_t {
+        const uint64_t cells = cells_of(g);
+        hashed = force_hash || cells * cell_bytes > kTableBudget;
+        return hashed ? pow2_at_least(2 * cap) : cells;
+      };
+      auto setup = [&](bool on, uint32_t g, size_t cell_bytes, DevBuf& tab, DevBuf& keys, uint64_t& slots_now, uint64_t& frames_now,
+                       bool& hashed_now) -> tmc2_status {
+        if (!on) return TMC2_OK;
+        bool hashed = false;
+        const uint64_t slots = table_slots(g, cell_bytes, hashed);
+        if (slots != slots_now || GF > frames_now || hashed != hashed_now) {
+          CU(tab.ensure((size_t)GF * slots * cell_bytes));
+          CU(cudaMemsetAsync(tab.p, 0, (size_t)GF * slots * cell_bytes, stream));     // all-zero == empty cell
+          if (hashed) {
+            CU(keys.ensure((size_t)GF * slots * 4));
+            KL(launch_fill_u32(keys.as<uint32_t>(), (uint64_t)GF * slots, kCellEmpty, stream));
+          }
+          slots_now = slots; frames_now = GF; hashed_now = hashed;
         }
-      }
-      if (smoothing_col) {
-        const uint64_t slots = table_slots(params.cgrid_size, sizeof(ColCell));
-        if (slots != coltab_slots || GF > coltab_frames) {
-          CU(d_coltab.ensure((size_t)GF * slots * sizeof(ColCell)));
-          CU(d_touched_col.ensure((size_t)GF * touched_cap * 4));
-          coltab_slots = slots; coltab_frames = GF;
-          KL(launch_table_init(d_coltab.p, (uint64_t)GF * slots, 1, stream));
-        }
-      }
+        return TMC2_OK;
+      };
+      if (setup(smoothing_geo, params.grid_size, sizeof(GeoCell), d_geotab, d_geokeys, geotab_slots, geotab_frames, geotab_hashed)) return err.st;
+      if (setup(smoothing_col, params.cgrid_size, sizeof(ColCell), d_coltab, d_colkeys, coltab_slots, coltab_frames, coltab_hashed)) return err.st;
+      // per-slot logs of the table slots each unpack slot added to (walked by finalize and clear)
+      log_stride = 2 * res * res;
+      max_group_slots = 0;
+      for (uint32_t f0 = 0; f0 < F; f0 += GF)
+        max_group_slots = std::max(max_group_slots, (h_ftb[std::min(F, f0 + GF)] - h_ftb[f0]) * (uint32_t)kWarpsPerTile);
+      const size_t log_bytes = std::max<size_t>((size_t)max_group_slots * log_stride * 4, 4);
+      const size_t cnt_bytes = std::max<size_t>((size_t)max_group_slots * 4, 4);
+      if (smoothing_geo) { CU(d_geolog.ensure(log_bytes)); CU(d_geolog_count.ensure(cnt_bytes)); }
+      if (smoothing_col) { CU(d_collog.ensure(log_bytes)); CU(d_collog_count.ensure(cnt_bytes)); }
     }
     return TMC2_OK;
   }
@@ -570,38 +586,25 @@ struct Batch {
     a.out.btype = dbg ? d_bt.as<uint8_t>() : nullptr;
     a.out.pix = dbg ? d_pix.as<uint32_t>() : nullptr;
     a.want_btype = a.out.btype != nullptr || smooth;
-    // shared-memory layout of one warp: scan scratch, then one staging area per stream (16 bytes of phase slack each)
-    uint32_t off = 0;
-    auto place = [&](bool on, uint32_t bytes) {
-      const uint32_t o = off;
-      if (on) off += round_up(bytes, 16);
-      return o;
-    };
-    a.off_scan = place(true, 768);
-    a.off_pos = place(true, kSlotPoints * 6 + 16);
-    a.off_rgb = place(a.out.rgb != nullptr, kSlotPoints * 3 + 16);
-    a.off_yuv = place(a.has_attr && (a.out.yuv != nullptr || smooth), kSlotPoints * 6 + 16);
-    a.off_part = place(a.out.part != nullptr, kSlotPoints * 2 + 16);
-    a.off_pix = place(a.out.pix != nullptr, kSlotPoints * 4 + 16);
-    a.off_bt = place(a.out.btype != nullptr || smooth, kSlotPoints + 16);
-    a.warp_bytes = off;
     if (smooth) {
       const uint32_t maxs = 1u << params.geometry_bitdepth_3d;
-      auto grid = [&](GridDesc& G, bool on, uint32_t g, void* table, uint64_t slots, uint32_t* touched, uint32_t* tcount) {
+      auto grid = [&](GridDesc& G, bool on, uint32_t g, void* table, uint32_t* keys, uint64_t slots, bool hashed, uint32_t* log,
+                      uint32_t* log_count) {
         G.on = on ? 1 : 0;
         if (!on) return;
         G.g = g; G.w = (maxs + g - 1) / g; G.disth = std::max(g / 2, 1u); G.th = g * G.w;
         G.magic = g > 1 ? (uint32_t)(((1ull << 32) + g - 1) / g) : 0u;
-        G.slots = slots; G.table = table;
-        G.identity = (uint64_t)G.w * G.w * G.w <= slots ? 1 : 0;
-        G.touched = touched; G.touched_count = tcount;
+        G.g_shift = -1;
+        for (int sft = 0; sft < 16; ++sft) if ((1u << sft) == g) G.g_shift = sft;
+        G.slots = slots; G.table = table; G.keys = keys;
+        G.identity = hashed ? 0 : 1;
+        G.log = log; G.log_count = log_count;
       };
-      const uint32_t GF = group_frames_eff;
-      grid(a.sm.geo, smoothing_geo, params.grid_size, d_geotab.p, geotab_slots, d_touched_geo.as<uint32_t>(),
-           d_touched_count.as<uint32_t>());
-      grid(a.sm.col, smoothing_col, params.cgrid_size, d_coltab.p, coltab_slots, d_touched_col.as<uint32_t>(),
-           d_touched_count.as<uint32_t>() + GF);
-      a.sm.touched_cap = touched_cap;
+      grid(a.sm.geo, smoothing_geo, params.grid_size, d_geotab.p, d_geokeys.as<uint32_t>(), geotab_slots, geotab_hashed,
+           d_geolog.as<uint32_t>(), d_geolog_count.as<uint32_t>());
+      grid(a.sm.col, smoothing_col, params.cgrid_size, d_coltab.p, d_colkeys.as<uint32_t>(), coltab_slots, coltab_hashed,
+           d_collog.as<uint32_t>(), d_collog_count.as<uint32_t>());
+      a.sm.log_stride = log_stride;
       a.sm.blist = d_blist.as<BoundaryEntry>(); a.sm.blist_count = d_blist_count.as<uint32_t>(); a.sm.blist_cap = blist_cap;
       const uint32_t sc = params.attribute_bitdepth > 8 ? (1u << (params.attribute_bitdepth - 8)) : 1u;
       a.sm.thr_geo = params.threshold_smoothing;
@@ -639,6 +642,7 @@ struct Batch {
     const bool smooth = smoothing_geo || smoothing_col;
     const bool dbg = (want & WANT_DEBUG) != 0;
     CU(cudaMemsetAsync(d_changed.p, 0, std::max<size_t>((size_t)F * 16, 16), s));
+    if (smooth) CU(cudaMemsetAsync(d_blist_count.p, 0, std::max<size_t>((size_t)F * 4, 4), s));
     if (two_pass) {   // debug: the counts of every frame first, one scan, then the emit launches
       KL(launch_unpack(a, 1, false, 0, n_tiles, s));
       KL(launch_tile_scan(a, s));
@@ -658,6 +662,8 @@ struct Batch {
       for (uint32_t gi = 0; gi < n_groups; ++gi) {
         const uint32_t f0 = gi * GF, f1 = std::min(F, f0 + GF);
         a.sm.group_first_frame = f0; a.sm.group_frames = f1 - f0;
+        a.sm.group_first_slot = h_ftb[f0] * (uint32_t)kWarpsPerTile;
+        a.sm.group_slots = (h_ftb[f1] - h_ftb[f0]) * (uint32_t)kWarpsPerTile;
         CU(cudaEventRecord(ev_grp[2 * gi], s));
         KL(launch_unpack(a, emit_mode, true, h_ftb[f0], h_ftb[f1], s));
         CU(cudaEventRecord(ev_grp[2 * gi + 1], s));
@@ -668,6 +674,7 @@ struct Batch {
             CU(cudaMemcpyAsync(d_yuv_pre.as<uint8_t>() + (size_t)f0 * cap * 6, d_yuv.as<uint8_t>() + (size_t)f0 * cap * 6,
                                (size_t)(f1 - f0) * cap * 6, cudaMemcpyDeviceToDevice, s));
         }
+        KL(launch_smooth_finalize(a, s));
         KL(launch_smooth_filter(a, s));
         KL(launch_smooth_clear(a, s));
       }
