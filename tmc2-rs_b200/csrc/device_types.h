@@ -5,8 +5,8 @@
 //   geo    [F][2][H][pitch]            u16  geometry video, channel 0 only     (reference atlas.geo_frames[0], frame f*2+m)
 //   attr_y [F][2][H][pitch]            u16  attribute video, channel 0         (reference atlas.attr_frames[0])
 //   attr_u [F][2][H/2][pitch_c]        u16  channel 1 (4:2:0)      attr_v likewise
-//   patches[total]  DevPatch ; slot_patch[n_tiles*kWarpsPerTile] ; tile_frame[n_tiles] ; frame_tile_begin[F+1]
-//   block_to_patch [F][bw*bh] u32
+//   patches[total]  DevPatch ; slot_rec[n_tiles*kWarpsPerTile] SlotRec ; tile_frame[n_tiles] ; frame_tile_begin[F+1]
+//   block_to_patch [F][bw*bh] u32 ; owned[n_tiles*kWarpsPerTile] u32 (per frame: its owned slots, compacted, in order)
 // Pitches are multiples of 64 elements so every 16x16 canvas block row starts on a 32-byte boundary.
 // Outputs are per-frame slabs of `cap` points (cap % 16 == 0):  pos [F][cap][3] u16, rgb [F][cap][3] u8, and (debug /
 // stage API only) yuv [F][cap][3] u16, partition [F][cap] u16, pixel [F][cap] u32 (x | y<<15 | map<<30), btype [F][cap] u8;
@@ -40,6 +40,15 @@ struct alignas(16) DevPatch { // reference Patch (src/decoder.rs:711-783), pre-d
   uint32_t slot_base;        // index of this patch's first slot in slot_patch[]
   uint32_t local_index;      // patch index inside its frame (partition value; block_to_patch holds local_index+1)
   uint32_t frame;            // frame inside the batch
+};
+
+// One 16x16 block of one patch ("slot"), in the reference's iteration order (patch, v0, u0): everything the unpack
+// kernel needs to start loading planes, digested on the host.
+struct alignas(16) SlotRec {
+  uint32_t pid;              // index into patches[], kNoPatch = padding
+  uint16_t u0b, v0b;         // block inside the patch
+  uint16_t bx, by;           // canvas block it maps to (src/decoder.rs:827-837)
+  int8_t   ax, ay, rx, ry;   // copy of the patch's affine steps
 };
 
 struct Planes {
@@ -128,10 +137,12 @@ struct UnpackArgs {
   uint32_t n_frames, n_tiles;
   uint8_t  absolute_d1, spec_orientation, has_attr, want_btype;
   const DevPatch* patches;
-  const uint32_t* slot_patch;
+  const SlotRec*  slot_rec;
   const uint32_t* tile_frame;
   const uint32_t* frame_tile_begin;   // [F+1]
   const uint32_t* block_to_patch;     // [F][bw*bh]
+  uint32_t*       owned;              // [n_tiles*kWarpsPerTile] compacted owned slots of each frame, from frame_tile_begin[f]*8
+  uint32_t*       owned_count;        // [F]
   uint64_t*       tile_status;        // chained-scan state, one word per tile
   uint32_t        epoch;              // launch tag inside the status words (no memset between launches)
   uint32_t*       tile_total;         // two-pass mode: per-tile totals (count kernel) / exclusive bases (emit kernel)
@@ -149,6 +160,7 @@ constexpr uint32_t kWarpSmemBytes = kStagePosBytes + kStageRgbBytes + kBitmapByt
 
 // launch wrappers (kernels.cu); every one enqueues on `stream` and returns the cudaGetLastError() code
 int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream);
+int launch_compact_owned(const UnpackArgs& a, void* stream);   // after block_to_patch: per-frame list of owned slots
 // mode: 0 fused single pass, 1 count, 2 emit.  Tiles [tile_begin, tile_end).  smooth: accumulate cell tables + boundary list
 int launch_unpack(const UnpackArgs& a, int mode, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream);
 int launch_tile_scan(const UnpackArgs& a, void* stream);

@@ -273,23 +273,28 @@ __device__ __forceinline__ void col_cell_add(const GridDesc& G, uint32_t fig, ui
 // ----------------------------------------------------------------------------------------------------------------
 // K2: block-to-patch map.  One thread per slot (= one 16x16 block of one patch).
 // ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ SlotRec load_slot_rec(const SlotRec* p) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  SlotRec r;
+  r.pid = v.x; r.u0b = (uint16_t)v.y; r.v0b = (uint16_t)(v.y >> 16); r.bx = (uint16_t)v.z; r.by = (uint16_t)(v.z >> 16);
+  r.ax = (int8_t)v.w; r.ay = (int8_t)(v.w >> 8); r.rx = (int8_t)(v.w >> 16); r.ry = (int8_t)(v.w >> 24);
+  return r;
+}
+
 __global__ void __launch_bounds__(256) block_to_patch_kernel(const UnpackArgs a, uint32_t n_slots,
                                                              uint32_t* __restrict__ b2p) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_slots) return;
-  const uint32_t pid = a.slot_patch[slot];
-  if (pid == kNoPatch) return;
-  const DevPatch P = a.patches[pid];
-  const uint32_t s = slot - P.slot_base;
-  const uint32_t v0 = s / P.size_u0, u0 = s - v0 * P.size_u0;
-  int64_t bx, by;
-  patch_to_canvas(P, u0, v0, 1, 1, bx, by);                       // codec.rs:220-225 (block variant, resolution 1)
-  const uint8_t* occ_f = a.in.occ + (uint64_t)P.frame * a.in.occ_frame_stride;
+  const SlotRec R = load_slot_rec(a.slot_rec + slot);
+  if (R.pid == kNoPatch) return;
+  const uint32_t frame = a.tile_frame[slot / kWarpsPerTile];
+  const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
   const uint32_t res = a.res;
+  const uint32_t packed = __ldg(reinterpret_cast<const uint32_t*>(&a.patches[R.pid].orient));   // orient | aligned << 8 | ...
   bool nz = false;
-  if (P.aligned) {
+  if ((packed >> 8) & 0xFFu) {
     // the res x res patch pixels are exactly the canvas block: test the low-resolution samples that cover it
-    const uint32_t x0 = (uint32_t)bx * res, y0 = (uint32_t)by * res;
+    const uint32_t x0 = (uint32_t)R.bx * res, y0 = (uint32_t)R.by * res;
     const uint32_t cxa = div_prec(x0, a.prec, a.prec_shift), cxb = div_prec(x0 + res - 1, a.prec, a.prec_shift);
     const uint32_t cya = div_prec(y0, a.prec, a.prec_shift), cyb = div_prec(y0 + res - 1, a.prec, a.prec_shift);
     for (uint32_t cy = cya; cy <= cyb && !nz; ++cy) {
@@ -302,14 +307,52 @@ __global__ void __launch_bounds__(256) block_to_patch_kernel(const UnpackArgs a,
     }
   } else {
     // reference-literal pixel mapping for the rotated / mirrored orientations (codec.rs:227-241)
+    const DevPatch P = a.patches[R.pid];
     for (uint32_t i = 0; i < res * res && !nz; ++i) {
       const uint32_t v1 = i / res, u1 = i - v1 * res;
       int64_t x, y;
-      patch_to_canvas(P, (int64_t)u0 * res + u1, (int64_t)v0 * res + v1, res, 1, x, y);
+      patch_to_canvas(P, (int64_t)R.u0b * res + u1, (int64_t)R.v0b * res + v1, res, 1, x, y);
       nz |= occ_at(a, occ_f, (uint32_t)x, (uint32_t)y) != 0;
     }
   }
-  if (nz) atomicMax(&b2p[(uint64_t)P.frame * a.bw * a.bh + (uint64_t)by * a.bw + (uint64_t)bx], P.local_index + 1);
+  if (nz) {
+    const uint32_t local_index = __ldg(&a.patches[R.pid].local_index);
+    atomicMax(&b2p[(uint64_t)frame * a.bw * a.bh + (uint64_t)R.by * a.bw + (uint64_t)R.bx], local_index + 1);
+  }
+}
+
+// After K2: the slots that own their canvas block (codec.rs:379), compacted per frame in slot order.  One CTA per frame.
+// The unpack kernel walks this list, so every warp of a tile has work and no plane is touched for a block that is
+// skipped.
+__global__ void __launch_bounds__(1024) compact_owned_kernel(const UnpackArgs a) {
+  const uint32_t f = blockIdx.x;
+  const uint32_t s0 = a.frame_tile_begin[f] * kWarpsPerTile, s1 = a.frame_tile_begin[f + 1] * kWarpsPerTile;
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  for (uint32_t b = s0; b < s1; b += blockDim.x) {
+    const uint32_t slot = b + threadIdx.x;
+    bool own = false;
+    if (slot < s1) {
+      const SlotRec R = load_slot_rec(a.slot_rec + slot);
+      if (R.pid != kNoPatch) {
+        const uint32_t local_index = __ldg(&a.patches[R.pid].local_index);
+        own = a.block_to_patch[(uint64_t)f * a.bw * a.bh + (uint64_t)R.by * a.bw + R.bx] == local_index + 1;
+      }
+    }
+    const uint32_t m = __ballot_sync(kFull, own);
+    if (lane == 0) s_w[warp] = __popc(m);
+    __syncthreads();
+    uint32_t base = s_carry;
+    for (uint32_t w = 0; w < warp; ++w) base += s_w[w];
+    if (own) a.owned[s0 + base + __popc(m & ((1u << lane) - 1u))] = slot;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = base + __popc(m);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a.owned_count[f] = s_carry;
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -559,37 +602,70 @@ __device__ __forceinline__ void copy_out_rgb(uint8_t* __restrict__ grgb /* frame
   }
 }
 
-// ---- smoothing: geometry cell statistics of one slot, aggregated in registers ------------------------------------------
-// Every lane holds up to 16 points (8 pixels x 2 maps) as (key, packed contribution).  Rounds: each lane takes its
-// smallest remaining cell key, sums its own matching points, then lanes that hold the same key merge along a butterfly
-// (rows of a cell are neighbouring lanes), and whoever still holds a non-zero count issues the reductions.  Exact for
-// any input: a failed merge only means two reductions instead of one.
-struct GeoLaneCtx {
-  uint32_t shN, shT, shB;      // bit position (0, 10, 20) of the normal / tangent / bitangent cell index inside a key
-};
-
 template <bool kSmooth, bool kDebug> struct UnpackTraits { static constexpr int kMinCtas = (kSmooth || kDebug) ? 2 : 3; };
+
+// one row of the 20x20 occupancy bitmap (block + 2-pixel margin, patch-local axes): bit cc = pixel (cc-2, rr) of the block
+// is occupied, or lies outside the image (the 5x5 test ignores those).  Walks the row one occupancy cell at a time.
+__device__ __forceinline__ uint32_t bitmap_row(const UnpackArgs& a, const uint8_t* occ_f, int32_t x0, int32_t y0, int32_t sx,
+                                               int32_t sy) {
+  // pixel cc of the row is (x0 + sx*cc, y0 + sy*cc); exactly one of sx, sy is non-zero
+  const int32_t W = (int32_t)a.W, H = (int32_t)a.H, lp = a.prec_shift;
+  const bool along_x = sx != 0;
+  const int32_t fixed = along_x ? y0 : x0, flim = along_x ? H : W;
+  if (fixed < 0 || fixed >= flim) return 0xFFFFFu;
+  const int32_t m0 = along_x ? x0 : y0, st = along_x ? sx : sy, mlim = along_x ? W : H;
+  const uint8_t* rowp = along_x ? occ_f + (uint64_t)(fixed >> lp) * a.in.occ_pitch : occ_f + (fixed >> lp);
+  const uint32_t cell_stride = along_x ? 1u : a.in.occ_pitch;
+  const int32_t pm = (1 << lp) - 1;
+  uint32_t bits = 0;
+  int32_t cc = 0;
+  while (cc < 20) {
+    const int32_t m = m0 + st * cc;
+    if (m < 0 || m >= mlim) { bits |= 1u << cc; ++cc; continue; }
+    const int32_t run = min(20 - cc, st > 0 ? (pm + 1) - (m & pm) : (m & pm) + 1);     // pixels left inside this cell
+    if (rowp[(uint64_t)(m >> lp) * cell_stride] != 0) bits |= ((1u << run) - 1u) << cc;
+    cc += run;
+  }
+  // a cell run may have crossed the image edge (image size not a multiple of the precision): those pixels count as set
+  return bits | (st > 0 ? (m0 + 19 >= mlim ? (0xFFFFFu << max(mlim - m0, 0)) & 0xFFFFFu : 0u)
+                        : (m0 - 19 < 0 ? (0xFFFFFu << max(m0 + 1, 0)) & 0xFFFFFu : 0u));
+}
 
 // kMode 0: fused single pass (chained scan) ; 1: count only ; 2: emit with tile bases.  kDebug adds the streams the
 // reference materialises but nobody downstream needs (colors16bit, partition, point_to_pixel, boundary types).
 //
-// CTA protocol (no __syncthreads after the prologue): every warp posts its slot's point count, then stages its output
-// in shared memory BEFORE the tile's base is known; the first warp that gets that far claims the look-back, publishes the
-// base, and everybody copies out.  Look-back latency therefore overlaps the other warps' staging work.
+// CTA protocol (no __syncthreads after the prologue): every warp posts its slot's point count as soon as the geometry
+// planes are in; the warp that posts last does the look-back for the tile and publishes the base while the others are
+// still staging their output in shared memory; everybody copies out once the base is there.
 template <int kMode, bool kSmooth, bool kDebug>
 __global__ void __launch_bounds__(kWarpsPerTile * 32, UnpackTraits<kSmooth, kDebug>::kMinCtas)
 unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_tot[kWarpsPerTile];
   __shared__ uint32_t s_nlog[kWarpsPerTile][2];
-  __shared__ uint32_t s_posted, s_claim, s_ready, s_base;
+  __shared__ uint32_t s_posted, s_ready, s_base;
 
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t tile = blockIdx.x + tile_offset;
-  const uint32_t slot = tile * kWarpsPerTile + warp;
-  if (threadIdx.x == 0) { s_posted = 0; s_claim = 0; s_ready = 0; }
   const uint32_t frame = a.tile_frame[tile];
-  const uint32_t pid = a.slot_patch[slot];
+  const uint32_t first_tile = a.frame_tile_begin[frame];
+  const uint32_t n_owned = a.owned_count[frame];
+  const uint32_t pos_in_frame = (tile - first_tile) * kWarpsPerTile + warp;   // index into the frame's owned-slot list
+  const uint32_t lpos = tile * kWarpsPerTile + warp;                          // global position (log index)
+  if ((tile - first_tile) * kWarpsPerTile >= n_owned) {                       // tile past the end of the list: nothing to do
+    if (kMode == 1 && threadIdx.x == 0) a.tile_total[tile] = 0;
+    if (kSmooth && lane == 0) {
+      if (a.sm.geo.on) a.sm.geo.log_count[lpos - a.sm.group_first_slot] = 0;
+      if (a.sm.col.on) a.sm.col.log_count[lpos - a.sm.group_first_slot] = 0;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) { s_posted = 0; s_ready = 0; }
+  const bool active = pos_in_frame < n_owned;
+  const uint32_t slot = active ? a.owned[(uint64_t)first_tile * kWarpsPerTile + pos_in_frame] : 0u;
+  SlotRec R;
+  R.pid = kNoPatch; R.u0b = R.v0b = R.bx = R.by = 0; R.ax = R.ay = R.rx = R.ry = 0;
+  if (active) R = load_slot_rec(a.slot_rec + slot);
   const uint32_t res = a.res;
   __syncthreads();                                               // the only block-wide barrier
 
@@ -598,28 +674,17 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   uint8_t* s_rgb = wsm + kStagePosBytes;
   uint32_t* s_bmp = reinterpret_cast<uint32_t*>(wsm + kStagePosBytes + kStageRgbBytes);
 
-  DevPatch P;
-  bool owned = false, fast = false;
-  int32_t bx = 0, by = 0;
-  uint32_t u0b = 0, v0b = 0;
-  if (pid != kNoPatch) {
-    P = a.patches[pid];
-    const uint32_t s = slot - P.slot_base;
-    v0b = s / P.size_u0; u0b = s - v0b * P.size_u0;
-    int64_t bxx, byy;
-    patch_to_canvas(P, u0b, v0b, 1, 1, bxx, byy);                 // codec.rs:373-378
-    bx = (int32_t)bxx; by = (int32_t)byy;
-    owned = __ldg(a.block_to_patch + (uint64_t)frame * a.bw * a.bh + (uint64_t)by * a.bw + bx) == P.local_index + 1;   // codec.rs:379
-    fast = owned && res == 16 && a.prec_shift >= 0 && P.aligned;
-  }
   const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
+  const int32_t bx = R.bx, by = R.by;
+  const uint32_t u0b = R.u0b, v0b = R.v0b;
+  const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
 
-  // smoothing: this slot's log regions (table slots it added to); every slot of the group writes its counts
+  // smoothing: this slot's log regions (table slots it added to); every position of the group writes its counts
   const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
   uint32_t* log_geo = nullptr; uint32_t* log_col = nullptr;
   uint32_t n_log_geo = 0, n_log_col = 0;
   if (kSmooth) {
-    const uint64_t ls = (uint64_t)(slot - a.sm.group_first_slot) * a.sm.log_stride;
+    const uint64_t ls = (uint64_t)(lpos - a.sm.group_first_slot) * a.sm.log_stride;
     if (a.sm.geo.on) log_geo = a.sm.geo.log + ls;
     if (a.sm.col.on) log_col = a.sm.col.log + ls;
   }
@@ -632,138 +697,163 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   uint32_t m1 = 0, m2 = 0;               // bit j set = pixel j of this lane emits >= 1 / 2 points
   uint32_t total = 0, lane_excl = 0;
   int32_t xs = 0, ys = 0;                // canvas position of this lane's pixel 0; pixel j is (xs + ax*j, ys + ay*j)
-  const int32_t ax = pid != kNoPatch ? P.ax : 0, ay = pid != kNoPatch ? P.ay : 0;
+  DevPatch P;
+  bool fast = false;
 
-  if (fast) {
-    const int32_t cx0 = bx * 16 + ((P.ax < 0 || P.rx < 0) ? 15 : 0);
-    const int32_t cy0 = by * 16 + ((P.ay < 0 || P.ry < 0) ? 15 : 0);
-    xs = cx0 + P.ax * 8 * h + P.rx * r;
-    ys = cy0 + P.ay * 8 * h + P.ry * r;
-    const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
-    const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
-    const bool attr = kMode != 1 && a.has_attr;
-    const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride;
-    const uint16_t* ay1 = ay0 + a.in.attr_y_map_stride;
-    const uint64_t cf = (uint64_t)frame * 2 * a.in.attr_c_map_stride;
-    const uint16_t* au0 = a.in.attr_u + cf; const uint16_t* au1 = au0 + a.in.attr_c_map_stride;
-    const uint16_t* av0 = a.in.attr_v + cf; const uint16_t* av1 = av0 + a.in.attr_c_map_stride;
-    if (ax == 1) {
-      // Default-like rows: the 8 pixels are 16 contiguous bytes of every plane
-      const uint32_t goff = (uint32_t)ys * a.in.geo_pitch + (uint32_t)xs;
-      const uint4 g0 = ldg_nc_v4(geo0 + goff);
-      const uint4 g1 = ldg_nc_v4(geo1 + goff);
-      uint4 ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
-      uint2 ua = {0, 0}, va = {0, 0}, ub = {0, 0}, vb = {0, 0};
-      if (attr) {
-        const uint32_t yoff = (uint32_t)ys * a.in.attr_pitch_y + (uint32_t)xs;
-        ya = ldg_nc_v4(ay0 + yoff); yb = ldg_nc_v4(ay1 + yoff);
-        const uint32_t coff = (uint32_t)(ys >> 1) * a.in.attr_pitch_c + (uint32_t)(xs >> 1);
-        ua = ldg_nc_v2(au0 + coff); va = ldg_nc_v2(av0 + coff);
-        ub = ldg_nc_v2(au1 + coff); vb = ldg_nc_v2(av1 + coff);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
-        nn[j] = __byte_perm(word_of(g0, j >> 1), word_of(g1, j >> 1), sel);      // raw samples, converted below
-        yy[j] = __byte_perm(word_of(ya, j >> 1), word_of(yb, j >> 1), sel);
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t sel = (c & 1) ? 0x7632u : 0x5410u;
-        cA[c] = __byte_perm(word_of(ua, c >> 1), word_of(va, c >> 1), sel);
-        cB[c] = __byte_perm(word_of(ub, c >> 1), word_of(vb, c >> 1), sel);
-      }
-    } else {
-      // transposed / mirrored: eight 2-byte loads per plane; across the warp every load still covers whole 32-byte sectors
-      const int32_t dstep = ay * (int32_t)a.in.geo_pitch + ax;
-      const int32_t goff = ys * (int32_t)a.in.geo_pitch + xs;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int32_t o = goff + j * dstep;
-        nn[j] = ldg_nc_u16(geo0 + o) | (ldg_nc_u16(geo1 + o) << 16);
-      }
-      if (attr) {
-        const int32_t ystep = ay * (int32_t)a.in.attr_pitch_y + ax;
-        const int32_t yoff = ys * (int32_t)a.in.attr_pitch_y + xs;
+  if (active) {
+    // the plane addresses depend only on the slot record: issue the loads, then fetch the patch
+    const bool can_fast = res == 16 && a.prec_shift >= 0 && (ax != 0 || ay != 0) &&
+                          (a.spec_orientation || ((ax | ay) >= 0 && (rx | ry) >= 0));   // aligned <=> no flip, or SPEC mode
+    fast = can_fast;
+    if (fast) {
+      const int32_t cx0 = bx * 16 + ((ax < 0 || rx < 0) ? 15 : 0);
+      const int32_t cy0 = by * 16 + ((ay < 0 || ry < 0) ? 15 : 0);
+      xs = cx0 + ax * 8 * h + rx * r;
+      ys = cy0 + ay * 8 * h + ry * r;
+      const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
+      const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
+      const bool attr = kMode != 1 && a.has_attr;
+      const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride;
+      const uint16_t* ay1 = ay0 + a.in.attr_y_map_stride;
+      const uint64_t cf = (uint64_t)frame * 2 * a.in.attr_c_map_stride;
+      const uint16_t* au0 = a.in.attr_u + cf; const uint16_t* au1 = au0 + a.in.attr_c_map_stride;
+      const uint16_t* av0 = a.in.attr_v + cf; const uint16_t* av1 = av0 + a.in.attr_c_map_stride;
+      if (ax == 1) {
+        // Default-like rows: the 8 pixels are 16 contiguous bytes of every plane
+        const uint32_t goff = (uint32_t)ys * a.in.geo_pitch + (uint32_t)xs;
+        const uint4 g0 = ldg_nc_v4(geo0 + goff);
+        const uint4 g1 = ldg_nc_v4(geo1 + goff);
+        uint4 ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
+        uint2 ua = {0, 0}, va = {0, 0}, ub = {0, 0}, vb = {0, 0};
+        if (attr) {
+          const uint32_t yoff = (uint32_t)ys * a.in.attr_pitch_y + (uint32_t)xs;
+          ya = ldg_nc_v4(ay0 + yoff); yb = ldg_nc_v4(ay1 + yoff);
+          const uint32_t coff = (uint32_t)(ys >> 1) * a.in.attr_pitch_c + (uint32_t)(xs >> 1);
+          ua = ldg_nc_v2(au0 + coff); va = ldg_nc_v2(av0 + coff);
+          ub = ldg_nc_v2(au1 + coff); vb = ldg_nc_v2(av1 + coff);
+        }
+        P = a.patches[R.pid];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int32_t o = yoff + j * ystep;
-          yy[j] = ldg_nc_u16(ay0 + o) | (ldg_nc_u16(ay1 + o) << 16);
+          const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+          nn[j] = __byte_perm(word_of(g0, j >> 1), word_of(g1, j >> 1), sel);      // raw samples, converted below
+          yy[j] = __byte_perm(word_of(ya, j >> 1), word_of(yb, j >> 1), sel);
         }
-        const int32_t cstep = ay * (int32_t)a.in.attr_pitch_c + ax;
-        const int32_t coff = (ys >> 1) * (int32_t)a.in.attr_pitch_c + (xs >> 1);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int32_t o = coff + c * cstep;
-          cA[c] = ldg_nc_u16(au0 + o) | (ldg_nc_u16(av0 + o) << 16);
-          cB[c] = ldg_nc_u16(au1 + o) | (ldg_nc_u16(av1 + o) << 16);
+          const uint32_t sel = (c & 1) ? 0x7632u : 0x5410u;
+          cA[c] = __byte_perm(word_of(ua, c >> 1), word_of(va, c >> 1), sel);
+          cB[c] = __byte_perm(word_of(ub, c >> 1), word_of(vb, c >> 1), sel);
         }
       } else {
+        // transposed / mirrored: eight 2-byte loads per plane; across the warp every load still covers whole 32-byte sectors
+        const int32_t dstep = ay * (int32_t)a.in.geo_pitch + ax;
+        const int32_t goff = ys * (int32_t)a.in.geo_pitch + xs;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) yy[j] = 0;
+        for (int j = 0; j < 8; ++j) {
+          const int32_t o = goff + j * dstep;
+          nn[j] = ldg_nc_u16(geo0 + o) | (ldg_nc_u16(geo1 + o) << 16);
+        }
+        if (attr) {
+          const int32_t ystep = ay * (int32_t)a.in.attr_pitch_y + ax;
+          const int32_t yoff = ys * (int32_t)a.in.attr_pitch_y + xs;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { cA[c] = 0; cB[c] = 0; }
+          for (int j = 0; j < 8; ++j) {
+            const int32_t o = yoff + j * ystep;
+            yy[j] = ldg_nc_u16(ay0 + o) | (ldg_nc_u16(ay1 + o) << 16);
+          }
+          const int32_t cstep = ay * (int32_t)a.in.attr_pitch_c + ax;
+          const int32_t coff = (ys >> 1) * (int32_t)a.in.attr_pitch_c + (xs >> 1);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int32_t o = coff + c * cstep;
+            cA[c] = ldg_nc_u16(au0 + o) | (ldg_nc_u16(av0 + o) << 16);
+            cB[c] = ldg_nc_u16(au1 + o) | (ldg_nc_u16(av1 + o) << 16);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) yy[j] = 0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { cA[c] = 0; cB[c] = 0; }
+        }
+        P = a.patches[R.pid];
       }
-    }
-    // occupancy of the 8 pixels (codec.rs:393-396: any non-zero sample counts).  Pixels j*p .. j*p+p-1 share a sample.
-    {
-      const int32_t lp = a.prec_shift;
-      const int32_t p = 1 << lp;
-      const int32_t nb = lp >= 3 ? 1 : (8 >> lp);
-      const uint32_t ones = lp >= 3 ? 0xFFu : ((1u << p) - 1u);
-      for (int32_t k = 0; k < nb; ++k) {
-        const int32_t j = k << lp;
-        const uint32_t ox = (uint32_t)(xs + ax * j) >> lp, oy = (uint32_t)(ys + ay * j) >> lp;
-        if (occ_f[(uint64_t)oy * a.in.occ_pitch + ox] != 0) m1 |= ones << j;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      nn[j] = normals_of(P, nn[j] & 0xFFFFu, nn[j] >> 16, a.absolute_d1);
-      if ((nn[j] >> 16) != (nn[j] & 0xFFFFu)) m2 |= (m1 & (1u << j));            // codec.rs:422-428 duplicate skip
-    }
-    const uint32_t c = __popc(m1) + __popc(m2);
-    uint32_t incl = c;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(kFull, incl, d);
-      if (lane >= (uint32_t)d) incl += t;
-    }
-    total = __shfl_sync(kFull, incl, 31);
-    lane_excl = incl - c;
-  } else if (owned) {
-    // generic path (any resolution, reference-literal rotated orientations): lane = pixel, 32 at a time
-    const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
-    const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
-    const int64_t sscale = a.spec_orientation ? res : 1;
-    for (uint32_t base = 0; base < res * res; base += 32) {
-      const uint32_t i = base + lane;
-      uint32_t c = 0;
-      if (i < res * res) {
-        const uint32_t v1 = i / res, u1 = i - v1 * res;
-        int64_t x, y;
-        patch_to_canvas(P, (int64_t)u0b * res + u1, (int64_t)v0b * res + v1, res, sscale, x, y);
-        if (occ_at(a, occ_f, (uint32_t)x, (uint32_t)y)) {
-          const uint64_t off = (uint64_t)y * a.in.geo_pitch + (uint64_t)x;
-          const uint32_t n = normals_of(P, geo0[off], geo1[off], a.absolute_d1);
-          c = (n >> 16) != (n & 0xFFFFu) ? 2u : 1u;
+      // occupancy of the 8 pixels (codec.rs:393-396: any non-zero sample counts).  Pixels j*p .. j*p+p-1 share a sample.
+      {
+        const int32_t lp = a.prec_shift;
+        const int32_t p = 1 << lp;
+        const int32_t nb = lp >= 3 ? 1 : (8 >> lp);
+        const uint32_t ones = lp >= 3 ? 0xFFu : ((1u << p) - 1u);
+        for (int32_t k = 0; k < nb; ++k) {
+          const int32_t j = k << lp;
+          const uint32_t ox = (uint32_t)(xs + ax * j) >> lp, oy = (uint32_t)(ys + ay * j) >> lp;
+          if (occ_f[(uint64_t)oy * a.in.occ_pitch + ox] != 0) m1 |= ones << j;
         }
       }
-      total += __reduce_add_sync(kFull, c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        nn[j] = normals_of(P, nn[j] & 0xFFFFu, nn[j] >> 16, a.absolute_d1);
+        if ((nn[j] >> 16) != (nn[j] & 0xFFFFu)) m2 |= (m1 & (1u << j));            // codec.rs:422-428 duplicate skip
+      }
+      const uint32_t c = __popc(m1) + __popc(m2);
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+      }
+      total = __shfl_sync(kFull, incl, 31);
+      lane_excl = incl - c;
+    } else {
+      // generic path (any resolution / precision, reference-literal rotated orientations): lane = pixel, 32 at a time
+      P = a.patches[R.pid];
+      const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
+      const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
+      const int64_t sscale = a.spec_orientation ? res : 1;
+      for (uint32_t base = 0; base < res * res; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t c = 0;
+        if (i < res * res) {
+          const uint32_t v1 = i / res, u1 = i - v1 * res;
+          int64_t x, y;
+          patch_to_canvas(P, (int64_t)u0b * res + u1, (int64_t)v0b * res + v1, res, sscale, x, y);
+          if (occ_at(a, occ_f, (uint32_t)x, (uint32_t)y)) {
+            const uint64_t off = (uint64_t)y * a.in.geo_pitch + (uint64_t)x;
+            const uint32_t n = normals_of(P, geo0[off], geo1[off], a.absolute_d1);
+            c = (n >> 16) != (n & 0xFFFFu) ? 2u : 1u;
+          }
+        }
+        total += __reduce_add_sync(kFull, c);
+      }
     }
   }
 
-  // post this slot's count
-  if (lane == 0) {
-    s_tot[warp] = total;
-    s_nlog[warp][0] = 0; s_nlog[warp][1] = 0;
-    __threadfence_block();
-    const uint32_t prev = atomicAdd(&s_posted, 1u);
-    if (kMode == 1 && prev == kWarpsPerTile - 1) {               // count-only launch: the last poster sums the tile
-      uint32_t t = 0;
+  // ---- post this slot's count; the last warp to post resolves the tile's base -----------------------------------------
+  {
+    uint32_t prev = 0;
+    if (lane == 0) {
+      s_tot[warp] = total;
+      s_nlog[warp][0] = 0; s_nlog[warp][1] = 0;
+      __threadfence_block();
+      prev = atomicAdd(&s_posted, 1u);
+    }
+    prev = __shfl_sync(kFull, prev, 0);
+    if (prev == kWarpsPerTile - 1) {
+      __threadfence_block();
+      uint32_t tile_sum = 0;
 #pragma unroll
-      for (int w = 0; w < kWarpsPerTile; ++w) t += reinterpret_cast<volatile uint32_t*>(s_tot)[w];
-      a.tile_total[tile] = t;
+      for (int w = 0; w < kWarpsPerTile; ++w) tile_sum += reinterpret_cast<volatile uint32_t*>(s_tot)[w];
+      if (kMode == 1) {
+        if (lane == 0) a.tile_total[tile] = tile_sum;
+      } else {
+        const uint32_t excl = kMode == 2 ? a.tile_total[tile] : tile_lookback(a, tile, first_tile, tile_sum, lane);
+        if (lane == 0) {
+          if ((tile - first_tile + 1) * kWarpsPerTile >= n_owned) a.frame_count[frame] = excl + tile_sum;  // codec.rs:482
+          s_base = excl;
+          __threadfence_block();
+          *reinterpret_cast<volatile uint32_t*>(&s_ready) = 1u;
+        }
+      }
     }
   }
   if (kMode == 1) return;
@@ -772,21 +862,33 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   const bool w_rgb = a.out.rgb != nullptr;
   const bool want_bt = kSmooth || (kDebug && a.out.btype != nullptr);
   uint32_t bt1 = 0, bt2 = 0;             // bit j: pixel j is a type-1 / type-2 boundary pixel (meaningful where m1 is set)
-  const uint32_t T0 = ((u0b * 16u + 8u * (uint32_t)h) * P.lod_x + P.u1);                  // decoder.rs:875 at j = 0
-  const uint32_t Bc = ((v0b * 16u + (uint32_t)r) * P.lod_y + P.v1) & 0xFFFFu;            // decoder.rs:876
+  uint32_t T0 = 0, Bc = 0;
 
   if (fast && total) {
+    T0 = ((u0b * 16u + 8u * (uint32_t)h) * P.lod_x + P.u1);                  // decoder.rs:875 at j = 0
+    Bc = ((v0b * 16u + (uint32_t)r) * P.lod_y + P.v1) & 0xFFFFu;            // decoder.rs:876
     // generate_point (decoder.rs:871-878) stores normal, tangent, bitangent in that order; the selectors reproduce
     // "later stores overwrite earlier ones" and leave unset coordinates at 0
     const uint32_t s0 = sel_of_src(axis_source(P, 0)), s1 = sel_of_src(axis_source(P, 1)), s2 = sel_of_src(axis_source(P, 2));
     const uint32_t selA = s0 | (s1 << 8), selB = s2 | 0x7600u;
+
+    // chroma terms: the two lanes of a row pair (l, l^2) read the same chroma samples; one of them evaluates map 0, the
+    // other map 1, and they swap the results (three integers per sample, the flag travels in bit 0 of the blue term)
+    const bool odd = (lane & 2u) != 0;
     uint32_t k = lane_excl;
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {                                            // chroma column: pixels 2cc, 2cc+1
-      if (!((m1 >> (2 * cc)) & 3u)) continue;
       ChromaTerm ta, tb;
-      const uint32_t Ua = cA[cc] & 0xFFFFu, Va = cA[cc] >> 16, Ub = cB[cc] & 0xFFFFu, Vb = cB[cc] >> 16;   // decoder.rs:976-977
-      if (w_rgb) { ta = chroma_term(Ua, Va); tb = chroma_term(Ub, Vb); }
+      if (w_rgb) {
+        const uint32_t uv = odd ? cB[cc] : cA[cc];                              // decoder.rs:976-977
+        const ChromaTerm t = chroma_term(uv & 0xFFFFu, uv >> 16);
+        const int32_t mr = t.ir, mg = t.ig, mb = (int32_t)(((uint32_t)t.ib << 1) | t.flagged);
+        const int32_t orr = __shfl_xor_sync(kFull, mr, 2), og = __shfl_xor_sync(kFull, mg, 2), ob = __shfl_xor_sync(kFull, mb, 2);
+        const int32_t ab = odd ? ob : mb, bb = odd ? mb : ob;
+        ta.ir = odd ? orr : mr; ta.ig = odd ? og : mg; ta.ib = ab >> 1; ta.flagged = (uint32_t)ab & 1u;
+        tb.ir = odd ? mr : orr; tb.ig = odd ? mg : og; tb.ib = bb >> 1; tb.flagged = (uint32_t)bb & 1u;
+      }
+      if (!((m1 >> (2 * cc)) & 3u)) continue;
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
         const int j = 2 * cc + jj;
@@ -795,13 +897,14 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
         {                                                                         // map 0 (codec.rs:421, i == 0)
           const uint32_t A = (nn[j] & 0xFFFFu) | (t << 16);
           *reinterpret_cast<uint2*>(s_pos + spos_off(k)) = make_uint2(__byte_perm(A, Bc, selA), __byte_perm(A, Bc, selB));
-          if (w_rgb) *reinterpret_cast<uint32_t*>(s_rgb + srgb_off(k)) = yuv_to_rgb_term(yy[j] & 0xFFFFu, Ua, Va, ta);   // codec.rs:637-640
+          if (w_rgb) *reinterpret_cast<uint32_t*>(s_rgb + srgb_off(k)) =
+              yuv_to_rgb_term(yy[j] & 0xFFFFu, cA[cc] & 0xFFFFu, cA[cc] >> 16, ta);   // codec.rs:637-640
           ++k;
         }
         if ((m2 >> j) & 1u) {                                                     // map 1 unless it duplicates map 0
           const uint32_t A = (nn[j] >> 16) | (t << 16);
           *reinterpret_cast<uint2*>(s_pos + spos_off(k)) = make_uint2(__byte_perm(A, Bc, selA), __byte_perm(A, Bc, selB));
-          if (w_rgb) *reinterpret_cast<uint32_t*>(s_rgb + srgb_off(k)) = yuv_to_rgb_term(yy[j] >> 16, Ub, Vb, tb);
+          if (w_rgb) *reinterpret_cast<uint32_t*>(s_rgb + srgb_off(k)) = yuv_to_rgb_term(yy[j] >> 16, cB[cc] & 0xFFFFu, cB[cc] >> 16, tb);
           ++k;
         }
       }
@@ -809,24 +912,11 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
 
     // ---- K5: boundary types from a 20x20 occupancy bitmap of the block and its 2-pixel margin (patch-local axes) ----
     if (want_bt) {
-      const int32_t W = (int32_t)a.W, H = (int32_t)a.H, lp = a.prec_shift;
-      const int32_t cx0 = xs - P.ax * 8 * h - P.rx * r, cy0 = ys - P.ay * 8 * h - P.ry * r;   // canvas of patch-local (0,0)
+      const int32_t W = (int32_t)a.W, H = (int32_t)a.H;
+      const int32_t cx0 = xs - ax * 8 * h - rx * r, cy0 = ys - ay * 8 * h - ry * r;   // canvas of patch-local (0,0)
       if (lane < 20) {
         const int32_t rr = (int32_t)lane - 2;
-        uint32_t bits = 0;
-        int32_t pox = -1, poy = -1; uint32_t pv = 0;
-        for (int32_t cc = 0; cc < 20; ++cc) {
-          const int32_t aa = cc - 2;
-          const int32_t x = cx0 + P.ax * aa + P.rx * rr, y = cy0 + P.ay * aa + P.ry * rr;
-          uint32_t o = 1;                                        // outside the image: ignored by the 5x5 test
-          if (x >= 0 && y >= 0 && x < W && y < H) {
-            const int32_t ox = x >> lp, oy = y >> lp;
-            if (ox != pox || oy != poy) { pox = ox; poy = oy; pv = occ_f[(uint64_t)oy * a.in.occ_pitch + ox]; }
-            o = pv != 0;
-          }
-          bits |= o << cc;
-        }
-        s_bmp[lane] = bits;
+        s_bmp[lane] = bitmap_row(a, occ_f, cx0 - 2 * ax + rx * rr, cy0 - 2 * ay + ry * rr, ax, ay);
       }
       __syncwarp();
       const uint32_t r0 = s_bmp[r], r1 = s_bmp[r + 1], r2 = s_bmp[r + 2], r3 = s_bmp[r + 3], r4 = s_bmp[r + 4];
@@ -848,10 +938,14 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
     __syncwarp();
 
     // ---- K6 statistics: geometry cells over ALL points of the slot ---------------------------------------------------
+    // Every lane holds up to 16 points (8 pixels x 2 maps) as (key, packed contribution).  Rounds: each lane takes its
+    // smallest remaining cell key and sums its own matching points; lanes that hold the same key merge along a butterfly
+    // (the rows of a cell are neighbouring lanes); whoever still holds a non-zero count issues the reductions.  Exact for
+    // any input: a missed merge only means two reductions instead of one.
     if (kSmooth && a.sm.geo.on) {
       const GridDesc& G = a.sm.geo;
       const bool perm = ((1u << P.normal) | (1u << P.tangent) | (1u << P.bitangent)) == 7u;
-      if (perm) {
+      if (perm && G.g <= 64u) {
         const uint32_t shN = 10u * P.normal, shT = 10u * P.tangent, shB = 10u * P.bitangent;
         const uint32_t g = G.g;
         const uint32_t cBc = cell_div(Bc, G), relB = Bc - cBc * g;
@@ -866,9 +960,9 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
           const uint32_t n0 = nn[j] & 0xFFFFu, n1 = nn[j] >> 16;
           const uint32_t c0 = cell_div(n0, G), c1 = cell_div(n1, G);
           key[2 * j] = (okTB && n0 < G.th) ? (kTB | (c0 << shN)) : kCellEmpty;
-          val[2 * j] = 1u | ((n0 - c0 * g) << 5) | (relT << 17);
+          val[2 * j] = 1u | ((n0 - c0 * g) << 6) | (relT << 18);      // count (<= 16) | sum relN (<= 1008) | sum relT
           key[2 * j + 1] = (okTB && ((m2 >> j) & 1u) && n1 < G.th) ? (kTB | (c1 << shN)) : kCellEmpty;
-          val[2 * j + 1] = 1u | ((n1 - c1 * g) << 5) | (relT << 17);
+          val[2 * j + 1] = 1u | ((n1 - c1 * g) << 6) | (relT << 18);
         }
         uint32_t cur = kCellEmpty;
 #pragma unroll
@@ -880,40 +974,44 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
             if (key[i] == cur) acc += val[i];
             else if (key[i] > cur) nxt = min(nxt, key[i]);
           }
-          uint32_t cnt = cur != kCellEmpty ? (acc & 31u) : 0u;
-          uint32_t sN = cnt ? ((acc >> 5) & 0xFFFu) : 0u, sT = cnt ? (acc >> 17) : 0u, sB = cnt * relB;
+          // packed partial sums: w0 = count | sumN << 16, w1 = sumT | sumB << 16 (each sum <= 512 * 63 < 2^15)
+          uint32_t w0 = 0, w1 = 0;
+          if (cur != kCellEmpty) {
+            const uint32_t cnt = acc & 63u;
+            w0 = cnt | (((acc >> 6) & 0xFFFu) << 16);
+            w1 = (acc >> 18) | ((cnt * relB) << 16);
+          }
           // merge lanes holding the same cell: the other half-row (xor 1) and the neighbouring rows (xor 2..16)
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
             const uint32_t ok = __shfl_xor_sync(kFull, cur, d);
-            const uint32_t oc = __shfl_xor_sync(kFull, cnt, d);
-            const uint32_t oN = __shfl_xor_sync(kFull, sN, d);
-            const uint32_t oT = __shfl_xor_sync(kFull, sT, d);
-            const uint32_t oB = __shfl_xor_sync(kFull, sB, d);
-            if (ok == cur && cur != kCellEmpty) {
-              if (lane & (uint32_t)d) { cnt = 0; sN = 0; sT = 0; sB = 0; }
-              else { cnt += oc; sN += oN; sT += oT; sB += oB; }
+            const uint32_t o0 = __shfl_xor_sync(kFull, w0, d);
+            const uint32_t o1 = __shfl_xor_sync(kFull, w1, d);
+            if (ok == cur) {
+              if (lane & (uint32_t)d) { w0 = 0; w1 = 0; }
+              else { w0 += o0; w1 += o1; }
             }
           }
-          const bool fl = cnt != 0;
+          const uint32_t cnt = w0 & 0xFFFFu;
           uint32_t cs = kCellEmpty;
-          if (fl) {
+          if (cnt != 0) {
             cs = cell_slot(G, fig, cur, a.err);
             if (cs != kCellEmpty) {
+              const uint32_t sN = w0 >> 16, sT = w1 & 0xFFFFu, sB = w1 >> 16;
               const uint32_t sx = P.normal == 0 ? sN : P.tangent == 0 ? sT : sB;
               const uint32_t sy = P.normal == 1 ? sN : P.tangent == 1 ? sT : sB;
               const uint32_t sz = P.normal == 2 ? sN : P.tangent == 2 ? sT : sB;
               geo_cell_add(G, fig, cs, P.local_index, cnt, sx, sy, sz);
             }
           }
-          const uint32_t fm = __ballot_sync(kFull, fl && cs != kCellEmpty);
-          if (fl && cs != kCellEmpty) log_geo[n_log_geo + __popc(fm & ((1u << lane) - 1u))] = cs;
+          const uint32_t fm = __ballot_sync(kFull, cs != kCellEmpty);
+          if (cs != kCellEmpty) log_geo[n_log_geo + __popc(fm & ((1u << lane) - 1u))] = cs;
           n_log_geo += __popc(fm);
           cur = nxt;
         }
       } else {
-        // axes that are not a permutation (never produced by the reference's set_view_id): per-point reductions on the
-        // staged positions
+        // axes that are not a permutation (never produced by the reference's set_view_id) or very coarse grids:
+        // per-point reductions on the staged positions
         for (uint32_t kb = 0; kb < total; kb += 32) {
           const uint32_t kk = kb + lane;
           uint32_t cs = kCellEmpty;
@@ -940,77 +1038,61 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
       const uint32_t sel_mask = m1 & bt2;
       if (__any_sync(kFull, sel_mask != 0)) {
         uint32_t k = lane_excl;
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 8; ++j) {
           const bool on = (m1 >> j) & 1u, two = (m2 >> j) & 1u;
           const bool sel = (sel_mask >> j) & 1u;
-          uint32_t cs0 = kCellEmpty, cs1 = kCellEmpty;
-          if (sel) {
-            const uint32_t U0 = cA[j >> 1] & 0xFFFFu, V0 = cA[j >> 1] >> 16, U1 = cB[j >> 1] & 0xFFFFu, V1 = cB[j >> 1] >> 16;
-            const uint32_t Y0 = yy[j] & 0xFFFFu, Y1 = yy[j] >> 16;
-            const uint2 p0 = *reinterpret_cast<const uint2*>(s_pos + spos_off(k));
-            const uint32_t key0 = cell_key_of(G, p0.x & 0xFFFFu, p0.x >> 16, p0.y & 0xFFFFu);
-            uint32_t key1 = kCellEmpty;
-            if (two) {
-              const uint2 p1 = *reinterpret_cast<const uint2*>(s_pos + spos_off(k + 1));
-              key1 = cell_key_of(G, p1.x & 0xFFFFu, p1.x >> 16, p1.y & 0xFFFFu);
-            }
-            if (key0 != kCellEmpty) {
-              cs0 = cell_slot(G, fig, key0, a.err);
-              if (cs0 != kCellEmpty) {
-                if (key1 == key0) {
-                  col_cell_add(G, fig, cs0, P.local_index, 2, Y0 + Y1, U0 + U1, V0 + V1,
-                               (unsigned long long)Y0 * Y0 + (unsigned long long)Y1 * Y1);
-                  key1 = kCellEmpty;
-                } else {
-                  col_cell_add(G, fig, cs0, P.local_index, 1, Y0, U0, V0, (unsigned long long)Y0 * Y0);
+          if (__any_sync(kFull, sel)) {
+            uint32_t cs0 = kCellEmpty, cs1 = kCellEmpty;
+            if (sel) {
+              const uint32_t U0 = cA[j >> 1] & 0xFFFFu, V0 = cA[j >> 1] >> 16, U1 = cB[j >> 1] & 0xFFFFu, V1 = cB[j >> 1] >> 16;
+              const uint32_t Y0 = yy[j] & 0xFFFFu, Y1 = yy[j] >> 16;
+              const uint2 p0 = *reinterpret_cast<const uint2*>(s_pos + spos_off(k));
+              const uint32_t key0 = cell_key_of(G, p0.x & 0xFFFFu, p0.x >> 16, p0.y & 0xFFFFu);
+              uint32_t key1 = kCellEmpty;
+              if (two) {
+                const uint2 p1 = *reinterpret_cast<const uint2*>(s_pos + spos_off(k + 1));
+                key1 = cell_key_of(G, p1.x & 0xFFFFu, p1.x >> 16, p1.y & 0xFFFFu);
+              }
+              if (key0 != kCellEmpty) {
+                cs0 = cell_slot(G, fig, key0, a.err);
+                if (cs0 != kCellEmpty) {
+                  if (key1 == key0) {
+                    col_cell_add(G, fig, cs0, P.local_index, 2, Y0 + Y1, U0 + U1, V0 + V1,
+                                 (unsigned long long)Y0 * Y0 + (unsigned long long)Y1 * Y1);
+                    key1 = kCellEmpty;
+                  } else {
+                    col_cell_add(G, fig, cs0, P.local_index, 1, Y0, U0, V0, (unsigned long long)Y0 * Y0);
+                  }
                 }
               }
+              if (key1 != kCellEmpty) {
+                cs1 = cell_slot(G, fig, key1, a.err);
+                if (cs1 != kCellEmpty) col_cell_add(G, fig, cs1, P.local_index, 1, Y1, U1, V1, (unsigned long long)Y1 * Y1);
+              }
             }
-            if (key1 != kCellEmpty) {
-              cs1 = cell_slot(G, fig, key1, a.err);
-              if (cs1 != kCellEmpty) col_cell_add(G, fig, cs1, P.local_index, 1, Y1, U1, V1, (unsigned long long)Y1 * Y1);
-            }
+            const uint32_t f0 = __ballot_sync(kFull, cs0 != kCellEmpty);
+            if (cs0 != kCellEmpty) log_col[n_log_col + __popc(f0 & ((1u << lane) - 1u))] = cs0;
+            n_log_col += __popc(f0);
+            const uint32_t f1 = __ballot_sync(kFull, cs1 != kCellEmpty);
+            if (cs1 != kCellEmpty) log_col[n_log_col + __popc(f1 & ((1u << lane) - 1u))] = cs1;
+            n_log_col += __popc(f1);
           }
-          const uint32_t f0 = __ballot_sync(kFull, cs0 != kCellEmpty);
-          if (cs0 != kCellEmpty) log_col[n_log_col + __popc(f0 & ((1u << lane) - 1u))] = cs0;
-          n_log_col += __popc(f0);
-          const uint32_t f1 = __ballot_sync(kFull, cs1 != kCellEmpty);
-          if (cs1 != kCellEmpty) log_col[n_log_col + __popc(f1 & ((1u << lane) - 1u))] = cs1;
-          n_log_col += __popc(f1);
           k += (on ? 1u : 0u) + (two ? 1u : 0u);
         }
       }
     }
   }
 
-  // ---- tile base: the first warp to get here does the look-back for the whole tile --------------------------------
-  uint32_t claim = 0;
-  if (lane == 0) claim = atomicAdd(&s_claim, 1u);
-  claim = __shfl_sync(kFull, claim, 0);
-  if (claim == 0) {
-    while (*reinterpret_cast<volatile uint32_t*>(&s_posted) < (uint32_t)kWarpsPerTile) { }
-    __threadfence_block();
-    uint32_t tile_sum = 0;
-#pragma unroll
-    for (int w = 0; w < kWarpsPerTile; ++w) tile_sum += reinterpret_cast<volatile uint32_t*>(s_tot)[w];
-    const uint32_t first_tile = a.frame_tile_begin[frame];
-    const uint32_t excl = kMode == 2 ? a.tile_total[tile] : tile_lookback(a, tile, first_tile, tile_sum, lane);
-    if (lane == 0) {
-      if (tile + 1 == a.frame_tile_begin[frame + 1]) a.frame_count[frame] = excl + tile_sum;  // codec.rs:482
-      s_base = excl;
-      __threadfence_block();
-      *reinterpret_cast<volatile uint32_t*>(&s_ready) = 1u;
-    }
-  }
-  if (!owned || total == 0) {
+  if (!active || total == 0) {
     if (kSmooth && lane == 0) {
-      if (a.sm.geo.on) a.sm.geo.log_count[slot - a.sm.group_first_slot] = 0;
-      if (a.sm.col.on) a.sm.col.log_count[slot - a.sm.group_first_slot] = 0;
+      if (a.sm.geo.on) a.sm.geo.log_count[lpos - a.sm.group_first_slot] = 0;
+      if (a.sm.col.on) a.sm.col.log_count[lpos - a.sm.group_first_slot] = 0;
     }
     return;
   }
-  while (*reinterpret_cast<volatile uint32_t*>(&s_ready) == 0u) { }
+  // ---- wait for the tile base (published by the last-posting warp) ------------------------------------------------------
+  while (*reinterpret_cast<volatile uint32_t*>(&s_ready) == 0u) __nanosleep(64);
   __threadfence_block();
   uint32_t run_base = *reinterpret_cast<volatile uint32_t*>(&s_base);
   for (uint32_t w = 0; w < warp; ++w) run_base += reinterpret_cast<volatile uint32_t*>(s_tot)[w];
@@ -1026,8 +1108,8 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
     generic_slot_emit<kSmooth, kDebug>(a, P, frame, fig, u0b, v0b, gidx, log_geo, log_col, &s_nlog[warp][0]);
     __syncwarp();
     if (kSmooth && lane == 0) {
-      if (a.sm.geo.on) a.sm.geo.log_count[slot - a.sm.group_first_slot] = reinterpret_cast<volatile uint32_t*>(&s_nlog[warp][0])[0];
-      if (a.sm.col.on) a.sm.col.log_count[slot - a.sm.group_first_slot] = reinterpret_cast<volatile uint32_t*>(&s_nlog[warp][0])[1];
+      if (a.sm.geo.on) a.sm.geo.log_count[lpos - a.sm.group_first_slot] = reinterpret_cast<volatile uint32_t*>(&s_nlog[warp][0])[0];
+      if (a.sm.col.on) a.sm.col.log_count[lpos - a.sm.group_first_slot] = reinterpret_cast<volatile uint32_t*>(&s_nlog[warp][0])[1];
     }
     return;
   }
@@ -1036,7 +1118,7 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
 
   if (kDebug) {                                                    // streams only the stage API / tests ask for
     uint64_t k = gidx + lane_excl;
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (!((m1 >> j) & 1u)) continue;
       const uint32_t np = 1u + ((m2 >> j) & 1u);
@@ -1076,7 +1158,7 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
       } else {
         uint4* L = reinterpret_cast<uint4*>(a.sm.blist + (uint64_t)frame * a.sm.blist_cap + lbase + (incl - nb_lane));
         uint32_t k = lane_excl;
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (!((m1 >> j) & 1u)) continue;
           const uint32_t np = 1u + ((m2 >> j) & 1u);
@@ -1096,8 +1178,8 @@ unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
       }
     }
     if (lane == 0) {
-      if (a.sm.geo.on) a.sm.geo.log_count[slot - a.sm.group_first_slot] = n_log_geo;
-      if (a.sm.col.on) a.sm.col.log_count[slot - a.sm.group_first_slot] = n_log_col;
+      if (a.sm.geo.on) a.sm.geo.log_count[lpos - a.sm.group_first_slot] = n_log_geo;
+      if (a.sm.col.on) a.sm.col.log_count[lpos - a.sm.group_first_slot] = n_log_col;
     }
   }
 }
@@ -1401,6 +1483,12 @@ int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream) {
   if (n_slots == 0) return 0;
   const uint32_t blocks = (n_slots + 255) / 256;
   block_to_patch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, n_slots, const_cast<uint32_t*>(a.block_to_patch));
+  return after_launch();
+}
+
+int launch_compact_owned(const UnpackArgs& a, void* stream) {
+  if (a.n_frames == 0) return 0;
+  compact_owned_kernel<<<a.n_frames, 1024, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
 }
 

@@ -242,9 +242,10 @@ struct Batch {
   bool smoothing_geo = false, smoothing_col = false;
 
   std::vector<DevPatch> h_patches;
-  std::vector<uint32_t> h_slot_patch, h_tile_frame, h_ftb;
+  std::vector<SlotRec> h_slot_rec;
+  std::vector<uint32_t> h_tile_frame, h_ftb;
 
-  DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_status, d_tile_total, d_count, d_err;
+  DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_status, d_tile_total, d_count, d_err, d_owned, d_owned_count;
   DevBuf d_pos, d_rgb, d_yuv, d_part, d_pix, d_bt, d_occ_full, d_pos_pre, d_yuv_pre;
   DevBuf d_geotab, d_coltab, d_geokeys, d_colkeys, d_geolog, d_collog, d_geolog_count, d_collog_count, d_changed, d_blist,
       d_blist_count;
@@ -274,7 +275,8 @@ struct Batch {
   ~Batch() { destroy(); }
   void destroy() {
     cudaSetDevice(device);
-    for (DevBuf* b : {&d_occ, &d_geo, &d_ay, &d_au, &d_av, &d_meta, &d_b2p, &d_status, &d_tile_total, &d_count, &d_err, &d_pos,
+    for (DevBuf* b : {&d_occ, &d_geo, &d_ay, &d_au, &d_av, &d_meta, &d_b2p, &d_status, &d_tile_total, &d_count, &d_err, &d_owned,
+                      &d_owned_count, &d_pos,
                       &d_rgb, &d_yuv, &d_part, &d_pix, &d_bt, &d_occ_full, &d_pos_pre, &d_yuv_pre, &d_geotab, &d_coltab,
                       &d_geokeys, &d_colkeys, &d_geolog, &d_collog, &d_geolog_count, &d_collog_count, &d_changed, &d_blist,
                       &d_blist_count})
@@ -319,7 +321,7 @@ struct Batch {
     smoothing_geo = params.geometry_smoothing != 0;
     smoothing_col = params.color_smoothing != 0 && params.attribute_count != 0;
 
-    h_patches.clear(); h_slot_patch.clear(); h_tile_frame.clear(); h_ftb.assign(1, 0);
+    h_patches.clear(); h_slot_rec.clear(); h_tile_frame.clear(); h_ftb.assign(1, 0);
     uint64_t total_points_bound = 0;
     for (uint32_t k = 0; k < count; ++k) {
       const tmc2_frame& fr = g->frames[first + k];
@@ -338,22 +340,31 @@ struct Batch {
           d.ax = kAx[o]; d.ay = kAy[o]; d.rx = kRx[o]; d.ry = kRy[o];
           d.aligned = (params.orientation_mode == TMC2_ORIENTATION_SPEC || o <= 1 || o == 8) ? 1 : 0;
         }
-        d.slot_base = (uint32_t)h_slot_patch.size();
+        d.slot_base = (uint32_t)h_slot_rec.size();
         d.local_index = i; d.frame = k;
         const uint64_t ns = (uint64_t)p.size_u0 * p.size_v0;
-        if (h_slot_patch.size() + ns > (1ull << 30)) FAIL(TMC2_ERR_CAPACITY, "too many patch blocks in one GOF");
+        if (h_slot_rec.size() + ns > (1ull << 30)) FAIL(TMC2_ERR_CAPACITY, "too many patch blocks in one GOF");
         const uint32_t pid = (uint32_t)h_patches.size();
         h_patches.push_back(d);
-        h_slot_patch.insert(h_slot_patch.end(), (size_t)ns, pid);
+        for (uint32_t v0b = 0; v0b < p.size_v0; ++v0b)
+          for (uint32_t u0b = 0; u0b < p.size_u0; ++u0b) {       // the reference's block order, codec.rs:371-372
+            int64_t bx, by;
+            helper_i64(p, u0b, v0b, 1, 1, bx, by);               // decoder.rs:827-837 (validated to be inside the grid)
+            SlotRec r{};
+            r.pid = pid; r.u0b = (uint16_t)u0b; r.v0b = (uint16_t)v0b; r.bx = (uint16_t)bx; r.by = (uint16_t)by;
+            r.ax = d.ax; r.ay = d.ay; r.rx = d.rx; r.ry = d.ry;
+            if (!d.aligned) { r.ax = r.ay = r.rx = r.ry = 0; }   // reference-literal rotated patch: generic device path
+            h_slot_rec.push_back(r);
+          }
         total_points_bound += ns * res * res * 2;
       }
       // pad the frame's slot list to whole tiles: a tile never straddles two frames (one scan domain per frame)
-      while (h_slot_patch.size() % kWarpsPerTile) h_slot_patch.push_back(kNoPatch);
-      const uint32_t tiles_now = (uint32_t)(h_slot_patch.size() / kWarpsPerTile);
+      while (h_slot_rec.size() % kWarpsPerTile) { SlotRec r{}; r.pid = kNoPatch; h_slot_rec.push_back(r); }
+      const uint32_t tiles_now = (uint32_t)(h_slot_rec.size() / kWarpsPerTile);
       h_tile_frame.resize(tiles_now, k);
       h_ftb.push_back(tiles_now);
     }
-    n_slots = (uint32_t)h_slot_patch.size();
+    n_slots = (uint32_t)h_slot_rec.size();
     n_tiles = n_slots / kWarpsPerTile;
     (void)total_points_bound;
 
@@ -368,7 +379,7 @@ struct Batch {
     }
     meta_patch_off = 0;
     meta_slot_off = round_up64(h_patches.size() * sizeof(DevPatch), 256);
-    meta_tf_off = meta_slot_off + round_up64((uint64_t)n_slots * 4, 256);
+    meta_tf_off = meta_slot_off + round_up64((uint64_t)n_slots * sizeof(SlotRec), 256);
     meta_ftb_off = meta_tf_off + round_up64((uint64_t)n_tiles * 4, 256);
     meta_bytes = meta_ftb_off + round_up64((uint64_t)(F + 1) * 4, 256);
     CU(d_meta.ensure(meta_bytes));
@@ -379,6 +390,8 @@ struct Batch {
     if (d_status.cap != old_status_cap) { CU(cudaMemsetAsync(d_status.p, 0, d_status.cap, stream)); epoch = 0; }
     CU(d_tile_total.ensure(std::max<size_t>((size_t)n_tiles * 4, 4)));
     CU(d_count.ensure(std::max<size_t>((size_t)F * 4, 4)));
+    CU(d_owned.ensure(std::max<size_t>((size_t)n_slots * 4, 4)));
+    CU(d_owned_count.ensure(std::max<size_t>((size_t)F * 4, 4)));
     CU(d_changed.ensure(std::max<size_t>((size_t)F * 16, 16)));
     CU(d_pos.ensure((size_t)F * cap * 6));
     const bool dbg = (want & WANT_DEBUG) != 0;
@@ -541,7 +554,7 @@ struct Batch {
     CU(cudaEventSynchronize(ev_inputs_free));
     uint8_t* m = h_meta.as<uint8_t>();
     if (!h_patches.empty()) memcpy(m + meta_patch_off, h_patches.data(), h_patches.size() * sizeof(DevPatch));
-    if (n_slots) memcpy(m + meta_slot_off, h_slot_patch.data(), (size_t)n_slots * 4);
+    if (n_slots) memcpy(m + meta_slot_off, h_slot_rec.data(), (size_t)n_slots * sizeof(SlotRec));
     if (n_tiles) memcpy(m + meta_tf_off, h_tile_frame.data(), (size_t)n_tiles * 4);
     memcpy(m + meta_ftb_off, h_ftb.data(), (size_t)(F + 1) * 4);
     CU(cudaMemcpyAsync(d_meta.p, m, meta_bytes, cudaMemcpyHostToDevice, stream));
@@ -568,10 +581,11 @@ struct Batch {
     a.has_attr = params.attribute_count ? 1 : 0;
     const uint8_t* m = d_meta.as<uint8_t>();
     a.patches = reinterpret_cast<const DevPatch*>(m + meta_patch_off);
-    a.slot_patch = reinterpret_cast<const uint32_t*>(m + meta_slot_off);
+    a.slot_rec = reinterpret_cast<const SlotRec*>(m + meta_slot_off);
     a.tile_frame = reinterpret_cast<const uint32_t*>(m + meta_tf_off);
     a.frame_tile_begin = reinterpret_cast<const uint32_t*>(m + meta_ftb_off);
     a.block_to_patch = d_b2p.as<uint32_t>();
+    a.owned = d_owned.as<uint32_t>(); a.owned_count = d_owned_count.as<uint32_t>();
     a.tile_status = d_status.as<uint64_t>();
     a.tile_total = d_tile_total.as<uint32_t>();
     a.frame_count = d_count.as<uint32_t>();
@@ -638,6 +652,7 @@ struct Batch {
     CU(cudaMemsetAsync(d_b2p.p, 0, std::max<size_t>((size_t)F * bw * bh * 4, 4), s));
     CU(cudaMemsetAsync(d_count.p, 0, std::max<size_t>((size_t)F * 4, 4), s));
     KL(launch_block_to_patch(a, n_slots, s));
+    KL(launch_compact_owned(a, s));
     CU(cudaEventRecord(ev[1], s));
     const bool smooth = smoothing_geo || smoothing_col;
     const bool dbg = (want & WANT_DEBUG) != 0;
