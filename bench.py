@@ -242,19 +242,26 @@ def main():
     def drain(n):
         got = 0
         for _ in range(n):
-            fr = ctx.next_frame(copy=False)
-            got += len(fr)
+            cnt, pos_addr, _col_addr = ctx.next_frame_raw()      # frame is in pinned host memory when this returns
+            got += cnt
         return got
-    for _ in range(max(1, min(args.warmup, 2))):
+    # warm-up with the same two-GOFs-in-flight pattern as the timed loop, so that every GOF slot of the context has its
+    # device buffers and pinned result slab allocated before timing starts
+    ctx.submit_gof(view)
+    for _ in range(max(3, args.warmup)):
         ctx.submit_gof(view)
         drain(frames)
+    drain(frames)
     barrier()
+    trace = os.environ.get("TMC2_TRACE") is not None
     t0 = time.perf_counter()
     got = 0
     ctx.submit_gof(view)
     for s in range(1, args.steps):
         ctx.submit_gof(view)
         got += drain(frames)
+        if trace:
+            sys.stderr.write(f"[bench] e2e step {s}: {(time.perf_counter() - t0) * 1e3:.2f} ms since start\n")
     got += drain(frames)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
@@ -288,9 +295,14 @@ def main():
             "roofline": roofline, "clocks": clocks}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = args.cpu_sample_frames or (8 if smoothing else 16)
-        sample = min(sample, frames) if frames > 1 else 8
-        pts, dt = cpu_reference_run(gof, min(sample, max(frames, 1)) if frames > 1 else 1, 1 if frames > 1 else sample, 0, 1)
+        # ~10-20 s of single-threaded CPU work: 64 frames (two passes over the GOF) with smoothing, 128 without
+        sample = args.cpu_sample_frames or ((64 if smoothing else 128) if frames > 1 else 16)
+        if frames > 1:
+            per, reps = min(sample, frames), max(1, sample // min(sample, frames))
+        else:
+            per, reps = 1, sample
+        sample = per * reps
+        pts, dt = cpu_reference_run(gof, per, reps, 0, 1)
         line["cpu_baseline"] = {"value": pts / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{sample} frame(s) of the same workload, {dt:.1f} s; single-threaded C restatement "
                                           "of tmc2-rs src/codec.rs (+ this repo's smoothing spec) -- the Rust reference "

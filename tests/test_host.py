@@ -75,3 +75,41 @@ def test_gof_view_keeps_pointers_and_strides():
     assert v.c.frames[1].geo[1] == g.geo[1, 1].ctypes.data
     assert v.c.frames[0].attr_stride_c == g.width // 2
     assert v.c.frames[0].patch_count == len(g.patches[0])
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        total = 37                                            # frames of a sequence, sharded frame-wise
+        lo, hi = shard.frames_for_rank(total, rank, world)
+        # every rank "reconstructs" its slice: elapsed differs per rank, points = a known function of the frame index
+        pts = sum(1000 + f for f in range(lo, hi))
+        ms, p, fr = shard.reduce_metrics(10.0 * (rank + 1), pts, hi - lo, "cpu")
+        q.put((rank, lo, hi, ms, p, fr))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_metric_reduction():
+    """N>1 host logic on CPU: world_size 2 over gloo -- disjoint frame slices, max-over-ranks time, summed counts; no
+    data-path collective exists on this path."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, lo0, hi0, ms0, p0, f0), (_, lo1, hi1, ms1, p1, f1) = res
+    assert (lo0, hi1) == (0, 37) and hi0 == lo1                    # contiguous, disjoint, complete
+    assert ms0 == ms1 == 20.0                                      # max over ranks
+    assert p0 == p1 == sum(1000 + f for f in range(37)) and f0 == f1 == 37

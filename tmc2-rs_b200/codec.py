@@ -49,6 +49,7 @@ class Context:
             raise abi.Tmc2Error(st, "tmc2gpu_create")
         self.h = h
         self.devices = list(devices)
+        self._fo = abi.CFrameOut()
 
     def close(self):
         if getattr(self, "h", None):
@@ -138,6 +139,21 @@ class Context:
         ps = PointSet3(pos, col, bool(fo.with_colors), int(fo.smoothed_positions), int(fo.smoothed_colors))
         self.check(self.lib.tmc2gpu_release_frame(self.h, C.byref(fo)), "release_frame")
         return ps
+
+    def next_frame_raw(self):
+        """Lean variant of next_frame for tight loops: (point_count, positions address, colours address) of the next frame in
+        the library's pinned host buffers, already released (valid until the GOF slot is reused); None at the end."""
+        fo = self._fo
+        st = self.lib.tmc2gpu_next_frame(self.h, C.byref(fo))
+        if st == abi.END:
+            return None
+        if st:
+            self.check(st, "next_frame")
+        r = (fo.point_count, fo.positions, fo.colors)
+        st = self.lib.tmc2gpu_release_frame(self.h, C.byref(fo))
+        if st:
+            self.check(st, "release_frame")
+        return r
 
     def decode_gof(self, view: abi.GofView) -> List[PointSet3]:
         self.submit_gof(view)

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -66,6 +67,18 @@ static std::string fmt(const char* f, ...) {
     err.msg = fmt(__VA_ARGS__);    \
     return err.st;                 \
   } while (0)
+
+// TMC2_TRACE=1: host-side phase timings of the streaming path on stderr (diagnostics only)
+static bool trace_on() { static const bool on = getenv("TMC2_TRACE") != nullptr; return on; }
+struct TraceClock {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double lap() {
+    const auto t1 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
+    return ms;
+  }
+};
 
 static inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 static inline uint64_t round_up64(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
@@ -271,6 +284,8 @@ struct Batch {
   uint64_t unpack_alg_bytes = 0;
   uint32_t frames_released = 0;
   bool busy = false;
+  std::chrono::steady_clock::time_point t_submit;   // TMC2_TRACE bookkeeping
+  double trace_wait_ms = 0;
 
   ~Batch() { destroy(); }
   void destroy() {
@@ -896,6 +911,7 @@ tmc2_status tmc2gpu_submit_gof(tmc2gpu_ctx* ctx, const tmc2_gof* gof) {
   if (!ctx) return TMC2_ERR_INVALID_ARG;
   Err& err = ctx->err;
   err = Err();
+  TraceClock tc;
   if (validate_params(gof, err)) return ctx->fail();
   if (ctx->limits.max_frames && gof->frame_count > ctx->limits.max_frames) {
     err.st = TMC2_ERR_CAPACITY; err.msg = "GOF has more frames than limits.max_frames"; return ctx->fail();
@@ -926,9 +942,18 @@ tmc2_status tmc2gpu_submit_gof(tmc2gpu_ctx* ctx, const tmc2_gof* gof) {
     const uint32_t lo = (uint32_t)((uint64_t)F * d / D), hi = (uint32_t)((uint64_t)F * (d + 1) / D);
     if (hi == lo) continue;
     Batch* b = chosen[d];
-    if (b->prepare(gof, lo, hi - lo, 0, err) || b->upload(gof, lo, err) || b->launch(b->stream, err)) return ctx->fail();
+    const double t_val = tc.lap();
+    if (b->prepare(gof, lo, hi - lo, 0, err)) return ctx->fail();
+    const double t_prep = tc.lap();
+    if (b->upload(gof, lo, err)) return ctx->fail();
+    const double t_up = tc.lap();
+    if (b->launch(b->stream, err)) return ctx->fail();
+    if (trace_on())
+      fprintf(stderr, "[tmc2gpu] submit dev %d: validate %.3f prepare %.3f upload-enqueue %.3f launch-enqueue %.3f ms\n", b->device,
+              t_val, t_prep, t_up, tc.lap());
     // counts travel right behind the kernels; result copies are enqueued when the first frame is asked for
     b->busy = true; b->frames_released = 0;
+    b->t_submit = std::chrono::steady_clock::now(); b->trace_wait_ms = 0;
     ctx->last_batch = b;
     for (uint32_t k = 0; k < hi - lo; ++k) ctx->pending.push_back({b, k, ctx->next_global++});
   }
@@ -942,11 +967,23 @@ tmc2_status tmc2gpu_next_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out) {
   if (ctx->pending.empty()) return TMC2_END;
   PendingFrame pf = ctx->pending.front();
   Batch* b = pf.batch;
+  TraceClock tc;
+  const bool first = !b->counts_ready;
   if (!b->counts_ready && b->fetch_counts(b->stream, err)) return ctx->fail();
+  const double t_counts = tc.lap();
   if (!b->outputs_enqueued && b->enqueue_outputs(err)) return ctx->fail();
+  const double t_enq = tc.lap();
   if (cudaSetDevice(b->device) != cudaSuccess || cudaEventSynchronize(b->ev_frame[pf.local]) != cudaSuccess) {
     err.st = TMC2_ERR_CUDA; err.msg = std::string("waiting for frame: ") + cudaGetErrorString(cudaGetLastError());
     return ctx->fail();
+  }
+  if (trace_on()) {
+    const double t_wait = tc.lap();
+    b->trace_wait_ms += t_counts + t_enq + t_wait;
+    if (first || pf.local + 1 == b->F)
+      fprintf(stderr, "[tmc2gpu] next_frame local %u: wait-counts %.3f enqueue-d2h %.3f wait-frame %.3f ms | GOF: inside next_frame "
+              "%.3f ms, since submit %.3f ms\n", pf.local, t_counts, t_enq, t_wait, b->trace_wait_ms,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - b->t_submit).count());
   }
   ctx->pending.pop_front();
   memset(out, 0, sizeof *out);
