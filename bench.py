@@ -275,7 +275,7 @@ def main():
     peak, peak_src = measured_peak()
     t_unpack = statistics.mean(unpack_ms) if unpack_ms else float("nan")
     achieved = alg_bytes / (t_unpack * 1e-3) / 1e9 if t_unpack and t_unpack > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "unpack_kernel<0> (fused occupancy / unpack / attribute / boundary)",
+    roofline = {"bound": "hbm", "kernel": "emit_kernel (fused occupancy upsample / unpack / attribute fetch / YUV->RGB; + boundary + cell statistics when smoothing)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_unpack, "traffic": None,
                 "stage_ms": {k: statistics.mean(v) for k, v in stage_acc.items()}}

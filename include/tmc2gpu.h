@@ -182,8 +182,7 @@ typedef struct tmc2_limits {
   uint32_t flags;                  /* TMC2_CTX_* bits                                                      */
 } tmc2_limits;
 
-#define TMC2_CTX_TWO_PASS_SCAN 1u  /* debug: count / scan / emit as three launches instead of the fused    */
-                                   /* single-pass chained scan                                             */
+#define TMC2_CTX_TWO_PASS_SCAN 1u  /* accepted for compatibility; the unpack is always count / scan / emit   */
 
 typedef struct tmc2gpu_ctx tmc2gpu_ctx;
 
@@ -226,8 +225,9 @@ TMC2_API tmc2_status tmc2gpu_last_launch_info(tmc2gpu_ctx* ctx, uint32_t* kernel
 /* Device time of the unpack kernel alone over the last reconstruct_resident, measured with CUDA
  * events recorded on the launching stream (synchronises). */
 TMC2_API tmc2_status tmc2gpu_last_unpack_ms(tmc2gpu_ctx* ctx, float* ms);
-/* All stage times of the last launch: ms[0] block_to_patch, [1] unpack, [2] geometry smoothing, [3] colour
- * smoothing, [4] final YUV->RGB pass (0 when the stage did not run). */
+/* All stage times of the last launch: ms[0] block_to_patch + owned-slot compaction, [1] unpack emit launches, [2] smoothing
+ * finalize / filter / clear launches (geometry + colour), [3] unpack count + slot-scan launches, [4] separate YUV->RGB
+ * pass (0: fused into the emit). */
 TMC2_API tmc2_status tmc2gpu_last_stage_ms(tmc2gpu_ctx* ctx, float* ms5);
 
 /* ---- stage entry points: one frame, host buffers in and out, synchronous ------------------------

@@ -173,7 +173,7 @@ class Context:
     def last_stage_ms(self):
         ms = (C.c_float * 5)()
         self.check(self.lib.tmc2gpu_last_stage_ms(self.h, ms), "last_stage_ms")
-        return dict(zip(("block_to_patch", "unpack", "geometry_smoothing", "color_smoothing", "yuv_to_rgb"), list(ms)))
+        return dict(zip(("block_to_patch", "unpack", "smoothing", "count_scan", "yuv_to_rgb"), list(ms)))
 
 
 class Resident:

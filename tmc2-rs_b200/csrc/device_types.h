@@ -143,27 +143,35 @@ struct UnpackArgs {
   const uint32_t* block_to_patch;     // [F][bw*bh]
   uint32_t*       owned;              // [n_tiles*kWarpsPerTile] compacted owned slots of each frame, from frame_tile_begin[f]*8
   uint32_t*       owned_count;        // [F]
-  uint64_t*       tile_status;        // chained-scan state, one word per tile
-  uint32_t        epoch;              // launch tag inside the status words (no memset between launches)
-  uint32_t*       tile_total;         // two-pass mode: per-tile totals (count kernel) / exclusive bases (emit kernel)
+  uint32_t*       slot_total;         // [n_tiles*kWarpsPerTile] points of each owned slot (count_kernel), same indexing as owned[]
+  uint32_t*       slot_base;          // first point of each owned slot inside its frame (slot_scan_kernel)
   uint32_t*       frame_count;        // [F] points per frame
   int*            err;                // device error flag (0 ok)
   SmoothArgs sm;                      // used by the smoothing instantiation only
 };
 
-// shared memory of one warp of unpack_kernel: staged positions (8 B / point, one pad slot every 8 points), staged
-// colours (4 B / point, one pad slot every 16 points), the 20x20 occupancy bitmap of the block and its 2-pixel margin
-constexpr uint32_t kStagePosBytes = (kSlotPoints + kSlotPoints / 8) * 8;    // 4608
-constexpr uint32_t kStageRgbBytes = (kSlotPoints + kSlotPoints / 16) * 4;   // 2176
-constexpr uint32_t kBitmapBytes = 32 * 4;
-constexpr uint32_t kWarpSmemBytes = kStagePosBytes + kStageRgbBytes + kBitmapBytes;   // 6912
+// shared memory of one warp of emit_kernel: per-pixel tables of the block, the point list, and one staged chunk
+constexpr uint32_t kChunkPoints = 256;       // points staged per pass (a block holds at most 512)
+constexpr uint32_t kOffNn = 0;                                   // [256] n0 | n1 << 16 by pixel rank
+constexpr uint32_t kOffYy = kOffNn + 1024;                       // [256] Y(map 0) | Y(map 1) << 16
+constexpr uint32_t kOffTerm = kOffYy + 1024;                     // [128] chroma term per (chroma sample, map), 16 B
+constexpr uint32_t kOffSrc = kOffTerm + 2048;                    // [512] u16: output point -> pixel rank << 1 | map
+constexpr uint32_t kOffBt = kOffSrc + 1024;                      // [32]  boundary classes of each lane's 8 pixels
+constexpr uint32_t kOffBmp = kOffBt + 128;                       // [32]  20x20 occupancy bitmap rows
+constexpr uint32_t kOffPos = kOffBmp + 128;                      // staged positions: 8 B / point + a pad slot every 8
+constexpr uint32_t kStagePosBytes = (kChunkPoints + kChunkPoints / 8) * 8;
+constexpr uint32_t kOffRgb = kOffPos + kStagePosBytes;           // staged colours: 4 B / point + a pad slot every 16
+constexpr uint32_t kStageRgbBytes = (kChunkPoints + kChunkPoints / 16) * 4;
+constexpr uint32_t kWarpSmemBytes = kOffRgb + kStageRgbBytes;    // 8768
 
 // launch wrappers (kernels.cu); every one enqueues on `stream` and returns the cudaGetLastError() code
 int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream);
 int launch_compact_owned(const UnpackArgs& a, void* stream);   // after block_to_patch: per-frame list of owned slots
-// mode: 0 fused single pass, 1 count, 2 emit.  Tiles [tile_begin, tile_end).  smooth: accumulate cell tables + boundary list
-int launch_unpack(const UnpackArgs& a, int mode, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream);
-int launch_tile_scan(const UnpackArgs& a, void* stream);
+// unpack = count (points per owned slot) -> slot_scan (run starts, per frame) -> emit.  Tiles [tile_begin, tile_end).
+// smooth: the emit also accumulates the cell tables and writes the boundary lists of the current frame group.
+int launch_count(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, void* stream);
+int launch_slot_scan(const UnpackArgs& a, void* stream);
+int launch_emit(const UnpackArgs& a, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream);
 int launch_upsample(const UnpackArgs& a, uint8_t* occ_full /*[F][H][W]*/, void* stream);
 int launch_smooth_finalize(const UnpackArgs& a, void* stream); // sums -> means for every cell the group touched
 int launch_smooth_filter(const UnpackArgs& a, void* stream);   // boundary points of the current frame group

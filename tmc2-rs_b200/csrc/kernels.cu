@@ -369,12 +369,12 @@ __global__ void __launch_bounds__(256) upsample_kernel(const UnpackArgs a, uint8
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// K3+K4(+K5, + K6/K7 statistics): fused unpack.
+// K3+K4(+K5, + K6/K7 statistics): unpack.  Three launches:
+//   count_kernel      per owned slot: how many points it emits (reads occupancy + the two geometry planes only)
+//   slot_scan_kernel  per frame: exclusive prefix of those counts in slot order == where every run starts (codec.rs:482)
+//   emit_kernel       per owned slot: reload, build positions + colours, write the run at its final place
+// A warp owns a slot; warps never talk to each other, so there is no barrier, flag or look-back anywhere.
 // ----------------------------------------------------------------------------------------------------------------
-constexpr unsigned long long kFlagAggregate = 1ull, kFlagInclusive = 2ull;
-__device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, unsigned long long flag, uint32_t value) {
-  return ((unsigned long long)epoch << 34) | (flag << 32) | value;
-}
 
 // normal coordinates (n0 | n1 << 16) of one pixel from its two geometry samples (codec.rs:534-558)
 __device__ __forceinline__ uint32_t normals_of(const DevPatch& P, uint32_t s0, uint32_t s1, bool absolute_d1) {
@@ -384,21 +384,163 @@ __device__ __forceinline__ uint32_t normals_of(const DevPatch& P, uint32_t s0, u
   return n0 | (n1 << 16);
 }
 
-// staged point k of a warp: positions 8 B apart with one pad slot every 8 points, colours 4 B apart with one pad slot
+// staged point k of a chunk: positions 8 B apart with one pad slot every 8 points, colours 4 B apart with one pad slot
 // every 16 points, so that the copy-out (one lane per group of 8 / 16 points) is free of bank conflicts
 __device__ __forceinline__ uint32_t spos_off(uint32_t k) { return (k + (k >> 3)) * 8u; }
 __device__ __forceinline__ uint32_t srgb_off(uint32_t k) { return (k + (k >> 4)) * 4u; }
-
-// ---- smoothing: per-point flush helpers (generic slots, colour statistics) -----------------------------------------
-struct SlotLog { uint32_t* geo; uint32_t* col; uint32_t n_geo, n_col; };   // this slot's log regions + warp-uniform counts
 
 __device__ __forceinline__ uint32_t cell_key_of(const GridDesc& G, uint32_t x, uint32_t y, uint32_t z) {
   if (!(x < G.th && y < G.th && z < G.th)) return kCellEmpty;
   return cell_div(x, G) | (cell_div(y, G) << 10) | (cell_div(z, G) << 20);
 }
 
-// Generic slot path (any occupancy resolution / precision; reference-literal rotated / mirrored orientations): lane =
-// pixel, 32 at a time in patch raster order, everything straight to global memory.  Rare; kept out of line.
+// Is the block-aligned lane layout usable for this slot?  (16x16 blocks, power-of-two precision, affine steps present:
+// the host zeroes the steps of reference-literal rotated patches, which take the generic per-pixel path.)
+__device__ __forceinline__ bool slot_is_fast(const UnpackArgs& a, const SlotRec& R) {
+  return a.res == 16 && a.prec_shift >= 0 && (R.ax != 0 || R.ay != 0);
+}
+
+// Lane layout of a slot.  Lane l owns the 8 pixels of patch-local ranks 8l .. 8l+7 (row v1 = l/2, columns
+// u1 = 8(l&1) .. +7), whatever the patch orientation: the orientation only changes WHERE those pixels are loaded from.
+struct LaneBlock {
+  uint32_t nn[8];            // n0 | n1 << 16 per pixel
+  uint32_t yy[8];            // attribute Y of map 0 | map 1 << 16 per pixel
+  uint32_t cA[4], cB[4];     // chroma of map 0 / map 1 per pixel pair: U | V << 16
+  uint32_t m1, m2;           // bit j set = pixel j of this lane emits >= 1 / 2 points
+  int32_t xs, ys;            // canvas position of pixel 0; pixel j is (xs + ax*j, ys + ay*j)
+};
+
+template <bool kAttr>
+__device__ __forceinline__ void load_lane_block(const UnpackArgs& a, const SlotRec& R, uint32_t frame, uint32_t lane,
+                                                DevPatch& P, LaneBlock& L) {
+  const int32_t h = (int32_t)(lane & 1u), r = (int32_t)(lane >> 1);
+  const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
+  const int32_t cx0 = (int32_t)R.bx * 16 + ((ax < 0 || rx < 0) ? 15 : 0);
+  const int32_t cy0 = (int32_t)R.by * 16 + ((ay < 0 || ry < 0) ? 15 : 0);
+  const int32_t xs = cx0 + ax * 8 * h + rx * r, ys = cy0 + ay * 8 * h + ry * r;
+  L.xs = xs; L.ys = ys;
+  const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
+  const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
+  const bool attr = kAttr && a.has_attr;
+  const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride;
+  const uint16_t* ay1 = ay0 + a.in.attr_y_map_stride;
+  const uint64_t cf = (uint64_t)frame * 2 * a.in.attr_c_map_stride;
+  const uint16_t* au0 = a.in.attr_u + cf; const uint16_t* au1 = au0 + a.in.attr_c_map_stride;
+  const uint16_t* av0 = a.in.attr_v + cf; const uint16_t* av1 = av0 + a.in.attr_c_map_stride;
+  if (ax == 1) {
+    // Default-like rows: the 8 pixels are 16 contiguous bytes of every plane
+    const uint32_t goff = (uint32_t)ys * a.in.geo_pitch + (uint32_t)xs;
+    const uint4 g0 = ldg_nc_v4(geo0 + goff);
+    const uint4 g1 = ldg_nc_v4(geo1 + goff);
+    uint4 ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
+    uint2 ua = {0, 0}, va = {0, 0}, ub = {0, 0}, vb = {0, 0};
+    if (attr) {
+      const uint32_t yoff = (uint32_t)ys * a.in.attr_pitch_y + (uint32_t)xs;
+      ya = ldg_nc_v4(ay0 + yoff); yb = ldg_nc_v4(ay1 + yoff);
+      const uint32_t coff = (uint32_t)(ys >> 1) * a.in.attr_pitch_c + (uint32_t)(xs >> 1);
+      ua = ldg_nc_v2(au0 + coff); va = ldg_nc_v2(av0 + coff);
+      ub = ldg_nc_v2(au1 + coff); vb = ldg_nc_v2(av1 + coff);
+    }
+    P = a.patches[R.pid];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+      L.nn[j] = __byte_perm(word_of(g0, j >> 1), word_of(g1, j >> 1), sel);      // raw samples, converted below
+      if (kAttr) L.yy[j] = __byte_perm(word_of(ya, j >> 1), word_of(yb, j >> 1), sel);
+    }
+    if (kAttr) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t sel = (c & 1) ? 0x7632u : 0x5410u;
+        L.cA[c] = __byte_perm(word_of(ua, c >> 1), word_of(va, c >> 1), sel);
+        L.cB[c] = __byte_perm(word_of(ub, c >> 1), word_of(vb, c >> 1), sel);
+      }
+    }
+  } else {
+    // transposed / mirrored: eight 2-byte loads per plane; across the warp every load still covers whole 32-byte sectors
+    const int32_t dstep = ay * (int32_t)a.in.geo_pitch + ax;
+    const int32_t goff = ys * (int32_t)a.in.geo_pitch + xs;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int32_t o = goff + j * dstep;
+      L.nn[j] = ldg_nc_u16(geo0 + o) | (ldg_nc_u16(geo1 + o) << 16);
+    }
+    if (kAttr) {
+      if (attr) {
+        const int32_t ystep = ay * (int32_t)a.in.attr_pitch_y + ax;
+        const int32_t yoff = ys * (int32_t)a.in.attr_pitch_y + xs;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int32_t o = yoff + j * ystep;
+          L.yy[j] = ldg_nc_u16(ay0 + o) | (ldg_nc_u16(ay1 + o) << 16);
+        }
+        const int32_t cstep = ay * (int32_t)a.in.attr_pitch_c + ax;
+        const int32_t coff = (ys >> 1) * (int32_t)a.in.attr_pitch_c + (xs >> 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int32_t o = coff + c * cstep;
+          L.cA[c] = ldg_nc_u16(au0 + o) | (ldg_nc_u16(av0 + o) << 16);
+          L.cB[c] = ldg_nc_u16(au1 + o) | (ldg_nc_u16(av1 + o) << 16);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) L.yy[j] = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { L.cA[c] = 0; L.cB[c] = 0; }
+      }
+    }
+    P = a.patches[R.pid];
+  }
+  // occupancy of the 8 pixels (codec.rs:393-396: any non-zero sample counts).  Pixels j*p .. j*p+p-1 share a sample.
+  uint32_t m1 = 0, m2 = 0;
+  {
+    const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
+    const int32_t lp = a.prec_shift;
+    const int32_t p = 1 << lp;
+    const int32_t nb = lp >= 3 ? 1 : (8 >> lp);
+    const uint32_t ones = lp >= 3 ? 0xFFu : ((1u << p) - 1u);
+    for (int32_t k = 0; k < nb; ++k) {
+      const int32_t j = k << lp;
+      const uint32_t ox = (uint32_t)(xs + ax * j) >> lp, oy = (uint32_t)(ys + ay * j) >> lp;
+      if (occ_f[(uint64_t)oy * a.in.occ_pitch + ox] != 0) m1 |= ones << j;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    L.nn[j] = normals_of(P, L.nn[j] & 0xFFFFu, L.nn[j] >> 16, a.absolute_d1);
+    if ((L.nn[j] >> 16) != (L.nn[j] & 0xFFFFu)) m2 |= (m1 & (1u << j));            // codec.rs:422-428 duplicate skip
+  }
+  L.m1 = m1; L.m2 = m2;
+}
+
+// points of a generic slot (any resolution / precision, reference-literal rotated orientations): lane = pixel
+__device__ __noinline__ uint32_t generic_slot_count(const UnpackArgs& a, const DevPatch& P, uint32_t frame, uint32_t u0b,
+                                                    uint32_t v0b) {
+  const uint32_t lane = lane_id(), res = a.res;
+  const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
+  const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
+  const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
+  const int64_t sscale = a.spec_orientation ? res : 1;
+  uint32_t total = 0;
+  for (uint32_t base = 0; base < res * res; base += 32) {
+    const uint32_t i = base + lane;
+    uint32_t c = 0;
+    if (i < res * res) {
+      const uint32_t v1 = i / res, u1 = i - v1 * res;
+      int64_t x, y;
+      patch_to_canvas(P, (int64_t)u0b * res + u1, (int64_t)v0b * res + v1, res, sscale, x, y);
+      if (occ_at(a, occ_f, (uint32_t)x, (uint32_t)y)) {
+        const uint64_t off = (uint64_t)y * a.in.geo_pitch + (uint64_t)x;
+        const uint32_t n = normals_of(P, geo0[off], geo1[off], a.absolute_d1);
+        c = (n >> 16) != (n & 0xFFFFu) ? 2u : 1u;
+      }
+    }
+    total += __reduce_add_sync(kFull, c);
+  }
+  return total;
+}
+
+// Generic slot path: lane = pixel, 32 at a time in patch raster order, everything straight to global memory.  Rare.
 template <bool kSmooth, bool kDebug>
 __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, const DevPatch& P, uint32_t frame, uint32_t fig,
                                                uint32_t u0b, uint32_t v0b, uint64_t gidx, uint32_t* log_geo, uint32_t* log_col,
@@ -494,44 +636,61 @@ __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, const DevPat
   }
 }
 
-// Exclusive prefix of this tile inside its frame by decoupled look-back over the tile status words (one warp).
-__device__ __forceinline__ uint32_t tile_lookback(const UnpackArgs& a, uint32_t tile, uint32_t first_tile, uint32_t tile_sum,
-                                                  uint32_t lane) {
-  unsigned long long* status = reinterpret_cast<unsigned long long*>(a.tile_status);
-  if (tile == first_tile) {
-    if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagInclusive, tile_sum));
-    return 0;
+// ---- pass 1: points per owned slot ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerTile * 32) count_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t tile = blockIdx.x + tile_offset;
+  const uint32_t frame = a.tile_frame[tile];
+  const uint32_t first_tile = a.frame_tile_begin[frame];
+  const uint32_t pos_in_frame = (tile - first_tile) * kWarpsPerTile + warp;
+  if (pos_in_frame >= a.owned_count[frame]) return;
+  const uint32_t lpos = tile * kWarpsPerTile + warp;
+  const SlotRec R = load_slot_rec(a.slot_rec + a.owned[lpos]);
+  uint32_t total;
+  DevPatch P;
+  if (slot_is_fast(a, R)) {
+    LaneBlock L;
+    load_lane_block<false>(a, R, frame, lane, P, L);
+    total = __reduce_add_sync(kFull, __popc(L.m1) + __popc(L.m2));
+  } else {
+    P = a.patches[R.pid];
+    total = generic_slot_count(a, P, frame, R.u0b, R.v0b);
   }
-  if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagAggregate, tile_sum));
-  uint32_t excl = 0, spins = 0;
-  int64_t look = (int64_t)tile - 1;
-  while (true) {
-    const int64_t idx = look - (int64_t)lane;
-    const bool valid = idx >= (int64_t)first_tile;
-    unsigned long long st = pack_status(a.epoch, kFlagInclusive, 0);       // before the frame: prefix 0
-    if (valid) st = ld_relaxed_u64(status + idx);
-    const bool ready = (st >> 34) == a.epoch && ((st >> 32) & 3ull) != 0;
-    const uint32_t ready_mask = __ballot_sync(kFull, ready);
-    const uint32_t incl_mask = __ballot_sync(kFull, ready && ((st >> 32) & 3ull) == kFlagInclusive);
-    // usable as soon as every predecessor up to the nearest inclusive one (or the whole window) has published
-    const uint32_t upto = incl_mask ? (uint32_t)(__ffs(incl_mask) - 1) : 31u;
-    const uint32_t need = upto == 31u ? kFull : ((2u << upto) - 1u);
-    if ((ready_mask & need) != need) {
-      if (++spins > (1u << 22)) { if (lane == 0) atomicExch(a.err, 11); break; }   // watchdog: never hang the GPU
-      __nanosleep(20);
-      continue;
-    }
-    const uint32_t v = lane <= upto ? (uint32_t)(st & 0xFFFFFFFFull) : 0u;
-    excl += __reduce_add_sync(kFull, v);
-    if (incl_mask) break;
-    look -= 32;
-  }
-  if (lane == 0) st_relaxed_u64(status + tile, pack_status(a.epoch, kFlagInclusive, excl + tile_sum));
-  return excl;
+  if (lane == 0) a.slot_total[lpos] = total;
 }
 
-// ---- copy-out of one warp's staged run ---------------------------------------------------------------------------------
-// The run starts at point `run_base` of its frame slab (slabs are 16-byte aligned and hold a multiple of 16 points).
+// ---- pass 2: where every run starts.  One CTA per frame; the scan domain is the frame's owned-slot list ---------------------
+__global__ void __launch_bounds__(1024) slot_scan_kernel(const UnpackArgs a) {
+  const uint32_t f = blockIdx.x;
+  const uint32_t s0 = a.frame_tile_begin[f] * kWarpsPerTile, n = a.owned_count[f];
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  for (uint32_t b = 0; b < n; b += blockDim.x) {
+    const uint32_t i = b + threadIdx.x;
+    const uint32_t v = i < n ? a.slot_total[s0 + i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = s_carry;
+    for (uint32_t w = 0; w < warp; ++w) wbase += s_w[w];
+    if (i < n) a.slot_base[s0 + i] = wbase + incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = wbase + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a.frame_count[f] = s_carry;              // tile.total_number_of_regular_points, codec.rs:482
+}
+
+// ---- copy-out of one staged chunk ----------------------------------------------------------------------------------------
+// The chunk starts at point `run_base` of its frame slab (slabs are 16-byte aligned and hold a multiple of 16 points).
 // Packed output is written in aligned groups: 8 points = 48 B = three 16-byte vectors for positions (a group starts at a
 // point index that is a multiple of 8), 16 points = 48 B for colours (multiple of 16).  One lane assembles one group
 // from the padded staging with byte permutes; the few points before the first / after the last full group go out as
@@ -602,8 +761,6 @@ __device__ __forceinline__ void copy_out_rgb(uint8_t* __restrict__ grgb /* frame
   }
 }
 
-template <bool kSmooth, bool kDebug> struct UnpackTraits { static constexpr int kMinCtas = (kSmooth || kDebug) ? 2 : 3; };
-
 // one row of the 20x20 occupancy bitmap (block + 2-pixel margin, patch-local axes): bit cc = pixel (cc-2, rr) of the block
 // is occupied, or lies outside the image (the 5x5 test ignores those).  Walks the row one occupancy cell at a time.
 __device__ __forceinline__ uint32_t bitmap_row(const UnpackArgs& a, const uint8_t* occ_f, int32_t x0, int32_t y0, int32_t sx,
@@ -631,584 +788,267 @@ __device__ __forceinline__ uint32_t bitmap_row(const UnpackArgs& a, const uint8_
                         : (m0 - 19 < 0 ? (0xFFFFFu << max(m0 + 1, 0)) & 0xFFFFFu : 0u));
 }
 
-// kMode 0: fused single pass (chained scan) ; 1: count only ; 2: emit with tile bases.  kDebug adds the streams the
-// reference materialises but nobody downstream needs (colors16bit, partition, point_to_pixel, boundary types).
-//
-// CTA protocol (no __syncthreads after the prologue): every warp posts its slot's point count as soon as the geometry
-// planes are in; the warp that posts last does the look-back for the tile and publishes the base while the others are
-// still staging their output in shared memory; everybody copies out once the base is there.
-template <int kMode, bool kSmooth, bool kDebug>
-__global__ void __launch_bounds__(kWarpsPerTile * 32, UnpackTraits<kSmooth, kDebug>::kMinCtas)
-unpack_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
+// ---- pass 3: emit ------------------------------------------------------------------------------------------------------------
+// Per warp (slot): (1) load the block in the lane layout, (2) spill it into per-pixel tables in shared memory and build
+// the list "output point k <- (pixel rank, map)", (3) POINT-parallel loop: lane = output point, dense, rolled (small code):
+// position, colour, and in the smoothing instantiation boundary class, cell statistics and the boundary list, staged in
+// chunks of <= 256 points, (4) aligned copy-out of each chunk.
+template <bool kSmooth, bool kDebug>
+__global__ void __launch_bounds__(kWarpsPerTile * 32, 3) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ uint32_t s_tot[kWarpsPerTile];
-  __shared__ uint32_t s_nlog[kWarpsPerTile][2];
-  __shared__ uint32_t s_posted, s_ready, s_base;
-
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t tile = blockIdx.x + tile_offset;
   const uint32_t frame = a.tile_frame[tile];
   const uint32_t first_tile = a.frame_tile_begin[frame];
-  const uint32_t n_owned = a.owned_count[frame];
   const uint32_t pos_in_frame = (tile - first_tile) * kWarpsPerTile + warp;   // index into the frame's owned-slot list
-  const uint32_t lpos = tile * kWarpsPerTile + warp;                          // global position (log index)
-  if ((tile - first_tile) * kWarpsPerTile >= n_owned) {                       // tile past the end of the list: nothing to do
-    if (kMode == 1 && threadIdx.x == 0) a.tile_total[tile] = 0;
-    if (kSmooth && lane == 0) {
-      if (a.sm.geo.on) a.sm.geo.log_count[lpos - a.sm.group_first_slot] = 0;
-      if (a.sm.col.on) a.sm.col.log_count[lpos - a.sm.group_first_slot] = 0;
-    }
-    return;
-  }
-  if (threadIdx.x == 0) { s_posted = 0; s_ready = 0; }
-  const bool active = pos_in_frame < n_owned;
-  const uint32_t slot = active ? a.owned[(uint64_t)first_tile * kWarpsPerTile + pos_in_frame] : 0u;
-  SlotRec R;
-  R.pid = kNoPatch; R.u0b = R.v0b = R.bx = R.by = 0; R.ax = R.ay = R.rx = R.ry = 0;
-  if (active) R = load_slot_rec(a.slot_rec + slot);
-  const uint32_t res = a.res;
-  __syncthreads();                                               // the only block-wide barrier
-
-  uint8_t* wsm = smem + (size_t)warp * kWarpSmemBytes;
-  uint8_t* s_pos = wsm;
-  uint8_t* s_rgb = wsm + kStagePosBytes;
-  uint32_t* s_bmp = reinterpret_cast<uint32_t*>(wsm + kStagePosBytes + kStageRgbBytes);
-
-  const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
-  const int32_t bx = R.bx, by = R.by;
-  const uint32_t u0b = R.u0b, v0b = R.v0b;
-  const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
-
-  // smoothing: this slot's log regions (table slots it added to); every position of the group writes its counts
-  const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
-  uint32_t* log_geo = nullptr; uint32_t* log_col = nullptr;
+  const uint32_t lpos = tile * kWarpsPerTile + warp;                          // global position (per-slot arrays, logs)
+  uint32_t total = 0;
+  const bool active = pos_in_frame < a.owned_count[frame];
+  if (active) total = a.slot_total[lpos];
   uint32_t n_log_geo = 0, n_log_col = 0;
-  if (kSmooth) {
-    const uint64_t ls = (uint64_t)(lpos - a.sm.group_first_slot) * a.sm.log_stride;
-    if (a.sm.geo.on) log_geo = a.sm.geo.log + ls;
-    if (a.sm.col.on) log_col = a.sm.col.log + ls;
-  }
+  if (total != 0) {
+    const uint32_t run_base = a.slot_base[lpos];
+    const SlotRec R = load_slot_rec(a.slot_rec + a.owned[lpos]);
+    const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
+    uint32_t* log_geo = nullptr; uint32_t* log_col = nullptr;
+    if (kSmooth) {
+      const uint64_t ls = (uint64_t)(lpos - a.sm.group_first_slot) * a.sm.log_stride;
+      if (a.sm.geo.on) log_geo = a.sm.geo.log + ls;
+      if (a.sm.col.on) log_col = a.sm.col.log + ls;
+    }
+    uint8_t* wsm = smem + (size_t)warp * kWarpSmemBytes;
+    uint32_t* s_nn = reinterpret_cast<uint32_t*>(wsm + kOffNn);
+    uint32_t* s_yy = reinterpret_cast<uint32_t*>(wsm + kOffYy);
+    uint4* s_term = reinterpret_cast<uint4*>(wsm + kOffTerm);
+    uint16_t* s_src = reinterpret_cast<uint16_t*>(wsm + kOffSrc);
+    uint32_t* s_bt = reinterpret_cast<uint32_t*>(wsm + kOffBt);
+    uint32_t* s_bmp = reinterpret_cast<uint32_t*>(wsm + kOffBmp);
+    uint8_t* s_pos = wsm + kOffPos;
+    uint8_t* s_rgb = wsm + kOffRgb;
+    DevPatch P;
 
-  // ---- phase 1: load the block, decide which pixels emit 1 or 2 points ------------------------------------------
-  const int32_t h = (int32_t)(lane & 1u), r = (int32_t)(lane >> 1);
-  uint32_t nn[8];                        // n0 | n1 << 16 per pixel
-  uint32_t yy[8];                        // attribute Y of map 0 | map 1 << 16 per pixel
-  uint32_t cA[4], cB[4];                 // chroma of map 0 / map 1 per pixel pair: U | V << 16
-  uint32_t m1 = 0, m2 = 0;               // bit j set = pixel j of this lane emits >= 1 / 2 points
-  uint32_t total = 0, lane_excl = 0;
-  int32_t xs = 0, ys = 0;                // canvas position of this lane's pixel 0; pixel j is (xs + ax*j, ys + ay*j)
-  DevPatch P;
-  bool fast = false;
-
-  if (active) {
-    // the plane addresses depend only on the slot record: issue the loads, then fetch the patch
-    const bool can_fast = res == 16 && a.prec_shift >= 0 && (ax != 0 || ay != 0) &&
-                          (a.spec_orientation || ((ax | ay) >= 0 && (rx | ry) >= 0));   // aligned <=> no flip, or SPEC mode
-    fast = can_fast;
-    if (fast) {
-      const int32_t cx0 = bx * 16 + ((ax < 0 || rx < 0) ? 15 : 0);
-      const int32_t cy0 = by * 16 + ((ay < 0 || ry < 0) ? 15 : 0);
-      xs = cx0 + ax * 8 * h + rx * r;
-      ys = cy0 + ay * 8 * h + ry * r;
-      const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
-      const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
-      const bool attr = kMode != 1 && a.has_attr;
-      const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride;
-      const uint16_t* ay1 = ay0 + a.in.attr_y_map_stride;
-      const uint64_t cf = (uint64_t)frame * 2 * a.in.attr_c_map_stride;
-      const uint16_t* au0 = a.in.attr_u + cf; const uint16_t* au1 = au0 + a.in.attr_c_map_stride;
-      const uint16_t* av0 = a.in.attr_v + cf; const uint16_t* av1 = av0 + a.in.attr_c_map_stride;
-      if (ax == 1) {
-        // Default-like rows: the 8 pixels are 16 contiguous bytes of every plane
-        const uint32_t goff = (uint32_t)ys * a.in.geo_pitch + (uint32_t)xs;
-        const uint4 g0 = ldg_nc_v4(geo0 + goff);
-        const uint4 g1 = ldg_nc_v4(geo1 + goff);
-        uint4 ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
-        uint2 ua = {0, 0}, va = {0, 0}, ub = {0, 0}, vb = {0, 0};
-        if (attr) {
-          const uint32_t yoff = (uint32_t)ys * a.in.attr_pitch_y + (uint32_t)xs;
-          ya = ldg_nc_v4(ay0 + yoff); yb = ldg_nc_v4(ay1 + yoff);
-          const uint32_t coff = (uint32_t)(ys >> 1) * a.in.attr_pitch_c + (uint32_t)(xs >> 1);
-          ua = ldg_nc_v2(au0 + coff); va = ldg_nc_v2(av0 + coff);
-          ub = ldg_nc_v2(au1 + coff); vb = ldg_nc_v2(av1 + coff);
-        }
-        P = a.patches[R.pid];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
-          nn[j] = __byte_perm(word_of(g0, j >> 1), word_of(g1, j >> 1), sel);      // raw samples, converted below
-          yy[j] = __byte_perm(word_of(ya, j >> 1), word_of(yb, j >> 1), sel);
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t sel = (c & 1) ? 0x7632u : 0x5410u;
-          cA[c] = __byte_perm(word_of(ua, c >> 1), word_of(va, c >> 1), sel);
-          cB[c] = __byte_perm(word_of(ub, c >> 1), word_of(vb, c >> 1), sel);
-        }
-      } else {
-        // transposed / mirrored: eight 2-byte loads per plane; across the warp every load still covers whole 32-byte sectors
-        const int32_t dstep = ay * (int32_t)a.in.geo_pitch + ax;
-        const int32_t goff = ys * (int32_t)a.in.geo_pitch + xs;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int32_t o = goff + j * dstep;
-          nn[j] = ldg_nc_u16(geo0 + o) | (ldg_nc_u16(geo1 + o) << 16);
-        }
-        if (attr) {
-          const int32_t ystep = ay * (int32_t)a.in.attr_pitch_y + ax;
-          const int32_t yoff = ys * (int32_t)a.in.attr_pitch_y + xs;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int32_t o = yoff + j * ystep;
-            yy[j] = ldg_nc_u16(ay0 + o) | (ldg_nc_u16(ay1 + o) << 16);
-          }
-          const int32_t cstep = ay * (int32_t)a.in.attr_pitch_c + ax;
-          const int32_t coff = (ys >> 1) * (int32_t)a.in.attr_pitch_c + (xs >> 1);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int32_t o = coff + c * cstep;
-            cA[c] = ldg_nc_u16(au0 + o) | (ldg_nc_u16(av0 + o) << 16);
-            cB[c] = ldg_nc_u16(au1 + o) | (ldg_nc_u16(av1 + o) << 16);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) yy[j] = 0;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) { cA[c] = 0; cB[c] = 0; }
-        }
-        P = a.patches[R.pid];
-      }
-      // occupancy of the 8 pixels (codec.rs:393-396: any non-zero sample counts).  Pixels j*p .. j*p+p-1 share a sample.
-      {
-        const int32_t lp = a.prec_shift;
-        const int32_t p = 1 << lp;
-        const int32_t nb = lp >= 3 ? 1 : (8 >> lp);
-        const uint32_t ones = lp >= 3 ? 0xFFu : ((1u << p) - 1u);
-        for (int32_t k = 0; k < nb; ++k) {
-          const int32_t j = k << lp;
-          const uint32_t ox = (uint32_t)(xs + ax * j) >> lp, oy = (uint32_t)(ys + ay * j) >> lp;
-          if (occ_f[(uint64_t)oy * a.in.occ_pitch + ox] != 0) m1 |= ones << j;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        nn[j] = normals_of(P, nn[j] & 0xFFFFu, nn[j] >> 16, a.absolute_d1);
-        if ((nn[j] >> 16) != (nn[j] & 0xFFFFu)) m2 |= (m1 & (1u << j));            // codec.rs:422-428 duplicate skip
-      }
-      const uint32_t c = __popc(m1) + __popc(m2);
-      uint32_t incl = c;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFull, incl, d);
-        if (lane >= (uint32_t)d) incl += t;
-      }
-      total = __shfl_sync(kFull, incl, 31);
-      lane_excl = incl - c;
-    } else {
-      // generic path (any resolution / precision, reference-literal rotated orientations): lane = pixel, 32 at a time
+    if ((uint64_t)run_base + total > a.out.cap) {                   // cannot happen for footprints inside the canvas
+      if (lane == 0) atomicExch(a.err, 7);
+    } else if (!slot_is_fast(a, R)) {
       P = a.patches[R.pid];
-      const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
-      const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
-      const int64_t sscale = a.spec_orientation ? res : 1;
-      for (uint32_t base = 0; base < res * res; base += 32) {
-        const uint32_t i = base + lane;
-        uint32_t c = 0;
-        if (i < res * res) {
-          const uint32_t v1 = i / res, u1 = i - v1 * res;
-          int64_t x, y;
-          patch_to_canvas(P, (int64_t)u0b * res + u1, (int64_t)v0b * res + v1, res, sscale, x, y);
-          if (occ_at(a, occ_f, (uint32_t)x, (uint32_t)y)) {
-            const uint64_t off = (uint64_t)y * a.in.geo_pitch + (uint64_t)x;
-            const uint32_t n = normals_of(P, geo0[off], geo1[off], a.absolute_d1);
-            c = (n >> 16) != (n & 0xFFFFu) ? 2u : 1u;
+      if (lane == 0) { s_bmp[0] = 0; s_bmp[1] = 0; }
+      __syncwarp();
+      generic_slot_emit<kSmooth, kDebug>(a, P, frame, fig, R.u0b, R.v0b, (uint64_t)frame * a.out.cap + run_base, log_geo,
+                                         log_col, s_bmp);
+      __syncwarp();
+      n_log_geo = reinterpret_cast<volatile uint32_t*>(s_bmp)[0];
+      n_log_col = reinterpret_cast<volatile uint32_t*>(s_bmp)[1];
+    } else {
+      const int32_t h = (int32_t)(lane & 1u), r = (int32_t)(lane >> 1);
+      const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
+      const bool w_rgb = a.out.rgb != nullptr;
+      const bool want_bt = kSmooth || (kDebug && a.out.btype != nullptr);
+      int32_t cx0, cy0;                                              // canvas pixel of patch-local (0,0) of the block
+      {
+        // ---- (1) + (2): lane layout -> tables ----------------------------------------------------------------------
+        LaneBlock L;
+        load_lane_block<true>(a, R, frame, lane, P, L);
+        cx0 = L.xs - ax * 8 * h - rx * r; cy0 = L.ys - ay * 8 * h - ry * r;
+        *reinterpret_cast<uint4*>(s_nn + 8 * lane) = make_uint4(L.nn[0], L.nn[1], L.nn[2], L.nn[3]);
+        *reinterpret_cast<uint4*>(s_nn + 8 * lane + 4) = make_uint4(L.nn[4], L.nn[5], L.nn[6], L.nn[7]);
+        if (a.has_attr) {
+          *reinterpret_cast<uint4*>(s_yy + 8 * lane) = make_uint4(L.yy[0], L.yy[1], L.yy[2], L.yy[3]);
+          *reinterpret_cast<uint4*>(s_yy + 8 * lane + 4) = make_uint4(L.yy[4], L.yy[5], L.yy[6], L.yy[7]);
+          // chroma terms, once per (chroma sample, map): the two lanes of a row pair read the same 4 samples; the even
+          // row evaluates map 0, the odd row map 1.  Entry = {ir, ig, ib << 1 | flagged, U | V << 16}.
+          const bool odd = (lane & 2u) != 0;
+          const uint32_t e0 = (((uint32_t)r >> 1) * 8u + 4u * (uint32_t)h) * 2u + (odd ? 1u : 0u);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t uv = odd ? L.cB[cc] : L.cA[cc];                            // decoder.rs:976-977
+            const ChromaTerm t = chroma_term(uv & 0xFFFFu, uv >> 16);
+            s_term[e0 + 2 * cc] = make_uint4((uint32_t)t.ir, (uint32_t)t.ig, ((uint32_t)t.ib << 1) | t.flagged, uv);
           }
         }
-        total += __reduce_add_sync(kFull, c);
-      }
-    }
-  }
-
-  // ---- post this slot's count; the last warp to post resolves the tile's base -----------------------------------------
-  {
-    uint32_t prev = 0;
-    if (lane == 0) {
-      s_tot[warp] = total;
-      s_nlog[warp][0] = 0; s_nlog[warp][1] = 0;
-      __threadfence_block();
-      prev = atomicAdd(&s_posted, 1u);
-    }
-    prev = __shfl_sync(kFull, prev, 0);
-    if (prev == kWarpsPerTile - 1) {
-      __threadfence_block();
-      uint32_t tile_sum = 0;
+        // output point k of the slot <- (pixel rank, map); this lane's points are consecutive
+        const uint32_t c = __popc(L.m1) + __popc(L.m2);
+        uint32_t incl = c;
 #pragma unroll
-      for (int w = 0; w < kWarpsPerTile; ++w) tile_sum += reinterpret_cast<volatile uint32_t*>(s_tot)[w];
-      if (kMode == 1) {
-        if (lane == 0) a.tile_total[tile] = tile_sum;
-      } else {
-        const uint32_t excl = kMode == 2 ? a.tile_total[tile] : tile_lookback(a, tile, first_tile, tile_sum, lane);
-        if (lane == 0) {
-          if ((tile - first_tile + 1) * kWarpsPerTile >= n_owned) a.frame_count[frame] = excl + tile_sum;  // codec.rs:482
-          s_base = excl;
-          __threadfence_block();
-          *reinterpret_cast<volatile uint32_t*>(&s_ready) = 1u;
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t = __shfl_up_sync(kFull, incl, d);
+          if (lane >= (uint32_t)d) incl += t;
         }
-      }
-    }
-  }
-  if (kMode == 1) return;
-
-  // ---- phase 2a: stage the run in shared memory (needs only warp-local offsets) -----------------------------------
-  const bool w_rgb = a.out.rgb != nullptr;
-  const bool want_bt = kSmooth || (kDebug && a.out.btype != nullptr);
-  uint32_t bt1 = 0, bt2 = 0;             // bit j: pixel j is a type-1 / type-2 boundary pixel (meaningful where m1 is set)
-  uint32_t T0 = 0, Bc = 0;
-
-  if (fast && total) {
-    T0 = ((u0b * 16u + 8u * (uint32_t)h) * P.lod_x + P.u1);                  // decoder.rs:875 at j = 0
-    Bc = ((v0b * 16u + (uint32_t)r) * P.lod_y + P.v1) & 0xFFFFu;            // decoder.rs:876
-    // generate_point (decoder.rs:871-878) stores normal, tangent, bitangent in that order; the selectors reproduce
-    // "later stores overwrite earlier ones" and leave unset coordinates at 0
-    const uint32_t s0 = sel_of_src(axis_source(P, 0)), s1 = sel_of_src(axis_source(P, 1)), s2 = sel_of_src(axis_source(P, 2));
-    const uint32_t selA = s0 | (s1 << 8), selB = s2 | 0x7600u;
-
-    // chroma terms: the two lanes of a row pair (l, l^2) read the same chroma samples; one of them evaluates map 0, the
-    // other map 1, and they swap the results (three integers per sample, the flag travels in bit 0 of the blue term)
-    const bool odd = (lane & 2u) != 0;
-    uint32_t k = lane_excl;
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {                                            // chroma column: pixels 2cc, 2cc+1
-      ChromaTerm ta, tb;
-      if (w_rgb) {
-        const uint32_t uv = odd ? cB[cc] : cA[cc];                              // decoder.rs:976-977
-        const ChromaTerm t = chroma_term(uv & 0xFFFFu, uv >> 16);
-        const int32_t mr = t.ir, mg = t.ig, mb = (int32_t)(((uint32_t)t.ib << 1) | t.flagged);
-        const int32_t orr = __shfl_xor_sync(kFull, mr, 2), og = __shfl_xor_sync(kFull, mg, 2), ob = __shfl_xor_sync(kFull, mb, 2);
-        const int32_t ab = odd ? ob : mb, bb = odd ? mb : ob;
-        ta.ir = odd ? orr : mr; ta.ig = odd ? og : mg; ta.ib = ab >> 1; ta.flagged = (uint32_t)ab & 1u;
-        tb.ir = odd ? mr : orr; tb.ig = odd ? mg : og; tb.ib = bb >> 1; tb.flagged = (uint32_t)bb & 1u;
-      }
-      if (!((m1 >> (2 * cc)) & 3u)) continue;
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int j = 2 * cc + jj;
-        if (!((m1 >> j) & 1u)) continue;
-        const uint32_t t = (T0 + (uint32_t)j * P.lod_x) & 0xFFFFu;
-        {                                                                         // map 0 (codec.rs:421, i == 0)
-          const uint32_t A = (nn[j] & 0xFFFFu) | (t << 16);
-          *reinterpret_cast<uint2*>(s_pos + spos_off(k)) = make_uint2(__byte_perm(A, Bc, selA), __byte_perm(A, Bc, selB));
-          if (w_rgb) *reinterpret_cast<uint32_t*>(s_rgb + srgb_off(k)) =
-              yuv_to_rgb_term(yy[j] & 0xFFFFu, cA[cc] & 0xFFFFu, cA[cc] >> 16, ta);   // codec.rs:637-640
-          ++k;
+        uint32_t k = incl - c;
+        const uint32_t m1 = L.m1, m2 = L.m2;
+#pragma unroll 1
+        for (uint32_t j = 0; j < 8; ++j) {
+          if ((m1 >> j) & 1u) {
+            const uint32_t e = (8u * lane + j) << 1;
+            s_src[k++] = (uint16_t)e;
+            if ((m2 >> j) & 1u) s_src[k++] = (uint16_t)(e | 1u);
+          }
         }
-        if ((m2 >> j) & 1u) {                                                     // map 1 unless it duplicates map 0
-          const uint32_t A = (nn[j] >> 16) | (t << 16);
-          *reinterpret_cast<uint2*>(s_pos + spos_off(k)) = make_uint2(__byte_perm(A, Bc, selA), __byte_perm(A, Bc, selB));
-          if (w_rgb) *reinterpret_cast<uint32_t*>(s_rgb + srgb_off(k)) = yuv_to_rgb_term(yy[j] >> 16, cB[cc] & 0xFFFFu, cB[cc] >> 16, tb);
-          ++k;
+        // ---- K5: boundary classes from a 20x20 occupancy bitmap of the block and its 2-pixel margin ---------------
+        if (want_bt) {
+          const int32_t W = (int32_t)a.W, H = (int32_t)a.H;
+          const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
+          if (lane < 20) {
+            const int32_t rr = (int32_t)lane - 2;
+            s_bmp[lane] = bitmap_row(a, occ_f, cx0 - 2 * ax + rx * rr, cy0 - 2 * ay + ry * rr, ax, ay);
+          }
+          __syncwarp();
+          const uint32_t r0 = s_bmp[r], r1 = s_bmp[r + 1], r2 = s_bmp[r + 2], r3 = s_bmp[r + 3], r4 = s_bmp[r + 4];
+          const uint32_t cross = r1 & r3 & (r2 >> 1) & (r2 << 1);    // bit c: the four neighbours of column c are occupied
+          const uint32_t all5 = r0 & r1 & r2 & r3 & r4;
+          const uint32_t full = all5 & (all5 >> 1) & (all5 >> 2) & (all5 << 1) & (all5 << 2);
+          const uint32_t sh = 8u * (uint32_t)h + 2u;
+          uint32_t border = 0;
+          if (R.bx == 0 || R.by == 0 || ((int32_t)R.bx + 1) * 16 >= W || ((int32_t)R.by + 1) * 16 >= H) {
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+              const int32_t x = L.xs + ax * j, y = L.ys + ay * j;
+              if (x == 0 || y == 0 || x == W - 1 || y == H - 1) border |= 1u << j;
+            }
+          }
+          const uint32_t bt1 = ((~(cross >> sh)) & 0xFFu) | border;
+          const uint32_t bt2 = (~(full >> sh)) & 0xFFu & ~bt1;
+          s_bt[lane] = bt1 | (bt2 << 8);     // bit j: pixel j is type 1 ; bit 8+j: type 2 (meaningful where occupied)
         }
-      }
-    }
-
-    // ---- K5: boundary types from a 20x20 occupancy bitmap of the block and its 2-pixel margin (patch-local axes) ----
-    if (want_bt) {
-      const int32_t W = (int32_t)a.W, H = (int32_t)a.H;
-      const int32_t cx0 = xs - ax * 8 * h - rx * r, cy0 = ys - ay * 8 * h - ry * r;   // canvas of patch-local (0,0)
-      if (lane < 20) {
-        const int32_t rr = (int32_t)lane - 2;
-        s_bmp[lane] = bitmap_row(a, occ_f, cx0 - 2 * ax + rx * rr, cy0 - 2 * ay + ry * rr, ax, ay);
       }
       __syncwarp();
-      const uint32_t r0 = s_bmp[r], r1 = s_bmp[r + 1], r2 = s_bmp[r + 2], r3 = s_bmp[r + 3], r4 = s_bmp[r + 4];
-      const uint32_t cross = r1 & r3 & (r2 >> 1) & (r2 << 1);    // bit c: the four neighbours of column c are occupied
-      const uint32_t all5 = r0 & r1 & r2 & r3 & r4;
-      const uint32_t full = all5 & (all5 >> 1) & (all5 >> 2) & (all5 << 1) & (all5 << 2);
-      const uint32_t sh = 8u * (uint32_t)h + 2u;
-      uint32_t border = 0;
-      if (bx == 0 || by == 0 || (bx + 1) * 16 >= W || (by + 1) * 16 >= H) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int32_t x = xs + ax * j, y = ys + ay * j;
-          if (x == 0 || y == 0 || x == W - 1 || y == H - 1) border |= 1u << j;
-        }
-      }
-      bt1 = ((~(cross >> sh)) & 0xFFu) | border;
-      bt2 = (~(full >> sh)) & 0xFFu & ~bt1;
-    }
-    __syncwarp();
 
-    // ---- K6 statistics: geometry cells over ALL points of the slot ---------------------------------------------------
-    // Every lane holds up to 16 points (8 pixels x 2 maps) as (key, packed contribution).  Rounds: each lane takes its
-    // smallest remaining cell key and sums its own matching points; lanes that hold the same key merge along a butterfly
-    // (the rows of a cell are neighbouring lanes); whoever still holds a non-zero count issues the reductions.  Exact for
-    // any input: a missed merge only means two reductions instead of one.
-    if (kSmooth && a.sm.geo.on) {
-      const GridDesc& G = a.sm.geo;
-      const bool perm = ((1u << P.normal) | (1u << P.tangent) | (1u << P.bitangent)) == 7u;
-      if (perm && G.g <= 64u) {
-        const uint32_t shN = 10u * P.normal, shT = 10u * P.tangent, shB = 10u * P.bitangent;
-        const uint32_t g = G.g;
-        const uint32_t cBc = cell_div(Bc, G), relB = Bc - cBc * g;
-        const bool okB = Bc < G.th;
-        uint32_t key[16], val[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t t = (T0 + (uint32_t)j * P.lod_x) & 0xFFFFu;
-          const uint32_t cT = cell_div(t, G), relT = t - cT * g;
-          const uint32_t kTB = (cT << shT) | (cBc << shB);
-          const bool okTB = okB && t < G.th && ((m1 >> j) & 1u);
-          const uint32_t n0 = nn[j] & 0xFFFFu, n1 = nn[j] >> 16;
-          const uint32_t c0 = cell_div(n0, G), c1 = cell_div(n1, G);
-          key[2 * j] = (okTB && n0 < G.th) ? (kTB | (c0 << shN)) : kCellEmpty;
-          val[2 * j] = 1u | ((n0 - c0 * g) << 6) | (relT << 18);      // count (<= 16) | sum relN (<= 1008) | sum relT
-          key[2 * j + 1] = (okTB && ((m2 >> j) & 1u) && n1 < G.th) ? (kTB | (c1 << shN)) : kCellEmpty;
-          val[2 * j + 1] = 1u | ((n1 - c1 * g) << 6) | (relT << 18);
-        }
-        uint32_t cur = kCellEmpty;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) cur = min(cur, key[i]);
-        while (__any_sync(kFull, cur != kCellEmpty)) {
-          uint32_t acc = 0, nxt = kCellEmpty;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (key[i] == cur) acc += val[i];
-            else if (key[i] > cur) nxt = min(nxt, key[i]);
-          }
-          // packed partial sums: w0 = count | sumN << 16, w1 = sumT | sumB << 16 (each sum <= 512 * 63 < 2^15)
-          uint32_t w0 = 0, w1 = 0;
-          if (cur != kCellEmpty) {
-            const uint32_t cnt = acc & 63u;
-            w0 = cnt | (((acc >> 6) & 0xFFFu) << 16);
-            w1 = (acc >> 18) | ((cnt * relB) << 16);
-          }
-          // merge lanes holding the same cell: the other half-row (xor 1) and the neighbouring rows (xor 2..16)
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t ok = __shfl_xor_sync(kFull, cur, d);
-            const uint32_t o0 = __shfl_xor_sync(kFull, w0, d);
-            const uint32_t o1 = __shfl_xor_sync(kFull, w1, d);
-            if (ok == cur) {
-              if (lane & (uint32_t)d) { w0 = 0; w1 = 0; }
-              else { w0 += o0; w1 += o1; }
-            }
-          }
-          const uint32_t cnt = w0 & 0xFFFFu;
-          uint32_t cs = kCellEmpty;
-          if (cnt != 0) {
-            cs = cell_slot(G, fig, cur, a.err);
-            if (cs != kCellEmpty) {
-              const uint32_t sN = w0 >> 16, sT = w1 & 0xFFFFu, sB = w1 >> 16;
-              const uint32_t sx = P.normal == 0 ? sN : P.tangent == 0 ? sT : sB;
-              const uint32_t sy = P.normal == 1 ? sN : P.tangent == 1 ? sT : sB;
-              const uint32_t sz = P.normal == 2 ? sN : P.tangent == 2 ? sT : sB;
-              geo_cell_add(G, fig, cs, P.local_index, cnt, sx, sy, sz);
-            }
-          }
-          const uint32_t fm = __ballot_sync(kFull, cs != kCellEmpty);
-          if (cs != kCellEmpty) log_geo[n_log_geo + __popc(fm & ((1u << lane) - 1u))] = cs;
-          n_log_geo += __popc(fm);
-          cur = nxt;
-        }
-      } else {
-        // axes that are not a permutation (never produced by the reference's set_view_id) or very coarse grids:
-        // per-point reductions on the staged positions
-        for (uint32_t kb = 0; kb < total; kb += 32) {
-          const uint32_t kk = kb + lane;
-          uint32_t cs = kCellEmpty;
-          if (kk < total) {
-            const uint2 pw = *reinterpret_cast<const uint2*>(s_pos + spos_off(kk));
-            const uint32_t X = pw.x & 0xFFFFu, Yc = pw.x >> 16, Z = pw.y & 0xFFFFu;
-            const uint32_t key = cell_key_of(G, X, Yc, Z);
-            if (key != kCellEmpty) {
-              cs = cell_slot(G, fig, key, a.err);
-              if (cs != kCellEmpty)
-                geo_cell_add(G, fig, cs, P.local_index, 1, X - (key & 1023u) * G.g, Yc - ((key >> 10) & 1023u) * G.g, Z - (key >> 20) * G.g);
-            }
-          }
-          const uint32_t fm = __ballot_sync(kFull, cs != kCellEmpty);
-          if (cs != kCellEmpty) log_geo[n_log_geo + __popc(fm & ((1u << lane) - 1u))] = cs;
-          n_log_geo += __popc(fm);
-        }
-      }
-    }
+      // ---- (3): point-parallel ------------------------------------------------------------------------------------------
+      // generate_point (decoder.rs:871-878) stores normal, tangent, bitangent in that order; the selectors reproduce
+      // "later stores overwrite earlier ones" and leave unset coordinates at 0
+      const uint32_t s0 = sel_of_src(axis_source(P, 0)), s1 = sel_of_src(axis_source(P, 1)), s2 = sel_of_src(axis_source(P, 2));
+      const uint32_t selA = s0 | (s1 << 8), selB = s2 | 0x7600u;
+      const uint32_t T00 = (uint32_t)R.u0b * 16u * P.lod_x + P.u1, B00 = (uint32_t)R.v0b * 16u * P.lod_y + P.v1;   // decoder.rs:875-876
+      const uint32_t lodx = P.lod_x, lody = P.lod_y, patch = P.local_index;
+      uint16_t* gpos = a.out.pos + (uint64_t)frame * a.out.cap * 3;
+      uint8_t* grgb = w_rgb ? a.out.rgb + (uint64_t)frame * a.out.cap * 3 : nullptr;
+      const uint64_t gidx = (uint64_t)frame * a.out.cap + run_base;
 
-    // ---- K7 statistics: colour cells over the type-2 (second ring) points ----------------------------------------------
-    if (kSmooth && a.sm.col.on && a.has_attr) {
-      const GridDesc& G = a.sm.col;
-      const uint32_t sel_mask = m1 & bt2;
-      if (__any_sync(kFull, sel_mask != 0)) {
-        uint32_t k = lane_excl;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const bool on = (m1 >> j) & 1u, two = (m2 >> j) & 1u;
-          const bool sel = (sel_mask >> j) & 1u;
-          if (__any_sync(kFull, sel)) {
-            uint32_t cs0 = kCellEmpty, cs1 = kCellEmpty;
-            if (sel) {
-              const uint32_t U0 = cA[j >> 1] & 0xFFFFu, V0 = cA[j >> 1] >> 16, U1 = cB[j >> 1] & 0xFFFFu, V1 = cB[j >> 1] >> 16;
-              const uint32_t Y0 = yy[j] & 0xFFFFu, Y1 = yy[j] >> 16;
-              const uint2 p0 = *reinterpret_cast<const uint2*>(s_pos + spos_off(k));
-              const uint32_t key0 = cell_key_of(G, p0.x & 0xFFFFu, p0.x >> 16, p0.y & 0xFFFFu);
-              uint32_t key1 = kCellEmpty;
-              if (two) {
-                const uint2 p1 = *reinterpret_cast<const uint2*>(s_pos + spos_off(k + 1));
-                key1 = cell_key_of(G, p1.x & 0xFFFFu, p1.x >> 16, p1.y & 0xFFFFu);
+      for (uint32_t c0 = 0; c0 < total;) {
+        // a chunk ends on a point whose index in the frame is a multiple of 16 (so the next one starts group-aligned)
+        uint32_t c1 = c0 + kChunkPoints - ((run_base + c0 + kChunkPoints) & 15u);
+        if (c1 > total) c1 = total;
+#pragma unroll 1
+        for (uint32_t kb = c0; kb < c1; kb += 32) {
+          const uint32_t k = kb + lane;
+          const bool valid = k < c1;
+          uint32_t w0 = 0, w1 = 0, Y = 0, uv = 0, rank = 0, map = 0;
+          if (valid) {
+            const uint32_t src = s_src[k];
+            rank = src >> 1; map = src & 1u;
+            const uint32_t n = (s_nn[rank] >> (16u * map)) & 0xFFFFu;
+            const uint32_t u1 = rank & 15u, v1 = rank >> 4;
+            const uint32_t t = (T00 + u1 * lodx) & 0xFFFFu, b = (B00 + v1 * lody) & 0xFFFFu;
+            const uint32_t A = n | (t << 16);
+            w0 = __byte_perm(A, b, selA); w1 = __byte_perm(A, b, selB);
+            *reinterpret_cast<uint2*>(s_pos + spos_off(k - c0)) = make_uint2(w0, w1);
+            if (a.has_attr) {
+              Y = (s_yy[rank] >> (16u * map)) & 0xFFFFu;                                     // codec.rs:637-640
+              const uint4 te = s_term[(((v1 >> 1) * 8u + (u1 >> 1)) << 1) | map];
+              uv = te.w;
+              if (w_rgb) {
+                ChromaTerm ct;
+                ct.ir = (int32_t)te.x; ct.ig = (int32_t)te.y; ct.ib = (int32_t)te.z >> 1; ct.flagged = te.z & 1u;
+                *reinterpret_cast<uint32_t*>(s_rgb + srgb_off(k - c0)) = yuv_to_rgb_term(Y, uv & 0xFFFFu, uv >> 16, ct);
               }
-              if (key0 != kCellEmpty) {
-                cs0 = cell_slot(G, fig, key0, a.err);
-                if (cs0 != kCellEmpty) {
-                  if (key1 == key0) {
-                    col_cell_add(G, fig, cs0, P.local_index, 2, Y0 + Y1, U0 + U1, V0 + V1,
-                                 (unsigned long long)Y0 * Y0 + (unsigned long long)Y1 * Y1);
-                    key1 = kCellEmpty;
-                  } else {
-                    col_cell_add(G, fig, cs0, P.local_index, 1, Y0, U0, V0, (unsigned long long)Y0 * Y0);
-                  }
+            }
+          }
+          uint32_t bt = 0;
+          if (kSmooth || kDebug) {
+            if (valid && want_bt) {
+              const uint32_t bw = s_bt[rank >> 3], j = rank & 7u;
+              bt = ((bw >> j) & 1u) ? 1u : ((bw >> (8u + j)) & 1u) ? 2u : 0u;
+            }
+          }
+          if (kDebug && valid) {                                       // streams only the stage API / tests ask for
+            const uint64_t gk = gidx + k;
+            if (a.out.yuv && a.has_attr) {
+              uint16_t* q = a.out.yuv + gk * 3;
+              q[0] = (uint16_t)Y; q[1] = (uint16_t)(uv & 0xFFFFu); q[2] = (uint16_t)(uv >> 16);
+            }
+            if (a.out.part) a.out.part[gk] = (uint16_t)patch;                          // codec.rs:452
+            if (a.out.pix) {                                                            // codec.rs:463-472
+              const int32_t u1 = (int32_t)(rank & 15u), v1 = (int32_t)(rank >> 4);
+              a.out.pix[gk] = (uint32_t)(cx0 + ax * u1 + rx * v1) | ((uint32_t)(cy0 + ay * u1 + ry * v1) << 15) | (map << 30);
+            }
+            if (a.out.btype) a.out.btype[gk] = (uint8_t)bt;
+          }
+          if (kSmooth) {
+            const uint32_t X = w0 & 0xFFFFu, Yc = w0 >> 16, Z = w1 & 0xFFFFu;
+            // K6 statistics: geometry cells over ALL points.  32 consecutive points hold a few runs of equal cell key
+            // (a row of the block crosses a cell every g pixels): segmented scan, the last lane of a run flushes it.
+            if (a.sm.geo.on) {
+              const GridDesc& G = a.sm.geo;
+              const uint32_t key = valid ? cell_key_of(G, X, Yc, Z) : kCellEmpty;
+              uint32_t v0 = 0, v1 = 0;
+              if (key != kCellEmpty) {
+                const uint32_t g = G.g;
+                v0 = 1u | ((X - (key & 1023u) * g) << 16);                              // count | sum rel x
+                v1 = (Yc - ((key >> 10) & 1023u) * g) | ((Z - (key >> 20) * g) << 16);  // sum rel y | sum rel z
+              }
+              const uint32_t kprev = __shfl_up_sync(kFull, key, 1), knext = __shfl_down_sync(kFull, key, 1);
+              uint32_t fl = (lane == 0 || kprev != key) ? 1u : 0u;
+#pragma unroll
+              for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o0 = __shfl_up_sync(kFull, v0, d), o1 = __shfl_up_sync(kFull, v1, d);
+                const uint32_t of = __shfl_up_sync(kFull, fl, d);
+                if (lane >= (uint32_t)d && !fl) { v0 += o0; v1 += o1; fl = of; }
+              }
+              const bool tail = key != kCellEmpty && (lane == 31 || knext != key);
+              uint32_t cs = kCellEmpty;
+              if (tail) {
+                cs = cell_slot(G, fig, key, a.err);
+                if (cs != kCellEmpty) geo_cell_add(G, fig, cs, patch, v0 & 0xFFFFu, v0 >> 16, v1 & 0xFFFFu, v1 >> 16);
+              }
+              const uint32_t fm = __ballot_sync(kFull, cs != kCellEmpty);
+              if (cs != kCellEmpty) log_geo[n_log_geo + __popc(fm & ((1u << lane) - 1u))] = cs;
+              n_log_geo += __popc(fm);
+            }
+            // K7 statistics: colour cells over the type-2 (second ring) points
+            if (a.sm.col.on && a.has_attr && __any_sync(kFull, bt == 2u)) {
+              const GridDesc& G = a.sm.col;
+              uint32_t cs = kCellEmpty;
+              if (bt == 2u) {
+                const uint32_t key = cell_key_of(G, X, Yc, Z);
+                if (key != kCellEmpty) {
+                  cs = cell_slot(G, fig, key, a.err);
+                  if (cs != kCellEmpty) col_cell_add(G, fig, cs, patch, 1, Y, uv & 0xFFFFu, uv >> 16, (unsigned long long)Y * Y);
                 }
               }
-              if (key1 != kCellEmpty) {
-                cs1 = cell_slot(G, fig, key1, a.err);
-                if (cs1 != kCellEmpty) col_cell_add(G, fig, cs1, P.local_index, 1, Y1, U1, V1, (unsigned long long)Y1 * Y1);
+              const uint32_t fm = __ballot_sync(kFull, cs != kCellEmpty);
+              if (cs != kCellEmpty) log_col[n_log_col + __popc(fm & ((1u << lane) - 1u))] = cs;
+              n_log_col += __popc(fm);
+            }
+            // compact list of the type-1 boundary points (order inside the list is irrelevant)
+            const uint32_t bm = __ballot_sync(kFull, bt == 1u);
+            if (bm) {
+              uint32_t lbase = 0;
+              if (lane == 0) lbase = atomicAdd(&a.sm.blist_count[frame], (uint32_t)__popc(bm));
+              lbase = __shfl_sync(kFull, lbase, 0);
+              if ((uint64_t)lbase + __popc(bm) > a.sm.blist_cap) {
+                if (lane == 0) atomicExch(a.err, 7);
+              } else if (bt == 1u) {
+                uint4 e;
+                e.x = run_base + k;
+                e.y = w0;                                  // pos[0] | pos[1] << 16
+                e.z = (w1 & 0xFFFFu) | (Y << 16);          // pos[2] | Y << 16
+                e.w = uv;                                  // U | V << 16
+                reinterpret_cast<uint4*>(a.sm.blist + (uint64_t)frame * a.sm.blist_cap)[lbase + __popc(bm & ((1u << lane) - 1u))] = e;
               }
             }
-            const uint32_t f0 = __ballot_sync(kFull, cs0 != kCellEmpty);
-            if (cs0 != kCellEmpty) log_col[n_log_col + __popc(f0 & ((1u << lane) - 1u))] = cs0;
-            n_log_col += __popc(f0);
-            const uint32_t f1 = __ballot_sync(kFull, cs1 != kCellEmpty);
-            if (cs1 != kCellEmpty) log_col[n_log_col + __popc(f1 & ((1u << lane) - 1u))] = cs1;
-            n_log_col += __popc(f1);
           }
-          k += (on ? 1u : 0u) + (two ? 1u : 0u);
         }
+        __syncwarp();
+        // ---- (4): copy-out of the chunk ----------------------------------------------------------------------------------
+        copy_out_pos(gpos, run_base + c0, c1 - c0, s_pos, lane);
+        if (w_rgb) copy_out_rgb(grgb, run_base + c0, c1 - c0, s_rgb, lane);
+        __syncwarp();
+        c0 = c1;
       }
     }
   }
-
-  if (!active || total == 0) {
-    if (kSmooth && lane == 0) {
-      if (a.sm.geo.on) a.sm.geo.log_count[lpos - a.sm.group_first_slot] = 0;
-      if (a.sm.col.on) a.sm.col.log_count[lpos - a.sm.group_first_slot] = 0;
-    }
-    return;
-  }
-  // ---- wait for the tile base (published by the last-posting warp) ------------------------------------------------------
-  while (*reinterpret_cast<volatile uint32_t*>(&s_ready) == 0u) __nanosleep(64);
-  __threadfence_block();
-  uint32_t run_base = *reinterpret_cast<volatile uint32_t*>(&s_base);
-  for (uint32_t w = 0; w < warp; ++w) run_base += reinterpret_cast<volatile uint32_t*>(s_tot)[w];
-  if ((uint64_t)run_base + total > a.out.cap) {                   // cannot happen for footprints inside the canvas
-    if (lane == 0) atomicExch(a.err, 7);
-    return;
-  }
-  const uint64_t gidx = (uint64_t)frame * a.out.cap + run_base;   // first point of this run
-
-  // ---- phase 2b: copy-out ---------------------------------------------------------------------------------------------
-  if (!fast) {
-    __syncwarp();
-    generic_slot_emit<kSmooth, kDebug>(a, P, frame, fig, u0b, v0b, gidx, log_geo, log_col, &s_nlog[warp][0]);
-    __syncwarp();
-    if (kSmooth && lane == 0) {
-      if (a.sm.geo.on) a.sm.geo.log_count[lpos - a.sm.group_first_slot] = reinterpret_cast<volatile uint32_t*>(&s_nlog[warp][0])[0];
-      if (a.sm.col.on) a.sm.col.log_count[lpos - a.sm.group_first_slot] = reinterpret_cast<volatile uint32_t*>(&s_nlog[warp][0])[1];
-    }
-    return;
-  }
-  copy_out_pos(a.out.pos + (uint64_t)frame * a.out.cap * 3, run_base, total, s_pos, lane);
-  if (w_rgb) copy_out_rgb(a.out.rgb + (uint64_t)frame * a.out.cap * 3, run_base, total, s_rgb, lane);
-
-  if (kDebug) {                                                    // streams only the stage API / tests ask for
-    uint64_t k = gidx + lane_excl;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (!((m1 >> j) & 1u)) continue;
-      const uint32_t np = 1u + ((m2 >> j) & 1u);
-      const uint32_t x = (uint32_t)(xs + ax * j), y = (uint32_t)(ys + ay * j);
-      const uint32_t bt = ((bt1 >> j) & 1u) ? 1u : ((bt2 >> j) & 1u) ? 2u : 0u;
-      for (uint32_t m = 0; m < np; ++m, ++k) {
-        if (a.out.yuv && a.has_attr) {
-          uint16_t* q = a.out.yuv + k * 3;
-          q[0] = (uint16_t)(m ? yy[j] >> 16 : yy[j] & 0xFFFFu);
-          q[1] = (uint16_t)(m ? cB[j >> 1] & 0xFFFFu : cA[j >> 1] & 0xFFFFu);
-          q[2] = (uint16_t)(m ? cB[j >> 1] >> 16 : cA[j >> 1] >> 16);
-        }
-        if (a.out.part) a.out.part[k] = (uint16_t)P.local_index;                    // codec.rs:452
-        if (a.out.pix) a.out.pix[k] = x | (y << 15) | (m << 30);                     // codec.rs:463-472
-        if (a.out.btype) a.out.btype[k] = (uint8_t)bt;
-      }
-    }
-  }
-
-  if (kSmooth) {
-    // compact list of the type-1 boundary points of this run (order inside the list is irrelevant)
-    const uint32_t b1 = m1 & bt1;
-    const uint32_t nb_lane = __popc(b1) + __popc(b1 & m2);
-    uint32_t incl = nb_lane;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(kFull, incl, d);
-      if (lane >= (uint32_t)d) incl += t;
-    }
-    const uint32_t n_boundary = __shfl_sync(kFull, incl, 31);
-    if (n_boundary) {
-      uint32_t lbase = 0;
-      if (lane == 0) lbase = atomicAdd(&a.sm.blist_count[frame], n_boundary);
-      lbase = __shfl_sync(kFull, lbase, 0);
-      if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
-        if (lane == 0) atomicExch(a.err, 7);
-      } else {
-        uint4* L = reinterpret_cast<uint4*>(a.sm.blist + (uint64_t)frame * a.sm.blist_cap + lbase + (incl - nb_lane));
-        uint32_t k = lane_excl;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (!((m1 >> j) & 1u)) continue;
-          const uint32_t np = 1u + ((m2 >> j) & 1u);
-          if ((b1 >> j) & 1u) {
-            for (uint32_t m = 0; m < np; ++m) {
-              const uint2 pw = *reinterpret_cast<const uint2*>(s_pos + spos_off(k + m));
-              uint4 e;
-              e.x = run_base + k + m;
-              e.y = pw.x;                                                  // pos[0] | pos[1] << 16
-              e.z = (pw.y & 0xFFFFu) | ((m ? yy[j] >> 16 : yy[j] & 0xFFFFu) << 16);   // pos[2] | Y << 16
-              e.w = m ? cB[j >> 1] : cA[j >> 1];                           // U | V << 16
-              *L++ = e;
-            }
-          }
-          k += np;
-        }
-      }
-    }
-    if (lane == 0) {
-      if (a.sm.geo.on) a.sm.geo.log_count[lpos - a.sm.group_first_slot] = n_log_geo;
-      if (a.sm.col.on) a.sm.col.log_count[lpos - a.sm.group_first_slot] = n_log_col;
-    }
-  }
-}
-
-// two-pass mode: exclusive scan of tile totals inside each frame (one CTA per frame)
-__global__ void __launch_bounds__(256) tile_scan_kernel(const UnpackArgs a) {
-  const uint32_t f = blockIdx.x;
-  const uint32_t t0 = a.frame_tile_begin[f], t1 = a.frame_tile_begin[f + 1];
-  __shared__ uint32_t s_w[8];
-  __shared__ uint32_t s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  for (uint32_t b = t0; b < t1; b += 256) {
-    const uint32_t i = b + threadIdx.x;
-    const uint32_t v = i < t1 ? a.tile_total[i] : 0;
-    uint32_t incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(kFull, incl, d);
-      if (lane_id() >= (uint32_t)d) incl += t;
-    }
-    if (lane_id() == 31) s_w[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    uint32_t wbase = s_carry;
-    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) wbase += s_w[w];
-    if (i < t1) a.tile_total[i] = wbase + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 255) s_carry = wbase + incl;
-    __syncthreads();
+  if (kSmooth && lane == 0) {                                      // every position of the group reports its log sizes
+    if (a.sm.geo.on) a.sm.geo.log_count[lpos - a.sm.group_first_slot] = n_log_geo;
+    if (a.sm.col.on) a.sm.col.log_count[lpos - a.sm.group_first_slot] = n_log_col;
   }
 }
 
@@ -1492,34 +1332,33 @@ int launch_compact_owned(const UnpackArgs& a, void* stream) {
   return after_launch();
 }
 
-template <int kMode, bool kSmooth, bool kDebug>
-static int launch_unpack_t(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute((const void*)unpack_kernel<kMode, kSmooth, kDebug>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <bool kSmooth, bool kDebug>
+static int launch_emit_t(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, cudaStream_t s) {
+  const size_t smem = (size_t)kWarpSmemBytes * kWarpsPerTile;
+  cudaError_t e = cudaFuncSetAttribute((const void*)emit_kernel<kSmooth, kDebug>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  unpack_kernel<kMode, kSmooth, kDebug><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin);
+  emit_kernel<kSmooth, kDebug><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin);
   return after_launch();
 }
-template <int kMode>
-static int launch_unpack_m(const UnpackArgs& a, bool smooth, bool debug, uint32_t t0, uint32_t t1, size_t smem, cudaStream_t s) {
-  if (smooth) return debug ? launch_unpack_t<kMode, true, true>(a, t0, t1, smem, s) : launch_unpack_t<kMode, true, false>(a, t0, t1, smem, s);
-  return debug ? launch_unpack_t<kMode, false, true>(a, t0, t1, smem, s) : launch_unpack_t<kMode, false, false>(a, t0, t1, smem, s);
+
+int launch_count(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, void* stream) {
+  if (tile_end <= tile_begin) return 0;
+  count_kernel<<<tile_end - tile_begin, kWarpsPerTile * 32, 0, (cudaStream_t)stream>>>(a, tile_begin);
+  return after_launch();
 }
 
-int launch_unpack(const UnpackArgs& a, int mode, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream) {
+int launch_slot_scan(const UnpackArgs& a, void* stream) {
+  if (a.n_frames == 0) return 0;
+  slot_scan_kernel<<<a.n_frames, 1024, 0, (cudaStream_t)stream>>>(a);
+  return after_launch();
+}
+
+int launch_emit(const UnpackArgs& a, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream) {
   if (tile_end <= tile_begin) return 0;
-  const size_t smem = mode == 1 ? 0 : (size_t)kWarpSmemBytes * kWarpsPerTile;
   const cudaStream_t s = (cudaStream_t)stream;
   const bool debug = a.out.yuv || a.out.part || a.out.pix || a.out.btype;
-  if (mode == 1) return launch_unpack_t<1, false, false>(a, tile_begin, tile_end, smem, s);
-  return mode == 0 ? launch_unpack_m<0>(a, smooth, debug, tile_begin, tile_end, smem, s)
-                   : launch_unpack_m<2>(a, smooth, debug, tile_begin, tile_end, smem, s);
-}
-
-int launch_tile_scan(const UnpackArgs& a, void* stream) {
-  if (a.n_frames == 0) return 0;
-  tile_scan_kernel<<<a.n_frames, 256, 0, (cudaStream_t)stream>>>(a);
-  return after_launch();
+  if (smooth) return debug ? launch_emit_t<true, true>(a, tile_begin, tile_end, s) : launch_emit_t<true, false>(a, tile_begin, tile_end, s);
+  return debug ? launch_emit_t<false, true>(a, tile_begin, tile_end, s) : launch_emit_t<false, false>(a, tile_begin, tile_end, s);
 }
 
 int launch_upsample(const UnpackArgs& a, uint8_t* occ_full, void* stream) {

@@ -236,7 +236,7 @@ enum : uint32_t {
   WANT_OCC_FULL = 2u,    // materialise tile.occupancy_map (K1)
 };
 
-struct StageTimes { float b2p = 0, unpack = 0, geo = 0, col = 0, rgb = 0; };
+struct StageTimes { float b2p = 0, count = 0, unpack = 0, geo = 0, col = 0, rgb = 0; };
 
 struct Batch {
   int device = 0;
@@ -251,14 +251,13 @@ struct Batch {
   uint32_t want = 0;
   uint64_t cap = 0;                   // points per frame slab
   uint32_t n_tiles = 0, n_slots = 0, bw = 0, bh = 0;
-  uint32_t epoch = 0;
   bool smoothing_geo = false, smoothing_col = false;
 
   std::vector<DevPatch> h_patches;
   std::vector<SlotRec> h_slot_rec;
   std::vector<uint32_t> h_tile_frame, h_ftb;
 
-  DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_status, d_tile_total, d_count, d_err, d_owned, d_owned_count;
+  DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_slot_total, d_slot_base, d_count, d_err, d_owned, d_owned_count;
   DevBuf d_pos, d_rgb, d_yuv, d_part, d_pix, d_bt, d_occ_full, d_pos_pre, d_yuv_pre;
   DevBuf d_geotab, d_coltab, d_geokeys, d_colkeys, d_geolog, d_collog, d_geolog_count, d_collog_count, d_changed, d_blist,
       d_blist_count;
@@ -290,7 +289,7 @@ struct Batch {
   ~Batch() { destroy(); }
   void destroy() {
     cudaSetDevice(device);
-    for (DevBuf* b : {&d_occ, &d_geo, &d_ay, &d_au, &d_av, &d_meta, &d_b2p, &d_status, &d_tile_total, &d_count, &d_err, &d_owned,
+    for (DevBuf* b : {&d_occ, &d_geo, &d_ay, &d_au, &d_av, &d_meta, &d_b2p, &d_slot_total, &d_slot_base, &d_count, &d_err, &d_owned,
                       &d_owned_count, &d_pos,
                       &d_rgb, &d_yuv, &d_part, &d_pix, &d_bt, &d_occ_full, &d_pos_pre, &d_yuv_pre, &d_geotab, &d_coltab,
                       &d_geokeys, &d_colkeys, &d_geolog, &d_collog, &d_geolog_count, &d_collog_count, &d_changed, &d_blist,
@@ -400,10 +399,8 @@ struct Batch {
     CU(d_meta.ensure(meta_bytes));
     CU(h_meta.ensure(meta_bytes));
     CU(d_b2p.ensure(std::max<size_t>((size_t)F * bw * bh * 4, 4)));
-    const size_t old_status_cap = d_status.cap;
-    CU(d_status.ensure(std::max<size_t>((size_t)n_tiles * 8, 8)));
-    if (d_status.cap != old_status_cap) { CU(cudaMemsetAsync(d_status.p, 0, d_status.cap, stream)); epoch = 0; }
-    CU(d_tile_total.ensure(std::max<size_t>((size_t)n_tiles * 4, 4)));
+    CU(d_slot_total.ensure(std::max<size_t>((size_t)n_slots * 4, 4)));
+    CU(d_slot_base.ensure(std::max<size_t>((size_t)n_slots * 4, 4)));
     CU(d_count.ensure(std::max<size_t>((size_t)F * 4, 4)));
     CU(d_owned.ensure(std::max<size_t>((size_t)n_slots * 4, 4)));
     CU(d_owned_count.ensure(std::max<size_t>((size_t)F * 4, 4)));
@@ -601,8 +598,8 @@ struct Batch {
     a.frame_tile_begin = reinterpret_cast<const uint32_t*>(m + meta_ftb_off);
     a.block_to_patch = d_b2p.as<uint32_t>();
     a.owned = d_owned.as<uint32_t>(); a.owned_count = d_owned_count.as<uint32_t>();
-    a.tile_status = d_status.as<uint64_t>();
-    a.tile_total = d_tile_total.as<uint32_t>();
+    a.slot_total = d_slot_total.as<uint32_t>();
+    a.slot_base = d_slot_base.as<uint32_t>();
     a.frame_count = d_count.as<uint32_t>();
     a.err = d_err.as<int>();
     const bool dbg = (want & WANT_DEBUG) != 0;
@@ -661,8 +658,6 @@ struct Batch {
     CU(cudaSetDevice(device));
     kernel_launch_count_reset();
     UnpackArgs a = make_args();
-    if (++epoch >= (1u << 30)) { CU(cudaMemsetAsync(d_status.p, 0, d_status.cap, s)); epoch = 1; }
-    a.epoch = epoch;
     CU(cudaEventRecord(ev[0], s));
     CU(cudaMemsetAsync(d_b2p.p, 0, std::max<size_t>((size_t)F * bw * bh * 4, 4), s));
     CU(cudaMemsetAsync(d_count.p, 0, std::max<size_t>((size_t)F * 4, 4), s));
@@ -673,16 +668,16 @@ struct Batch {
     const bool dbg = (want & WANT_DEBUG) != 0;
     CU(cudaMemsetAsync(d_changed.p, 0, std::max<size_t>((size_t)F * 16, 16), s));
     if (smooth) CU(cudaMemsetAsync(d_blist_count.p, 0, std::max<size_t>((size_t)F * 4, 4), s));
-    if (two_pass) {   // debug: the counts of every frame first, one scan, then the emit launches
-      KL(launch_unpack(a, 1, false, 0, n_tiles, s));
-      KL(launch_tile_scan(a, s));
-    }
-    const int emit_mode = two_pass ? 2 : 0;
+    // unpack = count (points per owned slot) -> slot scan (run starts per frame, frame totals) -> emit
+    CU(cudaEventRecord(ev[6], s));
+    KL(launch_count(a, 0, n_tiles, s));
+    KL(launch_slot_scan(a, s));
+    CU(cudaEventRecord(ev[7], s));
     if (!smooth) {
       while (ev_grp.size() < 2) { cudaEvent_t e; CU(cudaEventCreate(&e)); ev_grp.push_back(e); }
       n_groups = 1;
       CU(cudaEventRecord(ev_grp[0], s));
-      KL(launch_unpack(a, emit_mode, false, 0, n_tiles, s));
+      KL(launch_emit(a, false, 0, n_tiles, s));
       CU(cudaEventRecord(ev_grp[1], s));
     } else {
       // frame groups: unpack (+ cell statistics + boundary lists) -> filter -> clear, tables stay hot in L2
@@ -695,7 +690,7 @@ struct Batch {
         a.sm.group_first_slot = h_ftb[f0] * (uint32_t)kWarpsPerTile;
         a.sm.group_slots = (h_ftb[f1] - h_ftb[f0]) * (uint32_t)kWarpsPerTile;
         CU(cudaEventRecord(ev_grp[2 * gi], s));
-        KL(launch_unpack(a, emit_mode, true, h_ftb[f0], h_ftb[f1], s));
+        KL(launch_emit(a, true, h_ftb[f0], h_ftb[f1], s));
         CU(cudaEventRecord(ev_grp[2 * gi + 1], s));
         if (dbg) {
           CU(cudaMemcpyAsync(d_pos_pre.as<uint8_t>() + (size_t)f0 * cap * 6, d_pos.as<uint8_t>() + (size_t)f0 * cap * 6,
@@ -789,14 +784,15 @@ struct Batch {
     CU(cudaEventElapsedTime(&t.b2p, ev[0], ev[1]));
     float whole = 0;
     CU(cudaEventElapsedTime(&whole, ev[1], ev[2]));
+    CU(cudaEventElapsedTime(&t.count, ev[6], ev[7]));
     t.unpack = 0;
     for (uint32_t gi = 0; gi < n_groups; ++gi) {
       float ms = 0;
       CU(cudaEventElapsedTime(&ms, ev_grp[2 * gi], ev_grp[2 * gi + 1]));
       t.unpack += ms;
     }
-    t.geo = std::max(0.f, whole - t.unpack);   // filter + clear launches of all groups (both smoothing stages)
-    t.col = 0; t.rgb = 0;
+    t.geo = std::max(0.f, whole - t.unpack - t.count);   // filter + clear launches of all groups (both smoothing stages)
+    t.col = 0; t.rgb = 0;   // colour smoothing runs inside the same filter launch; RGB conversion is fused into the emit
     return TMC2_OK;
   }
 };
@@ -1118,7 +1114,7 @@ tmc2_status tmc2gpu_last_stage_ms(tmc2gpu_ctx* ctx, float* ms5) {
   StageTimes t;
   ctx->err = Err();
   if (ctx->last_batch->stage_times(t, ctx->err)) return ctx->fail();
-  ms5[0] = t.b2p; ms5[1] = t.unpack; ms5[2] = t.geo; ms5[3] = t.col; ms5[4] = t.rgb;
+  ms5[0] = t.b2p; ms5[1] = t.unpack; ms5[2] = t.geo; ms5[3] = t.count; ms5[4] = t.rgb;
   return TMC2_OK;
 }
 
