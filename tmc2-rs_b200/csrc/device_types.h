@@ -6,13 +6,13 @@
 //   attr_y [F][2][H][pitch]            u16  attribute video, channel 0         (reference atlas.attr_frames[0])
 //   attr_u [F][2][H/2][pitch_c]        u16  channel 1 (4:2:0)      attr_v likewise
 //   patches[total]  DevPatch ; slot_rec[n_tiles*kWarpsPerTile] SlotRec ; tile_frame[n_tiles] ; frame_tile_begin[F+1]
-//   block_to_patch [F][bw*bh] u32 ; owned[n_tiles*kWarpsPerTile] u32 (per frame: its owned slots, compacted, in order)
+//   block_to_patch [F][bw*bh] u32 ; work[n_tiles*kWarpsPerTile] WorkRec (per frame: its owned slots, compacted, in order)
 // Pitches are multiples of 64 elements so every 16x16 canvas block row starts on a 32-byte boundary.
 // Outputs are per-frame slabs of `cap` points (cap % 16 == 0):  pos [F][cap][3] u16, rgb [F][cap][3] u8, and (debug /
 // stage API only) yuv [F][cap][3] u16, partition [F][cap] u16, pixel [F][cap] u32 (x | y<<15 | map<<30), btype [F][cap] u8;
 // count [F] u32.
-// Smoothing state (per group of frames): voxel-cell tables (GeoCell / ColCell, dense or hashed), a per-slot log of the
-// cells each slot added to, and per frame a compact list of type-1 boundary points (BoundaryEntry).
+// Smoothing state (per group of frames): voxel-cell tables (GeoCell / ColCell, dense or hashed), per frame a log of the
+// cells that were touched (written once, by the first toucher) and a compact list of type-1 boundary points.
 #pragma once
 #include <cstdint>
 
@@ -49,6 +49,20 @@ struct alignas(16) SlotRec {
   uint16_t u0b, v0b;         // block inside the patch
   uint16_t bx, by;           // canvas block it maps to (src/decoder.rs:827-837)
   int8_t   ax, ay, rx, ry;   // copy of the patch's affine steps
+};
+
+// One owned slot at its position in the frame's compacted list: everything the count / emit warps need in two 16-byte
+// loads.  compact_owned_kernel fills the slot part (pid = kNoPatch for the unused tail of a frame's region), count_kernel
+// `total`, slot_scan_kernel `base`.
+struct alignas(16) WorkRec {
+  uint32_t pid;
+  uint16_t u0b, v0b;
+  uint16_t bx, by;
+  int8_t   ax, ay, rx, ry;
+  uint32_t frame;            // frame inside the batch
+  uint32_t total;            // points this slot emits
+  uint32_t base;             // first point of its run inside the frame
+  uint32_t _pad;
 };
 
 struct Planes {
@@ -109,15 +123,13 @@ struct GridDesc {               // geometry of one voxel grid
   uint64_t slots;               // table slots per frame-in-group (power of two unless identity)
   void*    table;               // GeoCell / ColCell [frames_in_group][slots]
   uint32_t* keys;               // hashed tables only: [frames_in_group][slots], kCellEmpty = free
-  uint32_t* log;                // [slots_in_group][log_stride] table slot of every flush of that unpack slot
-  uint32_t* log_count;          // [slots_in_group]
+  uint32_t* log;                // [frames_in_group][log_cap] table slots touched in that frame, each exactly once
+  uint32_t* log_count;          // [frames_in_group]
+  uint64_t log_cap;
 };
 
 struct SmoothArgs {
   GridDesc geo, col;
-  uint32_t log_stride;          // entries per unpack slot (2 * res * res)
-  uint32_t group_first_slot;    // first unpack slot of the group (logs are indexed by slot - group_first_slot)
-  uint32_t group_slots;
   BoundaryEntry* blist;         // [F][blist_cap]
   uint32_t* blist_count;        // [F]
   uint64_t blist_cap;
@@ -141,28 +153,20 @@ struct UnpackArgs {
   const uint32_t* tile_frame;
   const uint32_t* frame_tile_begin;   // [F+1]
   const uint32_t* block_to_patch;     // [F][bw*bh]
-  uint32_t*       owned;              // [n_tiles*kWarpsPerTile] compacted owned slots of each frame, from frame_tile_begin[f]*8
+  WorkRec*        work;               // [n_tiles*kWarpsPerTile] compacted owned slots of each frame, from frame_tile_begin[f]*8
   uint32_t*       owned_count;        // [F]
-  uint32_t*       slot_total;         // [n_tiles*kWarpsPerTile] points of each owned slot (count_kernel), same indexing as owned[]
-  uint32_t*       slot_base;          // first point of each owned slot inside its frame (slot_scan_kernel)
   uint32_t*       frame_count;        // [F] points per frame
   int*            err;                // device error flag (0 ok)
   SmoothArgs sm;                      // used by the smoothing instantiation only
 };
 
-// shared memory of one warp of emit_kernel: per-pixel tables of the block, the point list, and one staged chunk
-constexpr uint32_t kChunkPoints = 256;       // points staged per pass (a block holds at most 512)
-constexpr uint32_t kOffNn = 0;                                   // [256] n0 | n1 << 16 by pixel rank
-constexpr uint32_t kOffYy = kOffNn + 1024;                       // [256] Y(map 0) | Y(map 1) << 16
-constexpr uint32_t kOffTerm = kOffYy + 1024;                     // [128] chroma term per (chroma sample, map), 16 B
-constexpr uint32_t kOffSrc = kOffTerm + 2048;                    // [512] u16: output point -> pixel rank << 1 | map
-constexpr uint32_t kOffBt = kOffSrc + 1024;                      // [32]  boundary classes of each lane's 8 pixels
-constexpr uint32_t kOffBmp = kOffBt + 128;                       // [32]  20x20 occupancy bitmap rows
-constexpr uint32_t kOffPos = kOffBmp + 128;                      // staged positions: 8 B / point + a pad slot every 8
-constexpr uint32_t kStagePosBytes = (kChunkPoints + kChunkPoints / 8) * 8;
-constexpr uint32_t kOffRgb = kOffPos + kStagePosBytes;           // staged colours: 4 B / point + a pad slot every 16
-constexpr uint32_t kStageRgbBytes = (kChunkPoints + kChunkPoints / 16) * 4;
-constexpr uint32_t kWarpSmemBytes = kOffRgb + kStageRgbBytes;    // 8768
+// shared memory of one warp of emit_kernel: per-pixel tables of the block in PATCH raster order (rank = v1*16 + u1)
+constexpr uint32_t kOffPt = 0;                                   // [256][2] u32: n | Y << 16 of map 0 / map 1
+constexpr uint32_t kOffTerm = kOffPt + 2048;                     // [64][2] uint4: chroma term of (chroma sample, map)
+constexpr uint32_t kOffSrc = kOffTerm + 2048;                    // [512] u16: output point -> rank << 1 | map
+constexpr uint32_t kOffCnt = kOffSrc + 1024;                     // [256] u8: points of the pixel (0..2) | boundary class << 2
+constexpr uint32_t kOffBmp = kOffCnt + 256;                      // [32] u32: 20x20 occupancy bitmap rows (canvas axes)
+constexpr uint32_t kWarpSmemBytes = kOffBmp + 128;               // 5504
 
 // launch wrappers (kernels.cu); every one enqueues on `stream` and returns the cudaGetLastError() code
 int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream);
@@ -175,7 +179,7 @@ int launch_emit(const UnpackArgs& a, bool smooth, uint32_t tile_begin, uint32_t 
 int launch_upsample(const UnpackArgs& a, uint8_t* occ_full /*[F][H][W]*/, void* stream);
 int launch_smooth_finalize(const UnpackArgs& a, void* stream); // sums -> means for every cell the group touched
 int launch_smooth_filter(const UnpackArgs& a, void* stream);   // boundary points of the current frame group
-int launch_smooth_clear(const UnpackArgs& a, void* stream);    // reset touched cells + list counters of the group
+int launch_smooth_clear(const UnpackArgs& a, void* stream);    // reset touched cells (+ keys) of the group
 int launch_yuv_to_rgb_flat(const uint16_t* yuv, uint8_t* rgb, uint64_t n, void* stream);
 int launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, void* stream);
 int kernel_launch_count_reset();   // returns launches since the last reset

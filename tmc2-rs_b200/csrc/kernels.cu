@@ -335,11 +335,13 @@ __global__ void __launch_bounds__(1024) compact_owned_kernel(const UnpackArgs a)
   for (uint32_t b = s0; b < s1; b += blockDim.x) {
     const uint32_t slot = b + threadIdx.x;
     bool own = false;
+    uint4 rec = make_uint4(kNoPatch, 0, 0, 0);
     if (slot < s1) {
-      const SlotRec R = load_slot_rec(a.slot_rec + slot);
-      if (R.pid != kNoPatch) {
-        const uint32_t local_index = __ldg(&a.patches[R.pid].local_index);
-        own = a.block_to_patch[(uint64_t)f * a.bw * a.bh + (uint64_t)R.by * a.bw + R.bx] == local_index + 1;
+      rec = __ldg(reinterpret_cast<const uint4*>(a.slot_rec + slot));
+      if (rec.x != kNoPatch) {
+        const uint32_t local_index = __ldg(&a.patches[rec.x].local_index);
+        const uint32_t bx = rec.z & 0xFFFFu, by = rec.z >> 16;
+        own = a.block_to_patch[(uint64_t)f * a.bw * a.bh + (uint64_t)by * a.bw + bx] == local_index + 1;
       }
     }
     const uint32_t m = __ballot_sync(kFull, own);
@@ -347,10 +349,20 @@ __global__ void __launch_bounds__(1024) compact_owned_kernel(const UnpackArgs a)
     __syncthreads();
     uint32_t base = s_carry;
     for (uint32_t w = 0; w < warp; ++w) base += s_w[w];
-    if (own) a.owned[s0 + base + __popc(m & ((1u << lane) - 1u))] = slot;
+    if (own) {
+      uint4* dst = reinterpret_cast<uint4*>(a.work + s0 + base + __popc(m & ((1u << lane) - 1u)));
+      dst[0] = rec;
+      dst[1] = make_uint4(f, 0, 0, 0);
+    }
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) s_carry = base + __popc(m);
     __syncthreads();
+  }
+  // the unused tail of the frame's region: inactive records
+  for (uint32_t i = s0 + s_carry + threadIdx.x; i < s1; i += blockDim.x) {
+    uint4* dst = reinterpret_cast<uint4*>(a.work + i);
+    dst[0] = make_uint4(kNoPatch, 0, 0, 0);
+    dst[1] = make_uint4(f, 0, 0, 0);
   }
   if (threadIdx.x == 0) a.owned_count[f] = s_carry;
 }
@@ -374,6 +386,11 @@ __global__ void __launch_bounds__(256) upsample_kernel(const UnpackArgs a, uint8
 //   slot_scan_kernel  per frame: exclusive prefix of those counts in slot order == where every run starts (codec.rs:482)
 //   emit_kernel       per owned slot: reload, build positions + colours, write the run at its final place
 // A warp owns a slot; warps never talk to each other, so there is no barrier, flag or look-back anywhere.
+//
+// A block-aligned slot (16x16 block == one canvas block, every orientation whose pixel map is the affine one) is always
+// LOADED in canvas layout -- lane (r, h) = canvas row r, columns 8h..8h+7, one 16-byte vector per plane -- whatever the
+// patch orientation.  The orientation only decides where a pixel lands in the per-pixel tables in shared memory, which
+// are in PATCH raster order (rank = v1*16 + u1, the reference's emission order).
 // ----------------------------------------------------------------------------------------------------------------
 
 // normal coordinates (n0 | n1 << 16) of one pixel from its two geometry samples (codec.rs:534-558)
@@ -384,138 +401,80 @@ __device__ __forceinline__ uint32_t normals_of(const DevPatch& P, uint32_t s0, u
   return n0 | (n1 << 16);
 }
 
-// staged point k of a chunk: positions 8 B apart with one pad slot every 8 points, colours 4 B apart with one pad slot
-// every 16 points, so that the copy-out (one lane per group of 8 / 16 points) is free of bank conflicts
-__device__ __forceinline__ uint32_t spos_off(uint32_t k) { return (k + (k >> 3)) * 8u; }
-__device__ __forceinline__ uint32_t srgb_off(uint32_t k) { return (k + (k >> 4)) * 4u; }
-
 __device__ __forceinline__ uint32_t cell_key_of(const GridDesc& G, uint32_t x, uint32_t y, uint32_t z) {
   if (!(x < G.th && y < G.th && z < G.th)) return kCellEmpty;
   return cell_div(x, G) | (cell_div(y, G) << 10) | (cell_div(z, G) << 20);
 }
 
-// Is the block-aligned lane layout usable for this slot?  (16x16 blocks, power-of-two precision, affine steps present:
-// the host zeroes the steps of reference-literal rotated patches, which take the generic per-pixel path.)
-__device__ __forceinline__ bool slot_is_fast(const UnpackArgs& a, const SlotRec& R) {
+__device__ __forceinline__ WorkRec load_work(const WorkRec* p) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p), w = *(reinterpret_cast<const uint4*>(p) + 1);
+  WorkRec r;
+  r.pid = v.x; r.u0b = (uint16_t)v.y; r.v0b = (uint16_t)(v.y >> 16); r.bx = (uint16_t)v.z; r.by = (uint16_t)(v.z >> 16);
+  r.ax = (int8_t)v.w; r.ay = (int8_t)(v.w >> 8); r.rx = (int8_t)(v.w >> 16); r.ry = (int8_t)(v.w >> 24);
+  r.frame = w.x; r.total = w.y; r.base = w.z; r._pad = 0;
+  return r;
+}
+
+// Is the block-aligned layout usable for this slot?  (16x16 blocks, power-of-two precision, affine steps present: the
+// host zeroes the steps of reference-literal rotated patches, which take the generic per-pixel path.)
+__device__ __forceinline__ bool slot_is_fast(const UnpackArgs& a, const WorkRec& R) {
   return a.res == 16 && a.prec_shift >= 0 && (R.ax != 0 || R.ay != 0);
 }
 
-// Lane layout of a slot.  Lane l owns the 8 pixels of patch-local ranks 8l .. 8l+7 (row v1 = l/2, columns
-// u1 = 8(l&1) .. +7), whatever the patch orientation: the orientation only changes WHERE those pixels are loaded from.
-struct LaneBlock {
+// the fields of a DevPatch that the block-aligned path needs (three 16-byte loads, registers only)
+__device__ __forceinline__ void load_patch_fields(const DevPatch* p, DevPatch& P) {
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1), c = __ldg(reinterpret_cast<const uint4*>(p) + 2);
+  P.u1 = b.x; P.v1 = b.y; P.d1 = b.z; P.lod_x = (uint16_t)b.w; P.lod_y = (uint16_t)(b.w >> 16);
+  P.normal = (uint8_t)c.x; P.tangent = (uint8_t)(c.x >> 8); P.bitangent = (uint8_t)(c.x >> 16); P.mode = (uint8_t)(c.x >> 24);
+  P.local_index = __ldg(&p->local_index);
+}
+
+// Canvas-layout view of a block: lane (r = lane >> 1, h = lane & 1) holds canvas row r, columns 8h .. 8h+7.
+struct CanvasBlock {
   uint32_t nn[8];            // n0 | n1 << 16 per pixel
-  uint32_t yy[8];            // attribute Y of map 0 | map 1 << 16 per pixel
-  uint32_t cA[4], cB[4];     // chroma of map 0 / map 1 per pixel pair: U | V << 16
   uint32_t m1, m2;           // bit j set = pixel j of this lane emits >= 1 / 2 points
-  int32_t xs, ys;            // canvas position of pixel 0; pixel j is (xs + ax*j, ys + ay*j)
 };
 
-template <bool kAttr>
-__device__ __forceinline__ void load_lane_block(const UnpackArgs& a, const SlotRec& R, uint32_t frame, uint32_t lane,
-                                                DevPatch& P, LaneBlock& L) {
-  const int32_t h = (int32_t)(lane & 1u), r = (int32_t)(lane >> 1);
-  const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
-  const int32_t cx0 = (int32_t)R.bx * 16 + ((ax < 0 || rx < 0) ? 15 : 0);
-  const int32_t cy0 = (int32_t)R.by * 16 + ((ay < 0 || ry < 0) ? 15 : 0);
-  const int32_t xs = cx0 + ax * 8 * h + rx * r, ys = cy0 + ay * 8 * h + ry * r;
-  L.xs = xs; L.ys = ys;
-  const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
-  const uint16_t* geo1 = geo0 + a.in.geo_map_stride;
-  const bool attr = kAttr && a.has_attr;
-  const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride;
-  const uint16_t* ay1 = ay0 + a.in.attr_y_map_stride;
-  const uint64_t cf = (uint64_t)frame * 2 * a.in.attr_c_map_stride;
-  const uint16_t* au0 = a.in.attr_u + cf; const uint16_t* au1 = au0 + a.in.attr_c_map_stride;
-  const uint16_t* av0 = a.in.attr_v + cf; const uint16_t* av1 = av0 + a.in.attr_c_map_stride;
-  if (ax == 1) {
-    // Default-like rows: the 8 pixels are 16 contiguous bytes of every plane
-    const uint32_t goff = (uint32_t)ys * a.in.geo_pitch + (uint32_t)xs;
-    const uint4 g0 = ldg_nc_v4(geo0 + goff);
-    const uint4 g1 = ldg_nc_v4(geo1 + goff);
-    uint4 ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
-    uint2 ua = {0, 0}, va = {0, 0}, ub = {0, 0}, vb = {0, 0};
-    if (attr) {
-      const uint32_t yoff = (uint32_t)ys * a.in.attr_pitch_y + (uint32_t)xs;
-      ya = ldg_nc_v4(ay0 + yoff); yb = ldg_nc_v4(ay1 + yoff);
-      const uint32_t coff = (uint32_t)(ys >> 1) * a.in.attr_pitch_c + (uint32_t)(xs >> 1);
-      ua = ldg_nc_v2(au0 + coff); va = ldg_nc_v2(av0 + coff);
-      ub = ldg_nc_v2(au1 + coff); vb = ldg_nc_v2(av1 + coff);
-    }
-    P = a.patches[R.pid];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
-      L.nn[j] = __byte_perm(word_of(g0, j >> 1), word_of(g1, j >> 1), sel);      // raw samples, converted below
-      if (kAttr) L.yy[j] = __byte_perm(word_of(ya, j >> 1), word_of(yb, j >> 1), sel);
-    }
-    if (kAttr) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t sel = (c & 1) ? 0x7632u : 0x5410u;
-        L.cA[c] = __byte_perm(word_of(ua, c >> 1), word_of(va, c >> 1), sel);
-        L.cB[c] = __byte_perm(word_of(ub, c >> 1), word_of(vb, c >> 1), sel);
-      }
-    }
-  } else {
-    // transposed / mirrored: eight 2-byte loads per plane; across the warp every load still covers whole 32-byte sectors
-    const int32_t dstep = ay * (int32_t)a.in.geo_pitch + ax;
-    const int32_t goff = ys * (int32_t)a.in.geo_pitch + xs;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int32_t o = goff + j * dstep;
-      L.nn[j] = ldg_nc_u16(geo0 + o) | (ldg_nc_u16(geo1 + o) << 16);
-    }
-    if (kAttr) {
-      if (attr) {
-        const int32_t ystep = ay * (int32_t)a.in.attr_pitch_y + ax;
-        const int32_t yoff = ys * (int32_t)a.in.attr_pitch_y + xs;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int32_t o = yoff + j * ystep;
-          L.yy[j] = ldg_nc_u16(ay0 + o) | (ldg_nc_u16(ay1 + o) << 16);
-        }
-        const int32_t cstep = ay * (int32_t)a.in.attr_pitch_c + ax;
-        const int32_t coff = (ys >> 1) * (int32_t)a.in.attr_pitch_c + (xs >> 1);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int32_t o = coff + c * cstep;
-          L.cA[c] = ldg_nc_u16(au0 + o) | (ldg_nc_u16(av0 + o) << 16);
-          L.cB[c] = ldg_nc_u16(au1 + o) | (ldg_nc_u16(av1 + o) << 16);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) L.yy[j] = 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { L.cA[c] = 0; L.cB[c] = 0; }
-      }
-    }
-    P = a.patches[R.pid];
-  }
+// geometry + occupancy of the lane's 8 pixels -> normals and the two emission masks
+__device__ __forceinline__ void load_geometry(const UnpackArgs& a, const WorkRec& R, const DevPatch& P, uint32_t lane,
+                                              CanvasBlock& L) {
+  const uint32_t h = lane & 1u, r = lane >> 1;
+  const uint32_t x0 = (uint32_t)R.bx * 16u + 8u * h, y = (uint32_t)R.by * 16u + r;
+  const uint16_t* geo0 = a.in.geo + (uint64_t)R.frame * 2 * a.in.geo_map_stride;
+  const uint32_t goff = y * a.in.geo_pitch + x0;
+  const uint4 g0 = ldg_nc_v4(geo0 + goff);
+  const uint4 g1 = ldg_nc_v4(geo0 + a.in.geo_map_stride + goff);
   // occupancy of the 8 pixels (codec.rs:393-396: any non-zero sample counts).  Pixels j*p .. j*p+p-1 share a sample.
   uint32_t m1 = 0, m2 = 0;
   {
-    const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
+    const uint8_t* occ_f = a.in.occ + (uint64_t)R.frame * a.in.occ_frame_stride;
     const int32_t lp = a.prec_shift;
-    const int32_t p = 1 << lp;
-    const int32_t nb = lp >= 3 ? 1 : (8 >> lp);
-    const uint32_t ones = lp >= 3 ? 0xFFu : ((1u << p) - 1u);
-    for (int32_t k = 0; k < nb; ++k) {
-      const int32_t j = k << lp;
-      const uint32_t ox = (uint32_t)(xs + ax * j) >> lp, oy = (uint32_t)(ys + ay * j) >> lp;
-      if (occ_f[(uint64_t)oy * a.in.occ_pitch + ox] != 0) m1 |= ones << j;
+    const uint8_t* row = occ_f + (uint64_t)(y >> lp) * a.in.occ_pitch;
+    if (lp == 2) {
+      const uint32_t o = *reinterpret_cast<const uint16_t*>(row + (x0 >> 2));     // two samples, 2-byte aligned (x0 % 8 == 0)
+      m1 = ((o & 0xFFu) ? 0x0Fu : 0u) | ((o >> 8) ? 0xF0u : 0u);
+    } else {
+      const int32_t nb = lp >= 3 ? 1 : (8 >> lp);
+      const uint32_t ones = lp >= 3 ? 0xFFu : ((1u << (1 << lp)) - 1u);
+      for (int32_t k = 0; k < nb; ++k) {
+        const int32_t j = k << lp;
+        if (row[(x0 + j) >> lp] != 0) m1 |= ones << j;
+      }
     }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    L.nn[j] = normals_of(P, L.nn[j] & 0xFFFFu, L.nn[j] >> 16, a.absolute_d1);
-    if ((L.nn[j] >> 16) != (L.nn[j] & 0xFFFFu)) m2 |= (m1 & (1u << j));            // codec.rs:422-428 duplicate skip
+    const uint32_t s = __byte_perm(word_of(g0, j >> 1), word_of(g1, j >> 1), (j & 1) ? 0x7632u : 0x5410u);
+    L.nn[j] = normals_of(P, s & 0xFFFFu, s >> 16, a.absolute_d1);
+    if ((L.nn[j] >> 16) != (L.nn[j] & 0xFFFFu)) m2 |= 1u << j;                    // codec.rs:422-428 duplicate skip
   }
-  L.m1 = m1; L.m2 = m2;
+  L.m1 = m1; L.m2 = m2 & m1;
 }
 
 // points of a generic slot (any resolution / precision, reference-literal rotated orientations): lane = pixel
-__device__ __noinline__ uint32_t generic_slot_count(const UnpackArgs& a, const DevPatch& P, uint32_t frame, uint32_t u0b,
+__device__ __noinline__ uint32_t generic_slot_count(const UnpackArgs& a, uint32_t pid, uint32_t frame, uint32_t u0b,
                                                     uint32_t v0b) {
+  const DevPatch P = a.patches[pid];
   const uint32_t lane = lane_id(), res = a.res;
   const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
   const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
@@ -540,11 +499,47 @@ __device__ __noinline__ uint32_t generic_slot_count(const UnpackArgs& a, const D
   return total;
 }
 
+// ---- smoothing: accumulate into a cell; the first toucher of a cell appends it to the frame's log -----------------------
+// returns true when this call was the first to touch the cell (pmax1 was 0 == untouched)
+__device__ __forceinline__ bool geo_cell_add_first(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
+                                                   uint32_t sx, uint32_t sy, uint32_t sz) {
+  GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + slot;
+  const uint32_t old = atomicMax(&c->pmax1, patch + 1u);
+  atomicMax(&c->pminc, ~patch);
+  atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
+  atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
+  return old == 0u;
+}
+__device__ __forceinline__ bool col_cell_add_first(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
+                                                   uint32_t sy, uint32_t su, uint32_t sv, unsigned long long sy2) {
+  ColCell* c = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots + slot;
+  const uint32_t old = atomicMax(&c->pmax1, patch + 1u);
+  atomicMax(&c->pminc, ~patch);
+  atomicAdd(&c->cnt_sy, (unsigned long long)cnt | ((unsigned long long)sy << 24));
+  atomicAdd(&c->su_sv, (unsigned long long)su | ((unsigned long long)sv << 32));
+  atomicAdd(&c->sy2, sy2);
+  return old == 0u;
+}
+// warp-aggregated append of the lanes with `first` set (call with the whole warp converged)
+__device__ __forceinline__ void log_append(const UnpackArgs& a, const GridDesc& G, uint32_t fig, bool first, uint32_t cs,
+                                           uint32_t lane) {
+  const uint32_t fm = __ballot_sync(kFull, first);
+  if (fm == 0) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(&G.log_count[fig], (uint32_t)__popc(fm));
+  base = __shfl_sync(kFull, base, 0);
+  if (first) {
+    const uint64_t i = (uint64_t)base + __popc(fm & ((1u << lane) - 1u));
+    if (i < G.log_cap) G.log[(uint64_t)fig * G.log_cap + i] = cs;
+    else atomicExch(a.err, 11);
+  }
+}
+
 // Generic slot path: lane = pixel, 32 at a time in patch raster order, everything straight to global memory.  Rare.
 template <bool kSmooth, bool kDebug>
-__device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, const DevPatch& P, uint32_t frame, uint32_t fig,
-                                               uint32_t u0b, uint32_t v0b, uint64_t gidx, uint32_t* log_geo, uint32_t* log_col,
-                                               uint32_t* n_log /* shared: [0] geo, [1] col */) {
+__device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, uint32_t pid, uint32_t frame, uint32_t fig, uint32_t u0b,
+                                               uint32_t v0b, uint64_t gidx) {
+  const DevPatch P = a.patches[pid];
   const uint32_t lane = lane_id(), res = a.res;
   const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
   const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride;
@@ -579,48 +574,52 @@ __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, const DevPat
     uint64_t k = run + (incl - c);
     uint32_t bt = 0;
     if (c && ((kDebug && a.out.btype) || kSmooth)) bt = boundary_type(a, occ_f, (int32_t)x, (int32_t)y);
-    for (uint32_t m = 0; m < c; ++m, ++k) {
+    for (uint32_t m = 0; m < 2; ++m) {                               // warp-uniform trip count: log_append is convergent
+      const bool on = m < c;
       const uint32_t n = m == 0 ? n0 : n1;
       const uint32_t X = pick(srcx, n, t, b), Yc = pick(srcy, n, t, b), Z = pick(srcz, n, t, b);
-      if (a.out.pos) { uint16_t* d = a.out.pos + k * 3; d[0] = (uint16_t)X; d[1] = (uint16_t)Yc; d[2] = (uint16_t)Z; }
       uint32_t Y = 0, U = 0, V = 0;
-      if (a.has_attr) {
-        const uint64_t fm = (uint64_t)frame * 2 + m;
-        Y = a.in.attr_y[fm * a.in.attr_y_map_stride + (uint64_t)y * a.in.attr_pitch_y + (uint64_t)x];
-        const uint64_t co = fm * a.in.attr_c_map_stride + (uint64_t)(y >> 1) * a.in.attr_pitch_c + (uint64_t)(x >> 1);
-        U = a.in.attr_u[co]; V = a.in.attr_v[co];
-        if (kDebug && a.out.yuv) { uint16_t* d = a.out.yuv + k * 3; d[0] = (uint16_t)Y; d[1] = (uint16_t)U; d[2] = (uint16_t)V; }
-        if (a.out.rgb) {
-          const uint32_t cc = yuv_to_rgb_packed(Y, U, V);
-          uint8_t* d = a.out.rgb + k * 3; d[0] = (uint8_t)cc; d[1] = (uint8_t)(cc >> 8); d[2] = (uint8_t)(cc >> 16);
+      if (on) {
+        if (a.out.pos) { uint16_t* d = a.out.pos + k * 3; d[0] = (uint16_t)X; d[1] = (uint16_t)Yc; d[2] = (uint16_t)Z; }
+        if (a.has_attr) {
+          const uint64_t fm = (uint64_t)frame * 2 + m;
+          Y = a.in.attr_y[fm * a.in.attr_y_map_stride + (uint64_t)y * a.in.attr_pitch_y + (uint64_t)x];
+          const uint64_t co = fm * a.in.attr_c_map_stride + (uint64_t)(y >> 1) * a.in.attr_pitch_c + (uint64_t)(x >> 1);
+          U = a.in.attr_u[co]; V = a.in.attr_v[co];
+          if (kDebug && a.out.yuv) { uint16_t* d = a.out.yuv + k * 3; d[0] = (uint16_t)Y; d[1] = (uint16_t)U; d[2] = (uint16_t)V; }
+          if (a.out.rgb) {
+            const uint32_t cc = yuv_to_rgb_packed(Y, U, V);
+            uint8_t* d = a.out.rgb + k * 3; d[0] = (uint8_t)cc; d[1] = (uint8_t)(cc >> 8); d[2] = (uint8_t)(cc >> 16);
+          }
         }
+        if (kDebug && a.out.part) a.out.part[k] = (uint16_t)P.local_index;
+        if (kDebug && a.out.pix) a.out.pix[k] = (uint32_t)x | ((uint32_t)y << 15) | (m << 30);
+        if (kDebug && a.out.btype) a.out.btype[k] = (uint8_t)bt;
       }
-      if (kDebug && a.out.part) a.out.part[k] = (uint16_t)P.local_index;
-      if (kDebug && a.out.pix) a.out.pix[k] = (uint32_t)x | ((uint32_t)y << 15) | (m << 30);
-      if (kDebug && a.out.btype) a.out.btype[k] = (uint8_t)bt;
       if (kSmooth) {
         if (a.sm.geo.on) {
-          const uint32_t key = cell_key_of(a.sm.geo, X, Yc, Z);
+          bool first = false; uint32_t cs = kCellEmpty;
+          const uint32_t key = on ? cell_key_of(a.sm.geo, X, Yc, Z) : kCellEmpty;
           if (key != kCellEmpty) {
-            const uint32_t cs = cell_slot(a.sm.geo, fig, key, a.err);
+            cs = cell_slot(a.sm.geo, fig, key, a.err);
             if (cs != kCellEmpty) {
               const uint32_t g = a.sm.geo.g;
-              geo_cell_add(a.sm.geo, fig, cs, P.local_index, 1, X - (key & 1023u) * g, Yc - ((key >> 10) & 1023u) * g, Z - (key >> 20) * g);
-              log_geo[atomicAdd(&n_log[0], 1u)] = cs;
+              first = geo_cell_add_first(a.sm.geo, fig, cs, P.local_index, 1, X - (key & 1023u) * g,
+                                         Yc - ((key >> 10) & 1023u) * g, Z - (key >> 20) * g);
             }
           }
+          log_append(a, a.sm.geo, fig, first, cs, lane);
         }
-        if (a.sm.col.on && a.has_attr && bt == 2) {
-          const uint32_t key = cell_key_of(a.sm.col, X, Yc, Z);
+        if (a.sm.col.on && a.has_attr) {
+          bool first = false; uint32_t cs = kCellEmpty;
+          const uint32_t key = (on && bt == 2) ? cell_key_of(a.sm.col, X, Yc, Z) : kCellEmpty;
           if (key != kCellEmpty) {
-            const uint32_t cs = cell_slot(a.sm.col, fig, key, a.err);
-            if (cs != kCellEmpty) {
-              col_cell_add(a.sm.col, fig, cs, P.local_index, 1, Y, U, V, (unsigned long long)Y * Y);
-              log_col[atomicAdd(&n_log[1], 1u)] = cs;
-            }
+            cs = cell_slot(a.sm.col, fig, key, a.err);
+            if (cs != kCellEmpty) first = col_cell_add_first(a.sm.col, fig, cs, P.local_index, 1, Y, U, V, (unsigned long long)Y * Y);
           }
+          log_append(a, a.sm.col, fig, first, cs, lane);
         }
-        if (bt == 1) {
+        if (on && bt == 1) {
           const uint32_t li = atomicAdd(&a.sm.blist_count[frame], 1u);
           if (li < a.sm.blist_cap) {
             BoundaryEntry e;
@@ -631,6 +630,7 @@ __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, const DevPat
           } else atomicExch(a.err, 7);
         }
       }
+      if (on) ++k;
     }
     run += chunk_total;
   }
@@ -638,25 +638,25 @@ __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, const DevPat
 
 // ---- pass 1: points per owned slot ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerTile * 32) count_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
-  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-  const uint32_t tile = blockIdx.x + tile_offset;
-  const uint32_t frame = a.tile_frame[tile];
-  const uint32_t first_tile = a.frame_tile_begin[frame];
-  const uint32_t pos_in_frame = (tile - first_tile) * kWarpsPerTile + warp;
-  if (pos_in_frame >= a.owned_count[frame]) return;
-  const uint32_t lpos = tile * kWarpsPerTile + warp;
-  const SlotRec R = load_slot_rec(a.slot_rec + a.owned[lpos]);
+  const uint32_t lane = lane_id();
+  const uint32_t lpos = (blockIdx.x + tile_offset) * kWarpsPerTile + (threadIdx.x >> 5);
+  const WorkRec R = load_work(a.work + lpos);
+  if (R.pid == kNoPatch) return;                                   // unused tail of the frame's region (total stays 0)
   uint32_t total;
-  DevPatch P;
   if (slot_is_fast(a, R)) {
-    LaneBlock L;
-    load_lane_block<false>(a, R, frame, lane, P, L);
+    DevPatch P;
+    {
+      const DevPatch* p = a.patches + R.pid;
+      P.d1 = __ldg(&p->d1);
+      P.mode = (uint8_t)(__ldg(reinterpret_cast<const uint32_t*>(&p->normal)) >> 24);
+    }
+    CanvasBlock L;
+    load_geometry(a, R, P, lane, L);
     total = __reduce_add_sync(kFull, __popc(L.m1) + __popc(L.m2));
   } else {
-    P = a.patches[R.pid];
-    total = generic_slot_count(a, P, frame, R.u0b, R.v0b);
+    total = generic_slot_count(a, R.pid, R.frame, R.u0b, R.v0b);
   }
-  if (lane == 0) a.slot_total[lpos] = total;
+  if (lane == 0) a.work[lpos].total = total;
 }
 
 // ---- pass 2: where every run starts.  One CTA per frame; the scan domain is the frame's owned-slot list ---------------------
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(1024) slot_scan_kernel(const UnpackArgs a) {
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   for (uint32_t b = 0; b < n; b += blockDim.x) {
     const uint32_t i = b + threadIdx.x;
-    const uint32_t v = i < n ? a.slot_total[s0 + i] : 0u;
+    const uint32_t v = i < n ? a.work[s0 + i].total : 0u;
     uint32_t incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(1024) slot_scan_kernel(const UnpackArgs a) {
     __syncthreads();
     uint32_t wbase = s_carry;
     for (uint32_t w = 0; w < warp; ++w) wbase += s_w[w];
-    if (i < n) a.slot_base[s0 + i] = wbase + incl - v;
+    if (i < n) a.work[s0 + i].base = wbase + incl - v;
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) s_carry = wbase + incl;
     __syncthreads();
@@ -689,80 +689,8 @@ __global__ void __launch_bounds__(1024) slot_scan_kernel(const UnpackArgs a) {
   if (threadIdx.x == 0) a.frame_count[f] = s_carry;              // tile.total_number_of_regular_points, codec.rs:482
 }
 
-// ---- copy-out of one staged chunk ----------------------------------------------------------------------------------------
-// The chunk starts at point `run_base` of its frame slab (slabs are 16-byte aligned and hold a multiple of 16 points).
-// Packed output is written in aligned groups: 8 points = 48 B = three 16-byte vectors for positions (a group starts at a
-// point index that is a multiple of 8), 16 points = 48 B for colours (multiple of 16).  One lane assembles one group
-// from the padded staging with byte permutes; the few points before the first / after the last full group go out as
-// 2-byte / 1-byte stores.
-__device__ __forceinline__ void copy_out_pos(uint16_t* __restrict__ gpos /* frame slab */, uint32_t run_base, uint32_t total,
-                                             const uint8_t* s_pos, uint32_t lane) {
-  const uint32_t head = min(total, (0u - run_base) & 7u);
-  const uint32_t groups = (total - head) >> 3;
-  const uint32_t tail0 = head + (groups << 3);                  // first point of the tail
-  for (uint32_t g = lane; g < groups; g += 32) {
-    const uint32_t k0 = head + (g << 3);
-    // staged points k0 .. k0+7: slots are consecutive except for one pad slot after every 8th staged point
-    const uint32_t base = spos_off(k0);
-    const uint32_t brk = 8u - (k0 & 7u);                          // points at local index >= brk sit one slot further
-    uint2 p[8];
-#pragma unroll
-    for (uint32_t i = 0; i < 8; ++i)
-      p[i] = *reinterpret_cast<const uint2*>(s_pos + base + i * 8u + (i >= brk ? 8u : 0u));
-    // stream words: A(P) = x|y<<16 ; B(P,Pn) = z | Pn.x << 16 ; C(P) = y | z << 16   (two points = three words)
-    uint4 v0, v1, v2;
-    v0.x = p[0].x;                                    v0.y = __byte_perm(p[0].y, p[1].x, 0x5410);
-    v0.z = __byte_perm(p[1].x, p[1].y, 0x5432);      v0.w = p[2].x;
-    v1.x = __byte_perm(p[2].y, p[3].x, 0x5410);      v1.y = __byte_perm(p[3].x, p[3].y, 0x5432);
-    v1.z = p[4].x;                                    v1.w = __byte_perm(p[4].y, p[5].x, 0x5410);
-    v2.x = __byte_perm(p[5].x, p[5].y, 0x5432);      v2.y = p[6].x;
-    v2.z = __byte_perm(p[6].y, p[7].x, 0x5410);      v2.w = __byte_perm(p[7].x, p[7].y, 0x5432);
-    uint4* dst = reinterpret_cast<uint4*>(gpos + (uint64_t)(run_base + k0) * 3);
-    stg_cs_v4(dst, v0); stg_cs_v4(dst + 1, v1); stg_cs_v4(dst + 2, v2);
-  }
-  const uint32_t n16 = 3u * (head + (total - tail0));           // u16 elements outside full groups (<= 42)
-  for (uint32_t i = lane; i < n16; i += 32) {
-    const uint32_t pt = i / 3u, c = i - pt * 3u;
-    const uint32_t k = pt < head ? pt : tail0 + (pt - head);
-    gpos[(uint64_t)(run_base + k) * 3 + c] = *reinterpret_cast<const uint16_t*>(s_pos + spos_off(k) + c * 2u);
-  }
-}
-__device__ __forceinline__ void copy_out_rgb(uint8_t* __restrict__ grgb /* frame slab */, uint32_t run_base, uint32_t total,
-                                             const uint8_t* s_rgb, uint32_t lane) {
-  const uint32_t head = min(total, (0u - run_base) & 15u);
-  const uint32_t groups = (total - head) >> 4;
-  const uint32_t tail0 = head + (groups << 4);
-  for (uint32_t g = lane; g < groups; g += 32) {
-    const uint32_t k0 = head + (g << 4);
-    const uint32_t base = srgb_off(k0);
-    const uint32_t brk = 16u - (k0 & 15u);
-    uint32_t p[16];
-#pragma unroll
-    for (uint32_t i = 0; i < 16; ++i)
-      p[i] = *reinterpret_cast<const uint32_t*>(s_rgb + base + i * 4u + (i >= brk ? 4u : 0u));
-    // four points (r,g,b,0 each) = three stream words
-    uint32_t w[12];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      w[3 * q + 0] = __byte_perm(p[4 * q + 0], p[4 * q + 1], 0x4210);
-      w[3 * q + 1] = __byte_perm(p[4 * q + 1], p[4 * q + 2], 0x5421);
-      w[3 * q + 2] = __byte_perm(p[4 * q + 2], p[4 * q + 3], 0x6542);
-    }
-    uint4* dst = reinterpret_cast<uint4*>(grgb + (uint64_t)(run_base + k0) * 3);
-    stg_cs_v4(dst, make_uint4(w[0], w[1], w[2], w[3]));
-    stg_cs_v4(dst + 1, make_uint4(w[4], w[5], w[6], w[7]));
-    stg_cs_v4(dst + 2, make_uint4(w[8], w[9], w[10], w[11]));
-  }
-  const uint32_t n8 = 3u * (head + (total - tail0));            // bytes outside full groups (<= 90)
-  for (uint32_t i = lane; i < n8; i += 32) {
-    const uint32_t pt = i / 3u, c = i - pt * 3u;
-    const uint32_t k = pt < head ? pt : tail0 + (pt - head);
-    grgb[(uint64_t)(run_base + k) * 3 + c] = s_rgb[srgb_off(k) + c];
-  }
-}
-
-// one row of the 20x20 occupancy bitmap (block + 2-pixel margin, patch-local axes): bit cc = pixel (cc-2, rr) of the block
-// is occupied, or lies outside the image (the 5x5 test ignores those).  Walks the row one occupancy cell at a time.
+// one row of the 20x20 occupancy bitmap (block + 2-pixel margin): bit cc = pixel (x0 + sx*cc, y0 + sy*cc) is occupied, or
+// lies outside the image (the 5x5 test ignores those).  Walks the row one occupancy cell at a time.  Any precision.
 __device__ __forceinline__ uint32_t bitmap_row(const UnpackArgs& a, const uint8_t* occ_f, int32_t x0, int32_t y0, int32_t sx,
                                                int32_t sy) {
   // pixel cc of the row is (x0 + sx*cc, y0 + sy*cc); exactly one of sx, sy is non-zero
@@ -788,267 +716,327 @@ __device__ __forceinline__ uint32_t bitmap_row(const UnpackArgs& a, const uint8_
                         : (m0 - 19 < 0 ? (0xFFFFFu << max(m0 + 1, 0)) & 0xFFFFFu : 0u));
 }
 
+// K5 for a block-aligned slot, canvas axes: boundary classes of the lane's 8 pixels (bit j of bt1 / bt2 = type 1 / type 2;
+// meaningful where the pixel is occupied).  s_bmp: 32 words of warp-private shared memory.
+__device__ __forceinline__ void boundary_masks(const UnpackArgs& a, const WorkRec& R, uint32_t lane, uint32_t* s_bmp,
+                                               uint32_t& bt1, uint32_t& bt2) {
+  const int32_t W = (int32_t)a.W, H = (int32_t)a.H;
+  const uint8_t* occ_f = a.in.occ + (uint64_t)R.frame * a.in.occ_frame_stride;
+  const int32_t h = (int32_t)(lane & 1u), r = (int32_t)(lane >> 1);
+  const int32_t bx16 = (int32_t)R.bx * 16, by16 = (int32_t)R.by * 16;
+  if (a.prec_shift == 2 && ((a.W | a.H) & 3u) == 0) {
+    // precision 4: the 20x20 window is a 6x6 patch of occupancy samples (cells bx*4-1 .. bx*4+4); lane i < 30 fetches
+    // cell (row i / 6, column i % 6), lanes 0..5 then fetch row 5; cells outside the image count as occupied
+    const int32_t cw = W >> 2, ch = H >> 2, cxb = (int32_t)R.bx * 4 - 1, cyb = (int32_t)R.by * 4 - 1;
+    auto cell = [&](int32_t row, int32_t col) -> bool {
+      const int32_t cx = cxb + col, cy = cyb + row;
+      if (cx < 0 || cy < 0 || cx >= cw || cy >= ch) return true;
+      return occ_f[(uint64_t)cy * a.in.occ_pitch + cx] != 0;
+    };
+    const int32_t i = (int32_t)lane;
+    const uint32_t b0 = __ballot_sync(kFull, i < 30 ? cell(i / 6, i % 6) : false);
+    const uint32_t b1 = __ballot_sync(kFull, i < 6 ? cell(5, i) : false);
+    // lane = bitmap row rr (pixel row rr - 2): its cell row is (rr + 2) / 4
+    const uint32_t crow = (lane + 2u) >> 2;
+    const uint32_t m6 = crow < 5u ? (b0 >> (6u * crow)) & 63u : (b1 & 63u);
+    const uint32_t row20 = ((m6 & 1u) ? 0x3u : 0u) | ((m6 & 2u) ? 0x3Cu : 0u) | ((m6 & 4u) ? 0x3C0u : 0u) |
+                           ((m6 & 8u) ? 0x3C00u : 0u) | ((m6 & 16u) ? 0x3C000u : 0u) | ((m6 & 32u) ? 0xC0000u : 0u);
+    if (lane < 20) s_bmp[lane] = row20;
+  } else if (lane < 20) {
+    s_bmp[lane] = bitmap_row(a, occ_f, bx16 - 2, by16 + (int32_t)lane - 2, 1, 0);
+  }
+  __syncwarp();
+  const uint32_t r0 = s_bmp[r], r1 = s_bmp[r + 1], r2 = s_bmp[r + 2], r3 = s_bmp[r + 3], r4 = s_bmp[r + 4];
+  const uint32_t cross = r1 & r3 & (r2 >> 1) & (r2 << 1);    // bit c: the four neighbours of column c are occupied
+  const uint32_t all5 = r0 & r1 & r2 & r3 & r4;
+  const uint32_t full = all5 & (all5 >> 1) & (all5 >> 2) & (all5 << 1) & (all5 << 2);
+  const uint32_t sh = 8u * (uint32_t)h + 2u;
+  uint32_t border = 0;
+  if (R.bx == 0 || R.by == 0 || bx16 + 16 >= W || by16 + 16 >= H) {
+    const int32_t y = by16 + r;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      const int32_t x = bx16 + 8 * h + j;
+      if (x == 0 || y == 0 || x == W - 1 || y == H - 1) border |= 1u << j;
+    }
+  }
+  bt1 = ((~(cross >> sh)) & 0xFFu) | border;
+  bt2 = (~(full >> sh)) & 0xFFu & ~bt1;
+}
+
+__device__ __forceinline__ void stg_u32(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
+
 // ---- pass 3: emit ------------------------------------------------------------------------------------------------------------
-// Per warp (slot): (1) load the block in the lane layout, (2) spill it into per-pixel tables in shared memory and build
-// the list "output point k <- (pixel rank, map)", (3) POINT-parallel loop: lane = output point, dense, rolled (small code):
-// position, colour, and in the smoothing instantiation boundary class, cell statistics and the boundary list, staged in
-// chunks of <= 256 points, (4) aligned copy-out of each chunk.
+// Per warp (slot): (1) load the block in canvas layout, (2) spill it into per-pixel tables in shared memory in patch raster
+// order and build the list "output point k <- (pixel rank, map)", (3) POINT-parallel loop over 32-aligned windows of the
+// frame's point index (lane == point index mod 32): position, colour, and in the smoothing instantiation boundary
+// class, cell statistics and the boundary list.  Results go straight to global memory as aligned 32-bit words assembled
+// from neighbouring lanes (two positions = three words, four colours = three words); only the ragged ends of a run
+// use 16-bit / 8-bit stores.
 template <bool kSmooth, bool kDebug>
-__global__ void __launch_bounds__(kWarpsPerTile * 32, 3) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
+__global__ void __launch_bounds__(kWarpsPerTile * 32, 4) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-  const uint32_t tile = blockIdx.x + tile_offset;
-  const uint32_t frame = a.tile_frame[tile];
-  const uint32_t first_tile = a.frame_tile_begin[frame];
-  const uint32_t pos_in_frame = (tile - first_tile) * kWarpsPerTile + warp;   // index into the frame's owned-slot list
-  const uint32_t lpos = tile * kWarpsPerTile + warp;                          // global position (per-slot arrays, logs)
-  uint32_t total = 0;
-  const bool active = pos_in_frame < a.owned_count[frame];
-  if (active) total = a.slot_total[lpos];
-  uint32_t n_log_geo = 0, n_log_col = 0;
-  if (total != 0) {
-    const uint32_t run_base = a.slot_base[lpos];
-    const SlotRec R = load_slot_rec(a.slot_rec + a.owned[lpos]);
-    const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
-    uint32_t* log_geo = nullptr; uint32_t* log_col = nullptr;
-    if (kSmooth) {
-      const uint64_t ls = (uint64_t)(lpos - a.sm.group_first_slot) * a.sm.log_stride;
-      if (a.sm.geo.on) log_geo = a.sm.geo.log + ls;
-      if (a.sm.col.on) log_col = a.sm.col.log + ls;
+  const uint32_t lpos = (blockIdx.x + tile_offset) * kWarpsPerTile + warp;
+  const WorkRec R = load_work(a.work + lpos);
+  const uint32_t total = R.pid == kNoPatch ? 0u : R.total;
+  if (total == 0) return;
+  const uint32_t run_base = R.base, frame = R.frame;
+  if ((uint64_t)run_base + total > a.out.cap) {                   // cannot happen for footprints inside the canvas
+    if (lane == 0) atomicExch(a.err, 7);
+    return;
+  }
+  const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
+  if (!slot_is_fast(a, R)) {
+    generic_slot_emit<kSmooth, kDebug>(a, R.pid, frame, fig, R.u0b, R.v0b, (uint64_t)frame * a.out.cap + run_base);
+    return;
+  }
+  uint8_t* wsm = smem + (size_t)warp * kWarpSmemBytes;
+  uint32_t* s_pt = reinterpret_cast<uint32_t*>(wsm + kOffPt);
+  uint4* s_term = reinterpret_cast<uint4*>(wsm + kOffTerm);
+  uint16_t* s_src = reinterpret_cast<uint16_t*>(wsm + kOffSrc);
+  uint8_t* s_cnt = wsm + kOffCnt;
+  uint32_t* s_bmp = reinterpret_cast<uint32_t*>(wsm + kOffBmp);
+
+  const bool has_attr = a.has_attr != 0;
+  const bool want_bt = kSmooth || (kDebug && a.out.btype != nullptr);
+  const uint32_t h = lane & 1u, r = lane >> 1;
+  const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
+  DevPatch P;
+  load_patch_fields(a.patches + R.pid, P);
+  uint32_t n_boundary = 0;
+
+  {
+    // ---- (1): canvas layout ----------------------------------------------------------------------------------------
+    const uint32_t x0 = (uint32_t)R.bx * 16u + 8u * h, y = (uint32_t)R.by * 16u + r;
+    uint4 ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
+    uint2 ua = {0, 0}, va = {0, 0}, ub = {0, 0}, vb = {0, 0};
+    if (has_attr) {                                                                  // decoder.rs:976-977
+      const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride;
+      const uint32_t yoff = y * a.in.attr_pitch_y + x0;
+      ya = ldg_nc_v4(ay0 + yoff); yb = ldg_nc_v4(ay0 + a.in.attr_y_map_stride + yoff);
+      const uint64_t cf = (uint64_t)frame * 2 * a.in.attr_c_map_stride;
+      const uint32_t coff = (y >> 1) * a.in.attr_pitch_c + (x0 >> 1);
+      const uint16_t* au0 = a.in.attr_u + cf + coff; const uint16_t* av0 = a.in.attr_v + cf + coff;
+      // the two rows of a chroma row pair ask for the same addresses in the same instruction: one fetch
+      ua = ldg_nc_v2(au0); va = ldg_nc_v2(av0);
+      ub = ldg_nc_v2(au0 + a.in.attr_c_map_stride); vb = ldg_nc_v2(av0 + a.in.attr_c_map_stride);
     }
-    uint8_t* wsm = smem + (size_t)warp * kWarpSmemBytes;
-    uint32_t* s_nn = reinterpret_cast<uint32_t*>(wsm + kOffNn);
-    uint32_t* s_yy = reinterpret_cast<uint32_t*>(wsm + kOffYy);
-    uint4* s_term = reinterpret_cast<uint4*>(wsm + kOffTerm);
-    uint16_t* s_src = reinterpret_cast<uint16_t*>(wsm + kOffSrc);
-    uint32_t* s_bt = reinterpret_cast<uint32_t*>(wsm + kOffBt);
-    uint32_t* s_bmp = reinterpret_cast<uint32_t*>(wsm + kOffBmp);
-    uint8_t* s_pos = wsm + kOffPos;
-    uint8_t* s_rgb = wsm + kOffRgb;
-    DevPatch P;
+    CanvasBlock L;
+    load_geometry(a, R, P, lane, L);
+    uint32_t bt1 = 0, bt2 = 0;
+    if (want_bt) boundary_masks(a, R, lane, s_bmp, bt1, bt2);
+    if (kSmooth) {
+      const uint32_t b1 = L.m1 & bt1;
+      n_boundary = __reduce_add_sync(kFull, __popc(b1) + __popc(b1 & L.m2));
+    }
 
-    if ((uint64_t)run_base + total > a.out.cap) {                   // cannot happen for footprints inside the canvas
-      if (lane == 0) atomicExch(a.err, 7);
-    } else if (!slot_is_fast(a, R)) {
-      P = a.patches[R.pid];
-      if (lane == 0) { s_bmp[0] = 0; s_bmp[1] = 0; }
-      __syncwarp();
-      generic_slot_emit<kSmooth, kDebug>(a, P, frame, fig, R.u0b, R.v0b, (uint64_t)frame * a.out.cap + run_base, log_geo,
-                                         log_col, s_bmp);
-      __syncwarp();
-      n_log_geo = reinterpret_cast<volatile uint32_t*>(s_bmp)[0];
-      n_log_col = reinterpret_cast<volatile uint32_t*>(s_bmp)[1];
-    } else {
-      const int32_t h = (int32_t)(lane & 1u), r = (int32_t)(lane >> 1);
-      const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
-      const bool w_rgb = a.out.rgb != nullptr;
-      const bool want_bt = kSmooth || (kDebug && a.out.btype != nullptr);
-      int32_t cx0, cy0;                                              // canvas pixel of patch-local (0,0) of the block
-      {
-        // ---- (1) + (2): lane layout -> tables ----------------------------------------------------------------------
-        LaneBlock L;
-        load_lane_block<true>(a, R, frame, lane, P, L);
-        cx0 = L.xs - ax * 8 * h - rx * r; cy0 = L.ys - ay * 8 * h - ry * r;
-        *reinterpret_cast<uint4*>(s_nn + 8 * lane) = make_uint4(L.nn[0], L.nn[1], L.nn[2], L.nn[3]);
-        *reinterpret_cast<uint4*>(s_nn + 8 * lane + 4) = make_uint4(L.nn[4], L.nn[5], L.nn[6], L.nn[7]);
-        if (a.has_attr) {
-          *reinterpret_cast<uint4*>(s_yy + 8 * lane) = make_uint4(L.yy[0], L.yy[1], L.yy[2], L.yy[3]);
-          *reinterpret_cast<uint4*>(s_yy + 8 * lane + 4) = make_uint4(L.yy[4], L.yy[5], L.yy[6], L.yy[7]);
-          // chroma terms, once per (chroma sample, map): the two lanes of a row pair read the same 4 samples; the even
-          // row evaluates map 0, the odd row map 1.  Entry = {ir, ig, ib << 1 | flagged, U | V << 16}.
-          const bool odd = (lane & 2u) != 0;
-          const uint32_t e0 = (((uint32_t)r >> 1) * 8u + 4u * (uint32_t)h) * 2u + (odd ? 1u : 0u);
+    // ---- (2): tables in patch raster order -----------------------------------------------------------------------------
+    // canvas-local (lx, ly) = (8h + j, r) -> patch-local (u1, v1) through the inverse of the affine map (decoder.rs:853-867)
+    uint32_t rank0; int32_t dr;
+    if (ax != 0) {                          // u runs along canvas x, v along canvas y
+      const uint32_t u1 = ax > 0 ? 8u * h : 15u - 8u * h, v1 = ry > 0 ? r : 15u - r;
+      rank0 = v1 * 16u + u1; dr = ax;
+    } else {                                // transposed: u runs along canvas y, v along canvas x
+      const uint32_t u1 = ay > 0 ? r : 15u - r, v1 = rx > 0 ? 8u * h : 15u - 8u * h;
+      rank0 = v1 * 16u + u1; dr = 16 * rx;
+    }
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const uint32_t uv = odd ? L.cB[cc] : L.cA[cc];                            // decoder.rs:976-977
-            const ChromaTerm t = chroma_term(uv & 0xFFFFu, uv >> 16);
-            s_term[e0 + 2 * cc] = make_uint4((uint32_t)t.ir, (uint32_t)t.ig, ((uint32_t)t.ib << 1) | t.flagged, uv);
-          }
-        }
-        // output point k of the slot <- (pixel rank, map); this lane's points are consecutive
-        const uint32_t c = __popc(L.m1) + __popc(L.m2);
-        uint32_t incl = c;
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t rank = rank0 + (uint32_t)(j * dr);
+      const uint32_t yy = __byte_perm(word_of(ya, j >> 1), word_of(yb, j >> 1), (j & 1) ? 0x7632u : 0x5410u);   // Y0 | Y1 << 16
+      // entry of (pixel, map) = n | Y << 16
+      *reinterpret_cast<uint2*>(s_pt + 2u * rank) = make_uint2(__byte_perm(L.nn[j], yy, 0x5410), __byte_perm(L.nn[j], yy, 0x7632));
+      const uint32_t c = ((L.m1 >> j) & 1u) + ((L.m2 >> j) & 1u);
+      const uint32_t bt = ((bt1 >> j) & 1u) ? 1u : ((bt2 >> j) & 1u) ? 2u : 0u;
+      s_cnt[rank] = (uint8_t)(c | (bt << 2));
+    }
+    if (has_attr) {
+      // chroma terms, once per (chroma sample, map): the two lanes of a row pair hold the same 4 samples; the even row
+      // evaluates map 0, the odd row map 1.  Entry = {ir, ig, ib << 1 | flagged, U | V << 16}, indexed by the patch-local
+      // chroma position (cv * 8 + cu) * 2 + map.
+      const bool odd = (r & 1u) != 0;
+      const uint32_t ccy = r >> 1;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t t = __shfl_up_sync(kFull, incl, d);
-          if (lane >= (uint32_t)d) incl += t;
-        }
-        uint32_t k = incl - c;
-        const uint32_t m1 = L.m1, m2 = L.m2;
-#pragma unroll 1
-        for (uint32_t j = 0; j < 8; ++j) {
-          if ((m1 >> j) & 1u) {
-            const uint32_t e = (8u * lane + j) << 1;
-            s_src[k++] = (uint16_t)e;
-            if ((m2 >> j) & 1u) s_src[k++] = (uint16_t)(e | 1u);
-          }
-        }
-        // ---- K5: boundary classes from a 20x20 occupancy bitmap of the block and its 2-pixel margin ---------------
-        if (want_bt) {
-          const int32_t W = (int32_t)a.W, H = (int32_t)a.H;
-          const uint8_t* occ_f = a.in.occ + (uint64_t)frame * a.in.occ_frame_stride;
-          if (lane < 20) {
-            const int32_t rr = (int32_t)lane - 2;
-            s_bmp[lane] = bitmap_row(a, occ_f, cx0 - 2 * ax + rx * rr, cy0 - 2 * ay + ry * rr, ax, ay);
-          }
-          __syncwarp();
-          const uint32_t r0 = s_bmp[r], r1 = s_bmp[r + 1], r2 = s_bmp[r + 2], r3 = s_bmp[r + 3], r4 = s_bmp[r + 4];
-          const uint32_t cross = r1 & r3 & (r2 >> 1) & (r2 << 1);    // bit c: the four neighbours of column c are occupied
-          const uint32_t all5 = r0 & r1 & r2 & r3 & r4;
-          const uint32_t full = all5 & (all5 >> 1) & (all5 >> 2) & (all5 << 1) & (all5 << 2);
-          const uint32_t sh = 8u * (uint32_t)h + 2u;
-          uint32_t border = 0;
-          if (R.bx == 0 || R.by == 0 || ((int32_t)R.bx + 1) * 16 >= W || ((int32_t)R.by + 1) * 16 >= H) {
-#pragma unroll 1
-            for (int j = 0; j < 8; ++j) {
-              const int32_t x = L.xs + ax * j, y = L.ys + ay * j;
-              if (x == 0 || y == 0 || x == W - 1 || y == H - 1) border |= 1u << j;
-            }
-          }
-          const uint32_t bt1 = ((~(cross >> sh)) & 0xFFu) | border;
-          const uint32_t bt2 = (~(full >> sh)) & 0xFFu & ~bt1;
-          s_bt[lane] = bt1 | (bt2 << 8);     // bit j: pixel j is type 1 ; bit 8+j: type 2 (meaningful where occupied)
-        }
-      }
-      __syncwarp();
-
-      // ---- (3): point-parallel ------------------------------------------------------------------------------------------
-      // generate_point (decoder.rs:871-878) stores normal, tangent, bitangent in that order; the selectors reproduce
-      // "later stores overwrite earlier ones" and leave unset coordinates at 0
-      const uint32_t s0 = sel_of_src(axis_source(P, 0)), s1 = sel_of_src(axis_source(P, 1)), s2 = sel_of_src(axis_source(P, 2));
-      const uint32_t selA = s0 | (s1 << 8), selB = s2 | 0x7600u;
-      const uint32_t T00 = (uint32_t)R.u0b * 16u * P.lod_x + P.u1, B00 = (uint32_t)R.v0b * 16u * P.lod_y + P.v1;   // decoder.rs:875-876
-      const uint32_t lodx = P.lod_x, lody = P.lod_y, patch = P.local_index;
-      uint16_t* gpos = a.out.pos + (uint64_t)frame * a.out.cap * 3;
-      uint8_t* grgb = w_rgb ? a.out.rgb + (uint64_t)frame * a.out.cap * 3 : nullptr;
-      const uint64_t gidx = (uint64_t)frame * a.out.cap + run_base;
-
-      for (uint32_t c0 = 0; c0 < total;) {
-        // a chunk ends on a point whose index in the frame is a multiple of 16 (so the next one starts group-aligned)
-        uint32_t c1 = c0 + kChunkPoints - ((run_base + c0 + kChunkPoints) & 15u);
-        if (c1 > total) c1 = total;
-#pragma unroll 1
-        for (uint32_t kb = c0; kb < c1; kb += 32) {
-          const uint32_t k = kb + lane;
-          const bool valid = k < c1;
-          uint32_t w0 = 0, w1 = 0, Y = 0, uv = 0, rank = 0, map = 0;
-          if (valid) {
-            const uint32_t src = s_src[k];
-            rank = src >> 1; map = src & 1u;
-            const uint32_t n = (s_nn[rank] >> (16u * map)) & 0xFFFFu;
-            const uint32_t u1 = rank & 15u, v1 = rank >> 4;
-            const uint32_t t = (T00 + u1 * lodx) & 0xFFFFu, b = (B00 + v1 * lody) & 0xFFFFu;
-            const uint32_t A = n | (t << 16);
-            w0 = __byte_perm(A, b, selA); w1 = __byte_perm(A, b, selB);
-            *reinterpret_cast<uint2*>(s_pos + spos_off(k - c0)) = make_uint2(w0, w1);
-            if (a.has_attr) {
-              Y = (s_yy[rank] >> (16u * map)) & 0xFFFFu;                                     // codec.rs:637-640
-              const uint4 te = s_term[(((v1 >> 1) * 8u + (u1 >> 1)) << 1) | map];
-              uv = te.w;
-              if (w_rgb) {
-                ChromaTerm ct;
-                ct.ir = (int32_t)te.x; ct.ig = (int32_t)te.y; ct.ib = (int32_t)te.z >> 1; ct.flagged = te.z & 1u;
-                *reinterpret_cast<uint32_t*>(s_rgb + srgb_off(k - c0)) = yuv_to_rgb_term(Y, uv & 0xFFFFu, uv >> 16, ct);
-              }
-            }
-          }
-          uint32_t bt = 0;
-          if (kSmooth || kDebug) {
-            if (valid && want_bt) {
-              const uint32_t bw = s_bt[rank >> 3], j = rank & 7u;
-              bt = ((bw >> j) & 1u) ? 1u : ((bw >> (8u + j)) & 1u) ? 2u : 0u;
-            }
-          }
-          if (kDebug && valid) {                                       // streams only the stage API / tests ask for
-            const uint64_t gk = gidx + k;
-            if (a.out.yuv && a.has_attr) {
-              uint16_t* q = a.out.yuv + gk * 3;
-              q[0] = (uint16_t)Y; q[1] = (uint16_t)(uv & 0xFFFFu); q[2] = (uint16_t)(uv >> 16);
-            }
-            if (a.out.part) a.out.part[gk] = (uint16_t)patch;                          // codec.rs:452
-            if (a.out.pix) {                                                            // codec.rs:463-472
-              const int32_t u1 = (int32_t)(rank & 15u), v1 = (int32_t)(rank >> 4);
-              a.out.pix[gk] = (uint32_t)(cx0 + ax * u1 + rx * v1) | ((uint32_t)(cy0 + ay * u1 + ry * v1) << 15) | (map << 30);
-            }
-            if (a.out.btype) a.out.btype[gk] = (uint8_t)bt;
-          }
-          if (kSmooth) {
-            const uint32_t X = w0 & 0xFFFFu, Yc = w0 >> 16, Z = w1 & 0xFFFFu;
-            // K6 statistics: geometry cells over ALL points.  32 consecutive points hold a few runs of equal cell key
-            // (a row of the block crosses a cell every g pixels): segmented scan, the last lane of a run flushes it.
-            if (a.sm.geo.on) {
-              const GridDesc& G = a.sm.geo;
-              const uint32_t key = valid ? cell_key_of(G, X, Yc, Z) : kCellEmpty;
-              uint32_t v0 = 0, v1 = 0;
-              if (key != kCellEmpty) {
-                const uint32_t g = G.g;
-                v0 = 1u | ((X - (key & 1023u) * g) << 16);                              // count | sum rel x
-                v1 = (Yc - ((key >> 10) & 1023u) * g) | ((Z - (key >> 20) * g) << 16);  // sum rel y | sum rel z
-              }
-              const uint32_t kprev = __shfl_up_sync(kFull, key, 1), knext = __shfl_down_sync(kFull, key, 1);
-              uint32_t fl = (lane == 0 || kprev != key) ? 1u : 0u;
-#pragma unroll
-              for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o0 = __shfl_up_sync(kFull, v0, d), o1 = __shfl_up_sync(kFull, v1, d);
-                const uint32_t of = __shfl_up_sync(kFull, fl, d);
-                if (lane >= (uint32_t)d && !fl) { v0 += o0; v1 += o1; fl = of; }
-              }
-              const bool tail = key != kCellEmpty && (lane == 31 || knext != key);
-              uint32_t cs = kCellEmpty;
-              if (tail) {
-                cs = cell_slot(G, fig, key, a.err);
-                if (cs != kCellEmpty) geo_cell_add(G, fig, cs, patch, v0 & 0xFFFFu, v0 >> 16, v1 & 0xFFFFu, v1 >> 16);
-              }
-              const uint32_t fm = __ballot_sync(kFull, cs != kCellEmpty);
-              if (cs != kCellEmpty) log_geo[n_log_geo + __popc(fm & ((1u << lane) - 1u))] = cs;
-              n_log_geo += __popc(fm);
-            }
-            // K7 statistics: colour cells over the type-2 (second ring) points
-            if (a.sm.col.on && a.has_attr && __any_sync(kFull, bt == 2u)) {
-              const GridDesc& G = a.sm.col;
-              uint32_t cs = kCellEmpty;
-              if (bt == 2u) {
-                const uint32_t key = cell_key_of(G, X, Yc, Z);
-                if (key != kCellEmpty) {
-                  cs = cell_slot(G, fig, key, a.err);
-                  if (cs != kCellEmpty) col_cell_add(G, fig, cs, patch, 1, Y, uv & 0xFFFFu, uv >> 16, (unsigned long long)Y * Y);
-                }
-              }
-              const uint32_t fm = __ballot_sync(kFull, cs != kCellEmpty);
-              if (cs != kCellEmpty) log_col[n_log_col + __popc(fm & ((1u << lane) - 1u))] = cs;
-              n_log_col += __popc(fm);
-            }
-            // compact list of the type-1 boundary points (order inside the list is irrelevant)
-            const uint32_t bm = __ballot_sync(kFull, bt == 1u);
-            if (bm) {
-              uint32_t lbase = 0;
-              if (lane == 0) lbase = atomicAdd(&a.sm.blist_count[frame], (uint32_t)__popc(bm));
-              lbase = __shfl_sync(kFull, lbase, 0);
-              if ((uint64_t)lbase + __popc(bm) > a.sm.blist_cap) {
-                if (lane == 0) atomicExch(a.err, 7);
-              } else if (bt == 1u) {
-                uint4 e;
-                e.x = run_base + k;
-                e.y = w0;                                  // pos[0] | pos[1] << 16
-                e.z = (w1 & 0xFFFFu) | (Y << 16);          // pos[2] | Y << 16
-                e.w = uv;                                  // U | V << 16
-                reinterpret_cast<uint4*>(a.sm.blist + (uint64_t)frame * a.sm.blist_cap)[lbase + __popc(bm & ((1u << lane) - 1u))] = e;
-              }
-            }
-          }
-        }
-        __syncwarp();
-        // ---- (4): copy-out of the chunk ----------------------------------------------------------------------------------
-        copy_out_pos(gpos, run_base + c0, c1 - c0, s_pos, lane);
-        if (w_rgb) copy_out_rgb(grgb, run_base + c0, c1 - c0, s_rgb, lane);
-        __syncwarp();
-        c0 = c1;
+      for (int cc = 0; cc < 4; ++cc) {
+        const uint32_t sel = (cc & 1) ? 0x7632u : 0x5410u;
+        const uint32_t uv = odd ? __byte_perm(word_of(ub, cc >> 1), word_of(vb, cc >> 1), sel)
+                                : __byte_perm(word_of(ua, cc >> 1), word_of(va, cc >> 1), sel);
+        const uint32_t ccx = 4u * h + (uint32_t)cc;
+        uint32_t cu, cv;
+        if (ax != 0) { cu = ax > 0 ? ccx : 7u - ccx; cv = ry > 0 ? ccy : 7u - ccy; }
+        else { cu = ay > 0 ? ccy : 7u - ccy; cv = rx > 0 ? ccx : 7u - ccx; }
+        const ChromaTerm t = chroma_term(uv & 0xFFFFu, uv >> 16);
+        s_term[((cv * 8u + cu) << 1) | (odd ? 1u : 0u)] = make_uint4((uint32_t)t.ir, (uint32_t)t.ig, ((uint32_t)t.ib << 1) | t.flagged, uv);
       }
     }
   }
-  if (kSmooth && lane == 0) {                                      // every position of the group reports its log sizes
-    if (a.sm.geo.on) a.sm.geo.log_count[lpos - a.sm.group_first_slot] = n_log_geo;
-    if (a.sm.col.on) a.sm.col.log_count[lpos - a.sm.group_first_slot] = n_log_col;
+  __syncwarp();
+
+  // ---- (2b): patch raster order: lane l owns ranks 8l .. 8l+7; where its points go inside the run --------------------------
+  {
+    const uint2 cb = *reinterpret_cast<const uint2*>(s_cnt + 8u * lane);
+    const uint32_t c_lo = cb.x & 0x03030303u, c_hi = cb.y & 0x03030303u;
+    const uint32_t p_lo = c_lo * 0x01010101u;                       // byte i: points of pixels 0..i (inclusive), <= 8
+    const uint32_t p_hi = c_hi * 0x01010101u + (p_lo >> 24) * 0x01010101u;
+    const uint32_t c = p_hi >> 24;                                  // points of this lane
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    const uint32_t lane_excl = incl - c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t cj = ((j < 4 ? c_lo : c_hi) >> (8 * (j & 3))) & 3u;
+      const uint32_t ij = ((j < 4 ? p_lo : p_hi) >> (8 * (j & 3))) & 0xFFu;
+      const uint32_t k = lane_excl + ij - cj;
+      const uint32_t e = (8u * lane + (uint32_t)j) << 1;
+      if (cj >= 1u) s_src[k] = (uint16_t)e;
+      if (cj == 2u) s_src[k + 1] = (uint16_t)(e | 1u);
+    }
+  }
+  __syncwarp();
+
+  // ---- (3): point-parallel ------------------------------------------------------------------------------------------
+  // generate_point (decoder.rs:871-878) stores normal, tangent, bitangent in that order; the selectors reproduce
+  // "later stores overwrite earlier ones" and leave unset coordinates at 0
+  const uint32_t s0 = sel_of_src(axis_source(P, 0)), s1 = sel_of_src(axis_source(P, 1)), s2 = sel_of_src(axis_source(P, 2));
+  const uint32_t selA = s0 | (s1 << 8), selB = s2 | 0x7600u;
+  const uint32_t T00 = (uint32_t)R.u0b * 16u * P.lod_x + P.u1, B00 = (uint32_t)R.v0b * 16u * P.lod_y + P.v1;   // decoder.rs:875-876
+  const uint32_t lodx = P.lod_x, lody = P.lod_y, patch = P.local_index;
+  uint16_t* gpos = a.out.pos + (uint64_t)frame * a.out.cap * 3;
+  uint8_t* grgb = has_attr ? a.out.rgb + (uint64_t)frame * a.out.cap * 3 : nullptr;
+  const uint64_t gframe = (uint64_t)frame * a.out.cap;
+  const uint32_t q = lane & 3u;
+  const uint32_t sel_rgb = q == 0 ? 0x4210u : q == 1 ? 0x5421u : 0x6542u;
+  const bool odd_lane = (lane & 1u) != 0;
+
+  uint32_t lbase = 0, n_done = 0;
+  if (kSmooth && n_boundary) {                                     // room in the frame's boundary list for this slot
+    if (lane == 0) lbase = atomicAdd(&a.sm.blist_count[frame], n_boundary);
+    lbase = __shfl_sync(kFull, lbase, 0);
+    if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
+      if (lane == 0) atomicExch(a.err, 7);
+      return;
+    }
+  }
+
+  const uint32_t run_end = run_base + total;
+#pragma unroll 1
+  for (uint32_t g0 = run_base & ~31u; g0 < run_end; g0 += 32) {
+    const uint32_t g = g0 + lane;                                  // point index inside the frame; g % 32 == lane
+    const uint32_t k = g - run_base;                               // point index inside the run (wraps for g < run_base)
+    const bool valid = k < total;
+    const uint32_t e = valid ? (uint32_t)s_src[k] : 0u;            // rank << 1 | map
+    const uint32_t pt = s_pt[e];                                   // n | Y << 16
+    const uint32_t rank = e >> 1, map = e & 1u;
+    const uint32_t u1 = rank & 15u, v1 = rank >> 4;
+    const uint32_t t = T00 + u1 * lodx, b = (B00 + v1 * lody) & 0xFFFFu;
+    const uint32_t A = __byte_perm(pt, t, 0x5410);                 // n | t << 16
+    const uint32_t w0 = __byte_perm(A, b, selA), w1 = __byte_perm(A, b, selB);      // x | y << 16 ; z
+    {
+      // two points = three words: [x0 y0] [z0 x1] [y1 z1]; even lane writes the first two, odd lane the third
+      const uint32_t nw0 = __shfl_down_sync(kFull, w0, 1);
+      const bool nvalid = (k + 1u) < total, pvalid = (k - 1u) < total;
+      uint16_t* p = gpos + (uint64_t)g * 3;
+      if (valid) {
+        stg_u32(p + (odd_lane ? 1 : 0), odd_lane ? __byte_perm(w0, w1, 0x5432) : w0);
+        if (!odd_lane) {
+          if (nvalid) stg_u32(p + 2, __byte_perm(w1, nw0, 0x5410));
+          else p[2] = (uint16_t)w1;
+        } else if (!pvalid) {
+          p[0] = (uint16_t)w0;
+        }
+      }
+    }
+    uint32_t Y = 0, uv = 0;
+    if (has_attr) {
+      Y = pt >> 16;                                                                  // codec.rs:637-640
+      const uint4 te = s_term[((e >> 6) << 4) | (((e >> 2) & 7u) << 1) | map];
+      uv = te.w;
+      ChromaTerm ct;
+      ct.ir = (int32_t)te.x; ct.ig = (int32_t)te.y; ct.ib = (int32_t)te.z >> 1; ct.flagged = te.z & 1u;
+      const uint32_t c = yuv_to_rgb_term(Y, uv & 0xFFFFu, uv >> 16, ct);
+      // four colours = three words; lanes 4i .. 4i+2 of a complete quad write one word each
+      const uint32_t nc = __shfl_down_sync(kFull, c, 1);
+      const uint32_t quad = (__ballot_sync(kFull, valid) >> (lane & ~3u)) & 0xFu;
+      if (valid) {
+        uint8_t* p = grgb + (uint64_t)g * 3;
+        if (quad == 0xFu) {
+          if (q != 3u) stg_u32(p + q, __byte_perm(c, nc, sel_rgb));
+        } else {
+          p[0] = (uint8_t)c; p[1] = (uint8_t)(c >> 8); p[2] = (uint8_t)(c >> 16);
+        }
+      }
+    }
+    uint32_t bt = 0;
+    if (kSmooth || kDebug) {
+      if (valid && want_bt) bt = (uint32_t)s_cnt[rank] >> 2;
+    }
+    if (kDebug && valid) {                                       // streams only the stage API / tests ask for
+      const uint64_t gk = gframe + g;
+      if (a.out.yuv && has_attr) {
+        uint16_t* qy = a.out.yuv + gk * 3;
+        qy[0] = (uint16_t)Y; qy[1] = (uint16_t)(uv & 0xFFFFu); qy[2] = (uint16_t)(uv >> 16);
+      }
+      if (a.out.part) a.out.part[gk] = (uint16_t)patch;                          // codec.rs:452
+      if (a.out.pix) {                                                            // codec.rs:463-472
+        const int32_t cx0 = (int32_t)R.bx * 16 + ((ax < 0 || rx < 0) ? 15 : 0), cy0 = (int32_t)R.by * 16 + ((ay < 0 || ry < 0) ? 15 : 0);
+        a.out.pix[gk] = (uint32_t)(cx0 + ax * (int32_t)u1 + rx * (int32_t)v1) |
+                        ((uint32_t)(cy0 + ay * (int32_t)u1 + ry * (int32_t)v1) << 15) | (map << 30);
+      }
+      if (a.out.btype) a.out.btype[gk] = (uint8_t)bt;
+    }
+    if (kSmooth) {
+      const uint32_t X = w0 & 0xFFFFu, Yc = w0 >> 16, Z = w1 & 0xFFFFu;
+      // K6 statistics: geometry cells over ALL points.  The lanes of the window that fall into the same cell are found
+      // with match.any and summed with one masked reduction per packed word; the lowest lane of each group issues the
+      // reductions, and the first toucher of a cell logs it.
+      if (a.sm.geo.on) {
+        const GridDesc& G = a.sm.geo;
+        const uint32_t key = valid ? cell_key_of(G, X, Yc, Z) : kCellEmpty;
+        uint32_t v0 = 0, v1s = 0;
+        if (key != kCellEmpty) {
+          const uint32_t gg = G.g;
+          v0 = 1u | ((X - (key & 1023u) * gg) << 16);                               // count | sum rel x   (<= 32 * 255)
+          v1s = (Yc - ((key >> 10) & 1023u) * gg) | ((Z - (key >> 20) * gg) << 16);  // sum rel y | sum rel z
+        }
+        const uint32_t peers = __match_any_sync(kFull, key);
+        const uint32_t r0 = __reduce_add_sync(peers, v0), r1 = __reduce_add_sync(peers, v1s);
+        bool first = false; uint32_t cs = kCellEmpty;
+        if (key != kCellEmpty && lane == (uint32_t)(__ffs(peers) - 1)) {
+          cs = cell_slot(G, fig, key, a.err);
+          if (cs != kCellEmpty) first = geo_cell_add_first(G, fig, cs, patch, r0 & 0xFFFFu, r0 >> 16, r1 & 0xFFFFu, r1 >> 16);
+        }
+        log_append(a, G, fig, first, cs, lane);
+      }
+      // K7 statistics: colour cells over the type-2 (second ring) points
+      if (a.sm.col.on && has_attr && __any_sync(kFull, bt == 2u)) {
+        const GridDesc& G = a.sm.col;
+        bool first = false; uint32_t cs = kCellEmpty;
+        if (bt == 2u) {
+          const uint32_t key = cell_key_of(G, X, Yc, Z);
+          if (key != kCellEmpty) {
+            cs = cell_slot(G, fig, key, a.err);
+            if (cs != kCellEmpty) first = col_cell_add_first(G, fig, cs, patch, 1, Y, uv & 0xFFFFu, uv >> 16, (unsigned long long)Y * Y);
+          }
+        }
+        log_append(a, G, fig, first, cs, lane);
+      }
+      // compact list of the type-1 boundary points (order inside the list is irrelevant)
+      const uint32_t bm = __ballot_sync(kFull, bt == 1u);
+      if (bt == 1u) {
+        uint4 ent;
+        ent.x = g;
+        ent.y = w0;                                  // pos[0] | pos[1] << 16
+        ent.z = (w1 & 0xFFFFu) | (Y << 16);          // pos[2] | Y << 16
+        ent.w = uv;                                  // U | V << 16
+        reinterpret_cast<uint4*>(a.sm.blist + (uint64_t)frame * a.sm.blist_cap)[lbase + n_done + __popc(bm & ((1u << lane) - 1u))] = ent;
+      }
+      n_done += __popc(bm);
+    }
   }
 }
 
@@ -1074,17 +1062,13 @@ __device__ __forceinline__ uint32_t mean_q8_u32(uint32_t s, uint32_t cnt) {     
   return num < (1ull << 32) ? (uint32_t)num / cnt : (uint32_t)(num / cnt);
 }
 __global__ void __launch_bounds__(256) smooth_finalize_kernel(const __grid_constant__ UnpackArgs a) {
-  const uint32_t ls = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // slot inside the group
-  if (ls >= a.sm.group_slots) return;
-  const uint32_t lane = lane_id();
-  const uint32_t frame = a.tile_frame[(a.sm.group_first_slot + ls) / kWarpsPerTile];
-  const uint32_t fig = frame - a.sm.group_first_frame;
+  const uint32_t fig = blockIdx.y;
   if (a.sm.geo.on) {
     const GridDesc& G = a.sm.geo;
-    const uint32_t n = min(G.log_count[ls], a.sm.log_stride);
-    const uint32_t* log = G.log + (uint64_t)ls * a.sm.log_stride;
+    const uint32_t n = (uint32_t)min((uint64_t)G.log_count[fig], G.log_cap);
+    const uint32_t* log = G.log + (uint64_t)fig * G.log_cap;
     GeoCell* tab = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots;
-    for (uint32_t i = lane; i < n; i += 32) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       GeoCell* c = tab + log[i];
       const unsigned long long w0 = c->cnt_sx, w1 = c->sy_sz;
       const uint32_t cnt = (uint32_t)w0;
@@ -1096,14 +1080,14 @@ __global__ void __launch_bounds__(256) smooth_finalize_kernel(const __grid_const
   }
   if (a.sm.col.on) {
     const GridDesc& G = a.sm.col;
-    const uint32_t n = min(G.log_count[ls], a.sm.log_stride);
-    const uint32_t* log = G.log + (uint64_t)ls * a.sm.log_stride;
+    const uint32_t n = (uint32_t)min((uint64_t)G.log_count[fig], G.log_cap);
+    const uint32_t* log = G.log + (uint64_t)fig * G.log_cap;
     ColCell* tab = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots;
-    for (uint32_t i = lane; i < n; i += 32) {
-      ColCell* c = tab + log[i];
-      if (atomicOr(&c->pmax1, kCellFinal) & kCellFinal) continue;          // somebody else finalizes / finalized it
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      ColCell* c = tab + log[i];                                            // every cell is logged exactly once
       const unsigned long long w0 = c->cnt_sy, w1 = c->su_sv, sy2 = c->sy2;
       const unsigned long long cnt = w0 & 0xFFFFFFull, sy = w0 >> 24, su = w1 & 0xFFFFFFFFull, sv = w1 >> 32;
+      if (cnt == 0) continue;
       if (cnt > 65536ull) atomicExch(a.err, 6);     // the packed U / V sums are only exact up to 65536 points per cell
       const unsigned long long my = (256ull * sy + cnt / 2) / cnt, mu = (256ull * su + cnt / 2) / cnt,
                                mv = (256ull * sv + cnt / 2) / cnt;
@@ -1111,6 +1095,7 @@ __global__ void __launch_bounds__(256) smooth_finalize_kernel(const __grid_const
       const unsigned __int128 num = (unsigned __int128)cnt * sy2 - (unsigned __int128)sy * sy;
       const unsigned long long tv = (unsigned long long)a.sm.thr_col_var * cnt;
       const unsigned __int128 lim = (unsigned __int128)tv * tv;
+      c->pmax1 |= kCellFinal;
       c->cnt_sy = cnt | (my << 32);
       c->su_sv = mu | (mv << 32);
       c->sy2 = num > lim ? 0ull : 1ull;
@@ -1287,21 +1272,17 @@ __global__ void __launch_bounds__(256) smooth_filter_kernel(const __grid_constan
   }
 }
 
-// back to all-zero cells (and free keys) for the next group: walk the same per-slot logs
+// back to all-zero cells (and free keys) for the next group: walk the same logs
 __global__ void __launch_bounds__(256) smooth_clear_kernel(const __grid_constant__ UnpackArgs a) {
-  const uint32_t ls = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (ls >= a.sm.group_slots) return;
-  const uint32_t lane = lane_id();
-  const uint32_t frame = a.tile_frame[(a.sm.group_first_slot + ls) / kWarpsPerTile];
-  const uint32_t fig = frame - a.sm.group_first_frame;
+  const uint32_t fig = blockIdx.y;
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
     const GridDesc& G = which ? a.sm.col : a.sm.geo;
     if (!G.on) continue;
-    const uint32_t n = min(G.log_count[ls], a.sm.log_stride);
-    const uint32_t* log = G.log + (uint64_t)ls * a.sm.log_stride;
+    const uint32_t n = (uint32_t)min((uint64_t)G.log_count[fig], G.log_cap);
+    const uint32_t* log = G.log + (uint64_t)fig * G.log_cap;
     uint4* tab = reinterpret_cast<uint4*>(G.table) + ((uint64_t)fig * G.slots) * 2;      // 32-byte cells
-    for (uint32_t i = lane; i < n; i += 32) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       const uint32_t cs = log[i];
       tab[(uint64_t)cs * 2] = make_uint4(0, 0, 0, 0);
       tab[(uint64_t)cs * 2 + 1] = make_uint4(0, 0, 0, 0);
@@ -1367,8 +1348,9 @@ int launch_upsample(const UnpackArgs& a, uint8_t* occ_full, void* stream) {
 }
 
 int launch_smooth_finalize(const UnpackArgs& a, void* stream) {
-  if (a.sm.group_slots == 0) return 0;
-  smooth_finalize_kernel<<<(a.sm.group_slots * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+  if (a.sm.group_frames == 0) return 0;
+  const unsigned bx = (148u * 8u + a.sm.group_frames - 1) / a.sm.group_frames;
+  smooth_finalize_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
 }
 
@@ -1380,8 +1362,9 @@ int launch_smooth_filter(const UnpackArgs& a, void* stream) {
 }
 
 int launch_smooth_clear(const UnpackArgs& a, void* stream) {
-  if (a.sm.group_slots == 0) return 0;
-  smooth_clear_kernel<<<(a.sm.group_slots * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+  if (a.sm.group_frames == 0) return 0;
+  const unsigned bx = (148u * 8u + a.sm.group_frames - 1) / a.sm.group_frames;
+  smooth_clear_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
 }
 

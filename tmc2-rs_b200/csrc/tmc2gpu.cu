@@ -257,13 +257,13 @@ struct Batch {
   std::vector<SlotRec> h_slot_rec;
   std::vector<uint32_t> h_tile_frame, h_ftb;
 
-  DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_slot_total, d_slot_base, d_count, d_err, d_owned, d_owned_count;
+  DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_count, d_err, d_work, d_owned_count;
   DevBuf d_pos, d_rgb, d_yuv, d_part, d_pix, d_bt, d_occ_full, d_pos_pre, d_yuv_pre;
   DevBuf d_geotab, d_coltab, d_geokeys, d_colkeys, d_geolog, d_collog, d_geolog_count, d_collog_count, d_changed, d_blist,
       d_blist_count;
   uint64_t geotab_slots = 0, coltab_slots = 0, geotab_frames = 0, coltab_frames = 0, blist_cap = 0;
   bool geotab_hashed = false, coltab_hashed = false;
-  uint32_t max_group_slots = 0, log_stride = 0;
+  uint64_t geolog_cap = 0, collog_cap = 0;
   uint32_t group_frames = 8;          // frames per smoothing group (cell tables stay L2-resident inside a group)
   uint32_t group_frames_eff = 8;      // after fitting the dense tables into the memory budget
   std::vector<cudaEvent_t> ev_grp;    // 2 per group: around the unpack launch
@@ -289,7 +289,7 @@ struct Batch {
   ~Batch() { destroy(); }
   void destroy() {
     cudaSetDevice(device);
-    for (DevBuf* b : {&d_occ, &d_geo, &d_ay, &d_au, &d_av, &d_meta, &d_b2p, &d_slot_total, &d_slot_base, &d_count, &d_err, &d_owned,
+    for (DevBuf* b : {&d_occ, &d_geo, &d_ay, &d_au, &d_av, &d_meta, &d_b2p, &d_count, &d_err, &d_work,
                       &d_owned_count, &d_pos,
                       &d_rgb, &d_yuv, &d_part, &d_pix, &d_bt, &d_occ_full, &d_pos_pre, &d_yuv_pre, &d_geotab, &d_coltab,
                       &d_geokeys, &d_colkeys, &d_geolog, &d_collog, &d_geolog_count, &d_collog_count, &d_changed, &d_blist,
@@ -399,10 +399,8 @@ struct Batch {
     CU(d_meta.ensure(meta_bytes));
     CU(h_meta.ensure(meta_bytes));
     CU(d_b2p.ensure(std::max<size_t>((size_t)F * bw * bh * 4, 4)));
-    CU(d_slot_total.ensure(std::max<size_t>((size_t)n_slots * 4, 4)));
-    CU(d_slot_base.ensure(std::max<size_t>((size_t)n_slots * 4, 4)));
     CU(d_count.ensure(std::max<size_t>((size_t)F * 4, 4)));
-    CU(d_owned.ensure(std::max<size_t>((size_t)n_slots * 4, 4)));
+    CU(d_work.ensure(std::max<size_t>((size_t)n_slots * sizeof(WorkRec), sizeof(WorkRec))));
     CU(d_owned_count.ensure(std::max<size_t>((size_t)F * 4, 4)));
     CU(d_changed.ensure(std::max<size_t>((size_t)F * 16, 16)));
     CU(d_pos.ensure((size_t)F * cap * 6));
@@ -463,15 +461,12 @@ struct Batch {
       };
       if (setup(smoothing_geo, params.grid_size, sizeof(GeoCell), d_geotab, d_geokeys, geotab_slots, geotab_frames, geotab_hashed)) return err.st;
       if (setup(smoothing_col, params.cgrid_size, sizeof(ColCell), d_coltab, d_colkeys, coltab_slots, coltab_frames, coltab_hashed)) return err.st;
-      // per-slot logs of the table slots each unpack slot added to (walked by finalize and clear)
-      log_stride = 2 * res * res;
-      max_group_slots = 0;
-      for (uint32_t f0 = 0; f0 < F; f0 += GF)
-        max_group_slots = std::max(max_group_slots, (h_ftb[std::min(F, f0 + GF)] - h_ftb[f0]) * (uint32_t)kWarpsPerTile);
-      const size_t log_bytes = std::max<size_t>((size_t)max_group_slots * log_stride * 4, 4);
-      const size_t cnt_bytes = std::max<size_t>((size_t)max_group_slots * 4, 4);
-      if (smoothing_geo) { CU(d_geolog.ensure(log_bytes)); CU(d_geolog_count.ensure(cnt_bytes)); }
-      if (smoothing_col) { CU(d_collog.ensure(log_bytes)); CU(d_collog_count.ensure(cnt_bytes)); }
+      // per-frame logs of the touched table slots (each cell once, by its first toucher; walked by finalize and clear)
+      geolog_cap = std::min<uint64_t>(cap, geotab_slots ? geotab_slots : cap);
+      collog_cap = std::min<uint64_t>(cap, coltab_slots ? coltab_slots : cap);
+      const size_t cnt_bytes = std::max<size_t>((size_t)GF * 4, 4);
+      if (smoothing_geo) { CU(d_geolog.ensure((size_t)GF * geolog_cap * 4)); CU(d_geolog_count.ensure(cnt_bytes)); }
+      if (smoothing_col) { CU(d_collog.ensure((size_t)GF * collog_cap * 4)); CU(d_collog_count.ensure(cnt_bytes)); }
     }
     return TMC2_OK;
   }
@@ -597,9 +592,7 @@ struct Batch {
     a.tile_frame = reinterpret_cast<const uint32_t*>(m + meta_tf_off);
     a.frame_tile_begin = reinterpret_cast<const uint32_t*>(m + meta_ftb_off);
     a.block_to_patch = d_b2p.as<uint32_t>();
-    a.owned = d_owned.as<uint32_t>(); a.owned_count = d_owned_count.as<uint32_t>();
-    a.slot_total = d_slot_total.as<uint32_t>();
-    a.slot_base = d_slot_base.as<uint32_t>();
+    a.work = d_work.as<WorkRec>(); a.owned_count = d_owned_count.as<uint32_t>();
     a.frame_count = d_count.as<uint32_t>();
     a.err = d_err.as<int>();
     const bool dbg = (want & WANT_DEBUG) != 0;
@@ -615,7 +608,7 @@ struct Batch {
     if (smooth) {
       const uint32_t maxs = 1u << params.geometry_bitdepth_3d;
       auto grid = [&](GridDesc& G, bool on, uint32_t g, void* table, uint32_t* keys, uint64_t slots, bool hashed, uint32_t* log,
-                      uint32_t* log_count) {
+                      uint32_t* log_count, uint64_t log_cap) {
         G.on = on ? 1 : 0;
         if (!on) return;
         G.g = g; G.w = (maxs + g - 1) / g; G.disth = std::max(g / 2, 1u); G.th = g * G.w;
@@ -624,13 +617,12 @@ struct Batch {
         for (int sft = 0; sft < 16; ++sft) if ((1u << sft) == g) G.g_shift = sft;
         G.slots = slots; G.table = table; G.keys = keys;
         G.identity = hashed ? 0 : 1;
-        G.log = log; G.log_count = log_count;
+        G.log = log; G.log_count = log_count; G.log_cap = log_cap;
       };
       grid(a.sm.geo, smoothing_geo, params.grid_size, d_geotab.p, d_geokeys.as<uint32_t>(), geotab_slots, geotab_hashed,
-           d_geolog.as<uint32_t>(), d_geolog_count.as<uint32_t>());
+           d_geolog.as<uint32_t>(), d_geolog_count.as<uint32_t>(), geolog_cap);
       grid(a.sm.col, smoothing_col, params.cgrid_size, d_coltab.p, d_colkeys.as<uint32_t>(), coltab_slots, coltab_hashed,
-           d_collog.as<uint32_t>(), d_collog_count.as<uint32_t>());
-      a.sm.log_stride = log_stride;
+           d_collog.as<uint32_t>(), d_collog_count.as<uint32_t>(), collog_cap);
       a.sm.blist = d_blist.as<BoundaryEntry>(); a.sm.blist_count = d_blist_count.as<uint32_t>(); a.sm.blist_cap = blist_cap;
       const uint32_t sc = params.attribute_bitdepth > 8 ? (1u << (params.attribute_bitdepth - 8)) : 1u;
       a.sm.thr_geo = params.threshold_smoothing;
@@ -687,8 +679,8 @@ struct Batch {
       for (uint32_t gi = 0; gi < n_groups; ++gi) {
         const uint32_t f0 = gi * GF, f1 = std::min(F, f0 + GF);
         a.sm.group_first_frame = f0; a.sm.group_frames = f1 - f0;
-        a.sm.group_first_slot = h_ftb[f0] * (uint32_t)kWarpsPerTile;
-        a.sm.group_slots = (h_ftb[f1] - h_ftb[f0]) * (uint32_t)kWarpsPerTile;
+        if (smoothing_geo) CU(cudaMemsetAsync(d_geolog_count.p, 0, (size_t)GF * 4, s));
+        if (smoothing_col) CU(cudaMemsetAsync(d_collog_count.p, 0, (size_t)GF * 4, s));
         CU(cudaEventRecord(ev_grp[2 * gi], s));
         KL(launch_emit(a, true, h_ftb[f0], h_ftb[f1], s));
         CU(cudaEventRecord(ev_grp[2 * gi + 1], s));
