@@ -161,7 +161,9 @@ __device__ __forceinline__ ChromaTerm chroma_term(uint32_t U, uint32_t V) {
 // clamp(floor(m / 1023), 0, 255): clamp m to [0, 255*1023 + 1022] first, then floor(m / 1023) == umulhi(m, ceil(2^32/1023))
 // (exact while m * 1019 < 2^32, i.e. m < 4.2e6)
 __device__ __forceinline__ uint32_t quant_int(int32_t m) {
-  return __umulhi((uint32_t)min(max(m, 0), 261887), 4198405u);
+  int32_t c;
+  asm("min.s32.relu %0, %1, %2;" : "=r"(c) : "r"(m), "r"(261887));   // clamp to [0, 261887] in one instruction
+  return __umulhi((uint32_t)c, 4198405u);
 }
 // A flagged chroma sample only matters when 255*Y + I sits right at a multiple of 1023: then the f64 chain decides.
 __device__ __noinline__ uint32_t yuv_to_rgb_flagged(uint32_t Y, uint32_t U, uint32_t V, int32_t ir, int32_t ig, int32_t ib) {
@@ -181,6 +183,10 @@ __device__ __forceinline__ uint32_t yuv_to_rgb_term(uint32_t Y, uint32_t U, uint
   if (c.flagged) return yuv_to_rgb_flagged(Y, U, V, c.ir, c.ig, c.ib);   // rare unless the chroma is exactly neutral
   const int32_t y255 = (int32_t)(255u * Y);
   return quant_int(y255 + c.ir) | (quant_int(y255 + c.ig) << 8) | (quant_int(y255 + c.ib) << 16);
+}
+__device__ __forceinline__ uint32_t yuv_to_rgb_fast(uint32_t Y, int32_t ir, int32_t ig, int32_t ib) {
+  const uint32_t r = quant_int((int32_t)(255u * Y) + ir), g = quant_int((int32_t)(255u * Y) + ig), b = quant_int((int32_t)(255u * Y) + ib);
+  return (b * 256u + g) * 256u + r;
 }
 __device__ __forceinline__ uint32_t yuv_to_rgb_packed(uint32_t Y, uint32_t U, uint32_t V) {
   return yuv_to_rgb_term(Y, U, V, chroma_term(U, V));
@@ -766,6 +772,134 @@ __device__ __forceinline__ void boundary_masks(const UnpackArgs& a, const WorkRe
 
 __device__ __forceinline__ void stg_u32(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
 
+// ---- smoothing work of the emit loop (K6 / K7 statistics + boundary list), one call per 32-point window -----------------
+// Latency discipline: a window ISSUES its cell reductions; whether it was the first toucher of a cell (the returned old
+// value of the atomicMax) is looked at one window later, so the round trip overlaps the next window's work.  First-touched
+// cells are queued in shared memory and appended to the frame's log with one atomicAdd per 32 entries.
+struct SmoothState {
+  uint32_t frame, fig, patch, lane, lbase, n_done;
+  uint32_t* q;                   // [2][64] queued table slots: geometry, colour
+  uint32_t nq_geo, nq_col;       // warp-uniform fill of the two queues
+  uint32_t pend_geo_old, pend_geo_cs, pend_col_old, pend_col_cs;   // issued in the previous window (cs == kCellEmpty: none)
+
+  __device__ __forceinline__ void init(const UnpackArgs& a, uint32_t frame_, uint32_t fig_, uint32_t patch_, uint32_t lane_,
+                                       uint32_t* queue) {
+    frame = frame_; fig = fig_; patch = patch_; lane = lane_; lbase = 0; n_done = 0; q = queue; nq_geo = nq_col = 0;
+    pend_geo_old = pend_col_old = 1; pend_geo_cs = pend_col_cs = kCellEmpty;
+  }
+  __device__ __forceinline__ void flush(const UnpackArgs& a, const GridDesc& G, uint32_t* queue, uint32_t& nq) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&G.log_count[fig], nq);
+    base = __shfl_sync(kFull, base, 0);
+    __syncwarp();
+    for (uint32_t i = lane; i < nq; i += 32) {
+      if ((uint64_t)base + i < G.log_cap) G.log[(uint64_t)fig * G.log_cap + base + i] = queue[i];
+      else atomicExch(a.err, 11);
+    }
+    __syncwarp();
+    nq = 0;
+  }
+  // retire the reductions issued one window ago: queue the cells this warp touched first
+  __device__ __forceinline__ void retire(const UnpackArgs& a, const GridDesc& G, uint32_t* queue, uint32_t& nq, uint32_t old,
+                                         uint32_t cs) {
+    const bool first = cs != kCellEmpty && old == 0u;
+    const uint32_t fm = __ballot_sync(kFull, first);
+    if (fm == 0) return;
+    if (first) queue[nq + __popc(fm & ((1u << lane) - 1u))] = cs;
+    nq += __popc(fm);
+    if (nq > 32u) flush(a, G, queue, nq);
+  }
+
+  __device__ __forceinline__ void point(const UnpackArgs& a, bool valid, uint32_t g, uint32_t w0, uint32_t w1, uint32_t Y,
+                                        uint32_t uv, uint32_t bt, bool has_attr) {
+    const uint32_t X = w0 & 0xFFFFu, Yc = w0 >> 16, Z = w1 & 0xFFFFu;
+    // K6 statistics: geometry cells over ALL points.  The lanes of the window that fall into the same cell are found with
+    // match.any and summed with masked reductions; the lowest lane of each group issues the reductions.
+    if (a.sm.geo.on) {
+      const GridDesc& G = a.sm.geo;
+      uint32_t key = kCellEmpty, rx_ = 0, ry_ = 0, rz_ = 0;
+      if (valid && X < G.th && Yc < G.th && Z < G.th) {
+        if (G.g_shift >= 0) {
+          const uint32_t m = G.g - 1u;
+          key = (X >> G.g_shift) | ((Yc >> G.g_shift) << 10) | ((Z >> G.g_shift) << 20);
+          rx_ = X & m; ry_ = Yc & m; rz_ = Z & m;
+        } else {
+          const uint32_t cx = __umulhi(X, G.magic), cy = __umulhi(Yc, G.magic), cz = __umulhi(Z, G.magic);
+          key = cx | (cy << 10) | (cz << 20);
+          rx_ = X - cx * G.g; ry_ = Yc - cy * G.g; rz_ = Z - cz * G.g;
+        }
+      }
+      const uint32_t peers = __match_any_sync(kFull, key);
+      uint32_t cnt, sx, sy, sz;
+      if (G.g <= 8u) {                      // one packed word: count (6 bits) | three sums of at most 32 * 7 (8 bits each)
+        const uint32_t v = key != kCellEmpty ? (1u | (rx_ << 8) | (ry_ << 16) | (rz_ << 24)) : 0u;
+        const uint32_t r = __reduce_add_sync(peers, v);
+        cnt = r & 0xFFu; sx = (r >> 8) & 0xFFu; sy = (r >> 16) & 0xFFu; sz = r >> 24;
+      } else {                              // sums of at most 32 * 255
+        const uint32_t v0 = key != kCellEmpty ? (1u | (rx_ << 16)) : 0u, v1 = ry_ | (rz_ << 16);
+        const uint32_t r0 = __reduce_add_sync(peers, v0), r1 = __reduce_add_sync(peers, v1);
+        cnt = r0 & 0xFFFFu; sx = r0 >> 16; sy = r1 & 0xFFFFu; sz = r1 >> 16;
+      }
+      uint32_t old = 1, cs = kCellEmpty;
+      if (key != kCellEmpty && lane == (uint32_t)(__ffs(peers) - 1)) {
+        cs = cell_slot(G, fig, key, a.err);
+        if (cs != kCellEmpty) {
+          GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + cs;
+          old = atomicMax(&c->pmax1, patch + 1u);                                   // 0 == this is the first touch
+          atomicMax(&c->pminc, ~patch);
+          atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
+          atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
+        }
+      }
+      retire(a, G, q, nq_geo, pend_geo_old, pend_geo_cs);
+      pend_geo_old = old; pend_geo_cs = cs;
+    }
+    // K7 statistics: colour cells over the type-2 (second ring) points
+    if (a.sm.col.on && has_attr) {
+      const GridDesc& G = a.sm.col;
+      uint32_t old = 1, cs = kCellEmpty;
+      if (bt == 2u) {
+        const uint32_t key = cell_key_of(G, X, Yc, Z);
+        if (key != kCellEmpty) {
+          cs = cell_slot(G, fig, key, a.err);
+          if (cs != kCellEmpty) {
+            ColCell* c = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots + cs;
+            old = atomicMax(&c->pmax1, patch + 1u);
+            atomicMax(&c->pminc, ~patch);
+            atomicAdd(&c->cnt_sy, 1ull | ((unsigned long long)Y << 24));
+            atomicAdd(&c->su_sv, (unsigned long long)(uv & 0xFFFFu) | ((unsigned long long)(uv >> 16) << 32));
+            atomicAdd(&c->sy2, (unsigned long long)Y * Y);
+          }
+        }
+      }
+      retire(a, G, q + 64, nq_col, pend_col_old, pend_col_cs);
+      pend_col_old = old; pend_col_cs = cs;
+    }
+    // compact list of the type-1 boundary points (order inside the list is irrelevant)
+    const uint32_t bm = __ballot_sync(kFull, bt == 1u);
+    if (bt == 1u) {
+      uint4 ent;
+      ent.x = g;
+      ent.y = w0;                                  // pos[0] | pos[1] << 16
+      ent.z = (w1 & 0xFFFFu) | (Y << 16);          // pos[2] | Y << 16
+      ent.w = uv;                                  // U | V << 16
+      reinterpret_cast<uint4*>(a.sm.blist + (uint64_t)frame * a.sm.blist_cap)[lbase + n_done + __popc(bm & ((1u << lane) - 1u))] = ent;
+    }
+    n_done += __popc(bm);
+  }
+
+  __device__ __forceinline__ void finish(const UnpackArgs& a) {
+    if (a.sm.geo.on) {
+      retire(a, a.sm.geo, q, nq_geo, pend_geo_old, pend_geo_cs);
+      if (nq_geo) flush(a, a.sm.geo, q, nq_geo);
+    }
+    if (a.sm.col.on) {
+      retire(a, a.sm.col, q + 64, nq_col, pend_col_old, pend_col_cs);
+      if (nq_col) flush(a, a.sm.col, q + 64, nq_col);
+    }
+  }
+};
+
 // ---- pass 3: emit ------------------------------------------------------------------------------------------------------------
 // Per warp (slot): (1) load the block in canvas layout, (2) spill it into per-pixel tables in shared memory in patch raster
 // order and build the list "output point k <- (pixel rank, map)", (3) POINT-parallel loop over 32-aligned windows of the
@@ -774,7 +908,7 @@ __device__ __forceinline__ void stg_u32(void* p, uint32_t v) { *reinterpret_cast
 // from neighbouring lanes (two positions = three words, four colours = three words); only the ragged ends of a run
 // use 16-bit / 8-bit stores.
 template <bool kSmooth, bool kDebug>
-__global__ void __launch_bounds__(kWarpsPerTile * 32, 4) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
+__global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t lpos = (blockIdx.x + tile_offset) * kWarpsPerTile + warp;
@@ -804,7 +938,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, 4) emit_kernel(const __gri
   const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
   DevPatch P;
   load_patch_fields(a.patches + R.pid, P);
-  uint32_t n_boundary = 0;
+  uint32_t n_boundary = 0, any_flag = 0;
 
   {
     // ---- (1): canvas layout ----------------------------------------------------------------------------------------
@@ -841,15 +975,33 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, 4) emit_kernel(const __gri
       const uint32_t u1 = ay > 0 ? r : 15u - r, v1 = rx > 0 ? 8u * h : 15u - 8u * h;
       rank0 = v1 * 16u + u1; dr = 16 * rx;
     }
+    // per-pixel byte = points of the pixel (0..2) | boundary class << 2, for the lane's 8 pixels at once: spread4(m) puts bit i
+    // of a 4-bit mask into byte i ((m * 0x00204081) & 0x01010101: the four shifted copies do not overlap)
+    uint32_t cb_lo, cb_hi;
+    {
+      auto spread4 = [](uint32_t m) -> uint32_t { return (m * 0x00204081u) & 0x01010101u; };
+      cb_lo = spread4(L.m1 & 15u) + spread4(L.m2 & 15u);
+      cb_hi = spread4(L.m1 >> 4) + spread4(L.m2 >> 4);
+      if (want_bt) {
+        cb_lo += 4u * spread4(bt1 & 15u) + 8u * spread4(bt2 & 15u);
+        cb_hi += 4u * spread4((bt1 >> 4) & 15u) + 8u * spread4((bt2 >> 4) & 15u);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t rank = rank0 + (uint32_t)(j * dr);
       const uint32_t yy = __byte_perm(word_of(ya, j >> 1), word_of(yb, j >> 1), (j & 1) ? 0x7632u : 0x5410u);   // Y0 | Y1 << 16
       // entry of (pixel, map) = n | Y << 16
       *reinterpret_cast<uint2*>(s_pt + 2u * rank) = make_uint2(__byte_perm(L.nn[j], yy, 0x5410), __byte_perm(L.nn[j], yy, 0x7632));
-      const uint32_t c = ((L.m1 >> j) & 1u) + ((L.m2 >> j) & 1u);
-      const uint32_t bt = ((bt1 >> j) & 1u) ? 1u : ((bt2 >> j) & 1u) ? 2u : 0u;
-      s_cnt[rank] = (uint8_t)(c | (bt << 2));
+    }
+    if (dr == 1) {
+      *reinterpret_cast<uint2*>(s_cnt + rank0) = make_uint2(cb_lo, cb_hi);
+    } else if (dr == -1) {                                          // descending ranks: rank0 - 7 .. rank0, bytes reversed
+      *reinterpret_cast<uint2*>(s_cnt + rank0 - 7u) = make_uint2(__byte_perm(cb_hi, 0, 0x0123), __byte_perm(cb_lo, 0, 0x0123));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        s_cnt[rank0 + (uint32_t)(j * dr)] = (uint8_t)((j < 4 ? cb_lo : cb_hi) >> (8 * (j & 3)));
     }
     if (has_attr) {
       // chroma terms, once per (chroma sample, map): the two lanes of a row pair hold the same 4 samples; the even row
@@ -867,10 +1019,12 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, 4) emit_kernel(const __gri
         if (ax != 0) { cu = ax > 0 ? ccx : 7u - ccx; cv = ry > 0 ? ccy : 7u - ccy; }
         else { cu = ay > 0 ? ccy : 7u - ccy; cv = rx > 0 ? ccx : 7u - ccx; }
         const ChromaTerm t = chroma_term(uv & 0xFFFFu, uv >> 16);
+        any_flag |= t.flagged;
         s_term[((cv * 8u + cu) << 1) | (odd ? 1u : 0u)] = make_uint4((uint32_t)t.ir, (uint32_t)t.ig, ((uint32_t)t.ib << 1) | t.flagged, uv);
       }
     }
   }
+  const bool slot_flagged = __any_sync(kFull, any_flag != 0);      // some chroma sample of the block needs the f64 check
   __syncwarp();
 
   // ---- (2b): patch raster order: lane l owns ranks 8l .. 8l+7; where its points go inside the run --------------------------
@@ -906,68 +1060,76 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, 4) emit_kernel(const __gri
   const uint32_t selA = s0 | (s1 << 8), selB = s2 | 0x7600u;
   const uint32_t T00 = (uint32_t)R.u0b * 16u * P.lod_x + P.u1, B00 = (uint32_t)R.v0b * 16u * P.lod_y + P.v1;   // decoder.rs:875-876
   const uint32_t lodx = P.lod_x, lody = P.lod_y, patch = P.local_index;
-  uint16_t* gpos = a.out.pos + (uint64_t)frame * a.out.cap * 3;
-  uint8_t* grgb = has_attr ? a.out.rgb + (uint64_t)frame * a.out.cap * 3 : nullptr;
   const uint64_t gframe = (uint64_t)frame * a.out.cap;
   const uint32_t q = lane & 3u;
   const uint32_t sel_rgb = q == 0 ? 0x4210u : q == 1 ? 0x5421u : 0x6542u;
   const bool odd_lane = (lane & 1u) != 0;
 
-  uint32_t lbase = 0, n_done = 0;
-  if (kSmooth && n_boundary) {                                     // room in the frame's boundary list for this slot
-    if (lane == 0) lbase = atomicAdd(&a.sm.blist_count[frame], n_boundary);
-    lbase = __shfl_sync(kFull, lbase, 0);
-    if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
-      if (lane == 0) atomicExch(a.err, 7);
-      return;
+  SmoothState S;
+  if (kSmooth) {
+    S.init(a, frame, fig, patch, lane, reinterpret_cast<uint32_t*>(wsm + kOffLogQ));
+    if (n_boundary) {                                              // room in the frame's boundary list for this slot
+      uint32_t lbase = 0;
+      if (lane == 0) lbase = atomicAdd(&a.sm.blist_count[frame], n_boundary);
+      lbase = __shfl_sync(kFull, lbase, 0);
+      if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
+        if (lane == 0) atomicExch(a.err, 7);
+        return;
+      }
+      S.lbase = lbase;
     }
   }
 
   const uint32_t run_end = run_base + total;
+  uint32_t g = (run_base & ~31u) + lane;                           // point index inside the frame; g % 32 == lane
+  uint32_t k = g - run_base;                                       // point index inside the run (wraps for g < run_base)
+  uint16_t* ppos = a.out.pos + (gframe + g) * 3;                   // this lane's point in the packed position stream
+  uint8_t* prgb = has_attr ? a.out.rgb + (gframe + g) * 3 : nullptr;
+  const uint16_t* psrc = s_src + (int32_t)k;
 #pragma unroll 1
-  for (uint32_t g0 = run_base & ~31u; g0 < run_end; g0 += 32) {
-    const uint32_t g = g0 + lane;                                  // point index inside the frame; g % 32 == lane
-    const uint32_t k = g - run_base;                               // point index inside the run (wraps for g < run_base)
+  for (; g - lane < run_end; g += 32, k += 32, ppos += 96, prgb += 96, psrc += 32) {
     const bool valid = k < total;
-    const uint32_t e = valid ? (uint32_t)s_src[k] : 0u;            // rank << 1 | map
+    const uint32_t vb = __ballot_sync(kFull, valid);
+    const uint32_t e = valid ? (uint32_t)*psrc : 0u;               // rank << 1 | map
     const uint32_t pt = s_pt[e];                                   // n | Y << 16
     const uint32_t rank = e >> 1, map = e & 1u;
     const uint32_t u1 = rank & 15u, v1 = rank >> 4;
     const uint32_t t = T00 + u1 * lodx, b = (B00 + v1 * lody) & 0xFFFFu;
     const uint32_t A = __byte_perm(pt, t, 0x5410);                 // n | t << 16
     const uint32_t w0 = __byte_perm(A, b, selA), w1 = __byte_perm(A, b, selB);      // x | y << 16 ; z
-    {
-      // two points = three words: [x0 y0] [z0 x1] [y1 z1]; even lane writes the first two, odd lane the third
-      const uint32_t nw0 = __shfl_down_sync(kFull, w0, 1);
-      const bool nvalid = (k + 1u) < total, pvalid = (k - 1u) < total;
-      uint16_t* p = gpos + (uint64_t)g * 3;
-      if (valid) {
-        stg_u32(p + (odd_lane ? 1 : 0), odd_lane ? __byte_perm(w0, w1, 0x5432) : w0);
-        if (!odd_lane) {
-          if (nvalid) stg_u32(p + 2, __byte_perm(w1, nw0, 0x5410));
-          else p[2] = (uint16_t)w1;
-        } else if (!pvalid) {
-          p[0] = (uint16_t)w0;
-        }
-      }
-    }
-    uint32_t Y = 0, uv = 0;
+    const uint32_t nw0 = __shfl_down_sync(kFull, w0, 1);
+    uint32_t Y = 0, uv = 0, c = 0, nc = 0;
     if (has_attr) {
       Y = pt >> 16;                                                                  // codec.rs:637-640
       const uint4 te = s_term[((e >> 6) << 4) | (((e >> 2) & 7u) << 1) | map];
       uv = te.w;
-      ChromaTerm ct;
-      ct.ir = (int32_t)te.x; ct.ig = (int32_t)te.y; ct.ib = (int32_t)te.z >> 1; ct.flagged = te.z & 1u;
-      const uint32_t c = yuv_to_rgb_term(Y, uv & 0xFFFFu, uv >> 16, ct);
-      // four colours = three words; lanes 4i .. 4i+2 of a complete quad write one word each
-      const uint32_t nc = __shfl_down_sync(kFull, c, 1);
-      const uint32_t quad = (__ballot_sync(kFull, valid) >> (lane & ~3u)) & 0xFu;
-      if (valid) {
-        uint8_t* p = grgb + (uint64_t)g * 3;
-        if (quad == 0xFu) {
-          if (q != 3u) stg_u32(p + q, __byte_perm(c, nc, sel_rgb));
+      c = yuv_to_rgb_fast(Y, (int32_t)te.x, (int32_t)te.y, (int32_t)te.z >> 1);
+      if (slot_flagged) {                                                            // rare: neutral / borderline chroma
+        if (valid && (te.z & 1u)) c = yuv_to_rgb_flagged(Y, uv & 0xFFFFu, uv >> 16, (int32_t)te.x, (int32_t)te.y, (int32_t)te.z >> 1);
+      }
+      nc = __shfl_down_sync(kFull, c, 1);
+    }
+    // two points = three words: [x0 y0] [z0 x1] [y1 z1]; even lane writes the first two, odd lane the third.
+    // four colours = three words; lanes 4i .. 4i+2 of a quad write one word each.
+    if (vb == kFull) {
+      stg_u32(ppos + (odd_lane ? 1 : 0), odd_lane ? __byte_perm(w0, w1, 0x5432) : w0);
+      if (!odd_lane) stg_u32(ppos + 2, __byte_perm(w1, nw0, 0x5410));
+      if (has_attr && q != 3u) stg_u32(prgb + q, __byte_perm(c, nc, sel_rgb));
+    } else if (valid) {
+      // ragged end of the run: partner lanes may belong to another slot
+      const bool nvalid = ((vb >> 1) >> lane) & 1u, pvalid = ((vb << 1) >> lane) & 1u;
+      stg_u32(ppos + (odd_lane ? 1 : 0), odd_lane ? __byte_perm(w0, w1, 0x5432) : w0);
+      if (!odd_lane) {
+        if (nvalid) stg_u32(ppos + 2, __byte_perm(w1, nw0, 0x5410));
+        else ppos[2] = (uint16_t)w1;
+      } else if (!pvalid) {
+        ppos[0] = (uint16_t)w0;
+      }
+      if (has_attr) {
+        if (((vb >> (lane & ~3u)) & 0xFu) == 0xFu) {
+          if (q != 3u) stg_u32(prgb + q, __byte_perm(c, nc, sel_rgb));
         } else {
-          p[0] = (uint8_t)c; p[1] = (uint8_t)(c >> 8); p[2] = (uint8_t)(c >> 16);
+          prgb[0] = (uint8_t)c; prgb[1] = (uint8_t)(c >> 8); prgb[2] = (uint8_t)(c >> 16);
         }
       }
     }
@@ -989,55 +1151,9 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, 4) emit_kernel(const __gri
       }
       if (a.out.btype) a.out.btype[gk] = (uint8_t)bt;
     }
-    if (kSmooth) {
-      const uint32_t X = w0 & 0xFFFFu, Yc = w0 >> 16, Z = w1 & 0xFFFFu;
-      // K6 statistics: geometry cells over ALL points.  The lanes of the window that fall into the same cell are found
-      // with match.any and summed with one masked reduction per packed word; the lowest lane of each group issues the
-      // reductions, and the first toucher of a cell logs it.
-      if (a.sm.geo.on) {
-        const GridDesc& G = a.sm.geo;
-        const uint32_t key = valid ? cell_key_of(G, X, Yc, Z) : kCellEmpty;
-        uint32_t v0 = 0, v1s = 0;
-        if (key != kCellEmpty) {
-          const uint32_t gg = G.g;
-          v0 = 1u | ((X - (key & 1023u) * gg) << 16);                               // count | sum rel x   (<= 32 * 255)
-          v1s = (Yc - ((key >> 10) & 1023u) * gg) | ((Z - (key >> 20) * gg) << 16);  // sum rel y | sum rel z
-        }
-        const uint32_t peers = __match_any_sync(kFull, key);
-        const uint32_t r0 = __reduce_add_sync(peers, v0), r1 = __reduce_add_sync(peers, v1s);
-        bool first = false; uint32_t cs = kCellEmpty;
-        if (key != kCellEmpty && lane == (uint32_t)(__ffs(peers) - 1)) {
-          cs = cell_slot(G, fig, key, a.err);
-          if (cs != kCellEmpty) first = geo_cell_add_first(G, fig, cs, patch, r0 & 0xFFFFu, r0 >> 16, r1 & 0xFFFFu, r1 >> 16);
-        }
-        log_append(a, G, fig, first, cs, lane);
-      }
-      // K7 statistics: colour cells over the type-2 (second ring) points
-      if (a.sm.col.on && has_attr && __any_sync(kFull, bt == 2u)) {
-        const GridDesc& G = a.sm.col;
-        bool first = false; uint32_t cs = kCellEmpty;
-        if (bt == 2u) {
-          const uint32_t key = cell_key_of(G, X, Yc, Z);
-          if (key != kCellEmpty) {
-            cs = cell_slot(G, fig, key, a.err);
-            if (cs != kCellEmpty) first = col_cell_add_first(G, fig, cs, patch, 1, Y, uv & 0xFFFFu, uv >> 16, (unsigned long long)Y * Y);
-          }
-        }
-        log_append(a, G, fig, first, cs, lane);
-      }
-      // compact list of the type-1 boundary points (order inside the list is irrelevant)
-      const uint32_t bm = __ballot_sync(kFull, bt == 1u);
-      if (bt == 1u) {
-        uint4 ent;
-        ent.x = g;
-        ent.y = w0;                                  // pos[0] | pos[1] << 16
-        ent.z = (w1 & 0xFFFFu) | (Y << 16);          // pos[2] | Y << 16
-        ent.w = uv;                                  // U | V << 16
-        reinterpret_cast<uint4*>(a.sm.blist + (uint64_t)frame * a.sm.blist_cap)[lbase + n_done + __popc(bm & ((1u << lane) - 1u))] = ent;
-      }
-      n_done += __popc(bm);
-    }
+    if (kSmooth) S.point(a, valid, g, w0, w1, Y, uv, bt, has_attr);
   }
+  if (kSmooth) S.finish(a);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
