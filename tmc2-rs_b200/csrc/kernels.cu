@@ -829,42 +829,58 @@ struct SmoothState {
           rx_ = X - cx * G.g; ry_ = Yc - cy * G.g; rz_ = Z - cz * G.g;
         }
       }
-      const uint32_t peers = __match_any_sync(kFull, key);
+      // Points are in patch raster order, so the lanes of a cell are (mostly) a run of consecutive lanes: segmented inclusive
+      // scan over runs of equal key, the last lane of a run issues the reductions (a cell split into several runs just
+      // gets several reductions).
+      const uint32_t kprev = __shfl_up_sync(kFull, key, 1);
+      const uint32_t heads = __ballot_sync(kFull, lane == 0 || kprev != key);
+      const uint32_t seg = 31u - (uint32_t)__clz(heads & (0xFFFFFFFFu >> (31u - lane)));     // first lane of this lane's run
       uint32_t cnt, sx, sy, sz;
-      if (G.g <= 8u) {                      // one packed word: count (6 bits) | three sums of at most 32 * 7 (8 bits each)
-        const uint32_t v = key != kCellEmpty ? (1u | (rx_ << 8) | (ry_ << 16) | (rz_ << 24)) : 0u;
-        const uint32_t r = __reduce_add_sync(peers, v);
-        cnt = r & 0xFFu; sx = (r >> 8) & 0xFFu; sy = (r >> 16) & 0xFFu; sz = r >> 24;
+      if (G.g <= 8u) {                      // one packed word: count | three sums of at most 32 * 7 (8 bits each)
+        uint32_t v = key != kCellEmpty ? (1u | (rx_ << 8) | (ry_ << 16) | (rz_ << 24)) : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t = __shfl_up_sync(kFull, v, d);
+          if (lane >= seg + (uint32_t)d) v += t;
+        }
+        cnt = v & 0xFFu; sx = (v >> 8) & 0xFFu; sy = (v >> 16) & 0xFFu; sz = v >> 24;
       } else {                              // sums of at most 32 * 255
-        const uint32_t v0 = key != kCellEmpty ? (1u | (rx_ << 16)) : 0u, v1 = ry_ | (rz_ << 16);
-        const uint32_t r0 = __reduce_add_sync(peers, v0), r1 = __reduce_add_sync(peers, v1);
-        cnt = r0 & 0xFFFFu; sx = r0 >> 16; sy = r1 & 0xFFFFu; sz = r1 >> 16;
+        uint32_t v0 = key != kCellEmpty ? (1u | (rx_ << 16)) : 0u, v1 = ry_ | (rz_ << 16);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t0 = __shfl_up_sync(kFull, v0, d), t1 = __shfl_up_sync(kFull, v1, d);
+          if (lane >= seg + (uint32_t)d) { v0 += t0; v1 += t1; }
+        }
+        cnt = v0 & 0xFFFFu; sx = v0 >> 16; sy = v1 & 0xFFFFu; sz = v1 >> 16;
       }
-      uint32_t old = 1, cs = kCellEmpty;
-      if (key != kCellEmpty && lane == (uint32_t)(__ffs(peers) - 1)) {
-        cs = cell_slot(G, fig, key, a.err);
+      const bool tail = key != kCellEmpty && (lane == 31u || ((heads >> 1) >> lane) & 1u);
+      retire(a, G, q, nq_geo, pend_geo_old, pend_geo_cs);          // the reductions issued one window ago
+      pend_geo_old = 1; pend_geo_cs = kCellEmpty;
+      if (tail) {
+        const uint32_t cs = cell_slot(G, fig, key, a.err);
         if (cs != kCellEmpty) {
           GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + cs;
-          old = atomicMax(&c->pmax1, patch + 1u);                                   // 0 == this is the first touch
+          pend_geo_cs = cs;
+          pend_geo_old = atomicMax(&c->pmax1, patch + 1u);                          // 0 == this is the first touch
           atomicMax(&c->pminc, ~patch);
           atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
           atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
         }
       }
-      retire(a, G, q, nq_geo, pend_geo_old, pend_geo_cs);
-      pend_geo_old = old; pend_geo_cs = cs;
     }
     // K7 statistics: colour cells over the type-2 (second ring) points
     if (a.sm.col.on && has_attr) {
       const GridDesc& G = a.sm.col;
-      uint32_t old = 1, cs = kCellEmpty;
+      retire(a, G, q + 64, nq_col, pend_col_old, pend_col_cs);
+      pend_col_old = 1; pend_col_cs = kCellEmpty;
       if (bt == 2u) {
         const uint32_t key = cell_key_of(G, X, Yc, Z);
         if (key != kCellEmpty) {
-          cs = cell_slot(G, fig, key, a.err);
+          const uint32_t cs = cell_slot(G, fig, key, a.err);
           if (cs != kCellEmpty) {
             ColCell* c = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots + cs;
-            old = atomicMax(&c->pmax1, patch + 1u);
+            pend_col_cs = cs;
+            pend_col_old = atomicMax(&c->pmax1, patch + 1u);
             atomicMax(&c->pminc, ~patch);
             atomicAdd(&c->cnt_sy, 1ull | ((unsigned long long)Y << 24));
             atomicAdd(&c->su_sv, (unsigned long long)(uv & 0xFFFFu) | ((unsigned long long)(uv >> 16) << 32));
@@ -872,8 +888,6 @@ struct SmoothState {
           }
         }
       }
-      retire(a, G, q + 64, nq_col, pend_col_old, pend_col_cs);
-      pend_col_old = old; pend_col_cs = cs;
     }
     // compact list of the type-1 boundary points (order inside the list is irrelevant)
     const uint32_t bm = __ballot_sync(kFull, bt == 1u);
@@ -938,7 +952,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) emit_kern
   const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
   DevPatch P;
   load_patch_fields(a.patches + R.pid, P);
-  uint32_t n_boundary = 0, any_flag = 0;
+  uint32_t n_boundary = 0, any_flag = 0, lbase0 = 0;
 
   {
     // ---- (1): canvas layout ----------------------------------------------------------------------------------------
@@ -963,6 +977,8 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) emit_kern
     if (kSmooth) {
       const uint32_t b1 = L.m1 & bt1;
       n_boundary = __reduce_add_sync(kFull, __popc(b1) + __popc(b1 & L.m2));
+      // room in the frame's boundary list for this slot; the answer is picked up right before the point loop
+      if (n_boundary && lane == 0) lbase0 = atomicAdd(&a.sm.blist_count[frame], n_boundary);
     }
 
     // ---- (2): tables in patch raster order -----------------------------------------------------------------------------
@@ -1068,10 +1084,8 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) emit_kern
   SmoothState S;
   if (kSmooth) {
     S.init(a, frame, fig, patch, lane, reinterpret_cast<uint32_t*>(wsm + kOffLogQ));
-    if (n_boundary) {                                              // room in the frame's boundary list for this slot
-      uint32_t lbase = 0;
-      if (lane == 0) lbase = atomicAdd(&a.sm.blist_count[frame], n_boundary);
-      lbase = __shfl_sync(kFull, lbase, 0);
+    if (n_boundary) {
+      const uint32_t lbase = __shfl_sync(kFull, lbase0, 0);
       if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
         if (lane == 0) atomicExch(a.err, 7);
         return;
