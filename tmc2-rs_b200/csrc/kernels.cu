@@ -856,7 +856,11 @@ struct SmoothState {
       const bool tail = key != kCellEmpty && (lane == 31u || ((heads >> 1) >> lane) & 1u);
       retire(a, G, q, nq_geo, pend_geo_old, pend_geo_cs);          // the reductions issued one window ago
       pend_geo_old = 1; pend_geo_cs = kCellEmpty;
+#if defined(TMC2_EXP) && (TMC2_EXP == 1 || TMC2_EXP == 3)
+      if (false) {
+#else
       if (tail) {
+#endif
         const uint32_t cs = cell_slot(G, fig, key, a.err);
         if (cs != kCellEmpty) {
           GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + cs;
@@ -873,7 +877,11 @@ struct SmoothState {
       const GridDesc& G = a.sm.col;
       retire(a, G, q + 64, nq_col, pend_col_old, pend_col_cs);
       pend_col_old = 1; pend_col_cs = kCellEmpty;
+#if defined(TMC2_EXP) && TMC2_EXP == 1
+      if (false) {
+#else
       if (bt == 2u) {
+#endif
         const uint32_t key = cell_key_of(G, X, Yc, Z);
         if (key != kCellEmpty) {
           const uint32_t cs = cell_slot(G, fig, key, a.err);
@@ -1165,7 +1173,9 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) emit_kern
       }
       if (a.out.btype) a.out.btype[gk] = (uint8_t)bt;
     }
+#if !defined(TMC2_EXP) || TMC2_EXP != 2
     if (kSmooth) S.point(a, valid, g, w0, w1, Y, uv, bt, has_attr);
+#endif
   }
   if (kSmooth) S.finish(a);
 }

@@ -242,6 +242,8 @@ struct Batch {
   int device = 0;
   cudaStream_t stream = nullptr;      // compute + H2D
   cudaStream_t d2h_stream = nullptr;  // result copies
+  cudaStream_t aux_stream = nullptr;  // smoothing post-passes of group g overlap the emit of group g+1
+  std::vector<cudaEvent_t> ev_emit, ev_post;   // per group: emit done (main stream) / finalize+filter+clear done (aux)
   bool two_pass = false;
 
   // description of the loaded GOF slice
@@ -303,6 +305,11 @@ struct Batch {
     ev_frame.clear();
     for (auto e : ev_grp) cudaEventDestroy(e);
     ev_grp.clear();
+    for (auto e : ev_emit) cudaEventDestroy(e);
+    ev_emit.clear();
+    for (auto e : ev_post) cudaEventDestroy(e);
+    ev_post.clear();
+    if (aux_stream) cudaStreamDestroy(aux_stream), aux_stream = nullptr;
     if (stream) cudaStreamDestroy(stream), stream = nullptr;
     if (d2h_stream) cudaStreamDestroy(d2h_stream), d2h_stream = nullptr;
   }
@@ -312,6 +319,7 @@ struct Batch {
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
     for (auto& e : ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&ev_counts, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ev_inputs_free, cudaEventDisableTiming));
@@ -433,7 +441,7 @@ struct Batch {
       auto fit = [&](bool on, uint32_t g, size_t cell_bytes) {
         if (!on || force_hash) return;
         const uint64_t per_frame = cells_of(g) * cell_bytes;
-        if (per_frame <= kTableBudget) GF = (uint32_t)std::min<uint64_t>(GF, std::max<uint64_t>(1, kTableBudget / per_frame));
+        if (per_frame <= kTableBudget) GF = (uint32_t)std::min<uint64_t>(GF, std::max<uint64_t>(1, kTableBudget / (2 * per_frame)));
       };
       fit(smoothing_geo, params.grid_size, sizeof(GeoCell));
       fit(smoothing_col, params.cgrid_size, sizeof(ColCell));
@@ -449,11 +457,12 @@ struct Batch {
         bool hashed = false;
         const uint64_t slots = table_slots(g, cell_bytes, hashed);
         if (slots != slots_now || GF > frames_now || hashed != hashed_now) {
-          CU(tab.ensure((size_t)GF * slots * cell_bytes));
-          CU(cudaMemsetAsync(tab.p, 0, (size_t)GF * slots * cell_bytes, stream));     // all-zero == empty cell
+          // two table sets: consecutive frame groups alternate, so the post-passes of one overlap the emit of the next
+          CU(tab.ensure((size_t)2 * GF * slots * cell_bytes));
+          CU(cudaMemsetAsync(tab.p, 0, (size_t)2 * GF * slots * cell_bytes, stream));     // all-zero == empty cell
           if (hashed) {
-            CU(keys.ensure((size_t)GF * slots * 4));
-            KL(launch_fill_u32(keys.as<uint32_t>(), (uint64_t)GF * slots, kCellEmpty, stream));
+            CU(keys.ensure((size_t)2 * GF * slots * 4));
+            KL(launch_fill_u32(keys.as<uint32_t>(), (uint64_t)2 * GF * slots, kCellEmpty, stream));
           }
           slots_now = slots; frames_now = GF; hashed_now = hashed;
         }
@@ -464,9 +473,9 @@ struct Batch {
       // per-frame logs of the touched table slots (each cell once, by its first toucher; walked by finalize and clear)
       geolog_cap = std::min<uint64_t>(cap, geotab_slots ? geotab_slots : cap);
       collog_cap = std::min<uint64_t>(cap, coltab_slots ? coltab_slots : cap);
-      const size_t cnt_bytes = std::max<size_t>((size_t)GF * 4, 4);
-      if (smoothing_geo) { CU(d_geolog.ensure((size_t)GF * geolog_cap * 4)); CU(d_geolog_count.ensure(cnt_bytes)); }
-      if (smoothing_col) { CU(d_collog.ensure((size_t)GF * collog_cap * 4)); CU(d_collog_count.ensure(cnt_bytes)); }
+      const size_t cnt_bytes = std::max<size_t>((size_t)2 * GF * 4, 4);
+      if (smoothing_geo) { CU(d_geolog.ensure((size_t)2 * GF * geolog_cap * 4)); CU(d_geolog_count.ensure(cnt_bytes)); }
+      if (smoothing_col) { CU(d_collog.ensure((size_t)2 * GF * collog_cap * 4)); CU(d_collog_count.ensure(cnt_bytes)); }
     }
     return TMC2_OK;
   }
@@ -676,11 +685,27 @@ struct Batch {
       const uint32_t GF = group_frames_eff;
       n_groups = (F + GF - 1) / GF;
       while (ev_grp.size() < 2 * (size_t)n_groups) { cudaEvent_t e; CU(cudaEventCreate(&e)); ev_grp.push_back(e); }
+      while (ev_emit.size() < n_groups) {
+        cudaEvent_t e1, e2;
+        CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming)); ev_emit.push_back(e1);
+        CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming)); ev_post.push_back(e2);
+      }
+      const GridDesc geo0 = a.sm.geo, col0 = a.sm.col;             // table set 0
+      auto use_set = [&](GridDesc& G, const GridDesc& G0, uint32_t set, size_t cell_bytes) {
+        if (!G0.on) return;
+        G.table = static_cast<uint8_t*>(G0.table) + (size_t)set * GF * G0.slots * cell_bytes;
+        G.keys = G0.keys ? G0.keys + (size_t)set * GF * G0.slots : nullptr;
+        G.log = G0.log + (size_t)set * GF * G0.log_cap;
+        G.log_count = G0.log_count + (size_t)set * GF;
+      };
       for (uint32_t gi = 0; gi < n_groups; ++gi) {
-        const uint32_t f0 = gi * GF, f1 = std::min(F, f0 + GF);
+        const uint32_t f0 = gi * GF, f1 = std::min(F, f0 + GF), set = gi & 1u;
         a.sm.group_first_frame = f0; a.sm.group_frames = f1 - f0;
-        if (smoothing_geo) CU(cudaMemsetAsync(d_geolog_count.p, 0, (size_t)GF * 4, s));
-        if (smoothing_col) CU(cudaMemsetAsync(d_collog_count.p, 0, (size_t)GF * 4, s));
+        use_set(a.sm.geo, geo0, set, sizeof(GeoCell));
+        use_set(a.sm.col, col0, set, sizeof(ColCell));
+        if (gi >= 2) CU(cudaStreamWaitEvent(s, ev_post[gi - 2], 0));          // this table set has been cleared
+        if (smoothing_geo) CU(cudaMemsetAsync(a.sm.geo.log_count, 0, (size_t)GF * 4, s));
+        if (smoothing_col) CU(cudaMemsetAsync(a.sm.col.log_count, 0, (size_t)GF * 4, s));
         CU(cudaEventRecord(ev_grp[2 * gi], s));
         KL(launch_emit(a, true, h_ftb[f0], h_ftb[f1], s));
         CU(cudaEventRecord(ev_grp[2 * gi + 1], s));
@@ -691,10 +716,15 @@ struct Batch {
             CU(cudaMemcpyAsync(d_yuv_pre.as<uint8_t>() + (size_t)f0 * cap * 6, d_yuv.as<uint8_t>() + (size_t)f0 * cap * 6,
                                (size_t)(f1 - f0) * cap * 6, cudaMemcpyDeviceToDevice, s));
         }
-        KL(launch_smooth_finalize(a, s));
-        KL(launch_smooth_filter(a, s));
-        KL(launch_smooth_clear(a, s));
+        // post-passes of this group on the auxiliary stream, while the main stream goes on with the next group's emit
+        CU(cudaEventRecord(ev_emit[gi], s));
+        CU(cudaStreamWaitEvent(aux_stream, ev_emit[gi], 0));
+        KL(launch_smooth_finalize(a, aux_stream));
+        KL(launch_smooth_filter(a, aux_stream));
+        KL(launch_smooth_clear(a, aux_stream));
+        CU(cudaEventRecord(ev_post[gi], aux_stream));
       }
+      for (uint32_t gi = n_groups >= 2 ? n_groups - 2 : 0; gi < n_groups; ++gi) CU(cudaStreamWaitEvent(s, ev_post[gi], 0));
     }
     CU(cudaEventRecord(ev[2], s));
     if (want & WANT_OCC_FULL) KL(launch_upsample(a, d_occ_full.as<uint8_t>(), s));
