@@ -1201,6 +1201,12 @@ __device__ __forceinline__ uint32_t mean_q8_u32(uint32_t s, uint32_t cnt) {     
   const unsigned long long num = 256ull * s + (cnt >> 1);
   return num < (1ull << 32) ? (uint32_t)num / cnt : (uint32_t)(num / cnt);
 }
+// After finalize the first 16 bytes of a touched cell are its SUMMARY (the accumulators are not needed any more):
+//   x = kCellFinal | kCellMulti (touched by more than one patch) | kCellUsable (colour: luminance variance test passed)
+//       | point count (24 bits; a frame has < 2^24 points)
+//   geometry: y = mean x | mean y << 16, z = mean z   (Q8, relative to the cell origin, < 256 * g <= 65536)
+//   colour:   y = mean Y, z = mean U, w = mean V      (Q8)
+constexpr uint32_t kCellMulti = 0x40000000u, kCellUsable = 0x20000000u, kCellCount = 0x00FFFFFFu;
 __global__ void __launch_bounds__(256) smooth_finalize_kernel(const __grid_constant__ UnpackArgs a) {
   const uint32_t fig = blockIdx.y;
   if (a.sm.geo.on) {
@@ -1209,13 +1215,13 @@ __global__ void __launch_bounds__(256) smooth_finalize_kernel(const __grid_const
     const uint32_t* log = G.log + (uint64_t)fig * G.log_cap;
     GeoCell* tab = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-      GeoCell* c = tab + log[i];
-      const unsigned long long w0 = c->cnt_sx, w1 = c->sy_sz;
-      const uint32_t cnt = (uint32_t)w0;
+      uint4* c = reinterpret_cast<uint4*>(tab + log[i]);                    // every cell is logged exactly once
+      const uint4 v0 = c[0], v1 = c[1];                                     // pmax1, pminc, count, sx ; sy, sz, -, -
+      const uint32_t cnt = v0.z;
       if (cnt == 0) continue;
-      const unsigned long long mx = mean_q8_u32((uint32_t)(w0 >> 32), cnt), my = mean_q8_u32((uint32_t)w1, cnt),
-                               mz = mean_q8_u32((uint32_t)(w1 >> 32), cnt);
-      c->mean = mx | (my << 16) | (mz << 32);
+      const uint32_t multi = (v0.x - 1u) != ~v0.y ? kCellMulti : 0u;
+      const uint32_t mx = mean_q8_u32(v0.w, cnt), my = mean_q8_u32(v1.x, cnt), mz = mean_q8_u32(v1.y, cnt);
+      c[0] = make_uint4(kCellFinal | multi | (cnt & kCellCount), mx | (my << 16), mz, 0u);
     }
   }
   if (a.sm.col.on) {
@@ -1225,20 +1231,25 @@ __global__ void __launch_bounds__(256) smooth_finalize_kernel(const __grid_const
     ColCell* tab = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       ColCell* c = tab + log[i];                                            // every cell is logged exactly once
+      const uint32_t multi = (c->pmax1 - 1u) != ~c->pminc ? kCellMulti : 0u;
       const unsigned long long w0 = c->cnt_sy, w1 = c->su_sv, sy2 = c->sy2;
       const unsigned long long cnt = w0 & 0xFFFFFFull, sy = w0 >> 24, su = w1 & 0xFFFFFFFFull, sv = w1 >> 32;
       if (cnt == 0) continue;
       if (cnt > 65536ull) atomicExch(a.err, 6);     // the packed U / V sums are only exact up to 65536 points per cell
-      const unsigned long long my = (256ull * sy + cnt / 2) / cnt, mu = (256ull * su + cnt / 2) / cnt,
-                               mv = (256ull * sv + cnt / 2) / cnt;
+      uint32_t my, mu, mv;
+      if (sy < (1ull << 24) && cnt < (1ull << 24)) {                        // the usual case fits 32-bit division
+        const uint32_t c32 = (uint32_t)cnt;
+        my = mean_q8_u32((uint32_t)sy, c32); mu = mean_q8_u32((uint32_t)su, c32); mv = mean_q8_u32((uint32_t)sv, c32);
+      } else {
+        my = (uint32_t)((256ull * sy + cnt / 2) / cnt); mu = (uint32_t)((256ull * su + cnt / 2) / cnt);
+        mv = (uint32_t)((256ull * sv + cnt / 2) / cnt);
+      }
       // luminance variation: var(Y) = (cnt*sumY2 - sumY^2)/cnt^2 must not exceed t_var^2
       const unsigned __int128 num = (unsigned __int128)cnt * sy2 - (unsigned __int128)sy * sy;
       const unsigned long long tv = (unsigned long long)a.sm.thr_col_var * cnt;
       const unsigned __int128 lim = (unsigned __int128)tv * tv;
-      c->pmax1 |= kCellFinal;
-      c->cnt_sy = cnt | (my << 32);
-      c->su_sv = mu | (mv << 32);
-      c->sy2 = num > lim ? 0ull : 1ull;
+      const uint32_t usable = num > lim ? 0u : kCellUsable;
+      *reinterpret_cast<uint4*>(c) = make_uint4(kCellFinal | multi | usable | ((uint32_t)cnt & kCellCount), my, mu, mv);
     }
   }
 }
@@ -1276,6 +1287,19 @@ __device__ __forceinline__ bool neighbourhood(const GridDesc& G, const uint32_t 
 __device__ __forceinline__ unsigned long long div_w3(unsigned long long x, const GridDesc& G, uint32_t w3) {
   return G.g_shift >= 0 ? (x >> (3 * (G.g_shift + 1))) : (x / w3);
 }
+// the summaries of the 8 cells of a neighbourhood: eight independent 16-byte loads (all in flight together)
+__device__ __forceinline__ void load_summaries(const GridDesc& G, uint32_t fig, size_t cell_bytes, bool on, const Nbhd& N,
+                                               uint4 c[8]) {
+  const uint8_t* tab = static_cast<const uint8_t*>(G.table) + (uint64_t)fig * G.slots * cell_bytes;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    c[j] = make_uint4(0, 0, 0, 0);
+    if (on && N.key[j] != kCellEmpty) {
+      const uint32_t cs = cell_find(G, fig, N.key[j]);
+      if (cs != kCellEmpty) c[j] = __ldg(reinterpret_cast<const uint4*>(tab + (uint64_t)cs * cell_bytes));
+    }
+  }
+}
 
 __global__ void __launch_bounds__(256) smooth_filter_kernel(const __grid_constant__ UnpackArgs a) {
   const uint32_t fig = blockIdx.y;
@@ -1284,50 +1308,43 @@ __global__ void __launch_bounds__(256) smooth_filter_kernel(const __grid_constan
   const BoundaryEntry* L = a.sm.blist + (uint64_t)f * a.sm.blist_cap;
   uint32_t moved = 0, recol = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(&L[i]);
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&L[i]));
     const uint32_t p[3] = {raw.y & 0xFFFFu, raw.y >> 16, raw.z & 0xFFFFu};
     const uint32_t col[3] = {raw.z >> 16, raw.w & 0xFFFFu, raw.w >> 16};
     const uint64_t gi = (uint64_t)f * a.out.cap + raw.x;
-    Nbhd N;
+    Nbhd Ng, Nc;
+    const bool do_geo = a.sm.geo.on && neighbourhood(a.sm.geo, p, Ng);
+    const bool do_col = a.sm.col.on && a.has_attr && neighbourhood(a.sm.col, p, Nc);   // colour cells: pre-smoothing position
+    uint4 cg[8], cc[8];
+    load_summaries(a.sm.geo, fig, sizeof(GeoCell), do_geo, Ng, cg);
+    load_summaries(a.sm.col, fig, sizeof(ColCell), do_col, Nc, cc);
     // ---- geometry (K6) ----
-    if (a.sm.geo.on && neighbourhood(a.sm.geo, p, N)) {
+    if (do_geo) {
       const GridDesc& G = a.sm.geo;
-      const GeoCell* tab = reinterpret_cast<const GeoCell*>(G.table) + (uint64_t)fig * G.slots;
-      uint4 c0[8]; uint2 cm[8];
       bool other = false;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        c0[j] = make_uint4(0, 0, 0, 0); cm[j] = make_uint2(0, 0);
-        const uint32_t cs = N.key[j] != kCellEmpty ? cell_find(G, fig, N.key[j]) : kCellEmpty;
-        if (cs != kCellEmpty) {
-          c0[j] = *reinterpret_cast<const uint4*>(tab + cs);                       // pmax1, pminc, count, sx
-          if (c0[j].z != 0) {
-            cm[j] = *reinterpret_cast<const uint2*>(&(tab + cs)->mean);
-            other |= (c0[j].x - 1u) != ~c0[j].y;
-          }
-        }
-      }
+      for (int j = 0; j < 8; ++j) other |= (cg[j].x & kCellMulti) != 0;
       if (other) {
         unsigned long long C[3] = {0, 0, 0}, cntw = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint32_t cnt = c0[j].z;
+          const uint32_t cnt = cg[j].x & kCellCount;
           uint32_t m[3] = {256u * p[0], 256u * p[1], 256u * p[2]};                  // empty cell -> the point itself
           if (cnt > 0) {
-            m[0] = 256u * ((N.key[j] & 1023u) * G.g) + (cm[j].x & 0xFFFFu);
-            m[1] = 256u * (((N.key[j] >> 10) & 1023u) * G.g) + (cm[j].x >> 16);
-            m[2] = 256u * ((N.key[j] >> 20) * G.g) + (cm[j].y & 0xFFFFu);
+            m[0] = 256u * ((Ng.key[j] & 1023u) * G.g) + (cg[j].y & 0xFFFFu);
+            m[1] = 256u * (((Ng.key[j] >> 10) & 1023u) * G.g) + (cg[j].y >> 16);
+            m[2] = 256u * ((Ng.key[j] >> 20) * G.g) + (cg[j].z & 0xFFFFu);
           }
 #pragma unroll
-          for (int ax = 0; ax < 3; ++ax) C[ax] += (unsigned long long)N.wgt[j] * m[ax];
-          cntw += (unsigned long long)N.wgt[j] * cnt;
+          for (int ax = 0; ax < 3; ++ax) C[ax] += (unsigned long long)Ng.wgt[j] * m[ax];
+          cntw += (unsigned long long)Ng.wgt[j] * cnt;
         }
-        const unsigned long long count = div_w3(cntw, G, N.w3);
+        const unsigned long long count = div_w3(cntw, G, Ng.w3);
         if (count > 0) {
           unsigned long long c4[3], D2 = 0;
 #pragma unroll
           for (int ax = 0; ax < 3; ++ax) {
-            c4[ax] = div_w3(C[ax] + N.w3 / 2, G, N.w3);
+            c4[ax] = div_w3(C[ax] + Ng.w3 / 2, G, Ng.w3);
             const long long d = (long long)(256ull * p[ax]) - (long long)c4[ax];
             D2 += (unsigned long long)(d * d);
           }
@@ -1354,40 +1371,28 @@ __global__ void __launch_bounds__(256) smooth_filter_kernel(const __grid_constan
       }
     }
     // ---- colour (K7), on the same pre-smoothing position ----
-    if (a.sm.col.on && a.has_attr && neighbourhood(a.sm.col, p, N)) {
+    if (do_col) {
       const GridDesc& G = a.sm.col;
-      const ColCell* tab = reinterpret_cast<const ColCell*>(G.table) + (uint64_t)fig * G.slots;
-      uint4 c0[8]; uint4 c1[8];
       bool other = false;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        c0[j] = make_uint4(0, 0, 0, 0); c1[j] = make_uint4(0, 0, 0, 0);
-        const uint32_t cs = N.key[j] != kCellEmpty ? cell_find(G, fig, N.key[j]) : kCellEmpty;
-        if (cs != kCellEmpty) {
-          c0[j] = *reinterpret_cast<const uint4*>(tab + cs);                       // pmax1 | final, pminc, count, meanY
-          if (c0[j].z != 0) {
-            c1[j] = *(reinterpret_cast<const uint4*>(tab + cs) + 1);               // meanU, meanV, variance verdict
-            other |= ((c0[j].x & ~kCellFinal) - 1u) != ~c0[j].y;
-          }
-        }
-      }
+      for (int j = 0; j < 8; ++j) other |= (cc[j].x & kCellMulti) != 0;
       if (other) {
         unsigned long long C[3] = {0, 0, 0};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          bool usable = c0[j].z != 0 && c1[j].z != 0;
-          const uint32_t mean[3] = {c0[j].w, c1[j].x, c1[j].y};
+          bool usable = (cc[j].x & kCellCount) != 0 && (cc[j].x & kCellUsable) != 0;
+          const uint32_t mean[3] = {cc[j].y, cc[j].z, cc[j].w};
           if (usable) {
             const long long dy = (long long)mean[0] - (long long)(256u * col[0]);
             if ((unsigned long long)(dy < 0 ? -dy : dy) > 256ull * a.sm.thr_col_diff) usable = false;
           }
 #pragma unroll
-          for (int ax = 0; ax < 3; ++ax) C[ax] += (unsigned long long)N.wgt[j] * (usable ? mean[ax] : 256u * col[ax]);
+          for (int ax = 0; ax < 3; ++ax) C[ax] += (unsigned long long)Nc.wgt[j] * (usable ? mean[ax] : 256u * col[ax]);
         }
         uint32_t q[3]; unsigned long long dist = 0;
 #pragma unroll
         for (int ax = 0; ax < 3; ++ax) {
-          const unsigned long long c4 = div_w3(C[ax] + N.w3 / 2, G, N.w3);
+          const unsigned long long c4 = div_w3(C[ax] + Nc.w3 / 2, G, Nc.w3);
           unsigned long long rr = (c4 + 128) >> 8;
           if (rr > 65535) rr = 65535;
           q[ax] = (uint32_t)rr;
