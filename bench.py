@@ -274,14 +274,19 @@ def main():
     # ---- roofline of the dominant kernel -------------------------------------------------------------------------------
     peak, peak_src = measured_peak()
     t_unpack = statistics.mean(unpack_ms) if unpack_ms else float("nan")
+    # the emit kernel is launched once per smoothing frame group (8 frames) -- once for the whole GOF without smoothing;
+    # algorithmic bytes and device time are per launch (SURVEY.md 8d figure x the frames one launch processes)
+    group = int(os.environ.get("TMC2_SMOOTH_GROUP", "8")) if smoothing else frames
+    n_emit = max(1, -(-frames // max(group, 1)))
     achieved = alg_bytes / (t_unpack * 1e-3) / 1e9 if t_unpack and t_unpack > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "emit_kernel (fused occupancy upsample / unpack / attribute fetch / YUV->RGB; + boundary + cell statistics when smoothing)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_unpack, "traffic": None,
+                "launches_per_step": n_emit, "frames_per_launch": min(group, frames),
+                "algorithmic_bytes_per_launch": alg_bytes / n_emit, "ms_per_launch": t_unpack / n_emit, "traffic": None,
                 "stage_ms": {k: statistics.mean(v) for k, v in stage_acc.items()}}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            roofline["traffic"] = json.load(f).get(args.config)
+            roofline["traffic"] = json.load(f).get(args.config + ("" if smoothing else "_nosmooth"))
     except Exception:
         pass
 
