@@ -161,8 +161,8 @@ struct UnpackArgs {
 };
 
 // shared memory of one warp of emit_kernel: per-pixel tables of the block in PATCH raster order (rank = v1*16 + u1)
-constexpr uint32_t kOffPt = 0;                                   // [256][2] u32: n | Y << 16 of map 0 / map 1
-constexpr uint32_t kOffTerm = kOffPt + 2048;                     // [64][2] uint4: chroma term of (chroma sample, map)
+constexpr uint32_t kOffPt = 0;                                   // [16 rows][17][2] u32: n | Y << 16 of map 0 / map 1
+constexpr uint32_t kOffTerm = kOffPt + 2176;                     // [64][2] uint4: chroma term of (chroma sample, map)
 constexpr uint32_t kOffSrc = kOffTerm + 2048;                    // [512] u16: output point -> rank << 1 | map
 constexpr uint32_t kOffCnt = kOffSrc + 1024;                     // [256] u8: points of the pixel (0..2) | boundary class << 2
 constexpr uint32_t kOffBmp = kOffCnt + 256;                      // [32] u32: 20x20 occupancy bitmap rows (canvas axes)

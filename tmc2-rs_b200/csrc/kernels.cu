@@ -437,7 +437,7 @@ __device__ __forceinline__ void load_patch_fields(const DevPatch* p, DevPatch& P
 
 // Canvas-layout view of a block: lane (r = lane >> 1, h = lane & 1) holds canvas row r, columns 8h .. 8h+7.
 struct CanvasBlock {
-  uint32_t nn[8];            // n0 | n1 << 16 per pixel
+  uint32_t n0p[4], n1p[4];   // normal coordinates of map 0 / map 1, two pixels per word (pixel 2q in the low half)
   uint32_t m1, m2;           // bit j set = pixel j of this lane emits >= 1 / 2 points
 };
 
@@ -468,11 +468,30 @@ __device__ __forceinline__ void load_geometry(const UnpackArgs& a, const WorkRec
       }
     }
   }
+  if (a.absolute_d1 && P.mode == 0 && P.d1 <= 49152u) {
+    // the usual case (codec.rs:534-548, decoder.rs:883): n = sample / 4 + d1 for both maps, two pixels per instruction
+    // (sample / 4 <= 16383, so the packed sums cannot carry into the neighbouring half)
+    const uint32_t dd = P.d1 * 0x10001u;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint32_t s = __byte_perm(word_of(g0, j >> 1), word_of(g1, j >> 1), (j & 1) ? 0x7632u : 0x5410u);
-    L.nn[j] = normals_of(P, s & 0xFFFFu, s >> 16, a.absolute_d1);
-    if ((L.nn[j] >> 16) != (L.nn[j] & 0xFFFFu)) m2 |= 1u << j;                    // codec.rs:422-428 duplicate skip
+    for (int q = 0; q < 4; ++q) {
+      L.n0p[q] = ((word_of(g0, q) >> 2) & 0x3FFF3FFFu) + dd;
+      L.n1p[q] = ((word_of(g1, q) >> 2) & 0x3FFF3FFFu) + dd;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t w0 = word_of(g0, q), w1 = word_of(g1, q);
+      const uint32_t na = normals_of(P, w0 & 0xFFFFu, w1 & 0xFFFFu, a.absolute_d1);      // n0 | n1 << 16 of pixel 2q
+      const uint32_t nb = normals_of(P, w0 >> 16, w1 >> 16, a.absolute_d1);              // pixel 2q + 1
+      L.n0p[q] = __byte_perm(na, nb, 0x5410);
+      L.n1p[q] = __byte_perm(na, nb, 0x7632);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {                                     // codec.rs:422-428 duplicate skip
+    const uint32_t diff = L.n0p[q] ^ L.n1p[q];
+    if (diff & 0xFFFFu) m2 |= 1u << (2 * q);
+    if (diff >> 16) m2 |= 2u << (2 * q);
   }
   L.m1 = m1; L.m2 = m2 & m1;
 }
@@ -1011,12 +1030,14 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) emit_kern
         cb_hi += 4u * spread4((bt1 >> 4) & 15u) + 8u * spread4((bt2 >> 4) & 15u);
       }
     }
+    // entry of (pixel, map) = n | Y << 16; a table row (16 pixels) is padded by one entry pair so that neither the row-wise
+    // nor the column-wise (transposed patches) stores run into shared-memory bank conflicts
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t rank = rank0 + (uint32_t)(j * dr);
-      const uint32_t yy = __byte_perm(word_of(ya, j >> 1), word_of(yb, j >> 1), (j & 1) ? 0x7632u : 0x5410u);   // Y0 | Y1 << 16
-      // entry of (pixel, map) = n | Y << 16
-      *reinterpret_cast<uint2*>(s_pt + 2u * rank) = make_uint2(__byte_perm(L.nn[j], yy, 0x5410), __byte_perm(L.nn[j], yy, 0x7632));
+      const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+      *reinterpret_cast<uint2*>(s_pt + 2u * (rank + (rank >> 4))) =
+          make_uint2(__byte_perm(L.n0p[j >> 1], word_of(ya, j >> 1), sel), __byte_perm(L.n1p[j >> 1], word_of(yb, j >> 1), sel));
     }
     if (dr == 1) {
       *reinterpret_cast<uint2*>(s_cnt + rank0) = make_uint2(cb_lo, cb_hi);
@@ -1042,6 +1063,9 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) emit_kern
         uint32_t cu, cv;
         if (ax != 0) { cu = ax > 0 ? ccx : 7u - ccx; cv = ry > 0 ? ccy : 7u - ccy; }
         else { cu = ay > 0 ? ccy : 7u - ccy; cv = rx > 0 ? ccx : 7u - ccx; }
+        // no occupied pixel under the sample (the other row of the pair lies in the same occupancy cell unless the
+        // precision is 1): nobody will read the term
+        if (a.prec_shift >= 1 && !((L.m1 >> (2 * cc)) & 3u)) continue;
         const ChromaTerm t = chroma_term(uv & 0xFFFFu, uv >> 16);
         any_flag |= t.flagged;
         s_term[((cv * 8u + cu) << 1) | (odd ? 1u : 0u)] = make_uint4((uint32_t)t.ir, (uint32_t)t.ig, ((uint32_t)t.ib << 1) | t.flagged, uv);
@@ -1113,7 +1137,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) emit_kern
     const bool valid = k < total;
     const uint32_t vb = __ballot_sync(kFull, valid);
     const uint32_t e = valid ? (uint32_t)*psrc : 0u;               // rank << 1 | map
-    const uint32_t pt = s_pt[e];                                   // n | Y << 16
+    const uint32_t pt = s_pt[e + ((e >> 5) << 1)];                 // n | Y << 16 (rows are padded by one pixel)
     const uint32_t rank = e >> 1, map = e & 1u;
     const uint32_t u1 = rank & 15u, v1 = rank >> 4;
     const uint32_t t = T00 + u1 * lodx, b = (B00 + v1 * lody) & 0xFFFFu;
