@@ -948,8 +948,15 @@ struct SmoothState {
 // class, cell statistics and the boundary list.  Results go straight to global memory as aligned 32-bit words assembled
 // from neighbouring lanes (two positions = three words, four colours = three words); only the ragged ends of a run
 // use 16-bit / 8-bit stores.
+#ifndef TMC2_MINCTA
+#define TMC2_MINCTA 4
+#endif
+#ifndef TMC2_UNROLL
+#define TMC2_UNROLL 1
+#endif
+constexpr int kEmitUnroll = TMC2_UNROLL;
 template <bool kSmooth, bool kDebug>
-__global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
+__global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : TMC2_MINCTA) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t lpos = (blockIdx.x + tile_offset) * kWarpsPerTile + warp;
@@ -1132,7 +1139,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : 4) emit_kern
   uint16_t* ppos = a.out.pos + (gframe + g) * 3;                   // this lane's point in the packed position stream
   uint8_t* prgb = has_attr ? a.out.rgb + (gframe + g) * 3 : nullptr;
   const uint16_t* psrc = s_src + (int32_t)k;
-#pragma unroll 1
+#pragma unroll kEmitUnroll
   for (; g - lane < run_end; g += 32, k += 32, ppos += 96, prgb += 96, psrc += 32) {
     const bool valid = k < total;
     const uint32_t vb = __ballot_sync(kFull, valid);
