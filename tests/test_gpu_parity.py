@@ -279,3 +279,40 @@ def test_config2_gof_properties_at_full_size(gpu_ctx):
             assert np.array_equal(pos, want["positions"]) and np.array_equal(col, want["colors"])
     finally:
         r.free()
+
+
+@pytest.mark.parametrize("name", ["c3", "c4"])
+def test_config3_config4_frame_bit_exact_with_smoothing(gpu_ctx, name):
+    """BASELINE configs 3 (1280x1344, width not a power of two) and 4 (2048x2048, 11-bit geometry, ~4M points): one full-size
+    frame, every stream against the oracle, smoothing on."""
+    g = synth.make_gof(synth.config(name, frames=1))
+    assert g.params.geometry_smoothing and g.params.color_smoothing
+    got, want = both(gpu_ctx, g)
+    lo, hi = (900_000, 1_300_000) if name == "c3" else (3_400_000, 4_600_000)
+    assert lo < want["point_count"] < hi, want["point_count"]
+    util.assert_same(got, want, what=name)
+    util.assert_same(got, want, keys=("positions_presmooth", "colors16bit_presmooth", "boundary_type"), what=name + " pre-smoothing")
+    assert got["smoothed_positions"] == want["smoothed_positions"] and got["smoothed_colors"] == want["smoothed_colors"]
+    assert want["smoothed_positions"] > 0
+
+
+def test_three_entry_points_agree_at_full_size(gpu_ctx):
+    """Size-independent property at BASELINE size: the stage API, the streaming API (pinned host planes) and the resident
+    path give byte-identical frames for a C3-shaped GOF, and the frames arrive in order."""
+    g = synth.replicate_gof(synth.make_gof(synth.config("c3", frames=2)), 5)
+    view = abi.GofView(g)
+    frames = gpu_ctx.decode_gof(view)
+    assert len(frames) == 5
+    r = gpu_ctx.upload_gof(view)
+    try:
+        r.reconstruct()
+        counts = r.counts()
+        for f, fr in enumerate(frames):
+            assert len(fr) == counts[f]
+            pos, col = r.fetch(f, int(counts[f]))
+            assert np.array_equal(pos, fr.positions) and np.array_equal(col, fr.colors)
+    finally:
+        r.free()
+    st = gpu_ctx.generate_point_cloud(view, 3, debug=False)
+    assert np.array_equal(st["positions"], frames[3].positions) and np.array_equal(st["colors"], frames[3].colors)
+    assert np.array_equal(frames[0].positions, frames[2].positions) and np.array_equal(frames[1].colors, frames[3].colors)
