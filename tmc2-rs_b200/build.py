@@ -44,6 +44,25 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     return out
 
 
+EXAMPLE_SRC = os.path.join(os.path.dirname(HERE), "examples", "stream_decode.cpp")
+EXAMPLE_BIN = os.path.join(os.path.dirname(HERE), "examples", "stream_decode")
+
+
+def build_example(force: bool = False) -> str:
+    """The plain C++ streaming driver (examples/stream_decode.cpp): g++ only, links the C ABI library, no CUDA headers."""
+    if not force and os.path.exists(EXAMPLE_BIN) and os.path.getmtime(EXAMPLE_BIN) >= max(
+            os.path.getmtime(EXAMPLE_SRC), os.path.getmtime(LIB) if os.path.exists(LIB) else 0):
+        return EXAMPLE_BIN
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-std=c++17", "-O2", "-pthread", EXAMPLE_SRC, "-o", EXAMPLE_BIN, "-L" + HERE, "-l:libtmc2gpu.so",
+           "-Wl,-rpath," + HERE]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building examples/stream_decode")
+    return EXAMPLE_BIN
+
+
 if __name__ == "__main__":
     build(force=True, verbose="-v" in sys.argv)
     print(LIB)

@@ -438,14 +438,24 @@ struct Batch {
       const bool force_hash = getenv("TMC2_FORCE_HASH") != nullptr;        // test hook for the hashed-table path
       auto cells_of = [&](uint32_t g) -> uint64_t { const uint64_t w = (maxs + g - 1) / g; return w * w * w; };
       uint32_t GF = std::min(group_frames, std::max(F, 1u));
-      auto fit = [&](bool on, uint32_t g, size_t cell_bytes) {
+      auto fit = [&](bool on, uint32_t g, size_t cell_bytes, uint32_t sets) {
         if (!on || force_hash) return;
         const uint64_t per_frame = cells_of(g) * cell_bytes;
-        if (per_frame <= kTableBudget) GF = (uint32_t)std::min<uint64_t>(GF, std::max<uint64_t>(1, kTableBudget / (2 * per_frame)));
+        if (per_frame <= kTableBudget) GF = (uint32_t)std::min<uint64_t>(GF, std::max<uint64_t>(1, kTableBudget / (sets * per_frame)));
       };
-      fit(smoothing_geo, params.grid_size, sizeof(GeoCell));
-      fit(smoothing_col, params.cgrid_size, sizeof(ColCell));
+      // one table set when the whole batch is a single group, else two alternating sets (post-passes of a group overlap the
+      // next group's emit)
+      fit(smoothing_geo, params.grid_size, sizeof(GeoCell), 1);
+      fit(smoothing_col, params.cgrid_size, sizeof(ColCell), 1);
+      uint32_t n_sets = 1;
+      if (GF < F) {
+        GF = std::min(group_frames, std::max(F, 1u));
+        fit(smoothing_geo, params.grid_size, sizeof(GeoCell), 2);
+        fit(smoothing_col, params.cgrid_size, sizeof(ColCell), 2);
+        n_sets = 2;
+      }
       group_frames_eff = GF;
+      const uint64_t TF = (uint64_t)n_sets * GF;                              // table frames to hold
       auto table_slots = [&](uint32_t g, size_t cell_bytes, bool& hashed) -> uint64_t {
         const uint64_t cells = cells_of(g);
         hashed = force_hash || cells * cell_bytes > kTableBudget;
@@ -456,15 +466,14 @@ struct Batch {
         if (!on) return TMC2_OK;
         bool hashed = false;
         const uint64_t slots = table_slots(g, cell_bytes, hashed);
-        if (slots != slots_now || GF > frames_now || hashed != hashed_now) {
-          // two table sets: consecutive frame groups alternate, so the post-passes of one overlap the emit of the next
-          CU(tab.ensure((size_t)2 * GF * slots * cell_bytes));
-          CU(cudaMemsetAsync(tab.p, 0, (size_t)2 * GF * slots * cell_bytes, stream));     // all-zero == empty cell
+        if (slots != slots_now || TF > frames_now || hashed != hashed_now) {
+          CU(tab.ensure((size_t)TF * slots * cell_bytes));
+          CU(cudaMemsetAsync(tab.p, 0, (size_t)TF * slots * cell_bytes, stream));     // all-zero == empty cell
           if (hashed) {
-            CU(keys.ensure((size_t)2 * GF * slots * 4));
-            KL(launch_fill_u32(keys.as<uint32_t>(), (uint64_t)2 * GF * slots, kCellEmpty, stream));
+            CU(keys.ensure((size_t)TF * slots * 4));
+            KL(launch_fill_u32(keys.as<uint32_t>(), (uint64_t)TF * slots, kCellEmpty, stream));
           }
-          slots_now = slots; frames_now = GF; hashed_now = hashed;
+          slots_now = slots; frames_now = TF; hashed_now = hashed;
         }
         return TMC2_OK;
       };
@@ -473,9 +482,9 @@ struct Batch {
       // per-frame logs of the touched table slots (each cell once, by its first toucher; walked by finalize and clear)
       geolog_cap = std::min<uint64_t>(cap, geotab_slots ? geotab_slots : cap);
       collog_cap = std::min<uint64_t>(cap, coltab_slots ? coltab_slots : cap);
-      const size_t cnt_bytes = std::max<size_t>((size_t)2 * GF * 4, 4);
-      if (smoothing_geo) { CU(d_geolog.ensure((size_t)2 * GF * geolog_cap * 4)); CU(d_geolog_count.ensure(cnt_bytes)); }
-      if (smoothing_col) { CU(d_collog.ensure((size_t)2 * GF * collog_cap * 4)); CU(d_collog_count.ensure(cnt_bytes)); }
+      const size_t cnt_bytes = std::max<size_t>((size_t)TF * 4, 4);
+      if (smoothing_geo) { CU(d_geolog.ensure((size_t)TF * geolog_cap * 4)); CU(d_geolog_count.ensure(cnt_bytes)); }
+      if (smoothing_col) { CU(d_collog.ensure((size_t)TF * collog_cap * 4)); CU(d_collog_count.ensure(cnt_bytes)); }
     }
     return TMC2_OK;
   }
