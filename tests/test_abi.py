@@ -78,3 +78,19 @@ def test_product_path_never_touches_oracle():
                 assert "liboracle" not in text and "tmc2_oracle" not in text, f
                 if f.endswith(".py"):
                     assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
+
+
+def test_rust_ffi_crate_mirrors_header():
+    """integration/tmc2gpu-sys cannot be compiled here (no cargo/rustc): keep its #[repr(C)] structs textually in step with
+    the ctypes mirror (which test_struct_layout_matches_c pins to the C header) -- same field names in the same order --
+    and make sure every extern fn it declares exists in the header."""
+    text = open(os.path.join(ROOT, "integration", "tmc2gpu-sys", "src", "lib.rs")).read()
+    for rust_name, cls in {"tmc2_patch": abi.CPatch, "tmc2_params": abi.CParams, "tmc2_frame": abi.CFrame,
+                           "tmc2_gof": abi.CGof, "tmc2_frame_out": abi.CFrameOut, "tmc2_limits": abi.CLimits}.items():
+        m = re.search(r"pub struct %s \{(.*?)\n\}" % rust_name, text, re.S)
+        assert m, rust_name
+        fields = re.findall(r"pub (\w+):", m.group(1))
+        assert fields == [f for f, _ in cls._fields_], rust_name
+    header = open(HEADER).read()
+    for fn in re.findall(r"pub fn (tmc2gpu_\w+)\(", text):
+        assert re.search(r"\b%s\(" % fn, header), fn
