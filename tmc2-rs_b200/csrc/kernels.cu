@@ -1332,113 +1332,143 @@ __device__ __forceinline__ void load_summaries(const GridDesc& G, uint32_t fig, 
   }
 }
 
+// One type-1 boundary point against the two grids.  `want` bit 0: geometry, bit 1: colour (the grids whose neighbourhood
+// holds a multi-patch cell).  Returns moved | recoloured << 1.
+__device__ __forceinline__ uint32_t filter_apply(const UnpackArgs& a, uint32_t fig, uint32_t f, const uint4& raw, uint32_t want) {
+  const uint32_t p[3] = {raw.y & 0xFFFFu, raw.y >> 16, raw.z & 0xFFFFu};
+  const uint32_t col[3] = {raw.z >> 16, raw.w & 0xFFFFu, raw.w >> 16};
+  const uint64_t gi = (uint64_t)f * a.out.cap + raw.x;
+  uint32_t result = 0;
+  // ---- geometry (K6) ----
+  if (want & 1u) {
+    const GridDesc& G = a.sm.geo;
+    Nbhd Ng;
+    neighbourhood(G, p, Ng);
+    uint4 cg[8];
+    load_summaries(G, fig, sizeof(GeoCell), true, Ng, cg);
+    unsigned long long C[3] = {0, 0, 0}, cntw = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t cnt = cg[j].x & kCellCount;
+      uint32_t m[3] = {256u * p[0], 256u * p[1], 256u * p[2]};                  // empty cell -> the point itself
+      if (cnt > 0) {
+        m[0] = 256u * ((Ng.key[j] & 1023u) * G.g) + (cg[j].y & 0xFFFFu);
+        m[1] = 256u * (((Ng.key[j] >> 10) & 1023u) * G.g) + (cg[j].y >> 16);
+        m[2] = 256u * ((Ng.key[j] >> 20) * G.g) + (cg[j].z & 0xFFFFu);
+      }
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) C[ax] += (unsigned long long)Ng.wgt[j] * m[ax];
+      cntw += (unsigned long long)Ng.wgt[j] * cnt;
+    }
+    const unsigned long long count = div_w3(cntw, G, Ng.w3);
+    if (count > 0) {
+      unsigned long long c4[3], D2 = 0;
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        c4[ax] = div_w3(C[ax] + Ng.w3 / 2, G, Ng.w3);
+        const long long d = (long long)(256ull * p[ax]) - (long long)c4[ax];
+        D2 += (unsigned long long)(d * d);
+      }
+      const unsigned long long m = a.sm.thr_geo > count ? a.sm.thr_geo : count;
+      const unsigned __int128 lhs = (unsigned __int128)2 * count * D2 + 65536u;
+      const unsigned __int128 rhs = (unsigned __int128)262144u * m;
+      if (lhs >= rhs) {
+        bool changed = false;
+        uint16_t q[3];
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+          unsigned long long rr = (c4[ax] + 128) >> 8;
+          if (rr > 65535) rr = 65535;
+          q[ax] = (uint16_t)rr;
+          changed |= q[ax] != p[ax];
+        }
+        if (changed) {
+          uint16_t* d = a.out.pos + gi * 3;
+          d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
+          result |= 1u;
+        }
+      }
+    }
+  }
+  // ---- colour (K7), on the same pre-smoothing position ----
+  if (want & 2u) {
+    const GridDesc& G = a.sm.col;
+    Nbhd Nc;
+    neighbourhood(G, p, Nc);
+    uint4 cc[8];
+    load_summaries(G, fig, sizeof(ColCell), true, Nc, cc);
+    unsigned long long C[3] = {0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      bool usable = (cc[j].x & kCellCount) != 0 && (cc[j].x & kCellUsable) != 0;
+      const uint32_t mean[3] = {cc[j].y, cc[j].z, cc[j].w};
+      if (usable) {
+        const long long dy = (long long)mean[0] - (long long)(256u * col[0]);
+        if ((unsigned long long)(dy < 0 ? -dy : dy) > 256ull * a.sm.thr_col_diff) usable = false;
+      }
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) C[ax] += (unsigned long long)Nc.wgt[j] * (usable ? mean[ax] : 256u * col[ax]);
+    }
+    uint32_t q[3]; unsigned long long dist = 0;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      const unsigned long long c4 = div_w3(C[ax] + Nc.w3 / 2, G, Nc.w3);
+      unsigned long long rr = (c4 + 128) >> 8;
+      if (rr > 65535) rr = 65535;
+      q[ax] = (uint32_t)rr;
+      const long long d = (long long)q[ax] - (long long)col[ax];
+      dist += (unsigned long long)(d < 0 ? -d : d) * (ax == 0 ? 10u : 1u);
+    }
+    if (dist >= a.sm.thr_col_smooth && dist > 0) {
+      const uint32_t c = yuv_to_rgb_packed(q[0], q[1], q[2]);
+      uint8_t* d = a.out.rgb + gi * 3;
+      d[0] = (uint8_t)c; d[1] = (uint8_t)(c >> 8); d[2] = (uint8_t)(c >> 16);
+      if (a.out.yuv) { uint16_t* y = a.out.yuv + gi * 3; y[0] = (uint16_t)q[0]; y[1] = (uint16_t)q[1]; y[2] = (uint16_t)q[2]; }
+      result |= 2u;
+    }
+  }
+  return result;
+}
+
+// Two phases per CTA and batch of 256 list entries.  PROBE (every entry, cheap): fetch the 16 cell summaries, keep the
+// entry if some neighbouring cell of a grid is multi-patch -- most boundary points have none and are done.  APPLY (the
+// survivors, compacted through shared memory so that the expensive blend runs in full warps).
 __global__ void __launch_bounds__(256) smooth_filter_kernel(const __grid_constant__ UnpackArgs a) {
+  __shared__ uint32_t s_q[256];
+  __shared__ uint32_t s_n;
   const uint32_t fig = blockIdx.y;
   const uint32_t f = a.sm.group_first_frame + fig;
   const uint32_t n = min((uint64_t)a.sm.blist_count[f], a.sm.blist_cap);
   const BoundaryEntry* L = a.sm.blist + (uint64_t)f * a.sm.blist_cap;
   uint32_t moved = 0, recol = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&L[i]));
-    const uint32_t p[3] = {raw.y & 0xFFFFu, raw.y >> 16, raw.z & 0xFFFFu};
-    const uint32_t col[3] = {raw.z >> 16, raw.w & 0xFFFFu, raw.w >> 16};
-    const uint64_t gi = (uint64_t)f * a.out.cap + raw.x;
-    Nbhd Ng, Nc;
-    const bool do_geo = a.sm.geo.on && neighbourhood(a.sm.geo, p, Ng);
-    const bool do_col = a.sm.col.on && a.has_attr && neighbourhood(a.sm.col, p, Nc);   // colour cells: pre-smoothing position
-    uint4 cg[8], cc[8];
-    load_summaries(a.sm.geo, fig, sizeof(GeoCell), do_geo, Ng, cg);
-    load_summaries(a.sm.col, fig, sizeof(ColCell), do_col, Nc, cc);
-    // ---- geometry (K6) ----
-    if (do_geo) {
-      const GridDesc& G = a.sm.geo;
-      bool other = false;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const uint32_t i = base + threadIdx.x;
+    if (i < n) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&L[i]));
+      const uint32_t p[3] = {raw.y & 0xFFFFu, raw.y >> 16, raw.z & 0xFFFFu};
+      Nbhd Ng, Nc;
+      const bool do_geo = a.sm.geo.on && neighbourhood(a.sm.geo, p, Ng);
+      const bool do_col = a.sm.col.on && a.has_attr && neighbourhood(a.sm.col, p, Nc);   // colour cells: pre-smoothing position
+      uint4 cg[8], cc[8];
+      load_summaries(a.sm.geo, fig, sizeof(GeoCell), do_geo, Ng, cg);
+      load_summaries(a.sm.col, fig, sizeof(ColCell), do_col, Nc, cc);
+      uint32_t og = 0, oc = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) other |= (cg[j].x & kCellMulti) != 0;
-      if (other) {
-        unsigned long long C[3] = {0, 0, 0}, cntw = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t cnt = cg[j].x & kCellCount;
-          uint32_t m[3] = {256u * p[0], 256u * p[1], 256u * p[2]};                  // empty cell -> the point itself
-          if (cnt > 0) {
-            m[0] = 256u * ((Ng.key[j] & 1023u) * G.g) + (cg[j].y & 0xFFFFu);
-            m[1] = 256u * (((Ng.key[j] >> 10) & 1023u) * G.g) + (cg[j].y >> 16);
-            m[2] = 256u * ((Ng.key[j] >> 20) * G.g) + (cg[j].z & 0xFFFFu);
-          }
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax) C[ax] += (unsigned long long)Ng.wgt[j] * m[ax];
-          cntw += (unsigned long long)Ng.wgt[j] * cnt;
-        }
-        const unsigned long long count = div_w3(cntw, G, Ng.w3);
-        if (count > 0) {
-          unsigned long long c4[3], D2 = 0;
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax) {
-            c4[ax] = div_w3(C[ax] + Ng.w3 / 2, G, Ng.w3);
-            const long long d = (long long)(256ull * p[ax]) - (long long)c4[ax];
-            D2 += (unsigned long long)(d * d);
-          }
-          const unsigned long long m = a.sm.thr_geo > count ? a.sm.thr_geo : count;
-          const unsigned __int128 lhs = (unsigned __int128)2 * count * D2 + 65536u;
-          const unsigned __int128 rhs = (unsigned __int128)262144u * m;
-          if (lhs >= rhs) {
-            bool changed = false;
-            uint16_t q[3];
-#pragma unroll
-            for (int ax = 0; ax < 3; ++ax) {
-              unsigned long long rr = (c4[ax] + 128) >> 8;
-              if (rr > 65535) rr = 65535;
-              q[ax] = (uint16_t)rr;
-              changed |= q[ax] != p[ax];
-            }
-            if (changed) {
-              uint16_t* d = a.out.pos + gi * 3;
-              d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
-              moved += 1;
-            }
-          }
-        }
-      }
+      for (int j = 0; j < 8; ++j) { og |= cg[j].x; oc |= cc[j].x; }
+      const uint32_t want = ((og & kCellMulti) ? 1u : 0u) | ((oc & kCellMulti) ? 2u : 0u);
+      if (want) s_q[atomicAdd(&s_n, 1u)] = i | (want << 30);
     }
-    // ---- colour (K7), on the same pre-smoothing position ----
-    if (do_col) {
-      const GridDesc& G = a.sm.col;
-      bool other = false;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) other |= (cc[j].x & kCellMulti) != 0;
-      if (other) {
-        unsigned long long C[3] = {0, 0, 0};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          bool usable = (cc[j].x & kCellCount) != 0 && (cc[j].x & kCellUsable) != 0;
-          const uint32_t mean[3] = {cc[j].y, cc[j].z, cc[j].w};
-          if (usable) {
-            const long long dy = (long long)mean[0] - (long long)(256u * col[0]);
-            if ((unsigned long long)(dy < 0 ? -dy : dy) > 256ull * a.sm.thr_col_diff) usable = false;
-          }
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax) C[ax] += (unsigned long long)Nc.wgt[j] * (usable ? mean[ax] : 256u * col[ax]);
-        }
-        uint32_t q[3]; unsigned long long dist = 0;
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {
-          const unsigned long long c4 = div_w3(C[ax] + Nc.w3 / 2, G, Nc.w3);
-          unsigned long long rr = (c4 + 128) >> 8;
-          if (rr > 65535) rr = 65535;
-          q[ax] = (uint32_t)rr;
-          const long long d = (long long)q[ax] - (long long)col[ax];
-          dist += (unsigned long long)(d < 0 ? -d : d) * (ax == 0 ? 10u : 1u);
-        }
-        if (dist >= a.sm.thr_col_smooth && dist > 0) {
-          const uint32_t c = yuv_to_rgb_packed(q[0], q[1], q[2]);
-          uint8_t* d = a.out.rgb + gi * 3;
-          d[0] = (uint8_t)c; d[1] = (uint8_t)(c >> 8); d[2] = (uint8_t)(c >> 16);
-          if (a.out.yuv) { uint16_t* y = a.out.yuv + gi * 3; y[0] = (uint16_t)q[0]; y[1] = (uint16_t)q[1]; y[2] = (uint16_t)q[2]; }
-          recol += 1;
-        }
-      }
+    __syncthreads();
+    const uint32_t m = s_n;
+    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) {
+      const uint32_t e = s_q[j];
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&L[e & 0x3FFFFFFFu]));
+      const uint32_t r = filter_apply(a, fig, f, raw, e >> 30);
+      moved += r & 1u; recol += r >> 1;
     }
+    __syncthreads();
   }
   moved = __reduce_add_sync(kFull, moved);
   recol = __reduce_add_sync(kFull, recol);
