@@ -257,25 +257,6 @@ __device__ __forceinline__ uint32_t cell_find(const GridDesc& G, uint32_t fig, u
   return kCellEmpty;
 }
 
-// fire-and-forget accumulation into a cell (REDs: nothing is read back)
-__device__ __forceinline__ void geo_cell_add(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
-                                             uint32_t sx, uint32_t sy, uint32_t sz) {
-  GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + slot;
-  atomicMax(&c->pmax1, patch + 1u);
-  atomicMax(&c->pminc, ~patch);
-  atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
-  atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
-}
-__device__ __forceinline__ void col_cell_add(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
-                                             uint32_t sy, uint32_t su, uint32_t sv, unsigned long long sy2) {
-  ColCell* c = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots + slot;
-  atomicMax(&c->pmax1, patch + 1u);
-  atomicMax(&c->pminc, ~patch);
-  atomicAdd(&c->cnt_sy, (unsigned long long)cnt | ((unsigned long long)sy << 24));
-  atomicAdd(&c->su_sv, (unsigned long long)su | ((unsigned long long)sv << 32));
-  atomicAdd(&c->sy2, sy2);
-}
-
 // ----------------------------------------------------------------------------------------------------------------
 // K2: block-to-patch map.  One thread per slot (= one 16x16 block of one patch).
 // ----------------------------------------------------------------------------------------------------------------
@@ -529,8 +510,8 @@ __device__ __noinline__ uint32_t generic_slot_count(const UnpackArgs& a, uint32_
 __device__ __forceinline__ bool geo_cell_add_first(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
                                                    uint32_t sx, uint32_t sy, uint32_t sz) {
   GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + slot;
-  const uint32_t old = atomicMax(&c->pmax1, patch + 1u);
-  atomicMax(&c->pminc, ~patch);
+  const uint32_t old = atomicCAS(&c->first1, 0u, patch + 1u);
+  if (old != 0u && old != patch + 1u) *reinterpret_cast<volatile uint32_t*>(&c->multi) = 1u;
   atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
   atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
   return old == 0u;
@@ -538,8 +519,8 @@ __device__ __forceinline__ bool geo_cell_add_first(const GridDesc& G, uint32_t f
 __device__ __forceinline__ bool col_cell_add_first(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
                                                    uint32_t sy, uint32_t su, uint32_t sv, unsigned long long sy2) {
   ColCell* c = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots + slot;
-  const uint32_t old = atomicMax(&c->pmax1, patch + 1u);
-  atomicMax(&c->pminc, ~patch);
+  const uint32_t old = atomicCAS(&c->first1, 0u, patch + 1u);
+  if (old != 0u && old != patch + 1u) *reinterpret_cast<volatile uint32_t*>(&c->multi) = 1u;
   atomicAdd(&c->cnt_sy, (unsigned long long)cnt | ((unsigned long long)sy << 24));
   atomicAdd(&c->su_sv, (unsigned long long)su | ((unsigned long long)sv << 32));
   atomicAdd(&c->sy2, sy2);
@@ -821,6 +802,9 @@ struct SmoothState {
   // retire the reductions issued one window ago: queue the cells this warp touched first
   __device__ __forceinline__ void retire(const UnpackArgs& a, const GridDesc& G, uint32_t* queue, uint32_t& nq, uint32_t old,
                                          uint32_t cs) {
+    // the cell had been claimed by another patch: it is a multi-patch cell (idempotent plain store, 32-byte cells)
+    if (cs != kCellEmpty && old != 0u && old != patch + 1u)
+      reinterpret_cast<volatile uint32_t*>(static_cast<uint8_t*>(G.table) + ((uint64_t)fig * G.slots + cs) * 32u)[1] = 1u;
     const bool first = cs != kCellEmpty && old == 0u;
     const uint32_t fm = __ballot_sync(kFull, first);
     if (fm == 0) return;
@@ -884,8 +868,7 @@ struct SmoothState {
         if (cs != kCellEmpty) {
           GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + cs;
           pend_geo_cs = cs;
-          pend_geo_old = atomicMax(&c->pmax1, patch + 1u);                          // 0 == this is the first touch
-          atomicMax(&c->pminc, ~patch);
+          pend_geo_old = atomicCAS(&c->first1, 0u, patch + 1u);   // 0: first touch; another patch + 1: multi-patch cell
           atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
           atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
         }
@@ -907,8 +890,7 @@ struct SmoothState {
           if (cs != kCellEmpty) {
             ColCell* c = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots + cs;
             pend_col_cs = cs;
-            pend_col_old = atomicMax(&c->pmax1, patch + 1u);
-            atomicMax(&c->pminc, ~patch);
+            pend_col_old = atomicCAS(&c->first1, 0u, patch + 1u);
             atomicAdd(&c->cnt_sy, 1ull | ((unsigned long long)Y << 24));
             atomicAdd(&c->su_sv, (unsigned long long)(uv & 0xFFFFu) | ((unsigned long long)(uv >> 16) << 32));
             atomicAdd(&c->sy2, (unsigned long long)Y * Y);
@@ -954,9 +936,12 @@ struct SmoothState {
 #ifndef TMC2_UNROLL
 #define TMC2_UNROLL 1
 #endif
+#ifndef TMC2_SMOOTH_MINCTA
+#define TMC2_SMOOTH_MINCTA 3
+#endif
 constexpr int kEmitUnroll = TMC2_UNROLL;
 template <bool kSmooth, bool kDebug>
-__global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? 3 : TMC2_MINCTA) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
+__global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINCTA : TMC2_MINCTA) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t lpos = (blockIdx.x + tile_offset) * kWarpsPerTile + warp;
@@ -1247,10 +1232,10 @@ __global__ void __launch_bounds__(256) smooth_finalize_kernel(const __grid_const
     GeoCell* tab = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       uint4* c = reinterpret_cast<uint4*>(tab + log[i]);                    // every cell is logged exactly once
-      const uint4 v0 = c[0], v1 = c[1];                                     // pmax1, pminc, count, sx ; sy, sz, -, -
+      const uint4 v0 = c[0], v1 = c[1];                                     // first1, multi, count, sx ; sy, sz, -, -
       const uint32_t cnt = v0.z;
       if (cnt == 0) continue;
-      const uint32_t multi = (v0.x - 1u) != ~v0.y ? kCellMulti : 0u;
+      const uint32_t multi = v0.y != 0u ? kCellMulti : 0u;
       const uint32_t mx = mean_q8_u32(v0.w, cnt), my = mean_q8_u32(v1.x, cnt), mz = mean_q8_u32(v1.y, cnt);
       c[0] = make_uint4(kCellFinal | multi | (cnt & kCellCount), mx | (my << 16), mz, 0u);
     }
@@ -1262,7 +1247,7 @@ __global__ void __launch_bounds__(256) smooth_finalize_kernel(const __grid_const
     ColCell* tab = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       ColCell* c = tab + log[i];                                            // every cell is logged exactly once
-      const uint32_t multi = (c->pmax1 - 1u) != ~c->pminc ? kCellMulti : 0u;
+      const uint32_t multi = c->multi != 0u ? kCellMulti : 0u;
       const unsigned long long w0 = c->cnt_sy, w1 = c->su_sv, sy2 = c->sy2;
       const unsigned long long cnt = w0 & 0xFFFFFFull, sy = w0 >> 24, su = w1 & 0xFFFFFFFFull, sv = w1 >> 32;
       if (cnt == 0) continue;
