@@ -958,7 +958,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
     generic_slot_emit<kSmooth, kDebug>(a, R.pid, frame, fig, R.u0b, R.v0b, (uint64_t)frame * a.out.cap + run_base);
     return;
   }
-  uint8_t* wsm = smem + (size_t)warp * kWarpSmemBytes;
+  uint8_t* wsm = smem + (size_t)warp * (kSmooth ? kWarpSmemBytes : kOffLogQ);
   uint32_t* s_pt = reinterpret_cast<uint32_t*>(wsm + kOffPt);
   uint4* s_term = reinterpret_cast<uint4*>(wsm + kOffTerm);
   uint16_t* s_src = reinterpret_cast<uint16_t*>(wsm + kOffSrc);
@@ -1506,7 +1506,7 @@ int launch_compact_owned(const UnpackArgs& a, void* stream) {
 
 template <bool kSmooth, bool kDebug>
 static int launch_emit_t(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, cudaStream_t s) {
-  const size_t smem = (size_t)kWarpSmemBytes * kWarpsPerTile;
+  const size_t smem = (size_t)(kSmooth ? kWarpSmemBytes : kOffLogQ) * kWarpsPerTile;   // the log queues are smoothing-only
   cudaError_t e = cudaFuncSetAttribute((const void*)emit_kernel<kSmooth, kDebug>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   emit_kernel<kSmooth, kDebug><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin);
