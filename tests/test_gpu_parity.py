@@ -316,3 +316,28 @@ def test_three_entry_points_agree_at_full_size(gpu_ctx):
     st = gpu_ctx.generate_point_cloud(view, 3, debug=False)
     assert np.array_equal(st["positions"], frames[3].positions) and np.array_equal(st["colors"], frames[3].colors)
     assert np.array_equal(frames[0].positions, frames[2].positions) and np.array_equal(frames[1].colors, frames[3].colors)
+
+
+SMOOTH_CASES = [CASES[i] for i in (0, 2, 3, 4, 5, 6, 7, 9, 11, 12, 13)]
+
+
+@pytest.mark.parametrize("case", SMOOTH_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items() if k != "orientations"))
+@pytest.mark.parametrize("grids", [(8, 4), (6, 3)], ids=["g8c4", "g6c3"])
+def test_random_small_atlases_with_smoothing(gpu_ctx, case, grids):
+    """Every orientation / precision / resolution / no-attribute case again with boundary detection + both smoothing stages
+    on (power-of-two and non-power-of-two cell edges): all streams, pre- and post-smoothing, equal the oracle."""
+    g = util.random_small_gof(**case)
+    util.crowd_into_one_region(g)              # patches overlap in 3D -> multi-patch cells -> the filters have work
+    g.params.geometry_smoothing = True
+    g.params.color_smoothing = True
+    g.params.grid_size, g.params.cgrid_size = grids
+    g.params.threshold_smoothing = 4          # low thresholds: plenty of points move / get recoloured on random content
+    g.params.threshold_color_smoothing = 2
+    g.params.threshold_color_variation = 200
+    g.params.threshold_color_difference = 200
+    got, want = both(gpu_ctx, g)
+    keys = [k for k in util.STREAMS if g.params.attribute_count or k not in ("colors", "colors16bit")]
+    util.assert_same(got, want, keys=keys, what=str(case))
+    pre = ["positions_presmooth", "boundary_type"] + (["colors16bit_presmooth"] if g.params.attribute_count else [])
+    util.assert_same(got, want, keys=pre, what=str(case) + " pre-smoothing")
+    assert got["smoothed_positions"] == want["smoothed_positions"] and got["smoothed_colors"] == want["smoothed_colors"]

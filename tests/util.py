@@ -95,3 +95,29 @@ def assert_same(gpu, orc, keys=STREAMS, what=""):
             bad = np.argwhere(a.astype(np.int64) != b.astype(np.int64))
             raise AssertionError(f"{what}: {k} differs at {len(bad)} entries, first {bad[0].tolist()}: "
                                  f"gpu {a[tuple(bad[0])]} oracle {b[tuple(bad[0])]}")
+
+
+def crowd_into_one_region(g):
+    """Rewrite a GOF in place so that its patches overlap in 3D (same axes, nearly the same offsets, slowly varying depth):
+    many voxel cells then hold points of several patches, which is what triggers the smoothing filters."""
+    for p in g.patches:
+        n = len(p)
+        p["u1"] = 100 + (np.arange(n) % 3)
+        p["v1"] = 100 + (np.arange(n) % 2)
+        p["lod_x"] = 1
+        p["lod_y"] = 1
+        p["d1"] = np.where(p["projection_mode"] == 0, 64, 1024 - 64 - 300)
+        p["normal_axis"], p["tangent_axis"], p["bitangent_axis"] = 0, 2, 1
+    F, _, H, W = g.geo.shape
+    yy, xx = np.mgrid[0:H, 0:W]
+    rng = np.random.RandomState(1234)
+    d0 = 100 + ((xx // 5 + yy // 7) % 9)
+    delta = np.where(rng.rand(F, H, W) < 0.4, 0, rng.randint(1, 5, (F, H, W)))
+    g.geo[:, 0] = (4 * d0 + rng.randint(0, 4, (F, H, W))).astype(np.uint16)
+    g.geo[:, 1] = (4 * (d0 + delta) + rng.randint(0, 4, (F, H, W))).astype(np.uint16)
+    if g.attr_y is not None:                   # smooth colours with a few outliers (so that the variance test passes)
+        base = (400 + 2 * (xx % 50)).astype(np.uint16)
+        g.attr_y[:, :] = base
+        g.attr_y[:, :, ::9, ::4] += 150
+        g.attr_u[:, :] = 500
+        g.attr_v[:, :] = 530
