@@ -100,6 +100,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this rank to the CPU cores next to its GPU (NVML affinity) before any pinned memory is allocated, so that the
+    staging buffers land on the GPU's own NUMA node.  Best effort: silently keeps the inherited affinity on failure."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = cpus & allowed
+        if target:
+            os.sched_setaffinity(0, target)
+        return sorted(target) if target else None
+    except Exception:
+        return None
+
+
 def cpu_reference_run(gof, frames_per_step: int, steps: int, warmup: int, threads: int):
     """The reference algorithm on host cores: oracle port (the Rust reference cannot be built here), single-threaded
     like the reference (README.md:7, src/lib.rs:113) unless --ref-threads asks for frame-parallel workers."""
@@ -180,6 +198,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the reconstruction path is CUDA-only (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    cpus = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -190,6 +209,7 @@ def main():
     cfg_desc.update({"atlas": f"{cfg.width}x{cfg.height}", "smoothing": smoothing, "maps": 2,
                      "occupancy_precision": cfg.occupancy_precision, "bitdepth_3d": cfg.bitdepth_3d,
                      "sharding": f"{world} rank(s), one GOF per rank per step, no collective",
+                     "host_cpus_of_rank0": (f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else "inherited"),
                      "l2": f"inputs {gof.input_bytes() / 1e6:.0f} MB/step > 126 MB L2 (no flush needed)"})
     ctx = codec.Context(devices=(local_rank,), two_pass_scan=args.two_pass)
     pinned = codec.pinned_copy_of(gof)
