@@ -311,47 +311,74 @@ __global__ void __launch_bounds__(256) block_to_patch_kernel(const UnpackArgs a,
 // After K2: the slots that own their canvas block (codec.rs:379), compacted per frame in slot order.  One CTA per frame.
 // The unpack kernel walks this list, so every warp of a tile has work and no plane is touched for a block that is
 // skipped.
+// exclusive prefix of `v` over the CTA (1024 threads) + the CTA total; s_w: 32 words of shared memory
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_w, uint32_t& total) {
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFull, incl, d);
+    if (lane >= (uint32_t)d) incl += t;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  uint32_t w = lane < (blockDim.x >> 5) ? s_w[lane] : 0u, wincl = w;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFull, wincl, d);
+    if (lane >= (uint32_t)d) wincl += t;
+  }
+  total = __shfl_sync(kFull, wincl, 31);
+  const uint32_t wbase = __shfl_sync(kFull, wincl - w, warp);
+  __syncthreads();
+  return wbase + incl - v;
+}
+
+constexpr int kPerThread = 8;   // slots per thread and pass of the per-frame kernels (all loads of a pass are in flight together)
+
 __global__ void __launch_bounds__(1024) compact_owned_kernel(const UnpackArgs a) {
   const uint32_t f = blockIdx.x;
   const uint32_t s0 = a.frame_tile_begin[f] * kWarpsPerTile, s1 = a.frame_tile_begin[f + 1] * kWarpsPerTile;
   __shared__ uint32_t s_w[32];
-  __shared__ uint32_t s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  for (uint32_t b = s0; b < s1; b += blockDim.x) {
-    const uint32_t slot = b + threadIdx.x;
-    bool own = false;
-    uint4 rec = make_uint4(kNoPatch, 0, 0, 0);
-    if (slot < s1) {
-      rec = __ldg(reinterpret_cast<const uint4*>(a.slot_rec + slot));
-      if (rec.x != kNoPatch) {
-        const uint32_t local_index = __ldg(&a.patches[rec.x].local_index);
-        const uint32_t bx = rec.z & 0xFFFFu, by = rec.z >> 16;
-        own = a.block_to_patch[(uint64_t)f * a.bw * a.bh + (uint64_t)by * a.bw + bx] == local_index + 1;
-      }
+  uint32_t carry = 0;
+  for (uint32_t b = s0; b < s1; b += 1024 * kPerThread) {
+    // thread t owns the kPerThread consecutive slots from b + t * kPerThread (slot order == thread order)
+    const uint32_t first = b + threadIdx.x * kPerThread;
+    uint4 rec[kPerThread];
+    uint32_t li[kPerThread];
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+      rec[i] = make_uint4(kNoPatch, 0, 0, 0);
+      if (first + i < s1) rec[i] = __ldg(reinterpret_cast<const uint4*>(a.slot_rec + first + i));
     }
-    const uint32_t m = __ballot_sync(kFull, own);
-    if (lane == 0) s_w[warp] = __popc(m);
-    __syncthreads();
-    uint32_t base = s_carry;
-    for (uint32_t w = 0; w < warp; ++w) base += s_w[w];
-    if (own) {
-      uint4* dst = reinterpret_cast<uint4*>(a.work + s0 + base + __popc(m & ((1u << lane) - 1u)));
-      dst[0] = rec;
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) li[i] = rec[i].x != kNoPatch ? __ldg(&a.patches[rec[i].x].local_index) : 0u;
+    uint32_t own = 0;
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+      if (rec[i].x == kNoPatch) continue;
+      const uint32_t bx = rec[i].z & 0xFFFFu, by = rec[i].z >> 16;
+      if (a.block_to_patch[(uint64_t)f * a.bw * a.bh + (uint64_t)by * a.bw + bx] == li[i] + 1) own |= 1u << i;
+    }
+    uint32_t total;
+    uint32_t pos = carry + cta_exclusive_scan(__popc(own), s_w, total);
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+      if (!((own >> i) & 1u)) continue;
+      uint4* dst = reinterpret_cast<uint4*>(a.work + s0 + pos);
+      dst[0] = rec[i];
       dst[1] = make_uint4(f, 0, 0, 0);
+      ++pos;
     }
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) s_carry = base + __popc(m);
-    __syncthreads();
+    carry += total;
   }
   // the unused tail of the frame's region: inactive records
-  for (uint32_t i = s0 + s_carry + threadIdx.x; i < s1; i += blockDim.x) {
+  for (uint32_t i = s0 + carry + threadIdx.x; i < s1; i += blockDim.x) {
     uint4* dst = reinterpret_cast<uint4*>(a.work + i);
     dst[0] = make_uint4(kNoPatch, 0, 0, 0);
     dst[1] = make_uint4(f, 0, 0, 0);
   }
-  if (threadIdx.x == 0) a.owned_count[f] = s_carry;
+  if (threadIdx.x == 0) a.owned_count[f] = carry;
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -670,29 +697,25 @@ __global__ void __launch_bounds__(1024) slot_scan_kernel(const UnpackArgs a) {
   const uint32_t f = blockIdx.x;
   const uint32_t s0 = a.frame_tile_begin[f] * kWarpsPerTile, n = a.owned_count[f];
   __shared__ uint32_t s_w[32];
-  __shared__ uint32_t s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  for (uint32_t b = 0; b < n; b += blockDim.x) {
-    const uint32_t i = b + threadIdx.x;
-    const uint32_t v = i < n ? a.work[s0 + i].total : 0u;
-    uint32_t incl = v;
+  uint32_t carry = 0;
+  for (uint32_t b = 0; b < n; b += 1024 * kPerThread) {
+    const uint32_t first = b + threadIdx.x * kPerThread;
+    uint32_t v[kPerThread], sum = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(kFull, incl, d);
-      if (lane >= (uint32_t)d) incl += t;
+    for (int i = 0; i < kPerThread; ++i) {
+      v[i] = first + i < n ? a.work[s0 + first + i].total : 0u;
+      sum += v[i];
     }
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    uint32_t wbase = s_carry;
-    for (uint32_t w = 0; w < warp; ++w) wbase += s_w[w];
-    if (i < n) a.work[s0 + i].base = wbase + incl - v;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) s_carry = wbase + incl;
-    __syncthreads();
+    uint32_t total;
+    uint32_t base = carry + cta_exclusive_scan(sum, s_w, total);
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+      if (first + i < n) a.work[s0 + first + i].base = base;
+      base += v[i];
+    }
+    carry += total;
   }
-  if (threadIdx.x == 0) a.frame_count[f] = s_carry;              // tile.total_number_of_regular_points, codec.rs:482
+  if (threadIdx.x == 0) a.frame_count[f] = carry;                // tile.total_number_of_regular_points, codec.rs:482
 }
 
 // one row of the 20x20 occupancy bitmap (block + 2-pixel margin): bit cc = pixel (x0 + sx*cc, y0 + sy*cc) is occupied, or
