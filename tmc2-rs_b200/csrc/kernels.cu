@@ -2,24 +2,22 @@
 //
 //   K2  block_to_patch_kernel     src/codec.rs:205-250   (atomicMax == "later patch overwrites", :242-244)
 //   K1  upsample_kernel           src/codec.rs:288-300   (materialised only for the stage API; fused otherwise)
-//   K3+K4 unpack_kernel           src/codec.rs:352-480 (unpack loop, order, dedup), :517-565 (generate_points),
+//   K3+K4 count_kernel / slot_scan_kernel / emit_kernel
+//                                 src/codec.rs:352-480 (unpack loop, order, dedup), :517-565 (generate_points),
 //                                 :569-658 (attribute fetch), :661-687 (YUV->RGB), src/decoder.rs:827-888 (patch maths)
-//       + K5 boundary type per pixel, K6/K7 cell statistics (own spec) in the smoothing instantiation
+//       + K5 boundary class per pixel, K6/K7 cell statistics (own spec) in the smoothing instantiation of emit_kernel
 //   K6/K7 smooth_finalize_kernel / smooth_filter_kernel / smooth_clear_kernel
 //                                 grid geometry + colour smoothing of the boundary points (own integer spec, DESIGN.md;
 //                                 the reference has only stubs: decoder.rs:291-299)
 //
 // Ordering.  The reference emits points in (patch, v0, u0, v1, u1, map) order.  A 16x16 patch block ("slot") that
 // owns its canvas block emits one contiguous run, so the output position of a run is an exclusive prefix sum of
-// per-slot counts in slot order.  unpack_kernel is ONE pass: a warp owns a slot, a CTA owns a tile of 8 consecutive
-// slots, and tiles publish / look back their prefix through `tile_status` (single-pass chained scan with decoupled
-// look-back, tile id == blockIdx.x, one scan domain per frame).  Nothing is read twice from HBM.
+// per-slot counts in slot order: count_kernel (points per owned slot), slot_scan_kernel (prefix per frame), emit_kernel
+// (a warp per slot writes its run at its final place).  Warps never talk to each other.
 //
-// Lane layout of a slot.  Lane l owns the 8 pixels of patch-local ranks 8l .. 8l+7 (row v1 = l/2, columns
-// u1 = 8(l&1) .. +7), whatever the patch orientation: the orientation only changes WHERE those pixels are loaded from
-// (an affine map with steps in {-1,0,+1}; a 16-byte vector per plane for Default, eight 2-byte loads per plane for the
-// transposed / mirrored cases).  A lane therefore emits one contiguous piece of the output run and the ordered
-// compaction is a plain warp scan of lane totals.
+// A block-aligned slot is loaded in CANVAS layout (lane = canvas row + half: one 16-byte vector per plane, whatever the
+// patch orientation), spilled into per-pixel tables in shared memory in PATCH raster order, and emitted by a
+// point-parallel loop (lane == point index mod 32) that writes aligned 32-bit words assembled from neighbouring lanes.
 //
 // All arithmetic on the bit-exact path is integer.  The colour conversion of the reference is IEEE f64; it is evaluated
 // here in 32.32 fixed point with a proven error margin, and re-done with the literal f64 sequence (__dmul_rn/__dadd_rn/
@@ -839,8 +837,7 @@ struct SmoothState {
   __device__ __forceinline__ void point(const UnpackArgs& a, bool valid, uint32_t g, uint32_t w0, uint32_t w1, uint32_t Y,
                                         uint32_t uv, uint32_t bt, bool has_attr) {
     const uint32_t X = w0 & 0xFFFFu, Yc = w0 >> 16, Z = w1 & 0xFFFFu;
-    // K6 statistics: geometry cells over ALL points.  The lanes of the window that fall into the same cell are found with
-    // match.any and summed with masked reductions; the lowest lane of each group issues the reductions.
+    // K6 statistics: geometry cells over ALL points (segmented scan over runs of equal cell, see below)
     if (a.sm.geo.on) {
       const GridDesc& G = a.sm.geo;
       uint32_t key = kCellEmpty, rx_ = 0, ry_ = 0, rz_ = 0;
@@ -882,11 +879,7 @@ struct SmoothState {
       const bool tail = key != kCellEmpty && (lane == 31u || ((heads >> 1) >> lane) & 1u);
       retire(a, G, q, nq_geo, pend_geo_old, pend_geo_cs);          // the reductions issued one window ago
       pend_geo_old = 1; pend_geo_cs = kCellEmpty;
-#if defined(TMC2_EXP) && (TMC2_EXP == 1 || TMC2_EXP == 3)
-      if (false) {
-#else
       if (tail) {
-#endif
         const uint32_t cs = cell_slot(G, fig, key, a.err);
         if (cs != kCellEmpty) {
           GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + cs;
@@ -902,11 +895,7 @@ struct SmoothState {
       const GridDesc& G = a.sm.col;
       retire(a, G, q + 64, nq_col, pend_col_old, pend_col_cs);
       pend_col_old = 1; pend_col_cs = kCellEmpty;
-#if defined(TMC2_EXP) && TMC2_EXP == 1
-      if (false) {
-#else
       if (bt == 2u) {
-#endif
         const uint32_t key = cell_key_of(G, X, Yc, Z);
         if (key != kCellEmpty) {
           const uint32_t cs = cell_slot(G, fig, key, a.err);
@@ -1212,9 +1201,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
       }
       if (a.out.btype) a.out.btype[gk] = (uint8_t)bt;
     }
-#if !defined(TMC2_EXP) || TMC2_EXP != 2
     if (kSmooth) S.point(a, valid, g, w0, w1, Y, uv, bt, has_attr);
-#endif
   }
   if (kSmooth) S.finish(a);
 }
