@@ -296,7 +296,7 @@ def main():
     t_unpack = statistics.mean(unpack_ms) if unpack_ms else float("nan")
     # the emit kernel is launched once per smoothing frame group (8 frames) -- once for the whole GOF without smoothing;
     # algorithmic bytes and device time are per launch (SURVEY.md 8d figure x the frames one launch processes)
-    group = int(os.environ.get("TMC2_SMOOTH_GROUP", "8")) if smoothing else frames
+    group = int(os.environ.get("TMC2_SMOOTH_GROUP", "32")) if smoothing else frames
     n_emit = max(1, -(-frames // max(group, 1)))
     achieved = alg_bytes / (t_unpack * 1e-3) / 1e9 if t_unpack and t_unpack > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "emit_kernel (fused occupancy upsample / unpack / attribute fetch / YUV->RGB; + boundary + cell statistics when smoothing)",

@@ -266,7 +266,7 @@ struct Batch {
   uint64_t geotab_slots = 0, coltab_slots = 0, geotab_frames = 0, coltab_frames = 0, blist_cap = 0;
   bool geotab_hashed = false, coltab_hashed = false;
   uint64_t geolog_cap = 0, collog_cap = 0;
-  uint32_t group_frames = 8;          // frames per smoothing group (cell tables stay L2-resident inside a group)
+  uint32_t group_frames = 32;         // frames per smoothing group (one group = no post-pass tails between groups; a GOF is <= 32 frames)
   uint32_t group_frames_eff = 8;      // after fitting the dense tables into the memory budget
   std::vector<cudaEvent_t> ev_grp;    // 2 per group: around the unpack launch
   PinBuf h_in, h_meta, h_small, h_out;
