@@ -244,6 +244,8 @@ struct Batch {
   cudaStream_t d2h_stream = nullptr;  // result copies
   cudaStream_t aux_stream = nullptr;  // smoothing post-passes of group g overlap the emit of group g+1
   std::vector<cudaEvent_t> ev_emit, ev_post;   // per group: emit done (main stream) / finalize+filter+clear done (aux)
+  cudaEvent_t ev_tables_clean = nullptr;       // single-group launches: the clear pass runs on aux, off the critical path
+  bool clear_pending = false;
   bool two_pass = false;
 
   // description of the loaded GOF slice
@@ -310,6 +312,7 @@ struct Batch {
     for (auto e : ev_post) cudaEventDestroy(e);
     ev_post.clear();
     if (aux_stream) cudaStreamDestroy(aux_stream), aux_stream = nullptr;
+    if (ev_tables_clean) cudaEventDestroy(ev_tables_clean), ev_tables_clean = nullptr;
     if (stream) cudaStreamDestroy(stream), stream = nullptr;
     if (d2h_stream) cudaStreamDestroy(d2h_stream), d2h_stream = nullptr;
   }
@@ -320,6 +323,7 @@ struct Batch {
     CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ev_tables_clean, cudaEventDisableTiming));
     for (auto& e : ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&ev_counts, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ev_inputs_free, cudaEventDisableTiming));
@@ -713,6 +717,7 @@ struct Batch {
         use_set(a.sm.geo, geo0, set, sizeof(GeoCell));
         use_set(a.sm.col, col0, set, sizeof(ColCell));
         if (gi >= 2) CU(cudaStreamWaitEvent(s, ev_post[gi - 2], 0));          // this table set has been cleared
+        if (clear_pending) { CU(cudaStreamWaitEvent(s, ev_tables_clean, 0)); clear_pending = false; }   // ... by the previous launch
         if (smoothing_geo) CU(cudaMemsetAsync(a.sm.geo.log_count, 0, (size_t)GF * 4, s));
         if (smoothing_col) CU(cudaMemsetAsync(a.sm.col.log_count, 0, (size_t)GF * 4, s));
         CU(cudaEventRecord(ev_grp[2 * gi], s));
@@ -725,15 +730,28 @@ struct Batch {
             CU(cudaMemcpyAsync(d_yuv_pre.as<uint8_t>() + (size_t)f0 * cap * 6, d_yuv.as<uint8_t>() + (size_t)f0 * cap * 6,
                                (size_t)(f1 - f0) * cap * 6, cudaMemcpyDeviceToDevice, s));
         }
-        // post-passes of this group on the auxiliary stream, while the main stream goes on with the next group's emit
-        CU(cudaEventRecord(ev_emit[gi], s));
-        CU(cudaStreamWaitEvent(aux_stream, ev_emit[gi], 0));
-        KL(launch_smooth_finalize(a, aux_stream));
-        KL(launch_smooth_filter(a, aux_stream));
-        KL(launch_smooth_clear(a, aux_stream));
-        CU(cudaEventRecord(ev_post[gi], aux_stream));
+        if (n_groups == 1) {
+          // one group: finalize + filter in line; the clear pass only matters to the NEXT launch, so it runs on the auxiliary
+          // stream under that launch's block-to-patch / count passes (which do not touch the tables)
+          KL(launch_smooth_finalize(a, s));
+          KL(launch_smooth_filter(a, s));
+          CU(cudaEventRecord(ev_emit[gi], s));
+          CU(cudaStreamWaitEvent(aux_stream, ev_emit[gi], 0));
+          KL(launch_smooth_clear(a, aux_stream));
+          CU(cudaEventRecord(ev_tables_clean, aux_stream));
+          clear_pending = true;
+        } else {
+          // post-passes of this group on the auxiliary stream, while the main stream goes on with the next group's emit
+          CU(cudaEventRecord(ev_emit[gi], s));
+          CU(cudaStreamWaitEvent(aux_stream, ev_emit[gi], 0));
+          KL(launch_smooth_finalize(a, aux_stream));
+          KL(launch_smooth_filter(a, aux_stream));
+          KL(launch_smooth_clear(a, aux_stream));
+          CU(cudaEventRecord(ev_post[gi], aux_stream));
+        }
       }
-      for (uint32_t gi = n_groups >= 2 ? n_groups - 2 : 0; gi < n_groups; ++gi) CU(cudaStreamWaitEvent(s, ev_post[gi], 0));
+      if (n_groups >= 2)
+        for (uint32_t gi = n_groups - 2; gi < n_groups; ++gi) CU(cudaStreamWaitEvent(s, ev_post[gi], 0));
     }
     CU(cudaEventRecord(ev[2], s));
     if (want & WANT_OCC_FULL) KL(launch_upsample(a, d_occ_full.as<uint8_t>(), s));
