@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "device_types.h"
 
@@ -1500,6 +1501,11 @@ __global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t* p, uint64_t n, 
 // launch wrappers
 // ----------------------------------------------------------------------------------------------------------------
 static inline int after_launch() { ++g_launches; return (int)cudaGetLastError(); }
+// grid.x of the per-frame post-pass kernels (grid.y = frames of the group): TMC2_POST_BLOCKS blocks per SM over all frames
+static unsigned post_blocks(unsigned frames) {
+  static const unsigned per_sm = [] { const char* e = getenv("TMC2_POST_BLOCKS"); return e ? (unsigned)atoi(e) : 16u; }();
+  return (148u * per_sm + frames - 1) / frames;
+}
 
 int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream) {
   if (n_slots == 0) return 0;
@@ -1550,21 +1556,21 @@ int launch_upsample(const UnpackArgs& a, uint8_t* occ_full, void* stream) {
 
 int launch_smooth_finalize(const UnpackArgs& a, void* stream) {
   if (a.sm.group_frames == 0) return 0;
-  const unsigned bx = (148u * 8u + a.sm.group_frames - 1) / a.sm.group_frames;
+  const unsigned bx = post_blocks(a.sm.group_frames);
   smooth_finalize_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
 }
 
 int launch_smooth_filter(const UnpackArgs& a, void* stream) {
   if (a.sm.group_frames == 0) return 0;
-  const unsigned bx = (148u * 8u + a.sm.group_frames - 1) / a.sm.group_frames;
+  const unsigned bx = post_blocks(a.sm.group_frames);
   smooth_filter_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
 }
 
 int launch_smooth_clear(const UnpackArgs& a, void* stream) {
   if (a.sm.group_frames == 0) return 0;
-  const unsigned bx = (148u * 8u + a.sm.group_frames - 1) / a.sm.group_frames;
+  const unsigned bx = post_blocks(a.sm.group_frames);
   smooth_clear_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
 }
