@@ -121,6 +121,10 @@ struct GridDesc {               // geometry of one voxel grid
   uint32_t magic;               // ceil(2^32 / g): x / g == umulhi(x, magic) for x < 65536
   int32_t  g_shift;             // log2(g) when g is a power of two, else -1
   uint32_t identity;            // 1: slot = dense cell index (table covers the whole grid)
+  // fast: dense table, g and w powers of two, w <= 256, g * w == 2^bitdepth.  Then cell coordinates come from shifts and
+  // masks on the packed position words (x | y << 16, z): oob_mask = bits that must be zero in every coordinate, replicated
+  // in both halves; cmask = (w - 1) in both halves; w_shift = log2(w).
+  uint32_t fast, w_shift, oob_mask, cmask;
   uint64_t slots;               // table slots per frame-in-group (power of two unless identity)
   void*    table;               // GeoCell / ColCell [frames_in_group][slots]
   uint32_t* keys;               // hashed tables only: [frames_in_group][slots], kCellEmpty = free

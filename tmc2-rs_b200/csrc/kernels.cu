@@ -803,11 +803,20 @@ struct SmoothState {
   uint32_t* q;                   // [2][64] queued table slots: geometry, colour
   uint32_t nq_geo, nq_col;       // warp-uniform fill of the two queues
   uint32_t pend_geo_old, pend_geo_cs, pend_col_old, pend_col_cs;   // issued in the previous window (cs == kCellEmpty: none)
+  bool pend_col_any;             // warp-uniform: the previous window issued colour reductions
+  GeoCell* geo_tab;              // this frame's tables
+  ColCell* col_tab;
 
   __device__ __forceinline__ void init(const UnpackArgs& a, uint32_t frame_, uint32_t fig_, uint32_t patch_, uint32_t lane_,
                                        uint32_t* queue) {
     frame = frame_; fig = fig_; patch = patch_; lane = lane_; lbase = 0; n_done = 0; q = queue; nq_geo = nq_col = 0;
-    pend_geo_old = pend_col_old = 1; pend_geo_cs = pend_col_cs = kCellEmpty;
+    pend_geo_old = pend_col_old = 1; pend_geo_cs = pend_col_cs = kCellEmpty; pend_col_any = false;
+    geo_tab = reinterpret_cast<GeoCell*>(a.sm.geo.table) + (uint64_t)fig * a.sm.geo.slots;
+    col_tab = reinterpret_cast<ColCell*>(a.sm.col.table) + (uint64_t)fig * a.sm.col.slots;
+  }
+  // dense slot of a cell from the packed key cx | cz << 8 | cy << 16 of a fast grid
+  static __device__ __forceinline__ uint32_t fast_slot(const GridDesc& G, uint32_t key) {
+    return (key & 0xFFu) | ((key >> 16) << G.w_shift) | (((key >> 8) & 0xFFu) << (2u * G.w_shift));
   }
   __device__ __forceinline__ void flush(const UnpackArgs& a, const GridDesc& G, uint32_t* queue, uint32_t& nq) {
     uint32_t base = 0;
@@ -841,8 +850,16 @@ struct SmoothState {
     // K6 statistics: geometry cells over ALL points (segmented scan over runs of equal cell, see below)
     if (a.sm.geo.on) {
       const GridDesc& G = a.sm.geo;
-      uint32_t key = kCellEmpty, rx_ = 0, ry_ = 0, rz_ = 0;
-      if (valid && X < G.th && Yc < G.th && Z < G.th) {
+      const bool fast8 = G.fast && G.g <= 8u;                       // packed single-word sums need 32 * (g - 1) < 256
+      uint32_t key = kCellEmpty, rx_ = 0, ry_ = 0, rz_ = 0, vfast = 0;
+      if (fast8) {
+        // cell coordinates straight from the packed position words (w1's upper half is zero)
+        if (valid && ((w0 | w1) & G.oob_mask) == 0u) {
+          const uint32_t m2 = (G.g - 1u) * 0x10001u;
+          key = ((w0 >> G.g_shift) & G.cmask) | ((w1 >> G.g_shift) << 8);          // cx | cz << 8 | cy << 16
+          vfast = __byte_perm(w0 & m2, (w1 & m2) | 0x100u, 0x4205);                // 1 | rel x << 8 | rel y << 16 | rel z << 24
+        }
+      } else if (valid && X < G.th && Yc < G.th && Z < G.th) {
         if (G.g_shift >= 0) {
           const uint32_t m = G.g - 1u;
           key = (X >> G.g_shift) | ((Yc >> G.g_shift) << 10) | ((Z >> G.g_shift) << 20);
@@ -858,14 +875,14 @@ struct SmoothState {
       // gets several reductions).
       const uint32_t kprev = __shfl_up_sync(kFull, key, 1);
       const uint32_t heads = __ballot_sync(kFull, lane == 0 || kprev != key);
-      const uint32_t seg = 31u - (uint32_t)__clz(heads & (0xFFFFFFFFu >> (31u - lane)));     // first lane of this lane's run
+      const uint32_t dist = lane - (31u - (uint32_t)__clz(heads & (0xFFFFFFFFu >> (31u - lane))));   // lanes since the run began
       uint32_t cnt, sx, sy, sz;
       if (G.g <= 8u) {                      // one packed word: count | three sums of at most 32 * 7 (8 bits each)
-        uint32_t v = key != kCellEmpty ? (1u | (rx_ << 8) | (ry_ << 16) | (rz_ << 24)) : 0u;
+        uint32_t v = fast8 ? vfast : (key != kCellEmpty ? (1u | (rx_ << 8) | (ry_ << 16) | (rz_ << 24)) : 0u);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           const uint32_t t = __shfl_up_sync(kFull, v, d);
-          if (lane >= seg + (uint32_t)d) v += t;
+          if (dist >= (uint32_t)d) v += t;
         }
         cnt = v & 0xFFu; sx = (v >> 8) & 0xFFu; sy = (v >> 16) & 0xFFu; sz = v >> 24;
       } else {                              // sums of at most 32 * 255
@@ -873,7 +890,7 @@ struct SmoothState {
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           const uint32_t t0 = __shfl_up_sync(kFull, v0, d), t1 = __shfl_up_sync(kFull, v1, d);
-          if (lane >= seg + (uint32_t)d) { v0 += t0; v1 += t1; }
+          if (dist >= (uint32_t)d) { v0 += t0; v1 += t1; }
         }
         cnt = v0 & 0xFFFFu; sx = v0 >> 16; sy = v1 & 0xFFFFu; sz = v1 >> 16;
       }
@@ -881,9 +898,9 @@ struct SmoothState {
       retire(a, G, q, nq_geo, pend_geo_old, pend_geo_cs);          // the reductions issued one window ago
       pend_geo_old = 1; pend_geo_cs = kCellEmpty;
       if (tail) {
-        const uint32_t cs = cell_slot(G, fig, key, a.err);
+        const uint32_t cs = fast8 ? fast_slot(G, key) : cell_slot(G, fig, key, a.err);
         if (cs != kCellEmpty) {
-          GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + cs;
+          GeoCell* c = geo_tab + cs;
           pend_geo_cs = cs;
           pend_geo_old = atomicCAS(&c->first1, 0u, patch + 1u);   // 0: first touch; another patch + 1: multi-patch cell
           atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
@@ -894,20 +911,26 @@ struct SmoothState {
     // K7 statistics: colour cells over the type-2 (second ring) points
     if (a.sm.col.on && has_attr) {
       const GridDesc& G = a.sm.col;
-      retire(a, G, q + 64, nq_col, pend_col_old, pend_col_cs);
-      pend_col_old = 1; pend_col_cs = kCellEmpty;
+      if (pend_col_any) {
+        retire(a, G, q + 64, nq_col, pend_col_old, pend_col_cs);
+        pend_col_old = 1; pend_col_cs = kCellEmpty;
+      }
+      pend_col_any = __any_sync(kFull, bt == 2u);
       if (bt == 2u) {
-        const uint32_t key = cell_key_of(G, X, Yc, Z);
-        if (key != kCellEmpty) {
-          const uint32_t cs = cell_slot(G, fig, key, a.err);
-          if (cs != kCellEmpty) {
-            ColCell* c = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots + cs;
-            pend_col_cs = cs;
-            pend_col_old = atomicCAS(&c->first1, 0u, patch + 1u);
-            atomicAdd(&c->cnt_sy, 1ull | ((unsigned long long)Y << 24));
-            atomicAdd(&c->su_sv, (unsigned long long)(uv & 0xFFFFu) | ((unsigned long long)(uv >> 16) << 32));
-            atomicAdd(&c->sy2, (unsigned long long)Y * Y);
-          }
+        uint32_t cs = kCellEmpty;
+        if (G.fast) {
+          if (((w0 | w1) & G.oob_mask) == 0u) cs = fast_slot(G, ((w0 >> G.g_shift) & G.cmask) | ((w1 >> G.g_shift) << 8));
+        } else {
+          const uint32_t key = cell_key_of(G, X, Yc, Z);
+          if (key != kCellEmpty) cs = cell_slot(G, fig, key, a.err);
+        }
+        if (cs != kCellEmpty) {
+          ColCell* c = col_tab + cs;
+          pend_col_cs = cs;
+          pend_col_old = atomicCAS(&c->first1, 0u, patch + 1u);
+          atomicAdd(&c->cnt_sy, 1ull | ((unsigned long long)Y << 24));
+          atomicAdd(&c->su_sv, (unsigned long long)(uv & 0xFFFFu) | ((unsigned long long)(uv >> 16) << 32));
+          atomicAdd(&c->sy2, (unsigned long long)Y * Y);
         }
       }
     }

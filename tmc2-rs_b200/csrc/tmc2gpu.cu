@@ -639,6 +639,16 @@ struct Batch {
         for (int sft = 0; sft < 16; ++sft) if ((1u << sft) == g) G.g_shift = sft;
         G.slots = slots; G.table = table; G.keys = keys;
         G.identity = hashed ? 0 : 1;
+        G.fast = 0; G.w_shift = 0; G.oob_mask = 0; G.cmask = 0;
+        {
+          int wl = -1;
+          for (int sft = 0; sft <= 8; ++sft) if ((1u << sft) == G.w) wl = sft;
+          if (!hashed && G.g_shift >= 0 && wl >= 0 && G.th <= 65536u) {
+            G.fast = 1; G.w_shift = (uint32_t)wl;
+            G.oob_mask = (0xFFFFu & ~(G.th - 1u)) * 0x10001u;
+            G.cmask = (G.w - 1u) * 0x10001u;
+          }
+        }
         G.log = log; G.log_count = log_count; G.log_cap = log_cap;
       };
       grid(a.sm.geo, smoothing_geo, params.grid_size, d_geotab.p, d_geokeys.as<uint32_t>(), geotab_slots, geotab_hashed,
