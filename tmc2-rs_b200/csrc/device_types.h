@@ -172,7 +172,7 @@ constexpr uint32_t kOffSrc = kOffTerm + 2048;                    // [512] u16: o
 constexpr uint32_t kOffCnt = kOffSrc + 1024;                     // [256] u8: points of the pixel (0..2) | boundary class << 2
 constexpr uint32_t kOffBmp = kOffCnt + 256;                      // [32] u32: 20x20 occupancy bitmap rows (canvas axes)
 constexpr uint32_t kOffLogQ = kOffBmp + 128;                     // [2][64] u32: first-touched cells waiting for the log
-constexpr uint32_t kWarpSmemBytes = kOffLogQ + 512;              // 6016
+constexpr uint32_t kWarpSmemBytes = kOffLogQ + 512 + 256;        // + [2][32] claimed-cell memo
 
 // launch wrappers (kernels.cu); every one enqueues on `stream` and returns the cudaGetLastError() code
 int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream);

@@ -804,6 +804,7 @@ struct SmoothState {
   uint32_t nq_geo, nq_col;       // warp-uniform fill of the two queues
   uint32_t pend_geo_old, pend_geo_cs, pend_col_old, pend_col_cs;   // issued in the previous window (cs == kCellEmpty: none)
   bool pend_col_any;             // warp-uniform: the previous window issued colour reductions
+  uint32_t* memo;                // [2][32] cells this warp has already claimed for its slot (direct-mapped, geometry / colour)
   GeoCell* geo_tab;              // this frame's tables
   ColCell* col_tab;
 
@@ -811,8 +812,19 @@ struct SmoothState {
                                        uint32_t* queue) {
     frame = frame_; fig = fig_; patch = patch_; lane = lane_; lbase = 0; n_done = 0; q = queue; nq_geo = nq_col = 0;
     pend_geo_old = pend_col_old = 1; pend_geo_cs = pend_col_cs = kCellEmpty; pend_col_any = false;
+    memo = queue + 128;
+    memo[lane] = kCellEmpty; memo[32 + lane] = kCellEmpty;
+    __syncwarp();
     geo_tab = reinterpret_cast<GeoCell*>(a.sm.geo.table) + (uint64_t)fig * a.sm.geo.slots;
     col_tab = reinterpret_cast<ColCell*>(a.sm.col.table) + (uint64_t)fig * a.sm.col.slots;
+  }
+  // true when this warp claimed `cs` before (then the claim is skipped); remembers it otherwise.  Two lanes of one window may
+  // both miss on the same cell: the claim is then simply issued twice.
+  __device__ __forceinline__ bool claimed_before(uint32_t* m, uint32_t cs) const {
+    const uint32_t e = (cs ^ (cs >> 7) ^ (cs >> 14)) & 31u;
+    if (m[e] == cs) return true;
+    m[e] = cs;
+    return false;
   }
   // dense slot of a cell from the packed key cx | cz << 8 | cy << 16 of a fast grid
   static __device__ __forceinline__ uint32_t fast_slot(const GridDesc& G, uint32_t key) {
@@ -901,8 +913,10 @@ struct SmoothState {
         const uint32_t cs = fast8 ? fast_slot(G, key) : cell_slot(G, fig, key, a.err);
         if (cs != kCellEmpty) {
           GeoCell* c = geo_tab + cs;
-          pend_geo_cs = cs;
-          pend_geo_old = atomicCAS(&c->first1, 0u, patch + 1u);   // 0: first touch; another patch + 1: multi-patch cell
+          if (!claimed_before(memo, cs)) {
+            pend_geo_cs = cs;
+            pend_geo_old = atomicCAS(&c->first1, 0u, patch + 1u);   // 0: first touch; another patch + 1: multi-patch cell
+          }
           atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
           atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
         }
@@ -926,8 +940,10 @@ struct SmoothState {
         }
         if (cs != kCellEmpty) {
           ColCell* c = col_tab + cs;
-          pend_col_cs = cs;
-          pend_col_old = atomicCAS(&c->first1, 0u, patch + 1u);
+          if (!claimed_before(memo + 32, cs)) {
+            pend_col_cs = cs;
+            pend_col_old = atomicCAS(&c->first1, 0u, patch + 1u);
+          }
           atomicAdd(&c->cnt_sy, 1ull | ((unsigned long long)Y << 24));
           atomicAdd(&c->su_sv, (unsigned long long)(uv & 0xFFFFu) | ((unsigned long long)(uv >> 16) << 32));
           atomicAdd(&c->sy2, (unsigned long long)Y * Y);
