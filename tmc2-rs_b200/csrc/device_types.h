@@ -138,6 +138,8 @@ struct SmoothArgs {
   BoundaryEntry* blist;         // [F][blist_cap]
   uint32_t* blist_count;        // [F]
   uint64_t blist_cap;
+  uint32_t* slist;              // [F][blist_cap] survivors of the probe pass: list index | grids-to-filter << 30
+  uint32_t* slist_count;        // [F]
   uint32_t group_first_frame;   // tables are indexed by (frame - group_first_frame)
   uint32_t group_frames;
   uint32_t thr_geo;             // threshold_smoothing

@@ -1465,45 +1465,59 @@ __device__ __forceinline__ uint32_t filter_apply(const UnpackArgs& a, uint32_t f
   return result;
 }
 
-// Two phases per CTA and batch of 256 list entries.  PROBE (every entry, cheap): fetch the 16 cell summaries, keep the
-// entry if some neighbouring cell of a grid is multi-patch -- most boundary points have none and are done.  APPLY (the
-// survivors, compacted through shared memory so that the expensive blend runs in full warps).
-__global__ void __launch_bounds__(256) smooth_filter_kernel(const __grid_constant__ UnpackArgs a) {
-  __shared__ uint32_t s_q[256];
-  __shared__ uint32_t s_n;
+// The filter is two kernels.  PROBE (every type-1 boundary point, light in registers so that many loads are in flight): fetch
+// the first word of the 16 neighbouring cell summaries and keep the point if some cell of a grid is multi-patch -- most
+// boundary points have none and are done.  APPLY (the survivors): the expensive blend, in full warps.
+__device__ __forceinline__ uint32_t probe_multi(const GridDesc& G, uint32_t fig, size_t cell_bytes, const uint32_t p[3]) {
+  Nbhd N;
+  if (!neighbourhood(G, p, N)) return 0u;
+  const uint8_t* tab = static_cast<const uint8_t*>(G.table) + (uint64_t)fig * G.slots * cell_bytes;
+  uint32_t any = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (N.key[j] == kCellEmpty) continue;
+    const uint32_t cs = cell_find(G, fig, N.key[j]);
+    if (cs != kCellEmpty) any |= __ldg(reinterpret_cast<const uint32_t*>(tab + (uint64_t)cs * cell_bytes));
+  }
+  return any & kCellMulti;
+}
+
+__global__ void __launch_bounds__(256) smooth_probe_kernel(const __grid_constant__ UnpackArgs a) {
   const uint32_t fig = blockIdx.y;
   const uint32_t f = a.sm.group_first_frame + fig;
   const uint32_t n = min((uint64_t)a.sm.blist_count[f], a.sm.blist_cap);
   const BoundaryEntry* L = a.sm.blist + (uint64_t)f * a.sm.blist_cap;
-  uint32_t moved = 0, recol = 0;
-  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    const uint32_t i = base + threadIdx.x;
+  const uint32_t lane = lane_id();
+  const uint32_t n_round = (n + 31u) & ~31u;                                     // whole warps stay in the loop together
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    uint32_t want = 0;
     if (i < n) {
       const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&L[i]));
       const uint32_t p[3] = {raw.y & 0xFFFFu, raw.y >> 16, raw.z & 0xFFFFu};
-      Nbhd Ng, Nc;
-      const bool do_geo = a.sm.geo.on && neighbourhood(a.sm.geo, p, Ng);
-      const bool do_col = a.sm.col.on && a.has_attr && neighbourhood(a.sm.col, p, Nc);   // colour cells: pre-smoothing position
-      uint4 cg[8], cc[8];
-      load_summaries(a.sm.geo, fig, sizeof(GeoCell), do_geo, Ng, cg);
-      load_summaries(a.sm.col, fig, sizeof(ColCell), do_col, Nc, cc);
-      uint32_t og = 0, oc = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { og |= cg[j].x; oc |= cc[j].x; }
-      const uint32_t want = ((og & kCellMulti) ? 1u : 0u) | ((oc & kCellMulti) ? 2u : 0u);
-      if (want) s_q[atomicAdd(&s_n, 1u)] = i | (want << 30);
+      if (a.sm.geo.on && probe_multi(a.sm.geo, fig, sizeof(GeoCell), p)) want |= 1u;
+      if (a.sm.col.on && a.has_attr && probe_multi(a.sm.col, fig, sizeof(ColCell), p)) want |= 2u;   // pre-smoothing position
     }
-    __syncthreads();
-    const uint32_t m = s_n;
-    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) {
-      const uint32_t e = s_q[j];
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&L[e & 0x3FFFFFFFu]));
-      const uint32_t r = filter_apply(a, fig, f, raw, e >> 30);
-      moved += r & 1u; recol += r >> 1;
-    }
-    __syncthreads();
+    const uint32_t wm = __ballot_sync(kFull, want != 0u);
+    if (wm == 0u) continue;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&a.sm.slist_count[f], (uint32_t)__popc(wm));
+    base = __shfl_sync(kFull, base, 0);
+    if (want) a.sm.slist[(uint64_t)f * a.sm.blist_cap + base + __popc(wm & ((1u << lane) - 1u))] = i | (want << 30);
+  }
+}
+
+__global__ void __launch_bounds__(256) smooth_apply_kernel(const __grid_constant__ UnpackArgs a) {
+  const uint32_t fig = blockIdx.y;
+  const uint32_t f = a.sm.group_first_frame + fig;
+  const uint32_t m = min((uint64_t)a.sm.slist_count[f], a.sm.blist_cap);
+  const BoundaryEntry* L = a.sm.blist + (uint64_t)f * a.sm.blist_cap;
+  const uint32_t* S = a.sm.slist + (uint64_t)f * a.sm.blist_cap;
+  uint32_t moved = 0, recol = 0;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+    const uint32_t e = S[j];
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&L[e & 0x3FFFFFFFu]));
+    const uint32_t r = filter_apply(a, fig, f, raw, e >> 30);
+    moved += r & 1u; recol += r >> 1;
   }
   moved = __reduce_add_sync(kFull, moved);
   recol = __reduce_add_sync(kFull, recol);
@@ -1603,7 +1617,10 @@ int launch_smooth_finalize(const UnpackArgs& a, void* stream) {
 int launch_smooth_filter(const UnpackArgs& a, void* stream) {
   if (a.sm.group_frames == 0) return 0;
   const unsigned bx = post_blocks(a.sm.group_frames);
-  smooth_filter_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
+  smooth_probe_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
+  int e = after_launch();
+  if (e) return e;
+  smooth_apply_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
 }
 

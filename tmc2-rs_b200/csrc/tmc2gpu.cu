@@ -264,7 +264,7 @@ struct Batch {
   DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_count, d_err, d_work, d_owned_count;
   DevBuf d_pos, d_rgb, d_yuv, d_part, d_pix, d_bt, d_occ_full, d_pos_pre, d_yuv_pre;
   DevBuf d_geotab, d_coltab, d_geokeys, d_colkeys, d_geolog, d_collog, d_geolog_count, d_collog_count, d_changed, d_blist,
-      d_blist_count;
+      d_blist_count, d_slist, d_slist_count;
   uint64_t geotab_slots = 0, coltab_slots = 0, geotab_frames = 0, coltab_frames = 0, blist_cap = 0;
   bool geotab_hashed = false, coltab_hashed = false;
   uint64_t geolog_cap = 0, collog_cap = 0;
@@ -297,7 +297,7 @@ struct Batch {
                       &d_owned_count, &d_pos,
                       &d_rgb, &d_yuv, &d_part, &d_pix, &d_bt, &d_occ_full, &d_pos_pre, &d_yuv_pre, &d_geotab, &d_coltab,
                       &d_geokeys, &d_colkeys, &d_geolog, &d_collog, &d_geolog_count, &d_collog_count, &d_changed, &d_blist,
-                      &d_blist_count})
+                      &d_blist_count, &d_slist, &d_slist_count})
       b->release();
     for (PinBuf* b : {&h_in, &h_meta, &h_small, &h_out}) b->release();
     for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -433,9 +433,11 @@ struct Batch {
       // boundary-point lists (one per frame) and their counters
       if (blist_cap != cap || d_blist.cap < (size_t)F * cap * sizeof(BoundaryEntry)) {
         CU(d_blist.ensure((size_t)F * cap * sizeof(BoundaryEntry)));
+        CU(d_slist.ensure((size_t)F * cap * 4));
         blist_cap = cap;
       }
       CU(d_blist_count.ensure(std::max<size_t>((size_t)F * 4, 4)));
+      CU(d_slist_count.ensure(std::max<size_t>((size_t)F * 4, 4)));
       // Cell tables: dense (direct-indexed, no probing) when the whole grid fits the per-table budget for at least one
       // frame, hashed (separate key array) otherwise.  The group size shrinks until the dense tables fit.
       const uint64_t kTableBudget = 16ull << 30;
@@ -656,6 +658,7 @@ struct Batch {
       grid(a.sm.col, smoothing_col, params.cgrid_size, d_coltab.p, d_colkeys.as<uint32_t>(), coltab_slots, coltab_hashed,
            d_collog.as<uint32_t>(), d_collog_count.as<uint32_t>(), collog_cap);
       a.sm.blist = d_blist.as<BoundaryEntry>(); a.sm.blist_count = d_blist_count.as<uint32_t>(); a.sm.blist_cap = blist_cap;
+      a.sm.slist = d_slist.as<uint32_t>(); a.sm.slist_count = d_slist_count.as<uint32_t>();
       const uint32_t sc = params.attribute_bitdepth > 8 ? (1u << (params.attribute_bitdepth - 8)) : 1u;
       a.sm.thr_geo = params.threshold_smoothing;
       a.sm.thr_col_smooth = params.threshold_color_smoothing * sc;
@@ -691,7 +694,10 @@ struct Batch {
     const bool smooth = smoothing_geo || smoothing_col;
     const bool dbg = (want & WANT_DEBUG) != 0;
     CU(cudaMemsetAsync(d_changed.p, 0, std::max<size_t>((size_t)F * 16, 16), s));
-    if (smooth) CU(cudaMemsetAsync(d_blist_count.p, 0, std::max<size_t>((size_t)F * 4, 4), s));
+    if (smooth) {
+      CU(cudaMemsetAsync(d_blist_count.p, 0, std::max<size_t>((size_t)F * 4, 4), s));
+      CU(cudaMemsetAsync(d_slist_count.p, 0, std::max<size_t>((size_t)F * 4, 4), s));
+    }
     // unpack = count (points per owned slot) -> slot scan (run starts per frame, frame totals) -> emit
     CU(cudaEventRecord(ev[6], s));
     KL(launch_count(a, 0, n_tiles, s));
