@@ -95,7 +95,6 @@ struct Outputs {                // any pointer may be null = stream not wanted
 // a compare-and-swap (0 -> patch + 1); whoever finds another patch's claim stores 1 into `multi` (idempotent).
 // The finalize pass (once per touched cell, before the filter) turns the sums into Q8 means.
 constexpr uint32_t kCellEmpty = 0xFFFFFFFFu;      // free slot of a hashed table's key array
-constexpr uint32_t kCellFinal = 0x80000000u;      // summary flag: finalized
 struct GeoCell {     // 32 B = one DRAM sector
   uint32_t first1;              // patch index + 1 of the first toucher, 0 = untouched
   uint32_t multi;               // 1 = touched by more than one patch
@@ -185,7 +184,6 @@ int launch_count(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, vo
 int launch_slot_scan(const UnpackArgs& a, void* stream);
 int launch_emit(const UnpackArgs& a, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream);
 int launch_upsample(const UnpackArgs& a, uint8_t* occ_full /*[F][H][W]*/, void* stream);
-int launch_smooth_finalize(const UnpackArgs& a, void* stream); // sums -> means for every cell the group touched
 int launch_smooth_filter(const UnpackArgs& a, void* stream);   // boundary points of the current frame group
 int launch_smooth_clear(const UnpackArgs& a, void* stream);    // reset touched cells (+ keys) of the group
 int launch_yuv_to_rgb_flat(const uint16_t* yuv, uint8_t* rgb, uint64_t n, void* stream);

@@ -6,7 +6,7 @@
 //                                 src/codec.rs:352-480 (unpack loop, order, dedup), :517-565 (generate_points),
 //                                 :569-658 (attribute fetch), :661-687 (YUV->RGB), src/decoder.rs:827-888 (patch maths)
 //       + K5 boundary class per pixel, K6/K7 cell statistics (own spec) in the smoothing instantiation of emit_kernel
-//   K6/K7 smooth_finalize_kernel / smooth_filter_kernel / smooth_clear_kernel
+//   K6/K7 smooth_probe_kernel / smooth_apply_kernel / smooth_clear_kernel
 //                                 grid geometry + colour smoothing of the boundary points (own integer spec, DESIGN.md;
 //                                 the reference has only stubs: decoder.rs:291-299)
 //
@@ -1267,57 +1267,42 @@ __device__ __forceinline__ uint32_t mean_q8_u32(uint32_t s, uint32_t cnt) {     
   const unsigned long long num = 256ull * s + (cnt >> 1);
   return num < (1ull << 32) ? (uint32_t)num / cnt : (uint32_t)(num / cnt);
 }
-// After finalize the first 16 bytes of a touched cell are its SUMMARY (the accumulators are not needed any more):
-//   x = kCellFinal | kCellMulti (touched by more than one patch) | kCellUsable (colour: luminance variance test passed)
+// SUMMARY of a cell, computed on the fly from its accumulators by whoever needs it (only the few boundary points that
+// survive the probe pass do):
+//   x = kCellMulti (touched by more than one patch) | kCellUsable (colour: luminance variance test passed)
 //       | point count (24 bits; a frame has < 2^24 points)
 //   geometry: y = mean x | mean y << 16, z = mean z   (Q8, relative to the cell origin, < 256 * g <= 65536)
 //   colour:   y = mean Y, z = mean U, w = mean V      (Q8)
 constexpr uint32_t kCellMulti = 0x40000000u, kCellUsable = 0x20000000u, kCellCount = 0x00FFFFFFu;
-__global__ void __launch_bounds__(256) smooth_finalize_kernel(const __grid_constant__ UnpackArgs a) {
-  const uint32_t fig = blockIdx.y;
-  if (a.sm.geo.on) {
-    const GridDesc& G = a.sm.geo;
-    const uint32_t n = (uint32_t)min((uint64_t)G.log_count[fig], G.log_cap);
-    const uint32_t* log = G.log + (uint64_t)fig * G.log_cap;
-    GeoCell* tab = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-      uint4* c = reinterpret_cast<uint4*>(tab + log[i]);                    // every cell is logged exactly once
-      const uint4 v0 = c[0], v1 = c[1];                                     // first1, multi, count, sx ; sy, sz, -, -
-      const uint32_t cnt = v0.z;
-      if (cnt == 0) continue;
-      const uint32_t multi = v0.y != 0u ? kCellMulti : 0u;
-      const uint32_t mx = mean_q8_u32(v0.w, cnt), my = mean_q8_u32(v1.x, cnt), mz = mean_q8_u32(v1.y, cnt);
-      c[0] = make_uint4(kCellFinal | multi | (cnt & kCellCount), mx | (my << 16), mz, 0u);
-    }
+__device__ __forceinline__ uint4 geo_summary(const uint4& v0, const uint4& v1) {   // first1, multi, count, sx ; sy, sz, -, -
+  const uint32_t cnt = v0.z;
+  if (cnt == 0) return make_uint4(0, 0, 0, 0);
+  const uint32_t multi = v0.y != 0u ? kCellMulti : 0u;
+  const uint32_t mx = mean_q8_u32(v0.w, cnt), my = mean_q8_u32(v1.x, cnt), mz = mean_q8_u32(v1.y, cnt);
+  return make_uint4(multi | (cnt & kCellCount), mx | (my << 16), mz, 0u);
+}
+__device__ __forceinline__ uint4 col_summary(const uint4& v0, const uint4& v1, uint32_t thr_col_var, int* err) {
+  // first1, multi, cnt_sy (lo, hi) ; su, sv, sy2 (lo, hi)
+  const unsigned long long w0 = (unsigned long long)v0.z | ((unsigned long long)v0.w << 32);
+  const unsigned long long sy2 = (unsigned long long)v1.z | ((unsigned long long)v1.w << 32);
+  const unsigned long long cnt = w0 & 0xFFFFFFull, sy = w0 >> 24, su = v1.x, sv = v1.y;
+  if (cnt == 0) return make_uint4(0, 0, 0, 0);
+  if (cnt > 65536ull) atomicExch(err, 6);       // the packed U / V sums are only exact up to 65536 points per cell
+  const uint32_t multi = v0.y != 0u ? kCellMulti : 0u;
+  uint32_t my, mu, mv;
+  if (sy < (1ull << 24) && cnt < (1ull << 24)) {                          // the usual case fits 32-bit division
+    const uint32_t c32 = (uint32_t)cnt;
+    my = mean_q8_u32((uint32_t)sy, c32); mu = mean_q8_u32((uint32_t)su, c32); mv = mean_q8_u32((uint32_t)sv, c32);
+  } else {
+    my = (uint32_t)((256ull * sy + cnt / 2) / cnt); mu = (uint32_t)((256ull * su + cnt / 2) / cnt);
+    mv = (uint32_t)((256ull * sv + cnt / 2) / cnt);
   }
-  if (a.sm.col.on) {
-    const GridDesc& G = a.sm.col;
-    const uint32_t n = (uint32_t)min((uint64_t)G.log_count[fig], G.log_cap);
-    const uint32_t* log = G.log + (uint64_t)fig * G.log_cap;
-    ColCell* tab = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-      ColCell* c = tab + log[i];                                            // every cell is logged exactly once
-      const uint32_t multi = c->multi != 0u ? kCellMulti : 0u;
-      const unsigned long long w0 = c->cnt_sy, w1 = c->su_sv, sy2 = c->sy2;
-      const unsigned long long cnt = w0 & 0xFFFFFFull, sy = w0 >> 24, su = w1 & 0xFFFFFFFFull, sv = w1 >> 32;
-      if (cnt == 0) continue;
-      if (cnt > 65536ull) atomicExch(a.err, 6);     // the packed U / V sums are only exact up to 65536 points per cell
-      uint32_t my, mu, mv;
-      if (sy < (1ull << 24) && cnt < (1ull << 24)) {                        // the usual case fits 32-bit division
-        const uint32_t c32 = (uint32_t)cnt;
-        my = mean_q8_u32((uint32_t)sy, c32); mu = mean_q8_u32((uint32_t)su, c32); mv = mean_q8_u32((uint32_t)sv, c32);
-      } else {
-        my = (uint32_t)((256ull * sy + cnt / 2) / cnt); mu = (uint32_t)((256ull * su + cnt / 2) / cnt);
-        mv = (uint32_t)((256ull * sv + cnt / 2) / cnt);
-      }
-      // luminance variation: var(Y) = (cnt*sumY2 - sumY^2)/cnt^2 must not exceed t_var^2
-      const unsigned __int128 num = (unsigned __int128)cnt * sy2 - (unsigned __int128)sy * sy;
-      const unsigned long long tv = (unsigned long long)a.sm.thr_col_var * cnt;
-      const unsigned __int128 lim = (unsigned __int128)tv * tv;
-      const uint32_t usable = num > lim ? 0u : kCellUsable;
-      *reinterpret_cast<uint4*>(c) = make_uint4(kCellFinal | multi | usable | ((uint32_t)cnt & kCellCount), my, mu, mv);
-    }
-  }
+  // luminance variation: var(Y) = (cnt*sumY2 - sumY^2)/cnt^2 must not exceed t_var^2
+  const unsigned __int128 num = (unsigned __int128)cnt * sy2 - (unsigned __int128)sy * sy;
+  const unsigned long long tv = (unsigned long long)thr_col_var * cnt;
+  const unsigned __int128 lim = (unsigned __int128)tv * tv;
+  const uint32_t usable = num > lim ? 0u : kCellUsable;
+  return make_uint4(multi | usable | ((uint32_t)cnt & kCellCount), my, mu, mv);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1353,18 +1338,24 @@ __device__ __forceinline__ bool neighbourhood(const GridDesc& G, const uint32_t 
 __device__ __forceinline__ unsigned long long div_w3(unsigned long long x, const GridDesc& G, uint32_t w3) {
   return G.g_shift >= 0 ? (x >> (3 * (G.g_shift + 1))) : (x / w3);
 }
-// the summaries of the 8 cells of a neighbourhood: eight independent 16-byte loads (all in flight together)
-__device__ __forceinline__ void load_summaries(const GridDesc& G, uint32_t fig, size_t cell_bytes, bool on, const Nbhd& N,
-                                               uint4 c[8]) {
-  const uint8_t* tab = static_cast<const uint8_t*>(G.table) + (uint64_t)fig * G.slots * cell_bytes;
+// the summaries of the 8 cells of a neighbourhood, from the cells' accumulators (16 independent 16-byte loads in flight)
+template <bool kColour>
+__device__ __forceinline__ void load_summaries(const UnpackArgs& a, const GridDesc& G, uint32_t fig, const Nbhd& N, uint4 c[8]) {
+  const uint8_t* tab = static_cast<const uint8_t*>(G.table) + (uint64_t)fig * G.slots * 32u;      // 32-byte cells
+  uint4 r0[8], r1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    c[j] = make_uint4(0, 0, 0, 0);
-    if (on && N.key[j] != kCellEmpty) {
+    r0[j] = make_uint4(0, 0, 0, 0); r1[j] = make_uint4(0, 0, 0, 0);
+    if (N.key[j] != kCellEmpty) {
       const uint32_t cs = cell_find(G, fig, N.key[j]);
-      if (cs != kCellEmpty) c[j] = __ldg(reinterpret_cast<const uint4*>(tab + (uint64_t)cs * cell_bytes));
+      if (cs != kCellEmpty) {
+        r0[j] = __ldg(reinterpret_cast<const uint4*>(tab + (uint64_t)cs * 32u));
+        r1[j] = __ldg(reinterpret_cast<const uint4*>(tab + (uint64_t)cs * 32u) + 1);
+      }
     }
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c[j] = kColour ? col_summary(r0[j], r1[j], a.sm.thr_col_var, a.err) : geo_summary(r0[j], r1[j]);
 }
 
 // One type-1 boundary point against the two grids.  `want` bit 0: geometry, bit 1: colour (the grids whose neighbourhood
@@ -1380,7 +1371,7 @@ __device__ __forceinline__ uint32_t filter_apply(const UnpackArgs& a, uint32_t f
     Nbhd Ng;
     neighbourhood(G, p, Ng);
     uint4 cg[8];
-    load_summaries(G, fig, sizeof(GeoCell), true, Ng, cg);
+    load_summaries<false>(a, G, fig, Ng, cg);
     unsigned long long C[3] = {0, 0, 0}, cntw = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1431,7 +1422,7 @@ __device__ __forceinline__ uint32_t filter_apply(const UnpackArgs& a, uint32_t f
     Nbhd Nc;
     neighbourhood(G, p, Nc);
     uint4 cc[8];
-    load_summaries(G, fig, sizeof(ColCell), true, Nc, cc);
+    load_summaries<true>(a, G, fig, Nc, cc);
     unsigned long long C[3] = {0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1466,7 +1457,7 @@ __device__ __forceinline__ uint32_t filter_apply(const UnpackArgs& a, uint32_t f
 }
 
 // The filter is two kernels.  PROBE (every type-1 boundary point, light in registers so that many loads are in flight): fetch
-// the first word of the 16 neighbouring cell summaries and keep the point if some cell of a grid is multi-patch -- most
+// the multi-patch flag of the 16 neighbouring cells and keep the point if some cell of a grid has it set -- most
 // boundary points have none and are done.  APPLY (the survivors): the expensive blend, in full warps.
 __device__ __forceinline__ uint32_t probe_multi(const GridDesc& G, uint32_t fig, size_t cell_bytes, const uint32_t p[3]) {
   Nbhd N;
@@ -1477,9 +1468,9 @@ __device__ __forceinline__ uint32_t probe_multi(const GridDesc& G, uint32_t fig,
   for (int j = 0; j < 8; ++j) {
     if (N.key[j] == kCellEmpty) continue;
     const uint32_t cs = cell_find(G, fig, N.key[j]);
-    if (cs != kCellEmpty) any |= __ldg(reinterpret_cast<const uint32_t*>(tab + (uint64_t)cs * cell_bytes));
+    if (cs != kCellEmpty) any |= __ldg(reinterpret_cast<const uint32_t*>(tab + (uint64_t)cs * cell_bytes) + 1);   // cell.multi
   }
-  return any & kCellMulti;
+  return any;
 }
 
 __global__ void __launch_bounds__(256) smooth_probe_kernel(const __grid_constant__ UnpackArgs a) {
@@ -1604,13 +1595,6 @@ int launch_emit(const UnpackArgs& a, bool smooth, uint32_t tile_begin, uint32_t 
 
 int launch_upsample(const UnpackArgs& a, uint8_t* occ_full, void* stream) {
   upsample_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(a, occ_full);
-  return after_launch();
-}
-
-int launch_smooth_finalize(const UnpackArgs& a, void* stream) {
-  if (a.sm.group_frames == 0) return 0;
-  const unsigned bx = post_blocks(a.sm.group_frames);
-  smooth_finalize_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
 }
 

@@ -749,7 +749,6 @@ struct Batch {
         if (n_groups == 1) {
           // one group: finalize + filter in line; the clear pass only matters to the NEXT launch, so it runs on the auxiliary
           // stream under that launch's block-to-patch / count passes (which do not touch the tables)
-          KL(launch_smooth_finalize(a, s));
           KL(launch_smooth_filter(a, s));
           CU(cudaEventRecord(ev_emit[gi], s));
           CU(cudaStreamWaitEvent(aux_stream, ev_emit[gi], 0));
@@ -760,7 +759,6 @@ struct Batch {
           // post-passes of this group on the auxiliary stream, while the main stream goes on with the next group's emit
           CU(cudaEventRecord(ev_emit[gi], s));
           CU(cudaStreamWaitEvent(aux_stream, ev_emit[gi], 0));
-          KL(launch_smooth_finalize(a, aux_stream));
           KL(launch_smooth_filter(a, aux_stream));
           KL(launch_smooth_clear(a, aux_stream));
           CU(cudaEventRecord(ev_post[gi], aux_stream));
