@@ -1342,20 +1342,25 @@ __device__ __forceinline__ unsigned long long div_w3(unsigned long long x, const
 template <bool kColour>
 __device__ __forceinline__ void load_summaries(const UnpackArgs& a, const GridDesc& G, uint32_t fig, const Nbhd& N, uint4 c[8]) {
   const uint8_t* tab = static_cast<const uint8_t*>(G.table) + (uint64_t)fig * G.slots * 32u;      // 32-byte cells
-  uint4 r0[8], r1[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    r0[j] = make_uint4(0, 0, 0, 0); r1[j] = make_uint4(0, 0, 0, 0);
-    if (N.key[j] != kCellEmpty) {
-      const uint32_t cs = cell_find(G, fig, N.key[j]);
-      if (cs != kCellEmpty) {
-        r0[j] = __ldg(reinterpret_cast<const uint4*>(tab + (uint64_t)cs * 32u));
-        r1[j] = __ldg(reinterpret_cast<const uint4*>(tab + (uint64_t)cs * 32u) + 1);
+  for (int h = 0; h < 2; ++h) {                                      // four cells (eight loads) in flight at a time
+    uint4 r0[4], r1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = 4 * h + i;
+      r0[i] = make_uint4(0, 0, 0, 0); r1[i] = make_uint4(0, 0, 0, 0);
+      if (N.key[j] != kCellEmpty) {
+        const uint32_t cs = cell_find(G, fig, N.key[j]);
+        if (cs != kCellEmpty) {
+          r0[i] = __ldg(reinterpret_cast<const uint4*>(tab + (uint64_t)cs * 32u));
+          r1[i] = __ldg(reinterpret_cast<const uint4*>(tab + (uint64_t)cs * 32u) + 1);
+        }
       }
     }
-  }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) c[j] = kColour ? col_summary(r0[j], r1[j], a.sm.thr_col_var, a.err) : geo_summary(r0[j], r1[j]);
+    for (int i = 0; i < 4; ++i)
+      c[4 * h + i] = kColour ? col_summary(r0[i], r1[i], a.sm.thr_col_var, a.err) : geo_summary(r0[i], r1[i]);
+  }
 }
 
 // One type-1 boundary point against the two grids.  `want` bit 0: geometry, bit 1: colour (the grids whose neighbourhood
@@ -1497,7 +1502,7 @@ __global__ void __launch_bounds__(256) smooth_probe_kernel(const __grid_constant
   }
 }
 
-__global__ void __launch_bounds__(256) smooth_apply_kernel(const __grid_constant__ UnpackArgs a) {
+__global__ void __launch_bounds__(128) smooth_apply_kernel(const __grid_constant__ UnpackArgs a) {
   const uint32_t fig = blockIdx.y;
   const uint32_t f = a.sm.group_first_frame + fig;
   const uint32_t m = min((uint64_t)a.sm.slist_count[f], a.sm.blist_cap);
@@ -1604,7 +1609,7 @@ int launch_smooth_filter(const UnpackArgs& a, void* stream) {
   smooth_probe_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
   int e = after_launch();
   if (e) return e;
-  smooth_apply_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
+  smooth_apply_kernel<<<dim3(bx, a.sm.group_frames), 128, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
 }
 
