@@ -130,6 +130,8 @@ struct GridDesc {               // geometry of one voxel grid
   uint32_t* log;                // [frames_in_group][log_cap] table slots touched in that frame, each exactly once
   uint32_t* log_count;          // [frames_in_group]
   uint64_t log_cap;
+  uint32_t* mbits;              // [frames_in_group][mwords] one bit per table slot: the cell is multi-patch (what the probe reads)
+  uint64_t mwords;
 };
 
 struct SmoothArgs {

@@ -230,8 +230,7 @@ __device__ __forceinline__ uint64_t hash_slot0(uint32_t key, const GridDesc& G) 
 }
 // table slot of cell `key` (cx | cy<<10 | cz<<20) in the table of frame-in-group `fig`: the dense index, or find-or-claim
 // in the key array of a hashed table.  kCellEmpty on failure (table full: cannot happen, slots >= 2 * points).
-__device__ __forceinline__ uint32_t cell_slot(const GridDesc& G, uint32_t fig, uint32_t key, int* err) {
-  if (G.identity) return (key & 1023u) + G.w * (((key >> 10) & 1023u) + G.w * (key >> 20));
+__device__ __noinline__ uint32_t cell_slot_hashed(const GridDesc& G, uint32_t fig, uint32_t key, int* err) {
   uint32_t* keys = G.keys + (uint64_t)fig * G.slots;
   uint64_t i = hash_slot0(key, G);
   for (uint64_t probe = 0; probe < G.slots; ++probe) {
@@ -243,8 +242,11 @@ __device__ __forceinline__ uint32_t cell_slot(const GridDesc& G, uint32_t fig, u
   atomicExch(err, 11);
   return kCellEmpty;
 }
-__device__ __forceinline__ uint32_t cell_find(const GridDesc& G, uint32_t fig, uint32_t key) {
+__device__ __forceinline__ uint32_t cell_slot(const GridDesc& G, uint32_t fig, uint32_t key, int* err) {
   if (G.identity) return (key & 1023u) + G.w * (((key >> 10) & 1023u) + G.w * (key >> 20));
+  return cell_slot_hashed(G, fig, key, err);          // rare (grids too large for a dense table): kept out of the hot loops
+}
+__device__ __noinline__ uint32_t cell_find_hashed(const GridDesc& G, uint32_t fig, uint32_t key) {
   const uint32_t* keys = G.keys + (uint64_t)fig * G.slots;
   uint64_t i = hash_slot0(key, G);
   for (uint64_t probe = 0; probe < G.slots; ++probe) {
@@ -254,6 +256,10 @@ __device__ __forceinline__ uint32_t cell_find(const GridDesc& G, uint32_t fig, u
     i = (i + 1) & (G.slots - 1);
   }
   return kCellEmpty;
+}
+__device__ __forceinline__ uint32_t cell_find(const GridDesc& G, uint32_t fig, uint32_t key) {
+  if (G.identity) return (key & 1023u) + G.w * (((key >> 10) & 1023u) + G.w * (key >> 20));
+  return cell_find_hashed(G, fig, key);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -531,13 +537,19 @@ __device__ __noinline__ uint32_t generic_slot_count(const UnpackArgs& a, uint32_
   return total;
 }
 
+// a second patch reached the cell: flag it in the cell itself (idempotent plain store) and in the frame's bitmap
+__device__ __forceinline__ void mark_multi(const GridDesc& G, uint32_t fig, uint32_t cs) {
+  reinterpret_cast<volatile uint32_t*>(static_cast<uint8_t*>(G.table) + ((uint64_t)fig * G.slots + cs) * 32u)[1] = 1u;
+  atomicOr(&G.mbits[(uint64_t)fig * G.mwords + (cs >> 5)], 1u << (cs & 31u));
+}
+
 // ---- smoothing: accumulate into a cell; the first toucher of a cell appends it to the frame's log -----------------------
 // returns true when this call was the first to touch the cell (pmax1 was 0 == untouched)
 __device__ __forceinline__ bool geo_cell_add_first(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
                                                    uint32_t sx, uint32_t sy, uint32_t sz) {
   GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + slot;
   const uint32_t old = atomicCAS(&c->first1, 0u, patch + 1u);
-  if (old != 0u && old != patch + 1u) *reinterpret_cast<volatile uint32_t*>(&c->multi) = 1u;
+  if (old != 0u && old != patch + 1u) mark_multi(G, fig, slot);
   atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
   atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
   return old == 0u;
@@ -546,7 +558,7 @@ __device__ __forceinline__ bool col_cell_add_first(const GridDesc& G, uint32_t f
                                                    uint32_t sy, uint32_t su, uint32_t sv, unsigned long long sy2) {
   ColCell* c = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots + slot;
   const uint32_t old = atomicCAS(&c->first1, 0u, patch + 1u);
-  if (old != 0u && old != patch + 1u) *reinterpret_cast<volatile uint32_t*>(&c->multi) = 1u;
+  if (old != 0u && old != patch + 1u) mark_multi(G, fig, slot);
   atomicAdd(&c->cnt_sy, (unsigned long long)cnt | ((unsigned long long)sy << 24));
   atomicAdd(&c->su_sv, (unsigned long long)su | ((unsigned long long)sv << 32));
   atomicAdd(&c->sy2, sy2);
@@ -794,6 +806,21 @@ __device__ __forceinline__ void boundary_masks(const UnpackArgs& a, const WorkRe
 
 __device__ __forceinline__ void stg_u32(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
 
+// append a warp's queue of first-touched table slots to the frame's log (one atomicAdd); out of line: rare
+__device__ __noinline__ void flush_queue(uint32_t* log, uint32_t* log_count, uint64_t log_cap, const uint32_t* queue, uint32_t nq,
+                                         int* err) {
+  const uint32_t lane = lane_id();
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(log_count, nq);
+  base = __shfl_sync(kFull, base, 0);
+  __syncwarp();
+  for (uint32_t i = lane; i < nq; i += 32) {
+    if ((uint64_t)base + i < log_cap) log[base + i] = queue[i];
+    else atomicExch(err, 11);
+  }
+  __syncwarp();
+}
+
 // ---- smoothing work of the emit loop (K6 / K7 statistics + boundary list), one call per 32-point window -----------------
 // Latency discipline: a window ISSUES its cell reductions; whether it was the first toucher of a cell (the returned old
 // value of the atomicMax) is looked at one window later, so the round trip overlaps the next window's work.  First-touched
@@ -807,6 +834,8 @@ struct SmoothState {
   uint32_t* memo;                // [2][32] cells this warp has already claimed for its slot (direct-mapped, geometry / colour)
   GeoCell* geo_tab;              // this frame's tables
   ColCell* col_tab;
+  uint32_t* geo_mb;              // this frame's multi-patch bitmaps
+  uint32_t* col_mb;
 
   __device__ __forceinline__ void init(const UnpackArgs& a, uint32_t frame_, uint32_t fig_, uint32_t patch_, uint32_t lane_,
                                        uint32_t* queue) {
@@ -817,6 +846,8 @@ struct SmoothState {
     __syncwarp();
     geo_tab = reinterpret_cast<GeoCell*>(a.sm.geo.table) + (uint64_t)fig * a.sm.geo.slots;
     col_tab = reinterpret_cast<ColCell*>(a.sm.col.table) + (uint64_t)fig * a.sm.col.slots;
+    geo_mb = a.sm.geo.mbits + (uint64_t)fig * a.sm.geo.mwords;
+    col_mb = a.sm.col.mbits + (uint64_t)fig * a.sm.col.mwords;
   }
   // true when this warp claimed `cs` before (then the claim is skipped); remembers it otherwise.  Two lanes of one window may
   // both miss on the same cell: the claim is then simply issued twice.
@@ -831,23 +862,18 @@ struct SmoothState {
     return (key & 0xFFu) | ((key >> 16) << G.w_shift) | (((key >> 8) & 0xFFu) << (2u * G.w_shift));
   }
   __device__ __forceinline__ void flush(const UnpackArgs& a, const GridDesc& G, uint32_t* queue, uint32_t& nq) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&G.log_count[fig], nq);
-    base = __shfl_sync(kFull, base, 0);
-    __syncwarp();
-    for (uint32_t i = lane; i < nq; i += 32) {
-      if ((uint64_t)base + i < G.log_cap) G.log[(uint64_t)fig * G.log_cap + base + i] = queue[i];
-      else atomicExch(a.err, 11);
-    }
-    __syncwarp();
+    flush_queue(G.log + (uint64_t)fig * G.log_cap, &G.log_count[fig], G.log_cap, queue, nq, a.err);
     nq = 0;
   }
   // retire the reductions issued one window ago: queue the cells this warp touched first
-  __device__ __forceinline__ void retire(const UnpackArgs& a, const GridDesc& G, uint32_t* queue, uint32_t& nq, uint32_t old,
-                                         uint32_t cs) {
-    // the cell had been claimed by another patch: it is a multi-patch cell (idempotent plain store, 32-byte cells)
-    if (cs != kCellEmpty && old != 0u && old != patch + 1u)
-      reinterpret_cast<volatile uint32_t*>(static_cast<uint8_t*>(G.table) + ((uint64_t)fig * G.slots + cs) * 32u)[1] = 1u;
+  __device__ __forceinline__ void retire(const UnpackArgs& a, const GridDesc& G, void* tab, uint32_t* mb, uint32_t* queue,
+                                         uint32_t& nq, uint32_t old, uint32_t cs) {
+    // the cell had been claimed by another patch: it is a multi-patch cell (idempotent plain store into the 32-byte cell +
+    // its bit in the frame's bitmap)
+    if (cs != kCellEmpty && old != 0u && old != patch + 1u) {
+      reinterpret_cast<volatile uint32_t*>(static_cast<uint8_t*>(tab) + (size_t)cs * 32u)[1] = 1u;
+      atomicOr(mb + (cs >> 5), 1u << (cs & 31u));
+    }
     const bool first = cs != kCellEmpty && old == 0u;
     const uint32_t fm = __ballot_sync(kFull, first);
     if (fm == 0) return;
@@ -907,7 +933,7 @@ struct SmoothState {
         cnt = v0 & 0xFFFFu; sx = v0 >> 16; sy = v1 & 0xFFFFu; sz = v1 >> 16;
       }
       const bool tail = key != kCellEmpty && (lane == 31u || ((heads >> 1) >> lane) & 1u);
-      retire(a, G, q, nq_geo, pend_geo_old, pend_geo_cs);          // the reductions issued one window ago
+      retire(a, G, geo_tab, geo_mb, q, nq_geo, pend_geo_old, pend_geo_cs);          // the reductions issued one window ago
       pend_geo_old = 1; pend_geo_cs = kCellEmpty;
       if (tail) {
         const uint32_t cs = fast8 ? fast_slot(G, key) : cell_slot(G, fig, key, a.err);
@@ -926,7 +952,7 @@ struct SmoothState {
     if (a.sm.col.on && has_attr) {
       const GridDesc& G = a.sm.col;
       if (pend_col_any) {
-        retire(a, G, q + 64, nq_col, pend_col_old, pend_col_cs);
+        retire(a, G, col_tab, col_mb, q + 64, nq_col, pend_col_old, pend_col_cs);
         pend_col_old = 1; pend_col_cs = kCellEmpty;
       }
       pend_col_any = __any_sync(kFull, bt == 2u);
@@ -965,11 +991,11 @@ struct SmoothState {
 
   __device__ __forceinline__ void finish(const UnpackArgs& a) {
     if (a.sm.geo.on) {
-      retire(a, a.sm.geo, q, nq_geo, pend_geo_old, pend_geo_cs);
+      retire(a, a.sm.geo, geo_tab, geo_mb, q, nq_geo, pend_geo_old, pend_geo_cs);
       if (nq_geo) flush(a, a.sm.geo, q, nq_geo);
     }
     if (a.sm.col.on) {
-      retire(a, a.sm.col, q + 64, nq_col, pend_col_old, pend_col_cs);
+      retire(a, a.sm.col, col_tab, col_mb, q + 64, nq_col, pend_col_old, pend_col_cs);
       if (nq_col) flush(a, a.sm.col, q + 64, nq_col);
     }
   }
@@ -1462,18 +1488,18 @@ __device__ __forceinline__ uint32_t filter_apply(const UnpackArgs& a, uint32_t f
 }
 
 // The filter is two kernels.  PROBE (every type-1 boundary point, light in registers so that many loads are in flight): fetch
-// the multi-patch flag of the 16 neighbouring cells and keep the point if some cell of a grid has it set -- most
+// the multi-patch bits of the 16 neighbouring cells (a bitmap, 32 cells per word) and keep the point if some cell of a grid has it set -- most
 // boundary points have none and are done.  APPLY (the survivors): the expensive blend, in full warps.
-__device__ __forceinline__ uint32_t probe_multi(const GridDesc& G, uint32_t fig, size_t cell_bytes, const uint32_t p[3]) {
+__device__ __forceinline__ uint32_t probe_multi(const GridDesc& G, uint32_t fig, const uint32_t p[3]) {
   Nbhd N;
   if (!neighbourhood(G, p, N)) return 0u;
-  const uint8_t* tab = static_cast<const uint8_t*>(G.table) + (uint64_t)fig * G.slots * cell_bytes;
+  const uint32_t* bits = G.mbits + (uint64_t)fig * G.mwords;         // one bit per table slot: 32 cells per word
   uint32_t any = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (N.key[j] == kCellEmpty) continue;
     const uint32_t cs = cell_find(G, fig, N.key[j]);
-    if (cs != kCellEmpty) any |= __ldg(reinterpret_cast<const uint32_t*>(tab + (uint64_t)cs * cell_bytes) + 1);   // cell.multi
+    if (cs != kCellEmpty) any |= (__ldg(bits + (cs >> 5)) >> (cs & 31u)) & 1u;
   }
   return any;
 }
@@ -1490,8 +1516,8 @@ __global__ void __launch_bounds__(256) smooth_probe_kernel(const __grid_constant
     if (i < n) {
       const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&L[i]));
       const uint32_t p[3] = {raw.y & 0xFFFFu, raw.y >> 16, raw.z & 0xFFFFu};
-      if (a.sm.geo.on && probe_multi(a.sm.geo, fig, sizeof(GeoCell), p)) want |= 1u;
-      if (a.sm.col.on && a.has_attr && probe_multi(a.sm.col, fig, sizeof(ColCell), p)) want |= 2u;   // pre-smoothing position
+      if (a.sm.geo.on && probe_multi(a.sm.geo, fig, p)) want |= 1u;
+      if (a.sm.col.on && a.has_attr && probe_multi(a.sm.col, fig, p)) want |= 2u;   // pre-smoothing position
     }
     const uint32_t wm = __ballot_sync(kFull, want != 0u);
     if (wm == 0u) continue;
@@ -1535,6 +1561,9 @@ __global__ void __launch_bounds__(256) smooth_clear_kernel(const __grid_constant
     uint4* tab = reinterpret_cast<uint4*>(G.table) + ((uint64_t)fig * G.slots) * 2;      // 32-byte cells
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       const uint32_t cs = log[i];
+      // a multi-patch cell also has its bit in the frame's bitmap: the whole word goes (its other bits belong to cells of
+      // the same log)
+      if (reinterpret_cast<const uint32_t*>(tab + (uint64_t)cs * 2)[1] != 0u) G.mbits[(uint64_t)fig * G.mwords + (cs >> 5)] = 0u;
       tab[(uint64_t)cs * 2] = make_uint4(0, 0, 0, 0);
       tab[(uint64_t)cs * 2 + 1] = make_uint4(0, 0, 0, 0);
       if (!G.identity) G.keys[(uint64_t)fig * G.slots + cs] = kCellEmpty;

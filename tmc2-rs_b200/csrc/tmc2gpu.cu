@@ -264,7 +264,7 @@ struct Batch {
   DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_count, d_err, d_work, d_owned_count;
   DevBuf d_pos, d_rgb, d_yuv, d_part, d_pix, d_bt, d_occ_full, d_pos_pre, d_yuv_pre;
   DevBuf d_geotab, d_coltab, d_geokeys, d_colkeys, d_geolog, d_collog, d_geolog_count, d_collog_count, d_changed, d_blist,
-      d_blist_count, d_slist, d_slist_count;
+      d_blist_count, d_slist, d_slist_count, d_geombits, d_colmbits;
   uint64_t geotab_slots = 0, coltab_slots = 0, geotab_frames = 0, coltab_frames = 0, blist_cap = 0;
   bool geotab_hashed = false, coltab_hashed = false;
   uint64_t geolog_cap = 0, collog_cap = 0;
@@ -297,7 +297,7 @@ struct Batch {
                       &d_owned_count, &d_pos,
                       &d_rgb, &d_yuv, &d_part, &d_pix, &d_bt, &d_occ_full, &d_pos_pre, &d_yuv_pre, &d_geotab, &d_coltab,
                       &d_geokeys, &d_colkeys, &d_geolog, &d_collog, &d_geolog_count, &d_collog_count, &d_changed, &d_blist,
-                      &d_blist_count, &d_slist, &d_slist_count})
+                      &d_blist_count, &d_slist, &d_slist_count, &d_geombits, &d_colmbits})
       b->release();
     for (PinBuf* b : {&h_in, &h_meta, &h_small, &h_out}) b->release();
     for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -322,7 +322,12 @@ struct Batch {
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+    {
+      // the auxiliary stream only runs small clean-up kernels under the next launch: let them jump the queue
+      int lo = 0, hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU(cudaStreamCreateWithPriority(&aux_stream, cudaStreamNonBlocking, hi));
+    }
     CU(cudaEventCreateWithFlags(&ev_tables_clean, cudaEventDisableTiming));
     for (auto& e : ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&ev_counts, cudaEventDisableTiming));
@@ -467,14 +472,16 @@ struct Batch {
         hashed = force_hash || cells * cell_bytes > kTableBudget;
         return hashed ? pow2_at_least(2 * cap) : cells;
       };
-      auto setup = [&](bool on, uint32_t g, size_t cell_bytes, DevBuf& tab, DevBuf& keys, uint64_t& slots_now, uint64_t& frames_now,
-                       bool& hashed_now) -> tmc2_status {
+      auto setup = [&](bool on, uint32_t g, size_t cell_bytes, DevBuf& tab, DevBuf& keys, DevBuf& mbits, uint64_t& slots_now,
+                       uint64_t& frames_now, bool& hashed_now) -> tmc2_status {
         if (!on) return TMC2_OK;
         bool hashed = false;
         const uint64_t slots = table_slots(g, cell_bytes, hashed);
         if (slots != slots_now || TF > frames_now || hashed != hashed_now) {
           CU(tab.ensure((size_t)TF * slots * cell_bytes));
           CU(cudaMemsetAsync(tab.p, 0, (size_t)TF * slots * cell_bytes, stream));     // all-zero == empty cell
+          CU(mbits.ensure((size_t)TF * ((slots + 31) / 32) * 4));
+          CU(cudaMemsetAsync(mbits.p, 0, (size_t)TF * ((slots + 31) / 32) * 4, stream));
           if (hashed) {
             CU(keys.ensure((size_t)TF * slots * 4));
             KL(launch_fill_u32(keys.as<uint32_t>(), (uint64_t)TF * slots, kCellEmpty, stream));
@@ -483,8 +490,8 @@ struct Batch {
         }
         return TMC2_OK;
       };
-      if (setup(smoothing_geo, params.grid_size, sizeof(GeoCell), d_geotab, d_geokeys, geotab_slots, geotab_frames, geotab_hashed)) return err.st;
-      if (setup(smoothing_col, params.cgrid_size, sizeof(ColCell), d_coltab, d_colkeys, coltab_slots, coltab_frames, coltab_hashed)) return err.st;
+      if (setup(smoothing_geo, params.grid_size, sizeof(GeoCell), d_geotab, d_geokeys, d_geombits, geotab_slots, geotab_frames, geotab_hashed)) return err.st;
+      if (setup(smoothing_col, params.cgrid_size, sizeof(ColCell), d_coltab, d_colkeys, d_colmbits, coltab_slots, coltab_frames, coltab_hashed)) return err.st;
       // per-frame logs of the touched table slots (each cell once, by its first toucher; walked by finalize and clear)
       geolog_cap = std::min<uint64_t>(cap, geotab_slots ? geotab_slots : cap);
       collog_cap = std::min<uint64_t>(cap, coltab_slots ? coltab_slots : cap);
@@ -632,7 +639,7 @@ struct Batch {
     if (smooth) {
       const uint32_t maxs = 1u << params.geometry_bitdepth_3d;
       auto grid = [&](GridDesc& G, bool on, uint32_t g, void* table, uint32_t* keys, uint64_t slots, bool hashed, uint32_t* log,
-                      uint32_t* log_count, uint64_t log_cap) {
+                      uint32_t* log_count, uint64_t log_cap, uint32_t* mbits) {
         G.on = on ? 1 : 0;
         if (!on) return;
         G.g = g; G.w = (maxs + g - 1) / g; G.disth = std::max(g / 2, 1u); G.th = g * G.w;
@@ -652,11 +659,12 @@ struct Batch {
           }
         }
         G.log = log; G.log_count = log_count; G.log_cap = log_cap;
+        G.mbits = mbits; G.mwords = (slots + 31) / 32;
       };
       grid(a.sm.geo, smoothing_geo, params.grid_size, d_geotab.p, d_geokeys.as<uint32_t>(), geotab_slots, geotab_hashed,
-           d_geolog.as<uint32_t>(), d_geolog_count.as<uint32_t>(), geolog_cap);
+           d_geolog.as<uint32_t>(), d_geolog_count.as<uint32_t>(), geolog_cap, d_geombits.as<uint32_t>());
       grid(a.sm.col, smoothing_col, params.cgrid_size, d_coltab.p, d_colkeys.as<uint32_t>(), coltab_slots, coltab_hashed,
-           d_collog.as<uint32_t>(), d_collog_count.as<uint32_t>(), collog_cap);
+           d_collog.as<uint32_t>(), d_collog_count.as<uint32_t>(), collog_cap, d_colmbits.as<uint32_t>());
       a.sm.blist = d_blist.as<BoundaryEntry>(); a.sm.blist_count = d_blist_count.as<uint32_t>(); a.sm.blist_cap = blist_cap;
       a.sm.slist = d_slist.as<uint32_t>(); a.sm.slist_count = d_slist_count.as<uint32_t>();
       const uint32_t sc = params.attribute_bitdepth > 8 ? (1u << (params.attribute_bitdepth - 8)) : 1u;
@@ -726,6 +734,7 @@ struct Batch {
         G.keys = G0.keys ? G0.keys + (size_t)set * GF * G0.slots : nullptr;
         G.log = G0.log + (size_t)set * GF * G0.log_cap;
         G.log_count = G0.log_count + (size_t)set * GF;
+        G.mbits = G0.mbits + (size_t)set * GF * G0.mwords;
       };
       for (uint32_t gi = 0; gi < n_groups; ++gi) {
         const uint32_t f0 = gi * GF, f1 = std::min(F, f0 + GF), set = gi & 1u;
