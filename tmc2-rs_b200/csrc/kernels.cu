@@ -882,13 +882,16 @@ struct SmoothState {
     if (nq > 32u) flush(a, G, queue, nq);
   }
 
+  // kFast: both grids are known (at launch) to be dense power-of-two grids with cell edge <= 8 (geometry): the generic
+  // branches drop out of the instantiation, which keeps the hot loop small
+  template <bool kFast>
   __device__ __forceinline__ void point(const UnpackArgs& a, bool valid, uint32_t g, uint32_t w0, uint32_t w1, uint32_t Y,
                                         uint32_t uv, uint32_t bt, bool has_attr) {
     const uint32_t X = w0 & 0xFFFFu, Yc = w0 >> 16, Z = w1 & 0xFFFFu;
     // K6 statistics: geometry cells over ALL points (segmented scan over runs of equal cell, see below)
     if (a.sm.geo.on) {
       const GridDesc& G = a.sm.geo;
-      const bool fast8 = G.fast && G.g <= 8u;                       // packed single-word sums need 32 * (g - 1) < 256
+      const bool fast8 = kFast || (G.fast && G.g <= 8u);            // packed single-word sums need 32 * (g - 1) < 256
       uint32_t key = kCellEmpty, rx_ = 0, ry_ = 0, rz_ = 0, vfast = 0;
       if (fast8) {
         // cell coordinates straight from the packed position words (w1's upper half is zero)
@@ -915,7 +918,7 @@ struct SmoothState {
       const uint32_t heads = __ballot_sync(kFull, lane == 0 || kprev != key);
       const uint32_t dist = lane - (31u - (uint32_t)__clz(heads & (0xFFFFFFFFu >> (31u - lane))));   // lanes since the run began
       uint32_t cnt, sx, sy, sz;
-      if (G.g <= 8u) {                      // one packed word: count | three sums of at most 32 * 7 (8 bits each)
+      if (kFast || G.g <= 8u) {             // one packed word: count | three sums of at most 32 * 7 (8 bits each)
         uint32_t v = fast8 ? vfast : (key != kCellEmpty ? (1u | (rx_ << 8) | (ry_ << 16) | (rz_ << 24)) : 0u);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -958,7 +961,7 @@ struct SmoothState {
       pend_col_any = __any_sync(kFull, bt == 2u);
       if (bt == 2u) {
         uint32_t cs = kCellEmpty;
-        if (G.fast) {
+        if (kFast || G.fast) {
           if (((w0 | w1) & G.oob_mask) == 0u) cs = fast_slot(G, ((w0 >> G.g_shift) & G.cmask) | ((w1 >> G.g_shift) << 8));
         } else {
           const uint32_t key = cell_key_of(G, X, Yc, Z);
@@ -1018,7 +1021,7 @@ struct SmoothState {
 #define TMC2_SMOOTH_MINCTA 3
 #endif
 constexpr int kEmitUnroll = TMC2_UNROLL;
-template <bool kSmooth, bool kDebug>
+template <bool kSmooth, bool kDebug, bool kFast>
 __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINCTA : TMC2_MINCTA) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
@@ -1267,7 +1270,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
       }
       if (a.out.btype) a.out.btype[gk] = (uint8_t)bt;
     }
-    if (kSmooth) S.point(a, valid, g, w0, w1, Y, uv, bt, has_attr);
+    if (kSmooth) S.template point<kFast>(a, valid, g, w0, w1, Y, uv, bt, has_attr);
   }
   if (kSmooth) S.finish(a);
 }
@@ -1598,12 +1601,12 @@ int launch_compact_owned(const UnpackArgs& a, void* stream) {
   return after_launch();
 }
 
-template <bool kSmooth, bool kDebug>
+template <bool kSmooth, bool kDebug, bool kFast>
 static int launch_emit_t(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, cudaStream_t s) {
   const size_t smem = (size_t)(kSmooth ? kWarpSmemBytes : kOffLogQ) * kWarpsPerTile;   // the log queues are smoothing-only
-  cudaError_t e = cudaFuncSetAttribute((const void*)emit_kernel<kSmooth, kDebug>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute((const void*)emit_kernel<kSmooth, kDebug, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  emit_kernel<kSmooth, kDebug><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin);
+  emit_kernel<kSmooth, kDebug, kFast><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin);
   return after_launch();
 }
 
@@ -1623,8 +1626,13 @@ int launch_emit(const UnpackArgs& a, bool smooth, uint32_t tile_begin, uint32_t 
   if (tile_end <= tile_begin) return 0;
   const cudaStream_t s = (cudaStream_t)stream;
   const bool debug = a.out.yuv || a.out.part || a.out.pix || a.out.btype;
-  if (smooth) return debug ? launch_emit_t<true, true>(a, tile_begin, tile_end, s) : launch_emit_t<true, false>(a, tile_begin, tile_end, s);
-  return debug ? launch_emit_t<false, true>(a, tile_begin, tile_end, s) : launch_emit_t<false, false>(a, tile_begin, tile_end, s);
+  if (smooth) {
+    if (debug) return launch_emit_t<true, true, false>(a, tile_begin, tile_end, s);
+    // the usual grids (dense tables, power-of-two cell edges, geometry edge <= 8) get the instantiation without generic branches
+    const bool fast = (!a.sm.geo.on || (a.sm.geo.fast && a.sm.geo.g <= 8u)) && (!a.sm.col.on || a.sm.col.fast);
+    return fast ? launch_emit_t<true, false, true>(a, tile_begin, tile_end, s) : launch_emit_t<true, false, false>(a, tile_begin, tile_end, s);
+  }
+  return debug ? launch_emit_t<false, true, false>(a, tile_begin, tile_end, s) : launch_emit_t<false, false, false>(a, tile_begin, tile_end, s);
 }
 
 int launch_upsample(const UnpackArgs& a, uint8_t* occ_full, void* stream) {
