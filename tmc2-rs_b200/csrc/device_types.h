@@ -59,11 +59,12 @@ struct alignas(16) WorkRec {
   uint16_t u0b, v0b;
   uint16_t bx, by;
   int8_t   ax, ay, rx, ry;
-  uint32_t frame;            // frame inside the batch
+  uint32_t frame;            // frame inside the batch (in memory: | projection mode << 31)
   uint32_t total;            // points this slot emits
   uint32_t base;             // first point of its run inside the frame
-  uint32_t _pad;
+  uint32_t d1;               // the patch's depth shift (copy, so that count_kernel needs no patch load)
 };
+static_assert(sizeof(WorkRec) == 32, "WorkRec is two 16-byte vectors");
 
 struct Planes {
   const uint8_t*  occ;

@@ -27,6 +27,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "device_types.h"
 
@@ -350,14 +351,22 @@ __global__ void __launch_bounds__(1024) compact_owned_kernel(const UnpackArgs a)
     // thread t owns the kPerThread consecutive slots from b + t * kPerThread (slot order == thread order)
     const uint32_t first = b + threadIdx.x * kPerThread;
     uint4 rec[kPerThread];
-    uint32_t li[kPerThread];
+    uint32_t li[kPerThread], d1m[kPerThread][2];
 #pragma unroll
     for (int i = 0; i < kPerThread; ++i) {
       rec[i] = make_uint4(kNoPatch, 0, 0, 0);
       if (first + i < s1) rec[i] = __ldg(reinterpret_cast<const uint4*>(a.slot_rec + first + i));
     }
 #pragma unroll
-    for (int i = 0; i < kPerThread; ++i) li[i] = rec[i].x != kNoPatch ? __ldg(&a.patches[rec[i].x].local_index) : 0u;
+    for (int i = 0; i < kPerThread; ++i) {
+      li[i] = 0; d1m[i][0] = d1m[i][1] = 0;
+      if (rec[i].x != kNoPatch) {
+        const DevPatch* p = a.patches + rec[i].x;
+        li[i] = __ldg(&p->local_index);
+        d1m[i][0] = __ldg(&p->d1);
+        d1m[i][1] = __ldg(reinterpret_cast<const uint32_t*>(&p->normal)) >> 24;     // projection mode
+      }
+    }
     uint32_t own = 0;
 #pragma unroll
     for (int i = 0; i < kPerThread; ++i) {
@@ -372,7 +381,7 @@ __global__ void __launch_bounds__(1024) compact_owned_kernel(const UnpackArgs a)
       if (!((own >> i) & 1u)) continue;
       uint4* dst = reinterpret_cast<uint4*>(a.work + s0 + pos);
       dst[0] = rec[i];
-      dst[1] = make_uint4(f, 0, 0, 0);
+      dst[1] = make_uint4(f | (d1m[i][1] << 31), 0, 0, d1m[i][0]);      // frame | mode << 31, total, base, d1
       ++pos;
     }
     carry += total;
@@ -425,12 +434,13 @@ __device__ __forceinline__ uint32_t cell_key_of(const GridDesc& G, uint32_t x, u
   return cell_div(x, G) | (cell_div(y, G) << 10) | (cell_div(z, G) << 20);
 }
 
-__device__ __forceinline__ WorkRec load_work(const WorkRec* p) {
+__device__ __forceinline__ WorkRec load_work(const WorkRec* p, uint32_t* mode = nullptr) {
   const uint4 v = *reinterpret_cast<const uint4*>(p), w = *(reinterpret_cast<const uint4*>(p) + 1);
   WorkRec r;
   r.pid = v.x; r.u0b = (uint16_t)v.y; r.v0b = (uint16_t)(v.y >> 16); r.bx = (uint16_t)v.z; r.by = (uint16_t)(v.z >> 16);
   r.ax = (int8_t)v.w; r.ay = (int8_t)(v.w >> 8); r.rx = (int8_t)(v.w >> 16); r.ry = (int8_t)(v.w >> 24);
-  r.frame = w.x; r.total = w.y; r.base = w.z; r._pad = 0;
+  r.frame = w.x & 0x7FFFFFFFu; r.total = w.y; r.base = w.z; r.d1 = w.w;
+  if (mode) *mode = w.x >> 31;                                     // projection mode travels in the top bit of `frame`
   return r;
 }
 
@@ -681,19 +691,16 @@ __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, uint32_t pid
 }
 
 // ---- pass 1: points per owned slot ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerTile * 32) count_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
+__global__ void __launch_bounds__(kWarpsPerTile * 32, 6) count_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   const uint32_t lane = lane_id();
   const uint32_t lpos = (blockIdx.x + tile_offset) * kWarpsPerTile + (threadIdx.x >> 5);
-  const WorkRec R = load_work(a.work + lpos);
+  uint32_t mode;
+  const WorkRec R = load_work(a.work + lpos, &mode);
   if (R.pid == kNoPatch) return;                                   // unused tail of the frame's region (total stays 0)
   uint32_t total;
   if (slot_is_fast(a, R)) {
     DevPatch P;
-    {
-      const DevPatch* p = a.patches + R.pid;
-      P.d1 = __ldg(&p->d1);
-      P.mode = (uint8_t)(__ldg(reinterpret_cast<const uint32_t*>(&p->normal)) >> 24);
-    }
+    P.d1 = R.d1; P.mode = (uint8_t)mode;                 // copied into the work record: no patch load on this path
     CanvasBlock L;
     load_geometry(a, R, P, lane, L);
     total = __reduce_add_sync(kFull, __popc(L.m1) + __popc(L.m2));
@@ -829,8 +836,10 @@ struct SmoothState {
   uint32_t frame, fig, patch, lane, lbase, n_done;
   uint32_t* q;                   // [2][64] queued table slots: geometry, colour
   uint32_t nq_geo, nq_col;       // warp-uniform fill of the two queues
-  uint32_t pend_geo_old, pend_geo_cs, pend_col_old, pend_col_cs;   // issued in the previous window (cs == kCellEmpty: none)
-  bool pend_col_any;             // warp-uniform: the previous window issued colour reductions
+  // Claims issued kDepth windows ago (window parity selects the slot when the loop body is instantiated twice;
+  // cs == kCellEmpty: none)
+  uint32_t pend_geo_old[2], pend_geo_cs[2], pend_col_old[2], pend_col_cs[2];
+  bool pend_col_any[2];          // warp-uniform: that window issued colour reductions
   uint32_t* memo;                // [2][32] cells this warp has already claimed for its slot (direct-mapped, geometry / colour)
   GeoCell* geo_tab;              // this frame's tables
   ColCell* col_tab;
@@ -840,7 +849,7 @@ struct SmoothState {
   __device__ __forceinline__ void init(const UnpackArgs& a, uint32_t frame_, uint32_t fig_, uint32_t patch_, uint32_t lane_,
                                        uint32_t* queue) {
     frame = frame_; fig = fig_; patch = patch_; lane = lane_; lbase = 0; n_done = 0; q = queue; nq_geo = nq_col = 0;
-    pend_geo_old = pend_col_old = 1; pend_geo_cs = pend_col_cs = kCellEmpty; pend_col_any = false;
+    for (int i = 0; i < 2; ++i) { pend_geo_old[i] = pend_col_old[i] = 1; pend_geo_cs[i] = pend_col_cs[i] = kCellEmpty; pend_col_any[i] = false; }
     memo = queue + 128;
     memo[lane] = kCellEmpty; memo[32 + lane] = kCellEmpty;
     __syncwarp();
@@ -884,7 +893,7 @@ struct SmoothState {
 
   // kFast: both grids are known (at launch) to be dense power-of-two grids with cell edge <= 8 (geometry): the generic
   // branches drop out of the instantiation, which keeps the hot loop small
-  template <bool kFast>
+  template <bool kFast, int kSlot>
   __device__ __forceinline__ void point(const UnpackArgs& a, bool valid, uint32_t g, uint32_t w0, uint32_t w1, uint32_t Y,
                                         uint32_t uv, uint32_t bt, bool has_attr) {
     const uint32_t X = w0 & 0xFFFFu, Yc = w0 >> 16, Z = w1 & 0xFFFFu;
@@ -936,15 +945,15 @@ struct SmoothState {
         cnt = v0 & 0xFFFFu; sx = v0 >> 16; sy = v1 & 0xFFFFu; sz = v1 >> 16;
       }
       const bool tail = key != kCellEmpty && (lane == 31u || ((heads >> 1) >> lane) & 1u);
-      retire(a, G, geo_tab, geo_mb, q, nq_geo, pend_geo_old, pend_geo_cs);          // the reductions issued one window ago
-      pend_geo_old = 1; pend_geo_cs = kCellEmpty;
+      retire(a, G, geo_tab, geo_mb, q, nq_geo, pend_geo_old[kSlot], pend_geo_cs[kSlot]);   // claims issued one / two windows ago
+      pend_geo_old[kSlot] = 1; pend_geo_cs[kSlot] = kCellEmpty;
       if (tail) {
         const uint32_t cs = fast8 ? fast_slot(G, key) : cell_slot(G, fig, key, a.err);
         if (cs != kCellEmpty) {
           GeoCell* c = geo_tab + cs;
           if (!claimed_before(memo, cs)) {
-            pend_geo_cs = cs;
-            pend_geo_old = atomicCAS(&c->first1, 0u, patch + 1u);   // 0: first touch; another patch + 1: multi-patch cell
+            pend_geo_cs[kSlot] = cs;
+            pend_geo_old[kSlot] = atomicCAS(&c->first1, 0u, patch + 1u);   // 0: first touch; another patch + 1: multi-patch cell
           }
           atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
           atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
@@ -954,11 +963,11 @@ struct SmoothState {
     // K7 statistics: colour cells over the type-2 (second ring) points
     if (a.sm.col.on && has_attr) {
       const GridDesc& G = a.sm.col;
-      if (pend_col_any) {
-        retire(a, G, col_tab, col_mb, q + 64, nq_col, pend_col_old, pend_col_cs);
-        pend_col_old = 1; pend_col_cs = kCellEmpty;
+      if (pend_col_any[kSlot]) {
+        retire(a, G, col_tab, col_mb, q + 64, nq_col, pend_col_old[kSlot], pend_col_cs[kSlot]);
+        pend_col_old[kSlot] = 1; pend_col_cs[kSlot] = kCellEmpty;
       }
-      pend_col_any = __any_sync(kFull, bt == 2u);
+      pend_col_any[kSlot] = __any_sync(kFull, bt == 2u);
       if (bt == 2u) {
         uint32_t cs = kCellEmpty;
         if (kFast || G.fast) {
@@ -970,8 +979,8 @@ struct SmoothState {
         if (cs != kCellEmpty) {
           ColCell* c = col_tab + cs;
           if (!claimed_before(memo + 32, cs)) {
-            pend_col_cs = cs;
-            pend_col_old = atomicCAS(&c->first1, 0u, patch + 1u);
+            pend_col_cs[kSlot] = cs;
+            pend_col_old[kSlot] = atomicCAS(&c->first1, 0u, patch + 1u);
           }
           atomicAdd(&c->cnt_sy, 1ull | ((unsigned long long)Y << 24));
           atomicAdd(&c->su_sv, (unsigned long long)(uv & 0xFFFFu) | ((unsigned long long)(uv >> 16) << 32));
@@ -994,11 +1003,13 @@ struct SmoothState {
 
   __device__ __forceinline__ void finish(const UnpackArgs& a) {
     if (a.sm.geo.on) {
-      retire(a, a.sm.geo, geo_tab, geo_mb, q, nq_geo, pend_geo_old, pend_geo_cs);
+      retire(a, a.sm.geo, geo_tab, geo_mb, q, nq_geo, pend_geo_old[0], pend_geo_cs[0]);
+      retire(a, a.sm.geo, geo_tab, geo_mb, q, nq_geo, pend_geo_old[1], pend_geo_cs[1]);
       if (nq_geo) flush(a, a.sm.geo, q, nq_geo);
     }
     if (a.sm.col.on) {
-      retire(a, a.sm.col, col_tab, col_mb, q + 64, nq_col, pend_col_old, pend_col_cs);
+      retire(a, a.sm.col, col_tab, col_mb, q + 64, nq_col, pend_col_old[0], pend_col_cs[0]);
+      retire(a, a.sm.col, col_tab, col_mb, q + 64, nq_col, pend_col_old[1], pend_col_cs[1]);
       if (nq_col) flush(a, a.sm.col, q + 64, nq_col);
     }
   }
@@ -1014,13 +1025,12 @@ struct SmoothState {
 #ifndef TMC2_MINCTA
 #define TMC2_MINCTA 4
 #endif
-#ifndef TMC2_UNROLL
-#define TMC2_UNROLL 1
+#ifndef TMC2_CLAIM_DEPTH
+#define TMC2_CLAIM_DEPTH 1
 #endif
 #ifndef TMC2_SMOOTH_MINCTA
 #define TMC2_SMOOTH_MINCTA 3
 #endif
-constexpr int kEmitUnroll = TMC2_UNROLL;
 template <bool kSmooth, bool kDebug, bool kFast>
 __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINCTA : TMC2_MINCTA) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -1205,8 +1215,10 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
   uint16_t* ppos = a.out.pos + (gframe + g) * 3;                   // this lane's point in the packed position stream
   uint8_t* prgb = has_attr ? a.out.rgb + (gframe + g) * 3 : nullptr;
   const uint16_t* psrc = s_src + (int32_t)k;
-#pragma unroll kEmitUnroll
-  for (; g - lane < run_end; g += 32, k += 32, ppos += 96, prgb += 96, psrc += 32) {
+  // one 32-point window; returns false when the run is exhausted.  kSlot selects the pending-claim registers (see SmoothState)
+  auto window = [&](auto slot_tag) -> bool {
+    constexpr int kSlot = decltype(slot_tag)::value;
+    if (!(g - lane < run_end)) return false;
     const bool valid = k < total;
     const uint32_t vb = __ballot_sync(kFull, valid);
     const uint32_t e = valid ? (uint32_t)*psrc : 0u;               // rank << 1 | map
@@ -1270,7 +1282,14 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
       }
       if (a.out.btype) a.out.btype[gk] = (uint8_t)bt;
     }
-    if (kSmooth) S.template point<kFast>(a, valid, g, w0, w1, Y, uv, bt, has_attr);
+    if (kSmooth) S.template point<kFast, kSlot>(a, valid, g, w0, w1, Y, uv, bt, has_attr);
+    g += 32; k += 32; ppos += 96; prgb += 96; psrc += 32;
+    return true;
+  };
+  if (kSmooth && kFast && TMC2_CLAIM_DEPTH == 2) {   // two instantiations of the body: a claim's round trip overlaps two windows
+    while (window(std::integral_constant<int, 0>{}) && window(std::integral_constant<int, 1>{})) {}
+  } else {
+    while (window(std::integral_constant<int, 0>{})) {}
   }
   if (kSmooth) S.finish(a);
 }
