@@ -209,9 +209,11 @@ def main():
     cfg_desc.update({"atlas": f"{cfg.width}x{cfg.height}", "smoothing": smoothing, "maps": 2,
                      "occupancy_precision": cfg.occupancy_precision, "bitdepth_3d": cfg.bitdepth_3d,
                      "sharding": f"{world} rank(s), one GOF per rank per step, no collective",
+                     "e2e_gofs_in_flight": 3,
                      "host_cpus_of_rank0": (f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else "inherited"),
                      "l2": f"inputs {gof.input_bytes() / 1e6:.0f} MB/step > 126 MB L2 (no flush needed)"})
-    ctx = codec.Context(devices=(local_rank,), two_pass_scan=args.two_pass)
+    depth = 3                                             # GOFs in flight on the streaming path (keeps both DMA engines busy)
+    ctx = codec.Context(devices=(local_rank,), gofs_in_flight=depth, two_pass_scan=args.two_pass)
     pinned = codec.pinned_copy_of(gof)
     view = abi.GofView(pinned)
 
@@ -264,24 +266,29 @@ def main():
             cnt, pos_addr, _col_addr = ctx.next_frame_raw()      # frame is in pinned host memory when this returns
             got += cnt
         return got
-    # warm-up with the same two-GOFs-in-flight pattern as the timed loop, so that every GOF slot of the context has its
-    # device buffers and pinned result slab allocated before timing starts
-    ctx.submit_gof(view)
-    for _ in range(max(3, args.warmup)):
+    # warm-up with the same GOFs-in-flight pattern as the timed loop, so that every GOF slot of the context has its device
+    # buffers and pinned result slab allocated before timing starts
+    for _ in range(depth - 1):
+        ctx.submit_gof(view)
+    for _ in range(max(depth + 1, args.warmup)):
         ctx.submit_gof(view)
         drain(frames)
-    drain(frames)
+    for _ in range(depth - 1):
+        drain(frames)
     barrier()
     trace = os.environ.get("TMC2_TRACE") is not None
     t0 = time.perf_counter()
     got = 0
-    ctx.submit_gof(view)
-    for s in range(1, args.steps):
+    ahead = min(depth - 1, args.steps)
+    for _ in range(ahead):
+        ctx.submit_gof(view)
+    for s in range(args.steps - ahead):
         ctx.submit_gof(view)
         got += drain(frames)
         if trace:
             sys.stderr.write(f"[bench] e2e step {s}: {(time.perf_counter() - t0) * 1e3:.2f} ms since start\n")
-    got += drain(frames)
+    for _ in range(ahead):
+        got += drain(frames)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop()            # sampled over both timed regions (kernel-only steps and the end-to-end steps)
