@@ -153,7 +153,6 @@ def main():
     ap.add_argument("--ref-threads", type=int, default=1)
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--two-pass", action="store_true", help="debug: count/scan/emit instead of the fused single pass")
     ap.add_argument("--no-smoothing", action="store_true", help="reference-exact rec0 path only (no post-processing)")
     args = ap.parse_args()
 
@@ -213,7 +212,7 @@ def main():
                      "host_cpus_of_rank0": (f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else "inherited"),
                      "l2": f"inputs {gof.input_bytes() / 1e6:.0f} MB/step > 126 MB L2 (no flush needed)"})
     depth = 3                                             # GOFs in flight on the streaming path (keeps both DMA engines busy)
-    ctx = codec.Context(devices=(local_rank,), gofs_in_flight=depth, two_pass_scan=args.two_pass)
+    ctx = codec.Context(devices=(local_rank,), gofs_in_flight=depth)
     pinned = codec.pinned_copy_of(gof)
     view = abi.GofView(pinned)
 

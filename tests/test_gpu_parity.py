@@ -60,7 +60,9 @@ def test_config1_full_frame_bit_exact(gpu_ctx):
     util.assert_same(got, want, what="c1")
 
 
-def test_two_pass_scan_equals_single_pass(gpu_ctx):
+def test_two_contexts_agree(gpu_ctx):
+    """A second, independent context (own streams, own device buffers; created with the reserved legacy flag) gives the
+    same frames as the session context, and both equal the oracle."""
     g = synth.make_gof(synth.config("small"))
     view = abi.GofView(g)
     ctx2 = codec.Context(two_pass_scan=True)
@@ -68,7 +70,7 @@ def test_two_pass_scan_equals_single_pass(gpu_ctx):
         for f in range(g.frame_count):
             a = gpu_ctx.generate_point_cloud(view, f)
             b = ctx2.generate_point_cloud(view, f)
-            util.assert_same(a, b, what=f"two-pass frame {f}")
+            util.assert_same(a, b, what=f"second context, frame {f}")
             util.assert_same(a, oracle.reconstruct_frame(view, f), what=f"frame {f}")
     finally:
         ctx2.close()

@@ -33,7 +33,8 @@ class PointSet3:
 
 
 class Context:
-    """Owns a ``tmc2gpu_ctx`` (device buffers, streams, pinned staging)."""
+    """Owns a ``tmc2gpu_ctx`` (device buffers, streams, pinned staging).  ``two_pass_scan`` sets a reserved legacy flag that
+    the library accepts and ignores (the unpack is always count / scan / emit)."""
 
     def __init__(self, devices: Sequence[int] = (0,), max_frames: int = 0, gofs_in_flight: int = 2,
                  two_pass_scan: bool = False):
