@@ -343,3 +343,29 @@ def test_random_small_atlases_with_smoothing(gpu_ctx, case, grids):
     pre = ["positions_presmooth", "boundary_type"] + (["colors16bit_presmooth"] if g.params.attribute_count else [])
     util.assert_same(got, want, keys=pre, what=str(case) + " pre-smoothing")
     assert got["smoothed_positions"] == want["smoothed_positions"] and got["smoothed_colors"] == want["smoothed_colors"]
+
+
+def test_one_process_two_devices_shard_frames_in_order():
+    """SURVEY 8e inside ONE process: a context over two devices shards the frames of a GOF frame-wise (contiguous halves, no
+    collective) and hands them back in order; results equal the single-device context.  Skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = synth.replicate_gof(synth.make_gof(synth.config("small")), 7)      # odd frame count: slices of 3 and 4
+    g.params.geometry_smoothing = True
+    g.params.color_smoothing = True
+    view = abi.GofView(g)
+    one, two = codec.Context(devices=(0,)), codec.Context(devices=(0, 1))
+    try:
+        a = one.decode_gof(view)
+        b = two.decode_gof(view)
+        b2 = two.decode_gof(view)                                           # second GOF through the same two-device context
+        assert len(a) == len(b) == len(b2) == 7
+        for x, y, z in zip(a, b, b2):
+            assert np.array_equal(x.positions, y.positions) and np.array_equal(x.colors, y.colors)
+            assert np.array_equal(x.positions, z.positions) and np.array_equal(x.colors, z.colors)
+        want = oracle.reconstruct_frame(view, 5)
+        assert np.array_equal(b[5].positions, want["positions"]) and np.array_equal(b[5].colors, want["colors"])
+    finally:
+        one.close()
+        two.close()
