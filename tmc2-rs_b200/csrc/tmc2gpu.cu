@@ -992,38 +992,58 @@ tmc2_status tmc2gpu_submit_gof(tmc2gpu_ctx* ctx, const tmc2_gof* gof) {
     if (validate_frame(gof, f, err)) return ctx->fail();
   if (gof->frame_count == 0) return TMC2_OK;
 
-  // frame-wise sharding: contiguous chunks of the GOF, one per device; no collective
+  // Frame-wise sharding: contiguous slices of the GOF, one per device; no collective.  A device's slice can
+  // be cut further into chunks of TMC2_CHUNK_FRAMES frames, each an independent batch on its own stream (lower latency to
+  // the first frame); measured on B200 it does not raise throughput once several GOFs are in flight, so the default is
+  // one batch per device slice.
   const uint32_t D = (uint32_t)ctx->devices.size();
   const uint32_t F = gof->frame_count;
-  std::vector<Batch*> chosen(D, nullptr);
+  static const uint32_t chunk_frames = [] { const char* e = getenv("TMC2_CHUNK_FRAMES"); return e ? (uint32_t)atoi(e) : 0u; }();
+  struct Piece { uint32_t d, lo, hi; Batch* b; };
+  std::vector<Piece> pieces;
   for (uint32_t d = 0; d < D; ++d) {
     const uint32_t lo = (uint32_t)((uint64_t)F * d / D), hi = (uint32_t)((uint64_t)F * (d + 1) / D);
-    if (hi == lo) continue;
-    for (auto& b : ctx->slots[d]) if (!b->busy) { chosen[d] = b.get(); break; }
-    if (!chosen[d]) {
+    const uint32_t step = chunk_frames ? chunk_frames : std::max(hi - lo, 1u);
+    for (uint32_t c = lo; c < hi; c += step) pieces.push_back({d, c, std::min(hi, c + step), nullptr});
+  }
+  // every piece needs a free batch of its device; batches are created on demand, up to gofs_in_flight GOFs of this shape
+  for (uint32_t d = 0; d < D; ++d) {
+    uint32_t need = 0;
+    for (auto& pc : pieces) need += pc.d == d;
+    if (!need) continue;
+    std::vector<Batch*> free_list;
+    for (auto& b : ctx->slots[d]) if (!b->busy) free_list.push_back(b.get());
+    const size_t cap_batches = (size_t)ctx->limits.gofs_in_flight * need;
+    while (free_list.size() < need && ctx->slots[d].size() < cap_batches) {
+      std::unique_ptr<Batch> b(new Batch());
+      if (b->init(ctx->devices[d], ctx->two_pass, err)) return ctx->fail();
+      free_list.push_back(b.get());
+      ctx->slots[d].push_back(std::move(b));
+    }
+    if (free_list.size() < need) {
       err.st = TMC2_ERR_STATE;
       err.msg = "all GOF slots in flight: drain frames with tmc2gpu_next_frame / release_frame first";
       return ctx->fail();
     }
+    size_t k = 0;
+    for (auto& pc : pieces) if (pc.d == d) pc.b = free_list[k++];
   }
-  for (uint32_t d = 0; d < D; ++d) {
-    const uint32_t lo = (uint32_t)((uint64_t)F * d / D), hi = (uint32_t)((uint64_t)F * (d + 1) / D);
-    if (hi == lo) continue;
-    Batch* b = chosen[d];
+  for (auto& pc : pieces) {
+    Batch* b = pc.b;
     const double t_val = tc.lap();
-    if (b->prepare(gof, lo, hi - lo, 0, err)) return ctx->fail();
+    if (b->prepare(gof, pc.lo, pc.hi - pc.lo, 0, err)) return ctx->fail();
     const double t_prep = tc.lap();
-    if (b->upload(gof, lo, err)) return ctx->fail();
+    if (b->upload(gof, pc.lo, err)) return ctx->fail();
     const double t_up = tc.lap();
     if (b->launch(b->stream, err)) return ctx->fail();
     if (trace_on())
-      fprintf(stderr, "[tmc2gpu] submit dev %d: validate %.3f prepare %.3f upload-enqueue %.3f launch-enqueue %.3f ms\n", b->device,
-              t_val, t_prep, t_up, tc.lap());
+      fprintf(stderr, "[tmc2gpu] submit dev %d frames %u..%u: validate %.3f prepare %.3f upload-enqueue %.3f launch-enqueue %.3f ms\n",
+              b->device, pc.lo, pc.hi, t_val, t_prep, t_up, tc.lap());
     // counts travel right behind the kernels; result copies are enqueued when the first frame is asked for
     b->busy = true; b->frames_released = 0;
     b->t_submit = std::chrono::steady_clock::now(); b->trace_wait_ms = 0;
     ctx->last_batch = b;
-    for (uint32_t k = 0; k < hi - lo; ++k) ctx->pending.push_back({b, k, ctx->next_global++});
+    for (uint32_t k = 0; k < pc.hi - pc.lo; ++k) ctx->pending.push_back({b, k, ctx->next_global++});
   }
   return TMC2_OK;
 }
