@@ -310,6 +310,14 @@ def main():
                 "launches_per_step": n_emit, "frames_per_launch": min(group, frames),
                 "algorithmic_bytes_per_launch": alg_bytes / n_emit, "ms_per_launch": t_unpack / n_emit, "traffic": None,
                 "stage_ms": {k: statistics.mean(v) for k, v in stage_acc.items()}}
+    # the other HBM-streaming kernel of the path: the count pass reads the occupancy video and both geometry planes once
+    # (its stage time also holds the tiny per-frame scan launch, so the fraction is a lower bound)
+    t_count = statistics.mean(stage_acc.get("count_scan", [0.0])) if stage_acc else 0.0
+    count_bytes = frames * (cfg.width // cfg.occupancy_precision) * (cfg.height // cfg.occupancy_precision) + frames * 2 * cfg.width * cfg.height * 2
+    if t_count > 0:
+        roofline["other_kernels"] = {"count_kernel+slot_scan_kernel": {
+            "algorithmic_bytes_per_launch": count_bytes, "ms_per_launch": t_count,
+            "achieved": count_bytes / (t_count * 1e-3) / 1e9, "frac": count_bytes / (t_count * 1e-3) / 1e9 / peak}}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             roofline["traffic"] = json.load(f).get(args.config + ("" if smoothing else "_nosmooth"))
