@@ -11,8 +11,8 @@
 // Outputs are per-frame slabs of `cap` points (cap % 16 == 0):  pos [F][cap][3] u16, rgb [F][cap][3] u8, and (debug /
 // stage API only) yuv [F][cap][3] u16, partition [F][cap] u16, pixel [F][cap] u32 (x | y<<15 | map<<30), btype [F][cap] u8;
 // count [F] u32.
-// Smoothing state (per group of frames): voxel-cell tables (GeoCell / ColCell, dense or hashed), per frame a log of the
-// cells that were touched (written once, by the first toucher) and a compact list of type-1 boundary points.
+// Smoothing state (per group of frames): voxel-cell tables (GeoCell / ColCell, dense or hashed), per frame two bitmaps over
+// the table slots (touched / multi-patch) and a compact list of type-1 boundary points.
 #pragma once
 #include <cstdint>
 
@@ -92,19 +92,18 @@ struct Outputs {                // any pointer may be null = stream not wanted
 
 // ---- voxel-cell tables of the grid smoothing stages (own spec) ------------------------------------------
 // A cell is written only with fire-and-forget reductions (RED): two max, two / three 64-bit adds.  All-zero == empty.
-// "multi-patch" (the smoothing trigger) <=> two different patches touched the cell: the first toucher claims `first1` with
-// a compare-and-swap (0 -> patch + 1); whoever finds another patch's claim stores 1 into `multi` (idempotent).
+// "multi-patch" (the smoothing trigger) <=> max(patch) != min(patch) <=> pmax1 - 1 != ~pminc.
 // The finalize pass (once per touched cell, before the filter) turns the sums into Q8 means.
 constexpr uint32_t kCellEmpty = 0xFFFFFFFFu;      // free slot of a hashed table's key array
 struct GeoCell {     // 32 B = one DRAM sector
-  uint32_t first1;              // patch index + 1 of the first toucher, 0 = untouched
-  uint32_t multi;               // 1 = touched by more than one patch
+  uint32_t pmax1;               // max(patch index + 1), 0 = untouched
+  uint32_t pminc;               // max(~patch index)
   unsigned long long cnt_sx;    // count | sum(x - cell origin) << 32
   unsigned long long sy_sz;     // sum(y - origin) | sum(z - origin) << 32
   unsigned long long mean;      // finalize: Q8 means relative to the cell origin, 16 bits each (x | y<<16 | z<<32)
 };
 struct ColCell {     // 32 B
-  uint32_t first1, multi;
+  uint32_t pmax1, pminc;
   unsigned long long cnt_sy;    // count (24 bits) | sum(Y) << 24         finalize -> count | meanY_Q8 << 32
   unsigned long long su_sv;     // sum(U) | sum(V) << 32                  finalize -> meanU_Q8 | meanV_Q8 << 32
   unsigned long long sy2;       // sum(Y*Y)                               finalize -> 1 if the luminance variance test passes
@@ -128,10 +127,8 @@ struct GridDesc {               // geometry of one voxel grid
   uint64_t slots;               // table slots per frame-in-group (power of two unless identity)
   void*    table;               // GeoCell / ColCell [frames_in_group][slots]
   uint32_t* keys;               // hashed tables only: [frames_in_group][slots], kCellEmpty = free
-  uint32_t* log;                // [frames_in_group][log_cap] table slots touched in that frame, each exactly once
-  uint32_t* log_count;          // [frames_in_group]
-  uint64_t log_cap;
-  uint32_t* mbits;              // [frames_in_group][mwords] one bit per table slot: the cell is multi-patch (what the probe reads)
+  uint32_t* tbits;              // [frames_in_group][mwords] one bit per table slot: the cell was touched (set by the emit)
+  uint32_t* mbits;              // [frames_in_group][mwords] ... the cell is multi-patch (set by the collect pass, read by the probe)
   uint64_t mwords;
 };
 
@@ -175,8 +172,8 @@ constexpr uint32_t kOffTerm = kOffPt + 2176;                     // [64][2] uint
 constexpr uint32_t kOffSrc = kOffTerm + 2048;                    // [512] u16: output point -> rank << 1 | map
 constexpr uint32_t kOffCnt = kOffSrc + 1024;                     // [256] u8: points of the pixel (0..2) | boundary class << 2
 constexpr uint32_t kOffBmp = kOffCnt + 256;                      // [32] u32: 20x20 occupancy bitmap rows (canvas axes)
-constexpr uint32_t kOffLogQ = kOffBmp + 128;                     // [2][64] u32: first-touched cells waiting for the log
-constexpr uint32_t kWarpSmemBytes = kOffLogQ + 512 + 256;        // + [2][32] claimed-cell memo
+constexpr uint32_t kOffMemo = kOffBmp + 128;                     // [2][32] u32: cells the slot has already claimed (smoothing only)
+constexpr uint32_t kWarpSmemBytes = kOffMemo + 256;
 
 // launch wrappers (kernels.cu); every one enqueues on `stream` and returns the cudaGetLastError() code
 int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream);

@@ -547,46 +547,28 @@ __device__ __noinline__ uint32_t generic_slot_count(const UnpackArgs& a, uint32_
   return total;
 }
 
-// a second patch reached the cell: flag it in the cell itself (idempotent plain store) and in the frame's bitmap
-__device__ __forceinline__ void mark_multi(const GridDesc& G, uint32_t fig, uint32_t cs) {
-  reinterpret_cast<volatile uint32_t*>(static_cast<uint8_t*>(G.table) + ((uint64_t)fig * G.slots + cs) * 32u)[1] = 1u;
-  atomicOr(&G.mbits[(uint64_t)fig * G.mwords + (cs >> 5)], 1u << (cs & 31u));
+// ---- smoothing: accumulate into a cell.  Every update is a fire-and-forget reduction (nothing is read back):
+//   pmax1 = max(patch + 1), pminc = max(~patch)  ->  multi-patch  <=>  pmax1 - 1 != ~pminc
+//   two / three 64-bit adds for the count and the sums, and the cell's bit in the frame's "touched" bitmap
+__device__ __forceinline__ void cell_claim(uint32_t* cell_words, uint32_t* tbits, uint32_t cs, uint32_t patch) {
+  atomicMax(cell_words, patch + 1u);
+  atomicMax(cell_words + 1, ~patch);
+  atomicOr(tbits + (cs >> 5), 1u << (cs & 31u));
 }
-
-// ---- smoothing: accumulate into a cell; the first toucher of a cell appends it to the frame's log -----------------------
-// returns true when this call was the first to touch the cell (pmax1 was 0 == untouched)
-__device__ __forceinline__ bool geo_cell_add_first(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
-                                                   uint32_t sx, uint32_t sy, uint32_t sz) {
+__device__ __forceinline__ void geo_cell_add(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
+                                             uint32_t sx, uint32_t sy, uint32_t sz) {
   GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + slot;
-  const uint32_t old = atomicCAS(&c->first1, 0u, patch + 1u);
-  if (old != 0u && old != patch + 1u) mark_multi(G, fig, slot);
+  cell_claim(&c->pmax1, G.tbits + (uint64_t)fig * G.mwords, slot, patch);
   atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
   atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
-  return old == 0u;
 }
-__device__ __forceinline__ bool col_cell_add_first(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
-                                                   uint32_t sy, uint32_t su, uint32_t sv, unsigned long long sy2) {
+__device__ __forceinline__ void col_cell_add(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
+                                             uint32_t sy, uint32_t su, uint32_t sv, unsigned long long sy2) {
   ColCell* c = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots + slot;
-  const uint32_t old = atomicCAS(&c->first1, 0u, patch + 1u);
-  if (old != 0u && old != patch + 1u) mark_multi(G, fig, slot);
+  cell_claim(&c->pmax1, G.tbits + (uint64_t)fig * G.mwords, slot, patch);
   atomicAdd(&c->cnt_sy, (unsigned long long)cnt | ((unsigned long long)sy << 24));
   atomicAdd(&c->su_sv, (unsigned long long)su | ((unsigned long long)sv << 32));
   atomicAdd(&c->sy2, sy2);
-  return old == 0u;
-}
-// warp-aggregated append of the lanes with `first` set (call with the whole warp converged)
-__device__ __forceinline__ void log_append(const UnpackArgs& a, const GridDesc& G, uint32_t fig, bool first, uint32_t cs,
-                                           uint32_t lane) {
-  const uint32_t fm = __ballot_sync(kFull, first);
-  if (fm == 0) return;
-  uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(&G.log_count[fig], (uint32_t)__popc(fm));
-  base = __shfl_sync(kFull, base, 0);
-  if (first) {
-    const uint64_t i = (uint64_t)base + __popc(fm & ((1u << lane) - 1u));
-    if (i < G.log_cap) G.log[(uint64_t)fig * G.log_cap + i] = cs;
-    else atomicExch(a.err, 11);
-  }
 }
 
 // Generic slot path: lane = pixel, 32 at a time in patch raster order, everything straight to global memory.  Rare.
@@ -628,7 +610,7 @@ __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, uint32_t pid
     uint64_t k = run + (incl - c);
     uint32_t bt = 0;
     if (c && ((kDebug && a.out.btype) || kSmooth)) bt = boundary_type(a, occ_f, (int32_t)x, (int32_t)y);
-    for (uint32_t m = 0; m < 2; ++m) {                               // warp-uniform trip count: log_append is convergent
+    for (uint32_t m = 0; m < 2; ++m) {
       const bool on = m < c;
       const uint32_t n = m == 0 ? n0 : n1;
       const uint32_t X = pick(srcx, n, t, b), Yc = pick(srcy, n, t, b), Z = pick(srcz, n, t, b);
@@ -652,26 +634,22 @@ __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, uint32_t pid
       }
       if (kSmooth) {
         if (a.sm.geo.on) {
-          bool first = false; uint32_t cs = kCellEmpty;
           const uint32_t key = on ? cell_key_of(a.sm.geo, X, Yc, Z) : kCellEmpty;
           if (key != kCellEmpty) {
-            cs = cell_slot(a.sm.geo, fig, key, a.err);
+            const uint32_t cs = cell_slot(a.sm.geo, fig, key, a.err);
             if (cs != kCellEmpty) {
               const uint32_t g = a.sm.geo.g;
-              first = geo_cell_add_first(a.sm.geo, fig, cs, P.local_index, 1, X - (key & 1023u) * g,
-                                         Yc - ((key >> 10) & 1023u) * g, Z - (key >> 20) * g);
+              geo_cell_add(a.sm.geo, fig, cs, P.local_index, 1, X - (key & 1023u) * g, Yc - ((key >> 10) & 1023u) * g,
+                           Z - (key >> 20) * g);
             }
           }
-          log_append(a, a.sm.geo, fig, first, cs, lane);
         }
         if (a.sm.col.on && a.has_attr) {
-          bool first = false; uint32_t cs = kCellEmpty;
           const uint32_t key = (on && bt == 2) ? cell_key_of(a.sm.col, X, Yc, Z) : kCellEmpty;
           if (key != kCellEmpty) {
-            cs = cell_slot(a.sm.col, fig, key, a.err);
-            if (cs != kCellEmpty) first = col_cell_add_first(a.sm.col, fig, cs, P.local_index, 1, Y, U, V, (unsigned long long)Y * Y);
+            const uint32_t cs = cell_slot(a.sm.col, fig, key, a.err);
+            if (cs != kCellEmpty) col_cell_add(a.sm.col, fig, cs, P.local_index, 1, Y, U, V, (unsigned long long)Y * Y);
           }
-          log_append(a, a.sm.col, fig, first, cs, lane);
         }
         if (on && bt == 1) {
           const uint32_t li = atomicAdd(&a.sm.blist_count[frame], 1u);
@@ -813,53 +791,31 @@ __device__ __forceinline__ void boundary_masks(const UnpackArgs& a, const WorkRe
 
 __device__ __forceinline__ void stg_u32(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
 
-// append a warp's queue of first-touched table slots to the frame's log (one atomicAdd); out of line: rare
-__device__ __noinline__ void flush_queue(uint32_t* log, uint32_t* log_count, uint64_t log_cap, const uint32_t* queue, uint32_t nq,
-                                         int* err) {
-  const uint32_t lane = lane_id();
-  uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(log_count, nq);
-  base = __shfl_sync(kFull, base, 0);
-  __syncwarp();
-  for (uint32_t i = lane; i < nq; i += 32) {
-    if ((uint64_t)base + i < log_cap) log[base + i] = queue[i];
-    else atomicExch(err, 11);
-  }
-  __syncwarp();
-}
-
 // ---- smoothing work of the emit loop (K6 / K7 statistics + boundary list), one call per 32-point window -----------------
-// Latency discipline: a window ISSUES its cell reductions; whether it was the first toucher of a cell (the returned old
-// value of the atomicMax) is looked at one window later, so the round trip overlaps the next window's work.  First-touched
-// cells are queued in shared memory and appended to the frame's log with one atomicAdd per 32 entries.
+// Every cell update is a fire-and-forget reduction, so nothing in the loop waits for the memory system.  A slot "claims" a
+// cell (patch max / min + the cell's bit in the frame's touched bitmap) once, remembered in a warp-local memo; the sums go
+// out with every flushed run.  Which cells were touched / are multi-patch is read off the bitmaps by later passes.
 struct SmoothState {
   uint32_t frame, fig, patch, lane, lbase, n_done;
-  uint32_t* q;                   // [2][64] queued table slots: geometry, colour
-  uint32_t nq_geo, nq_col;       // warp-uniform fill of the two queues
-  // Claims issued kDepth windows ago (window parity selects the slot when the loop body is instantiated twice;
-  // cs == kCellEmpty: none)
-  uint32_t pend_geo_old[2], pend_geo_cs[2], pend_col_old[2], pend_col_cs[2];
-  bool pend_col_any[2];          // warp-uniform: that window issued colour reductions
   uint32_t* memo;                // [2][32] cells this warp has already claimed for its slot (direct-mapped, geometry / colour)
   GeoCell* geo_tab;              // this frame's tables
   ColCell* col_tab;
-  uint32_t* geo_mb;              // this frame's multi-patch bitmaps
-  uint32_t* col_mb;
+  uint32_t* geo_tb;              // this frame's touched bitmaps
+  uint32_t* col_tb;
 
   __device__ __forceinline__ void init(const UnpackArgs& a, uint32_t frame_, uint32_t fig_, uint32_t patch_, uint32_t lane_,
-                                       uint32_t* queue) {
-    frame = frame_; fig = fig_; patch = patch_; lane = lane_; lbase = 0; n_done = 0; q = queue; nq_geo = nq_col = 0;
-    for (int i = 0; i < 2; ++i) { pend_geo_old[i] = pend_col_old[i] = 1; pend_geo_cs[i] = pend_col_cs[i] = kCellEmpty; pend_col_any[i] = false; }
-    memo = queue + 128;
+                                       uint32_t* memo_) {
+    frame = frame_; fig = fig_; patch = patch_; lane = lane_; lbase = 0; n_done = 0;
+    memo = memo_;
     memo[lane] = kCellEmpty; memo[32 + lane] = kCellEmpty;
     __syncwarp();
     geo_tab = reinterpret_cast<GeoCell*>(a.sm.geo.table) + (uint64_t)fig * a.sm.geo.slots;
     col_tab = reinterpret_cast<ColCell*>(a.sm.col.table) + (uint64_t)fig * a.sm.col.slots;
-    geo_mb = a.sm.geo.mbits + (uint64_t)fig * a.sm.geo.mwords;
-    col_mb = a.sm.col.mbits + (uint64_t)fig * a.sm.col.mwords;
+    geo_tb = a.sm.geo.tbits + (uint64_t)fig * a.sm.geo.mwords;
+    col_tb = a.sm.col.tbits + (uint64_t)fig * a.sm.col.mwords;
   }
   // true when this warp claimed `cs` before (then the claim is skipped); remembers it otherwise.  Two lanes of one window may
-  // both miss on the same cell: the claim is then simply issued twice.
+  // both miss on the same cell: the claim is then simply issued twice (it is idempotent).
   __device__ __forceinline__ bool claimed_before(uint32_t* m, uint32_t cs) const {
     const uint32_t e = (cs ^ (cs >> 7) ^ (cs >> 14)) & 31u;
     if (m[e] == cs) return true;
@@ -870,30 +826,10 @@ struct SmoothState {
   static __device__ __forceinline__ uint32_t fast_slot(const GridDesc& G, uint32_t key) {
     return (key & 0xFFu) | ((key >> 16) << G.w_shift) | (((key >> 8) & 0xFFu) << (2u * G.w_shift));
   }
-  __device__ __forceinline__ void flush(const UnpackArgs& a, const GridDesc& G, uint32_t* queue, uint32_t& nq) {
-    flush_queue(G.log + (uint64_t)fig * G.log_cap, &G.log_count[fig], G.log_cap, queue, nq, a.err);
-    nq = 0;
-  }
-  // retire the reductions issued one window ago: queue the cells this warp touched first
-  __device__ __forceinline__ void retire(const UnpackArgs& a, const GridDesc& G, void* tab, uint32_t* mb, uint32_t* queue,
-                                         uint32_t& nq, uint32_t old, uint32_t cs) {
-    // the cell had been claimed by another patch: it is a multi-patch cell (idempotent plain store into the 32-byte cell +
-    // its bit in the frame's bitmap)
-    if (cs != kCellEmpty && old != 0u && old != patch + 1u) {
-      reinterpret_cast<volatile uint32_t*>(static_cast<uint8_t*>(tab) + (size_t)cs * 32u)[1] = 1u;
-      atomicOr(mb + (cs >> 5), 1u << (cs & 31u));
-    }
-    const bool first = cs != kCellEmpty && old == 0u;
-    const uint32_t fm = __ballot_sync(kFull, first);
-    if (fm == 0) return;
-    if (first) queue[nq + __popc(fm & ((1u << lane) - 1u))] = cs;
-    nq += __popc(fm);
-    if (nq > 32u) flush(a, G, queue, nq);
-  }
 
   // kFast: both grids are known (at launch) to be dense power-of-two grids with cell edge <= 8 (geometry): the generic
   // branches drop out of the instantiation, which keeps the hot loop small
-  template <bool kFast, int kSlot>
+  template <bool kFast>
   __device__ __forceinline__ void point(const UnpackArgs& a, bool valid, uint32_t g, uint32_t w0, uint32_t w1, uint32_t Y,
                                         uint32_t uv, uint32_t bt, bool has_attr) {
     const uint32_t X = w0 & 0xFFFFu, Yc = w0 >> 16, Z = w1 & 0xFFFFu;
@@ -945,16 +881,11 @@ struct SmoothState {
         cnt = v0 & 0xFFFFu; sx = v0 >> 16; sy = v1 & 0xFFFFu; sz = v1 >> 16;
       }
       const bool tail = key != kCellEmpty && (lane == 31u || ((heads >> 1) >> lane) & 1u);
-      retire(a, G, geo_tab, geo_mb, q, nq_geo, pend_geo_old[kSlot], pend_geo_cs[kSlot]);   // claims issued one / two windows ago
-      pend_geo_old[kSlot] = 1; pend_geo_cs[kSlot] = kCellEmpty;
       if (tail) {
         const uint32_t cs = fast8 ? fast_slot(G, key) : cell_slot(G, fig, key, a.err);
         if (cs != kCellEmpty) {
           GeoCell* c = geo_tab + cs;
-          if (!claimed_before(memo, cs)) {
-            pend_geo_cs[kSlot] = cs;
-            pend_geo_old[kSlot] = atomicCAS(&c->first1, 0u, patch + 1u);   // 0: first touch; another patch + 1: multi-patch cell
-          }
+          if (!claimed_before(memo, cs)) cell_claim(&c->pmax1, geo_tb, cs, patch);
           atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
           atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
         }
@@ -963,11 +894,6 @@ struct SmoothState {
     // K7 statistics: colour cells over the type-2 (second ring) points
     if (a.sm.col.on && has_attr) {
       const GridDesc& G = a.sm.col;
-      if (pend_col_any[kSlot]) {
-        retire(a, G, col_tab, col_mb, q + 64, nq_col, pend_col_old[kSlot], pend_col_cs[kSlot]);
-        pend_col_old[kSlot] = 1; pend_col_cs[kSlot] = kCellEmpty;
-      }
-      pend_col_any[kSlot] = __any_sync(kFull, bt == 2u);
       if (bt == 2u) {
         uint32_t cs = kCellEmpty;
         if (kFast || G.fast) {
@@ -978,10 +904,7 @@ struct SmoothState {
         }
         if (cs != kCellEmpty) {
           ColCell* c = col_tab + cs;
-          if (!claimed_before(memo + 32, cs)) {
-            pend_col_cs[kSlot] = cs;
-            pend_col_old[kSlot] = atomicCAS(&c->first1, 0u, patch + 1u);
-          }
+          if (!claimed_before(memo + 32, cs)) cell_claim(&c->pmax1, col_tb, cs, patch);
           atomicAdd(&c->cnt_sy, 1ull | ((unsigned long long)Y << 24));
           atomicAdd(&c->su_sv, (unsigned long long)(uv & 0xFFFFu) | ((unsigned long long)(uv >> 16) << 32));
           atomicAdd(&c->sy2, (unsigned long long)Y * Y);
@@ -1001,18 +924,6 @@ struct SmoothState {
     n_done += __popc(bm);
   }
 
-  __device__ __forceinline__ void finish(const UnpackArgs& a) {
-    if (a.sm.geo.on) {
-      retire(a, a.sm.geo, geo_tab, geo_mb, q, nq_geo, pend_geo_old[0], pend_geo_cs[0]);
-      retire(a, a.sm.geo, geo_tab, geo_mb, q, nq_geo, pend_geo_old[1], pend_geo_cs[1]);
-      if (nq_geo) flush(a, a.sm.geo, q, nq_geo);
-    }
-    if (a.sm.col.on) {
-      retire(a, a.sm.col, col_tab, col_mb, q + 64, nq_col, pend_col_old[0], pend_col_cs[0]);
-      retire(a, a.sm.col, col_tab, col_mb, q + 64, nq_col, pend_col_old[1], pend_col_cs[1]);
-      if (nq_col) flush(a, a.sm.col, q + 64, nq_col);
-    }
-  }
 };
 
 // ---- pass 3: emit ------------------------------------------------------------------------------------------------------------
@@ -1024,9 +935,6 @@ struct SmoothState {
 // use 16-bit / 8-bit stores.
 #ifndef TMC2_MINCTA
 #define TMC2_MINCTA 4
-#endif
-#ifndef TMC2_CLAIM_DEPTH
-#define TMC2_CLAIM_DEPTH 1
 #endif
 #ifndef TMC2_SMOOTH_MINCTA
 #define TMC2_SMOOTH_MINCTA 3
@@ -1049,7 +957,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
     generic_slot_emit<kSmooth, kDebug>(a, R.pid, frame, fig, R.u0b, R.v0b, (uint64_t)frame * a.out.cap + run_base);
     return;
   }
-  uint8_t* wsm = smem + (size_t)warp * (kSmooth ? kWarpSmemBytes : kOffLogQ);
+  uint8_t* wsm = smem + (size_t)warp * (kSmooth ? kWarpSmemBytes : kOffMemo);
   uint32_t* s_pt = reinterpret_cast<uint32_t*>(wsm + kOffPt);
   uint4* s_term = reinterpret_cast<uint4*>(wsm + kOffTerm);
   uint16_t* s_src = reinterpret_cast<uint16_t*>(wsm + kOffSrc);
@@ -1198,7 +1106,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
 
   SmoothState S;
   if (kSmooth) {
-    S.init(a, frame, fig, patch, lane, reinterpret_cast<uint32_t*>(wsm + kOffLogQ));
+    S.init(a, frame, fig, patch, lane, reinterpret_cast<uint32_t*>(wsm + kOffMemo));
     if (n_boundary) {
       const uint32_t lbase = __shfl_sync(kFull, lbase0, 0);
       if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
@@ -1215,10 +1123,8 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
   uint16_t* ppos = a.out.pos + (gframe + g) * 3;                   // this lane's point in the packed position stream
   uint8_t* prgb = has_attr ? a.out.rgb + (gframe + g) * 3 : nullptr;
   const uint16_t* psrc = s_src + (int32_t)k;
-  // one 32-point window; returns false when the run is exhausted.  kSlot selects the pending-claim registers (see SmoothState)
-  auto window = [&](auto slot_tag) -> bool {
-    constexpr int kSlot = decltype(slot_tag)::value;
-    if (!(g - lane < run_end)) return false;
+#pragma unroll 1
+  for (; g - lane < run_end; g += 32, k += 32, ppos += 96, prgb += 96, psrc += 32) {
     const bool valid = k < total;
     const uint32_t vb = __ballot_sync(kFull, valid);
     const uint32_t e = valid ? (uint32_t)*psrc : 0u;               // rank << 1 | map
@@ -1282,16 +1188,8 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
       }
       if (a.out.btype) a.out.btype[gk] = (uint8_t)bt;
     }
-    if (kSmooth) S.template point<kFast, kSlot>(a, valid, g, w0, w1, Y, uv, bt, has_attr);
-    g += 32; k += 32; ppos += 96; prgb += 96; psrc += 32;
-    return true;
-  };
-  if (kSmooth && kFast && TMC2_CLAIM_DEPTH == 2) {   // two instantiations of the body: a claim's round trip overlaps two windows
-    while (window(std::integral_constant<int, 0>{}) && window(std::integral_constant<int, 1>{})) {}
-  } else {
-    while (window(std::integral_constant<int, 0>{})) {}
+    if (kSmooth) S.template point<kFast>(a, valid, g, w0, w1, Y, uv, bt, has_attr);
   }
-  if (kSmooth) S.finish(a);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1322,21 +1220,21 @@ __device__ __forceinline__ uint32_t mean_q8_u32(uint32_t s, uint32_t cnt) {     
 //   geometry: y = mean x | mean y << 16, z = mean z   (Q8, relative to the cell origin, < 256 * g <= 65536)
 //   colour:   y = mean Y, z = mean U, w = mean V      (Q8)
 constexpr uint32_t kCellMulti = 0x40000000u, kCellUsable = 0x20000000u, kCellCount = 0x00FFFFFFu;
-__device__ __forceinline__ uint4 geo_summary(const uint4& v0, const uint4& v1) {   // first1, multi, count, sx ; sy, sz, -, -
+__device__ __forceinline__ uint4 geo_summary(const uint4& v0, const uint4& v1) {   // pmax1, pminc, count, sx ; sy, sz, -, -
   const uint32_t cnt = v0.z;
   if (cnt == 0) return make_uint4(0, 0, 0, 0);
-  const uint32_t multi = v0.y != 0u ? kCellMulti : 0u;
+  const uint32_t multi = (v0.x - 1u) != ~v0.y ? kCellMulti : 0u;
   const uint32_t mx = mean_q8_u32(v0.w, cnt), my = mean_q8_u32(v1.x, cnt), mz = mean_q8_u32(v1.y, cnt);
   return make_uint4(multi | (cnt & kCellCount), mx | (my << 16), mz, 0u);
 }
 __device__ __forceinline__ uint4 col_summary(const uint4& v0, const uint4& v1, uint32_t thr_col_var, int* err) {
-  // first1, multi, cnt_sy (lo, hi) ; su, sv, sy2 (lo, hi)
+  // pmax1, pminc, cnt_sy (lo, hi) ; su, sv, sy2 (lo, hi)
   const unsigned long long w0 = (unsigned long long)v0.z | ((unsigned long long)v0.w << 32);
   const unsigned long long sy2 = (unsigned long long)v1.z | ((unsigned long long)v1.w << 32);
   const unsigned long long cnt = w0 & 0xFFFFFFull, sy = w0 >> 24, su = v1.x, sv = v1.y;
   if (cnt == 0) return make_uint4(0, 0, 0, 0);
   if (cnt > 65536ull) atomicExch(err, 6);       // the packed U / V sums are only exact up to 65536 points per cell
-  const uint32_t multi = v0.y != 0u ? kCellMulti : 0u;
+  const uint32_t multi = (v0.x - 1u) != ~v0.y ? kCellMulti : 0u;
   uint32_t my, mu, mv;
   if (sy < (1ull << 24) && cnt < (1ull << 24)) {                          // the usual case fits 32-bit division
     const uint32_t c32 = (uint32_t)cnt;
@@ -1571,24 +1469,51 @@ __global__ void __launch_bounds__(128) smooth_apply_kernel(const __grid_constant
   }
 }
 
-// back to all-zero cells (and free keys) for the next group: walk the same logs
+// After the emit: which touched cells are multi-patch?  One thread per word of the frame's touched bitmap (32 table slots);
+// the answer goes into the matching word of the multi-patch bitmap, which is all the probe pass reads.
+__global__ void __launch_bounds__(256) smooth_collect_kernel(const __grid_constant__ UnpackArgs a) {
+  const uint32_t fig = blockIdx.y;
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const GridDesc& G = which ? a.sm.col : a.sm.geo;
+    if (!G.on) continue;
+    const uint32_t* tb = G.tbits + (uint64_t)fig * G.mwords;
+    uint32_t* mb = G.mbits + (uint64_t)fig * G.mwords;
+    const uint2* tab = reinterpret_cast<const uint2*>(G.table) + ((uint64_t)fig * G.slots) * 4;      // 32-byte cells
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < G.mwords; w += (uint64_t)gridDim.x * blockDim.x) {
+      uint32_t t = tb[w], m = 0;
+      while (t) {
+        const uint32_t b = (uint32_t)__ffs(t) - 1u;
+        t &= t - 1u;
+        const uint2 pm = tab[(w * 32u + b) * 4];                              // pmax1, pminc
+        if ((pm.x - 1u) != ~pm.y) m |= 1u << b;
+      }
+      if (m) mb[w] = m;
+    }
+  }
+}
+
+// back to all-zero cells (free keys, clean bitmaps) for the next launch: the touched bitmap names the cells
 __global__ void __launch_bounds__(256) smooth_clear_kernel(const __grid_constant__ UnpackArgs a) {
   const uint32_t fig = blockIdx.y;
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
     const GridDesc& G = which ? a.sm.col : a.sm.geo;
     if (!G.on) continue;
-    const uint32_t n = (uint32_t)min((uint64_t)G.log_count[fig], G.log_cap);
-    const uint32_t* log = G.log + (uint64_t)fig * G.log_cap;
+    uint32_t* tb = G.tbits + (uint64_t)fig * G.mwords;
+    uint32_t* mb = G.mbits + (uint64_t)fig * G.mwords;
     uint4* tab = reinterpret_cast<uint4*>(G.table) + ((uint64_t)fig * G.slots) * 2;      // 32-byte cells
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-      const uint32_t cs = log[i];
-      // a multi-patch cell also has its bit in the frame's bitmap: the whole word goes (its other bits belong to cells of
-      // the same log)
-      if (reinterpret_cast<const uint32_t*>(tab + (uint64_t)cs * 2)[1] != 0u) G.mbits[(uint64_t)fig * G.mwords + (cs >> 5)] = 0u;
-      tab[(uint64_t)cs * 2] = make_uint4(0, 0, 0, 0);
-      tab[(uint64_t)cs * 2 + 1] = make_uint4(0, 0, 0, 0);
-      if (!G.identity) G.keys[(uint64_t)fig * G.slots + cs] = kCellEmpty;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < G.mwords; w += (uint64_t)gridDim.x * blockDim.x) {
+      uint32_t t = tb[w];
+      if (t == 0) continue;
+      tb[w] = 0; mb[w] = 0;
+      while (t) {
+        const uint64_t cs = w * 32u + ((uint32_t)__ffs(t) - 1u);
+        t &= t - 1u;
+        tab[cs * 2] = make_uint4(0, 0, 0, 0);
+        tab[cs * 2 + 1] = make_uint4(0, 0, 0, 0);
+        if (!G.identity) G.keys[(uint64_t)fig * G.slots + cs] = kCellEmpty;
+      }
     }
   }
 }
@@ -1622,7 +1547,7 @@ int launch_compact_owned(const UnpackArgs& a, void* stream) {
 
 template <bool kSmooth, bool kDebug, bool kFast>
 static int launch_emit_t(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, cudaStream_t s) {
-  const size_t smem = (size_t)(kSmooth ? kWarpSmemBytes : kOffLogQ) * kWarpsPerTile;   // the log queues are smoothing-only
+  const size_t smem = (size_t)(kSmooth ? kWarpSmemBytes : kOffMemo) * kWarpsPerTile;   // the log queues are smoothing-only
   cudaError_t e = cudaFuncSetAttribute((const void*)emit_kernel<kSmooth, kDebug, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   emit_kernel<kSmooth, kDebug, kFast><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin);
@@ -1662,8 +1587,11 @@ int launch_upsample(const UnpackArgs& a, uint8_t* occ_full, void* stream) {
 int launch_smooth_filter(const UnpackArgs& a, void* stream) {
   if (a.sm.group_frames == 0) return 0;
   const unsigned bx = post_blocks(a.sm.group_frames);
-  smooth_probe_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
+  smooth_collect_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
   int e = after_launch();
+  if (e) return e;
+  smooth_probe_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
+  e = after_launch();
   if (e) return e;
   smooth_apply_kernel<<<dim3(bx, a.sm.group_frames), 128, 0, (cudaStream_t)stream>>>(a);
   return after_launch();

@@ -263,11 +263,10 @@ struct Batch {
 
   DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_count, d_err, d_work, d_owned_count;
   DevBuf d_pos, d_rgb, d_yuv, d_part, d_pix, d_bt, d_occ_full, d_pos_pre, d_yuv_pre;
-  DevBuf d_geotab, d_coltab, d_geokeys, d_colkeys, d_geolog, d_collog, d_geolog_count, d_collog_count, d_changed, d_blist,
-      d_blist_count, d_slist, d_slist_count, d_geombits, d_colmbits;
+  DevBuf d_geotab, d_coltab, d_geokeys, d_colkeys, d_changed, d_blist,
+      d_blist_count, d_slist, d_slist_count, d_geombits, d_colmbits, d_geotbits, d_coltbits;
   uint64_t geotab_slots = 0, coltab_slots = 0, geotab_frames = 0, coltab_frames = 0, blist_cap = 0;
   bool geotab_hashed = false, coltab_hashed = false;
-  uint64_t geolog_cap = 0, collog_cap = 0;
   uint32_t group_frames = 32;         // frames per smoothing group (one group = no post-pass tails between groups; a GOF is <= 32 frames)
   uint32_t group_frames_eff = 8;      // after fitting the dense tables into the memory budget
   std::vector<cudaEvent_t> ev_grp;    // 2 per group: around the unpack launch
@@ -296,8 +295,8 @@ struct Batch {
     for (DevBuf* b : {&d_occ, &d_geo, &d_ay, &d_au, &d_av, &d_meta, &d_b2p, &d_count, &d_err, &d_work,
                       &d_owned_count, &d_pos,
                       &d_rgb, &d_yuv, &d_part, &d_pix, &d_bt, &d_occ_full, &d_pos_pre, &d_yuv_pre, &d_geotab, &d_coltab,
-                      &d_geokeys, &d_colkeys, &d_geolog, &d_collog, &d_geolog_count, &d_collog_count, &d_changed, &d_blist,
-                      &d_blist_count, &d_slist, &d_slist_count, &d_geombits, &d_colmbits})
+                      &d_geokeys, &d_colkeys, &d_changed, &d_blist,
+                      &d_blist_count, &d_slist, &d_slist_count, &d_geombits, &d_colmbits, &d_geotbits, &d_coltbits})
       b->release();
     for (PinBuf* b : {&h_in, &h_meta, &h_small, &h_out}) b->release();
     for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -472,7 +471,7 @@ struct Batch {
         hashed = force_hash || cells * cell_bytes > kTableBudget;
         return hashed ? pow2_at_least(2 * cap) : cells;
       };
-      auto setup = [&](bool on, uint32_t g, size_t cell_bytes, DevBuf& tab, DevBuf& keys, DevBuf& mbits, uint64_t& slots_now,
+      auto setup = [&](bool on, uint32_t g, size_t cell_bytes, DevBuf& tab, DevBuf& keys, DevBuf& mbits, DevBuf& tbits, uint64_t& slots_now,
                        uint64_t& frames_now, bool& hashed_now) -> tmc2_status {
         if (!on) return TMC2_OK;
         bool hashed = false;
@@ -482,6 +481,8 @@ struct Batch {
           CU(cudaMemsetAsync(tab.p, 0, (size_t)TF * slots * cell_bytes, stream));     // all-zero == empty cell
           CU(mbits.ensure((size_t)TF * ((slots + 31) / 32) * 4));
           CU(cudaMemsetAsync(mbits.p, 0, (size_t)TF * ((slots + 31) / 32) * 4, stream));
+          CU(tbits.ensure((size_t)TF * ((slots + 31) / 32) * 4));
+          CU(cudaMemsetAsync(tbits.p, 0, (size_t)TF * ((slots + 31) / 32) * 4, stream));
           if (hashed) {
             CU(keys.ensure((size_t)TF * slots * 4));
             KL(launch_fill_u32(keys.as<uint32_t>(), (uint64_t)TF * slots, kCellEmpty, stream));
@@ -490,14 +491,8 @@ struct Batch {
         }
         return TMC2_OK;
       };
-      if (setup(smoothing_geo, params.grid_size, sizeof(GeoCell), d_geotab, d_geokeys, d_geombits, geotab_slots, geotab_frames, geotab_hashed)) return err.st;
-      if (setup(smoothing_col, params.cgrid_size, sizeof(ColCell), d_coltab, d_colkeys, d_colmbits, coltab_slots, coltab_frames, coltab_hashed)) return err.st;
-      // per-frame logs of the touched table slots (each cell once, by its first toucher; walked by finalize and clear)
-      geolog_cap = std::min<uint64_t>(cap, geotab_slots ? geotab_slots : cap);
-      collog_cap = std::min<uint64_t>(cap, coltab_slots ? coltab_slots : cap);
-      const size_t cnt_bytes = std::max<size_t>((size_t)TF * 4, 4);
-      if (smoothing_geo) { CU(d_geolog.ensure((size_t)TF * geolog_cap * 4)); CU(d_geolog_count.ensure(cnt_bytes)); }
-      if (smoothing_col) { CU(d_collog.ensure((size_t)TF * collog_cap * 4)); CU(d_collog_count.ensure(cnt_bytes)); }
+      if (setup(smoothing_geo, params.grid_size, sizeof(GeoCell), d_geotab, d_geokeys, d_geombits, d_geotbits, geotab_slots, geotab_frames, geotab_hashed)) return err.st;
+      if (setup(smoothing_col, params.cgrid_size, sizeof(ColCell), d_coltab, d_colkeys, d_colmbits, d_coltbits, coltab_slots, coltab_frames, coltab_hashed)) return err.st;
     }
     return TMC2_OK;
   }
@@ -638,8 +633,8 @@ struct Batch {
     a.want_btype = a.out.btype != nullptr || smooth;
     if (smooth) {
       const uint32_t maxs = 1u << params.geometry_bitdepth_3d;
-      auto grid = [&](GridDesc& G, bool on, uint32_t g, void* table, uint32_t* keys, uint64_t slots, bool hashed, uint32_t* log,
-                      uint32_t* log_count, uint64_t log_cap, uint32_t* mbits) {
+      auto grid = [&](GridDesc& G, bool on, uint32_t g, void* table, uint32_t* keys, uint64_t slots, bool hashed, uint32_t* mbits,
+                      uint32_t* tbits) {
         G.on = on ? 1 : 0;
         if (!on) return;
         G.g = g; G.w = (maxs + g - 1) / g; G.disth = std::max(g / 2, 1u); G.th = g * G.w;
@@ -658,13 +653,12 @@ struct Batch {
             G.cmask = (G.w - 1u) * 0x10001u;
           }
         }
-        G.log = log; G.log_count = log_count; G.log_cap = log_cap;
-        G.mbits = mbits; G.mwords = (slots + 31) / 32;
+        G.mbits = mbits; G.tbits = tbits; G.mwords = (slots + 31) / 32;
       };
       grid(a.sm.geo, smoothing_geo, params.grid_size, d_geotab.p, d_geokeys.as<uint32_t>(), geotab_slots, geotab_hashed,
-           d_geolog.as<uint32_t>(), d_geolog_count.as<uint32_t>(), geolog_cap, d_geombits.as<uint32_t>());
+           d_geombits.as<uint32_t>(), d_geotbits.as<uint32_t>());
       grid(a.sm.col, smoothing_col, params.cgrid_size, d_coltab.p, d_colkeys.as<uint32_t>(), coltab_slots, coltab_hashed,
-           d_collog.as<uint32_t>(), d_collog_count.as<uint32_t>(), collog_cap, d_colmbits.as<uint32_t>());
+           d_colmbits.as<uint32_t>(), d_coltbits.as<uint32_t>());
       a.sm.blist = d_blist.as<BoundaryEntry>(); a.sm.blist_count = d_blist_count.as<uint32_t>(); a.sm.blist_cap = blist_cap;
       a.sm.slist = d_slist.as<uint32_t>(); a.sm.slist_count = d_slist_count.as<uint32_t>();
       const uint32_t sc = params.attribute_bitdepth > 8 ? (1u << (params.attribute_bitdepth - 8)) : 1u;
@@ -732,9 +726,8 @@ struct Batch {
         if (!G0.on) return;
         G.table = static_cast<uint8_t*>(G0.table) + (size_t)set * GF * G0.slots * cell_bytes;
         G.keys = G0.keys ? G0.keys + (size_t)set * GF * G0.slots : nullptr;
-        G.log = G0.log + (size_t)set * GF * G0.log_cap;
-        G.log_count = G0.log_count + (size_t)set * GF;
         G.mbits = G0.mbits + (size_t)set * GF * G0.mwords;
+        G.tbits = G0.tbits + (size_t)set * GF * G0.mwords;
       };
       for (uint32_t gi = 0; gi < n_groups; ++gi) {
         const uint32_t f0 = gi * GF, f1 = std::min(F, f0 + GF), set = gi & 1u;
@@ -743,8 +736,6 @@ struct Batch {
         use_set(a.sm.col, col0, set, sizeof(ColCell));
         if (gi >= 2) CU(cudaStreamWaitEvent(s, ev_post[gi - 2], 0));          // this table set has been cleared
         if (clear_pending) { CU(cudaStreamWaitEvent(s, ev_tables_clean, 0)); clear_pending = false; }   // ... by the previous launch
-        if (smoothing_geo) CU(cudaMemsetAsync(a.sm.geo.log_count, 0, (size_t)GF * 4, s));
-        if (smoothing_col) CU(cudaMemsetAsync(a.sm.col.log_count, 0, (size_t)GF * 4, s));
         CU(cudaEventRecord(ev_grp[2 * gi], s));
         KL(launch_emit(a, true, h_ftb[f0], h_ftb[f1], s));
         CU(cudaEventRecord(ev_grp[2 * gi + 1], s));
