@@ -173,7 +173,8 @@ constexpr uint32_t kOffSrc = kOffTerm + 2048;                    // [512] u16: o
 constexpr uint32_t kOffCnt = kOffSrc + 1024;                     // [256] u8: points of the pixel (0..2) | boundary class << 2
 constexpr uint32_t kOffBmp = kOffCnt + 256;                      // [32] u32: 20x20 occupancy bitmap rows (canvas axes)
 constexpr uint32_t kOffMemo = kOffBmp + 128;                     // [2][32] u32: cells the slot has already claimed (smoothing only)
-constexpr uint32_t kWarpSmemBytes = kOffMemo + 256;
+constexpr uint32_t kOffTab = kOffMemo + 256;                     // [128] uint2: the slot's geometry-cell table (fast smoothing grids)
+constexpr uint32_t kWarpSmemBytes = kOffTab + 1024;
 
 // launch wrappers (kernels.cu); every one enqueues on `stream` and returns the cudaGetLastError() code
 int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream);

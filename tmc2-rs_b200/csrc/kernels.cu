@@ -802,12 +802,23 @@ struct SmoothState {
   ColCell* col_tab;
   uint32_t* geo_tb;              // this frame's touched bitmaps
   uint32_t* col_tb;
+  // kFast only: the slot's own geometry-cell table in shared memory, [4 bitangent][4 tangent][8 normal] cells from the slot's
+  // lowest cell (kmin, in packed-key form) -- a 16x16 block with lod 1 spans at most 3 cells of edge 8 along either tangential
+  // axis.  Entry = {count | sum x << 10, sum y | sum z << 12} (at most 512 points of offsets <= 7: 10 + 12 bits).
+  uint32_t* tab;
+  uint32_t kmin, bad, mul;       // local cell = key - kmin (valid iff no bit of `bad`); entry = (local * mul) >> 24
 
   __device__ __forceinline__ void init(const UnpackArgs& a, uint32_t frame_, uint32_t fig_, uint32_t patch_, uint32_t lane_,
-                                       uint32_t* memo_) {
+                                       uint32_t* memo_, bool with_table) {
     frame = frame_; fig = fig_; patch = patch_; lane = lane_; lbase = 0; n_done = 0;
     memo = memo_;
     memo[lane] = kCellEmpty; memo[32 + lane] = kCellEmpty;
+    tab = memo_ + 64;
+    if (with_table) {
+      reinterpret_cast<uint4*>(tab)[lane] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(tab)[32 + lane] = make_uint4(0, 0, 0, 0);
+    }
+    kmin = 0xFF000000u; bad = 0xFFFFFFFFu; mul = 0;                  // no table until table_origin() says otherwise
     __syncwarp();
     geo_tab = reinterpret_cast<GeoCell*>(a.sm.geo.table) + (uint64_t)fig * a.sm.geo.slots;
     col_tab = reinterpret_cast<ColCell*>(a.sm.col.table) + (uint64_t)fig * a.sm.col.slots;
@@ -827,16 +838,70 @@ struct SmoothState {
     return (key & 0xFFu) | ((key >> 16) << G.w_shift) | (((key >> 8) & 0xFFu) << (2u * G.w_shift));
   }
 
+  // byte of a packed cell key (cx | cz << 8 | cy << 16) that holds the cell coordinate of position axis `ax` (0 x, 1 y, 2 z)
+  static __device__ __forceinline__ uint32_t key_byte(uint32_t ax) { return ax == 0u ? 0u : ax == 2u ? 1u : 2u; }
+  // kFast: place the slot's table.  nmin = smallest normal coordinate of the slot's points, t0 / b0 = tangent / bitangent of
+  // pixel (0, 0) of the block, t_hi / b_hi of pixel (15, 15).  Without a table (degenerate axes, 16-bit wrap) every point takes
+  // the per-point path.
+  __device__ __forceinline__ void table_origin(const GridDesc& G, const DevPatch& P, uint32_t nmin, uint32_t t0, uint32_t b0,
+                                               uint32_t t_hi, uint32_t b_hi) {
+    const uint32_t an = P.normal, at = P.tangent, ab = P.bitangent;
+    const bool ok = an < 3u && at < 3u && ab < 3u && an != at && an != ab && at != ab && t_hi < 65536u && b_hi < 65536u;
+    if (!ok) return;
+    const uint32_t sn = 8u * key_byte(an), st = 8u * key_byte(at), sb = 8u * key_byte(ab);
+    kmin = (((nmin >> G.g_shift) & 0xFFu) << sn) | (((t0 >> G.g_shift) & 0xFFu) << st) | (((b0 >> G.g_shift) & 0xFFu) << sb);
+    bad = ~((7u << sn) | (3u << st) | (3u << sb));
+    mul = (1u << (24u - sn)) | (8u << (24u - st)) | (32u << (24u - sb));
+  }
+  // kFast, after the point loop: every non-empty entry of the slot's table goes to its cell (one claim + two reductions)
+  __device__ __forceinline__ void flush_table(const GridDesc& G, const DevPatch& P) {
+    __syncwarp();
+    const uint32_t sn = 8u * key_byte(P.normal), st = 8u * key_byte(P.tangent), sb = 8u * key_byte(P.bitangent);
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+      const uint32_t ent = 32u * i + lane;
+      const uint2 e = reinterpret_cast<const uint2*>(tab)[ent];
+      if (e.x == 0u) continue;
+      const uint32_t key = kmin + (((ent & 7u) << sn) | (((ent >> 3) & 3u) << st) | ((ent >> 5) << sb));
+      const uint32_t cs = fast_slot(G, key);
+      GeoCell* c = geo_tab + cs;
+      cell_claim(&c->pmax1, geo_tb, cs, patch);
+      atomicAdd(&c->cnt_sx, (unsigned long long)(e.x & 1023u) | ((unsigned long long)(e.x >> 10) << 32));
+      atomicAdd(&c->sy_sz, (unsigned long long)(e.y & 4095u) | ((unsigned long long)(e.y >> 12) << 32));
+    }
+  }
+
   // kFast: both grids are known (at launch) to be dense power-of-two grids with cell edge <= 8 (geometry): the generic
   // branches drop out of the instantiation, which keeps the hot loop small
   template <bool kFast>
   __device__ __forceinline__ void point(const UnpackArgs& a, bool valid, uint32_t g, uint32_t w0, uint32_t w1, uint32_t Y,
                                         uint32_t uv, uint32_t bt, bool has_attr) {
     const uint32_t X = w0 & 0xFFFFu, Yc = w0 >> 16, Z = w1 & 0xFFFFu;
-    // K6 statistics: geometry cells over ALL points (segmented scan over runs of equal cell, see below)
-    if (a.sm.geo.on) {
+    // K6 statistics: geometry cells over ALL points
+    if (kFast && a.sm.geo.on) {
+      // into the slot's shared-memory table (flushed once per slot); the rare point outside the table goes to its cell directly
       const GridDesc& G = a.sm.geo;
-      const bool fast8 = kFast || (G.fast && G.g <= 8u);            // packed single-word sums need 32 * (g - 1) < 256
+      if (valid && ((w0 | w1) & G.oob_mask) == 0u) {
+        const uint32_t m2 = (G.g - 1u) * 0x10001u;
+        const uint32_t key = ((w0 >> G.g_shift) & G.cmask) | ((w1 >> G.g_shift) << 8);          // cx | cz << 8 | cy << 16
+        const uint32_t rel = w0 & m2, relz = w1 & m2;                                           // w1's upper half is zero
+        const uint32_t d = key - kmin;
+        if ((d & bad) == 0u) {
+          uint32_t* e = tab + 2u * ((d * mul) >> 24);
+          atomicAdd(e, 1u | ((rel & 0xFFFFu) << 10));
+          atomicAdd(e + 1, (rel >> 16) | (relz << 12));
+        } else {
+          const uint32_t cs = fast_slot(G, key);
+          GeoCell* c = geo_tab + cs;
+          cell_claim(&c->pmax1, geo_tb, cs, patch);
+          atomicAdd(&c->cnt_sx, 1ull | ((unsigned long long)(rel & 0xFFFFu) << 32));
+          atomicAdd(&c->sy_sz, (unsigned long long)(rel >> 16) | ((unsigned long long)relz << 32));
+        }
+      }
+    } else if (!kFast && a.sm.geo.on) {
+      // generic grids: segmented scan over runs of equal cell, see below
+      const GridDesc& G = a.sm.geo;
+      const bool fast8 = G.fast && G.g <= 8u;                        // packed single-word sums need 32 * (g - 1) < 256
       uint32_t key = kCellEmpty, rx_ = 0, ry_ = 0, rz_ = 0, vfast = 0;
       if (fast8) {
         // cell coordinates straight from the packed position words (w1's upper half is zero)
@@ -863,7 +928,7 @@ struct SmoothState {
       const uint32_t heads = __ballot_sync(kFull, lane == 0 || kprev != key);
       const uint32_t dist = lane - (31u - (uint32_t)__clz(heads & (0xFFFFFFFFu >> (31u - lane))));   // lanes since the run began
       uint32_t cnt, sx, sy, sz;
-      if (kFast || G.g <= 8u) {             // one packed word: count | three sums of at most 32 * 7 (8 bits each)
+      if (G.g <= 8u) {             // one packed word: count | three sums of at most 32 * 7 (8 bits each)
         uint32_t v = fast8 ? vfast : (key != kCellEmpty ? (1u | (rx_ << 8) | (ry_ << 16) | (rz_ << 24)) : 0u);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -957,7 +1022,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
     generic_slot_emit<kSmooth, kDebug>(a, R.pid, frame, fig, R.u0b, R.v0b, (uint64_t)frame * a.out.cap + run_base);
     return;
   }
-  uint8_t* wsm = smem + (size_t)warp * (kSmooth ? kWarpSmemBytes : kOffMemo);
+  uint8_t* wsm = smem + (size_t)warp * (kSmooth ? (kFast ? kWarpSmemBytes : kOffTab) : kOffMemo);
   uint32_t* s_pt = reinterpret_cast<uint32_t*>(wsm + kOffPt);
   uint4* s_term = reinterpret_cast<uint4*>(wsm + kOffTerm);
   uint16_t* s_src = reinterpret_cast<uint16_t*>(wsm + kOffSrc);
@@ -970,7 +1035,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
   const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
   DevPatch P;
   load_patch_fields(a.patches + R.pid, P);
-  uint32_t n_boundary = 0, any_flag = 0, lbase0 = 0;
+  uint32_t n_boundary = 0, any_flag = 0, lbase0 = 0, nmin = 0;
 
   {
     // ---- (1): canvas layout ----------------------------------------------------------------------------------------
@@ -997,6 +1062,18 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
       n_boundary = __reduce_add_sync(kFull, __popc(b1) + __popc(b1 & L.m2));
       // room in the frame's boundary list for this slot; the answer is picked up right before the point loop
       if (n_boundary && lane == 0) lbase0 = atomicAdd(&a.sm.blist_count[frame], n_boundary);
+      if (kFast && a.sm.geo.on) {
+        // smallest normal coordinate among the slot's points (both maps; a skipped duplicate equals its map-0 point):
+        // origin of the slot's cell table along the projection axis
+        uint32_t lo = 0xFFFFFFFFu;
+        const uint32_t inv = ~L.m1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t off = (((inv >> (2 * q)) & 1u) * 0xFFFFu) | (((inv >> (2 * q + 1)) & 1u) * 0xFFFF0000u);
+          lo = __vminu2(lo, __vminu2(L.n0p[q] | off, L.n1p[q] | off));
+        }
+        nmin = __reduce_min_sync(kFull, min(lo & 0xFFFFu, lo >> 16));
+      }
     }
 
     // ---- (2): tables in patch raster order -----------------------------------------------------------------------------
@@ -1106,7 +1183,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
 
   SmoothState S;
   if (kSmooth) {
-    S.init(a, frame, fig, patch, lane, reinterpret_cast<uint32_t*>(wsm + kOffMemo));
+    S.init(a, frame, fig, patch, lane, reinterpret_cast<uint32_t*>(wsm + kOffMemo), kFast);
     if (n_boundary) {
       const uint32_t lbase = __shfl_sync(kFull, lbase0, 0);
       if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
@@ -1115,6 +1192,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
       }
       S.lbase = lbase;
     }
+    if (kFast && a.sm.geo.on) S.table_origin(a.sm.geo, P, nmin, T00, B00, T00 + 15u * lodx, B00 + 15u * lody);
   }
 
   const uint32_t run_end = run_base + total;
@@ -1190,6 +1268,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
     }
     if (kSmooth) S.template point<kFast>(a, valid, g, w0, w1, Y, uv, bt, has_attr);
   }
+  if (kSmooth && kFast && a.sm.geo.on) S.flush_table(a.sm.geo, P);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1547,7 +1626,7 @@ int launch_compact_owned(const UnpackArgs& a, void* stream) {
 
 template <bool kSmooth, bool kDebug, bool kFast>
 static int launch_emit_t(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, cudaStream_t s) {
-  const size_t smem = (size_t)(kSmooth ? kWarpSmemBytes : kOffMemo) * kWarpsPerTile;   // the log queues are smoothing-only
+  const size_t smem = (size_t)(kSmooth ? (kFast ? kWarpSmemBytes : kOffTab) : kOffMemo) * kWarpsPerTile;   // memo / cell table: smoothing only
   cudaError_t e = cudaFuncSetAttribute((const void*)emit_kernel<kSmooth, kDebug, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   emit_kernel<kSmooth, kDebug, kFast><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin);
