@@ -345,6 +345,46 @@ def test_random_small_atlases_with_smoothing(gpu_ctx, case, grids):
     assert got["smoothed_positions"] == want["smoothed_positions"] and got["smoothed_colors"] == want["smoothed_colors"]
 
 
+FAST_CASES = [
+    dict(seed=21, orientations=(0, 1), W=208, H=112, n_patches=14),
+    dict(seed=22, orientations=tuple(range(9)), spec=True, W=208, H=112, n_patches=14),
+    dict(seed=23, orientations=(0, 1, 8), extreme=True, W=96, H=64, n_patches=8),
+    dict(seed=24, orientations=(0, 1), prec=2, W=64, H=64),
+    dict(seed=25, orientations=(0, 1), absolute_d1=False, W=96, H=64, n_patches=8),
+]
+
+
+@pytest.mark.parametrize("case", FAST_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items() if k != "orientations"))
+@pytest.mark.parametrize("content", ["smooth", "noisy", "asis"])
+@pytest.mark.parametrize("grids", [(8, 4), (4, 2), (2, 8)], ids=["g8c4", "g4c2", "g2c8"])
+def test_streaming_smoothing_fast_grids(gpu_ctx, case, content, grids):
+    """The production (non-debug) smoothing instantiation for dense power-of-two grids keeps per-slot cell tables in shared
+    memory: frames from submit_gof / next_frame must equal the oracle on slowly varying depth (everything lands in the
+    table), on noisy depth (a slot spans more cells along the projection axis than its table holds: per-point path) and on
+    the generator's own patches (level of detail 2, 16-bit wrap of the tangential coordinates: no table at all)."""
+    g = util.random_small_gof(frames=2, **case)
+    if content != "asis":
+        geo = g.geo.copy()
+        util.crowd_into_one_region(g)
+        if content == "noisy":
+            g.geo[:] = geo
+    g.params.geometry_smoothing = True
+    g.params.color_smoothing = True
+    g.params.grid_size, g.params.cgrid_size = grids
+    g.params.threshold_smoothing = 4
+    g.params.threshold_color_smoothing = 2
+    g.params.threshold_color_variation = 200
+    g.params.threshold_color_difference = 200
+    view = abi.GofView(g)
+    frames = gpu_ctx.decode_gof(view)
+    for f, fr in enumerate(frames):
+        want = oracle.reconstruct_frame(view, f)
+        assert len(fr) == want["point_count"]
+        assert np.array_equal(fr.positions, want["positions"]), (case, content, f)
+        assert np.array_equal(fr.colors, want["colors"]), (case, content, f)
+        assert fr.smoothed_positions == want["smoothed_positions"] and fr.smoothed_colors == want["smoothed_colors"]
+
+
 def test_one_process_two_devices_shard_frames_in_order():
     """SURVEY 8e inside ONE process: a context over two devices shards the frames of a GOF frame-wise (contiguous halves, no
     collective) and hands them back in order; results equal the single-device context.  Skipped on a one-GPU box."""

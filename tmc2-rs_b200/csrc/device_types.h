@@ -92,18 +92,19 @@ struct Outputs {                // any pointer may be null = stream not wanted
 
 // ---- voxel-cell tables of the grid smoothing stages (own spec) ------------------------------------------
 // A cell is written only with fire-and-forget reductions (RED): two max, two / three 64-bit adds.  All-zero == empty.
-// "multi-patch" (the smoothing trigger) <=> max(patch) != min(patch) <=> pmax1 - 1 != ~pminc.
+// "multi-patch" (the smoothing trigger) <=> two different patches touched the cell: the first toucher claims `first1` with
+// a compare-and-swap (0 -> patch + 1); whoever finds another patch's claim stores 1 into `multi` (idempotent).
 // The finalize pass (once per touched cell, before the filter) turns the sums into Q8 means.
 constexpr uint32_t kCellEmpty = 0xFFFFFFFFu;      // free slot of a hashed table's key array
 struct GeoCell {     // 32 B = one DRAM sector
-  uint32_t pmax1;               // max(patch index + 1), 0 = untouched
-  uint32_t pminc;               // max(~patch index)
+  uint32_t first1;              // patch index + 1 of the first toucher, 0 = untouched
+  uint32_t multi;               // 1 = touched by more than one patch
   unsigned long long cnt_sx;    // count | sum(x - cell origin) << 32
   unsigned long long sy_sz;     // sum(y - origin) | sum(z - origin) << 32
   unsigned long long mean;      // finalize: Q8 means relative to the cell origin, 16 bits each (x | y<<16 | z<<32)
 };
 struct ColCell {     // 32 B
-  uint32_t pmax1, pminc;
+  uint32_t first1, multi;
   unsigned long long cnt_sy;    // count (24 bits) | sum(Y) << 24         finalize -> count | meanY_Q8 << 32
   unsigned long long su_sv;     // sum(U) | sum(V) << 32                  finalize -> meanU_Q8 | meanV_Q8 << 32
   unsigned long long sy2;       // sum(Y*Y)                               finalize -> 1 if the luminance variance test passes
@@ -127,8 +128,8 @@ struct GridDesc {               // geometry of one voxel grid
   uint64_t slots;               // table slots per frame-in-group (power of two unless identity)
   void*    table;               // GeoCell / ColCell [frames_in_group][slots]
   uint32_t* keys;               // hashed tables only: [frames_in_group][slots], kCellEmpty = free
-  uint32_t* tbits;              // [frames_in_group][mwords] one bit per table slot: the cell was touched (set by the emit)
-  uint32_t* mbits;              // [frames_in_group][mwords] ... the cell is multi-patch (set by the collect pass, read by the probe)
+  uint32_t* tbits;              // [frames_in_group][mwords] one bit per table slot: the cell was touched (set by its first toucher)
+  uint32_t* mbits;              // [frames_in_group][mwords] ... the cell is multi-patch (set by whoever finds another patch's claim, read by the probe)
   uint64_t mwords;
 };
 

@@ -547,25 +547,36 @@ __device__ __noinline__ uint32_t generic_slot_count(const UnpackArgs& a, uint32_
   return total;
 }
 
-// ---- smoothing: accumulate into a cell.  Every update is a fire-and-forget reduction (nothing is read back):
-//   pmax1 = max(patch + 1), pminc = max(~patch)  ->  multi-patch  <=>  pmax1 - 1 != ~pminc
-//   two / three 64-bit adds for the count and the sums, and the cell's bit in the frame's "touched" bitmap
-__device__ __forceinline__ void cell_claim(uint32_t* cell_words, uint32_t* tbits, uint32_t cs, uint32_t patch) {
-  atomicMax(cell_words, patch + 1u);
-  atomicMax(cell_words + 1, ~patch);
-  atomicOr(tbits + (cs >> 5), 1u << (cs & 31u));
+// ---- smoothing: accumulate into a cell.  The sums are fire-and-forget reductions (two / three 64-bit adds).  Who touched a
+// cell is settled by a CLAIM: compare-and-swap 0 -> patch + 1 on the cell's first word.  The first toucher (old value 0) sets
+// the cell's bit in the frame's "touched" bitmap (what the clear pass walks); whoever finds another patch's claim marks the
+// cell multi-patch (idempotent flag word in the cell + its bit in the frame's multi-patch bitmap, which the probe reads).
+__device__ __forceinline__ void claim_result(const GridDesc& G, uint32_t fig, uint32_t cs, uint32_t old, uint32_t patch) {
+  if (old == 0u) {
+    atomicOr(G.tbits + (uint64_t)fig * G.mwords + (cs >> 5), 1u << (cs & 31u));
+  } else if (old != patch + 1u) {
+    reinterpret_cast<volatile uint32_t*>(static_cast<uint8_t*>(G.table) + ((uint64_t)fig * G.slots + cs) * 32u)[1] = 1u;
+    atomicOr(G.mbits + (uint64_t)fig * G.mwords + (cs >> 5), 1u << (cs & 31u));
+  }
+}
+__device__ __forceinline__ uint32_t claim_issue(const GridDesc& G, uint32_t fig, uint32_t cs, uint32_t patch) {
+  return atomicCAS(reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(G.table) + ((uint64_t)fig * G.slots + cs) * 32u), 0u, patch + 1u);
+}
+// claim and wait for the answer (the rare paths)
+__device__ __forceinline__ void cell_claim_now(const GridDesc& G, uint32_t fig, uint32_t cs, uint32_t patch) {
+  claim_result(G, fig, cs, claim_issue(G, fig, cs, patch), patch);
 }
 __device__ __forceinline__ void geo_cell_add(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
                                              uint32_t sx, uint32_t sy, uint32_t sz) {
   GeoCell* c = reinterpret_cast<GeoCell*>(G.table) + (uint64_t)fig * G.slots + slot;
-  cell_claim(&c->pmax1, G.tbits + (uint64_t)fig * G.mwords, slot, patch);
+  cell_claim_now(G, fig, slot, patch);
   atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
   atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
 }
 __device__ __forceinline__ void col_cell_add(const GridDesc& G, uint32_t fig, uint32_t slot, uint32_t patch, uint32_t cnt,
                                              uint32_t sy, uint32_t su, uint32_t sv, unsigned long long sy2) {
   ColCell* c = reinterpret_cast<ColCell*>(G.table) + (uint64_t)fig * G.slots + slot;
-  cell_claim(&c->pmax1, G.tbits + (uint64_t)fig * G.mwords, slot, patch);
+  cell_claim_now(G, fig, slot, patch);
   atomicAdd(&c->cnt_sy, (unsigned long long)cnt | ((unsigned long long)sy << 24));
   atomicAdd(&c->su_sv, (unsigned long long)su | ((unsigned long long)sv << 32));
   atomicAdd(&c->sy2, sy2);
@@ -792,16 +803,15 @@ __device__ __forceinline__ void boundary_masks(const UnpackArgs& a, const WorkRe
 __device__ __forceinline__ void stg_u32(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
 
 // ---- smoothing work of the emit loop (K6 / K7 statistics + boundary list), one call per 32-point window -----------------
-// Every cell update is a fire-and-forget reduction, so nothing in the loop waits for the memory system.  A slot "claims" a
-// cell (patch max / min + the cell's bit in the frame's touched bitmap) once, remembered in a warp-local memo; the sums go
-// out with every flushed run.  Which cells were touched / are multi-patch is read off the bitmaps by later passes.
+// The sums are fire-and-forget reductions, so nothing in the loop waits for the memory system.  A slot claims each cell once,
+// and (fast grids) only after its point loop: geometry cells sit in the slot's shared-memory table anyway, colour cells are
+// remembered in a warp-local memo; all claims of the slot are then issued together and their answers looked at together.
 struct SmoothState {
   uint32_t frame, fig, patch, lane, lbase, n_done;
   uint32_t* memo;                // [2][32] cells this warp has already claimed for its slot (direct-mapped, geometry / colour)
   GeoCell* geo_tab;              // this frame's tables
   ColCell* col_tab;
-  uint32_t* geo_tb;              // this frame's touched bitmaps
-  uint32_t* col_tb;
+  uint32_t pend_cs, pend_old;    // a claim issued in the loop (memo entry taken by another cell); bit 31 of pend_cs: colour grid
   // kFast only: the slot's own geometry-cell table in shared memory, [4 bitangent][4 tangent][8 normal] cells from the slot's
   // lowest cell (kmin, in packed-key form) -- a 16x16 block with lod 1 spans at most 3 cells of edge 8 along either tangential
   // axis.  Entry = {count | sum x << 10, sum y | sum z << 12} (at most 512 points of offsets <= 7: 10 + 12 bits).
@@ -819,11 +829,10 @@ struct SmoothState {
       reinterpret_cast<uint4*>(tab)[32 + lane] = make_uint4(0, 0, 0, 0);
     }
     kmin = 0xFF000000u; bad = 0xFFFFFFFFu; mul = 0;                  // no table until table_origin() says otherwise
+    pend_cs = kCellEmpty; pend_old = 0;
     __syncwarp();
     geo_tab = reinterpret_cast<GeoCell*>(a.sm.geo.table) + (uint64_t)fig * a.sm.geo.slots;
     col_tab = reinterpret_cast<ColCell*>(a.sm.col.table) + (uint64_t)fig * a.sm.col.slots;
-    geo_tb = a.sm.geo.tbits + (uint64_t)fig * a.sm.geo.mwords;
-    col_tb = a.sm.col.tbits + (uint64_t)fig * a.sm.col.mwords;
   }
   // true when this warp claimed `cs` before (then the claim is skipped); remembers it otherwise.  Two lanes of one window may
   // both miss on the same cell: the claim is then simply issued twice (it is idempotent).
@@ -832,6 +841,22 @@ struct SmoothState {
     if (m[e] == cs) return true;
     m[e] = cs;
     return false;
+  }
+  // fast grids: remember `cs` for the claims after the loop.  Its memo entry may hold another cell: then this one is claimed
+  // right away, but the answer is looked at only when the next such claim comes up (or after the loop).
+  __device__ __forceinline__ void retire_pending(const UnpackArgs& a) {
+    if (pend_cs != kCellEmpty) {
+      claim_result((pend_cs >> 31) ? a.sm.col : a.sm.geo, fig, pend_cs & 0x7FFFFFFFu, pend_old, patch);
+      pend_cs = kCellEmpty;
+    }
+  }
+  __device__ __forceinline__ void claim_later(const UnpackArgs& a, uint32_t colour, uint32_t cs) {
+    const uint32_t prev = atomicCAS(memo + 32u * colour + ((cs ^ (cs >> 7) ^ (cs >> 14)) & 31u), kCellEmpty, cs);
+    if (prev != kCellEmpty && prev != cs) {
+      retire_pending(a);
+      pend_cs = cs | (colour << 31);
+      pend_old = claim_issue(colour ? a.sm.col : a.sm.geo, fig, cs, patch);
+    }
   }
   // dense slot of a cell from the packed key cx | cz << 8 | cy << 16 of a fast grid
   static __device__ __forceinline__ uint32_t fast_slot(const GridDesc& G, uint32_t key) {
@@ -853,22 +878,35 @@ struct SmoothState {
     bad = ~((7u << sn) | (3u << st) | (3u << sb));
     mul = (1u << (24u - sn)) | (8u << (24u - st)) | (32u << (24u - sb));
   }
-  // kFast, after the point loop: every non-empty entry of the slot's table goes to its cell (one claim + two reductions)
-  __device__ __forceinline__ void flush_table(const GridDesc& G, const DevPatch& P) {
+  // kFast, after the point loop: every non-empty entry of the slot's table goes to its cell (two reductions), and all claims
+  // of the slot -- table entries, memo entries of both grids, the pending one -- are issued before any answer is looked at
+  __device__ __forceinline__ void finish(const UnpackArgs& a, const DevPatch& P) {
     __syncwarp();
+    const GridDesc& G = a.sm.geo;
     const uint32_t sn = 8u * key_byte(P.normal), st = 8u * key_byte(P.tangent), sb = 8u * key_byte(P.bitangent);
+    uint32_t cs[6], old[6];
 #pragma unroll
     for (uint32_t i = 0; i < 4; ++i) {
+      cs[i] = kCellEmpty; old[i] = 0;
+      if (!G.on) continue;
       const uint32_t ent = 32u * i + lane;
       const uint2 e = reinterpret_cast<const uint2*>(tab)[ent];
       if (e.x == 0u) continue;
       const uint32_t key = kmin + (((ent & 7u) << sn) | (((ent >> 3) & 3u) << st) | ((ent >> 5) << sb));
-      const uint32_t cs = fast_slot(G, key);
-      GeoCell* c = geo_tab + cs;
-      cell_claim(&c->pmax1, geo_tb, cs, patch);
+      cs[i] = fast_slot(G, key);
+      GeoCell* c = geo_tab + cs[i];
+      old[i] = atomicCAS(&c->first1, 0u, patch + 1u);
       atomicAdd(&c->cnt_sx, (unsigned long long)(e.x & 1023u) | ((unsigned long long)(e.x >> 10) << 32));
       atomicAdd(&c->sy_sz, (unsigned long long)(e.y & 4095u) | ((unsigned long long)(e.y >> 12) << 32));
     }
+    cs[4] = G.on ? memo[lane] : kCellEmpty;
+    old[4] = cs[4] != kCellEmpty ? claim_issue(G, fig, cs[4], patch) : 0u;
+    cs[5] = a.sm.col.on ? memo[32u + lane] : kCellEmpty;
+    old[5] = cs[5] != kCellEmpty ? claim_issue(a.sm.col, fig, cs[5], patch) : 0u;
+    retire_pending(a);
+#pragma unroll
+    for (uint32_t i = 0; i < 6; ++i)
+      if (cs[i] != kCellEmpty) claim_result(i == 5 ? a.sm.col : G, fig, cs[i], old[i], patch);
   }
 
   // kFast: both grids are known (at launch) to be dense power-of-two grids with cell edge <= 8 (geometry): the generic
@@ -893,7 +931,7 @@ struct SmoothState {
         } else {
           const uint32_t cs = fast_slot(G, key);
           GeoCell* c = geo_tab + cs;
-          cell_claim(&c->pmax1, geo_tb, cs, patch);
+          claim_later(a, 0u, cs);
           atomicAdd(&c->cnt_sx, 1ull | ((unsigned long long)(rel & 0xFFFFu) << 32));
           atomicAdd(&c->sy_sz, (unsigned long long)(rel >> 16) | ((unsigned long long)relz << 32));
         }
@@ -950,7 +988,7 @@ struct SmoothState {
         const uint32_t cs = fast8 ? fast_slot(G, key) : cell_slot(G, fig, key, a.err);
         if (cs != kCellEmpty) {
           GeoCell* c = geo_tab + cs;
-          if (!claimed_before(memo, cs)) cell_claim(&c->pmax1, geo_tb, cs, patch);
+          if (!claimed_before(memo, cs)) cell_claim_now(G, fig, cs, patch);
           atomicAdd(&c->cnt_sx, (unsigned long long)cnt | ((unsigned long long)sx << 32));
           atomicAdd(&c->sy_sz, (unsigned long long)sy | ((unsigned long long)sz << 32));
         }
@@ -969,7 +1007,8 @@ struct SmoothState {
         }
         if (cs != kCellEmpty) {
           ColCell* c = col_tab + cs;
-          if (!claimed_before(memo + 32, cs)) cell_claim(&c->pmax1, col_tb, cs, patch);
+          if (kFast) claim_later(a, 1u, cs);
+          else if (!claimed_before(memo + 32, cs)) cell_claim_now(G, fig, cs, patch);
           atomicAdd(&c->cnt_sy, 1ull | ((unsigned long long)Y << 24));
           atomicAdd(&c->su_sv, (unsigned long long)(uv & 0xFFFFu) | ((unsigned long long)(uv >> 16) << 32));
           atomicAdd(&c->sy2, (unsigned long long)Y * Y);
@@ -1268,7 +1307,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
     }
     if (kSmooth) S.template point<kFast>(a, valid, g, w0, w1, Y, uv, bt, has_attr);
   }
-  if (kSmooth && kFast && a.sm.geo.on) S.flush_table(a.sm.geo, P);
+  if (kSmooth && kFast) S.finish(a, P);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1299,21 +1338,21 @@ __device__ __forceinline__ uint32_t mean_q8_u32(uint32_t s, uint32_t cnt) {     
 //   geometry: y = mean x | mean y << 16, z = mean z   (Q8, relative to the cell origin, < 256 * g <= 65536)
 //   colour:   y = mean Y, z = mean U, w = mean V      (Q8)
 constexpr uint32_t kCellMulti = 0x40000000u, kCellUsable = 0x20000000u, kCellCount = 0x00FFFFFFu;
-__device__ __forceinline__ uint4 geo_summary(const uint4& v0, const uint4& v1) {   // pmax1, pminc, count, sx ; sy, sz, -, -
+__device__ __forceinline__ uint4 geo_summary(const uint4& v0, const uint4& v1) {   // first1, multi, count, sx ; sy, sz, -, -
   const uint32_t cnt = v0.z;
   if (cnt == 0) return make_uint4(0, 0, 0, 0);
-  const uint32_t multi = (v0.x - 1u) != ~v0.y ? kCellMulti : 0u;
+  const uint32_t multi = v0.y != 0u ? kCellMulti : 0u;
   const uint32_t mx = mean_q8_u32(v0.w, cnt), my = mean_q8_u32(v1.x, cnt), mz = mean_q8_u32(v1.y, cnt);
   return make_uint4(multi | (cnt & kCellCount), mx | (my << 16), mz, 0u);
 }
 __device__ __forceinline__ uint4 col_summary(const uint4& v0, const uint4& v1, uint32_t thr_col_var, int* err) {
-  // pmax1, pminc, cnt_sy (lo, hi) ; su, sv, sy2 (lo, hi)
+  // first1, multi, cnt_sy (lo, hi) ; su, sv, sy2 (lo, hi)
   const unsigned long long w0 = (unsigned long long)v0.z | ((unsigned long long)v0.w << 32);
   const unsigned long long sy2 = (unsigned long long)v1.z | ((unsigned long long)v1.w << 32);
   const unsigned long long cnt = w0 & 0xFFFFFFull, sy = w0 >> 24, su = v1.x, sv = v1.y;
   if (cnt == 0) return make_uint4(0, 0, 0, 0);
   if (cnt > 65536ull) atomicExch(err, 6);       // the packed U / V sums are only exact up to 65536 points per cell
-  const uint32_t multi = (v0.x - 1u) != ~v0.y ? kCellMulti : 0u;
+  const uint32_t multi = v0.y != 0u ? kCellMulti : 0u;
   uint32_t my, mu, mv;
   if (sy < (1ull << 24) && cnt < (1ull << 24)) {                          // the usual case fits 32-bit division
     const uint32_t c32 = (uint32_t)cnt;
@@ -1548,30 +1587,6 @@ __global__ void __launch_bounds__(128) smooth_apply_kernel(const __grid_constant
   }
 }
 
-// After the emit: which touched cells are multi-patch?  One thread per word of the frame's touched bitmap (32 table slots);
-// the answer goes into the matching word of the multi-patch bitmap, which is all the probe pass reads.
-__global__ void __launch_bounds__(256) smooth_collect_kernel(const __grid_constant__ UnpackArgs a) {
-  const uint32_t fig = blockIdx.y;
-#pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    const GridDesc& G = which ? a.sm.col : a.sm.geo;
-    if (!G.on) continue;
-    const uint32_t* tb = G.tbits + (uint64_t)fig * G.mwords;
-    uint32_t* mb = G.mbits + (uint64_t)fig * G.mwords;
-    const uint2* tab = reinterpret_cast<const uint2*>(G.table) + ((uint64_t)fig * G.slots) * 4;      // 32-byte cells
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < G.mwords; w += (uint64_t)gridDim.x * blockDim.x) {
-      uint32_t t = tb[w], m = 0;
-      while (t) {
-        const uint32_t b = (uint32_t)__ffs(t) - 1u;
-        t &= t - 1u;
-        const uint2 pm = tab[(w * 32u + b) * 4];                              // pmax1, pminc
-        if ((pm.x - 1u) != ~pm.y) m |= 1u << b;
-      }
-      if (m) mb[w] = m;
-    }
-  }
-}
-
 // back to all-zero cells (free keys, clean bitmaps) for the next launch: the touched bitmap names the cells
 __global__ void __launch_bounds__(256) smooth_clear_kernel(const __grid_constant__ UnpackArgs a) {
   const uint32_t fig = blockIdx.y;
@@ -1666,11 +1681,8 @@ int launch_upsample(const UnpackArgs& a, uint8_t* occ_full, void* stream) {
 int launch_smooth_filter(const UnpackArgs& a, void* stream) {
   if (a.sm.group_frames == 0) return 0;
   const unsigned bx = post_blocks(a.sm.group_frames);
-  smooth_collect_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
-  int e = after_launch();
-  if (e) return e;
   smooth_probe_kernel<<<dim3(bx, a.sm.group_frames), 256, 0, (cudaStream_t)stream>>>(a);
-  e = after_launch();
+  int e = after_launch();
   if (e) return e;
   smooth_apply_kernel<<<dim3(bx, a.sm.group_frames), 128, 0, (cudaStream_t)stream>>>(a);
   return after_launch();
