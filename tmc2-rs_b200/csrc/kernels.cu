@@ -1542,6 +1542,28 @@ __device__ __forceinline__ uint32_t probe_multi(const GridDesc& G, uint32_t fig,
   return any;
 }
 
+// The same for a dense grid with power-of-two cell edge and width: the neighbourhood's first cell along an axis is
+// (p - g/2) >> log2(g) (the margin test guarantees both cells of every axis exist), and the two cells along x are neighbouring
+// bits of the bitmap -- four word loads instead of eight (a fifth when the pair straddles a word).
+__device__ __forceinline__ uint32_t probe_multi_fast(const GridDesc& G, uint32_t fig, const uint32_t p[3]) {
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax)
+    if (p[ax] >= G.th || p[ax] < G.disth || p[ax] + G.disth >= G.th) return 0u;
+  const uint32_t hg = G.g >> 1, gs = (uint32_t)G.g_shift, ws = G.w_shift;
+  const uint32_t sx = (p[0] - hg) >> gs, sy = (p[1] - hg) >> gs, sz = (p[2] - hg) >> gs;
+  const uint32_t* bits = G.mbits + (uint64_t)fig * G.mwords;
+  const uint32_t c00 = sx + (sy << ws) + (sz << (2u * ws));
+  uint32_t any = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t cs = c00 + ((k & 1) ? (1u << ws) : 0u) + ((k & 2) ? (1u << (2u * ws)) : 0u);
+    const uint32_t b = cs & 31u;
+    any |= (__ldg(bits + (cs >> 5)) >> b) & 3u;
+    if (b == 31u) any |= __ldg(bits + (cs >> 5) + 1) & 1u;
+  }
+  return any;
+}
+
 __global__ void __launch_bounds__(256) smooth_probe_kernel(const __grid_constant__ UnpackArgs a) {
   const uint32_t fig = blockIdx.y;
   const uint32_t f = a.sm.group_first_frame + fig;
@@ -1554,8 +1576,9 @@ __global__ void __launch_bounds__(256) smooth_probe_kernel(const __grid_constant
     if (i < n) {
       const uint4 raw = __ldg(reinterpret_cast<const uint4*>(&L[i]));
       const uint32_t p[3] = {raw.y & 0xFFFFu, raw.y >> 16, raw.z & 0xFFFFu};
-      if (a.sm.geo.on && probe_multi(a.sm.geo, fig, p)) want |= 1u;
-      if (a.sm.col.on && a.has_attr && probe_multi(a.sm.col, fig, p)) want |= 2u;   // pre-smoothing position
+      if (a.sm.geo.on && (a.sm.geo.fast ? probe_multi_fast(a.sm.geo, fig, p) : probe_multi(a.sm.geo, fig, p))) want |= 1u;
+      if (a.sm.col.on && a.has_attr && (a.sm.col.fast ? probe_multi_fast(a.sm.col, fig, p) : probe_multi(a.sm.col, fig, p)))
+        want |= 2u;                                                                 // pre-smoothing position
     }
     const uint32_t wm = __ballot_sync(kFull, want != 0u);
     if (wm == 0u) continue;
