@@ -296,6 +296,10 @@ def test_config3_config4_frame_bit_exact_with_smoothing(gpu_ctx, name):
     util.assert_same(got, want, keys=("positions_presmooth", "colors16bit_presmooth", "boundary_type"), what=name + " pre-smoothing")
     assert got["smoothed_positions"] == want["smoothed_positions"] and got["smoothed_colors"] == want["smoothed_colors"]
     assert want["smoothed_positions"] > 0
+    # the production instantiation (streaming path; c4: colour grid 512 cells wide, beyond the packed cell keys)
+    fr = gpu_ctx.decode_gof(abi.GofView(g))[0]
+    assert np.array_equal(fr.positions, want["positions"]) and np.array_equal(fr.colors, want["colors"])
+    assert fr.smoothed_positions == want["smoothed_positions"] and fr.smoothed_colors == want["smoothed_colors"]
 
 
 def test_three_entry_points_agree_at_full_size(gpu_ctx):

@@ -121,7 +121,8 @@ struct GridDesc {               // geometry of one voxel grid
   uint32_t magic;               // ceil(2^32 / g): x / g == umulhi(x, magic) for x < 65536
   int32_t  g_shift;             // log2(g) when g is a power of two, else -1
   uint32_t identity;            // 1: slot = dense cell index (table covers the whole grid)
-  // fast: dense table, g and w powers of two, w <= 256, g * w == 2^bitdepth.  Then cell coordinates come from shifts and
+  // fast: dense table, g and w powers of two, g * w == 2^bitdepth (1: w <= 256, cell keys pack into bytes; 2: w <= 1024,
+  // direct slot arithmetic only -- colour statistics and the probe).  Then cell coordinates come from shifts and
   // masks on the packed position words (x | y << 16, z): oob_mask = bits that must be zero in every coordinate, replicated
   // in both halves; cmask = (w - 1) in both halves; w_shift = log2(w).
   uint32_t fast, w_shift, oob_mask, cmask;

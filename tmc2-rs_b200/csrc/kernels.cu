@@ -939,7 +939,7 @@ struct SmoothState {
     } else if (!kFast && a.sm.geo.on) {
       // generic grids: segmented scan over runs of equal cell, see below
       const GridDesc& G = a.sm.geo;
-      const bool fast8 = G.fast && G.g <= 8u;                        // packed single-word sums need 32 * (g - 1) < 256
+      const bool fast8 = G.fast == 1u && G.g <= 8u;                     // packed single-word sums need 32 * (g - 1) < 256
       uint32_t key = kCellEmpty, rx_ = 0, ry_ = 0, rz_ = 0, vfast = 0;
       if (fast8) {
         // cell coordinates straight from the packed position words (w1's upper half is zero)
@@ -1000,7 +1000,9 @@ struct SmoothState {
       if (bt == 2u) {
         uint32_t cs = kCellEmpty;
         if (kFast || G.fast) {
-          if (((w0 | w1) & G.oob_mask) == 0u) cs = fast_slot(G, ((w0 >> G.g_shift) & G.cmask) | ((w1 >> G.g_shift) << 8));
+          // dense slot cx + w * (cy + w * cz) straight from the packed position words (any power-of-two width)
+          if (((w0 | w1) & G.oob_mask) == 0u)
+            cs = ((w0 & 0xFFFFu) >> G.g_shift) | (((w0 >> 16) >> G.g_shift) << G.w_shift) | ((w1 >> G.g_shift) << (2u * G.w_shift));
         } else {
           const uint32_t key = cell_key_of(G, X, Yc, Z);
           if (key != kCellEmpty) cs = cell_slot(G, fig, key, a.err);
@@ -1690,7 +1692,7 @@ int launch_emit(const UnpackArgs& a, bool smooth, uint32_t tile_begin, uint32_t 
   if (smooth) {
     if (debug) return launch_emit_t<true, true, false>(a, tile_begin, tile_end, s);
     // the usual grids (dense tables, power-of-two cell edges, geometry edge <= 8) get the instantiation without generic branches
-    const bool fast = (!a.sm.geo.on || (a.sm.geo.fast && a.sm.geo.g <= 8u)) && (!a.sm.col.on || a.sm.col.fast);
+    const bool fast = (!a.sm.geo.on || (a.sm.geo.fast == 1u && a.sm.geo.g <= 8u)) && (!a.sm.col.on || a.sm.col.fast);
     return fast ? launch_emit_t<true, false, true>(a, tile_begin, tile_end, s) : launch_emit_t<true, false, false>(a, tile_begin, tile_end, s);
   }
   return debug ? launch_emit_t<false, true, false>(a, tile_begin, tile_end, s) : launch_emit_t<false, false, false>(a, tile_begin, tile_end, s);

@@ -646,9 +646,9 @@ struct Batch {
         G.fast = 0; G.w_shift = 0; G.oob_mask = 0; G.cmask = 0;
         {
           int wl = -1;
-          for (int sft = 0; sft <= 8; ++sft) if ((1u << sft) == G.w) wl = sft;
+          for (int sft = 0; sft <= 10; ++sft) if ((1u << sft) == G.w) wl = sft;
           if (!hashed && G.g_shift >= 0 && wl >= 0 && G.th <= 65536u) {
-            G.fast = 1; G.w_shift = (uint32_t)wl;
+            G.fast = wl <= 8 ? 1 : 2; G.w_shift = (uint32_t)wl;      // 2: wider than the packed 8-bit cell keys (colour / probe only)
             G.oob_mask = (0xFFFFu & ~(G.th - 1u)) * 0x10001u;
             G.cmask = (G.w - 1u) * 0x10001u;
           }
