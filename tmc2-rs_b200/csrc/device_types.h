@@ -94,20 +94,20 @@ struct Outputs {                // any pointer may be null = stream not wanted
 // A cell is written only with fire-and-forget reductions (RED): two max, two / three 64-bit adds.  All-zero == empty.
 // "multi-patch" (the smoothing trigger) <=> two different patches touched the cell: the first toucher claims `first1` with
 // a compare-and-swap (0 -> patch + 1); whoever finds another patch's claim stores 1 into `multi` (idempotent).
-// The finalize pass (once per touched cell, before the filter) turns the sums into Q8 means.
+// The apply pass computes Q8 means from the sums on the fly (there is no finalize pass).
 constexpr uint32_t kCellEmpty = 0xFFFFFFFFu;      // free slot of a hashed table's key array
 struct GeoCell {     // 32 B = one DRAM sector
   uint32_t first1;              // patch index + 1 of the first toucher, 0 = untouched
   uint32_t multi;               // 1 = touched by more than one patch
   unsigned long long cnt_sx;    // count | sum(x - cell origin) << 32
   unsigned long long sy_sz;     // sum(y - origin) | sum(z - origin) << 32
-  unsigned long long mean;      // finalize: Q8 means relative to the cell origin, 16 bits each (x | y<<16 | z<<32)
+  unsigned long long mean;      // unused (pads the cell to one 32-byte sector)
 };
 struct ColCell {     // 32 B
   uint32_t first1, multi;
-  unsigned long long cnt_sy;    // count (24 bits) | sum(Y) << 24         finalize -> count | meanY_Q8 << 32
-  unsigned long long su_sv;     // sum(U) | sum(V) << 32                  finalize -> meanU_Q8 | meanV_Q8 << 32
-  unsigned long long sy2;       // sum(Y*Y)                               finalize -> 1 if the luminance variance test passes
+  unsigned long long cnt_sy;    // count (24 bits) | sum(Y) << 24
+  unsigned long long su_sv;     // sum(U) | sum(V) << 32
+  unsigned long long sy2;       // sum(Y*Y)
 };
 struct alignas(16) BoundaryEntry {  // one type-1 boundary point (16 B)
   uint32_t idx;         // point index inside its frame

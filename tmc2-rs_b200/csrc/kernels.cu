@@ -1324,10 +1324,8 @@ __global__ void __launch_bounds__(256) yuv_to_rgb_flat_kernel(const uint16_t* __
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// K6 / K7 finalize: once per touched cell, sums -> Q8 means (and the colour cell's luminance-variance verdict), so that
-// the filter (8 cells per boundary point per grid) does no division.  One warp per unpack slot of the group walks that
-// slot's log; a cell logged by several slots is finalized more than once (geometry: idempotent, means live in their own
-// field; colour: claimed with an atomic flag because the means replace the sums).
+// K6 / K7 cell summaries: sums -> Q8 means (and the colour cell's luminance-variance verdict).  There is no finalize pass:
+// only the boundary points that survive the probe need summaries, and they compute them from the raw accumulators.
 // ----------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t mean_q8_u32(uint32_t s, uint32_t cnt) {       // (256*s + cnt/2) / cnt
   const unsigned long long num = 256ull * s + (cnt >> 1);

@@ -243,7 +243,7 @@ struct Batch {
   cudaStream_t stream = nullptr;      // compute + H2D
   cudaStream_t d2h_stream = nullptr;  // result copies
   cudaStream_t aux_stream = nullptr;  // smoothing post-passes of group g overlap the emit of group g+1
-  std::vector<cudaEvent_t> ev_emit, ev_post;   // per group: emit done (main stream) / finalize+filter+clear done (aux)
+  std::vector<cudaEvent_t> ev_emit, ev_post;   // per group: emit done (main stream) / filter+clear done (aux)
   cudaEvent_t ev_tables_clean = nullptr;       // single-group launches: the clear pass runs on aux, off the critical path
   bool clear_pending = false;
   bool two_pass = false;
@@ -747,7 +747,7 @@ struct Batch {
                                (size_t)(f1 - f0) * cap * 6, cudaMemcpyDeviceToDevice, s));
         }
         if (n_groups == 1) {
-          // one group: finalize + filter in line; the clear pass only matters to the NEXT launch, so it runs on the auxiliary
+          // one group: filter (probe + apply) in line; the clear pass only matters to the NEXT launch, so it runs on the auxiliary
           // stream under that launch's block-to-patch / count passes (which do not touch the tables)
           KL(launch_smooth_filter(a, s));
           CU(cudaEventRecord(ev_emit[gi], s));
