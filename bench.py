@@ -9,7 +9,9 @@ A "step" is one pass of the hot path over one synthetic GOF (BASELINE config 2: 
 geometry, 2 maps, occupancy precision 4, grid geometry smoothing + colour smoothing ON).  With N ranks every rank
 reconstructs its own GOF per step (weak scaling; frames / GOFs are independent).
 
-  value  points/s with the planes already resident in HBM (kernels only, CUDA events on the launching stream)
+  value  points/s with the planes already resident in HBM (kernels only, CUDA events on the launching streams): step i
+         reconstructs resident GOF i % 3 on stream i % 3, like the three GOFs in flight of the streaming path, so the
+         small latency-bound passes of one GOF run under the emit of another (--resident-gofs 1: one stream, GOF latency)
   e2e    points/s through the public C ABI (tmc2gpu_submit_gof / tmc2gpu_next_frame) from PINNED HOST planes:
          H2D of every plane and D2H of every reconstructed frame inside the timed region
   roofline  algorithmic bytes of the dominant kernel (fused unpack) / its device time, against the measured HBM peak
@@ -154,6 +156,9 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-smoothing", action="store_true", help="reference-exact rec0 path only (no post-processing)")
+    ap.add_argument("--resident-gofs", type=int, default=3,
+                    help="resident GOFs the kernel-only loop alternates between, each on its own stream (consecutive GOFs "
+                         "of a stream overlap: the small latency-bound passes of one run under the emit of the other)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -223,15 +228,20 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: planes resident in HBM, kernels only -----------------------------------------------------------------
-    res = ctx.upload_gof(view)
-    # a dedicated torch stream: torch.cuda.Event only sees the stream it is recorded on, and torch's default stream
+    n_res = max(1, args.resident_gofs)
+    cfg_desc["resident_gofs_in_flight"] = n_res
+    residents = [ctx.upload_gof(view) for _ in range(n_res)]
+    res = residents[0]
+    # dedicated torch streams: torch.cuda.Event only sees the stream it is recorded on, and torch's default stream
     # has handle 0, which the C ABI reads as "use the library's own stream"
-    tstream = torch.cuda.Stream(device=dev)
+    tstreams = [torch.cuda.Stream(device=dev) for _ in range(n_res)]
+    tstream = tstreams[0]
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
-    assert stream != 0
+    assert all(t.cuda_stream != 0 for t in tstreams)
     for _ in range(args.warmup):
-        res.reconstruct(stream)
+        for r, t in zip(residents, tstreams):
+            r.reconstruct(t.cuda_stream)
     counts = res.counts()
     points_per_step = int(counts.sum())
     launches_per_step, alg_bytes, _ = ctx.last_launch_info()
@@ -240,10 +250,18 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     unpack_ms, stage_acc = [], {}
-    e0.record()
-    for _ in range(args.steps):
-        res.reconstruct(stream)
-    e1.record()
+    # step i reconstructs resident GOF i % n_res on stream i % n_res; the timed region starts when every stream has passed
+    # e0 and ends when every stream has finished its last step
+    e0.record(tstream)
+    for t in tstreams[1:]:
+        t.wait_event(e0)
+    for i in range(args.steps):
+        residents[i % n_res].reconstruct(tstreams[i % n_res].cuda_stream)
+    for t in tstreams[1:]:
+        done = torch.cuda.Event()
+        done.record(t)
+        tstream.wait_event(done)
+    e1.record(tstream)
     barrier()
     kernel_ms = e0.elapsed_time(e1)
     # per-stage device times (library-recorded CUDA events on the same stream), measured on separate launches so that
@@ -256,7 +274,8 @@ def main():
             stage_acc.setdefault(k, []).append(v)
     kernel_ms_max, pts_all, frames_all = shard.reduce_metrics(kernel_ms, points_per_step * args.steps, frames * args.steps, dev)
     value = pts_all / (kernel_ms_max * 1e-3)
-    res.free()
+    for r in residents:
+        r.free()
 
     # ---- e2e: public C ABI, pinned host planes in, pinned host frames out, two GOFs in flight ---------------------------
     def drain(n):

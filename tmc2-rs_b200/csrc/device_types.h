@@ -91,7 +91,7 @@ struct Outputs {                // any pointer may be null = stream not wanted
 };
 
 // ---- voxel-cell tables of the grid smoothing stages (own spec) ------------------------------------------
-// A cell is written only with fire-and-forget reductions (RED): two max, two / three 64-bit adds.  All-zero == empty.
+// The sums of a cell are written only with fire-and-forget reductions (RED): two / three 64-bit adds.  All-zero == empty.
 // "multi-patch" (the smoothing trigger) <=> two different patches touched the cell: the first toucher claims `first1` with
 // a compare-and-swap (0 -> patch + 1); whoever finds another patch's claim stores 1 into `multi` (idempotent).
 // The apply pass computes Q8 means from the sums on the fly (there is no finalize pass).
