@@ -198,10 +198,15 @@ def test_smoothing_dense_overlap_case(gpu_ctx):
     assert frames[1].smoothed_positions == want["smoothed_positions"]
 
 
-def test_smoothing_hashed_tables_and_small_groups(monkeypatch):
-    """Same answers when the voxel-cell tables are hashed (grids too large for a dense table) and with 1-frame groups."""
-    monkeypatch.setenv("TMC2_FORCE_HASH", "1")
-    monkeypatch.setenv("TMC2_SMOOTH_GROUP", "2")
+@pytest.mark.parametrize("env", [{"TMC2_FORCE_HASH": "1", "TMC2_SMOOTH_GROUP": "2"}, {"TMC2_SMOOTH_GROUP": "2"},
+                                 {"TMC2_TABLE_BUDGET_MB": "600"}, {"TMC2_TABLE_BUDGET_MB": "100"}],
+                         ids=["hashed-groups-of-2", "dense-groups-of-2", "budget-600MB", "budget-100MB"])
+def test_smoothing_hashed_tables_and_small_groups(monkeypatch, env):
+    """Same answers when the voxel-cell tables are hashed (grids too large for a dense table), when a GOF is cut into frame
+    groups with two alternating table sets (dense tables: the fast instantiation, as for config 4), and when the per-table
+    memory budget is small (600 MB: one-frame groups; 100 MB: the colour grid no longer fits and is hashed)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     g = synth.make_gof(synth.config("small", frames=5))
     for p in g.patches:
         p["u1"] = 100 + (np.arange(len(p)) % 3)

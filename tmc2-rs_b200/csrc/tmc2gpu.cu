@@ -266,6 +266,7 @@ struct Batch {
   DevBuf d_geotab, d_coltab, d_geokeys, d_colkeys, d_changed, d_blist,
       d_blist_count, d_slist, d_slist_count, d_geombits, d_colmbits, d_geotbits, d_coltbits;
   uint64_t geotab_slots = 0, coltab_slots = 0, geotab_frames = 0, coltab_frames = 0, blist_cap = 0;
+  uint64_t table_budget = 0;          // bytes per cell table, decided when the batch first needs tables
   bool geotab_hashed = false, coltab_hashed = false;
   uint32_t group_frames = 32;         // frames per smoothing group (one group = no post-pass tails between groups; a GOF is <= 32 frames)
   uint32_t group_frames_eff = 8;      // after fitting the dense tables into the memory budget
@@ -444,7 +445,19 @@ struct Batch {
       CU(d_slist_count.ensure(std::max<size_t>((size_t)F * 4, 4)));
       // Cell tables: dense (direct-indexed, no probing) when the whole grid fits the per-table budget for at least one
       // frame, hashed (separate key array) otherwise.  The group size shrinks until the dense tables fit.
-      const uint64_t kTableBudget = 16ull << 30;
+      // Budget per table: 16 GB, less when the device is short of memory (a quarter of what is free now, so that the GOFs in
+      // flight after this one still find room; at least 1 GB) -- smaller budgets mean smaller frame groups, then hashed tables.
+      // Decided once per batch (the tables are kept from GOF to GOF).
+      if (table_budget == 0) {
+        table_budget = 16ull << 30;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+          table_budget = std::min<uint64_t>(table_budget, std::max<uint64_t>(1ull << 30, (uint64_t)free_b / 4));
+        else
+          cudaGetLastError();
+        if (const char* e = getenv("TMC2_TABLE_BUDGET_MB")) table_budget = std::max<uint64_t>(1, strtoull(e, nullptr, 10)) << 20;
+      }
+      const uint64_t kTableBudget = table_budget;
       const bool force_hash = getenv("TMC2_FORCE_HASH") != nullptr;        // test hook for the hashed-table path
       auto cells_of = [&](uint32_t g) -> uint64_t { const uint64_t w = (maxs + g - 1) / g; return w * w * w; };
       uint32_t GF = std::min(group_frames, std::max(F, 1u));
