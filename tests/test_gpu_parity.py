@@ -1,5 +1,6 @@
 """Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run on a B200: pytest -m gpu."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -177,6 +178,22 @@ def test_smoothing_matches_own_spec_oracle(gpu_ctx, name):
     util.assert_same(got, want, keys=("positions", "colors16bit", "colors"), what=name + " smoothed")   # own spec: exact
     assert got["smoothed_positions"] == want["smoothed_positions"]
     assert got["smoothed_colors"] == want["smoothed_colors"]
+
+
+def test_smoothing_golden_fixture(gpu_ctx):
+    """The CUDA path against the committed smoothing fixture (tests/golden/small_smooth_f1.npz), without the oracle in between."""
+    import importlib.util
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(gold, "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    z = np.load(os.path.join(gold, "small_smooth_f1.npz"))
+    fr = gpu_ctx.decode_gof(abi.GofView(m.smoothing_case()))[1]
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert len(fr) == int(z["point_count"])
+    assert fr.smoothed_positions == int(z["smoothed_positions"]) and fr.smoothed_colors == int(z["smoothed_colors"])
+    assert sha(fr.positions) == z["sha_positions"].item() and sha(fr.colors) == z["sha_colors"].item()
+    assert np.array_equal(z["moved_positions_head"], fr.positions[z["moved_index_head"]])
 
 
 def test_smoothing_dense_overlap_case(gpu_ctx):

@@ -57,6 +57,27 @@ def test_golden_fixture_small():
     assert np.array_equal(z["colors_head"], r["colors"][:256])
 
 
+def _load_make_golden():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_golden_fixture_smoothing():
+    """tests/golden/small_smooth_f1.npz freezes this repository's own smoothing specification (boundary classes, grid geometry
+    smoothing, grid colour smoothing; the reference has only stubs): the oracle must still produce it."""
+    z = np.load(os.path.join(GOLD, "small_smooth_f1.npz"))
+    r = oracle.reconstruct_frame(abi.GofView(_load_make_golden().smoothing_case()), 1)
+    assert int(z["point_count"]) == r["point_count"]
+    assert int(z["smoothed_positions"]) == r["smoothed_positions"] and int(z["smoothed_colors"]) == r["smoothed_colors"]
+    assert z["sha_boundary_type"].item() == digest(r["boundary_type"])
+    assert z["sha_positions"].item() == digest(r["positions"])
+    assert z["sha_colors"].item() == digest(r["colors"])
+    assert np.array_equal(z["moved_positions_head"], r["positions"][z["moved_index_head"]])
+
+
 def test_frame_sharding_covers_every_frame_once():
     for total in (0, 1, 7, 32, 300):
         for world in (1, 2, 3, 4, 8):
