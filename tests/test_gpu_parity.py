@@ -411,6 +411,34 @@ def test_streaming_smoothing_fast_grids(gpu_ctx, case, content, grids):
         assert fr.smoothed_positions == want["smoothed_positions"] and fr.smoothed_colors == want["smoothed_colors"]
 
 
+def test_row_padded_planes_like_ffmpeg_linesize(gpu_ctx):
+    """Planes whose row pitch exceeds the width (libavcodec pads linesize; the reference ignores it, decoder.rs:976-978): the
+    C ABI takes the pitch per plane kind and must give the same frames as tight copies, whatever sits in the padding."""
+    g = util.random_small_gof(seed=31, W=208, H=112, n_patches=14, frames=2)
+    util.crowd_into_one_region(g)
+    g.params.geometry_smoothing = True
+    g.params.color_smoothing = True
+    rng = np.random.RandomState(7)
+
+    def padded(a, pad):
+        big = rng.randint(0, 256 if a.dtype == np.uint8 else 65536, a.shape[:-1] + (a.shape[-1] + pad,)).astype(a.dtype)
+        big[..., :a.shape[-1]] = a
+        return big[..., :a.shape[-1]]
+
+    gp = abi.Gof(g.width, g.height, padded(g.occ, 12), padded(g.geo, 48), padded(g.attr_y, 48), padded(g.attr_u, 24),
+                 padded(g.attr_v, 24), g.patches, g.params)
+    vp = abi.GofView(gp)
+    assert vp.c.frames[0].geo_stride == g.width + 48 and vp.c.frames[0].attr_stride_c == g.width // 2 + 24
+    tight = gpu_ctx.decode_gof(abi.GofView(g))
+    pad = gpu_ctx.decode_gof(vp)
+    for a, b in zip(tight, pad):
+        assert np.array_equal(a.positions, b.positions) and np.array_equal(a.colors, b.colors)
+    want = oracle.reconstruct_frame(abi.GofView(g), 1)
+    assert np.array_equal(pad[1].positions, want["positions"]) and np.array_equal(pad[1].colors, want["colors"])
+    st = gpu_ctx.generate_point_cloud(vp, 1, debug=True)
+    assert np.array_equal(st["positions"], want["positions"]) and np.array_equal(st["occupancy_map"], want["occupancy_map"])
+
+
 def test_one_process_two_devices_shard_frames_in_order():
     """SURVEY 8e inside ONE process: a context over two devices shards the frames of a GOF frame-wise (contiguous halves, no
     collective) and hands them back in order; results equal the single-device context.  Skipped on a one-GPU box."""

@@ -187,27 +187,32 @@ class GofView:
     def __init__(self, gof: Gof):
         self.gof = gof
         F = gof.frame_count
-        for name in ("occ", "geo", "attr_y", "attr_u", "attr_v"):
+        # planes may be row-padded views (ffmpeg's linesize > width): samples of a row contiguous, row pitch a multiple of
+        # the sample size -- the pitch travels in the *_stride fields (the reference itself assumes tight planes)
+        def pitch(name):
             a = getattr(gof, name)
-            if a is not None and not a.flags["C_CONTIGUOUS"]:
-                raise ValueError(f"{name} must be C-contiguous")
+            if a.strides[-1] != a.itemsize or a.strides[-2] % a.itemsize or a.strides[-2] < a.shape[-1] * a.itemsize:
+                raise ValueError(f"{name}: rows must be contiguous runs of samples (row pitch >= width)")
+            return a.strides[-2] // a.itemsize
         assert gof.occ.dtype == np.uint8 and gof.geo.dtype == np.uint16
         self._frames = (CFrame * max(F, 1))()
         self._keep = []
         for f in range(F):
             fr = self._frames[f]
             fr.occ = gof.occ[f].ctypes.data
-            fr.occ_stride = gof.occ.shape[2]
+            fr.occ_stride = pitch("occ")
             for m in range(2):
                 fr.geo[m] = gof.geo[f, m].ctypes.data if gof.geo.shape[1] > m else None
                 if gof.attr_y is not None:
                     fr.attr_y[m] = gof.attr_y[f, m].ctypes.data
                     fr.attr_u[m] = gof.attr_u[f, m].ctypes.data
                     fr.attr_v[m] = gof.attr_v[f, m].ctypes.data
-            fr.geo_stride = gof.geo.shape[3]
+            fr.geo_stride = pitch("geo")
             if gof.attr_y is not None:
-                fr.attr_stride_y = gof.attr_y.shape[3]
-                fr.attr_stride_c = gof.attr_u.shape[3]
+                fr.attr_stride_y = pitch("attr_y")
+                fr.attr_stride_c = pitch("attr_u")
+                if pitch("attr_v") != fr.attr_stride_c:
+                    raise ValueError("attr_u and attr_v must share one row pitch")
             p = np.ascontiguousarray(gof.patches[f], dtype=PATCH_DTYPE)
             self._keep.append(p)
             fr.patches = p.ctypes.data if len(p) else None
