@@ -445,11 +445,11 @@ struct Batch {
       CU(d_slist_count.ensure(std::max<size_t>((size_t)F * 4, 4)));
       // Cell tables: dense (direct-indexed, no probing) when the whole grid fits the per-table budget for at least one
       // frame, hashed (separate key array) otherwise.  The group size shrinks until the dense tables fit.
-      // Budget per table: 16 GB, less when the device is short of memory (a quarter of what is free now, so that the GOFs in
+      // Budget per table: 40 GB, less when the device is short of memory (a quarter of what is free now, so that the GOFs in
       // flight after this one still find room; at least 1 GB) -- smaller budgets mean smaller frame groups, then hashed tables.
       // Decided once per batch (the tables are kept from GOF to GOF).
       if (table_budget == 0) {
-        table_budget = 16ull << 30;
+        table_budget = 40ull << 30;
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
           table_budget = std::min<uint64_t>(table_budget, std::max<uint64_t>(1ull << 30, (uint64_t)free_b / 4));
