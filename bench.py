@@ -326,6 +326,7 @@ def main():
     achieved = alg_bytes / (t_unpack * 1e-3) / 1e9 if t_unpack and t_unpack > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "emit_kernel (fused occupancy upsample / unpack / attribute fetch / YUV->RGB; + boundary + cell statistics when smoothing)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "frac_of_nominal_8TBps": achieved / 8000.0,
                 "launches_per_step": n_emit, "frames_per_launch": min(group, frames),
                 "algorithmic_bytes_per_launch": alg_bytes / n_emit, "ms_per_launch": t_unpack / n_emit, "traffic": None,
                 "stage_ms": {k: statistics.mean(v) for k, v in stage_acc.items()}}
