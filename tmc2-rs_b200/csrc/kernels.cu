@@ -801,6 +801,30 @@ __device__ __forceinline__ void boundary_masks(const UnpackArgs& a, const WorkRe
 }
 
 __device__ __forceinline__ void stg_u32(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+// The planes of the block a warp of a LATER tile will work on, into L2: the inputs stream through once (338 MB per GOF
+// against 126 MB of L2), so without this every slot starts with a full DRAM round trip behind its work record.
+__device__ __forceinline__ void prefetch_slot_planes(const UnpackArgs& a, uint32_t pid, uint32_t frame, uint32_t bxy, uint32_t lane) {
+  if (pid == kNoPatch) return;
+  const uint32_t h = lane & 1u, r = lane >> 1;
+  const uint32_t x0 = (bxy & 0xFFFFu) * 16u + 8u * h, y = (bxy >> 16) * 16u + r;
+  const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride + (uint64_t)y * a.in.geo_pitch + x0;
+  prefetch_l2(geo0);
+  prefetch_l2(geo0 + a.in.geo_map_stride);
+  if (a.has_attr) {
+    const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride + (uint64_t)y * a.in.attr_pitch_y + x0;
+    prefetch_l2(ay0);
+    prefetch_l2(ay0 + a.in.attr_y_map_stride);
+    if (!(r & 1u)) {
+      const uint64_t co = (uint64_t)frame * 2 * a.in.attr_c_map_stride + (uint64_t)(y >> 1) * a.in.attr_pitch_c + (x0 >> 1);
+      prefetch_l2(a.in.attr_u + co);
+      prefetch_l2(a.in.attr_v + co);
+      prefetch_l2(a.in.attr_u + co + a.in.attr_c_map_stride);
+      prefetch_l2(a.in.attr_v + co + a.in.attr_c_map_stride);
+    }
+  }
+}
 
 // ---- smoothing work of the emit loop (K6 / K7 statistics + boundary list), one call per 32-point window -----------------
 // The sums are fire-and-forget reductions, so nothing in the loop waits for the memory system.  A slot claims each cell once,
@@ -1042,14 +1066,27 @@ struct SmoothState {
 #ifndef TMC2_MINCTA
 #define TMC2_MINCTA 4
 #endif
+#ifndef TMC2_PREFETCH_TILES
+#define TMC2_PREFETCH_TILES 296
+#endif
 #ifndef TMC2_SMOOTH_MINCTA
 #define TMC2_SMOOTH_MINCTA 3
 #endif
 template <bool kSmooth, bool kDebug, bool kFast>
-__global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINCTA : TMC2_MINCTA) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
+__global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINCTA : TMC2_MINCTA) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset, uint32_t tile_end) {
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t lpos = (blockIdx.x + tile_offset) * kWarpsPerTile + warp;
+  // the slot a warp will meet kPrefetchTiles tiles from now (about one generation of resident CTAs ahead)
+  // (measured: 0.222 -> 0.212 ms without smoothing; no gain for the smoothing instantiation, which is off)
+  constexpr uint32_t kPrefetchTiles = kSmooth ? 0u : (uint32_t)TMC2_PREFETCH_TILES;
+  uint4 pf = make_uint4(kNoPatch, 0, 0, 0);
+  uint32_t pf_frame = 0;
+  if (kPrefetchTiles && blockIdx.x + tile_offset + kPrefetchTiles < tile_end) {
+    const uint4* q = reinterpret_cast<const uint4*>(a.work + lpos + kPrefetchTiles * kWarpsPerTile);
+    pf = q[0];
+    pf_frame = reinterpret_cast<const uint32_t*>(q + 1)[0] & 0x7FFFFFFFu;
+  }
   const WorkRec R = load_work(a.work + lpos);
   const uint32_t total = R.pid == kNoPatch ? 0u : R.total;
   if (total == 0) return;
@@ -1096,6 +1133,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
     }
     CanvasBlock L;
     load_geometry(a, R, P, lane, L);
+    if (kPrefetchTiles) prefetch_slot_planes(a, pf.x, pf_frame, pf.z, lane);
     uint32_t bt1 = 0, bt2 = 0;
     if (want_bt) boundary_masks(a, R, lane, s_bmp, bt1, bt2);
     if (kSmooth) {
@@ -1667,7 +1705,7 @@ static int launch_emit_t(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile
   const size_t smem = (size_t)(kSmooth ? (kFast ? kWarpSmemBytes : kOffTab) : kOffMemo) * kWarpsPerTile;   // memo / cell table: smoothing only
   cudaError_t e = cudaFuncSetAttribute((const void*)emit_kernel<kSmooth, kDebug, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  emit_kernel<kSmooth, kDebug, kFast><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin);
+  emit_kernel<kSmooth, kDebug, kFast><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin, tile_end);
   return after_launch();
 }
 
