@@ -805,6 +805,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 // The planes of the block a warp of a LATER tile will work on, into L2: the inputs stream through once (338 MB per GOF
 // against 126 MB of L2), so without this every slot starts with a full DRAM round trip behind its work record.
+template <bool kChroma>
 __device__ __forceinline__ void prefetch_slot_planes(const UnpackArgs& a, uint32_t pid, uint32_t frame, uint32_t bxy, uint32_t lane) {
   if (pid == kNoPatch) return;
   const uint32_t h = lane & 1u, r = lane >> 1;
@@ -816,7 +817,7 @@ __device__ __forceinline__ void prefetch_slot_planes(const UnpackArgs& a, uint32
     const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride + (uint64_t)y * a.in.attr_pitch_y + x0;
     prefetch_l2(ay0);
     prefetch_l2(ay0 + a.in.attr_y_map_stride);
-    if (!(r & 1u)) {
+    if (kChroma && !(r & 1u)) {
       const uint64_t co = (uint64_t)frame * 2 * a.in.attr_c_map_stride + (uint64_t)(y >> 1) * a.in.attr_pitch_c + (x0 >> 1);
       prefetch_l2(a.in.attr_u + co);
       prefetch_l2(a.in.attr_v + co);
@@ -1066,6 +1067,9 @@ struct SmoothState {
 #ifndef TMC2_MINCTA
 #define TMC2_MINCTA 4
 #endif
+#ifndef TMC2_PREFETCH_TILES_SMOOTH
+#define TMC2_PREFETCH_TILES_SMOOTH 0
+#endif
 #ifndef TMC2_PREFETCH_TILES
 #define TMC2_PREFETCH_TILES 296
 #endif
@@ -1079,7 +1083,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
   const uint32_t lpos = (blockIdx.x + tile_offset) * kWarpsPerTile + warp;
   // the slot a warp will meet kPrefetchTiles tiles from now (about one generation of resident CTAs ahead)
   // (measured: 0.222 -> 0.212 ms without smoothing; no gain for the smoothing instantiation, which is off)
-  constexpr uint32_t kPrefetchTiles = kSmooth ? 0u : (uint32_t)TMC2_PREFETCH_TILES;
+  constexpr uint32_t kPrefetchTiles = kSmooth ? (uint32_t)TMC2_PREFETCH_TILES_SMOOTH : (uint32_t)TMC2_PREFETCH_TILES;
   uint4 pf = make_uint4(kNoPatch, 0, 0, 0);
   uint32_t pf_frame = 0;
   if (kPrefetchTiles && blockIdx.x + tile_offset + kPrefetchTiles < tile_end) {
@@ -1133,7 +1137,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
     }
     CanvasBlock L;
     load_geometry(a, R, P, lane, L);
-    if (kPrefetchTiles) prefetch_slot_planes(a, pf.x, pf_frame, pf.z, lane);
+    if (kPrefetchTiles) prefetch_slot_planes<!kSmooth>(a, pf.x, pf_frame, pf.z, lane);
     uint32_t bt1 = 0, bt2 = 0;
     if (want_bt) boundary_masks(a, R, lane, s_bmp, bt1, bt2);
     if (kSmooth) {
