@@ -129,9 +129,11 @@ struct GridDesc {               // geometry of one voxel grid
   uint64_t slots;               // table slots per frame-in-group (power of two unless identity)
   void*    table;               // GeoCell / ColCell [frames_in_group][slots]
   uint32_t* keys;               // hashed tables only: [frames_in_group][slots], kCellEmpty = free
-  uint32_t* tbits;              // [frames_in_group][mwords] one bit per table slot: the cell was touched (set by its first toucher)
+  uint32_t* tbits;              // [frames_in_group][twords] one bit per 4 consecutive table slots (one 128-byte line of cells): some
+                                // cell of the quad was touched (set by its first toucher; what the clear pass walks)
   uint32_t* mbits;              // [frames_in_group][mwords] ... the cell is multi-patch (set by whoever finds another patch's claim, read by the probe)
   uint64_t mwords;
+  uint64_t twords;              // words per frame of tbits = ceil(slots / 128)
 };
 
 struct SmoothArgs {

@@ -553,7 +553,7 @@ __device__ __noinline__ uint32_t generic_slot_count(const UnpackArgs& a, uint32_
 // cell multi-patch (idempotent flag word in the cell + its bit in the frame's multi-patch bitmap, which the probe reads).
 __device__ __forceinline__ void claim_result(const GridDesc& G, uint32_t fig, uint32_t cs, uint32_t old, uint32_t patch) {
   if (old == 0u) {
-    atomicOr(G.tbits + (uint64_t)fig * G.mwords + (cs >> 5), 1u << (cs & 31u));
+    atomicOr(G.tbits + (uint64_t)fig * G.twords + (cs >> 7), 1u << ((cs >> 2) & 31u));
   } else if (old != patch + 1u) {
     reinterpret_cast<volatile uint32_t*>(static_cast<uint8_t*>(G.table) + ((uint64_t)fig * G.slots + cs) * 32u)[1] = 1u;
     atomicOr(G.mbits + (uint64_t)fig * G.mwords + (cs >> 5), 1u << (cs & 31u));
@@ -1659,19 +1659,28 @@ __global__ void __launch_bounds__(256) smooth_clear_kernel(const __grid_constant
   for (int which = 0; which < 2; ++which) {
     const GridDesc& G = which ? a.sm.col : a.sm.geo;
     if (!G.on) continue;
-    uint32_t* tb = G.tbits + (uint64_t)fig * G.mwords;
+    uint32_t* tb = G.tbits + (uint64_t)fig * G.twords;
     uint32_t* mb = G.mbits + (uint64_t)fig * G.mwords;
     uint4* tab = reinterpret_cast<uint4*>(G.table) + ((uint64_t)fig * G.slots) * 2;      // 32-byte cells
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < G.mwords; w += (uint64_t)gridDim.x * blockDim.x) {
+    // a word of the touched bitmap = 32 quads = 128 cells = four words of the multi-patch bitmap
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < G.twords; w += (uint64_t)gridDim.x * blockDim.x) {
       uint32_t t = tb[w];
       if (t == 0) continue;
-      tb[w] = 0; mb[w] = 0;
+      tb[w] = 0;
+#pragma unroll
+      for (uint32_t i = 0; i < 4; ++i)
+        if (4u * w + i < G.mwords) mb[4u * w + i] = 0;
       while (t) {
-        const uint64_t cs = w * 32u + ((uint32_t)__ffs(t) - 1u);
+        const uint64_t q = w * 32u + ((uint32_t)__ffs(t) - 1u);                     // quad = cells 4q .. 4q+3 = one 128-byte line
         t &= t - 1u;
-        tab[cs * 2] = make_uint4(0, 0, 0, 0);
-        tab[cs * 2 + 1] = make_uint4(0, 0, 0, 0);
-        if (!G.identity) G.keys[(uint64_t)fig * G.slots + cs] = kCellEmpty;
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+          const uint64_t cs = 4u * q + i;
+          if (cs >= G.slots) break;
+          tab[cs * 2] = make_uint4(0, 0, 0, 0);
+          tab[cs * 2 + 1] = make_uint4(0, 0, 0, 0);
+          if (!G.identity) G.keys[(uint64_t)fig * G.slots + cs] = kCellEmpty;
+        }
       }
     }
   }
