@@ -95,6 +95,10 @@ struct Outputs {                // any pointer may be null = stream not wanted
 // "multi-patch" (the smoothing trigger) <=> two different patches touched the cell: the first toucher claims `first1` with
 // a compare-and-swap (0 -> patch + 1); whoever finds another patch's claim stores 1 into `multi` (idempotent).
 // The apply pass computes Q8 means from the sums on the fly (there is no finalize pass).
+#ifndef TMC2_TOUCH_SHIFT
+#define TMC2_TOUCH_SHIFT 2
+#endif
+constexpr uint32_t kTouchShift = TMC2_TOUCH_SHIFT;   // log2(cells per bit of the touched bitmap)
 constexpr uint32_t kCellEmpty = 0xFFFFFFFFu;      // free slot of a hashed table's key array
 struct GeoCell {     // 32 B = one DRAM sector
   uint32_t first1;              // patch index + 1 of the first toucher, 0 = untouched

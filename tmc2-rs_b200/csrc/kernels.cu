@@ -553,7 +553,7 @@ __device__ __noinline__ uint32_t generic_slot_count(const UnpackArgs& a, uint32_
 // cell multi-patch (idempotent flag word in the cell + its bit in the frame's multi-patch bitmap, which the probe reads).
 __device__ __forceinline__ void claim_result(const GridDesc& G, uint32_t fig, uint32_t cs, uint32_t old, uint32_t patch) {
   if (old == 0u) {
-    atomicOr(G.tbits + (uint64_t)fig * G.twords + (cs >> 7), 1u << ((cs >> 2) & 31u));
+    atomicOr(G.tbits + (uint64_t)fig * G.twords + (cs >> (5u + kTouchShift)), 1u << ((cs >> kTouchShift) & 31u));
   } else if (old != patch + 1u) {
     reinterpret_cast<volatile uint32_t*>(static_cast<uint8_t*>(G.table) + ((uint64_t)fig * G.slots + cs) * 32u)[1] = 1u;
     atomicOr(G.mbits + (uint64_t)fig * G.mwords + (cs >> 5), 1u << (cs & 31u));
@@ -1668,14 +1668,14 @@ __global__ void __launch_bounds__(256) smooth_clear_kernel(const __grid_constant
       if (t == 0) continue;
       tb[w] = 0;
 #pragma unroll
-      for (uint32_t i = 0; i < 4; ++i)
-        if (4u * w + i < G.mwords) mb[4u * w + i] = 0;
+      for (uint32_t i = 0; i < (1u << kTouchShift); ++i)
+        if ((w << kTouchShift) + i < G.mwords) mb[(w << kTouchShift) + i] = 0;
       while (t) {
         const uint64_t q = w * 32u + ((uint32_t)__ffs(t) - 1u);                     // quad = cells 4q .. 4q+3 = one 128-byte line
         t &= t - 1u;
 #pragma unroll
-        for (uint32_t i = 0; i < 4; ++i) {
-          const uint64_t cs = 4u * q + i;
+        for (uint32_t i = 0; i < (1u << kTouchShift); ++i) {
+          const uint64_t cs = (q << kTouchShift) + i;
           if (cs >= G.slots) break;
           tab[cs * 2] = make_uint4(0, 0, 0, 0);
           tab[cs * 2 + 1] = make_uint4(0, 0, 0, 0);

@@ -494,8 +494,8 @@ struct Batch {
           CU(cudaMemsetAsync(tab.p, 0, (size_t)TF * slots * cell_bytes, stream));     // all-zero == empty cell
           CU(mbits.ensure((size_t)TF * ((slots + 31) / 32) * 4));
           CU(cudaMemsetAsync(mbits.p, 0, (size_t)TF * ((slots + 31) / 32) * 4, stream));
-          CU(tbits.ensure((size_t)TF * ((slots + 127) / 128) * 4));
-          CU(cudaMemsetAsync(tbits.p, 0, (size_t)TF * ((slots + 127) / 128) * 4, stream));
+          CU(tbits.ensure((size_t)TF * ((slots + (32u << kTouchShift) - 1) / (32u << kTouchShift)) * 4));
+          CU(cudaMemsetAsync(tbits.p, 0, (size_t)TF * ((slots + (32u << kTouchShift) - 1) / (32u << kTouchShift)) * 4, stream));
           if (hashed) {
             CU(keys.ensure((size_t)TF * slots * 4));
             KL(launch_fill_u32(keys.as<uint32_t>(), (uint64_t)TF * slots, kCellEmpty, stream));
@@ -666,7 +666,7 @@ struct Batch {
             G.cmask = (G.w - 1u) * 0x10001u;
           }
         }
-        G.mbits = mbits; G.tbits = tbits; G.mwords = (slots + 31) / 32; G.twords = (slots + 127) / 128;
+        G.mbits = mbits; G.tbits = tbits; G.mwords = (slots + 31) / 32; G.twords = (slots + (32u << kTouchShift) - 1) / (32u << kTouchShift);
       };
       grid(a.sm.geo, smoothing_geo, params.grid_size, d_geotab.p, d_geokeys.as<uint32_t>(), geotab_slots, geotab_hashed,
            d_geombits.as<uint32_t>(), d_geotbits.as<uint32_t>());
