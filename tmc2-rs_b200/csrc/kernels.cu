@@ -680,7 +680,10 @@ __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, uint32_t pid
 }
 
 // ---- pass 1: points per owned slot ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerTile * 32, 6) count_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
+#ifndef TMC2_COUNT_MINCTA
+#define TMC2_COUNT_MINCTA 8
+#endif
+__global__ void __launch_bounds__(kWarpsPerTile * 32, TMC2_COUNT_MINCTA) count_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
   const uint32_t lane = lane_id();
   const uint32_t lpos = (blockIdx.x + tile_offset) * kWarpsPerTile + (threadIdx.x >> 5);
   uint32_t mode;
@@ -1606,7 +1609,10 @@ __device__ __forceinline__ uint32_t probe_multi_fast(const GridDesc& G, uint32_t
   return any;
 }
 
-__global__ void __launch_bounds__(256) smooth_probe_kernel(const __grid_constant__ UnpackArgs a) {
+#ifndef TMC2_PROBE_MINCTA
+#define TMC2_PROBE_MINCTA 1
+#endif
+__global__ void __launch_bounds__(256, TMC2_PROBE_MINCTA) smooth_probe_kernel(const __grid_constant__ UnpackArgs a) {
   const uint32_t fig = blockIdx.y;
   const uint32_t f = a.sm.group_first_frame + fig;
   const uint32_t n = min((uint64_t)a.sm.blist_count[f], a.sm.blist_cap);
