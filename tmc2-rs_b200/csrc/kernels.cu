@@ -1610,7 +1610,7 @@ __device__ __forceinline__ uint32_t probe_multi_fast(const GridDesc& G, uint32_t
 }
 
 #ifndef TMC2_PROBE_MINCTA
-#define TMC2_PROBE_MINCTA 1
+#define TMC2_PROBE_MINCTA 8
 #endif
 __global__ void __launch_bounds__(256, TMC2_PROBE_MINCTA) smooth_probe_kernel(const __grid_constant__ UnpackArgs a) {
   const uint32_t fig = blockIdx.y;
@@ -1637,7 +1637,10 @@ __global__ void __launch_bounds__(256, TMC2_PROBE_MINCTA) smooth_probe_kernel(co
   }
 }
 
-__global__ void __launch_bounds__(128) smooth_apply_kernel(const __grid_constant__ UnpackArgs a) {
+#ifndef TMC2_APPLY_MINCTA
+#define TMC2_APPLY_MINCTA 1
+#endif
+__global__ void __launch_bounds__(128, TMC2_APPLY_MINCTA) smooth_apply_kernel(const __grid_constant__ UnpackArgs a) {
   const uint32_t fig = blockIdx.y;
   const uint32_t f = a.sm.group_first_frame + fig;
   const uint32_t m = min((uint64_t)a.sm.slist_count[f], a.sm.blist_cap);
