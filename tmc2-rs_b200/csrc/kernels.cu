@@ -1070,6 +1070,12 @@ struct SmoothState {
 #ifndef TMC2_MINCTA
 #define TMC2_MINCTA 4
 #endif
+#ifndef TMC2_LATE_ATTR_ALL
+#define TMC2_LATE_ATTR_ALL 0
+#endif
+#ifndef TMC2_LATE_ATTR
+#define TMC2_LATE_ATTR 1
+#endif
 #ifndef TMC2_PREFETCH_TILES_SMOOTH
 #define TMC2_PREFETCH_TILES_SMOOTH 0
 #endif
@@ -1127,16 +1133,35 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
     const uint32_t x0 = (uint32_t)R.bx * 16u + 8u * h, y = (uint32_t)R.by * 16u + r;
     uint4 ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
     uint2 ua = {0, 0}, va = {0, 0}, ub = {0, 0}, vb = {0, 0};
-    if (has_attr) {                                                                  // decoder.rs:976-977
+    // kLateAttr (experiment): the attribute planes are only prefetched into L2 here and loaded after the geometry has been
+    // digested, so that fewer load results are in registers at once
+    constexpr bool kLateAttr = (kSmooth && TMC2_LATE_ATTR) || TMC2_LATE_ATTR_ALL;
+    // (addresses are worked out inside the lambda: nothing attribute-related stays live while the geometry is digested)
+    auto attr_planes = [&](auto&& touch) {                                           // decoder.rs:976-977
       const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride;
       const uint32_t yoff = y * a.in.attr_pitch_y + x0;
-      ya = ldg_nc_v4(ay0 + yoff); yb = ldg_nc_v4(ay0 + a.in.attr_y_map_stride + yoff);
       const uint64_t cf = (uint64_t)frame * 2 * a.in.attr_c_map_stride;
       const uint32_t coff = (y >> 1) * a.in.attr_pitch_c + (x0 >> 1);
       const uint16_t* au0 = a.in.attr_u + cf + coff; const uint16_t* av0 = a.in.attr_v + cf + coff;
-      // the two rows of a chroma row pair ask for the same addresses in the same instruction: one fetch
-      ua = ldg_nc_v2(au0); va = ldg_nc_v2(av0);
-      ub = ldg_nc_v2(au0 + a.in.attr_c_map_stride); vb = ldg_nc_v2(av0 + a.in.attr_c_map_stride);
+      touch(ay0 + yoff, ay0 + a.in.attr_y_map_stride + yoff, au0, av0, au0 + a.in.attr_c_map_stride, av0 + a.in.attr_c_map_stride);
+    };
+    auto load_attr = [&]() {
+      attr_planes([&](const uint16_t* y0, const uint16_t* y1, const uint16_t* u0, const uint16_t* v0, const uint16_t* u1,
+                      const uint16_t* v1) {
+        ya = ldg_nc_v4(y0); yb = ldg_nc_v4(y1);
+        // the two rows of a chroma row pair ask for the same addresses in the same instruction: one fetch
+        ua = ldg_nc_v2(u0); va = ldg_nc_v2(v0); ub = ldg_nc_v2(u1); vb = ldg_nc_v2(v1);
+      });
+    };
+    if (has_attr) {
+      if (kLateAttr) {
+        attr_planes([&](const uint16_t* y0, const uint16_t* y1, const uint16_t* u0, const uint16_t* v0, const uint16_t* u1,
+                        const uint16_t* v1) {
+          prefetch_l2(y0); prefetch_l2(y1); prefetch_l2(u0); prefetch_l2(v0); prefetch_l2(u1); prefetch_l2(v1);
+        });
+      } else {
+        load_attr();
+      }
     }
     CanvasBlock L;
     load_geometry(a, R, P, lane, L);
@@ -1161,6 +1186,8 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
         nmin = __reduce_min_sync(kFull, min(lo & 0xFFFFu, lo >> 16));
       }
     }
+
+    if (kLateAttr && has_attr) load_attr();
 
     // ---- (2): tables in patch raster order -----------------------------------------------------------------------------
     // canvas-local (lx, ly) = (8h + j, r) -> patch-local (u1, v1) through the inverse of the affine map (decoder.rs:853-867)
