@@ -807,6 +807,9 @@ struct Batch {
     memcpy(&dev_err, hs + (size_t)F * 20, 4);
     if (dev_err) {
       CU(cudaMemsetAsync(d_err.p, 0, 4, s));
+      // a slot that bailed out may have claimed cells without marking them touched: the clear pass would miss them, so the
+      // next launch of this batch starts from freshly zeroed tables
+      geotab_slots = coltab_slots = 0; geotab_frames = coltab_frames = 0;
       FAIL((tmc2_status)dev_err, "device-side failure flag %d (7 = output capacity, 11 = watchdog / table)", dev_err);
     }
     counts.assign(F, 0); moved.assign(F, 0); recoloured.assign(F, 0);
