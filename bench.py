@@ -191,6 +191,14 @@ def main():
                                  "host_cores": os.cpu_count()},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
+        # context only: the same port with one worker per host core, frames in parallel (the reference itself reconstructs on
+        # one thread, src/lib.rs:113 -- the headline `value` above is that)
+        cores = len(os.sched_getaffinity(0))
+        if cores > 1 and args.ref_threads <= 1:
+            par = min(cores, max(frames, 1))
+            pts2, dt2 = cpu_reference_run(gof, par, 2, 1, par)
+            line["cpu_baseline"]["frame_parallel"] = {"value": pts2 / dt2, "unit": UNIT, "cores": par,
+                                                      "sample": f"{par} frames at once x 2 steps"}
         print(json.dumps(line))
         return 0
 
