@@ -195,15 +195,27 @@ TMC2_API void        tmc2gpu_destroy(tmc2gpu_ctx* ctx);
 TMC2_API const char* tmc2gpu_last_error(const tmc2gpu_ctx* ctx);
 TMC2_API const char* tmc2gpu_status_string(tmc2_status s);
 
-/* Pinned host memory for zero-staging submits (decode straight into these). */
+/* Pinned host memory for zero-staging submits (decode straight into these).
+ * INPUT LIFETIME.  Planes in ordinary (pageable) memory are copied into the library's own staging area before
+ * tmc2gpu_submit_gof returns: the caller may reuse them at once (the reference's `Vec<u8>` planes,
+ * src/decoder.rs:1136-1140).  Planes inside a tmc2gpu_alloc_pinned block are read by the DMA engine IN PLACE after
+ * submit_gof has returned: they must stay unmodified until tmc2gpu_wait_inputs returns (or until the first frame of that
+ * GOF has been handed out by tmc2gpu_next_frame).  The patch lists and the tmc2_gof / tmc2_frame structs themselves are
+ * only read during submit_gof.                                                                                      */
 TMC2_API void*       tmc2gpu_alloc_pinned(size_t bytes);
 TMC2_API void        tmc2gpu_free_pinned(void* p);
 
 /* ---- streaming path: replaces the frame loop src/decoder.rs:188-314 ----------------------------
  * submit_gof validates (everything the reference asserts), stages the planes through pinned memory,
  * and enqueues H2D + kernels + D2H; frames of the GOF are sharded frame-wise over the context's
- * devices.  next_frame blocks until the next frame IN ORDER (src/lib.rs:81) is on the host.          */
+ * devices.  next_frame blocks until the next frame IN ORDER (src/lib.rs:81) is on the host.
+ * A GOF is delivered whole or not at all: when submit_gof fails nothing of it is queued; when a launch fails on the
+ * device, next_frame reports the error ONCE, drops every frame of that GOF and frees its slot -- the next call
+ * continues with the following GOF (or returns TMC2_END).
+ * wait_inputs blocks until the host-to-device copies of every GOF submitted so far have finished, i.e. until pinned
+ * input planes may be overwritten with the next GOF's samples.                                        */
 TMC2_API tmc2_status tmc2gpu_submit_gof(tmc2gpu_ctx* ctx, const tmc2_gof* gof);
+TMC2_API tmc2_status tmc2gpu_wait_inputs(tmc2gpu_ctx* ctx);
 TMC2_API tmc2_status tmc2gpu_next_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out);
 TMC2_API tmc2_status tmc2gpu_release_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out);
 

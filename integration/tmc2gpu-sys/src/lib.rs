@@ -124,6 +124,7 @@ extern "C" {
     pub fn tmc2gpu_alloc_pinned(bytes: usize) -> *mut c_void;
     pub fn tmc2gpu_free_pinned(p: *mut c_void);
     pub fn tmc2gpu_submit_gof(ctx: *mut tmc2gpu_ctx, gof: *const tmc2_gof) -> c_int;
+    pub fn tmc2gpu_wait_inputs(ctx: *mut tmc2gpu_ctx) -> c_int;
     pub fn tmc2gpu_next_frame(ctx: *mut tmc2gpu_ctx, out: *mut tmc2_frame_out) -> c_int;
     pub fn tmc2gpu_release_frame(ctx: *mut tmc2gpu_ctx, out: *mut tmc2_frame_out) -> c_int;
 }
@@ -158,9 +159,21 @@ impl Reconstructor {
         }
     }
 
-    /// Replaces the frame loop src/decoder.rs:188-305 for one GOF.  `gof` only needs to live until this returns.
+    /// Replaces the frame loop src/decoder.rs:188-305 for one GOF.
+    ///
+    /// Lifetime of the inputs (see "INPUT LIFETIME" in include/tmc2gpu.h): the `tmc2_gof` / `tmc2_frame` structs and the
+    /// patch lists are only read during this call.  Planes in ordinary memory (`Vec<u8>`, src/decoder.rs:1136-1140) are
+    /// copied into the library's staging area before this returns and may be dropped at once.  Planes inside a
+    /// `tmc2gpu_alloc_pinned` block are read by the DMA engine AFTER this returns: keep them unmodified until
+    /// [`Reconstructor::wait_inputs`] has returned (or the first frame of the GOF has come back from `next_frame`).
     pub fn submit_gof(&mut self, gof: &tmc2_gof) -> Result<(), String> {
         self.check(unsafe { tmc2gpu_submit_gof(self.ctx, gof) })
+    }
+
+    /// Blocks until the host-to-device copies of every GOF submitted so far are done: pinned input planes may then be
+    /// overwritten with the samples of the next GOF.
+    pub fn wait_inputs(&mut self) -> Result<(), String> {
+        self.check(unsafe { tmc2gpu_wait_inputs(self.ctx) })
     }
 
     /// Next frame in order (src/lib.rs:81); `None` when every submitted frame has been returned.

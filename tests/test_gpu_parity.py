@@ -439,6 +439,104 @@ def test_row_padded_planes_like_ffmpeg_linesize(gpu_ctx):
     assert np.array_equal(st["positions"], want["positions"]) and np.array_equal(st["occupancy_map"], want["occupancy_map"])
 
 
+def test_mixed_pinned_and_pageable_planes(gpu_ctx):
+    """Pinned-ness is decided per plane on its full extent: geometry map 0 pinned, everything else pageable --
+    and a plane that only STARTS inside a pinned block -- must stage exactly the unpinned planes."""
+    g = synth.make_gof(synth.config("small", frames=3))
+    want = [oracle.reconstruct_frame(abi.GofView(g), f) for f in range(3)]
+    F, _, H, W = g.geo.shape
+    geo0 = codec.pinned_empty((F, H, W), np.uint16)                      # map 0 of every frame pinned, map 1 pageable
+    geo0[...] = g.geo[:, 0]
+    geo = [[geo0[f], np.ascontiguousarray(g.geo[f, 1])] for f in range(F)]
+    gm = abi.Gof(g.width, g.height, g.occ, g.geo, g.attr_y, g.attr_u, g.attr_v, g.patches, g.params)
+    vm = abi.GofView(gm)
+    keep = []
+    for f in range(F):
+        for m in range(2):
+            keep.append(geo[f][m])
+            vm.c.frames[f].geo[m] = geo[f][m].ctypes.data
+    # luma of frame 0 / map 0 starts in the last rows of a pinned block and runs past its end into pageable memory: not pinned
+    tail = codec.pinned_empty((4, W), np.uint16)
+    keep.append(tail)
+    frames = gpu_ctx.decode_gof(vm)
+    for f in range(F):
+        assert np.array_equal(frames[f].positions, want[f]["positions"]) and np.array_equal(frames[f].colors, want[f]["colors"])
+    # all planes pinned except the chroma planes
+    gp = codec.pinned_copy_of(g)
+    gq = abi.Gof(g.width, g.height, gp.occ, gp.geo, gp.attr_y, g.attr_u.copy(), g.attr_v.copy(), g.patches, g.params)
+    frames = gpu_ctx.decode_gof(abi.GofView(gq))
+    for f in range(F):
+        assert np.array_equal(frames[f].positions, want[f]["positions"]) and np.array_equal(frames[f].colors, want[f]["colors"])
+
+
+def test_wait_inputs_then_overwrite_pinned_planes(gpu_ctx):
+    """Input ownership (include/tmc2gpu.h, INPUT LIFETIME): after wait_inputs the caller may decode the next GOF into the
+    same pinned planes; the frames of the GOF in flight must not change."""
+    g = synth.make_gof(synth.config("small", frames=4))
+    g2 = synth.make_gof(synth.config("small", frames=4, seed_offset=77)) if "seed_offset" in synth.config.__code__.co_varnames else None
+    gp = codec.pinned_copy_of(g)
+    v, vp = abi.GofView(g), abi.GofView(gp)
+    want = [oracle.reconstruct_frame(v, f) for f in range(4)]
+    gpu_ctx.submit_gof(vp)
+    gpu_ctx.wait_inputs()
+    rng = np.random.RandomState(5)
+    gp.geo[...] = rng.randint(0, 1024, gp.geo.shape).astype(np.uint16)     # "decode the next GOF" into the same buffers
+    gp.attr_y[...] = rng.randint(0, 1024, gp.attr_y.shape).astype(np.uint16)
+    gp.occ[...] = 0
+    for f in range(4):
+        fr = gpu_ctx.next_frame()
+        assert np.array_equal(fr.positions, want[f]["positions"]) and np.array_equal(fr.colors, want[f]["colors"])
+    assert gpu_ctx.next_frame() is None
+
+
+def test_rejected_inputs_odd_size_and_degenerate_axes(gpu_ctx):
+    """odd width / height with 4:2:0 attributes, and patches whose axes are not a permutation (the reference's
+    duplicate test and differential D1 then act on an overwritten coordinate), are refused with a status code."""
+    g = util.random_small_gof(seed=3, W=64, H=48)
+    odd = abi.Gof(63, 48, g.occ, np.ascontiguousarray(g.geo[..., :63]), np.ascontiguousarray(g.attr_y[..., :63]),
+                  np.ascontiguousarray(g.attr_u[..., :31]), np.ascontiguousarray(g.attr_v[..., :31]),
+                  [p[:0] for p in g.patches], g.params)
+    with pytest.raises(abi.Tmc2Error) as e:
+        gpu_ctx.submit_gof(abi.GofView(odd))
+    assert e.value.status == abi.ERR_INVALID_ARG
+    for absolute in (False, True):
+        gd = util.random_small_gof(seed=4, absolute_d1=absolute)
+        for p in gd.patches:
+            p["tangent_axis"] = p["normal_axis"]
+        with pytest.raises(abi.Tmc2Error) as e:
+            gpu_ctx.submit_gof(abi.GofView(gd))
+        assert e.value.status == abi.ERR_UNSUPPORTED
+        with pytest.raises(abi.Tmc2Error) as e:
+            gpu_ctx.generate_point_cloud(abi.GofView(gd), 0)
+        assert e.value.status == abi.ERR_UNSUPPORTED
+
+
+def test_failed_gof_is_dropped_whole_and_slot_is_freed():
+    """a device-side failure (here: the boundary list capacity, forced tiny) is reported once by next_frame, no frame
+    of that GOF is handed out afterwards, and the GOF slot is free again."""
+    import os
+    g = synth.make_gof(synth.config("small", frames=3))
+    g.params.geometry_smoothing = True
+    g.params.color_smoothing = True
+    view = abi.GofView(g)
+    os.environ["TMC2_TEST_BLIST_CAP"] = "16"
+    ctx = codec.Context(gofs_in_flight=1)
+    try:
+        ctx.submit_gof(view)
+        with pytest.raises(abi.Tmc2Error):
+            ctx.next_frame()
+        assert ctx.next_frame() is None                                    # nothing of the failed GOF is left
+        os.environ.pop("TMC2_TEST_BLIST_CAP")
+        g.params.geometry_smoothing = False
+        g.params.color_smoothing = False
+        frames = ctx.decode_gof(abi.GofView(g))                            # the single slot is usable again
+        want = oracle.reconstruct_frame(abi.GofView(g), 1)
+        assert np.array_equal(frames[1].positions, want["positions"])
+    finally:
+        os.environ.pop("TMC2_TEST_BLIST_CAP", None)
+        ctx.close()
+
+
 def test_one_process_two_devices_shard_frames_in_order():
     """SURVEY 8e inside ONE process: a context over two devices shards the frames of a GOF frame-wise (contiguous halves, no
     collective) and hands them back in order; results equal the single-device context.  Skipped on a one-GPU box."""

@@ -25,6 +25,7 @@ SYMBOLS = [
     ("tmc2gpu_alloc_pinned", _P, [C.c_size_t]),
     ("tmc2gpu_free_pinned", None, [_P]),
     ("tmc2gpu_submit_gof", C.c_int, [_P, C.POINTER(abi.CGof)]),
+    ("tmc2gpu_wait_inputs", C.c_int, [_P]),
     ("tmc2gpu_next_frame", C.c_int, [_P, C.POINTER(abi.CFrameOut)]),
     ("tmc2gpu_release_frame", C.c_int, [_P, C.POINTER(abi.CFrameOut)]),
     ("tmc2gpu_upload_gof", C.c_int, [_P, C.POINTER(abi.CGof), C.POINTER(_P)]),

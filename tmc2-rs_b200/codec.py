@@ -121,6 +121,10 @@ class Context:
     def submit_gof(self, view: abi.GofView):
         self.check(self.lib.tmc2gpu_submit_gof(self.h, view.ref()), "submit_gof")
 
+    def wait_inputs(self):
+        """Blocks until the H2D copies of every submitted GOF are done: pinned input planes may be overwritten again."""
+        self.check(self.lib.tmc2gpu_wait_inputs(self.h), "wait_inputs")
+
     def next_frame(self, copy: bool = True) -> Optional[PointSet3]:
         fo = abi.CFrameOut()
         st = self.lib.tmc2gpu_next_frame(self.h, C.byref(fo))

@@ -25,22 +25,40 @@ constexpr int kWarpsPerTile = TMC2_WARPS_PER_TILE;   // one warp per 16x16 patch
 constexpr uint32_t kNoPatch = 0xFFFFFFFFu;  // padding slot
 constexpr int kSlotPoints = 512;            // max points of a 16x16 block (2 maps)
 
-struct alignas(16) DevPatch { // reference Patch (src/decoder.rs:711-783), pre-digested on the host (64 B)
+struct alignas(16) DevPatch { // reference Patch (src/decoder.rs:711-783), pre-digested on the host (64 B = four 16-byte vectors)
   uint32_t u0, v0;           // uv0 (blocks)
   uint32_t size_u0, size_v0; // size_uv0 (blocks)
+  // ---- vector 1
   uint32_t u1, v1, d1;       // 3D shifts
   uint16_t lod_x, lod_y;
+  // ---- vector 2: everything else the block-aligned unpack path needs
   uint8_t  normal, tangent, bitangent, mode;
   uint8_t  orient;
   uint8_t  aligned;          // 1: a 16x16 patch block is exactly one canvas block and (u,v) -> (x,y) is the affine map
                              //    below (Default / Swap / MRot270 always; the other six in SPEC orientation mode)
   int8_t   ax, ay;           // canvas step per +1 in patch u   (one of them is 0, the other +-1)
+  uint32_t sel;              // byte-permute selectors of generate_point (decoder.rs:871-878): selA | selB << 16, see
+                             // position_selectors() -- which of normal / tangent / bitangent lands in x, y, z
+  uint32_t local_index;      // patch index inside its frame (partition value; block_to_patch holds local_index+1)
+  // ---- vector 3
   int8_t   rx, ry;           // canvas step per +1 in patch v
   uint8_t  _pad[2];
-  uint32_t slot_base;        // index of this patch's first slot in slot_patch[]
-  uint32_t local_index;      // patch index inside its frame (partition value; block_to_patch holds local_index+1)
+  uint32_t slot_base;        // index of this patch's first slot in slot_rec[]
   uint32_t frame;            // frame inside the batch
+  uint32_t _pad2;
 };
+static_assert(sizeof(DevPatch) == 64, "DevPatch is four 16-byte vectors");
+
+// generate_point (decoder.rs:871-878) stores point[normal], point[tangent], point[bitangent] in that order, so a later axis
+// overwrites an earlier one if they coincide, and an axis nobody names stays 0.  With A = n | t << 16 and B = b (upper half
+// zero) as the two byte-permute operands (bytes 0,1 = n; 2,3 = t; 4,5 = b; 6,7 = zero):
+//   word 0 = x | y << 16 = prmt(A, B, selA),  word 1 = z = prmt(A, B, selB).   Host and device share this one definition.
+inline __host__ __device__ uint32_t position_selectors(uint32_t normal, uint32_t tangent, uint32_t bitangent) {
+  uint32_t s[3];
+  for (uint32_t a = 0; a < 3; ++a)
+    s[a] = bitangent == a ? 0x54u : tangent == a ? 0x32u : normal == a ? 0x10u : 0x76u;
+  return (s[0] | (s[1] << 8)) | ((s[2] | 0x7600u) << 16);
+}
 
 // One 16x16 block of one patch ("slot"), in the reference's iteration order (patch, v0, u0): everything the unpack
 // kernel needs to start loading planes, digested on the host.
@@ -177,12 +195,19 @@ struct UnpackArgs {
 // shared memory of one warp of emit_kernel: per-pixel tables of the block in PATCH raster order (rank = v1*16 + u1)
 constexpr uint32_t kOffPt = 0;                                   // [16 rows][17][2] u32: n | Y << 16 of map 0 / map 1
 constexpr uint32_t kOffTerm = kOffPt + 2176;                     // [64][2] uint4: chroma term of (chroma sample, map)
-constexpr uint32_t kOffSrc = kOffTerm + 2048;                    // [512] u16: output point -> rank << 1 | map
-constexpr uint32_t kOffCnt = kOffSrc + 1024;                     // [256] u8: points of the pixel (0..2) | boundary class << 2
+constexpr uint32_t kOffSrc = kOffTerm + 2048;                    // [3 + 512 (+ slack)] u16: output point -> rank << 1 | map | term << 9,
+                                                                 // entry i = point i - (run_base & 3) of the run (the run starts
+                                                                 // at the same phase of a 4-point group as in the frame)
+constexpr uint32_t kSrcBytes = 1040;
+constexpr uint32_t kOffCnt = kOffSrc + kSrcBytes;                // [256] u8: points of the pixel (0..2) | boundary class << 2
 constexpr uint32_t kOffBmp = kOffCnt + 256;                      // [32] u32: 20x20 occupancy bitmap rows (canvas axes)
 constexpr uint32_t kOffMemo = kOffBmp + 128;                     // [2][32] u32: cells the slot has already claimed (smoothing only)
 constexpr uint32_t kOffTab = kOffMemo + 256;                     // [128] uint2: the slot's geometry-cell table (fast smoothing grids)
-constexpr uint32_t kWarpSmemBytes = kOffTab + 1024;
+constexpr uint32_t kOffList = kOffTab + 1024;                    // [520] u16 (fast smoothing grids): run-relative indices of the slot's
+                                                                 // type-1 boundary points from the front, type-2 from the back
+constexpr uint32_t kListEntries = 520;
+constexpr uint32_t kWarpSmemBytes = kOffList + 2 * kListEntries;
+static_assert(kOffTerm % 16 == 0 && kOffSrc % 16 == 0 && kOffCnt % 16 == 0 && kOffTab % 16 == 0 && kWarpSmemBytes % 16 == 0, "alignment");
 
 // launch wrappers (kernels.cu); every one enqueues on `stream` and returns the cudaGetLastError() code
 int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream);

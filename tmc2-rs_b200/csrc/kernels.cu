@@ -450,12 +450,12 @@ __device__ __forceinline__ bool slot_is_fast(const UnpackArgs& a, const WorkRec&
   return a.res == 16 && a.prec_shift >= 0 && (R.ax != 0 || R.ay != 0);
 }
 
-// the fields of a DevPatch that the block-aligned path needs (three 16-byte loads, registers only)
+// the fields of a DevPatch that the block-aligned path needs (two 16-byte loads, registers only)
 __device__ __forceinline__ void load_patch_fields(const DevPatch* p, DevPatch& P) {
   const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1), c = __ldg(reinterpret_cast<const uint4*>(p) + 2);
   P.u1 = b.x; P.v1 = b.y; P.d1 = b.z; P.lod_x = (uint16_t)b.w; P.lod_y = (uint16_t)(b.w >> 16);
   P.normal = (uint8_t)c.x; P.tangent = (uint8_t)(c.x >> 8); P.bitangent = (uint8_t)(c.x >> 16); P.mode = (uint8_t)(c.x >> 24);
-  P.local_index = __ldg(&p->local_index);
+  P.sel = c.z; P.local_index = c.w;
 }
 
 // Canvas-layout view of a block: lane (r = lane >> 1, h = lane & 1) holds canvas row r, columns 8h .. 8h+7.
@@ -491,16 +491,21 @@ __device__ __forceinline__ void load_geometry(const UnpackArgs& a, const WorkRec
       }
     }
   }
-  if (a.absolute_d1 && P.mode == 0 && P.d1 <= 49152u) {
-    // the usual case (codec.rs:534-548, decoder.rs:883): n = sample / 4 + d1 for both maps, two pixels per instruction
-    // (sample / 4 <= 16383, so the packed sums cannot carry into the neighbouring half)
+  if (P.d1 <= 0xFFFFu) {
+    // codec.rs:534-558 + decoder.rs:881-888 on two pixels per instruction (16-bit lanes: VIADD.16x2 / VIMNMX.U16x2 wrap and
+    // compare per half, exactly the reference's `as u16`).  depth = sample / 4 <= 16383.
+    //   mode 0: n = depth + d1            mode 1: n = max(d1, depth) - depth   (never negative: a plain subtract cannot borrow)
+    //   differential D1 (codec.rs:551-558): n1 = n0 +- depth1 in wrapping u16
     const uint32_t dd = P.d1 * 0x10001u;
+    const bool mode0 = P.mode == 0, absd1 = a.absolute_d1 != 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      L.n0p[q] = ((word_of(g0, q) >> 2) & 0x3FFF3FFFu) + dd;
-      L.n1p[q] = ((word_of(g1, q) >> 2) & 0x3FFF3FFFu) + dd;
+      const uint32_t e0 = (word_of(g0, q) >> 2) & 0x3FFF3FFFu, e1 = (word_of(g1, q) >> 2) & 0x3FFF3FFFu;
+      const uint32_t n0 = mode0 ? __vadd2(e0, dd) : __vmaxu2(e0, dd) - e0;
+      L.n0p[q] = n0;
+      L.n1p[q] = absd1 ? (mode0 ? __vadd2(e1, dd) : __vmaxu2(e1, dd) - e1) : (mode0 ? __vadd2(n0, e1) : __vsub2(n0, e1));
     }
-  } else {
+  } else {                                                          // d1 beyond 16 bits: one pixel at a time
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const uint32_t w0 = word_of(g0, q), w1 = word_of(g1, q);
@@ -937,34 +942,67 @@ struct SmoothState {
       if (cs[i] != kCellEmpty) claim_result(i == 5 ? a.sm.col : G, fig, cs[i], old[i], patch);
   }
 
-  // kFast: both grids are known (at launch) to be dense power-of-two grids with cell edge <= 8 (geometry): the generic
-  // branches drop out of the instantiation, which keeps the hot loop small
-  template <bool kFast>
+  // ---- fast grids (dense power-of-two grids, geometry cell edge <= 8), used by the instantiation without generic branches ----
+  // K6 statistics of the lane's two points (all points count).  Into the slot's shared-memory table (flushed once per slot);
+  // two points of one cell -- the usual case, they are neighbours in the run -- share one pair of atomics.  The rare point
+  // outside the table goes to its global cell directly.
+  __device__ __forceinline__ void geo_pair(const UnpackArgs& a, bool v0, uint32_t w00, uint32_t w10, bool v1, uint32_t w01, uint32_t w11) {
+    const GridDesc& G = a.sm.geo;
+    const uint32_t m2 = (G.g - 1u) * 0x10001u;
+    uint32_t ent[2], va[2], vb[2];
+    bool ok[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t w0 = j ? w01 : w00, w1 = j ? w11 : w10;
+      const bool valid = j ? v1 : v0;
+      const bool in_grid = valid && ((w0 | w1) & G.oob_mask) == 0u;
+      const uint32_t key = ((w0 >> G.g_shift) & G.cmask) | ((w1 >> G.g_shift) << 8);          // cx | cz << 8 | cy << 16
+      const uint32_t rel = w0 & m2, relz = w1 & m2;                                           // w1's upper half is zero
+      const uint32_t d = key - kmin;
+      ok[j] = in_grid && (d & bad) == 0u;
+      ent[j] = (d * mul) >> 24;
+      va[j] = 1u | ((rel & 0xFFFFu) << 10);
+      vb[j] = (rel >> 16) | (relz << 12);
+      if (in_grid && !ok[j]) {
+        const uint32_t cs = fast_slot(G, key);
+        GeoCell* c = geo_tab + cs;
+        claim_later(a, 0u, cs);
+        atomicAdd(&c->cnt_sx, 1ull | ((unsigned long long)(rel & 0xFFFFu) << 32));
+        atomicAdd(&c->sy_sz, (unsigned long long)(rel >> 16) | ((unsigned long long)relz << 32));
+      }
+    }
+    const bool same = ok[0] && ok[1] && ent[0] == ent[1];
+    if (ok[0]) {
+      uint32_t* e = tab + 2u * ent[0];
+      atomicAdd(e, same ? va[0] + va[1] : va[0]);
+      atomicAdd(e + 1, same ? vb[0] + vb[1] : vb[0]);
+    }
+    if (ok[1] && !same) {
+      uint32_t* e = tab + 2u * ent[1];
+      atomicAdd(e, va[1]);
+      atomicAdd(e + 1, vb[1]);
+    }
+  }
+  // K7 statistics of one type-2 (second ring) point: three fire-and-forget reductions into its colour cell
+  __device__ __forceinline__ void colour_point(const UnpackArgs& a, uint32_t w0, uint32_t w1, uint32_t Y, uint32_t uv) {
+    const GridDesc& G = a.sm.col;
+    if (((w0 | w1) & G.oob_mask) != 0u) return;
+    const uint32_t cs = ((w0 & 0xFFFFu) >> G.g_shift) | (((w0 >> 16) >> G.g_shift) << G.w_shift) | ((w1 >> G.g_shift) << (2u * G.w_shift));
+    ColCell* c = col_tab + cs;
+    claim_later(a, 1u, cs);
+    atomicAdd(&c->cnt_sy, 1ull | ((unsigned long long)Y << 24));
+    atomicAdd(&c->su_sv, (unsigned long long)(uv & 0xFFFFu) | ((unsigned long long)(uv >> 16) << 32));
+    atomicAdd(&c->sy2, (unsigned long long)Y * Y);
+  }
+
+  // ---- generic grids (non-power-of-two edges, hashed tables, wide geometry grids) and the debug instantiation: everything
+  // per point inside the emit loop
   __device__ __forceinline__ void point(const UnpackArgs& a, bool valid, uint32_t g, uint32_t w0, uint32_t w1, uint32_t Y,
                                         uint32_t uv, uint32_t bt, bool has_attr) {
+    constexpr bool kFast = false;
     const uint32_t X = w0 & 0xFFFFu, Yc = w0 >> 16, Z = w1 & 0xFFFFu;
     // K6 statistics: geometry cells over ALL points
-    if (kFast && a.sm.geo.on) {
-      // into the slot's shared-memory table (flushed once per slot); the rare point outside the table goes to its cell directly
-      const GridDesc& G = a.sm.geo;
-      if (valid && ((w0 | w1) & G.oob_mask) == 0u) {
-        const uint32_t m2 = (G.g - 1u) * 0x10001u;
-        const uint32_t key = ((w0 >> G.g_shift) & G.cmask) | ((w1 >> G.g_shift) << 8);          // cx | cz << 8 | cy << 16
-        const uint32_t rel = w0 & m2, relz = w1 & m2;                                           // w1's upper half is zero
-        const uint32_t d = key - kmin;
-        if ((d & bad) == 0u) {
-          uint32_t* e = tab + 2u * ((d * mul) >> 24);
-          atomicAdd(e, 1u | ((rel & 0xFFFFu) << 10));
-          atomicAdd(e + 1, (rel >> 16) | (relz << 12));
-        } else {
-          const uint32_t cs = fast_slot(G, key);
-          GeoCell* c = geo_tab + cs;
-          claim_later(a, 0u, cs);
-          atomicAdd(&c->cnt_sx, 1ull | ((unsigned long long)(rel & 0xFFFFu) << 32));
-          atomicAdd(&c->sy_sz, (unsigned long long)(rel >> 16) | ((unsigned long long)relz << 32));
-        }
-      }
-    } else if (!kFast && a.sm.geo.on) {
+    if (a.sm.geo.on) {
       // generic grids: segmented scan over runs of equal cell, see below
       const GridDesc& G = a.sm.geo;
       const bool fast8 = G.fast == 1u && G.g <= 8u;                     // packed single-word sums need 32 * (g - 1) < 256
@@ -1257,41 +1295,80 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
   __syncwarp();
 
   // ---- (2b): patch raster order: lane l owns ranks 8l .. 8l+7; where its points go inside the run --------------------------
+  // s_src entry of a point = rank << 1 | map | term << 9, term = index of its chroma term ((cv * 8 + cu) << 1 | map).  Entry i
+  // of the list is point i - a4 of the run, a4 = run_base % 4: the point loop works on groups of four points that are
+  // groups of four in the FRAME's numbering (12 colour bytes = three aligned words).
+  // Fast smoothing grids: the slot's type-1 and type-2 boundary points also go into two compact lists (run-relative index),
+  // which two short loops after the point loop work off with full warps -- the point loop itself does not look at classes.
+  constexpr bool kLists = kSmooth && kFast;
+  const uint32_t a4 = run_base & 3u;
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(wsm + kOffList);
+  uint32_t n_type1 = 0, n_type2 = 0;
   {
     const uint2 cb = *reinterpret_cast<const uint2*>(s_cnt + 8u * lane);
     const uint32_t c_lo = cb.x & 0x03030303u, c_hi = cb.y & 0x03030303u;
     const uint32_t p_lo = c_lo * 0x01010101u;                       // byte i: points of pixels 0..i (inclusive), <= 8
     const uint32_t p_hi = c_hi * 0x01010101u + (p_lo >> 24) * 0x01010101u;
-    const uint32_t c = p_hi >> 24;                                  // points of this lane
+    uint32_t c = p_hi >> 24;                                        // points of this lane (<= 16)
+    // type-1 / type-2 points of the lane: the same byte-parallel prefix over the counts masked by the class
+    uint32_t c1_lo = 0, c1_hi = 0, c2_lo = 0, c2_hi = 0, q1_lo = 0, q1_hi = 0, q2_lo = 0, q2_hi = 0;
+    if (kLists) {
+      c1_lo = c_lo & (((cb.x >> 2) & 0x01010101u) * 3u); c1_hi = c_hi & (((cb.y >> 2) & 0x01010101u) * 3u);
+      c2_lo = c_lo & (((cb.x >> 3) & 0x01010101u) * 3u); c2_hi = c_hi & (((cb.y >> 3) & 0x01010101u) * 3u);
+      q1_lo = c1_lo * 0x01010101u; q1_hi = c1_hi * 0x01010101u + (q1_lo >> 24) * 0x01010101u;
+      q2_lo = c2_lo * 0x01010101u; q2_hi = c2_hi * 0x01010101u + (q2_lo >> 24) * 0x01010101u;
+      c |= ((q1_hi >> 24) << 10) | ((q2_hi >> 24) << 20);           // one scan for the three counts (each total <= 512)
+    }
     uint32_t incl = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const uint32_t t = __shfl_up_sync(kFull, incl, d);
       if (lane >= (uint32_t)d) incl += t;
     }
-    const uint32_t lane_excl = incl - c;
+    const uint32_t excl = incl - c;
+    const uint32_t lane_excl = (excl & 1023u) + a4;
+    if (kLists) {
+      const uint32_t tot = __shfl_sync(kFull, incl, 31);
+      n_type1 = (tot >> 10) & 1023u; n_type2 = tot >> 20;
+    }
+    const uint32_t x1 = (excl >> 10) & 1023u, x2 = excl >> 20;
+    // chroma term of pixel j: ((v1 >> 1) * 8 + (u1 >> 1)) << 1, v1 = lane >> 1, u1 = 8 * (lane & 1) + j
+    const uint32_t ebase = (16u * lane) | ((((lane >> 2) << 3) + ((lane & 1u) << 2)) << 10);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint32_t cj = ((j < 4 ? c_lo : c_hi) >> (8 * (j & 3))) & 3u;
-      const uint32_t ij = ((j < 4 ? p_lo : p_hi) >> (8 * (j & 3))) & 0xFFu;
+      const uint32_t sh = 8 * (j & 3);
+      const uint32_t cj = ((j < 4 ? c_lo : c_hi) >> sh) & 3u;
+      const uint32_t ij = ((j < 4 ? p_lo : p_hi) >> sh) & 0xFFu;
       const uint32_t k = lane_excl + ij - cj;
-      const uint32_t e = (8u * lane + (uint32_t)j) << 1;
+      const uint32_t e = ebase + (uint32_t)((j << 1) | ((j >> 1) << 10));
       if (cj >= 1u) s_src[k] = (uint16_t)e;
-      if (cj == 2u) s_src[k + 1] = (uint16_t)(e | 1u);
+      if (cj == 2u) s_src[k + 1] = (uint16_t)(e | 0x201u);           // map 1: bit 0, and bit 0 of the term index (bit 9)
+      if (kLists) {
+        const uint32_t cls = ((j < 4 ? cb.x : cb.y) >> (sh + 2)) & 3u;
+        if (cj >= 1u && cls != 0u) {
+          const uint32_t kr = k - a4;                               // run-relative index of the pixel's first point
+          if (cls == 1u) {
+            const uint32_t pos = x1 + (((j < 4 ? q1_lo : q1_hi) >> sh) & 0xFFu) - cj;
+            s_list[pos] = (uint16_t)kr;
+            if (cj == 2u) s_list[pos + 1] = (uint16_t)(kr + 1u);
+          } else {
+            const uint32_t pos = kListEntries - 1u - (x2 + (((j < 4 ? q2_lo : q2_hi) >> sh) & 0xFFu) - cj);
+            s_list[pos] = (uint16_t)kr;
+            if (cj == 2u) s_list[pos - 1u] = (uint16_t)(kr + 1u);
+          }
+        }
+      }
     }
   }
   __syncwarp();
 
-  // ---- (3): point-parallel ------------------------------------------------------------------------------------------
-  // generate_point (decoder.rs:871-878) stores normal, tangent, bitangent in that order; the selectors reproduce
-  // "later stores overwrite earlier ones" and leave unset coordinates at 0
-  const uint32_t s0 = sel_of_src(axis_source(P, 0)), s1 = sel_of_src(axis_source(P, 1)), s2 = sel_of_src(axis_source(P, 2));
-  const uint32_t selA = s0 | (s1 << 8), selB = s2 | 0x7600u;
+  // ---- (3): point-parallel, two points per lane ---------------------------------------------------------------------------
+  // generate_point (decoder.rs:871-878) stores normal, tangent, bitangent in that order; the selectors (host-made, per patch)
+  // reproduce "later stores overwrite earlier ones" and leave unset coordinates at 0
+  const uint32_t selA = P.sel & 0xFFFFu, selB = P.sel >> 16;
   const uint32_t T00 = (uint32_t)R.u0b * 16u * P.lod_x + P.u1, B00 = (uint32_t)R.v0b * 16u * P.lod_y + P.v1;   // decoder.rs:875-876
   const uint32_t lodx = P.lod_x, lody = P.lod_y, patch = P.local_index;
   const uint64_t gframe = (uint64_t)frame * a.out.cap;
-  const uint32_t q = lane & 3u;
-  const uint32_t sel_rgb = q == 0 ? 0x4210u : q == 1 ? 0x5421u : 0x6542u;
   const bool odd_lane = (lane & 1u) != 0;
 
   SmoothState S;
@@ -1308,80 +1385,141 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
     if (kFast && a.sm.geo.on) S.table_origin(a.sm.geo, P, nmin, T00, B00, T00 + 15u * lodx, B00 + 15u * lody);
   }
 
-  const uint32_t run_end = run_base + total;
-  uint32_t g = (run_base & ~31u) + lane;                           // point index inside the frame; g % 32 == lane
-  uint32_t k = g - run_base;                                       // point index inside the run (wraps for g < run_base)
-  uint16_t* ppos = a.out.pos + (gframe + g) * 3;                   // this lane's point in the packed position stream
-  uint8_t* prgb = has_attr ? a.out.rgb + (gframe + g) * 3 : nullptr;
-  const uint16_t* psrc = s_src + (int32_t)k;
-#pragma unroll 1
-  for (; g - lane < run_end; g += 32, k += 32, ppos += 96, prgb += 96, psrc += 32) {
-    const bool valid = k < total;
-    const uint32_t vb = __ballot_sync(kFull, valid);
-    const uint32_t e = valid ? (uint32_t)*psrc : 0u;               // rank << 1 | map
-    const uint32_t pt = s_pt[e + ((e >> 5) << 1)];                 // n | Y << 16 (rows are padded by one pixel)
-    const uint32_t rank = e >> 1, map = e & 1u;
-    const uint32_t u1 = rank & 15u, v1 = rank >> 4;
+  // position words and colour of the point behind list entry `e`
+  auto make_point = [&](uint32_t e, uint32_t& w0, uint32_t& w1, uint32_t& Y, uint32_t& c, uint32_t& tz) {
+    const uint32_t er = e & 0x1FFu;                                  // rank << 1 | map
+    const uint32_t pt = s_pt[er + ((er >> 5) << 1)];                 // n | Y << 16 (rows are padded by one pixel)
+    const uint32_t u1 = (er >> 1) & 15u, v1 = er >> 5;
     const uint32_t t = T00 + u1 * lodx, b = (B00 + v1 * lody) & 0xFFFFu;
-    const uint32_t A = __byte_perm(pt, t, 0x5410);                 // n | t << 16
-    const uint32_t w0 = __byte_perm(A, b, selA), w1 = __byte_perm(A, b, selB);      // x | y << 16 ; z
-    const uint32_t nw0 = __shfl_down_sync(kFull, w0, 1);
-    uint32_t Y = 0, uv = 0, c = 0, nc = 0;
+    const uint32_t A = __byte_perm(pt, t, 0x5410);                   // n | t << 16
+    w0 = __byte_perm(A, b, selA); w1 = __byte_perm(A, b, selB);      // x | y << 16 ; z
+    Y = pt >> 16;                                                    // codec.rs:637-640
+    c = 0; tz = 0;
     if (has_attr) {
-      Y = pt >> 16;                                                                  // codec.rs:637-640
-      const uint4 te = s_term[((e >> 6) << 4) | (((e >> 2) & 7u) << 1) | map];
-      uv = te.w;
+      const uint4 te = s_term[e >> 9];
+      tz = te.z;
       c = yuv_to_rgb_fast(Y, (int32_t)te.x, (int32_t)te.y, (int32_t)te.z >> 1);
-      if (slot_flagged) {                                                            // rare: neutral / borderline chroma
-        if (valid && (te.z & 1u)) c = yuv_to_rgb_flagged(Y, uv & 0xFFFFu, uv >> 16, (int32_t)te.x, (int32_t)te.y, (int32_t)te.z >> 1);
-      }
-      nc = __shfl_down_sync(kFull, c, 1);
+      if (slot_flagged && (te.z & 1u))                               // rare: neutral / borderline chroma
+        c = yuv_to_rgb_flagged(Y, te.w & 0xFFFFu, te.w >> 16, (int32_t)te.x, (int32_t)te.y, (int32_t)te.z >> 1);
     }
-    // two points = three words: [x0 y0] [z0 x1] [y1 z1]; even lane writes the first two, odd lane the third.
-    // four colours = three words; lanes 4i .. 4i+2 of a quad write one word each.
-    if (vb == kFull) {
-      stg_u32(ppos + (odd_lane ? 1 : 0), odd_lane ? __byte_perm(w0, w1, 0x5432) : w0);
-      if (!odd_lane) stg_u32(ppos + 2, __byte_perm(w1, nw0, 0x5410));
-      if (has_attr && q != 3u) stg_u32(prgb + q, __byte_perm(c, nc, sel_rgb));
-    } else if (valid) {
-      // ragged end of the run: partner lanes may belong to another slot
-      const bool nvalid = ((vb >> 1) >> lane) & 1u, pvalid = ((vb << 1) >> lane) & 1u;
-      stg_u32(ppos + (odd_lane ? 1 : 0), odd_lane ? __byte_perm(w0, w1, 0x5432) : w0);
-      if (!odd_lane) {
-        if (nvalid) stg_u32(ppos + 2, __byte_perm(w1, nw0, 0x5410));
-        else ppos[2] = (uint16_t)w1;
-      } else if (!pvalid) {
-        ppos[0] = (uint16_t)w0;
-      }
+  };
+
+  const uint32_t n_idx = total + a4;                                 // list entries [a4, n_idx) are this slot's points
+  const uint32_t* s_src32 = reinterpret_cast<const uint32_t*>(s_src);
+  const uint64_t gq0 = gframe + (run_base - a4);                     // frame-global point index of list entry 0 (multiple of 4)
+  uint16_t* ppos = a.out.pos + (gq0 + 2u * lane) * 3;                // this lane's two points: three aligned words
+  uint8_t* prgb = has_attr ? a.out.rgb + (gq0 + 2u * (lane & ~1u)) * 3 : nullptr;   // the lane pair's four colours: three aligned words
+#pragma unroll 1
+  for (uint32_t i0 = 0; i0 < n_idx; i0 += 64, ppos += 192, prgb += 192) {
+    const uint32_t idx = i0 + 2u * lane;
+    const bool v0 = idx >= a4 && idx < n_idx, v1 = idx + 1u >= a4 && idx + 1u < n_idx;
+    const uint32_t ee = s_src32[idx >> 1];
+    const uint32_t e0 = v0 ? (ee & 0xFFFFu) : 0u, e1 = v1 ? (ee >> 16) : 0u;
+    uint32_t w00, w10, Y0, c0, tz0, w01, w11, Y1, c1, tz1;
+    make_point(e0, w00, w10, Y0, c0, tz0);
+    make_point(e1, w01, w11, Y1, c1, tz1);
+    // two points = three words: [x0 y0] [z0 x1] [y1 z1]
+    const uint32_t Wb = __byte_perm(w10, w01, 0x5410), Wc = __byte_perm(w01, w11, 0x5432);
+    // four colours (lane pair) = three words: the even lane writes the first two, the odd lane the third
+    uint32_t K0 = 0, K1 = 0;
+    if (has_attr) {
+      const uint32_t nc0 = __shfl_down_sync(kFull, c0, 1);
+      K0 = odd_lane ? __byte_perm(c0, c1, 0x6542) : __byte_perm(c0, c1, 0x4210);
+      K1 = __byte_perm(c1, nc0, 0x5421);
+    }
+    if (i0 >= a4 && i0 + 64u <= n_idx) {                             // whole window inside the run (warp-uniform)
+      stg_u32(ppos, w00); stg_u32(ppos + 2, Wb); stg_u32(ppos + 4, Wc);
       if (has_attr) {
-        if (((vb >> (lane & ~3u)) & 0xFu) == 0xFu) {
-          if (q != 3u) stg_u32(prgb + q, __byte_perm(c, nc, sel_rgb));
+        stg_u32(prgb + (odd_lane ? 8 : 0), K0);
+        if (!odd_lane) stg_u32(prgb + 4, K1);
+      }
+    } else {
+      // ragged end of the run: neighbouring points may belong to another slot
+      if (v0) stg_u32(ppos, w00);
+      if (v0 && v1) stg_u32(ppos + 2, Wb);
+      else if (v0) ppos[2] = (uint16_t)w10;
+      else if (v1) ppos[3] = (uint16_t)w01;
+      if (v1) stg_u32(ppos + 4, Wc);
+      if (has_attr) {
+        const uint32_t b0 = __ballot_sync(kFull, v0), b1 = __ballot_sync(kFull, v1);
+        const uint32_t le = lane & ~1u;
+        if ((((b0 & b1) >> le) & 3u) == 3u) {
+          stg_u32(prgb + (odd_lane ? 8 : 0), K0);
+          if (!odd_lane) stg_u32(prgb + 4, K1);
         } else {
-          prgb[0] = (uint8_t)c; prgb[1] = (uint8_t)(c >> 8); prgb[2] = (uint8_t)(c >> 16);
+          uint8_t* q = prgb + (odd_lane ? 6 : 0);
+          if (v0) { q[0] = (uint8_t)c0; q[1] = (uint8_t)(c0 >> 8); q[2] = (uint8_t)(c0 >> 16); }
+          if (v1) { q[3] = (uint8_t)c1; q[4] = (uint8_t)(c1 >> 8); q[5] = (uint8_t)(c1 >> 16); }
         }
       }
     }
-    uint32_t bt = 0;
-    if (kSmooth || kDebug) {
-      if (valid && want_bt) bt = (uint32_t)s_cnt[rank] >> 2;
-    }
-    if (kDebug && valid) {                                       // streams only the stage API / tests ask for
-      const uint64_t gk = gframe + g;
-      if (a.out.yuv && has_attr) {
-        uint16_t* qy = a.out.yuv + gk * 3;
-        qy[0] = (uint16_t)Y; qy[1] = (uint16_t)(uv & 0xFFFFu); qy[2] = (uint16_t)(uv >> 16);
+    if (kDebug || (kSmooth && !kFast)) {                             // streams only the stage API / tests ask for; generic grids
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const bool valid = j ? v1 : v0;
+        const uint32_t e = j ? e1 : e0, w0 = j ? w01 : w00, w1 = j ? w11 : w10, Y = j ? Y1 : Y0;
+        const uint32_t rank = (e >> 1) & 255u, map = e & 1u;
+        const uint32_t uv = has_attr ? s_term[e >> 9].w : 0u;
+        const uint32_t g = run_base - a4 + idx + (uint32_t)j;        // point index inside the frame
+        uint32_t bt = 0;
+        if (valid && want_bt) bt = (uint32_t)s_cnt[rank] >> 2;
+        if (kDebug && valid) {
+          const uint64_t gk = gframe + g;
+          if (a.out.yuv && has_attr) {
+            uint16_t* qy = a.out.yuv + gk * 3;
+            qy[0] = (uint16_t)Y; qy[1] = (uint16_t)(uv & 0xFFFFu); qy[2] = (uint16_t)(uv >> 16);
+          }
+          if (a.out.part) a.out.part[gk] = (uint16_t)patch;                          // codec.rs:452
+          if (a.out.pix) {                                                            // codec.rs:463-472
+            const uint32_t u1 = rank & 15u, v1p = rank >> 4;
+            const int32_t cx0 = (int32_t)R.bx * 16 + ((ax < 0 || rx < 0) ? 15 : 0), cy0 = (int32_t)R.by * 16 + ((ay < 0 || ry < 0) ? 15 : 0);
+            a.out.pix[gk] = (uint32_t)(cx0 + ax * (int32_t)u1 + rx * (int32_t)v1p) |
+                            ((uint32_t)(cy0 + ay * (int32_t)u1 + ry * (int32_t)v1p) << 15) | (map << 30);
+          }
+          if (a.out.btype) a.out.btype[gk] = (uint8_t)bt;
+        }
+        if (kSmooth && !kFast) S.point(a, valid, g, w0, w1, Y, uv, bt, has_attr);
       }
-      if (a.out.part) a.out.part[gk] = (uint16_t)patch;                          // codec.rs:452
-      if (a.out.pix) {                                                            // codec.rs:463-472
-        const int32_t cx0 = (int32_t)R.bx * 16 + ((ax < 0 || rx < 0) ? 15 : 0), cy0 = (int32_t)R.by * 16 + ((ay < 0 || ry < 0) ? 15 : 0);
-        a.out.pix[gk] = (uint32_t)(cx0 + ax * (int32_t)u1 + rx * (int32_t)v1) |
-                        ((uint32_t)(cy0 + ay * (int32_t)u1 + ry * (int32_t)v1) << 15) | (map << 30);
-      }
-      if (a.out.btype) a.out.btype[gk] = (uint8_t)bt;
     }
-    if (kSmooth) S.template point<kFast>(a, valid, g, w0, w1, Y, uv, bt, has_attr);
+    if (kSmooth && kFast) {
+      if (a.sm.geo.on) S.geo_pair(a, v0, w00, w10, v1, w01, w11);
+    }
   }
-  if (kSmooth && kFast) S.finish(a, P);
+
+  if (kLists) {
+    // ---- (4): the slot's boundary points, full warps ----------------------------------------------------------------------
+    // type 1: entries of the frame's boundary list (what the filter passes read)
+    uint4* blist = reinterpret_cast<uint4*>(a.sm.blist + (uint64_t)frame * a.sm.blist_cap) + S.lbase;
+#pragma unroll 1
+    for (uint32_t i = lane; i - lane < n_type1; i += 32) {
+      if (i < n_type1) {
+        const uint32_t kr = s_list[i];
+        const uint32_t e = s_src[kr + a4];
+        uint32_t w0, w1, Y, c, tz;
+        make_point(e, w0, w1, Y, c, tz);
+        uint4 ent;
+        ent.x = run_base + kr;                       // point index inside the frame
+        ent.y = w0;                                  // pos[0] | pos[1] << 16
+        ent.z = (w1 & 0xFFFFu) | (Y << 16);          // pos[2] | Y << 16
+        ent.w = has_attr ? s_term[e >> 9].w : 0u;    // U | V << 16
+        blist[i] = ent;
+      }
+    }
+    // type 2: K7 statistics
+    if (a.sm.col.on && has_attr) {
+#pragma unroll 1
+      for (uint32_t i = lane; i - lane < n_type2; i += 32) {
+        if (i < n_type2) {
+          const uint32_t kr = s_list[kListEntries - 1u - i];
+          const uint32_t e = s_src[kr + a4];
+          uint32_t w0, w1, Y, c, tz;
+          make_point(e, w0, w1, Y, c, tz);
+          S.colour_point(a, w0, w1, Y, s_term[e >> 9].w);
+        }
+      }
+    }
+    S.finish(a, P);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------------------

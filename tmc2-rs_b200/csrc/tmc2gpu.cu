@@ -8,7 +8,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -117,13 +121,79 @@ struct PinBuf {
 // registry of memory handed out by tmc2gpu_alloc_pinned: planes inside it are DMA'd without staging
 std::mutex g_pin_mu;
 std::vector<std::pair<const uint8_t*, size_t>> g_pinned;
-static bool is_pinned(const void* p, size_t bytes) {
+static std::vector<std::pair<const uint8_t*, size_t>> pinned_snapshot() {
   std::lock_guard<std::mutex> lk(g_pin_mu);
+  return g_pinned;
+}
+static bool is_pinned(const std::vector<std::pair<const uint8_t*, size_t>>& reg, const void* p, size_t bytes) {
   const uint8_t* q = static_cast<const uint8_t*>(p);
-  for (auto& r : g_pinned)
+  for (auto& r : reg)
     if (q >= r.first && q + bytes <= r.first + r.second) return true;
   return false;
 }
+
+// Staging of pageable planes (what an unmodified tmc2-rs host hands over: `Vec<u8>`, src/decoder.rs:1136-1140) into pinned
+// memory runs on a small pool of host threads: one thread moves ~10 GB/s, the PCIe link takes 50+.  TMC2_STAGE_THREADS
+// overrides the pool size (1 = the calling thread only).
+class StagePool {
+ public:
+  // never destroyed: the workers wait on its condition variable for the life of the process (destroying a condition
+  // variable with waiters at exit would block)
+  static StagePool& get() { static StagePool* p = new StagePool(); return *p; }
+  unsigned threads() const { return n_; }
+  // fn(i) for i in [0, items); returns when all are done.  The calling thread takes part.
+  void run(size_t items, const std::function<void(size_t)>& fn) {
+    if (items == 0) return;
+    if (n_ <= 1 || items == 1) { for (size_t i = 0; i < items; ++i) fn(i); return; }
+    std::unique_lock<std::mutex> lk(mu_);
+    fn_ = &fn; items_ = items; next_.store(0); left_ = items; finished_ = 0; ++epoch_;
+    cv_.notify_all();
+    lk.unlock();
+    work();
+    lk.lock();
+    // every worker has passed through this job (none is still inside work() when the next job is set up)
+    done_.wait(lk, [&] { return left_ == 0 && finished_ == n_ - 1; });
+    fn_ = nullptr;
+  }
+ private:
+  StagePool() {
+    unsigned n = std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (const char* e = getenv("TMC2_STAGE_THREADS")) n = (unsigned)std::max(1, atoi(e));
+    n_ = n;
+    for (unsigned i = 1; i < n_; ++i) std::thread([this] { loop(); }).detach();
+  }
+  void work() {
+    for (;;) {
+      const size_t i = next_.fetch_add(1);
+      if (i >= items_) break;
+      (*fn_)(i);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--left_ == 0) done_.notify_all();
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return epoch_ != seen; });
+        seen = epoch_;
+      }
+      work();
+      std::lock_guard<std::mutex> lk(mu_);
+      ++finished_;
+      done_.notify_all();
+    }
+  }
+  unsigned n_ = 1;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(size_t)>* fn_ = nullptr;
+  size_t items_ = 0, left_ = 0;
+  unsigned finished_ = 0;
+  std::atomic<size_t> next_{0};
+  uint64_t epoch_ = 0;
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // validation: everything the reference asserts / unwraps / leaves unimplemented on this path
@@ -160,6 +230,10 @@ static tmc2_status validate_params(const tmc2_gof* g, Err& err) {
   if (P.map_count_minus1 != 1) FAIL(TMC2_ERR_MAP_COUNT, "map_count must be 2 (codec.rs:415-432)");
   if (P.attribute_count > 1) FAIL(TMC2_ERR_UNSUPPORTED, "attribute_count > 1 (decoder.rs:133)");
   if (P.orientation_mode > 1) FAIL(TMC2_ERR_INVALID_ARG, "orientation_mode");
+  // 4:2:0 chroma planes hold (W/2) x (H/2) samples (decoder.rs:976-977 indexes them with w/2 and v/2): with an odd width or
+  // height the last pixel row / column would read past them
+  if (P.attribute_count && ((g->width | g->height) & 1u))
+    FAIL(TMC2_ERR_INVALID_ARG, "odd frame width / height with 4:2:0 attributes (decoder.rs:976-977)");
   // Image::get asserts (decoder.rs:974): the upsample touches every pixel of the tile
   if ((g->width - 1) / P.occupancy_precision >= g->occ_width || (g->height - 1) / P.occupancy_precision >= g->occ_height)
     FAIL(TMC2_ERR_INVALID_ARG, "occupancy video smaller than frame / precision (decoder.rs:974 assert)");
@@ -207,6 +281,12 @@ static tmc2_status validate_frame(const tmc2_gof* g, uint32_t f, Err& err) {
     if (p.patch_orientation > 8) FAIL(TMC2_ERR_INVALID_ARG, "frame %u patch %u: orientation %u", f, i, p.patch_orientation);
     if (p.normal_axis > 2 || p.tangent_axis > 2 || p.bitangent_axis > 2 || p.projection_mode > 1)
       FAIL(TMC2_ERR_INVALID_ARG, "frame %u patch %u: axes / projection mode out of range", f, i);
+    // set_axis (decoder.rs:788-821) only ever produces a permutation of (0, 1, 2).  With coinciding axes the reference's
+    // duplicate test (codec.rs:425 compares the final points, after a later axis store has overwritten an earlier one) and
+    // its differential D1 (codec.rs:551-558 moves point[normal] after all three stores) act on the overwritten coordinate;
+    // the kernels compare / move the normal coordinate itself, so such patches are refused instead of silently differing
+    if (p.normal_axis == p.tangent_axis || p.normal_axis == p.bitangent_axis || p.tangent_axis == p.bitangent_axis)
+      FAIL(TMC2_ERR_UNSUPPORTED, "frame %u patch %u: normal / tangent / bitangent axes are not a permutation (decoder.rs:788-821)", f, i);
     if (p.axis_of_additional_plane != 0)
       FAIL(TMC2_ERR_UNSUPPORTED, "frame %u patch %u: axis_of_additional_plane (codec.rs:437)", f, i);
     if (p.size_u0 == 0 || p.size_v0 == 0) continue;
@@ -288,6 +368,7 @@ struct Batch {
   uint32_t frames_released = 0;
   bool busy = false;
   std::chrono::steady_clock::time_point t_submit;   // TMC2_TRACE bookkeeping
+  uint64_t t_epoch = 0;                             // submit call that made this batch busy
   double trace_wait_ms = 0;
 
   ~Batch() { destroy(); }
@@ -363,6 +444,7 @@ struct Batch {
         d.u1 = p.u1; d.v1 = p.v1; d.d1 = p.d1; d.lod_x = p.lod_x; d.lod_y = p.lod_y;
         d.normal = p.normal_axis; d.tangent = p.tangent_axis; d.bitangent = p.bitangent_axis; d.mode = p.projection_mode;
         d.orient = p.patch_orientation;
+        d.sel = position_selectors(p.normal_axis, p.tangent_axis, p.bitangent_axis);
         {
           // block-aligned affine form of decoder.rs:853-867: canvas step per +1 in patch u (ax, ay) and per +1 in v (rx, ry)
           static const int8_t kAx[9] = {1, 0, 0, -1, 0, -1, 0, 1, 0}, kAy[9] = {0, 1, 1, 0, -1, 0, -1, 0, 1};
@@ -511,9 +593,18 @@ struct Batch {
   }
 
   // ---- H2D: planes (through pinned staging unless the caller's memory is already pinned) + metadata -------------
-  tmc2_status copy_plane_set(const tmc2_gof* g, uint32_t first, int kind, Err& err, size_t& stage_off) {
-    // kind: 0 occ, 1 geo, 2 attr_y, 3 attr_u, 4 attr_v.  One row-pitched copy per (frame, map), merged when the source
-    // planes are contiguous in memory and tight.
+  // One row-pitched copy per (frame, map), merged when neighbouring planes are contiguous on both sides.  Whether a plane is
+  // DMA'd in place or staged is decided ONCE per plane, on its full extent, and the staging area is sized from exactly
+  // those decisions.
+  struct Seg {
+    const uint8_t* src; size_t spitch; uint8_t* dst; uint32_t rows;
+    size_t row_bytes, dpb, plane_dev;      // bytes per row, device pitch in bytes, bytes of the plane on the device
+    bool staged; size_t stage_off;
+    int kind;                              // runs are only merged inside one device allocation (= one plane kind)
+  };
+  void plan_plane_set(const tmc2_gof* g, uint32_t first, int kind, const std::vector<std::pair<const uint8_t*, size_t>>& reg,
+                      std::vector<Seg>& segs, size_t& stage_bytes) const {
+    // kind: 0 occ, 1 geo, 2 attr_y, 3 attr_u, 4 attr_v
     const int maps = kind == 0 ? 1 : 2;
     const uint32_t esz = kind == 0 ? 1 : 2;
     const uint32_t w = kind == 0 ? occ_w : (kind >= 3 ? W / 2 : W);
@@ -521,83 +612,91 @@ struct Batch {
     const uint32_t dpitch = kind == 0 ? occ_pitch : kind == 1 ? geo_pitch : kind == 2 ? attr_pitch_y : attr_pitch_c;
     uint8_t* dbase = kind == 0 ? d_occ.as<uint8_t>() : kind == 1 ? d_geo.as<uint8_t>() : kind == 2 ? d_ay.as<uint8_t>()
                    : kind == 3 ? d_au.as<uint8_t>() : d_av.as<uint8_t>();
-    if (w == 0 || h == 0) return TMC2_OK;
+    if (w == 0 || h == 0) return;
     const size_t plane_dev = (size_t)h * dpitch * esz;
-    struct Seg { const uint8_t* src; size_t spitch; uint8_t* dst; uint32_t rows; };
-    std::vector<Seg> segs;
     for (uint32_t k = 0; k < F; ++k) {
       const tmc2_frame& fr = g->frames[first + k];
       for (int m = 0; m < maps; ++m) {
         const void* src = kind == 0 ? (const void*)fr.occ : kind == 1 ? (const void*)fr.geo[m]
                         : kind == 2 ? (const void*)fr.attr_y[m] : kind == 3 ? (const void*)fr.attr_u[m] : (const void*)fr.attr_v[m];
         const uint32_t sstride = kind == 0 ? fr.occ_stride : kind == 1 ? fr.geo_stride : kind == 2 ? fr.attr_stride_y : fr.attr_stride_c;
-        segs.push_back({(const uint8_t*)src, (size_t)sstride * esz, dbase + ((size_t)k * maps + m) * plane_dev, h});
+        Seg s{(const uint8_t*)src, (size_t)sstride * esz, dbase + ((size_t)k * maps + m) * plane_dev, h,
+              (size_t)w * esz, (size_t)dpitch * esz, plane_dev, false, 0, kind};
+        const size_t src_bytes = (size_t)(s.rows - 1) * s.spitch + s.row_bytes;
+        s.staged = !is_pinned(reg, s.src, src_bytes);
+        if (s.staged) { s.stage_off = stage_bytes; stage_bytes += plane_dev; }
+        segs.push_back(s);
       }
     }
-    const size_t row_bytes = (size_t)w * esz;
-    const size_t dpb = (size_t)dpitch * esz;
+  }
+
+  tmc2_status upload(const tmc2_gof* g, uint32_t first, Err& err) {
+    CU(cudaSetDevice(device));
+    const bool attr = params.attribute_count != 0;
+    std::vector<Seg> segs;
+    size_t stage_bytes = 0;
+    {
+      const auto reg = pinned_snapshot();
+      for (int kind = 0; kind < (attr ? 5 : 2); ++kind) plan_plane_set(g, first, kind, reg, segs, stage_bytes);
+    }
+    // the previous GOF of this batch must have finished its H2D copies before its staging area (planes and metadata) is
+    // written again
+    CU(cudaEventSynchronize(ev_inputs_free));
+    if (stage_bytes) CU(h_in.ensure(stage_bytes));
     // current run of planes that are contiguous on both sides -> one cudaMemcpyAsync
-    const uint8_t* run_src = nullptr; uint8_t* run_dst = nullptr; size_t run_bytes = 0;
+    const uint8_t* run_src = nullptr; uint8_t* run_dst = nullptr; size_t run_bytes = 0; int run_kind = -1;
     auto flush = [&]() -> cudaError_t {
       cudaError_t e = cudaSuccess;
       if (run_bytes) e = cudaMemcpyAsync(run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, stream);
       run_bytes = 0;
       return e;
     };
-    for (const Seg& s : segs) {
-      const size_t src_bytes = (size_t)(s.rows - 1) * s.spitch + row_bytes;
-      const uint8_t* src = s.src;
-      size_t spitch = s.spitch;
-      if (!is_pinned(s.src, src_bytes)) {
-        // stage: repack into pinned memory with the device pitch
-        uint8_t* st = h_in.as<uint8_t>() + stage_off;
-        if (spitch == dpb && row_bytes == dpb) memcpy(st, s.src, plane_dev);
-        else for (uint32_t r = 0; r < s.rows; ++r) memcpy(st + (size_t)r * dpb, s.src + (size_t)r * s.spitch, row_bytes);
-        stage_off += plane_dev;
-        src = st; spitch = dpb;
-      }
-      if (spitch == dpb) {
-        if (run_bytes && src == run_src + run_bytes && s.dst == run_dst + run_bytes) {
-          run_bytes += plane_dev;
+    auto enqueue = [&](const Seg& s) -> tmc2_status {
+      const uint8_t* src = s.staged ? h_in.as<uint8_t>() + s.stage_off : s.src;
+      const size_t spitch = s.staged ? s.dpb : s.spitch;
+      // in-place planes: the last row of a plane may be shorter than the pitch in the SOURCE allocation -- never read past it
+      if (spitch == s.dpb && (s.staged || s.row_bytes == s.dpb)) {
+        if (run_bytes && s.kind == run_kind && src == run_src + run_bytes && s.dst == run_dst + run_bytes) {
+          run_bytes += s.plane_dev;
         } else {
           CU(flush());
-          run_src = src; run_dst = s.dst; run_bytes = plane_dev;
+          run_src = src; run_dst = s.dst; run_bytes = s.plane_dev; run_kind = s.kind;
         }
-        // the last row of a plane may be shorter than the pitch in the SOURCE allocation: never read past it
-        if (row_bytes != dpb && src == s.src) { run_bytes -= plane_dev; CU(flush());
-          CU(cudaMemcpy2DAsync(s.dst, dpb, src, spitch, row_bytes, s.rows, cudaMemcpyHostToDevice, stream)); }
       } else {
         CU(flush());
-        CU(cudaMemcpy2DAsync(s.dst, dpb, src, spitch, row_bytes, s.rows, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpy2DAsync(s.dst, s.dpb, src, spitch, s.row_bytes, s.rows, cudaMemcpyHostToDevice, stream));
       }
+      return TMC2_OK;
+    };
+    // Staged planes go in groups of ~1/8 of the staging area: the pool repacks a group (row ranges in parallel) into pinned
+    // memory with the device pitch, its copies are enqueued, and the DMA of group i runs under the repacking of group i+1.
+    const size_t group_bytes = std::max<size_t>(stage_bytes / 8, 4u << 20);
+    size_t i = 0;
+    while (i < segs.size()) {
+      size_t j = i, bytes = 0;
+      while (j < segs.size() && (j == i || bytes < group_bytes)) { if (segs[j].staged) bytes += segs[j].plane_dev; ++j; }
+      if (bytes) {
+        struct Item { const Seg* s; uint32_t r0, r1; };
+        std::vector<Item> items;
+        for (size_t k = i; k < j; ++k) {
+          if (!segs[k].staged) continue;
+          const uint32_t rows_per = std::max<uint32_t>(1, (uint32_t)((1u << 20) / std::max<size_t>(segs[k].dpb, 1)));   // ~1 MB pieces
+          for (uint32_t r = 0; r < segs[k].rows; r += rows_per) items.push_back({&segs[k], r, std::min(segs[k].rows, r + rows_per)});
+        }
+        uint8_t* base = h_in.as<uint8_t>();
+        StagePool::get().run(items.size(), [&](size_t n) {
+          const Item& it = items[n];
+          const Seg& sg = *it.s;
+          uint8_t* st = base + sg.stage_off;
+          if (sg.spitch == sg.dpb && sg.row_bytes == sg.dpb) memcpy(st + (size_t)it.r0 * sg.dpb, sg.src + (size_t)it.r0 * sg.spitch, (size_t)(it.r1 - it.r0) * sg.dpb);
+          else for (uint32_t r = it.r0; r < it.r1; ++r) memcpy(st + (size_t)r * sg.dpb, sg.src + (size_t)r * sg.spitch, sg.row_bytes);
+        });
+      }
+      for (size_t k = i; k < j; ++k) { tmc2_status st = enqueue(segs[k]); if (st) return st; }
+      i = j;
     }
     CU(flush());
-    return TMC2_OK;
-  }
-
-  tmc2_status upload(const tmc2_gof* g, uint32_t first, Err& err) {
-    CU(cudaSetDevice(device));
-    const bool attr = params.attribute_count != 0;
-    // worst-case staging need (nothing pinned)
-    size_t need = (size_t)F * occ_h * occ_pitch + (size_t)F * 2 * H * geo_pitch * 2;
-    if (attr) need += (size_t)F * 2 * H * attr_pitch_y * 2 + 2 * (size_t)F * 2 * std::max(Hc, 1u) * attr_pitch_c * 2;
-    bool any_unpinned = false;
-    for (uint32_t k = 0; k < F && !any_unpinned; ++k) {
-      const tmc2_frame& fr = g->frames[first + k];
-      any_unpinned |= !is_pinned(fr.geo[0], 2) || !is_pinned(fr.occ, 1) || (attr && !is_pinned(fr.attr_y[0], 2));
-    }
-    if (any_unpinned) {
-      // the previous batch using this staging area must have finished its H2D copies
-      CU(cudaEventSynchronize(ev_inputs_free));
-      CU(h_in.ensure(need));
-    }
-    size_t off = 0;
-    for (int kind = 0; kind < (attr ? 5 : 2); ++kind) {
-      tmc2_status s = copy_plane_set(g, first, kind, err, off);
-      if (s) return s;
-    }
     // metadata
-    CU(cudaEventSynchronize(ev_inputs_free));
     uint8_t* m = h_meta.as<uint8_t>();
     if (!h_patches.empty()) memcpy(m + meta_patch_off, h_patches.data(), h_patches.size() * sizeof(DevPatch));
     if (n_slots) memcpy(m + meta_slot_off, h_slot_rec.data(), (size_t)n_slots * sizeof(SlotRec));
@@ -673,6 +772,7 @@ struct Batch {
       grid(a.sm.col, smoothing_col, params.cgrid_size, d_coltab.p, d_colkeys.as<uint32_t>(), coltab_slots, coltab_hashed,
            d_colmbits.as<uint32_t>(), d_coltbits.as<uint32_t>());
       a.sm.blist = d_blist.as<BoundaryEntry>(); a.sm.blist_count = d_blist_count.as<uint32_t>(); a.sm.blist_cap = blist_cap;
+      if (const char* e = getenv("TMC2_TEST_BLIST_CAP")) a.sm.blist_cap = std::min<uint64_t>(blist_cap, strtoull(e, nullptr, 10));   // test hook: provoke the device-side capacity failure
       a.sm.slist = d_slist.as<uint32_t>(); a.sm.slist_count = d_slist_count.as<uint32_t>();
       const uint32_t sc = params.attribute_bitdepth > 8 ? (1u << (params.attribute_bitdepth - 8)) : 1u;
       a.sm.thr_geo = params.threshold_smoothing;
@@ -894,6 +994,7 @@ struct tmc2gpu_ctx {
   std::unique_ptr<Batch> stage_batch;                        // single-frame stage API
   std::deque<PendingFrame> pending;
   uint64_t next_global = 0;
+  uint64_t submit_epoch = 0;
   Err err;
   std::string last_error;
   Batch* last_batch = nullptr;                               // for launch info / stage times
@@ -1035,23 +1136,55 @@ tmc2_status tmc2gpu_submit_gof(tmc2gpu_ctx* ctx, const tmc2_gof* gof) {
     size_t k = 0;
     for (auto& pc : pieces) if (pc.d == d) pc.b = free_list[k++];
   }
+  // A failure part-way through leaves no trace: pieces already enqueued are drained and freed, and none of the GOF's frames
+  // stays in the hand-out queue (a GOF is delivered whole or not at all).
+  const size_t pending_mark = ctx->pending.size();
+  const uint64_t global_mark = ctx->next_global;
+  auto undo = [&]() {
+    for (auto& pc : pieces) {
+      if (!pc.b) continue;
+      cudaSetDevice(pc.b->device);
+      cudaStreamSynchronize(pc.b->stream);           // also the piece that failed: it may have enqueued some copies
+      cudaGetLastError();
+      if (pc.b->busy && pc.b->t_epoch == ctx->submit_epoch) pc.b->busy = false;
+    }
+    ctx->pending.resize(pending_mark);
+    ctx->next_global = global_mark;
+  };
+  ++ctx->submit_epoch;
   for (auto& pc : pieces) {
     Batch* b = pc.b;
     const double t_val = tc.lap();
-    if (b->prepare(gof, pc.lo, pc.hi - pc.lo, 0, err)) return ctx->fail();
+    if (b->prepare(gof, pc.lo, pc.hi - pc.lo, 0, err)) { undo(); return ctx->fail(); }
     const double t_prep = tc.lap();
-    if (b->upload(gof, pc.lo, err)) return ctx->fail();
+    if (b->upload(gof, pc.lo, err)) { undo(); return ctx->fail(); }
     const double t_up = tc.lap();
-    if (b->launch(b->stream, err)) return ctx->fail();
+    if (b->launch(b->stream, err)) { undo(); return ctx->fail(); }
     if (trace_on())
       fprintf(stderr, "[tmc2gpu] submit dev %d frames %u..%u: validate %.3f prepare %.3f upload-enqueue %.3f launch-enqueue %.3f ms\n",
               b->device, pc.lo, pc.hi, t_val, t_prep, t_up, tc.lap());
     // counts travel right behind the kernels; result copies are enqueued when the first frame is asked for
-    b->busy = true; b->frames_released = 0;
+    b->busy = true; b->frames_released = 0; b->t_epoch = ctx->submit_epoch;
     b->t_submit = std::chrono::steady_clock::now(); b->trace_wait_ms = 0;
     ctx->last_batch = b;
     for (uint32_t k = 0; k < pc.hi - pc.lo; ++k) ctx->pending.push_back({b, k, ctx->next_global++});
   }
+  return TMC2_OK;
+}
+
+tmc2_status tmc2gpu_wait_inputs(tmc2gpu_ctx* ctx) {
+  if (!ctx) return TMC2_ERR_INVALID_ARG;
+  Err& err = ctx->err;
+  err = Err();
+  auto body = [&]() -> tmc2_status {
+    for (auto& v : ctx->slots)
+      for (auto& b : v) {
+        CU(cudaSetDevice(b->device));
+        CU(cudaEventSynchronize(b->ev_inputs_free));
+      }
+    return TMC2_OK;
+  };
+  if (body()) return ctx->fail();
   return TMC2_OK;
 }
 
@@ -1063,13 +1196,24 @@ tmc2_status tmc2gpu_next_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out) {
   PendingFrame pf = ctx->pending.front();
   Batch* b = pf.batch;
   TraceClock tc;
+  // A GOF whose launch failed on the device (or whose copies failed) is dropped WHOLE: all of its frames leave the queue, its
+  // slot is drained and freed, and the error is reported once -- a later call never hands out frames of the failed launch.
+  auto drop_gof = [&]() {
+    while (!ctx->pending.empty() && ctx->pending.front().batch == b) ctx->pending.pop_front();
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    cudaStreamSynchronize(b->d2h_stream);
+    cudaGetLastError();
+    b->busy = false; b->counts_ready = false; b->outputs_enqueued = false;
+  };
   const bool first = !b->counts_ready;
-  if (!b->counts_ready && b->fetch_counts(b->stream, err)) return ctx->fail();
+  if (!b->counts_ready && b->fetch_counts(b->stream, err)) { drop_gof(); return ctx->fail(); }
   const double t_counts = tc.lap();
-  if (!b->outputs_enqueued && b->enqueue_outputs(err)) return ctx->fail();
+  if (!b->outputs_enqueued && b->enqueue_outputs(err)) { drop_gof(); return ctx->fail(); }
   const double t_enq = tc.lap();
   if (cudaSetDevice(b->device) != cudaSuccess || cudaEventSynchronize(b->ev_frame[pf.local]) != cudaSuccess) {
     err.st = TMC2_ERR_CUDA; err.msg = std::string("waiting for frame: ") + cudaGetErrorString(cudaGetLastError());
+    drop_gof();
     return ctx->fail();
   }
   if (trace_on()) {
