@@ -192,22 +192,52 @@ struct UnpackArgs {
   SmoothArgs sm;                      // used by the smoothing instantiation only
 };
 
-// shared memory of one warp of emit_kernel: per-pixel tables of the block in PATCH raster order (rank = v1*16 + u1)
-constexpr uint32_t kOffPt = 0;                                   // [16 rows][17][2] u32: n | Y << 16 of map 0 / map 1
-constexpr uint32_t kOffTerm = kOffPt + 2176;                     // [64][2] uint4: chroma term of (chroma sample, map)
-constexpr uint32_t kOffSrc = kOffTerm + 2048;                    // [3 + 512 (+ slack)] u16: output point -> rank << 1 | map | term << 9,
-                                                                 // entry i = point i - (run_base & 3) of the run (the run starts
-                                                                 // at the same phase of a 4-point group as in the frame)
-constexpr uint32_t kSrcBytes = 1040;
-constexpr uint32_t kOffCnt = kOffSrc + kSrcBytes;                // [256] u8: points of the pixel (0..2) | boundary class << 2
-constexpr uint32_t kOffBmp = kOffCnt + 256;                      // [32] u32: 20x20 occupancy bitmap rows (canvas axes)
-constexpr uint32_t kOffMemo = kOffBmp + 128;                     // [2][32] u32: cells the slot has already claimed (smoothing only)
+// Shared memory of one warp of emit_kernel (one warp = one slot; warps never talk to each other).
+//   RAW area: the plane tiles of the canvas block, written by the TMA unit (cp.async.bulk.tensor, 128-byte aligned boxes,
+//   completion on the warp's mbarrier).  It is dead once the tables below have been built; the smoothing instantiations
+//   then reuse it for their per-slot state.
+constexpr uint32_t kOffRawGeo = 0;                               // [2 maps][16 rows][16] u16  geometry samples of the canvas block
+constexpr uint32_t kOffRawY = kOffRawGeo + 1024;                 // [2][16][16] u16            attribute luma
+constexpr uint32_t kOffRawU = kOffRawY + 1024;                   // [2][8][8] u16              4:2:0 chroma
+constexpr uint32_t kOffRawV = kOffRawU + 256;
+constexpr uint32_t kOffRawOcc = kOffRawV + 256;                  // [8 rows][32] u8: occupancy samples from (ox, by*4-2), ox = (bx*4-1) rounded
+                                                                 // down to a multiple of 16 (the TMA unit wants the first byte of a box
+                                                                 // row 16-byte aligned): the block's 4x4 samples plus the ring around
+                                                                 // them that the boundary classes look at
+constexpr uint32_t kRawBytes = kOffRawOcc + 256;
+//   ... reused after the tables are built (smoothing only):
+constexpr uint32_t kOffMemo = 0;                                 // [2][32] u32: cells the slot has already claimed
 constexpr uint32_t kOffTab = kOffMemo + 256;                     // [128] uint2: the slot's geometry-cell table (fast smoothing grids)
 constexpr uint32_t kOffList = kOffTab + 1024;                    // [520] u16 (fast smoothing grids): run-relative indices of the slot's
                                                                  // type-1 boundary points from the front, type-2 from the back
 constexpr uint32_t kListEntries = 520;
-constexpr uint32_t kWarpSmemBytes = kOffList + 2 * kListEntries;
-static_assert(kOffTerm % 16 == 0 && kOffSrc % 16 == 0 && kOffCnt % 16 == 0 && kOffTab % 16 == 0 && kWarpSmemBytes % 16 == 0, "alignment");
+static_assert(kOffList + 2 * kListEntries <= kRawBytes, "the smoothing state fits the RAW area");
+//   per-pixel tables of the block in PATCH raster order (rank = v1*16 + u1):
+constexpr uint32_t kOffPt = kRawBytes;                           // [16 rows][17][2] u32: n | Y << 16 of map 0 / map 1 (17th pair of a row: padding)
+constexpr uint32_t kOffBar = kOffPt + 2176 - 8;                  // the warp's mbarrier sits in the padding pair of the last table row
+constexpr uint32_t kOffTerm = kOffPt + 2176;                     // [64][2] uint4: chroma term of (chroma sample, map)
+constexpr uint32_t kSrcBytes = 1040;                             // [3 + 512 (+ slack)] u16: output point -> rank << 1 | map | term << 9,
+                                                                 // entry i = point i - (run_base & 3) of the run (the run starts
+                                                                 // at the same phase of a 4-point group as in the frame).  Without
+                                                                 // smoothing the list lives in the (dead) RAW area.
+constexpr uint32_t kOffSrcSmooth = kOffTerm + 2048;
+constexpr uint32_t kOffSrcPlain = 0;
+constexpr uint32_t kOffCntSmooth = kOffSrcSmooth + kSrcBytes;    // [256] u8: points of the pixel (0..2) | boundary class << 2
+constexpr uint32_t kOffCntPlain = kOffSrcPlain + kSrcBytes;      // (RAW area, geometry / luma part: read into registers before anything is stored)
+constexpr uint32_t kBmpBytes = 128;                              // after the counts (smoothing / debug layout): [32] u32: 20x20 occupancy bitmap
+                                                                 // rows (canvas axes); later the list of non-empty cell-table entries
+constexpr uint32_t kWarpSmemSmooth = (kOffCntSmooth + 256 + kBmpBytes + 127) / 128 * 128;
+constexpr uint32_t kWarpSmemPlain = (kOffTerm + 2048 + 127) / 128 * 128;
+static_assert(kOffCntPlain + 256 <= kOffRawU, "plain layout: list and counts overwrite only the geometry / luma tiles");
+static_assert(kOffPt % 16 == 0 && kOffTerm % 16 == 0 && kOffSrcSmooth % 16 == 0 && kOffCntSmooth % 16 == 0 && kOffCntPlain % 16 == 0 && kOffTab % 16 == 0, "alignment");
+#ifndef TMC2_EMIT_WARPS
+#define TMC2_EMIT_WARPS 4
+#endif
+constexpr int kEmitWarps = TMC2_EMIT_WARPS;                      // warps per CTA of emit_kernel
+
+// TMA descriptors (CUtensorMap, 128 B each) of the five plane arrays of a batch; tiled, no swizzle, u16 / u8 elements:
+//   geo, attr_y: (x, y, map, frame) box 16 x 16 x 2 x 1      attr_u, attr_v: box 8 x 8 x 2 x 1      occ: (x, y, frame) box 32 x 8 x 1
+struct alignas(64) TileMaps { unsigned long long geo[16], attr_y[16], attr_u[16], attr_v[16], occ[16]; };
 
 // launch wrappers (kernels.cu); every one enqueues on `stream` and returns the cudaGetLastError() code
 int launch_block_to_patch(const UnpackArgs& a, uint32_t n_slots, void* stream);
@@ -216,7 +246,7 @@ int launch_compact_owned(const UnpackArgs& a, void* stream);   // after block_to
 // smooth: the emit also accumulates the cell tables and writes the boundary lists of the current frame group.
 int launch_count(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, void* stream);
 int launch_slot_scan(const UnpackArgs& a, void* stream);
-int launch_emit(const UnpackArgs& a, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream);
+int launch_emit(const UnpackArgs& a, const TileMaps& tm, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream);
 int launch_upsample(const UnpackArgs& a, uint8_t* occ_full /*[F][H][W]*/, void* stream);
 int launch_smooth_filter(const UnpackArgs& a, void* stream);   // boundary points of the current frame group
 int launch_smooth_clear(const UnpackArgs& a, void* stream);    // reset touched cells (+ keys) of the group

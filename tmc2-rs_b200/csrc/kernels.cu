@@ -24,6 +24,7 @@
 // __ddiv_rn, every operation rounded on its own like rustc's code) whenever the fixed-point value is within that margin
 // of an integer boundary, so the result is bit-exact for every u16 input.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -156,6 +157,25 @@ __device__ __forceinline__ ChromaTerm chroma_term(uint32_t U, uint32_t V) {
   c.ir = chroma_floor(255LL * kKr * dv, 128u * adv + 256u, c.flagged);
   c.ig = chroma_floor(-(255LL * kKgu) * du - (255LL * kKgv) * dv, 128u * (adu + adv) + 256u, c.flagged);
   c.ib = chroma_floor(255LL * kKb * du, 128u * adu + 256u, c.flagged);
+  return c;
+}
+// The same three integers for 10-bit chroma from 32-bit arithmetic: 255*k = Cint + Cfrac, Cfrac rounded to 21 fractional bits
+// (error <= 2^-22 per unit of d, so <= 2^-13 over |d| <= 512; the green channel adds two such terms).  The result is exact
+// unless the fraction lands within that error (plus a margin) of 0 or 1 -- about 5 chroma pairs in 10 000, and always for a
+// neutral component (d == 0) -- or the sample is not a 10-bit value; then `flagged` is set and the caller takes chroma_term().
+// Verified exhaustively over all 2^20 (U, V) pairs against exact rational arithmetic.
+__device__ __forceinline__ ChromaTerm chroma_term_fast(uint32_t U, uint32_t V) {
+  const uint32_t du = U - 512u, dv = V - 512u;                              // two's complement
+  constexpr uint32_t M = (1u << 21) - 1u;
+  const int32_t sr = (int32_t)(1203765u * dv), sb = (int32_t)(389336u * du);
+  const int32_t sg = (int32_t)(0u - 1613024u * du - 782552u * dv);
+  ChromaTerm c;
+  c.ir = (int32_t)(401u * dv) + (sr >> 21);
+  c.ib = (int32_t)(473u * du) + (sb >> 21);
+  c.ig = (int32_t)(0u - 47u * du - 119u * dv) + (sg >> 21);
+  const bool near = ((((uint32_t)sr & M) + 264u) & M) < 528u || ((((uint32_t)sb & M) + 264u) & M) < 528u ||
+                    ((((uint32_t)sg & M) + 520u) & M) < 1040u;
+  c.flagged = (near || (U | V) > 1023u) ? 1u : 0u;
   return c;
 }
 // clamp(floor(m / 1023), 0, 255): clamp m to [0, 255*1023 + 1022] first, then floor(m / 1023) == umulhi(m, ceil(2^32/1023))
@@ -464,17 +484,12 @@ struct CanvasBlock {
   uint32_t m1, m2;           // bit j set = pixel j of this lane emits >= 1 / 2 points
 };
 
-// geometry + occupancy of the lane's 8 pixels -> normals and the two emission masks
-__device__ __forceinline__ void load_geometry(const UnpackArgs& a, const WorkRec& R, const DevPatch& P, uint32_t lane,
-                                              CanvasBlock& L) {
+// occupancy of the lane's 8 pixels straight from the low-resolution video: bit j set = pixel j is occupied
+__device__ __forceinline__ uint32_t occupancy_mask(const UnpackArgs& a, const WorkRec& R, uint32_t lane) {
   const uint32_t h = lane & 1u, r = lane >> 1;
   const uint32_t x0 = (uint32_t)R.bx * 16u + 8u * h, y = (uint32_t)R.by * 16u + r;
-  const uint16_t* geo0 = a.in.geo + (uint64_t)R.frame * 2 * a.in.geo_map_stride;
-  const uint32_t goff = y * a.in.geo_pitch + x0;
-  const uint4 g0 = ldg_nc_v4(geo0 + goff);
-  const uint4 g1 = ldg_nc_v4(geo0 + a.in.geo_map_stride + goff);
   // occupancy of the 8 pixels (codec.rs:393-396: any non-zero sample counts).  Pixels j*p .. j*p+p-1 share a sample.
-  uint32_t m1 = 0, m2 = 0;
+  uint32_t m1 = 0;
   {
     const uint8_t* occ_f = a.in.occ + (uint64_t)R.frame * a.in.occ_frame_stride;
     const int32_t lp = a.prec_shift;
@@ -491,6 +506,13 @@ __device__ __forceinline__ void load_geometry(const UnpackArgs& a, const WorkRec
       }
     }
   }
+  return m1;
+}
+
+// the lane's 8 pixels: geometry samples of both maps + occupancy mask -> normals and the two emission masks
+__device__ __forceinline__ void geometry_digest(const UnpackArgs& a, const DevPatch& P, const uint4& g0, const uint4& g1, uint32_t m1,
+                                                CanvasBlock& L) {
+  uint32_t m2 = 0;
   if (P.d1 <= 0xFFFFu) {
     // codec.rs:534-558 + decoder.rs:881-888 on two pixels per instruction (16-bit lanes: VIADD.16x2 / VIMNMX.U16x2 wrap and
     // compare per half, exactly the reference's `as u16`).  depth = sample / 4 <= 16383.
@@ -522,6 +544,19 @@ __device__ __forceinline__ void load_geometry(const UnpackArgs& a, const WorkRec
     if (diff >> 16) m2 |= 2u << (2 * q);
   }
   L.m1 = m1; L.m2 = m2 & m1;
+}
+
+
+// geometry + occupancy of the lane's 8 pixels with ordinary loads (the count pass)
+__device__ __forceinline__ void load_geometry(const UnpackArgs& a, const WorkRec& R, const DevPatch& P, uint32_t lane,
+                                              CanvasBlock& L) {
+  const uint32_t h = lane & 1u, r = lane >> 1;
+  const uint32_t x0 = (uint32_t)R.bx * 16u + 8u * h, y = (uint32_t)R.by * 16u + r;
+  const uint16_t* geo0 = a.in.geo + (uint64_t)R.frame * 2 * a.in.geo_map_stride;
+  const uint32_t goff = y * a.in.geo_pitch + x0;
+  const uint4 g0 = ldg_nc_v4(geo0 + goff);
+  const uint4 g1 = ldg_nc_v4(geo0 + a.in.geo_map_stride + goff);
+  geometry_digest(a, P, g0, g1, occupancy_mask(a, R, lane), L);
 }
 
 // points of a generic slot (any resolution / precision, reference-literal rotated orientations): lane = pixel
@@ -811,30 +846,6 @@ __device__ __forceinline__ void boundary_masks(const UnpackArgs& a, const WorkRe
 __device__ __forceinline__ void stg_u32(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
-// The planes of the block a warp of a LATER tile will work on, into L2: the inputs stream through once (338 MB per GOF
-// against 126 MB of L2), so without this every slot starts with a full DRAM round trip behind its work record.
-template <bool kChroma>
-__device__ __forceinline__ void prefetch_slot_planes(const UnpackArgs& a, uint32_t pid, uint32_t frame, uint32_t bxy, uint32_t lane) {
-  if (pid == kNoPatch) return;
-  const uint32_t h = lane & 1u, r = lane >> 1;
-  const uint32_t x0 = (bxy & 0xFFFFu) * 16u + 8u * h, y = (bxy >> 16) * 16u + r;
-  const uint16_t* geo0 = a.in.geo + (uint64_t)frame * 2 * a.in.geo_map_stride + (uint64_t)y * a.in.geo_pitch + x0;
-  prefetch_l2(geo0);
-  prefetch_l2(geo0 + a.in.geo_map_stride);
-  if (a.has_attr) {
-    const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride + (uint64_t)y * a.in.attr_pitch_y + x0;
-    prefetch_l2(ay0);
-    prefetch_l2(ay0 + a.in.attr_y_map_stride);
-    if (kChroma && !(r & 1u)) {
-      const uint64_t co = (uint64_t)frame * 2 * a.in.attr_c_map_stride + (uint64_t)(y >> 1) * a.in.attr_pitch_c + (x0 >> 1);
-      prefetch_l2(a.in.attr_u + co);
-      prefetch_l2(a.in.attr_v + co);
-      prefetch_l2(a.in.attr_u + co + a.in.attr_c_map_stride);
-      prefetch_l2(a.in.attr_v + co + a.in.attr_c_map_stride);
-    }
-  }
-}
-
 // ---- smoothing work of the emit loop (K6 / K7 statistics + boundary list), one call per 32-point window -----------------
 // The sums are fire-and-forget reductions, so nothing in the loop waits for the memory system.  A slot claims each cell once,
 // and (fast grids) only after its point loop: geometry cells sit in the slot's shared-memory table anyway, colour cells are
@@ -842,6 +853,7 @@ __device__ __forceinline__ void prefetch_slot_planes(const UnpackArgs& a, uint32
 struct SmoothState {
   uint32_t frame, fig, patch, lane, lbase, n_done;
   uint32_t* memo;                // [2][32] cells this warp has already claimed for its slot (direct-mapped, geometry / colour)
+  uint8_t* scratch;              // 128 bytes (the bitmap rows of the boundary pass, free by then)
   GeoCell* geo_tab;              // this frame's tables
   ColCell* col_tab;
   uint32_t pend_cs, pend_old;    // a claim issued in the loop (memo entry taken by another cell); bit 31 of pend_cs: colour grid
@@ -852,9 +864,9 @@ struct SmoothState {
   uint32_t kmin, bad, mul;       // local cell = key - kmin (valid iff no bit of `bad`); entry = (local * mul) >> 24
 
   __device__ __forceinline__ void init(const UnpackArgs& a, uint32_t frame_, uint32_t fig_, uint32_t patch_, uint32_t lane_,
-                                       uint32_t* memo_, bool with_table) {
+                                       uint32_t* memo_, uint8_t* scratch_, bool with_table) {
     frame = frame_; fig = fig_; patch = patch_; lane = lane_; lbase = 0; n_done = 0;
-    memo = memo_;
+    memo = memo_; scratch = scratch_;
     memo[lane] = kCellEmpty; memo[32 + lane] = kCellEmpty;
     tab = memo_ + 64;
     if (with_table) {
@@ -917,29 +929,45 @@ struct SmoothState {
     __syncwarp();
     const GridDesc& G = a.sm.geo;
     const uint32_t sn = 8u * key_byte(P.normal), st = 8u * key_byte(P.tangent), sb = 8u * key_byte(P.bitangent);
-    uint32_t cs[6], old[6];
+    // the non-empty entries of the table (a handful out of 128), compacted: the bitmap rows of the boundary pass are free by now
+    uint8_t* idx8 = scratch;
+    uint32_t n_ne = 0;
+    if (G.on) {
+      const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-    for (uint32_t i = 0; i < 4; ++i) {
-      cs[i] = kCellEmpty; old[i] = 0;
-      if (!G.on) continue;
-      const uint32_t ent = 32u * i + lane;
-      const uint2 e = reinterpret_cast<const uint2*>(tab)[ent];
-      if (e.x == 0u) continue;
-      const uint32_t key = kmin + (((ent & 7u) << sn) | (((ent >> 3) & 3u) << st) | ((ent >> 5) << sb));
-      cs[i] = fast_slot(G, key);
-      GeoCell* c = geo_tab + cs[i];
-      old[i] = atomicCAS(&c->first1, 0u, patch + 1u);
-      atomicAdd(&c->cnt_sx, (unsigned long long)(e.x & 1023u) | ((unsigned long long)(e.x >> 10) << 32));
-      atomicAdd(&c->sy_sz, (unsigned long long)(e.y & 4095u) | ((unsigned long long)(e.y >> 12) << 32));
+      for (uint32_t i = 0; i < 4; ++i) {
+        const uint32_t ent = 32u * i + lane;
+        const bool ne = tab[2u * ent] != 0u;
+        const uint32_t b = __ballot_sync(kFull, ne);
+        if (ne) idx8[n_ne + __popc(b & lt)] = (uint8_t)ent;
+        n_ne += __popc(b);
+      }
+      __syncwarp();
     }
-    cs[4] = G.on ? memo[lane] : kCellEmpty;
-    old[4] = cs[4] != kCellEmpty ? claim_issue(G, fig, cs[4], patch) : 0u;
-    cs[5] = a.sm.col.on ? memo[32u + lane] : kCellEmpty;
-    old[5] = cs[5] != kCellEmpty ? claim_issue(a.sm.col, fig, cs[5], patch) : 0u;
+    // claims of the cells that did not go through the table (memo entries of both grids, the pending one) are issued first,
+    // their answers looked at last
+    const uint32_t cs4 = G.on ? memo[lane] : kCellEmpty;
+    const uint32_t old4 = cs4 != kCellEmpty ? claim_issue(G, fig, cs4, patch) : 0u;
+    const uint32_t cs5 = a.sm.col.on ? memo[32u + lane] : kCellEmpty;
+    const uint32_t old5 = cs5 != kCellEmpty ? claim_issue(a.sm.col, fig, cs5, patch) : 0u;
+#pragma unroll 1
+    for (uint32_t base = 0; base < n_ne; base += 32) {
+      uint32_t cs = kCellEmpty, old = 0;
+      if (base + lane < n_ne) {
+        const uint32_t ent = idx8[base + lane];
+        const uint2 e = reinterpret_cast<const uint2*>(tab)[ent];
+        const uint32_t key = kmin + (((ent & 7u) << sn) | (((ent >> 3) & 3u) << st) | ((ent >> 5) << sb));
+        cs = fast_slot(G, key);
+        GeoCell* c = geo_tab + cs;
+        old = atomicCAS(&c->first1, 0u, patch + 1u);
+        atomicAdd(&c->cnt_sx, (unsigned long long)(e.x & 1023u) | ((unsigned long long)(e.x >> 10) << 32));
+        atomicAdd(&c->sy_sz, (unsigned long long)(e.y & 4095u) | ((unsigned long long)(e.y >> 12) << 32));
+      }
+      if (cs != kCellEmpty) claim_result(G, fig, cs, old, patch);
+    }
     retire_pending(a);
-#pragma unroll
-    for (uint32_t i = 0; i < 6; ++i)
-      if (cs[i] != kCellEmpty) claim_result(i == 5 ? a.sm.col : G, fig, cs[i], old[i], patch);
+    if (cs4 != kCellEmpty) claim_result(G, fig, cs4, old4, patch);
+    if (cs5 != kCellEmpty) claim_result(a.sm.col, fig, cs5, old5, patch);
   }
 
   // ---- fast grids (dense power-of-two grids, geometry cell edge <= 8), used by the instantiation without generic branches ----
@@ -1099,113 +1127,137 @@ struct SmoothState {
 };
 
 // ---- pass 3: emit ------------------------------------------------------------------------------------------------------------
-// Per warp (slot): (1) load the block in canvas layout, (2) spill it into per-pixel tables in shared memory in patch raster
-// order and build the list "output point k <- (pixel rank, map)", (3) POINT-parallel loop over 32-aligned windows of the
-// frame's point index (lane == point index mod 32): position, colour, and in the smoothing instantiation boundary
-// class, cell statistics and the boundary list.  Results go straight to global memory as aligned 32-bit words assembled
-// from neighbouring lanes (two positions = three words, four colours = three words); only the ragged ends of a run
-// use 16-bit / 8-bit stores.
-#ifndef TMC2_MINCTA
-#define TMC2_MINCTA 4
-#endif
-#ifndef TMC2_LATE_ATTR_ALL
-#define TMC2_LATE_ATTR_ALL 0
-#endif
-#ifndef TMC2_LATE_ATTR
-#define TMC2_LATE_ATTR 1
-#endif
-#ifndef TMC2_PREFETCH_TILES_SMOOTH
-#define TMC2_PREFETCH_TILES_SMOOTH 0
-#endif
-#ifndef TMC2_PREFETCH_TILES
-#define TMC2_PREFETCH_TILES 296
-#endif
-#ifndef TMC2_SMOOTH_MINCTA
-#define TMC2_SMOOTH_MINCTA 3
-#endif
-template <bool kSmooth, bool kDebug, bool kFast>
-__global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINCTA : TMC2_MINCTA) emit_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset, uint32_t tile_end) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-  const uint32_t lpos = (blockIdx.x + tile_offset) * kWarpsPerTile + warp;
-  // the slot a warp will meet kPrefetchTiles tiles from now (about one generation of resident CTAs ahead)
-  // (measured: 0.222 -> 0.212 ms without smoothing; no gain for the smoothing instantiation, which is off)
-  constexpr uint32_t kPrefetchTiles = kSmooth ? (uint32_t)TMC2_PREFETCH_TILES_SMOOTH : (uint32_t)TMC2_PREFETCH_TILES;
-  uint4 pf = make_uint4(kNoPatch, 0, 0, 0);
-  uint32_t pf_frame = 0;
-  if (kPrefetchTiles && blockIdx.x + tile_offset + kPrefetchTiles < tile_end) {
-    const uint4* q = reinterpret_cast<const uint4*>(a.work + lpos + kPrefetchTiles * kWarpsPerTile);
-    pf = q[0];
-    pf_frame = reinterpret_cast<const uint32_t*>(q + 1)[0] & 0x7FFFFFFFu;
+// PERSISTENT: a warp walks a strided sequence of the frame group's slots.  Per slot: (1) the plane tiles of the block -- fetched
+// by the TMA unit into the warp's RAW area while the warp was still busy with its previous slot -- are read in canvas layout,
+// (2) spilled into per-pixel tables in shared memory in patch raster order together with the list "output point k <- (pixel
+// rank, map)"; as soon as the RAW area has been read, the tiles of the warp's NEXT slot are requested (work record and patch
+// fields by cp.async, planes by cp.async.bulk.tensor on the warp's mbarrier), so that no global load is ever waited for;
+// (3) POINT-parallel loop, two points per lane, over groups of 64 points aligned to multiples of four in the frame's
+// numbering: position, colour, straight to global memory as aligned 32-bit words (two positions = three words, four
+// colours = three words); only the ragged ends of a run use 16-bit / 8-bit stores; (4) smoothing: cell statistics and
+// the boundary list.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one box of a tiled tensor map -> shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, void* bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               :: "r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, void* bar, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               :: "r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// Can the occupancy samples of a block (and the ring around it that the boundary classes look at) come from the 16 x 8 box
+// of the occupancy tensor map?  (precision 4 and a frame that is whole samples wide and high; anything else reads the
+// occupancy video with ordinary loads)
+__device__ __forceinline__ bool occ_by_tma(const UnpackArgs& a) { return a.prec_shift == 2 && ((a.W | a.H) & 3u) == 0u; }
+
+// K5 for a block-aligned slot whose occupancy ring sits in the RAW area (box origin = sample (occ_box_x(bx), by*4 - 2); samples
+// outside the video arrive as zero from the TMA unit and count as occupied here, like pixels outside the image)
+__device__ __forceinline__ int32_t occ_box_x(uint32_t bx) { return ((int32_t)bx * 4 - 1) & ~15; }
+__device__ __forceinline__ void boundary_masks_raw(const UnpackArgs& a, const WorkRec& R, uint32_t lane, const uint8_t* raw_occ,
+                                                   uint32_t* s_bmp, uint32_t& bt1, uint32_t& bt2) {
+  const int32_t W = (int32_t)a.W, H = (int32_t)a.H;
+  const int32_t h = (int32_t)(lane & 1u), r = (int32_t)(lane >> 1);
+  const int32_t bx16 = (int32_t)R.bx * 16, by16 = (int32_t)R.by * 16;
+  const int32_t cw = W >> 2, ch = H >> 2, cxb = (int32_t)R.bx * 4 - 1, cyb = (int32_t)R.by * 4 - 1;
+  const int32_t col_off = cxb - occ_box_x(R.bx);
+  auto cell = [&](int32_t row, int32_t col) -> bool {
+    const int32_t cx = cxb + col, cy = cyb + row;
+    if (cx < 0 || cy < 0 || cx >= cw || cy >= ch) return true;
+    return raw_occ[(row + 1) * 32 + col + col_off] != 0;
+  };
+  const int32_t i = (int32_t)lane;
+  const uint32_t b0 = __ballot_sync(kFull, i < 30 ? cell(i / 6, i % 6) : false);
+  const uint32_t b1 = __ballot_sync(kFull, i < 6 ? cell(5, i) : false);
+  const uint32_t crow = (lane + 2u) >> 2;
+  const uint32_t m6 = crow < 5u ? (b0 >> (6u * crow)) & 63u : (b1 & 63u);
+  const uint32_t row20 = ((m6 & 1u) ? 0x3u : 0u) | ((m6 & 2u) ? 0x3Cu : 0u) | ((m6 & 4u) ? 0x3C0u : 0u) |
+                         ((m6 & 8u) ? 0x3C00u : 0u) | ((m6 & 16u) ? 0x3C000u : 0u) | ((m6 & 32u) ? 0xC0000u : 0u);
+  if (lane < 20) s_bmp[lane] = row20;
+  __syncwarp();
+  const uint32_t r0 = s_bmp[r], r1 = s_bmp[r + 1], r2 = s_bmp[r + 2], r3 = s_bmp[r + 3], r4 = s_bmp[r + 4];
+  const uint32_t cross = r1 & r3 & (r2 >> 1) & (r2 << 1);    // bit c: the four neighbours of column c are occupied
+  const uint32_t all5 = r0 & r1 & r2 & r3 & r4;
+  const uint32_t full = all5 & (all5 >> 1) & (all5 >> 2) & (all5 << 1) & (all5 << 2);
+  const uint32_t sh = 8u * (uint32_t)h + 2u;
+  uint32_t border = 0;
+  if (R.bx == 0 || R.by == 0 || bx16 + 16 >= W || by16 + 16 >= H) {
+    const int32_t y = by16 + r;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      const int32_t x = bx16 + 8 * h + j;
+      if (x == 0 || y == 0 || x == W - 1 || y == H - 1) border |= 1u << j;
+    }
   }
-  const WorkRec R = load_work(a.work + lpos);
-  const uint32_t total = R.pid == kNoPatch ? 0u : R.total;
-  if (total == 0) return;
-  const uint32_t run_base = R.base, frame = R.frame;
-  if ((uint64_t)run_base + total > a.out.cap) {                   // cannot happen for footprints inside the canvas
-    if (lane == 0) atomicExch(a.err, 7);
-    return;
-  }
+  bt1 = ((~(cross >> sh)) & 0xFFu) | border;
+  bt2 = (~(full >> sh)) & 0xFFu & ~bt1;
+}
+
+#ifndef TMC2_EMIT_CTAS
+#define TMC2_EMIT_CTAS 6
+#endif
+#ifndef TMC2_EMIT_CTAS_SMOOTH
+#define TMC2_EMIT_CTAS_SMOOTH 6
+#endif
+
+// One block-aligned slot.  `release_raw()` is called exactly when the RAW area has been read for the last time.
+// One block-aligned slot whose tiles have landed in the RAW area.
+template <bool kSmooth, bool kDebug, bool kFast, bool kAttr>
+__device__ __forceinline__ void emit_fast_slot(const UnpackArgs& a, const WorkRec& R, const DevPatch& P, uint8_t* wsm, uint32_t lane) {
+  const uint32_t total = R.total, run_base = R.base, frame = R.frame;
   const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
-  if (!slot_is_fast(a, R)) {
-    generic_slot_emit<kSmooth, kDebug>(a, R.pid, frame, fig, R.u0b, R.v0b, (uint64_t)frame * a.out.cap + run_base);
-    return;
-  }
-  uint8_t* wsm = smem + (size_t)warp * (kSmooth ? (kFast ? kWarpSmemBytes : kOffTab) : kOffMemo);
   uint32_t* s_pt = reinterpret_cast<uint32_t*>(wsm + kOffPt);
   uint4* s_term = reinterpret_cast<uint4*>(wsm + kOffTerm);
-  uint16_t* s_src = reinterpret_cast<uint16_t*>(wsm + kOffSrc);
-  uint8_t* s_cnt = wsm + kOffCnt;
-  uint32_t* s_bmp = reinterpret_cast<uint32_t*>(wsm + kOffBmp);
+  // debug streams look boundary classes up per point: those instantiations keep the smoothing layout
+  constexpr bool kWide = kSmooth || kDebug;
+  uint16_t* s_src = reinterpret_cast<uint16_t*>(wsm + (kWide ? kOffSrcSmooth : kOffSrcPlain));
+  uint8_t* s_cnt = wsm + (kWide ? kOffCntSmooth : kOffCntPlain);
+  uint32_t* s_bmp = reinterpret_cast<uint32_t*>(s_cnt + 256);
 
-  const bool has_attr = a.has_attr != 0;
+  constexpr bool has_attr = kAttr;
   const bool want_bt = kSmooth || (kDebug && a.out.btype != nullptr);
   const uint32_t h = lane & 1u, r = lane >> 1;
   const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
-  DevPatch P;
-  load_patch_fields(a.patches + R.pid, P);
   uint32_t n_boundary = 0, any_flag = 0, lbase0 = 0, nmin = 0;
 
   {
-    // ---- (1): canvas layout ----------------------------------------------------------------------------------------
-    const uint32_t x0 = (uint32_t)R.bx * 16u + 8u * h, y = (uint32_t)R.by * 16u + r;
-    uint4 ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
-    uint2 ua = {0, 0}, va = {0, 0}, ub = {0, 0}, vb = {0, 0};
-    // kLateAttr (experiment): the attribute planes are only prefetched into L2 here and loaded after the geometry has been
-    // digested, so that fewer load results are in registers at once
-    constexpr bool kLateAttr = (kSmooth && TMC2_LATE_ATTR) || TMC2_LATE_ATTR_ALL;
-    // (addresses are worked out inside the lambda: nothing attribute-related stays live while the geometry is digested)
-    auto attr_planes = [&](auto&& touch) {                                           // decoder.rs:976-977
-      const uint16_t* ay0 = a.in.attr_y + (uint64_t)frame * 2 * a.in.attr_y_map_stride;
-      const uint32_t yoff = y * a.in.attr_pitch_y + x0;
-      const uint64_t cf = (uint64_t)frame * 2 * a.in.attr_c_map_stride;
-      const uint32_t coff = (y >> 1) * a.in.attr_pitch_c + (x0 >> 1);
-      const uint16_t* au0 = a.in.attr_u + cf + coff; const uint16_t* av0 = a.in.attr_v + cf + coff;
-      touch(ay0 + yoff, ay0 + a.in.attr_y_map_stride + yoff, au0, av0, au0 + a.in.attr_c_map_stride, av0 + a.in.attr_c_map_stride);
-    };
-    auto load_attr = [&]() {
-      attr_planes([&](const uint16_t* y0, const uint16_t* y1, const uint16_t* u0, const uint16_t* v0, const uint16_t* u1,
-                      const uint16_t* v1) {
-        ya = ldg_nc_v4(y0); yb = ldg_nc_v4(y1);
-        // the two rows of a chroma row pair ask for the same addresses in the same instruction: one fetch
-        ua = ldg_nc_v2(u0); va = ldg_nc_v2(v0); ub = ldg_nc_v2(u1); vb = ldg_nc_v2(v1);
-      });
-    };
-    if (has_attr) {
-      if (kLateAttr) {
-        attr_planes([&](const uint16_t* y0, const uint16_t* y1, const uint16_t* u0, const uint16_t* v0, const uint16_t* u1,
-                        const uint16_t* v1) {
-          prefetch_l2(y0); prefetch_l2(y1); prefetch_l2(u0); prefetch_l2(v0); prefetch_l2(u1); prefetch_l2(v1);
-        });
-      } else {
-        load_attr();
-      }
+    // ---- (1): canvas layout: lane (r, h) = canvas row r, columns 8h .. 8h+7 -------------------------------------------
+    const uint4 g0 = *reinterpret_cast<const uint4*>(wsm + kOffRawGeo + 32u * r + 16u * h);
+    const uint4 g1 = *reinterpret_cast<const uint4*>(wsm + kOffRawGeo + 512u + 32u * r + 16u * h);
+    uint32_t m1 = 0;
+    if (occ_by_tma(a)) {
+      // occupancy of the 8 pixels (codec.rs:393-396: any non-zero sample counts): two samples of the box row (r >> 2) + 2
+      const uint32_t o = *reinterpret_cast<const uint16_t*>(wsm + kOffRawOcc + ((r >> 2) + 2u) * 32u +
+                                                            (uint32_t)((int32_t)R.bx * 4 - occ_box_x(R.bx)) + 2u * h);
+      m1 = ((o & 0xFFu) ? 0x0Fu : 0u) | ((o >> 8) ? 0xF0u : 0u);
+    } else {
+      m1 = occupancy_mask(a, R, lane);
     }
     CanvasBlock L;
-    load_geometry(a, R, P, lane, L);
-    if (kPrefetchTiles) prefetch_slot_planes<!kSmooth>(a, pf.x, pf_frame, pf.z, lane);
+    geometry_digest(a, P, g0, g1, m1, L);
     uint32_t bt1 = 0, bt2 = 0;
-    if (want_bt) boundary_masks(a, R, lane, s_bmp, bt1, bt2);
+    if (want_bt) {
+      if (occ_by_tma(a)) boundary_masks_raw(a, R, lane, wsm + kOffRawOcc, s_bmp, bt1, bt2);
+      else boundary_masks(a, R, lane, s_bmp, bt1, bt2);
+    }
     if (kSmooth) {
       const uint32_t b1 = L.m1 & bt1;
       n_boundary = __reduce_add_sync(kFull, __popc(b1) + __popc(b1 & L.m2));
@@ -1224,8 +1276,6 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
         nmin = __reduce_min_sync(kFull, min(lo & 0xFFFFu, lo >> 16));
       }
     }
-
-    if (kLateAttr && has_attr) load_attr();
 
     // ---- (2): tables in patch raster order -----------------------------------------------------------------------------
     // canvas-local (lx, ly) = (8h + j, r) -> patch-local (u1, v1) through the inverse of the affine map (decoder.rs:853-867)
@@ -1251,12 +1301,20 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
     }
     // entry of (pixel, map) = n | Y << 16; a table row (16 pixels) is padded by one entry pair so that neither the row-wise
     // nor the column-wise (transposed patches) stores run into shared-memory bank conflicts
+    {
+      uint4 ya = {0, 0, 0, 0}, yb = {0, 0, 0, 0};
+      if (has_attr) {                                                                // decoder.rs:976-977
+        ya = *reinterpret_cast<const uint4*>(wsm + kOffRawY + 32u * r + 16u * h);
+        yb = *reinterpret_cast<const uint4*>(wsm + kOffRawY + 512u + 32u * r + 16u * h);
+      }
+      if (!kWide) __syncwarp();        // plain layout: the per-pixel counts go where the geometry / luma tiles were
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t rank = rank0 + (uint32_t)(j * dr);
-      const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
-      *reinterpret_cast<uint2*>(s_pt + 2u * (rank + (rank >> 4))) =
-          make_uint2(__byte_perm(L.n0p[j >> 1], word_of(ya, j >> 1), sel), __byte_perm(L.n1p[j >> 1], word_of(yb, j >> 1), sel));
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t rank = rank0 + (uint32_t)(j * dr);
+        const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+        *reinterpret_cast<uint2*>(s_pt + 2u * (rank + (rank >> 4))) =
+            make_uint2(__byte_perm(L.n0p[j >> 1], word_of(ya, j >> 1), sel), __byte_perm(L.n1p[j >> 1], word_of(yb, j >> 1), sel));
+      }
     }
     if (dr == 1) {
       *reinterpret_cast<uint2*>(s_cnt + rank0) = make_uint2(cb_lo, cb_hi);
@@ -1267,17 +1325,23 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
       for (int j = 0; j < 8; ++j)
         s_cnt[rank0 + (uint32_t)(j * dr)] = (uint8_t)((j < 4 ? cb_lo : cb_hi) >> (8 * (j & 3)));
     }
+    uint2 cu2 = {0, 0}, cv2 = {0, 0};
     if (has_attr) {
-      // chroma terms, once per (chroma sample, map): the two lanes of a row pair hold the same 4 samples; the even row
-      // evaluates map 0, the odd row map 1.  Entry = {ir, ig, ib << 1 | flagged, U | V << 16}, indexed by the patch-local
-      // chroma position (cv * 8 + cu) * 2 + map.
+      // the two rows of a chroma row pair hold the same 4 samples; the even row evaluates map 0, the odd row map 1
+      const uint32_t coff = ((r & 1u) ? 128u : 0u) + 16u * (r >> 1) + 8u * h;
+      cu2 = *reinterpret_cast<const uint2*>(wsm + kOffRawU + coff);
+      cv2 = *reinterpret_cast<const uint2*>(wsm + kOffRawV + coff);
+    }
+    __syncwarp();                                                   // the RAW area has been read for the last time: the smoothing state may overwrite it
+    if (has_attr) {
+      // chroma terms, once per (chroma sample, map).  Entry = {ir, ig, ib << 1 | flagged, U | V << 16}, indexed by the
+      // patch-local chroma position (cv * 8 + cu) * 2 + map.
       const bool odd = (r & 1u) != 0;
       const uint32_t ccy = r >> 1;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         const uint32_t sel = (cc & 1) ? 0x7632u : 0x5410u;
-        const uint32_t uv = odd ? __byte_perm(word_of(ub, cc >> 1), word_of(vb, cc >> 1), sel)
-                                : __byte_perm(word_of(ua, cc >> 1), word_of(va, cc >> 1), sel);
+        const uint32_t uv = __byte_perm(word_of(cu2, cc >> 1), word_of(cv2, cc >> 1), sel);
         const uint32_t ccx = 4u * h + (uint32_t)cc;
         uint32_t cu, cv;
         if (ax != 0) { cu = ax > 0 ? ccx : 7u - ccx; cv = ry > 0 ? ccy : 7u - ccy; }
@@ -1285,7 +1349,8 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
         // no occupied pixel under the sample (the other row of the pair lies in the same occupancy cell unless the
         // precision is 1): nobody will read the term
         if (a.prec_shift >= 1 && !((L.m1 >> (2 * cc)) & 3u)) continue;
-        const ChromaTerm t = chroma_term(uv & 0xFFFFu, uv >> 16);
+        ChromaTerm t = chroma_term_fast(uv & 0xFFFFu, uv >> 16);
+        if (t.flagged) t = chroma_term(uv & 0xFFFFu, uv >> 16);   // rare (or not 10-bit content): the exact 32.32 evaluation
         any_flag |= t.flagged;
         s_term[((cv * 8u + cu) << 1) | (odd ? 1u : 0u)] = make_uint4((uint32_t)t.ir, (uint32_t)t.ig, ((uint32_t)t.ib << 1) | t.flagged, uv);
       }
@@ -1373,7 +1438,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
 
   SmoothState S;
   if (kSmooth) {
-    S.init(a, frame, fig, patch, lane, reinterpret_cast<uint32_t*>(wsm + kOffMemo), kFast);
+    S.init(a, frame, fig, patch, lane, reinterpret_cast<uint32_t*>(wsm + kOffMemo), reinterpret_cast<uint8_t*>(s_bmp), kFast);
     if (n_boundary) {
       const uint32_t lbase = __shfl_sync(kFull, lbase0, 0);
       if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
@@ -1520,6 +1585,48 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, kSmooth ? TMC2_SMOOTH_MINC
     }
     S.finish(a, P);
   }
+}
+
+template <bool kSmooth, bool kDebug, bool kFast, bool kAttr>
+__global__ void __launch_bounds__(kEmitWarps * 32, kSmooth ? TMC2_EMIT_CTAS_SMOOTH : TMC2_EMIT_CTAS)
+emit_kernel(const __grid_constant__ UnpackArgs a, const __grid_constant__ TileMaps tm, uint32_t slot_begin, uint32_t slot_end) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  uint8_t* wsm = smem + (size_t)warp * ((kSmooth || kDebug) ? kWarpSmemSmooth : kWarpSmemPlain);
+  void* bar = wsm + kOffBar;
+  const uint32_t lpos = slot_begin + blockIdx.x * kEmitWarps + warp;
+  if (lpos >= slot_end) return;
+  uint32_t mode;
+  const WorkRec R = load_work(a.work + lpos, &mode);
+  if (R.pid == kNoPatch || R.total == 0u) return;                // unused tail of the frame's region / nothing to emit
+  if ((uint64_t)R.base + R.total > a.out.cap) {                  // cannot happen for footprints inside the canvas
+    if (lane == 0) atomicExch(a.err, 7);
+    return;
+  }
+  if (!slot_is_fast(a, R)) {
+    const uint32_t fig = kSmooth ? R.frame - a.sm.group_first_frame : 0u;
+    generic_slot_emit<kSmooth, kDebug>(a, R.pid, R.frame, fig, R.u0b, R.v0b, (uint64_t)R.frame * a.out.cap + R.base);
+    return;
+  }
+  // the plane tiles of the block: five boxes (three without attributes), one mbarrier
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    const bool occ = occ_by_tma(a);
+    mbar_expect_tx(bar, 1024u + (kAttr ? 1536u : 0u) + (occ ? 256u : 0u));
+    const int32_t x0 = (int32_t)R.bx * 16, y0 = (int32_t)R.by * 16, f = (int32_t)R.frame;
+    tma_load_4d(wsm + kOffRawGeo, tm.geo, bar, x0, y0, 0, f);
+    if (kAttr) {
+      tma_load_4d(wsm + kOffRawY, tm.attr_y, bar, x0, y0, 0, f);
+      tma_load_4d(wsm + kOffRawU, tm.attr_u, bar, x0 >> 1, y0 >> 1, 0, f);
+      tma_load_4d(wsm + kOffRawV, tm.attr_v, bar, x0 >> 1, y0 >> 1, 0, f);
+    }
+    if (occ) tma_load_3d(wsm + kOffRawOcc, tm.occ, bar, occ_box_x(R.bx), (int32_t)R.by * 4 - 2, f);
+  }
+  DevPatch P;
+  load_patch_fields(a.patches + R.pid, P);                       // in flight together with the tiles
+  __syncwarp();
+  mbar_wait(bar, 0);
+  emit_fast_slot<kSmooth, kDebug, kFast, kAttr>(a, R, P, wsm, lane);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1887,12 +1994,22 @@ int launch_compact_owned(const UnpackArgs& a, void* stream) {
   return after_launch();
 }
 
-template <bool kSmooth, bool kDebug, bool kFast>
-static int launch_emit_t(const UnpackArgs& a, uint32_t tile_begin, uint32_t tile_end, cudaStream_t s) {
-  const size_t smem = (size_t)(kSmooth ? (kFast ? kWarpSmemBytes : kOffTab) : kOffMemo) * kWarpsPerTile;   // memo / cell table: smoothing only
-  cudaError_t e = cudaFuncSetAttribute((const void*)emit_kernel<kSmooth, kDebug, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <bool kSmooth, bool kDebug, bool kFast, bool kAttr>
+static int launch_emit_t(const UnpackArgs& a, const TileMaps& tm, uint32_t slot_begin, uint32_t slot_end, cudaStream_t s) {
+  const size_t smem = (size_t)((kSmooth || kDebug) ? kWarpSmemSmooth : kWarpSmemPlain) * kEmitWarps;
+  auto kern = emit_kernel<kSmooth, kDebug, kFast, kAttr>;
+  static bool configured[64] = {};               // the dynamic shared memory limit is a per-device attribute of the function
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
-  emit_kernel<kSmooth, kDebug, kFast><<<tile_end - tile_begin, kWarpsPerTile * 32, smem, s>>>(a, tile_begin, tile_end);
+  if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+  if (!configured[dev]) {
+    e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured[dev] = true;
+  }
+  const uint32_t blocks = (slot_end - slot_begin + kEmitWarps - 1) / kEmitWarps;
+  kern<<<blocks, kEmitWarps * 32, smem, s>>>(a, tm, slot_begin, slot_end);
   return after_launch();
 }
 
@@ -1908,17 +2025,21 @@ int launch_slot_scan(const UnpackArgs& a, void* stream) {
   return after_launch();
 }
 
-int launch_emit(const UnpackArgs& a, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream) {
+int launch_emit(const UnpackArgs& a, const TileMaps& tm, bool smooth, uint32_t tile_begin, uint32_t tile_end, void* stream) {
   if (tile_end <= tile_begin) return 0;
   const cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t s0 = tile_begin * kWarpsPerTile, s1 = tile_end * kWarpsPerTile;
   const bool debug = a.out.yuv || a.out.part || a.out.pix || a.out.btype;
+  const bool attr = a.has_attr != 0;
+#define TMC2_EMIT(S, D, F) (attr ? launch_emit_t<S, D, F, true>(a, tm, s0, s1, s) : launch_emit_t<S, D, F, false>(a, tm, s0, s1, s))
   if (smooth) {
-    if (debug) return launch_emit_t<true, true, false>(a, tile_begin, tile_end, s);
+    if (debug) return TMC2_EMIT(true, true, false);
     // the usual grids (dense tables, power-of-two cell edges, geometry edge <= 8) get the instantiation without generic branches
     const bool fast = (!a.sm.geo.on || (a.sm.geo.fast == 1u && a.sm.geo.g <= 8u)) && (!a.sm.col.on || a.sm.col.fast);
-    return fast ? launch_emit_t<true, false, true>(a, tile_begin, tile_end, s) : launch_emit_t<true, false, false>(a, tile_begin, tile_end, s);
+    return fast ? TMC2_EMIT(true, false, true) : TMC2_EMIT(true, false, false);
   }
-  return debug ? launch_emit_t<false, true, false>(a, tile_begin, tile_end, s) : launch_emit_t<false, false, false>(a, tile_begin, tile_end, s);
+  return debug ? TMC2_EMIT(false, true, false) : TMC2_EMIT(false, false, false);
+#undef TMC2_EMIT
 }
 
 int launch_upsample(const UnpackArgs& a, uint8_t* occ_full, void* stream) {

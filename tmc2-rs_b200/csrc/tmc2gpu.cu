@@ -5,6 +5,7 @@
 //   submit_gof  = validate + stage + H2D + [K2 block_to_patch] + [fused unpack] + [smoothing] + counts D2H
 //   next_frame  = in-order hand-out of PointSet3-compatible buffers (src/lib.rs:81, src/codec.rs:20-36)
 // There is no CPU fallback anywhere: without a CUDA device every entry point returns TMC2_ERR_NO_DEVICE.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -194,6 +195,40 @@ class StagePool {
   std::atomic<size_t> next_{0};
   uint64_t epoch_ = 0;
 };
+
+// TMA descriptors of the plane arrays (device_types.h TileMaps).  cuTensorMapEncodeTiled is reached through the runtime's
+// driver entry point lookup, so the library does not link against libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// rank-`rank` tensor of `esz`-byte elements: dims[] elements, strides[] bytes of dims 1.., box[] elements
+static bool encode_map(unsigned long long* out, void* base, uint32_t esz, uint32_t rank, const uint64_t* dims, const uint64_t* strides,
+                       const uint32_t* box) {
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || !base) return false;
+  cuuint64_t d[5]; cuuint64_t st[5]; cuuint32_t b[5]; cuuint32_t es[5];
+  for (uint32_t i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; if (i) st[i - 1] = strides[i - 1]; }
+  CUtensorMap m;
+  const CUresult r = fn(&m, esz == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, base, d, st, b, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  memcpy(out, &m, 128);
+  return true;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // validation: everything the reference asserts / unwraps / leaves unimplemented on this path
@@ -589,7 +624,7 @@ struct Batch {
       if (setup(smoothing_geo, params.grid_size, sizeof(GeoCell), d_geotab, d_geokeys, d_geombits, d_geotbits, geotab_slots, geotab_frames, geotab_hashed)) return err.st;
       if (setup(smoothing_col, params.cgrid_size, sizeof(ColCell), d_coltab, d_colkeys, d_colmbits, d_coltbits, coltab_slots, coltab_frames, coltab_hashed)) return err.st;
     }
-    return TMC2_OK;
+    return make_tile_maps(err);
   }
 
   // ---- H2D: planes (through pinned staging unless the caller's memory is already pinned) + metadata -------------
@@ -704,6 +739,36 @@ struct Batch {
     memcpy(m + meta_ftb_off, h_ftb.data(), (size_t)(F + 1) * 4);
     CU(cudaMemcpyAsync(d_meta.p, m, meta_bytes, cudaMemcpyHostToDevice, stream));
     CU(cudaEventRecord(ev_inputs_free, stream));
+    return TMC2_OK;
+  }
+
+  // TMA descriptors of this batch's plane arrays (rebuilt by prepare(): they hold device addresses and sizes)
+  TileMaps tile_maps{};
+  tmc2_status make_tile_maps(Err& err) {
+    memset(&tile_maps, 0, sizeof tile_maps);
+    if (F == 0 || res != 16) return TMC2_OK;                           // no block-aligned slots: the maps are never used
+    const uint64_t gms = (uint64_t)H * geo_pitch * 2, yms = (uint64_t)H * attr_pitch_y * 2, cms = (uint64_t)std::max(Hc, 1u) * attr_pitch_c * 2;
+    bool ok = true;
+    {
+      const uint64_t dims[4] = {W, H, 2, F}, st[3] = {(uint64_t)geo_pitch * 2, gms, 2 * gms};
+      const uint32_t box[4] = {16, 16, 2, 1};
+      ok &= encode_map(tile_maps.geo, d_geo.p, 2, 4, dims, st, box);
+    }
+    if (params.attribute_count) {
+      const uint64_t dims[4] = {W, H, 2, F}, st[3] = {(uint64_t)attr_pitch_y * 2, yms, 2 * yms};
+      const uint32_t box[4] = {16, 16, 2, 1};
+      ok &= encode_map(tile_maps.attr_y, d_ay.p, 2, 4, dims, st, box);
+      const uint64_t cd[4] = {std::max(W / 2, 1u), std::max(Hc, 1u), 2, F}, cs[3] = {(uint64_t)attr_pitch_c * 2, cms, 2 * cms};
+      const uint32_t cbox[4] = {8, 8, 2, 1};
+      ok &= encode_map(tile_maps.attr_u, d_au.p, 2, 4, cd, cs, cbox);
+      ok &= encode_map(tile_maps.attr_v, d_av.p, 2, 4, cd, cs, cbox);
+    }
+    {
+      const uint64_t dims[3] = {occ_w, occ_h, F}, st[2] = {(uint64_t)occ_pitch, (uint64_t)occ_h * occ_pitch};
+      const uint32_t box[3] = {32, 8, 1};
+      ok &= encode_map(tile_maps.occ, d_occ.p, 1, 3, dims, st, box);
+    }
+    if (!ok) FAIL(TMC2_ERR_CUDA, "cuTensorMapEncodeTiled failed (TMA descriptors of the plane arrays)");
     return TMC2_OK;
   }
 
@@ -822,7 +887,7 @@ struct Batch {
       while (ev_grp.size() < 2) { cudaEvent_t e; CU(cudaEventCreate(&e)); ev_grp.push_back(e); }
       n_groups = 1;
       CU(cudaEventRecord(ev_grp[0], s));
-      KL(launch_emit(a, false, 0, n_tiles, s));
+      KL(launch_emit(a, tile_maps, false, 0, n_tiles, s));
       CU(cudaEventRecord(ev_grp[1], s));
     } else {
       // frame groups: unpack (+ cell statistics + boundary lists) -> filter -> clear, tables stay hot in L2
@@ -850,7 +915,7 @@ struct Batch {
         if (gi >= 2) CU(cudaStreamWaitEvent(s, ev_post[gi - 2], 0));          // this table set has been cleared
         if (clear_pending) { CU(cudaStreamWaitEvent(s, ev_tables_clean, 0)); clear_pending = false; }   // ... by the previous launch
         CU(cudaEventRecord(ev_grp[2 * gi], s));
-        KL(launch_emit(a, true, h_ftb[f0], h_ftb[f1], s));
+          KL(launch_emit(a, tile_maps, true, h_ftb[f0], h_ftb[f1], s));
         CU(cudaEventRecord(ev_grp[2 * gi + 1], s));
         if (dbg) {
           CU(cudaMemcpyAsync(d_pos_pre.as<uint8_t>() + (size_t)f0 * cap * 6, d_pos.as<uint8_t>() + (size_t)f0 * cap * 6,
