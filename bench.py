@@ -3,17 +3,24 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
-    torchrun ... bench.py --gpus N ...                       # one rank per GPU, frames sharded GOF-wise, no collective
+    torchrun ... bench.py --gpus N ...                       # one rank per GPU, frames sharded, no collective
 
-A "step" is one pass of the hot path over one synthetic GOF (BASELINE config 2: 32 frames, 1024x1024 atlas, 10-bit
-geometry, 2 maps, occupancy precision 4, grid geometry smoothing + colour smoothing ON).  With N ranks every rank
-reconstructs its own GOF per step (weak scaling; frames / GOFs are independent).
+Workload (`config.workload`; the same for both arms):
+  N = 1   BASELINE config 2: a 32-frame GOF, 1024x1024 atlas, 10-bit geometry, 2 maps, occupancy precision 4, grid geometry
+          smoothing + colour smoothing ON.  A step = one pass of the hot path over a batch of GOFS_PER_STEP such GOFs.
+  N > 1   BASELINE config 3, STRONG scaling: a 300-frame sequence (1280x1344, ~1.1 M points per frame, smoothing ON) as ten
+          30-frame GOFs, sharded frame-wise over the N ranks with shard.frames_for_rank (contiguous slices, no collective:
+          frames and GOFs are independent, src/lib.rs:114-120).  A step = one pass over the whole sequence.
+          (--config c3s runs this workload on one GPU as well: the N = 1 point of the scaling curve.)
 
-  value  points/s with the planes already resident in HBM (kernels only, CUDA events on the launching streams): step i
-         reconstructs resident GOF i % 3 on stream i % 3, like the three GOFs in flight of the streaming path, so the
-         small latency-bound passes of one GOF run under the emit of another (--resident-gofs 1: one stream, GOF latency)
+  value  points/s with the planes already resident in HBM (kernels only, CUDA events on the launching streams); the resident
+         GOFs of a rank go round-robin over three streams, like the three GOFs in flight of the streaming path
   e2e    points/s through the public C ABI (tmc2gpu_submit_gof / tmc2gpu_next_frame) from PINNED HOST planes:
-         H2D of every plane and D2H of every reconstructed frame inside the timed region
+         H2D of every plane and D2H of every reconstructed frame inside the timed region; `e2e.host_ceiling` is the same
+         byte traffic as bare pinned copies on two streams (all ranks at once), `e2e.frac_of_host_ceiling` the ratio
+  e2e_pageable (N = 1)  the same with the planes in ordinary (pageable) memory, like the reference's `Vec<u8>`
+  one_context (N > 1)   rank 0 alone drives ONE tmc2gpu context over all N devices (the topology behind the unchanged
+         `Decoder` API): frames sharded inside the library, handed back in order
   roofline  algorithmic bytes of the dominant kernel (fused unpack) / its device time, against the measured HBM peak
   cpu_baseline  the reference's single-threaded algorithm (C restatement, oracle/) on this box's host cores
 """
@@ -143,13 +150,83 @@ def cpu_reference_run(gof, frames_per_step: int, steps: int, warmup: int, thread
     return pts, dt
 
 
+GOFS_PER_STEP = 64          # N = 1: GOFs per step (a step of 64 x 0.5 ms keeps the timed region of 10 steps above 0.3 s)
+SEQ_FRAMES, SEQ_GOF = 300, 30   # N > 1: BASELINE config 3
+
+
+def workload(args, world):
+    """(mode, synthetic config name, smoothing, config dict).  The dict depends on the arguments only, so both arms print the
+    same one."""
+    name = args.config
+    if name == "auto":
+        name = "c2" if max(world, args.gpus) <= 1 else "c3s"
+    strong = name == "c3s"
+    sname = "c3" if strong else name
+    cfg = synth.config(sname)
+    frames = args.frames or (SEQ_GOF if strong else {"c1": 1, "c2": 32, "c3": 32, "c4": 8}.get(sname, 32))
+    smoothing = sname != "c1" and not args.no_smoothing
+    n = max(world, args.gpus, 1)
+    if strong:
+        desc = {"workload": f"c3 strong scaling: {SEQ_FRAMES}-frame sequence as {SEQ_FRAMES // SEQ_GOF} GOFs of {SEQ_GOF} frames, "
+                            f"synthetic decoded planes + patch metadata, sharded frame-wise over {n} GPU(s)",
+                "frames_per_step": SEQ_FRAMES, "frames_per_gof": SEQ_GOF}
+    else:
+        per = 1 if sname == "c1" else GOFS_PER_STEP
+        desc = {"workload": f"{sname}: {frames}-frame GOF, synthetic decoded planes + patch metadata, {per} GOF(s) per step",
+                "frames_per_step": frames * per, "frames_per_gof": frames}
+    desc.update({"atlas": f"{cfg.width}x{cfg.height}", "maps": 2, "occupancy_precision": cfg.occupancy_precision,
+                 "bitdepth_3d": cfg.bitdepth_3d, "smoothing": smoothing,
+                 "sharding": (f"{n} rank(s), contiguous frame slices of the sequence, no collective" if strong else
+                              f"{n} rank(s), every rank its own GOFs, no collective"),
+                 "l2": "inputs of a step exceed the 126 MB L2 (no flush needed)"})
+    return ("strong" if strong else "weak"), sname, frames, smoothing, desc
+
+
+def rank_gofs(mode, frames, rank, world):
+    """Frame counts of the GOFs rank `rank` reconstructs per step."""
+    if mode == "weak":
+        return [frames] * (1 if frames == 1 else GOFS_PER_STEP)
+    lo, hi = shard.frames_for_rank(SEQ_FRAMES, rank, world)
+    out, f = [], lo
+    while f < hi:                      # the rank's slice, cut at the sequence's GOF boundaries
+        nxt = min(hi, (f // SEQ_GOF + 1) * SEQ_GOF)
+        out.append(nxt - f)
+        f = nxt
+    return out
+
+
+def host_copy_ceiling(torch, dev, h2d_bytes, d2h_bytes, iters, barrier):
+    """The step's byte traffic as bare pinned copies (H2D and D2H on two streams): what the host side of this box can move
+    with every rank busy.  Returns seconds per step."""
+    hi = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8).pin_memory()
+    di = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, device=dev)
+    ho = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8).pin_memory()
+    do = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def it():
+        with torch.cuda.stream(s1):
+            di.copy_(hi, non_blocking=True)
+        with torch.cuda.stream(s2):
+            ho.copy_(do, non_blocking=True)
+    it()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        it()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / iters
+    del hi, di, ho, do
+    return dt
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", help="synthetic workload: c2 (default, BASELINE config 2), c1, c3, c4")
+    ap.add_argument("--config", default="auto", help="auto (c2 on one GPU, c3s = config 3 strong scaling on several), c1, c2, c3, c3s, c4")
     ap.add_argument("--frames", type=int, default=0, help="frames per GOF (default: the config's)")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames cycled inside the GOF")
     ap.add_argument("--ref-threads", type=int, default=1)
@@ -157,36 +234,34 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-smoothing", action="store_true", help="reference-exact rec0 path only (no post-processing)")
     ap.add_argument("--resident-gofs", type=int, default=3,
-                    help="resident GOFs the kernel-only loop alternates between, each on its own stream (consecutive GOFs "
-                         "of a stream overlap: the small latency-bound passes of one run under the emit of the other)")
+                    help="streams the kernel-only loop spreads its GOFs over (consecutive GOFs of a stream overlap: the small "
+                         "latency-bound passes of one run under the emit of the other)")
+    ap.add_argument("--quick", action="store_true", help="skip the secondary measurements (pageable e2e, one-context, host ceiling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    frames_default = {"c1": 1, "c2": 32, "c3": 32, "c4": 8}.get(args.config, 32)
-    frames = args.frames or frames_default
-    smoothing = args.config != "c1" and not args.no_smoothing
-    cfg_desc = {"workload": f"{args.config}: {frames}-frame GOF, synthetic decoded planes + patch metadata", "frames_per_gof": frames}
+    mode, sname, frames, smoothing, cfg_desc = workload(args, world)
+    cfg = synth.config(sname)
 
     # ------------------------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        gof, cfg = build_workload(args.config, frames, min(args.distinct, 4))
+        gof, _ = build_workload(sname, frames, min(args.distinct, 4))
         gof.params.geometry_smoothing = smoothing
         gof.params.color_smoothing = smoothing
-        cfg_desc.update({"atlas": f"{cfg.width}x{cfg.height}", "smoothing": smoothing, "maps": 2,
-                         "occupancy_precision": cfg.occupancy_precision})
         sample = max(1, min(frames, 2))                   # frames per step: bounded so K steps end within minutes
         pts, dt = cpu_reference_run(gof, sample, args.steps, args.warmup, args.ref_threads)
         v = pts / dt
         line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "strong" if mode == "strong" else "weak",
                 "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": cfg_desc,
                 "frames_per_sec": sample * args.steps / dt,
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": args.ref_threads, "kind": "port",
-                                 "sample": f"{sample} frames/step x {args.steps} steps of the same GOF; C restatement of "
+                                 "sample": f"{sample} frames/step x {args.steps} steps of the same workload; C restatement of "
                                            "tmc2-rs src/codec.rs (the Rust reference cannot be built: no cargo/rustc)",
                                  "host_cores": os.cpu_count()},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -215,151 +290,187 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    gof, cfg = build_workload(args.config, frames, args.distinct)
-    gof.params.geometry_smoothing = smoothing
-    gof.params.color_smoothing = smoothing
-    cfg_desc.update({"atlas": f"{cfg.width}x{cfg.height}", "smoothing": smoothing, "maps": 2,
-                     "occupancy_precision": cfg.occupancy_precision, "bitdepth_3d": cfg.bitdepth_3d,
-                     "sharding": f"{world} rank(s), one GOF per rank per step, no collective",
-                     "e2e_gofs_in_flight": 3,
-                     "host_cpus_of_rank0": (f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else "inherited"),
-                     "l2": f"inputs {gof.input_bytes() / 1e6:.0f} MB/step > 126 MB L2 (no flush needed)"})
-    depth = 3                                             # GOFs in flight on the streaming path (keeps both DMA engines busy)
-    ctx = codec.Context(devices=(local_rank,), gofs_in_flight=depth)
-    pinned = codec.pinned_copy_of(gof)
-    view = abi.GofView(pinned)
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the GOFs this rank reconstructs per step, by size; one pinned copy of the planes per distinct size
+    sizes = rank_gofs(mode, frames, rank, world)
+    base, _ = build_workload(sname, max(sizes), args.distinct)
+    base.params.geometry_smoothing = smoothing
+    base.params.color_smoothing = smoothing
+    depth = 3                                             # GOFs in flight on the streaming path (keeps both DMA engines busy)
+    ctx = codec.Context(devices=(local_rank,), gofs_in_flight=depth)
+    pinned, views = {}, {}
+    for sz in sorted(set(sizes), reverse=True):
+        pinned[sz] = codec.pinned_copy_of(base if sz == base.frame_count else base.subset(range(sz)))
+        views[sz] = abi.GofView(pinned[sz])
+    frames_per_step_rank = sum(sizes)
+
     # ---- value: planes resident in HBM, kernels only -----------------------------------------------------------------
     n_res = max(1, args.resident_gofs)
-    cfg_desc["resident_gofs_in_flight"] = n_res
-    residents = [ctx.upload_gof(view) for _ in range(n_res)]
-    res = residents[0]
+    main_sz = max(sizes)
+    residents = {sz: [ctx.upload_gof(views[sz]) for _ in range(n_res if sz == main_sz else 1)] for sz in views}
     # dedicated torch streams: torch.cuda.Event only sees the stream it is recorded on, and torch's default stream
     # has handle 0, which the C ABI reads as "use the library's own stream"
     tstreams = [torch.cuda.Stream(device=dev) for _ in range(n_res)]
     tstream = tstreams[0]
     torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
     assert all(t.cuda_stream != 0 for t in tstreams)
-    for _ in range(args.warmup):
-        for r, t in zip(residents, tstreams):
+    # a kernel-only step repeats the rank's GOF list until it holds at least `inner` GOFs (strong scaling at N = 8 leaves a
+    # rank two GOFs of ~1 ms in total: far too short to time)
+    inner = max(1, -(-32 // len(sizes))) if mode == "strong" else 1
+    plan = []                                            # (resident, stream) of one kernel-only step
+    k = 0
+    for _ in range(inner):
+        for sz in sizes:
+            rs = residents[sz]
+            plan.append((rs[k % len(rs)], tstreams[k % n_res]))
+            k += 1
+    for rs in residents.values():                        # every resident once (buffers, tables), then the usual warm-up
+        for r in rs:
+            r.reconstruct(tstream.cuda_stream)
+    for _ in range(max(1, min(args.warmup, 3))):
+        for r, t in plan[:3 * n_res]:
             r.reconstruct(t.cuda_stream)
-    counts = res.counts()
-    points_per_step = int(counts.sum())
-    launches_per_step, alg_bytes, _ = ctx.last_launch_info()
+    points_by_size = {sz: int(residents[sz][0].counts().sum()) for sz in views}
+    points_per_step = sum(points_by_size[sz] for sz in sizes)            # this rank, one pass
+    residents[main_sz][0].reconstruct(tstream.cuda_stream)
+    launches_per_gof, alg_bytes, _ = ctx.last_launch_info()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    unpack_ms, stage_acc = [], {}
-    # step i reconstructs resident GOF i % n_res on stream i % n_res; the timed region starts when every stream has passed
-    # e0 and ends when every stream has finished its last step
     e0.record(tstream)
     for t in tstreams[1:]:
         t.wait_event(e0)
     for i in range(args.steps):
-        residents[i % n_res].reconstruct(tstreams[i % n_res].cuda_stream)
+        for r, t in plan:
+            r.reconstruct(t.cuda_stream)
     for t in tstreams[1:]:
         done = torch.cuda.Event()
         done.record(t)
         tstream.wait_event(done)
     e1.record(tstream)
     barrier()
-    kernel_ms = e0.elapsed_time(e1)
+    kernel_ms = e0.elapsed_time(e1) / inner               # per pass over the rank's GOF list
     # per-stage device times (library-recorded CUDA events on the same stream), measured on separate launches so that
     # reading them does not serialise the timed loop above
-    for _ in range(min(args.steps, 5)):
-        res.reconstruct(stream)
+    unpack_ms, stage_acc = [], {}
+    for _ in range(5):
+        residents[main_sz][0].reconstruct(tstream.cuda_stream)
         st = ctx.last_stage_ms()
         unpack_ms.append(st["unpack"])
-        for k, v in st.items():
-            stage_acc.setdefault(k, []).append(v)
-    kernel_ms_max, pts_all, frames_all = shard.reduce_metrics(kernel_ms, points_per_step * args.steps, frames * args.steps, dev)
+        for kk, v in st.items():
+            stage_acc.setdefault(kk, []).append(v)
+    kernel_ms_max, pts_all, frames_all = shard.reduce_metrics(kernel_ms, points_per_step * args.steps,
+                                                              frames_per_step_rank * args.steps, dev)
     value = pts_all / (kernel_ms_max * 1e-3)
-    for r in residents:
-        r.free()
+    for rs in residents.values():
+        for r in rs:
+            r.free()
 
-    # ---- e2e: public C ABI, pinned host planes in, pinned host frames out, two GOFs in flight ---------------------------
-    def drain(n):
-        got = 0
-        for _ in range(n):
-            cnt, pos_addr, _col_addr = ctx.next_frame_raw()      # frame is in pinned host memory when this returns
-            got += cnt
-        return got
-    # warm-up with the same GOFs-in-flight pattern as the timed loop, so that every GOF slot of the context has its device
-    # buffers and pinned result slab allocated before timing starts
-    for _ in range(depth - 1):
-        ctx.submit_gof(view)
-    for _ in range(max(depth + 1, args.warmup)):
-        ctx.submit_gof(view)
-        drain(frames)
-    for _ in range(depth - 1):
-        drain(frames)
-    barrier()
-    trace = os.environ.get("TMC2_TRACE") is not None
-    t0 = time.perf_counter()
-    got = 0
-    ahead = min(depth - 1, args.steps)
-    for _ in range(ahead):
-        ctx.submit_gof(view)
-    for s in range(args.steps - ahead):
-        ctx.submit_gof(view)
-        got += drain(frames)
-        if trace:
-            sys.stderr.write(f"[bench] e2e step {s}: {(time.perf_counter() - t0) * 1e3:.2f} ms since start\n")
-    for _ in range(ahead):
-        got += drain(frames)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    # ---- e2e: public C ABI, pinned host planes in, pinned host frames out, three GOFs in flight ---------------------------
+    def e2e_run(c, vws, gof_sizes, steps, warm):
+        return e2e_loop(c, vws, gof_sizes, steps, warm, depth, barrier)
+
+    e2e_sizes = sizes if mode == "strong" else sizes[:max(1, min(len(sizes), 8))]   # N = 1: 8 GOFs per e2e step (same rate, shorter run)
+    e2e_scale = len(sizes) / len(e2e_sizes)
+    warm_e2e = max(1, -(-(depth + 1) // len(e2e_sizes)))
+    dt_e2e, got_all = e2e_run(ctx, views, e2e_sizes, args.steps, warm_e2e)
+    pts_e2e_step = sum(points_by_size[sz] for sz in e2e_sizes)
     clocks = sampler.stop()            # sampled over both timed regions (kernel-only steps and the end-to-end steps)
     barrier()
-    e2e_ms_max, e2e_pts, _ = shard.reduce_metrics(e2e_ms, got, frames * args.steps, dev)
+    e2e_ms_max, e2e_pts, e2e_frames = shard.reduce_metrics(dt_e2e * 1e3, pts_e2e_step * args.steps, sum(e2e_sizes) * args.steps, dev)
     e2e_value = e2e_pts / (e2e_ms_max * 1e-3)
-    h2d = gof.input_bytes()
-    d2h = points_per_step * 9
+    h2d = int(sum(pinned[sz].input_bytes() for sz in e2e_sizes) * e2e_scale)
+    d2h = int(pts_e2e_step * 9 * e2e_scale)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "frames_per_sec": e2e_frames / (e2e_ms_max * 1e-3), "ms_per_step": e2e_ms_max / args.steps * e2e_scale,
+           "gofs_in_flight": depth, "input_memory": "pinned (tmc2gpu_alloc_pinned)"}
+    extra = {}
+    if not args.quick:
+        # the same bytes as bare pinned copies, every rank at once: the ceiling the host side of this box puts on e2e
+        dt_copy = host_copy_ceiling(torch, dev, int(h2d / e2e_scale), int(d2h / e2e_scale), 5, barrier)
+        copy_ms_max, _, _ = shard.reduce_metrics(dt_copy * 1e3, 0, 0, dev)
+        ceiling = e2e_pts / args.steps / (copy_ms_max * 1e-3)
+        e2e["host_ceiling"] = {"value": ceiling, "unit": UNIT, "ms_per_step": copy_ms_max * e2e_scale,
+                               "what": "the step's H2D + D2H bytes as bare pinned cudaMemcpyAsync on two streams, all ranks at once",
+                               "aggregate_GBps": (h2d + d2h) / e2e_scale * world / (copy_ms_max * 1e-3) / 1e9}
+        e2e["frac_of_host_ceiling"] = e2e_value / ceiling
+        if world == 1:
+            # planes in ordinary memory, like the reference's Vec<u8> (src/decoder.rs:1136-1140): staged by the library
+            pageable = {sz: abi.GofView(base if sz == base.frame_count else base.subset(range(sz))) for sz in set(e2e_sizes)}
+            dt_p, got_p = e2e_run(ctx, pageable, e2e_sizes, max(2, args.steps // 2), warm_e2e)
+            extra["e2e_pageable"] = {"value": pts_e2e_step * max(2, args.steps // 2) / dt_p, "unit": UNIT,
+                                     "frames_per_sec": sum(e2e_sizes) * max(2, args.steps // 2) / dt_p,
+                                     "input_memory": "pageable numpy arrays, staged by the library's thread pool",
+                                     "stage_threads": os.environ.get("TMC2_STAGE_THREADS", "default")}
+    ctx.close()
+    if world > 1 and not args.quick:
+        # ONE context over all N devices, driven by rank 0 alone (the other ranks wait): the topology behind the unchanged
+        # Decoder API -- tmc2gpu_create(ids, N), frames of every GOF sharded inside the library, handed back in order
+        barrier()
+        if rank == 0:
+            full, _ = build_workload(sname, SEQ_GOF, args.distinct)
+            full.params.geometry_smoothing = smoothing
+            full.params.color_smoothing = smoothing
+            pfull = codec.pinned_copy_of(full)
+            vfull = {SEQ_GOF: abi.GofView(pfull)}
+            octx = codec.Context(devices=tuple(range(world)), gofs_in_flight=depth)
+            try:
+                seq = [SEQ_GOF] * (SEQ_FRAMES // SEQ_GOF)
+                dt_o, got_o = e2e_loop(octx, vfull, seq, max(2, args.steps // 2), 1, depth)
+                extra["one_context"] = {"value": got_o / dt_o, "unit": UNIT, "devices": world,
+                                        "frames_per_sec": SEQ_FRAMES * max(2, args.steps // 2) / dt_o,
+                                        "what": "e2e through ONE tmc2gpu context over all devices, one host thread, frames in order"}
+            finally:
+                octx.close()
+        barrier()
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------------------------
     peak, peak_src = measured_peak()
     t_unpack = statistics.mean(unpack_ms) if unpack_ms else float("nan")
-    # the emit kernel is launched once per smoothing frame group (8 frames) -- once for the whole GOF without smoothing;
-    # algorithmic bytes and device time are per launch (SURVEY.md 8d figure x the frames one launch processes)
-    group = int(os.environ.get("TMC2_SMOOTH_GROUP", "32")) if smoothing else frames
-    n_emit = max(1, -(-frames // max(group, 1)))
+    # the emit kernel is launched once per smoothing frame group (the whole GOF unless the tables do not fit); algorithmic bytes
+    # and device time are per launch (SURVEY.md 8d figure x the frames one launch processes)
+    group = int(os.environ.get("TMC2_SMOOTH_GROUP", "32")) if smoothing else main_sz
+    n_emit = max(1, -(-main_sz // max(group, 1)))
     achieved = alg_bytes / (t_unpack * 1e-3) / 1e9 if t_unpack and t_unpack > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "emit_kernel (fused occupancy upsample / unpack / attribute fetch / YUV->RGB; + boundary + cell statistics when smoothing)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "frac_of_nominal_8TBps": achieved / 8000.0,
-                "launches_per_step": n_emit, "frames_per_launch": min(group, frames),
+                "launches_per_gof": n_emit, "frames_per_launch": min(group, main_sz),
                 "algorithmic_bytes_per_launch": alg_bytes / n_emit, "ms_per_launch": t_unpack / n_emit, "traffic": None,
-                "stage_ms": {k: statistics.mean(v) for k, v in stage_acc.items()}}
+                "stage_ms": {kk: statistics.mean(v) for kk, v in stage_acc.items()}}
     # the other HBM-streaming kernel of the path: the count pass reads the occupancy video and both geometry planes once
     # (its stage time also holds the tiny per-frame scan launch, so the fraction is a lower bound)
     t_count = statistics.mean(stage_acc.get("count_scan", [0.0])) if stage_acc else 0.0
-    count_bytes = frames * (cfg.width // cfg.occupancy_precision) * (cfg.height // cfg.occupancy_precision) + frames * 2 * cfg.width * cfg.height * 2
+    count_bytes = main_sz * (cfg.width // cfg.occupancy_precision) * (cfg.height // cfg.occupancy_precision) + main_sz * 2 * cfg.width * cfg.height * 2
     if t_count > 0:
         roofline["other_kernels"] = {"count_kernel+slot_scan_kernel": {
             "algorithmic_bytes_per_launch": count_bytes, "ms_per_launch": t_count,
             "achieved": count_bytes / (t_count * 1e-3) / 1e9, "frac": count_bytes / (t_count * 1e-3) / 1e9 / peak}}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            roofline["traffic"] = json.load(f).get(args.config + ("" if smoothing else "_nosmooth"))
+            roofline["traffic"] = json.load(f).get(sname + ("" if smoothing else "_nosmooth"))
     except Exception:
         pass
 
+    gofs_per_step_all = len(sizes) if mode == "weak" else SEQ_FRAMES // SEQ_GOF
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong" if mode == "strong" else "weak", "vs_baseline": None,
             "dtype": "u16", "data": "synthetic", "config": cfg_desc,
-            "frames_per_sec": frames_all / (kernel_ms_max * 1e-3), "points_per_step_per_gpu": points_per_step,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "frames_per_sec": frames * args.steps * world / (e2e_ms_max * 1e-3), "ms_per_step": e2e_ms_max / args.steps},
-            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-            "roofline": roofline, "clocks": clocks}
+            "frames_per_sec": frames_all / (kernel_ms_max * 1e-3), "points_per_step_rank0": points_per_step,
+            "e2e": e2e,
+            "gpu_launches": launches_per_gof * len(sizes) * inner * args.steps, "gpu_launches_per_gof": launches_per_gof,
+            "roofline": roofline, "clocks": clocks,
+            "timing": {"kernel_only_passes_per_step": inner, "resident_streams": n_res,
+                       "e2e_gofs_per_step_rank0": len(e2e_sizes), "timed_kernel_region_ms": kernel_ms_max * inner,
+                       "host_cpus_of_rank0": (f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else "inherited")}}
+    line.update(extra)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # ~10-20 s of single-threaded CPU work: 64 frames (two passes over the GOF) with smoothing, 128 without
@@ -369,18 +480,44 @@ def main():
         else:
             per, reps = 1, sample
         sample = per * reps
-        pts, dt = cpu_reference_run(gof, per, reps, 0, 1)
+        pts, dt = cpu_reference_run(base, per, reps, 0, 1)
         line["cpu_baseline"] = {"value": pts / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{sample} frame(s) of the same workload, {dt:.1f} s; single-threaded C restatement "
                                           "of tmc2-rs src/codec.rs (+ this repo's smoothing spec) -- the Rust reference "
                                           "cannot be built in this image",
                                 "host_cores": os.cpu_count(), "ms_per_frame": dt / sample * 1e3}
-    ctx.close()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def e2e_loop(c, vws, gof_sizes, steps, warm, depth, barrier=None):
+    """`warm` untimed + `steps` timed passes over `gof_sizes` through submit_gof / next_frame with `depth` GOFs in flight (the
+    warm-up GOFs are drained before the clock starts).  Returns (seconds, points of the timed passes)."""
+    seq = [sz for _ in range(warm + steps) for sz in gof_sizes]
+    n_warm = warm * len(gof_sizes)
+    got, t0, pending = 0, None, []
+    for i, sz in enumerate(seq):
+        if i == n_warm:
+            while pending:
+                for _ in range(pending.pop(0)):
+                    c.next_frame_raw()
+            if barrier:
+                barrier()
+            t0 = time.perf_counter()
+        c.submit_gof(vws[sz])
+        pending.append(sz)
+        if len(pending) >= depth:
+            for _ in range(pending.pop(0)):
+                n = c.next_frame_raw()[0]
+                if i >= n_warm:
+                    got += n
+    while pending:
+        for _ in range(pending.pop(0)):
+            got += c.next_frame_raw()[0]
+    return time.perf_counter() - t0, got
 
 
 if __name__ == "__main__":

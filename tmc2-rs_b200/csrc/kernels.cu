@@ -1212,7 +1212,7 @@ __device__ __forceinline__ void boundary_masks_raw(const UnpackArgs& a, const Wo
 }
 
 #ifndef TMC2_EMIT_CTAS
-#define TMC2_EMIT_CTAS 6
+#define TMC2_EMIT_CTAS 7
 #endif
 #ifndef TMC2_EMIT_CTAS_SMOOTH
 #define TMC2_EMIT_CTAS_SMOOTH 6
