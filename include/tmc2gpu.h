@@ -168,7 +168,9 @@ typedef struct tmc2_frame_out {
   const uint16_t* positions;      /* point_count * 3                                                       */
   const uint8_t*  colors;         /* point_count * 3 ; NULL when attribute_count == 0                      */
   uint8_t         with_colors;    /* PointSet3.with_colors                                                 */
-  uint8_t         _reserved[7];
+  uint8_t         memory_space;   /* 0: positions / colors are pinned HOST memory; 1: DEVICE memory (TMC2_CTX_DEVICE_OUTPUT) */
+  uint8_t         device;         /* CUDA device ordinal that reconstructed the frame (and holds it when memory_space == 1)  */
+  uint8_t         _reserved[5];
   uint64_t        smoothed_positions; /* points moved by geometry smoothing (0 when off)                   */
   uint64_t        smoothed_colors;    /* points recoloured by colour smoothing (0 when off)                */
   void*           _handle;        /* library cookie                                                        */
@@ -183,6 +185,11 @@ typedef struct tmc2_limits {
 } tmc2_limits;
 
 #define TMC2_CTX_TWO_PASS_SCAN 1u  /* accepted for compatibility; the unpack is always count / scan / emit   */
+/* Device-resident hand-off: frames are NOT copied to the host; next_frame returns device pointers
+ * (frame_out.memory_space == 1, on frame_out.device) that stay valid until every frame of that GOF has been released.
+ * For consumers on the same GPU (renderer, encoder, a PLY formatter): the 9 bytes per point of D2H -- 41 % of the PCIe
+ * traffic that bounds the streaming path -- are not moved at all.                                                 */
+#define TMC2_CTX_DEVICE_OUTPUT 2u
 
 typedef struct tmc2gpu_ctx tmc2gpu_ctx;
 

@@ -95,7 +95,9 @@ pub struct tmc2_frame_out {
     pub positions: *const u16,
     pub colors: *const u8,
     pub with_colors: u8,
-    pub _reserved: [u8; 7],
+    pub memory_space: u8, // 0 = pinned host memory, 1 = device memory (TMC2_CTX_DEVICE_OUTPUT)
+    pub device: u8,
+    pub _reserved: [u8; 5],
     pub smoothed_positions: u64,
     pub smoothed_colors: u64,
     pub _handle: *mut c_void,

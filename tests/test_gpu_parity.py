@@ -5,6 +5,7 @@ import os
 import numpy as np
 import pytest
 
+import kats
 import util
 from oracle import oracle
 from tmc2rs_b200 import abi, codec, synth
@@ -535,6 +536,49 @@ def test_failed_gof_is_dropped_whole_and_slot_is_freed():
     finally:
         os.environ.pop("TMC2_TEST_BLIST_CAP", None)
         ctx.close()
+
+
+@pytest.mark.parametrize("name,make", kats.ALL, ids=[n for n, _ in kats.ALL])
+def test_hand_derived_kats_on_gpu(gpu_ctx, name, make):
+    """The CUDA path against the hand-derived vectors of tests/kats.py (stage API and streaming API)."""
+    g, want = make()
+    view = abi.GofView(g)
+    kats.check(gpu_ctx.generate_point_cloud(view, 0), want, name)
+    fr = gpu_ctx.decode_gof(view)[0]
+    assert fr.positions.tolist() == want["positions"] and (fr.colors == 127).all()
+
+
+def test_device_resident_hand_off_matches_host_frames(gpu_ctx):
+    """a context created with TMC2_CTX_DEVICE_OUTPUT hands frames out as device pointers (no D2H copy); what
+    sits behind them equals the frames of the ordinary context and the oracle."""
+    import torch
+    g = synth.make_gof(synth.config("small", frames=3))
+    g.params.geometry_smoothing = True
+    g.params.color_smoothing = True
+    view = abi.GofView(g)
+    host = gpu_ctx.decode_gof(view)
+    dctx = codec.Context(device_output=True)
+
+    class Dev:                                             # zero-copy torch view of a raw device range
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    try:
+        dctx.submit_gof(view)
+        got = [dctx.next_frame_device() for _ in range(3)]
+        assert dctx.next_frame_device() is None
+        for f, (n, ppos, pcol, dev, release) in enumerate(got):
+            want = oracle.reconstruct_frame(view, f)
+            assert n == want["point_count"] == len(host[f]) and dev == 0
+            pos = torch.as_tensor(Dev(ppos, n * 6), device="cuda:0").cpu().numpy().view(np.uint16).reshape(n, 3)
+            col = torch.as_tensor(Dev(pcol, n * 3), device="cuda:0").cpu().numpy().reshape(n, 3)
+            assert np.array_equal(pos, want["positions"]) and np.array_equal(col, want["colors"])
+            assert np.array_equal(pos, host[f].positions) and np.array_equal(col, host[f].colors)
+        for *_, release in got:
+            release()
+        dctx.submit_gof(view)                               # the slot is free again
+        assert dctx.next_frame_device()[0] == len(host[0])
+    finally:
+        dctx.close()
 
 
 def test_one_process_two_devices_shard_frames_in_order():

@@ -134,3 +134,46 @@ def test_two_rank_gloo_sharding_and_metric_reduction():
     assert (lo0, hi1) == (0, 37) and hi0 == lo1                    # contiguous, disjoint, complete
     assert ms0 == ms1 == 20.0                                      # max over ranks
     assert p0 == p1 == sum(1000 + f for f in range(37)) and f0 == f1 == 37
+
+
+def test_ply_writer_matches_the_reference_format():
+    """tmc2rs_b200/ply.py against src/writer.rs:31-75 written out by hand for a two-point cloud."""
+    from tmc2rs_b200 import ply
+    pos = np.array([[1, 2, 3], [65535, 0, 7]], np.uint16)
+    col = np.array([[255, 0, 127], [1, 2, 3]], np.uint8)
+    want = ("ply\nformat ascii 1.0\nelement vertex 2\nproperty uint x\nproperty uint y\nproperty uint z\n"
+            "property uchar red\nproperty uchar green\nproperty uchar blue\nelement face 0\n"
+            "property list uint8 int32 vertex_index\nend_header\n1 2 3 255 0 127\n65535 0 7 1 2 3\n")
+    assert ply.ascii_ply(pos, col) == want.encode()
+    assert ply.ascii_ply(pos, None).endswith(b"end_header\n1 2 3\n65535 0 7\n") and b"red" not in ply.ascii_ply(pos, None)
+    for data in (ply.ascii_ply(pos, col), ply.binary_ply(pos, col)):
+        p2, c2 = ply.read_ply(data)
+        assert np.array_equal(p2, pos) and np.array_equal(c2, col)
+    assert len(ply.binary_ply(pos, col)) == len(ply._header("binary_little_endian", 2, True)) + 2 * 15
+
+
+def test_compare_dump_report(tmp_path):
+    """tools/compare_dump.py: the +-1 / differing-count report of north_star on synthetic pairs."""
+    import importlib.util
+    from tmc2rs_b200 import ply
+    spec = importlib.util.spec_from_file_location("compare_dump", os.path.join(os.path.dirname(GOLD), "..", "tools", "compare_dump.py"))
+    cd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cd)
+    rng = np.random.RandomState(3)
+    pos = rng.randint(0, 1024, (500, 3)).astype(np.uint16)
+    col = rng.randint(0, 256, (500, 3)).astype(np.uint8)
+    pos2, col2 = pos.copy(), col.copy()
+    pos2[10, 1] += 1; pos2[20, 2] += 3; col2[5, 0] ^= 1                       # two moved points (one beyond +-1), one recoloured
+    (tmp_path / "ref.ply").write_bytes(ply.ascii_ply(pos, col))
+    (tmp_path / "ours.ply").write_bytes(ply.binary_ply(pos2, col2))
+    pos2.astype("<u2").tofile(tmp_path / "ours.u16"); col2.tofile(tmp_path / "ours.u8")
+    for ours in ("ours.ply", "ours.u16"):
+        rep = cd.compare(cd.load(str(tmp_path / "ref.ply")), cd.load(str(tmp_path / ours)))
+        assert rep["positions_differing"] == 2 and rep["positions_beyond_tolerance"] == 1 and rep["colors_differing"] == 1
+        assert rep["colors_beyond_tolerance"] == 0 and not rep["within_tolerance"] and not rep["bit_exact"]
+    same = cd.compare(cd.load(str(tmp_path / "ref.ply")), cd.load(str(tmp_path / "ref.ply")))
+    assert same["bit_exact"]
+    perm = rng.permutation(500)
+    (tmp_path / "shuffled.ply").write_bytes(ply.ascii_ply(pos[perm], col[perm]))
+    assert cd.compare(cd.load(str(tmp_path / "ref.ply")), cd.load(str(tmp_path / "shuffled.ply")), unordered=True)["bit_exact"]
+    assert cd.main([str(tmp_path / "ref.ply"), str(tmp_path / "ref.ply"), "--json"]) == 0

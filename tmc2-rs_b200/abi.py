@@ -29,6 +29,7 @@ ORIENT_DEFAULT, ORIENT_SWAP, ORIENT_ROT90, ORIENT_ROT180, ORIENT_ROT270, ORIENT_
 ORIENTATION_REFERENCE, ORIENTATION_SPEC = 0, 1
 
 CTX_TWO_PASS_SCAN = 1
+CTX_DEVICE_OUTPUT = 2
 
 
 class Tmc2Error(RuntimeError):
@@ -86,7 +87,8 @@ class CGof(C.Structure):
 
 class CFrameOut(C.Structure):
     _fields_ = [("frame_index", C.c_uint64), ("point_count", C.c_uint64), ("positions", C.c_void_p),
-                ("colors", C.c_void_p), ("with_colors", C.c_uint8), ("_reserved", C.c_uint8 * 7),
+                ("colors", C.c_void_p), ("with_colors", C.c_uint8), ("memory_space", C.c_uint8), ("device", C.c_uint8),
+                ("_reserved", C.c_uint8 * 5),
                 ("smoothed_positions", C.c_uint64), ("smoothed_colors", C.c_uint64), ("_handle", C.c_void_p)]
 
 

@@ -37,12 +37,13 @@ class Context:
     the library accepts and ignores (the unpack is always count / scan / emit)."""
 
     def __init__(self, devices: Sequence[int] = (0,), max_frames: int = 0, gofs_in_flight: int = 2,
-                 two_pass_scan: bool = False):
+                 two_pass_scan: bool = False, device_output: bool = False):
         self.h = None
         self.lib = load()
         if self.lib.tmc2gpu_device_count() <= 0:
             raise abi.Tmc2Error(abi.ERR_NO_DEVICE, "tmc2gpu_create", "no CUDA device (there is no CPU fallback)")
-        lim = abi.CLimits(0, 0, max_frames, 0, gofs_in_flight, abi.CTX_TWO_PASS_SCAN if two_pass_scan else 0)
+        lim = abi.CLimits(0, 0, max_frames, 0, gofs_in_flight,
+                          (abi.CTX_TWO_PASS_SCAN if two_pass_scan else 0) | (abi.CTX_DEVICE_OUTPUT if device_output else 0))
         ids = (C.c_int * len(devices))(*devices)
         h = C.c_void_p()
         st = self.lib.tmc2gpu_create(ids, len(devices), C.byref(lim), C.byref(h))
@@ -144,6 +145,21 @@ class Context:
         ps = PointSet3(pos, col, bool(fo.with_colors), int(fo.smoothed_positions), int(fo.smoothed_colors))
         self.check(self.lib.tmc2gpu_release_frame(self.h, C.byref(fo)), "release_frame")
         return ps
+
+    def next_frame_device(self):
+        """Device-resident hand-off (contexts created with ``device_output=True``): ``(point_count, positions device pointer,
+        colours device pointer, device ordinal, release)`` of the next frame, or None at the end.  The pointers stay valid until
+        ``release()`` has been called for every frame of that GOF."""
+        fo = abi.CFrameOut()
+        st = self.lib.tmc2gpu_next_frame(self.h, C.byref(fo))
+        if st == abi.END:
+            return None
+        self.check(st, "next_frame")
+        assert fo.memory_space == 1, "context was not created with device_output=True"
+
+        def release(fo=fo):
+            self.check(self.lib.tmc2gpu_release_frame(self.h, C.byref(fo)), "release_frame")
+        return int(fo.point_count), int(fo.positions or 0), int(fo.colors or 0), int(fo.device), release
 
     def next_frame_raw(self):
         """Lean variant of next_frame for tight loops: (point_count, positions address, colours address) of the next frame in

@@ -1064,6 +1064,7 @@ struct tmc2gpu_ctx {
   std::string last_error;
   Batch* last_batch = nullptr;                               // for launch info / stage times
   bool two_pass = false;
+  bool device_output = false;                                // TMC2_CTX_DEVICE_OUTPUT: frames stay in HBM
 
   tmc2_status fail() { last_error = err.msg; return err.st; }
 };
@@ -1107,6 +1108,7 @@ tmc2_status tmc2gpu_create(const int* device_ids, int device_count, const tmc2_l
   if (ctx->limits.gofs_in_flight == 0) ctx->limits.gofs_in_flight = 2;
   if (ctx->limits.gofs_in_flight > 8) ctx->limits.gofs_in_flight = 8;
   ctx->two_pass = (ctx->limits.flags & TMC2_CTX_TWO_PASS_SCAN) != 0;
+  ctx->device_output = (ctx->limits.flags & TMC2_CTX_DEVICE_OUTPUT) != 0;
   ctx->slots.resize(ctx->devices.size());
   for (size_t d = 0; d < ctx->devices.size(); ++d) {
     for (uint32_t k = 0; k < ctx->limits.gofs_in_flight; ++k) {
@@ -1274,6 +1276,22 @@ tmc2_status tmc2gpu_next_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out) {
   const bool first = !b->counts_ready;
   if (!b->counts_ready && b->fetch_counts(b->stream, err)) { drop_gof(); return ctx->fail(); }
   const double t_counts = tc.lap();
+  if (ctx->device_output) {
+    // device-resident hand-off: the counts copy was enqueued behind the last kernel of the GOF, so every frame is complete
+    ctx->pending.pop_front();
+    memset(out, 0, sizeof *out);
+    out->frame_index = pf.global_index;
+    out->point_count = b->counts[pf.local];
+    out->positions = reinterpret_cast<const uint16_t*>(b->d_pos.as<uint8_t>() + (size_t)pf.local * b->cap * 6);
+    out->with_colors = b->params.attribute_count ? 1 : 0;
+    out->colors = out->with_colors ? b->d_rgb.as<uint8_t>() + (size_t)pf.local * b->cap * 3 : nullptr;
+    out->memory_space = 1;
+    out->device = (uint8_t)b->device;
+    out->smoothed_positions = b->moved[pf.local];
+    out->smoothed_colors = b->recoloured[pf.local];
+    out->_handle = b;
+    return TMC2_OK;
+  }
   if (!b->outputs_enqueued && b->enqueue_outputs(err)) { drop_gof(); return ctx->fail(); }
   const double t_enq = tc.lap();
   if (cudaSetDevice(b->device) != cudaSuccess || cudaEventSynchronize(b->ev_frame[pf.local]) != cudaSuccess) {
@@ -1296,6 +1314,8 @@ tmc2_status tmc2gpu_next_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out) {
   out->positions = reinterpret_cast<const uint16_t*>(b->h_out.as<uint8_t>() + b->out_pos_off[pf.local]);
   out->with_colors = b->params.attribute_count ? 1 : 0;
   out->colors = out->with_colors ? b->h_out.as<uint8_t>() + b->out_rgb_off[pf.local] : nullptr;
+  out->memory_space = 0;
+  out->device = (uint8_t)b->device;
   out->smoothed_positions = b->moved[pf.local];
   out->smoothed_colors = b->recoloured[pf.local];
   out->_handle = b;
