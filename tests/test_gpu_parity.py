@@ -605,3 +605,33 @@ def test_one_process_two_devices_shard_frames_in_order():
     finally:
         one.close()
         two.close()
+
+
+def test_one_context_over_all_devices_in_order():
+    """The product topology behind the unchanged `Decoder` API (src/lib.rs:81): ONE context over every GPU of the box, frames of
+    each GOF sharded frame-wise inside the library and handed back in order, several GOFs in flight.  Needs >= 2 GPUs (runs on
+    the multi-GPU scaling box; skipped on a one-GPU box)."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    g = synth.replicate_gof(synth.make_gof(synth.config("small")), 2 * n + 3)      # uneven slices
+    g.params.geometry_smoothing = True
+    g.params.color_smoothing = True
+    view = abi.GofView(g)
+    F = g.frame_count
+    want = {f: oracle.reconstruct_frame(view, f) for f in (0, F // 2, F - 1)}
+    ctx = codec.Context(devices=tuple(range(n)), gofs_in_flight=2)
+    try:
+        ctx.submit_gof(view)
+        ctx.submit_gof(view)                                                        # two GOFs in flight on every device
+        frames = [ctx.next_frame() for _ in range(2 * F)]
+        assert ctx.next_frame() is None
+        for k, fr in enumerate(frames):
+            f = k % F
+            if f in want:
+                assert np.array_equal(fr.positions, want[f]["positions"]) and np.array_equal(fr.colors, want[f]["colors"]), (k, f)
+        for a, b in zip(frames[:F], frames[F:]):
+            assert np.array_equal(a.positions, b.positions) and np.array_equal(a.colors, b.colors)
+    finally:
+        ctx.close()

@@ -34,7 +34,7 @@
 
 namespace tmc2 {
 
-static int g_launches = 0;
+static thread_local int g_launches = 0;   // per host thread: the pieces of a GOF are launched from one thread per device
 int kernel_launch_count_reset() { int n = g_launches; g_launches = 0; return n; }
 
 constexpr uint32_t kFull = 0xFFFFFFFFu;

@@ -397,13 +397,14 @@ struct Batch {
   std::vector<uint32_t> counts;
   std::vector<uint64_t> moved, recoloured;
   std::vector<size_t> out_pos_off, out_rgb_off;
-  bool counts_ready = false, outputs_enqueued = false;
+  bool counts_ready = false, outputs_enqueued = false, counts_enqueued = false;
   uint32_t launches = 0, n_groups = 1;
   uint64_t unpack_alg_bytes = 0;
   uint32_t frames_released = 0;
   bool busy = false;
   std::chrono::steady_clock::time_point t_submit;   // TMC2_TRACE bookkeeping
   uint64_t t_epoch = 0;                             // submit call that made this batch busy
+  Err failed_early;                                 // a failure found while this batch was not yet at the head of the queue
   double trace_wait_ms = 0;
 
   ~Batch() { destroy(); }
@@ -665,7 +666,7 @@ struct Batch {
     }
   }
 
-  tmc2_status upload(const tmc2_gof* g, uint32_t first, Err& err) {
+  tmc2_status upload(const tmc2_gof* g, uint32_t first, Err& err, bool use_pool = true) {
     CU(cudaSetDevice(device));
     const bool attr = params.attribute_count != 0;
     std::vector<Seg> segs;
@@ -719,13 +720,15 @@ struct Batch {
           for (uint32_t r = 0; r < segs[k].rows; r += rows_per) items.push_back({&segs[k], r, std::min(segs[k].rows, r + rows_per)});
         }
         uint8_t* base = h_in.as<uint8_t>();
-        StagePool::get().run(items.size(), [&](size_t n) {
+        auto stage_item = [&](size_t n) {
           const Item& it = items[n];
           const Seg& sg = *it.s;
           uint8_t* st = base + sg.stage_off;
           if (sg.spitch == sg.dpb && sg.row_bytes == sg.dpb) memcpy(st + (size_t)it.r0 * sg.dpb, sg.src + (size_t)it.r0 * sg.spitch, (size_t)(it.r1 - it.r0) * sg.dpb);
           else for (uint32_t r = it.r0; r < it.r1; ++r) memcpy(st + (size_t)r * sg.dpb, sg.src + (size_t)r * sg.spitch, sg.row_bytes);
-        });
+        };
+        if (use_pool) StagePool::get().run(items.size(), stage_item);
+        else for (size_t n = 0; n < items.size(); ++n) stage_item(n);     // already on a pool thread (one per device piece)
       }
       for (size_t k = i; k < j; ++k) { tmc2_status st = enqueue(segs[k]); if (st) return st; }
       i = j;
@@ -953,12 +956,13 @@ struct Batch {
     }
     CU(cudaEventRecord(ev[3], s)); CU(cudaEventRecord(ev[4], s)); CU(cudaEventRecord(ev[5], s));
     launches = (uint32_t)kernel_launch_count_reset();
-    counts_ready = false; outputs_enqueued = false;
+    counts_ready = false; outputs_enqueued = false; counts_enqueued = false;
     return TMC2_OK;
   }
 
-  // counts (+ error flag, + smoothing statistics) to the host; synchronises with `s`
-  tmc2_status fetch_counts(cudaStream_t s, Err& err) {
+  // counts (+ error flag, + smoothing statistics) to the host: enqueue_counts puts the copies behind the kernels on `s`,
+  // finish_counts waits for them and reads the result; fetch_counts does both
+  tmc2_status enqueue_counts(cudaStream_t s, Err& err) {
     CU(cudaSetDevice(device));
     const size_t bytes = (size_t)F * 4 + (size_t)F * 16 + 16;
     CU(h_small.ensure(bytes));
@@ -967,7 +971,21 @@ struct Batch {
     CU(cudaMemcpyAsync(hs + (size_t)F * 4, d_changed.p, (size_t)F * 16, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(hs + (size_t)F * 20, d_err.p, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(ev_counts, s));
+    counts_enqueued = true;
+    return TMC2_OK;
+  }
+  bool counts_arrived() {                       // non-blocking: have the kernels and the counts copy of this batch finished?
+    if (!counts_enqueued) return false;
+    cudaSetDevice(device);
+    const cudaError_t e = cudaEventQuery(ev_counts);
+    if (e != cudaSuccess) cudaGetLastError();
+    return e == cudaSuccess;
+  }
+  tmc2_status finish_counts(cudaStream_t s, Err& err) {
+    CU(cudaSetDevice(device));
+    uint8_t* hs = h_small.as<uint8_t>();
     CU(cudaEventSynchronize(ev_counts));
+    counts_enqueued = false;
     int dev_err = 0;
     memcpy(&dev_err, hs + (size_t)F * 20, 4);
     if (dev_err) {
@@ -988,6 +1006,10 @@ struct Batch {
     unpack_alg_bytes = algorithmic_bytes_core(total);
     counts_ready = true;
     return TMC2_OK;
+  }
+  tmc2_status fetch_counts(cudaStream_t s, Err& err) {
+    if (!counts_enqueued && enqueue_counts(s, err)) return err.st;
+    return finish_counts(s, err);
   }
 
   // enqueue the per-frame result copies into one pinned slab; per-frame events signal completion
@@ -1134,7 +1156,10 @@ const char* tmc2gpu_last_error(const tmc2gpu_ctx* ctx) { return ctx ? ctx->last_
 void* tmc2gpu_alloc_pinned(size_t bytes) {
   void* p = nullptr;
   if (bytes == 0) return nullptr;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  // TMC2_PINNED_WC=1: write-combined pages (the host only ever writes decoded samples into these planes; the DMA engine
+  // reads them without snooping the CPU caches) -- an experiment knob, measured in profiles/
+  static const bool wc = [] { const char* e = getenv("TMC2_PINNED_WC"); return e && atoi(e) != 0; }();
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | (wc ? cudaHostAllocWriteCombined : 0)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   std::lock_guard<std::mutex> lk(g_pin_mu);
   g_pinned.emplace_back((const uint8_t*)p, bytes);
   return p;
@@ -1219,23 +1244,38 @@ tmc2_status tmc2gpu_submit_gof(tmc2gpu_ctx* ctx, const tmc2_gof* gof) {
     ctx->next_global = global_mark;
   };
   ++ctx->submit_epoch;
+  // The pieces (one per device, or per chunk) are independent batches: digest of the patch lists, staging, H2D and launch
+  // enqueue of every piece run on their own host thread when there are several, so that one submitting thread keeps N devices
+  // busy (src/lib.rs has exactly one worker thread above this call).
+  std::vector<Err> perr(pieces.size());
+  auto do_piece = [&](size_t i) {
+    Piece& pc = pieces[i];
+    Batch* b = pc.b;
+    Err& e = perr[i];
+    TraceClock pt;
+    if (b->prepare(gof, pc.lo, pc.hi - pc.lo, 0, e)) return;
+    const double t_prep = pt.lap();
+    if (b->upload(gof, pc.lo, e, pieces.size() == 1)) return;
+    const double t_up = pt.lap();
+    if (b->launch(b->stream, e)) return;
+    if (b->enqueue_counts(b->stream, e)) return;          // counts travel right behind the kernels
+    if (trace_on())
+      fprintf(stderr, "[tmc2gpu] submit dev %d frames %u..%u: prepare %.3f upload-enqueue %.3f launch-enqueue %.3f ms\n",
+              b->device, pc.lo, pc.hi, t_prep, t_up, pt.lap());
+  };
+  if (pieces.size() == 1) do_piece(0);
+  else StagePool::get().run(pieces.size(), do_piece);
+  for (size_t i = 0; i < pieces.size(); ++i)
+    if (perr[i].st != TMC2_OK) { err = perr[i]; undo(); return ctx->fail(); }
   for (auto& pc : pieces) {
     Batch* b = pc.b;
-    const double t_val = tc.lap();
-    if (b->prepare(gof, pc.lo, pc.hi - pc.lo, 0, err)) { undo(); return ctx->fail(); }
-    const double t_prep = tc.lap();
-    if (b->upload(gof, pc.lo, err)) { undo(); return ctx->fail(); }
-    const double t_up = tc.lap();
-    if (b->launch(b->stream, err)) { undo(); return ctx->fail(); }
-    if (trace_on())
-      fprintf(stderr, "[tmc2gpu] submit dev %d frames %u..%u: validate %.3f prepare %.3f upload-enqueue %.3f launch-enqueue %.3f ms\n",
-              b->device, pc.lo, pc.hi, t_val, t_prep, t_up, tc.lap());
     // counts travel right behind the kernels; result copies are enqueued when the first frame is asked for
     b->busy = true; b->frames_released = 0; b->t_epoch = ctx->submit_epoch;
     b->t_submit = std::chrono::steady_clock::now(); b->trace_wait_ms = 0;
     ctx->last_batch = b;
     for (uint32_t k = 0; k < pc.hi - pc.lo; ++k) ctx->pending.push_back({b, k, ctx->next_global++});
   }
+  if (trace_on()) fprintf(stderr, "[tmc2gpu] submit_gof: %zu piece(s), %.3f ms on the calling thread\n", pieces.size(), tc.lap());
   return TMC2_OK;
 }
 
@@ -1271,10 +1311,26 @@ tmc2_status tmc2gpu_next_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out) {
     cudaStreamSynchronize(b->stream);
     cudaStreamSynchronize(b->d2h_stream);
     cudaGetLastError();
-    b->busy = false; b->counts_ready = false; b->outputs_enqueued = false;
+    b->busy = false; b->counts_ready = false; b->outputs_enqueued = false; b->counts_enqueued = false;
   };
   const bool first = !b->counts_ready;
   if (!b->counts_ready && b->fetch_counts(b->stream, err)) { drop_gof(); return ctx->fail(); }
+  // Result copies of the pieces BEHIND this one (other devices of the same GOF, later GOFs) are enqueued as soon as their
+  // kernels have finished, not when their turn comes: otherwise the D2H transfers of a GOF sharded over N devices would run
+  // one device after the other, in hand-out order.  Failures of those pieces are left for their own turn.
+  {
+    Batch* seen = b;
+    for (const PendingFrame& q : ctx->pending) {
+      if (q.batch == seen) continue;
+      seen = q.batch;
+      if (!seen->counts_ready && !seen->outputs_enqueued && seen->counts_arrived()) {
+        Err e2;
+        if (seen->finish_counts(seen->stream, e2) == TMC2_OK && !ctx->device_output) seen->enqueue_outputs(e2);
+        else if (e2.st != TMC2_OK) { seen->counts_ready = false; seen->failed_early = e2; }
+      }
+    }
+  }
+  if (b->failed_early.st != TMC2_OK) { err = b->failed_early; b->failed_early = Err(); drop_gof(); return ctx->fail(); }
   const double t_counts = tc.lap();
   if (ctx->device_output) {
     // device-resident hand-off: the counts copy was enqueued behind the last kernel of the GOF, so every frame is complete
