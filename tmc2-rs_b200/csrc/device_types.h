@@ -205,31 +205,40 @@ constexpr uint32_t kOffRawOcc = kOffRawV + 256;                  // [8 rows][32]
                                                                  // row 16-byte aligned): the block's 4x4 samples plus the ring around
                                                                  // them that the boundary classes look at
 constexpr uint32_t kRawBytes = kOffRawOcc + 256;
-//   ... reused after the tables are built (smoothing only):
-constexpr uint32_t kOffMemo = 0;                                 // [2][32] u32: cells the slot has already claimed
-constexpr uint32_t kOffTab = kOffMemo + 256;                     // [128] uint2: the slot's geometry-cell table (fast smoothing grids)
-constexpr uint32_t kOffList = kOffTab + 1024;                    // [520] u16 (fast smoothing grids): run-relative indices of the slot's
-                                                                 // type-1 boundary points from the front, type-2 from the back
 constexpr uint32_t kListEntries = 520;
-static_assert(kOffList + 2 * kListEntries <= kRawBytes, "the smoothing state fits the RAW area");
-//   per-pixel tables of the block in PATCH raster order (rank = v1*16 + u1):
-constexpr uint32_t kOffPt = kRawBytes;                           // [16 rows][17][2] u32: n | Y << 16 of map 0 / map 1 (17th pair of a row: padding)
-constexpr uint32_t kOffBar = kOffPt + 2176 - 8;                  // the warp's mbarrier sits in the padding pair of the last table row
-constexpr uint32_t kOffTerm = kOffPt + 2176;                     // [64][2] uint4: chroma term of (chroma sample, map)
-constexpr uint32_t kSrcBytes = 1040;                             // [3 + 512 (+ slack)] u16: output point -> rank << 1 | map | term << 9,
-                                                                 // entry i = point i - (run_base & 3) of the run (the run starts
-                                                                 // at the same phase of a 4-point group as in the frame).  Without
-                                                                 // smoothing the list lives in the (dead) RAW area.
-constexpr uint32_t kOffSrcSmooth = kOffTerm + 2048;
-constexpr uint32_t kOffSrcPlain = 0;
-constexpr uint32_t kOffCntSmooth = kOffSrcSmooth + kSrcBytes;    // [256] u8: points of the pixel (0..2) | boundary class << 2
-constexpr uint32_t kOffCntPlain = kOffSrcPlain + kSrcBytes;      // (RAW area, geometry / luma part: read into registers before anything is stored)
-constexpr uint32_t kBmpBytes = 128;                              // after the counts (smoothing / debug layout): [32] u32: 20x20 occupancy bitmap
-                                                                 // rows (canvas axes); later the list of non-empty cell-table entries
-constexpr uint32_t kWarpSmemSmooth = (kOffCntSmooth + 256 + kBmpBytes + 127) / 128 * 128;
-constexpr uint32_t kWarpSmemPlain = (kOffTerm + 2048 + 127) / 128 * 128;
-static_assert(kOffCntPlain + 256 <= kOffRawU, "plain layout: list and counts overwrite only the geometry / luma tiles");
-static_assert(kOffPt % 16 == 0 && kOffTerm % 16 == 0 && kOffSrcSmooth % 16 == 0 && kOffCntSmooth % 16 == 0 && kOffCntPlain % 16 == 0 && kOffTab % 16 == 0, "alignment");
+constexpr uint32_t kSrcBytes = 1040;
+// The rest of a warp's shared memory depends on the instantiation (byte offsets inside the warp's region):
+//   pt    [16 rows][17][2] u32: per-pixel table in PATCH raster order (rank = v1*16 + u1): n | Y << 16 of map 0 / map 1; the 17th
+//         pair of a row is padding (bank conflicts), and the warp's mbarrier (`bar`) sits in the padding pair of the last row
+//   term  [64][2] uint4: chroma term of (chroma sample, map)
+//   src   [3 + 512 (+ slack)] u16: output point -> rank << 1 | map | term << 9; entry i = point i - (run_base & 3) of the run
+//         (the run starts at the same phase of a 4-point group as in the frame)
+//   cnt   [256] u8: points of the pixel (0..2) | boundary class << 2
+//   bmp   [32] u32: 20x20 occupancy bitmap rows (canvas axes); later the list of non-empty cell-table entries
+//   memo  [2][32] u32: cells the slot has already claimed (smoothing)
+//   tab   [128] uint2: the slot's geometry-cell table; list [520] u16: run-relative indices of the slot's type-1 boundary points
+//         from the front, type-2 from the back (fast smoothing grids)
+// Whatever is only needed AFTER the tables have been built lives in the RAW area (dead by then):
+//   plain  (no smoothing, no debug streams): src and cnt in the RAW area                                         7 040 B
+//   fast   (smoothing, dense power-of-two grids): RAW region of 3 104 B holds tab, list and src; memo takes the place of
+//          cnt once the point list has been built                                                                7 808 B
+//   wide   (debug streams, generic smoothing grids: boundary classes are looked up per point): memo in the RAW area 8 576 B
+struct EmitLayout { uint32_t raw, pt, bar, term, src, cnt, bmp, memo, tab, list, bytes; };
+__host__ __device__ constexpr EmitLayout emit_layout(bool smooth, bool debug, bool fast) {
+  EmitLayout l{};
+  const bool compact = smooth && fast && !debug, plain = !smooth && !debug;
+  l.raw = compact ? 1024 + 2 * kListEntries + kSrcBytes : kRawBytes;
+  l.pt = l.raw; l.bar = l.pt + 2176 - 8; l.term = l.pt + 2176;
+  uint32_t end = l.term + 2048;
+  if (plain) { l.src = 0; l.cnt = kSrcBytes; l.bmp = 0; l.memo = 0; l.tab = 0; l.list = 0; }
+  else if (compact) { l.tab = 0; l.list = 1024; l.src = 1024 + 2 * kListEntries; l.cnt = end; l.memo = l.cnt; l.bmp = end + 256; end += 256 + 128; }
+  else { l.memo = 0; l.tab = 256; l.list = 1280; l.src = end; l.cnt = end + kSrcBytes; l.bmp = l.cnt + 256; end = l.bmp + 128; }
+  l.bytes = (end + 127) / 128 * 128;
+  return l;
+}
+static_assert(emit_layout(false, false, false).bytes == 7040 && emit_layout(true, false, true).bytes == 7808 && emit_layout(true, true, false).bytes == 8576, "layout sizes");
+static_assert(emit_layout(false, false, false).cnt + 256 <= kOffRawU, "plain layout: list and counts overwrite only the geometry / luma tiles");
+static_assert(emit_layout(true, false, true).raw >= kRawBytes && emit_layout(true, false, true).src % 16 == 0, "fast layout");
 #ifndef TMC2_EMIT_WARPS
 #define TMC2_EMIT_WARPS 4
 #endif

@@ -864,11 +864,11 @@ struct SmoothState {
   uint32_t kmin, bad, mul;       // local cell = key - kmin (valid iff no bit of `bad`); entry = (local * mul) >> 24
 
   __device__ __forceinline__ void init(const UnpackArgs& a, uint32_t frame_, uint32_t fig_, uint32_t patch_, uint32_t lane_,
-                                       uint32_t* memo_, uint8_t* scratch_, bool with_table) {
+                                       uint32_t* memo_, uint32_t* tab_, uint8_t* scratch_, bool with_table) {
     frame = frame_; fig = fig_; patch = patch_; lane = lane_; lbase = 0; n_done = 0;
     memo = memo_; scratch = scratch_;
     memo[lane] = kCellEmpty; memo[32 + lane] = kCellEmpty;
-    tab = memo_ + 64;
+    tab = tab_;
     if (with_table) {
       reinterpret_cast<uint4*>(tab)[lane] = make_uint4(0, 0, 0, 0);
       reinterpret_cast<uint4*>(tab)[32 + lane] = make_uint4(0, 0, 0, 0);
@@ -1215,7 +1215,7 @@ __device__ __forceinline__ void boundary_masks_raw(const UnpackArgs& a, const Wo
 #define TMC2_EMIT_CTAS 7
 #endif
 #ifndef TMC2_EMIT_CTAS_SMOOTH
-#define TMC2_EMIT_CTAS_SMOOTH 6
+#define TMC2_EMIT_CTAS_SMOOTH 7
 #endif
 
 // One block-aligned slot.  `release_raw()` is called exactly when the RAW area has been read for the last time.
@@ -1224,13 +1224,13 @@ template <bool kSmooth, bool kDebug, bool kFast, bool kAttr>
 __device__ __forceinline__ void emit_fast_slot(const UnpackArgs& a, const WorkRec& R, const DevPatch& P, uint8_t* wsm, uint32_t lane) {
   const uint32_t total = R.total, run_base = R.base, frame = R.frame;
   const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
-  uint32_t* s_pt = reinterpret_cast<uint32_t*>(wsm + kOffPt);
-  uint4* s_term = reinterpret_cast<uint4*>(wsm + kOffTerm);
-  // debug streams look boundary classes up per point: those instantiations keep the smoothing layout
-  constexpr bool kWide = kSmooth || kDebug;
-  uint16_t* s_src = reinterpret_cast<uint16_t*>(wsm + (kWide ? kOffSrcSmooth : kOffSrcPlain));
-  uint8_t* s_cnt = wsm + (kWide ? kOffCntSmooth : kOffCntPlain);
-  uint32_t* s_bmp = reinterpret_cast<uint32_t*>(s_cnt + 256);
+  constexpr EmitLayout LY = emit_layout(kSmooth, kDebug, kFast);
+  constexpr bool kWide = kSmooth || kDebug;              // (plain layout: list and counts live in the dead RAW area)
+  uint32_t* s_pt = reinterpret_cast<uint32_t*>(wsm + LY.pt);
+  uint4* s_term = reinterpret_cast<uint4*>(wsm + LY.term);
+  uint16_t* s_src = reinterpret_cast<uint16_t*>(wsm + LY.src);
+  uint8_t* s_cnt = wsm + LY.cnt;
+  uint32_t* s_bmp = reinterpret_cast<uint32_t*>(wsm + LY.bmp);
 
   constexpr bool has_attr = kAttr;
   const bool want_bt = kSmooth || (kDebug && a.out.btype != nullptr);
@@ -1367,7 +1367,7 @@ __device__ __forceinline__ void emit_fast_slot(const UnpackArgs& a, const WorkRe
   // which two short loops after the point loop work off with full warps -- the point loop itself does not look at classes.
   constexpr bool kLists = kSmooth && kFast;
   const uint32_t a4 = run_base & 3u;
-  uint16_t* s_list = reinterpret_cast<uint16_t*>(wsm + kOffList);
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(wsm + LY.list);
   uint32_t n_type1 = 0, n_type2 = 0;
   {
     const uint2 cb = *reinterpret_cast<const uint2*>(s_cnt + 8u * lane);
@@ -1438,7 +1438,8 @@ __device__ __forceinline__ void emit_fast_slot(const UnpackArgs& a, const WorkRe
 
   SmoothState S;
   if (kSmooth) {
-    S.init(a, frame, fig, patch, lane, reinterpret_cast<uint32_t*>(wsm + kOffMemo), reinterpret_cast<uint8_t*>(s_bmp), kFast);
+    S.init(a, frame, fig, patch, lane, reinterpret_cast<uint32_t*>(wsm + LY.memo), reinterpret_cast<uint32_t*>(wsm + LY.tab),
+           reinterpret_cast<uint8_t*>(s_bmp), kFast);
     if (n_boundary) {
       const uint32_t lbase = __shfl_sync(kFull, lbase0, 0);
       if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
@@ -1592,8 +1593,9 @@ __global__ void __launch_bounds__(kEmitWarps * 32, kSmooth ? TMC2_EMIT_CTAS_SMOO
 emit_kernel(const __grid_constant__ UnpackArgs a, const __grid_constant__ TileMaps tm, uint32_t slot_begin, uint32_t slot_end) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-  uint8_t* wsm = smem + (size_t)warp * ((kSmooth || kDebug) ? kWarpSmemSmooth : kWarpSmemPlain);
-  void* bar = wsm + kOffBar;
+  constexpr EmitLayout LY = emit_layout(kSmooth, kDebug, kFast);
+  uint8_t* wsm = smem + (size_t)warp * LY.bytes;
+  void* bar = wsm + LY.bar;
   const uint32_t lpos = slot_begin + blockIdx.x * kEmitWarps + warp;
   if (lpos >= slot_end) return;
   uint32_t mode;
@@ -1996,7 +1998,7 @@ int launch_compact_owned(const UnpackArgs& a, void* stream) {
 
 template <bool kSmooth, bool kDebug, bool kFast, bool kAttr>
 static int launch_emit_t(const UnpackArgs& a, const TileMaps& tm, uint32_t slot_begin, uint32_t slot_end, cudaStream_t s) {
-  const size_t smem = (size_t)((kSmooth || kDebug) ? kWarpSmemSmooth : kWarpSmemPlain) * kEmitWarps;
+  const size_t smem = (size_t)emit_layout(kSmooth, kDebug, kFast).bytes * kEmitWarps;
   auto kern = emit_kernel<kSmooth, kDebug, kFast, kAttr>;
   static bool configured[64] = {};               // the dynamic shared memory limit is a per-device attribute of the function
   int dev = 0;
