@@ -337,7 +337,7 @@ def main():
             r.reconstruct(t.cuda_stream)
     points_by_size = {sz: int(residents[sz][0].counts().sum()) for sz in views}
     points_per_step = sum(points_by_size[sz] for sz in sizes)            # this rank, one pass
-    residents[main_sz][0].reconstruct(tstream.cuda_stream)
+    residents[main_sz][0].reconstruct(tstream.cuda_stream, timed=True)
     launches_per_gof, alg_bytes, _ = ctx.last_launch_info()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -360,7 +360,7 @@ def main():
     # reading them does not serialise the timed loop above
     unpack_ms, stage_acc = [], {}
     for _ in range(5):
-        residents[main_sz][0].reconstruct(tstream.cuda_stream)
+        residents[main_sz][0].reconstruct(tstream.cuda_stream, timed=True)
         st = ctx.last_stage_ms()
         unpack_ms.append(st["unpack"])
         for kk, v in st.items():

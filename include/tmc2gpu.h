@@ -233,6 +233,10 @@ TMC2_API tmc2_status tmc2gpu_release_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out
 typedef struct tmc2_resident tmc2_resident;
 TMC2_API tmc2_status tmc2gpu_upload_gof(tmc2gpu_ctx* ctx, const tmc2_gof* gof, tmc2_resident** out);
 TMC2_API tmc2_status tmc2gpu_reconstruct_resident(tmc2gpu_ctx* ctx, tmc2_resident* r, void* cuda_stream);
+/* Same with flags.  Relaunches of a resident GOF without smoothing are replayed from a CUDA graph (one API call instead of
+ * a dozen); TMC2_LAUNCH_TIMED forces the ordinary launch sequence, which records the events tmc2gpu_last_stage_ms reads. */
+#define TMC2_LAUNCH_TIMED 1u
+TMC2_API tmc2_status tmc2gpu_reconstruct_resident_ex(tmc2gpu_ctx* ctx, tmc2_resident* r, void* cuda_stream, uint32_t flags);
 TMC2_API tmc2_status tmc2gpu_resident_counts(tmc2gpu_ctx* ctx, tmc2_resident* r, uint64_t* point_counts /*[frame_count]*/);
 TMC2_API tmc2_status tmc2gpu_resident_fetch(tmc2gpu_ctx* ctx, tmc2_resident* r, uint32_t frame,
                                             uint16_t* positions, uint8_t* colors, uint64_t capacity_points);

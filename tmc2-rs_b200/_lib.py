@@ -30,6 +30,7 @@ SYMBOLS = [
     ("tmc2gpu_release_frame", C.c_int, [_P, C.POINTER(abi.CFrameOut)]),
     ("tmc2gpu_upload_gof", C.c_int, [_P, C.POINTER(abi.CGof), C.POINTER(_P)]),
     ("tmc2gpu_reconstruct_resident", C.c_int, [_P, _P, _P]),
+    ("tmc2gpu_reconstruct_resident_ex", C.c_int, [_P, _P, _P, C.c_uint32]),
     ("tmc2gpu_resident_counts", C.c_int, [_P, _P, C.POINTER(C.c_uint64)]),
     ("tmc2gpu_resident_fetch", C.c_int, [_P, _P, C.c_uint32, _P, _P, C.c_uint64]),
     ("tmc2gpu_free_resident", C.c_int, [_P, _P]),

@@ -30,6 +30,7 @@ ORIENTATION_REFERENCE, ORIENTATION_SPEC = 0, 1
 
 CTX_TWO_PASS_SCAN = 1
 CTX_DEVICE_OUTPUT = 2
+LAUNCH_TIMED = 1
 
 
 class Tmc2Error(RuntimeError):

@@ -201,9 +201,11 @@ class Resident:
     def __init__(self, ctx: Context, h, frames: int):
         self.ctx, self.h, self.frames = ctx, h, frames
 
-    def reconstruct(self, cuda_stream: int = 0):
-        self.ctx.check(self.ctx.lib.tmc2gpu_reconstruct_resident(self.ctx.h, self.h, C.c_void_p(cuda_stream)),
-                       "reconstruct_resident")
+    def reconstruct(self, cuda_stream: int = 0, timed: bool = False):
+        """Launch the reconstruction of the resident GOF on `cuda_stream`.  `timed`: take the ordinary launch sequence (which
+        records the stage-timing events) even where a CUDA-graph replay would be used."""
+        self.ctx.check(self.ctx.lib.tmc2gpu_reconstruct_resident_ex(self.ctx.h, self.h, C.c_void_p(cuda_stream),
+                                                                    abi.LAUNCH_TIMED if timed else 0), "reconstruct_resident")
 
     def counts(self) -> np.ndarray:
         out = (C.c_uint64 * max(self.frames, 1))()

@@ -405,6 +405,8 @@ struct Batch {
   std::chrono::steady_clock::time_point t_submit;   // TMC2_TRACE bookkeeping
   uint64_t t_epoch = 0;                             // submit call that made this batch busy
   Err failed_early;                                 // a failure found while this batch was not yet at the head of the queue
+  cudaGraphExec_t graph_exec = nullptr;             // resident relaunches without smoothing: the whole launch sequence as one graph
+  bool graph_tried = false;
   double trace_wait_ms = 0;
 
   ~Batch() { destroy(); }
@@ -428,6 +430,7 @@ struct Batch {
     ev_emit.clear();
     for (auto e : ev_post) cudaEventDestroy(e);
     ev_post.clear();
+    if (graph_exec) cudaGraphExecDestroy(graph_exec), graph_exec = nullptr;
     if (aux_stream) cudaStreamDestroy(aux_stream), aux_stream = nullptr;
     if (ev_tables_clean) cudaEventDestroy(ev_tables_clean), ev_tables_clean = nullptr;
     if (stream) cudaStreamDestroy(stream), stream = nullptr;
@@ -864,16 +867,17 @@ struct Batch {
   }
 
   // ---- kernels ---------------------------------------------------------------------------------------------------
-  tmc2_status launch(cudaStream_t s, Err& err) {
+  // `timed`: record the stage-timing events (not inside a CUDA graph capture: captured events cannot be timed)
+  tmc2_status launch(cudaStream_t s, Err& err, bool timed = true) {
     CU(cudaSetDevice(device));
     kernel_launch_count_reset();
     UnpackArgs a = make_args();
-    CU(cudaEventRecord(ev[0], s));
+    if (timed) CU(cudaEventRecord(ev[0], s));
     CU(cudaMemsetAsync(d_b2p.p, 0, std::max<size_t>((size_t)F * bw * bh * 4, 4), s));
     CU(cudaMemsetAsync(d_count.p, 0, std::max<size_t>((size_t)F * 4, 4), s));
     KL(launch_block_to_patch(a, n_slots, s));
     KL(launch_compact_owned(a, s));
-    CU(cudaEventRecord(ev[1], s));
+    if (timed) CU(cudaEventRecord(ev[1], s));
     const bool smooth = smoothing_geo || smoothing_col;
     const bool dbg = (want & WANT_DEBUG) != 0;
     CU(cudaMemsetAsync(d_changed.p, 0, std::max<size_t>((size_t)F * 16, 16), s));
@@ -882,16 +886,16 @@ struct Batch {
       CU(cudaMemsetAsync(d_slist_count.p, 0, std::max<size_t>((size_t)F * 4, 4), s));
     }
     // unpack = count (points per owned slot) -> slot scan (run starts per frame, frame totals) -> emit
-    CU(cudaEventRecord(ev[6], s));
+    if (timed) CU(cudaEventRecord(ev[6], s));
     KL(launch_count(a, 0, n_tiles, s));
     KL(launch_slot_scan(a, s));
-    CU(cudaEventRecord(ev[7], s));
+    if (timed) CU(cudaEventRecord(ev[7], s));
     if (!smooth) {
       while (ev_grp.size() < 2) { cudaEvent_t e; CU(cudaEventCreate(&e)); ev_grp.push_back(e); }
       n_groups = 1;
-      CU(cudaEventRecord(ev_grp[0], s));
+      if (timed) CU(cudaEventRecord(ev_grp[0], s));
       KL(launch_emit(a, tile_maps, false, 0, n_tiles, s));
-      CU(cudaEventRecord(ev_grp[1], s));
+      if (timed) CU(cudaEventRecord(ev_grp[1], s));
     } else {
       // frame groups: unpack (+ cell statistics + boundary lists) -> filter -> clear, tables stay hot in L2
       const uint32_t GF = group_frames_eff;
@@ -917,9 +921,9 @@ struct Batch {
         use_set(a.sm.col, col0, set, sizeof(ColCell));
         if (gi >= 2) CU(cudaStreamWaitEvent(s, ev_post[gi - 2], 0));          // this table set has been cleared
         if (clear_pending) { CU(cudaStreamWaitEvent(s, ev_tables_clean, 0)); clear_pending = false; }   // ... by the previous launch
-        CU(cudaEventRecord(ev_grp[2 * gi], s));
+        if (timed) CU(cudaEventRecord(ev_grp[2 * gi], s));
           KL(launch_emit(a, tile_maps, true, h_ftb[f0], h_ftb[f1], s));
-        CU(cudaEventRecord(ev_grp[2 * gi + 1], s));
+        if (timed) CU(cudaEventRecord(ev_grp[2 * gi + 1], s));
         if (dbg) {
           CU(cudaMemcpyAsync(d_pos_pre.as<uint8_t>() + (size_t)f0 * cap * 6, d_pos.as<uint8_t>() + (size_t)f0 * cap * 6,
                              (size_t)(f1 - f0) * cap * 6, cudaMemcpyDeviceToDevice, s));
@@ -948,13 +952,13 @@ struct Batch {
       if (n_groups >= 2)
         for (uint32_t gi = n_groups - 2; gi < n_groups; ++gi) CU(cudaStreamWaitEvent(s, ev_post[gi], 0));
     }
-    CU(cudaEventRecord(ev[2], s));
+    if (timed) CU(cudaEventRecord(ev[2], s));
     if (want & WANT_OCC_FULL) KL(launch_upsample(a, d_occ_full.as<uint8_t>(), s));
     if (dbg && !smooth) {
       CU(cudaMemcpyAsync(d_pos_pre.p, d_pos.p, (size_t)F * cap * 6, cudaMemcpyDeviceToDevice, s));
       if (a.out.yuv) CU(cudaMemcpyAsync(d_yuv_pre.p, d_yuv.p, (size_t)F * cap * 6, cudaMemcpyDeviceToDevice, s));
     }
-    CU(cudaEventRecord(ev[3], s)); CU(cudaEventRecord(ev[4], s)); CU(cudaEventRecord(ev[5], s));
+    if (timed) CU(cudaEventRecord(ev[3], s)); if (timed) CU(cudaEventRecord(ev[4], s)); if (timed) CU(cudaEventRecord(ev[5], s));
     launches = (uint32_t)kernel_launch_count_reset();
     counts_ready = false; outputs_enqueued = false; counts_enqueued = false;
     return TMC2_OK;
@@ -1410,12 +1414,49 @@ tmc2_status tmc2gpu_upload_gof(tmc2gpu_ctx* ctx, const tmc2_gof* gof, tmc2_resid
 }
 
 tmc2_status tmc2gpu_reconstruct_resident(tmc2gpu_ctx* ctx, tmc2_resident* r, void* cuda_stream) {
+  return tmc2gpu_reconstruct_resident_ex(ctx, r, cuda_stream, 0);
+}
+
+tmc2_status tmc2gpu_reconstruct_resident_ex(tmc2gpu_ctx* ctx, tmc2_resident* r, void* cuda_stream, uint32_t flags) {
   if (!ctx || !r) return TMC2_ERR_INVALID_ARG;
   Err& err = ctx->err;
   err = Err();
   Batch* b = r->batch.get();
   cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
+  // Relaunches of a resident GOF are the same launch sequence every time: without smoothing (no auxiliary stream, nothing
+  // that outlives the launch) it is captured once into a CUDA graph and replayed with one API call -- for a small GOF
+  // (BASELINE config 1: one frame, 8 launches + 3 memsets of a few microseconds each) the CPU launch cost is what bounds the
+  // rate.  The first launch and every TMC2_GRAPH=0 launch take the ordinary path, which also records the stage-timing events.
+  static const bool graphs = [] { const char* e = getenv("TMC2_GRAPH"); return !e || atoi(e) != 0; }();
+  const bool eligible = graphs && !(flags & TMC2_LAUNCH_TIMED) && !(b->smoothing_geo || b->smoothing_col) && b->want == 0;
+  if (eligible && b->graph_exec) {
+    auto replay = [&]() -> tmc2_status {
+      CU(cudaSetDevice(b->device));
+      CU(cudaGraphLaunch(b->graph_exec, s));
+      b->counts_ready = false; b->outputs_enqueued = false; b->counts_enqueued = false;
+      return TMC2_OK;
+    };
+    if (replay()) return ctx->fail();
+    ctx->last_batch = b;
+    return TMC2_OK;
+  }
   if (b->launch(s, err)) return ctx->fail();
+  if (eligible && !b->graph_tried) {
+    // capture the NEXT launches (this one ran directly: buffers, function attributes and stage times are in place)
+    b->graph_tried = true;
+    cudaGraph_t g = nullptr;
+    const uint32_t launches = b->launches;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      Err e2;
+      const tmc2_status st = b->launch(s, e2, false);
+      const cudaError_t ce = cudaStreamEndCapture(s, &g);
+      if (st == TMC2_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&b->graph_exec, g, 0) != cudaSuccess) b->graph_exec = nullptr;
+      if (st != TMC2_OK || ce != cudaSuccess) b->graph_exec = nullptr;
+      if (g) cudaGraphDestroy(g);
+    }
+    cudaGetLastError();
+    b->launches = launches;
+  }
   ctx->last_batch = b;
   return TMC2_OK;
 }
