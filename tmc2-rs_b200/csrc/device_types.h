@@ -187,6 +187,10 @@ struct UnpackArgs {
   const uint32_t* block_to_patch;     // [F][bw*bh]
   WorkRec*        work;               // [n_tiles*kWarpsPerTile] compacted owned slots of each frame, from frame_tile_begin[f]*8
   uint32_t*       owned_count;        // [F]
+  uint16_t*       slot_bt;            // [n_tiles*kWarpsPerTile][32] boundary classes of a slot's pixels in canvas layout (lane = row, half):
+                                      // type-1 mask | type-2 mask << 8, written by count_kernel when want_btype
+  uint32_t*       slot_bbase;         // [n_tiles*kWarpsPerTile] count_kernel: type-1 boundary points of the slot; slot_scan_kernel: where its
+                                      // entries start in the frame's boundary list (exclusive prefix in slot order)
   uint32_t*       frame_count;        // [F] points per frame
   int*            err;                // device error flag (0 ok)
   SmoothArgs sm;                      // used by the smoothing instantiation only

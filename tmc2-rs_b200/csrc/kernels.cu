@@ -723,23 +723,38 @@ __device__ __noinline__ void generic_slot_emit(const UnpackArgs& a, uint32_t pid
 #ifndef TMC2_COUNT_MINCTA
 #define TMC2_COUNT_MINCTA 8
 #endif
+__device__ __forceinline__ void boundary_masks(const UnpackArgs& a, const WorkRec& R, uint32_t lane, uint32_t* s_bmp, uint32_t& bt1,
+                                               uint32_t& bt2);   // below
 __global__ void __launch_bounds__(kWarpsPerTile * 32, TMC2_COUNT_MINCTA) count_kernel(const __grid_constant__ UnpackArgs a, uint32_t tile_offset) {
+  __shared__ uint32_t s_bmp_all[kWarpsPerTile][32];
   const uint32_t lane = lane_id();
   const uint32_t lpos = (blockIdx.x + tile_offset) * kWarpsPerTile + (threadIdx.x >> 5);
   uint32_t mode;
   const WorkRec R = load_work(a.work + lpos, &mode);
   if (R.pid == kNoPatch) return;                                   // unused tail of the frame's region (total stays 0)
-  uint32_t total;
+  uint32_t total, n_boundary = 0;
   if (slot_is_fast(a, R)) {
     DevPatch P;
     P.d1 = R.d1; P.mode = (uint8_t)mode;                 // copied into the work record: no patch load on this path
     CanvasBlock L;
     load_geometry(a, R, P, lane, L);
     total = __reduce_add_sync(kFull, __popc(L.m1) + __popc(L.m2));
+    if (a.want_btype) {
+      // K5 here, where registers and warps are plentiful: the emit pass only reads the two 8-bit masks of its lane back.  The
+      // type-1 points of the slot are counted as well, so that the scan can hand every slot its place in the frame's boundary list.
+      uint32_t bt1, bt2;
+      boundary_masks(a, R, lane, s_bmp_all[threadIdx.x >> 5], bt1, bt2);
+      a.slot_bt[(uint64_t)lpos * 32u + lane] = (uint16_t)(bt1 | (bt2 << 8));
+      const uint32_t b1 = L.m1 & bt1;
+      n_boundary = __reduce_add_sync(kFull, __popc(b1) + __popc(b1 & L.m2));
+    }
   } else {
-    total = generic_slot_count(a, R.pid, R.frame, R.u0b, R.v0b);
+    total = generic_slot_count(a, R.pid, R.frame, R.u0b, R.v0b);   // (generic slots append to the boundary list with atomics)
   }
-  if (lane == 0) a.work[lpos].total = total;
+  if (lane == 0) {
+    a.work[lpos].total = total;
+    if (a.want_btype) a.slot_bbase[lpos] = n_boundary;
+  }
 }
 
 // ---- pass 2: where every run starts.  One CTA per frame; the scan domain is the frame's owned-slot list ---------------------
@@ -766,6 +781,30 @@ __global__ void __launch_bounds__(1024) slot_scan_kernel(const UnpackArgs a) {
     carry += total;
   }
   if (threadIdx.x == 0) a.frame_count[f] = carry;                // tile.total_number_of_regular_points, codec.rs:482
+  if (a.want_btype && a.sm.blist_count != nullptr) {
+    // the same for the type-1 boundary points: every block-aligned slot gets a fixed range of the frame's boundary list (no
+    // atomics, and the list comes out in slot order); generic slots append behind it
+    __syncthreads();
+    uint32_t bcarry = 0;
+    for (uint32_t b = 0; b < n; b += 1024 * kPerThread) {
+      const uint32_t first = b + threadIdx.x * kPerThread;
+      uint32_t v[kPerThread], sum = 0;
+#pragma unroll
+      for (int i = 0; i < kPerThread; ++i) {
+        v[i] = first + i < n ? a.slot_bbase[s0 + first + i] : 0u;
+        sum += v[i];
+      }
+      uint32_t total;
+      uint32_t base = bcarry + cta_exclusive_scan(sum, s_w, total);
+#pragma unroll
+      for (int i = 0; i < kPerThread; ++i) {
+        if (first + i < n) a.slot_bbase[s0 + first + i] = base;
+        base += v[i];
+      }
+      bcarry += total;
+    }
+    if (threadIdx.x == 0) a.sm.blist_count[f] = bcarry;
+  }
 }
 
 // one row of the 20x20 occupancy bitmap (block + 2-pixel margin): bit cc = pixel (x0 + sx*cc, y0 + sy*cc) is occupied, or
@@ -1169,47 +1208,9 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, void* b
 // occupancy video with ordinary loads)
 __device__ __forceinline__ bool occ_by_tma(const UnpackArgs& a) { return a.prec_shift == 2 && ((a.W | a.H) & 3u) == 0u; }
 
-// K5 for a block-aligned slot whose occupancy ring sits in the RAW area (box origin = sample (occ_box_x(bx), by*4 - 2); samples
-// outside the video arrive as zero from the TMA unit and count as occupied here, like pixels outside the image)
+// first sample column of the occupancy box of block column bx (a multiple of 16 samples: the TMA unit wants the first byte
+// of a box row 16-byte aligned)
 __device__ __forceinline__ int32_t occ_box_x(uint32_t bx) { return ((int32_t)bx * 4 - 1) & ~15; }
-__device__ __forceinline__ void boundary_masks_raw(const UnpackArgs& a, const WorkRec& R, uint32_t lane, const uint8_t* raw_occ,
-                                                   uint32_t* s_bmp, uint32_t& bt1, uint32_t& bt2) {
-  const int32_t W = (int32_t)a.W, H = (int32_t)a.H;
-  const int32_t h = (int32_t)(lane & 1u), r = (int32_t)(lane >> 1);
-  const int32_t bx16 = (int32_t)R.bx * 16, by16 = (int32_t)R.by * 16;
-  const int32_t cw = W >> 2, ch = H >> 2, cxb = (int32_t)R.bx * 4 - 1, cyb = (int32_t)R.by * 4 - 1;
-  const int32_t col_off = cxb - occ_box_x(R.bx);
-  auto cell = [&](int32_t row, int32_t col) -> bool {
-    const int32_t cx = cxb + col, cy = cyb + row;
-    if (cx < 0 || cy < 0 || cx >= cw || cy >= ch) return true;
-    return raw_occ[(row + 1) * 32 + col + col_off] != 0;
-  };
-  const int32_t i = (int32_t)lane;
-  const uint32_t b0 = __ballot_sync(kFull, i < 30 ? cell(i / 6, i % 6) : false);
-  const uint32_t b1 = __ballot_sync(kFull, i < 6 ? cell(5, i) : false);
-  const uint32_t crow = (lane + 2u) >> 2;
-  const uint32_t m6 = crow < 5u ? (b0 >> (6u * crow)) & 63u : (b1 & 63u);
-  const uint32_t row20 = ((m6 & 1u) ? 0x3u : 0u) | ((m6 & 2u) ? 0x3Cu : 0u) | ((m6 & 4u) ? 0x3C0u : 0u) |
-                         ((m6 & 8u) ? 0x3C00u : 0u) | ((m6 & 16u) ? 0x3C000u : 0u) | ((m6 & 32u) ? 0xC0000u : 0u);
-  if (lane < 20) s_bmp[lane] = row20;
-  __syncwarp();
-  const uint32_t r0 = s_bmp[r], r1 = s_bmp[r + 1], r2 = s_bmp[r + 2], r3 = s_bmp[r + 3], r4 = s_bmp[r + 4];
-  const uint32_t cross = r1 & r3 & (r2 >> 1) & (r2 << 1);    // bit c: the four neighbours of column c are occupied
-  const uint32_t all5 = r0 & r1 & r2 & r3 & r4;
-  const uint32_t full = all5 & (all5 >> 1) & (all5 >> 2) & (all5 << 1) & (all5 << 2);
-  const uint32_t sh = 8u * (uint32_t)h + 2u;
-  uint32_t border = 0;
-  if (R.bx == 0 || R.by == 0 || bx16 + 16 >= W || by16 + 16 >= H) {
-    const int32_t y = by16 + r;
-#pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
-      const int32_t x = bx16 + 8 * h + j;
-      if (x == 0 || y == 0 || x == W - 1 || y == H - 1) border |= 1u << j;
-    }
-  }
-  bt1 = ((~(cross >> sh)) & 0xFFu) | border;
-  bt2 = (~(full >> sh)) & 0xFFu & ~bt1;
-}
 
 #ifndef TMC2_EMIT_CTAS
 #define TMC2_EMIT_CTAS 7
@@ -1221,7 +1222,8 @@ __device__ __forceinline__ void boundary_masks_raw(const UnpackArgs& a, const Wo
 // One block-aligned slot.  `release_raw()` is called exactly when the RAW area has been read for the last time.
 // One block-aligned slot whose tiles have landed in the RAW area.
 template <bool kSmooth, bool kDebug, bool kFast, bool kAttr>
-__device__ __forceinline__ void emit_fast_slot(const UnpackArgs& a, const WorkRec& R, const DevPatch& P, uint8_t* wsm, uint32_t lane) {
+__device__ __forceinline__ void emit_fast_slot(const UnpackArgs& a, const WorkRec& R, const DevPatch& P, uint8_t* wsm, uint32_t lane,
+                                               uint32_t bt_word, uint32_t blist_base) {
   const uint32_t total = R.total, run_base = R.base, frame = R.frame;
   const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
   constexpr EmitLayout LY = emit_layout(kSmooth, kDebug, kFast);
@@ -1236,7 +1238,7 @@ __device__ __forceinline__ void emit_fast_slot(const UnpackArgs& a, const WorkRe
   const bool want_bt = kSmooth || (kDebug && a.out.btype != nullptr);
   const uint32_t h = lane & 1u, r = lane >> 1;
   const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
-  uint32_t n_boundary = 0, any_flag = 0, lbase0 = 0, nmin = 0;
+  uint32_t n_boundary = 0, any_flag = 0, nmin = 0;
 
   {
     // ---- (1): canvas layout: lane (r, h) = canvas row r, columns 8h .. 8h+7 -------------------------------------------
@@ -1253,16 +1255,13 @@ __device__ __forceinline__ void emit_fast_slot(const UnpackArgs& a, const WorkRe
     }
     CanvasBlock L;
     geometry_digest(a, P, g0, g1, m1, L);
-    uint32_t bt1 = 0, bt2 = 0;
-    if (want_bt) {
-      if (occ_by_tma(a)) boundary_masks_raw(a, R, lane, wsm + kOffRawOcc, s_bmp, bt1, bt2);
-      else boundary_masks(a, R, lane, s_bmp, bt1, bt2);
-    }
+    // K5: the boundary classes of the lane's 8 pixels were worked out by the count pass (slot_bt)
+    const uint32_t bt1 = want_bt ? (bt_word & 0xFFu) : 0u, bt2 = want_bt ? (bt_word >> 8) : 0u;
     if (kSmooth) {
-      const uint32_t b1 = L.m1 & bt1;
-      n_boundary = __reduce_add_sync(kFull, __popc(b1) + __popc(b1 & L.m2));
-      // room in the frame's boundary list for this slot; the answer is picked up right before the point loop
-      if (n_boundary && lane == 0) lbase0 = atomicAdd(&a.sm.blist_count[frame], n_boundary);
+      if (!(kFast)) {                       // generic grids append inside the point loop and check the list capacity up front
+        const uint32_t b1 = L.m1 & bt1;
+        n_boundary = __reduce_add_sync(kFull, __popc(b1) + __popc(b1 & L.m2));
+      }
       if (kFast && a.sm.geo.on) {
         // smallest normal coordinate among the slot's points (both maps; a skipped duplicate equals its map-0 point):
         // origin of the slot's cell table along the projection axis
@@ -1448,14 +1447,13 @@ __device__ __forceinline__ void emit_fast_slot(const UnpackArgs& a, const WorkRe
   if (kSmooth) {
     S.init(a, frame, fig, patch, lane, reinterpret_cast<uint32_t*>(wsm + LY.memo), reinterpret_cast<uint32_t*>(wsm + LY.tab),
            reinterpret_cast<uint8_t*>(s_bmp), kFast);
-    if (n_boundary) {
-      const uint32_t lbase = __shfl_sync(kFull, lbase0, 0);
-      if ((uint64_t)lbase + n_boundary > a.sm.blist_cap) {
-        if (lane == 0) atomicExch(a.err, 7);
-        return;
-      }
-      S.lbase = lbase;
+    // the slot's range of the frame's boundary list was fixed by the scan pass
+    if (kFast) n_boundary = n_type1;
+    if ((uint64_t)blist_base + n_boundary > a.sm.blist_cap) {
+      if (lane == 0) atomicExch(a.err, 7);
+      return;
     }
+    S.lbase = blist_base;
     if (kFast && a.sm.geo.on) S.table_origin(a.sm.geo, P, nmin, T00, B00, T00 + 15u * lodx, B00 + 15u * lody);
   }
 
@@ -1634,9 +1632,14 @@ emit_kernel(const __grid_constant__ UnpackArgs a, const __grid_constant__ TileMa
   }
   DevPatch P;
   load_patch_fields(a.patches + R.pid, P);                       // in flight together with the tiles
+  uint32_t bt_word = 0, blist_base = 0;
+  if (kSmooth || kDebug) {                                       // what the count / scan passes left for this slot
+    if (a.want_btype) bt_word = __ldg(a.slot_bt + (uint64_t)lpos * 32u + lane);
+    if (kSmooth) blist_base = __ldg(a.slot_bbase + lpos);
+  }
   __syncwarp();
   mbar_wait(bar, 0);
-  emit_fast_slot<kSmooth, kDebug, kFast, kAttr>(a, R, P, wsm, lane);
+  emit_fast_slot<kSmooth, kDebug, kFast, kAttr>(a, R, P, wsm, lane, bt_word, blist_base);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
