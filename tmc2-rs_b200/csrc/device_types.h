@@ -189,6 +189,7 @@ struct UnpackArgs {
   uint32_t*       owned_count;        // [F]
   uint16_t*       slot_bt;            // [n_tiles*kWarpsPerTile][32] boundary classes of a slot's pixels in canvas layout (lane = row, half):
                                       // type-1 mask | type-2 mask << 8, written by count_kernel when want_btype
+  uint16_t*       slot_nmin;          // [n_tiles*kWarpsPerTile] smallest normal coordinate among the slot's points (origin of its cell table)
   uint32_t*       slot_bbase;         // [n_tiles*kWarpsPerTile] count_kernel: type-1 boundary points of the slot; slot_scan_kernel: where its
                                       // entries start in the frame's boundary list (exclusive prefix in slot order)
   uint32_t*       frame_count;        // [F] points per frame

@@ -732,7 +732,7 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, TMC2_COUNT_MINCTA) count_k
   uint32_t mode;
   const WorkRec R = load_work(a.work + lpos, &mode);
   if (R.pid == kNoPatch) return;                                   // unused tail of the frame's region (total stays 0)
-  uint32_t total, n_boundary = 0;
+  uint32_t total, n_boundary = 0, nmin = 0;
   if (slot_is_fast(a, R)) {
     DevPatch P;
     P.d1 = R.d1; P.mode = (uint8_t)mode;                 // copied into the work record: no patch load on this path
@@ -747,13 +747,23 @@ __global__ void __launch_bounds__(kWarpsPerTile * 32, TMC2_COUNT_MINCTA) count_k
       a.slot_bt[(uint64_t)lpos * 32u + lane] = (uint16_t)(bt1 | (bt2 << 8));
       const uint32_t b1 = L.m1 & bt1;
       n_boundary = __reduce_add_sync(kFull, __popc(b1) + __popc(b1 & L.m2));
+      // smallest normal coordinate among the slot's points (both maps; a skipped duplicate equals its map-0 point): origin
+      // of the slot's cell table along the projection axis
+      uint32_t lo = 0xFFFFFFFFu;
+      const uint32_t inv = ~L.m1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t off = (((inv >> (2 * q)) & 1u) * 0xFFFFu) | (((inv >> (2 * q + 1)) & 1u) * 0xFFFF0000u);
+        lo = __vminu2(lo, __vminu2(L.n0p[q] | off, L.n1p[q] | off));
+      }
+      nmin = __reduce_min_sync(kFull, min(lo & 0xFFFFu, lo >> 16));
     }
   } else {
     total = generic_slot_count(a, R.pid, R.frame, R.u0b, R.v0b);   // (generic slots append to the boundary list with atomics)
   }
   if (lane == 0) {
     a.work[lpos].total = total;
-    if (a.want_btype) a.slot_bbase[lpos] = n_boundary;
+    if (a.want_btype) { a.slot_bbase[lpos] = n_boundary; a.slot_nmin[lpos] = (uint16_t)nmin; }
   }
 }
 
@@ -1223,7 +1233,7 @@ __device__ __forceinline__ int32_t occ_box_x(uint32_t bx) { return ((int32_t)bx 
 // One block-aligned slot whose tiles have landed in the RAW area.
 template <bool kSmooth, bool kDebug, bool kFast, bool kAttr>
 __device__ __forceinline__ void emit_fast_slot(const UnpackArgs& a, const WorkRec& R, const DevPatch& P, uint8_t* wsm, uint32_t lane,
-                                               uint32_t bt_word, uint32_t blist_base) {
+                                               uint32_t bt_word, uint32_t blist_base, uint32_t nmin) {
   const uint32_t total = R.total, run_base = R.base, frame = R.frame;
   const uint32_t fig = kSmooth ? frame - a.sm.group_first_frame : 0u;   // frame inside the smoothing group
   constexpr EmitLayout LY = emit_layout(kSmooth, kDebug, kFast);
@@ -1238,7 +1248,7 @@ __device__ __forceinline__ void emit_fast_slot(const UnpackArgs& a, const WorkRe
   const bool want_bt = kSmooth || (kDebug && a.out.btype != nullptr);
   const uint32_t h = lane & 1u, r = lane >> 1;
   const int32_t ax = R.ax, ay = R.ay, rx = R.rx, ry = R.ry;
-  uint32_t n_boundary = 0, any_flag = 0, nmin = 0;
+  uint32_t n_boundary = 0, any_flag = 0;
 
   {
     // ---- (1): canvas layout: lane (r, h) = canvas row r, columns 8h .. 8h+7 -------------------------------------------
@@ -1261,18 +1271,6 @@ __device__ __forceinline__ void emit_fast_slot(const UnpackArgs& a, const WorkRe
       if (!(kFast)) {                       // generic grids append inside the point loop and check the list capacity up front
         const uint32_t b1 = L.m1 & bt1;
         n_boundary = __reduce_add_sync(kFull, __popc(b1) + __popc(b1 & L.m2));
-      }
-      if (kFast && a.sm.geo.on) {
-        // smallest normal coordinate among the slot's points (both maps; a skipped duplicate equals its map-0 point):
-        // origin of the slot's cell table along the projection axis
-        uint32_t lo = 0xFFFFFFFFu;
-        const uint32_t inv = ~L.m1;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t off = (((inv >> (2 * q)) & 1u) * 0xFFFFu) | (((inv >> (2 * q + 1)) & 1u) * 0xFFFF0000u);
-          lo = __vminu2(lo, __vminu2(L.n0p[q] | off, L.n1p[q] | off));
-        }
-        nmin = __reduce_min_sync(kFull, min(lo & 0xFFFFu, lo >> 16));
       }
     }
 
@@ -1632,14 +1630,14 @@ emit_kernel(const __grid_constant__ UnpackArgs a, const __grid_constant__ TileMa
   }
   DevPatch P;
   load_patch_fields(a.patches + R.pid, P);                       // in flight together with the tiles
-  uint32_t bt_word = 0, blist_base = 0;
+  uint32_t bt_word = 0, blist_base = 0, nmin = 0;
   if (kSmooth || kDebug) {                                       // what the count / scan passes left for this slot
     if (a.want_btype) bt_word = __ldg(a.slot_bt + (uint64_t)lpos * 32u + lane);
-    if (kSmooth) blist_base = __ldg(a.slot_bbase + lpos);
+    if (kSmooth) { blist_base = __ldg(a.slot_bbase + lpos); nmin = __ldg(a.slot_nmin + lpos); }
   }
   __syncwarp();
   mbar_wait(bar, 0);
-  emit_fast_slot<kSmooth, kDebug, kFast, kAttr>(a, R, P, wsm, lane, bt_word, blist_base);
+  emit_fast_slot<kSmooth, kDebug, kFast, kAttr>(a, R, P, wsm, lane, bt_word, blist_base, nmin);
 }
 
 // ----------------------------------------------------------------------------------------------------------------

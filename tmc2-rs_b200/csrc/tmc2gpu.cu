@@ -376,7 +376,7 @@ struct Batch {
   std::vector<SlotRec> h_slot_rec;
   std::vector<uint32_t> h_tile_frame, h_ftb;
 
-  DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_count, d_err, d_work, d_owned_count, d_slot_bt, d_slot_bbase;
+  DevBuf d_occ, d_geo, d_ay, d_au, d_av, d_meta, d_b2p, d_count, d_err, d_work, d_owned_count, d_slot_bt, d_slot_bbase, d_slot_nmin;
   DevBuf d_pos, d_rgb, d_yuv, d_part, d_pix, d_bt, d_occ_full, d_pos_pre, d_yuv_pre;
   DevBuf d_geotab, d_coltab, d_geokeys, d_colkeys, d_changed, d_blist,
       d_blist_count, d_slist, d_slist_count, d_geombits, d_colmbits, d_geotbits, d_coltbits;
@@ -413,7 +413,7 @@ struct Batch {
   void destroy() {
     cudaSetDevice(device);
     for (DevBuf* b : {&d_occ, &d_geo, &d_ay, &d_au, &d_av, &d_meta, &d_b2p, &d_count, &d_err, &d_work,
-                      &d_owned_count, &d_slot_bt, &d_slot_bbase, &d_pos,
+                      &d_owned_count, &d_slot_bt, &d_slot_bbase, &d_slot_nmin, &d_pos,
                       &d_rgb, &d_yuv, &d_part, &d_pix, &d_bt, &d_occ_full, &d_pos_pre, &d_yuv_pre, &d_geotab, &d_coltab,
                       &d_geokeys, &d_colkeys, &d_changed, &d_blist,
                       &d_blist_count, &d_slist, &d_slist_count, &d_geombits, &d_colmbits, &d_geotbits, &d_coltbits})
@@ -543,6 +543,7 @@ struct Batch {
     if (smoothing_geo || smoothing_col || (want_flags & WANT_DEBUG)) {       // boundary classes per slot (count pass -> emit pass)
       CU(d_slot_bt.ensure(std::max<size_t>((size_t)n_slots * 64, 64)));
       CU(d_slot_bbase.ensure(std::max<size_t>((size_t)n_slots * 4, 4)));
+      CU(d_slot_nmin.ensure(std::max<size_t>((size_t)n_slots * 2, 2)));
     }
     CU(d_changed.ensure(std::max<size_t>((size_t)F * 16, 16)));
     CU(d_pos.ensure((size_t)F * cap * 6));
@@ -806,7 +807,7 @@ struct Batch {
     a.frame_tile_begin = reinterpret_cast<const uint32_t*>(m + meta_ftb_off);
     a.block_to_patch = d_b2p.as<uint32_t>();
     a.work = d_work.as<WorkRec>(); a.owned_count = d_owned_count.as<uint32_t>();
-    a.slot_bt = d_slot_bt.as<uint16_t>(); a.slot_bbase = d_slot_bbase.as<uint32_t>();
+    a.slot_bt = d_slot_bt.as<uint16_t>(); a.slot_bbase = d_slot_bbase.as<uint32_t>(); a.slot_nmin = d_slot_nmin.as<uint16_t>();
     a.frame_count = d_count.as<uint32_t>();
     a.err = d_err.as<int>();
     const bool dbg = (want & WANT_DEBUG) != 0;
