@@ -1223,7 +1223,7 @@ __device__ __forceinline__ bool occ_by_tma(const UnpackArgs& a) { return a.prec_
 __device__ __forceinline__ int32_t occ_box_x(uint32_t bx) { return ((int32_t)bx * 4 - 1) & ~15; }
 
 #ifndef TMC2_EMIT_CTAS
-#define TMC2_EMIT_CTAS 7
+#define TMC2_EMIT_CTAS 8
 #endif
 #ifndef TMC2_EMIT_CTAS_SMOOTH
 #define TMC2_EMIT_CTAS_SMOOTH 7
