@@ -226,6 +226,19 @@ TMC2_API tmc2_status tmc2gpu_wait_inputs(tmc2gpu_ctx* ctx);
 TMC2_API tmc2_status tmc2gpu_next_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out);
 TMC2_API tmc2_status tmc2gpu_release_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out);
 
+/* ---- PLY output: the reference's consumer of a PointSet3 (src/writer.rs:15-75 PlyWriter::write) -------------------
+ * The frame `frame` -- as handed out by tmc2gpu_next_frame and not yet released, host or device memory space -- is formatted
+ * ON ITS DEVICE from the copy that still sits in HBM, header (write_header, :31-60) and body (write_body, :62-75), and the
+ * finished file is copied to `dst` (host memory, pinned or not; or device memory on frame->device).  TMC2_PLY_ASCII is byte for
+ * byte the file the reference writes (Format::Ascii); TMC2_PLY_BINARY_LE is the binary_little_endian form the reference lists
+ * but leaves commented out (:10-11, :41-46): the same properties (uint x y z, uchar red green blue), 15 bytes per point.
+ * *file_bytes receives the size of the file; with dst == NULL nothing is written (size query); a destination that is too
+ * small gives TMC2_ERR_CAPACITY (and the size).  Synchronous.                                                          */
+#define TMC2_PLY_ASCII     0u
+#define TMC2_PLY_BINARY_LE 1u
+TMC2_API tmc2_status tmc2gpu_frame_to_ply(tmc2gpu_ctx* ctx, const tmc2_frame_out* frame, uint32_t format,
+                                          void* dst, uint64_t dst_capacity, uint64_t* file_bytes);
+
 /* ---- resident path: planes stay in HBM, kernels only (what bench.py's `value` times) ------------
  * upload copies a GOF to device 0 of the context once; reconstruct_resident launches the whole
  * reconstruction on `cuda_stream` (a cudaStream_t, NULL = the context's own stream) and returns

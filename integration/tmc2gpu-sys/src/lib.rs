@@ -129,7 +129,10 @@ extern "C" {
     pub fn tmc2gpu_wait_inputs(ctx: *mut tmc2gpu_ctx) -> c_int;
     pub fn tmc2gpu_next_frame(ctx: *mut tmc2gpu_ctx, out: *mut tmc2_frame_out) -> c_int;
     pub fn tmc2gpu_release_frame(ctx: *mut tmc2gpu_ctx, out: *mut tmc2_frame_out) -> c_int;
+    pub fn tmc2gpu_frame_to_ply(ctx: *mut tmc2gpu_ctx, frame: *const tmc2_frame_out, format: u32, dst: *mut c_void, dst_capacity: u64, file_bytes: *mut u64) -> c_int;
 }
+pub const TMC2_PLY_ASCII: u32 = 0;
+pub const TMC2_PLY_BINARY_LE: u32 = 1;
 
 /// One reconstructed frame: the payload of reference `PointSet3` (src/codec.rs:20-36).
 pub struct Frame {
@@ -196,6 +199,29 @@ impl Reconstructor {
         };
         self.check(unsafe { tmc2gpu_release_frame(self.ctx, &mut out) })?;
         Ok(Some(Frame { positions, colors }))
+    }
+}
+
+impl Reconstructor {
+    /// Next frame in order as a finished PLY file (what `PlyWriter::write`, src/writer.rs:24-75, would put on disk for it),
+    /// formatted on the GPU; `None` when every submitted frame has been returned.
+    pub fn next_frame_ply(&mut self, format: u32) -> Result<Option<Vec<u8>>, String> {
+        let mut out: tmc2_frame_out = unsafe { std::mem::zeroed() };
+        let st = unsafe { tmc2gpu_next_frame(self.ctx, &mut out) };
+        if st == TMC2_END {
+            return Ok(None);
+        }
+        self.check(st)?;
+        let mut size: u64 = 0;
+        let mut st = unsafe { tmc2gpu_frame_to_ply(self.ctx, &out, format, std::ptr::null_mut(), 0, &mut size) };
+        let mut file = vec![0u8; size as usize];
+        if st == TMC2_OK {
+            st = unsafe { tmc2gpu_frame_to_ply(self.ctx, &out, format, file.as_mut_ptr() as *mut c_void, size, &mut size) };
+        }
+        let released = unsafe { tmc2gpu_release_frame(self.ctx, &mut out) };
+        self.check(st)?;
+        self.check(released)?;
+        Ok(Some(file))
     }
 }
 

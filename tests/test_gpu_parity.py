@@ -581,6 +581,85 @@ def test_device_resident_hand_off_matches_host_frames(gpu_ctx):
         dctx.close()
 
 
+def _ply_frames(ctx, view, n, fmt, **kw):
+    ctx.submit_gof(view)
+    out = [ctx.next_frame_ply(fmt, **kw) for _ in range(n)]
+    assert ctx.next_frame() is None
+    return out
+
+
+@pytest.mark.parametrize("device_output", [False, True], ids=["host-frames", "device-frames"])
+def test_frame_to_ply_equals_the_reference_writer(gpu_ctx, device_output):
+    """tmc2gpu_frame_to_ply formats a frame on the device; the ASCII file equals, byte for byte, what the
+    reference's PlyWriter (src/writer.rs:24-75, restated in tmc2rs_b200/ply.py) writes for the oracle's PointSet3, and the
+    binary_little_endian file holds the same points."""
+    from tmc2rs_b200 import ply
+    g = synth.make_gof(synth.config("small", frames=3))
+    g.params.geometry_smoothing = True
+    g.params.color_smoothing = True
+    view = abi.GofView(g)
+    ctx = codec.Context(device_output=True) if device_output else gpu_ctx
+    try:
+        asc = _ply_frames(ctx, view, 3, abi.PLY_ASCII)
+        binr = _ply_frames(ctx, view, 3, abi.PLY_BINARY_LE)
+        for f in range(3):
+            want = oracle.reconstruct_frame(view, f)
+            assert want["point_count"] > 1000
+            assert asc[f] == ply.ascii_ply(want["positions"], want["colors"])
+            assert binr[f] == ply.binary_ply(want["positions"], want["colors"])
+            pos, col = ply.read_ply(binr[f])
+            assert np.array_equal(pos, want["positions"]) and np.array_equal(col, want["colors"])
+    finally:
+        if device_output:
+            ctx.close()
+
+
+def test_frame_to_ply_digit_widths_empty_frames_no_colours_and_capacity(gpu_ctx):
+    from tmc2rs_b200 import ply
+    # five-digit coordinates: the differential-D1 wrap vector (positions up to 65 5xx), colours 127
+    for absolute in (False, True):
+        g, want = kats.d1_wrap_and_mode1_clamp(absolute)
+        view = abi.GofView(g)
+        pos = np.array(want["positions"], np.uint16).reshape(-1, 3)
+        col = np.full((len(pos), 3), 127, np.uint8)
+        assert max(len(str(v)) for v in pos.ravel().tolist()) == 5 and min(len(str(v)) for v in pos.ravel().tolist()) == 1
+        assert _ply_frames(gpu_ctx, view, 1, abi.PLY_ASCII)[0] == ply.ascii_ply(pos, col)
+        assert _ply_frames(gpu_ctx, view, 1, abi.PLY_BINARY_LE)[0] == ply.binary_ply(pos, col)
+    # a frame without points is a header and nothing else; positions only (attribute_count == 0): three columns
+    g = util.random_small_gof(seed=12, frames=3)
+    occ = g.occ.copy(); occ[1] = 0
+    g.params.attribute_count = 0
+    g2 = abi.Gof(g.width, g.height, occ, g.geo, g.attr_y, g.attr_u, g.attr_v, [g.patches[0][:0], g.patches[1], g.patches[2]], g.params)
+    view = abi.GofView(g2)
+    files = _ply_frames(gpu_ctx, view, 3, abi.PLY_ASCII)
+    empty = np.zeros((0, 3), np.uint16)
+    assert files[0] == files[1] == ply.ascii_ply(empty, None) and b"red" not in files[0]
+    want = oracle.reconstruct_frame(view, 2)
+    assert files[2] == ply.ascii_ply(want["positions"], None)
+    assert _ply_frames(gpu_ctx, view, 3, abi.PLY_BINARY_LE)[2] == ply.binary_ply(want["positions"], None)
+    # destination too small: TMC2_ERR_CAPACITY, the frame is released all the same and the context goes on
+    gpu_ctx.submit_gof(view)
+    with pytest.raises(abi.Tmc2Error) as e:
+        gpu_ctx.next_frame_ply(abi.PLY_ASCII, capacity=64)
+    assert e.value.status == abi.ERR_CAPACITY
+    assert gpu_ctx.next_frame_ply(abi.PLY_ASCII) == files[1]
+    assert gpu_ctx.next_frame_ply(abi.PLY_ASCII, capacity=len(files[2])) == files[2]
+    assert gpu_ctx.next_frame_ply() is None
+
+
+def test_frame_to_ply_full_size_frame_round_trip(gpu_ctx):
+    """BASELINE config 1 (0.8 M points): the ASCII file parses back to the frame, the binary one equals the host writer."""
+    from tmc2rs_b200 import ply
+    g = synth.make_gof(synth.config("c1"))
+    view = abi.GofView(g)
+    fr = gpu_ctx.decode_gof(view)[0]
+    asc = _ply_frames(gpu_ctx, view, 1, abi.PLY_ASCII)[0]
+    pos, col = ply.read_ply(asc)
+    assert np.array_equal(pos, fr.positions) and np.array_equal(col, fr.colors)
+    assert hashlib.sha256(asc).digest() == hashlib.sha256(ply.ascii_ply(fr.positions, fr.colors)).digest()
+    assert _ply_frames(gpu_ctx, view, 1, abi.PLY_BINARY_LE)[0] == ply.binary_ply(fr.positions, fr.colors)
+
+
 def test_one_process_two_devices_shard_frames_in_order():
     """SURVEY 8e inside ONE process: a context over two devices shards the frames of a GOF frame-wise (contiguous halves, no
     collective) and hands them back in order; results equal the single-device context.  Skipped on a one-GPU box."""

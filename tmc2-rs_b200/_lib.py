@@ -28,6 +28,7 @@ SYMBOLS = [
     ("tmc2gpu_wait_inputs", C.c_int, [_P]),
     ("tmc2gpu_next_frame", C.c_int, [_P, C.POINTER(abi.CFrameOut)]),
     ("tmc2gpu_release_frame", C.c_int, [_P, C.POINTER(abi.CFrameOut)]),
+    ("tmc2gpu_frame_to_ply", C.c_int, [_P, C.POINTER(abi.CFrameOut), C.c_uint32, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("tmc2gpu_upload_gof", C.c_int, [_P, C.POINTER(abi.CGof), C.POINTER(_P)]),
     ("tmc2gpu_reconstruct_resident", C.c_int, [_P, _P, _P]),
     ("tmc2gpu_reconstruct_resident_ex", C.c_int, [_P, _P, _P, C.c_uint32]),

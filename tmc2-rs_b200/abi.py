@@ -31,6 +31,7 @@ ORIENTATION_REFERENCE, ORIENTATION_SPEC = 0, 1
 CTX_TWO_PASS_SCAN = 1
 CTX_DEVICE_OUTPUT = 2
 LAUNCH_TIMED = 1
+PLY_ASCII, PLY_BINARY_LE = 0, 1          # tmc2gpu_frame_to_ply formats (src/writer.rs:8-12)
 
 
 class Tmc2Error(RuntimeError):

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtmc2gpu.so")
-SOURCES = ["kernels.cu", "tmc2gpu.cu"]
+SOURCES = ["kernels.cu", "ply.cu", "tmc2gpu.cu"]
 HEADERS = ["device_types.h", os.path.join("..", "..", "include", "tmc2gpu.h")]
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

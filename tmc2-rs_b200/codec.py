@@ -146,6 +146,26 @@ class Context:
         self.check(self.lib.tmc2gpu_release_frame(self.h, C.byref(fo)), "release_frame")
         return ps
 
+    def next_frame_ply(self, fmt: int = abi.PLY_ASCII, capacity: Optional[int] = None) -> Optional[bytes]:
+        """The next frame as a finished PLY file (``src/writer.rs:15-75``), formatted on the device
+        (``tmc2gpu_frame_to_ply``); None at the end.  ``capacity``: size of the destination buffer (default: ask first)."""
+        fo = abi.CFrameOut()
+        st = self.lib.tmc2gpu_next_frame(self.h, C.byref(fo))
+        if st == abi.END:
+            return None
+        self.check(st, "next_frame")
+        try:
+            size = C.c_uint64(0)
+            if capacity is None:
+                self.check(self.lib.tmc2gpu_frame_to_ply(self.h, C.byref(fo), fmt, None, 0, C.byref(size)), "frame_to_ply")
+                capacity = int(size.value)
+            buf = np.empty(max(capacity, 1), np.uint8)
+            self.check(self.lib.tmc2gpu_frame_to_ply(self.h, C.byref(fo), fmt, buf.ctypes.data, capacity, C.byref(size)),
+                       "frame_to_ply")
+            return buf[:int(size.value)].tobytes()
+        finally:
+            self.lib.tmc2gpu_release_frame(self.h, C.byref(fo))
+
     def next_frame_device(self):
         """Device-resident hand-off (contexts created with ``device_output=True``): ``(point_count, positions device pointer,
         colours device pointer, device ordinal, release)`` of the next frame, or None at the end.  The pointers stay valid until

@@ -268,4 +268,12 @@ int launch_yuv_to_rgb_flat(const uint16_t* yuv, uint8_t* rgb, uint64_t n, void* 
 int launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, void* stream);
 int kernel_launch_count_reset();   // returns launches since the last reset
 
+// ply.cu: a frame in HBM formatted as the body of a PLY file (src/writer.rs:62-75).  measure -> scan -> write for the ASCII
+// form (block_sums / block_offs: one entry per 1024 points; *total = body bytes), write alone for the binary records.
+constexpr uint64_t ply_blocks(uint64_t n_points) { return (n_points + 1023u) / 1024u; }
+int launch_ply_measure(const uint16_t* pos, const uint8_t* rgb, uint64_t n, uint32_t* block_sums, void* stream);
+int launch_ply_scan(const uint32_t* block_sums, uint64_t n, unsigned long long* block_offs, unsigned long long* total, void* stream);
+int launch_ply_write(const uint16_t* pos, const uint8_t* rgb, uint64_t n, const unsigned long long* block_offs, uint8_t* body,
+                     bool ascii, void* stream);
+
 }  // namespace tmc2

@@ -386,7 +386,8 @@ struct Batch {
   uint32_t group_frames = 32;         // frames per smoothing group (one group = no post-pass tails between groups; a GOF is <= 32 frames)
   uint32_t group_frames_eff = 8;      // after fitting the dense tables into the memory budget
   std::vector<cudaEvent_t> ev_grp;    // 2 per group: around the unpack launch
-  PinBuf h_in, h_meta, h_small, h_out;
+  PinBuf h_in, h_meta, h_small, h_out, h_ply;
+  DevBuf d_ply, d_ply_sums;           // tmc2gpu_frame_to_ply: body scratch, block sums + offsets + total
   size_t meta_patch_off = 0, meta_slot_off = 0, meta_tf_off = 0, meta_ftb_off = 0, meta_bytes = 0;
 
   cudaEvent_t ev[8] = {};             // stage boundaries: 0 start,1 after b2p,2 after unpack,3 geo,4 col,5 rgb
@@ -416,9 +417,9 @@ struct Batch {
                       &d_owned_count, &d_slot_bt, &d_slot_bbase, &d_slot_nmin, &d_pos,
                       &d_rgb, &d_yuv, &d_part, &d_pix, &d_bt, &d_occ_full, &d_pos_pre, &d_yuv_pre, &d_geotab, &d_coltab,
                       &d_geokeys, &d_colkeys, &d_changed, &d_blist,
-                      &d_blist_count, &d_slist, &d_slist_count, &d_geombits, &d_colmbits, &d_geotbits, &d_coltbits})
+                      &d_blist_count, &d_slist, &d_slist_count, &d_geombits, &d_colmbits, &d_geotbits, &d_coltbits, &d_ply, &d_ply_sums})
       b->release();
-    for (PinBuf* b : {&h_in, &h_meta, &h_small, &h_out}) b->release();
+    for (PinBuf* b : {&h_in, &h_meta, &h_small, &h_out, &h_ply}) b->release();
     for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     if (ev_counts) cudaEventDestroy(ev_counts), ev_counts = nullptr;
     if (ev_inputs_free) cudaEventDestroy(ev_inputs_free), ev_inputs_free = nullptr;
@@ -1396,6 +1397,93 @@ tmc2_status tmc2gpu_release_frame(tmc2gpu_ctx* ctx, tmc2_frame_out* out) {
   if (!known || !b->busy) { ctx->last_error = "release_frame: frame was not handed out by this context"; return TMC2_ERR_STATE; }
   out->_handle = nullptr; out->positions = nullptr; out->colors = nullptr;
   if (++b->frames_released >= b->F) b->busy = false;
+  return TMC2_OK;
+}
+
+// ---- PLY output (src/writer.rs:15-75), formatted on the device -------------------------------------------------
+static std::string ply_header(uint32_t format, uint64_t n, bool colours) {
+  std::string h = "ply\n";                                                      // write_header, src/writer.rs:31-60
+  h += format == TMC2_PLY_ASCII ? "format ascii 1.0\n" : "format binary_little_endian 1.0\n";
+  h += "element vertex " + std::to_string(n) + "\n";
+  h += "property uint x\nproperty uint y\nproperty uint z\n";
+  if (colours) h += "property uchar red\nproperty uchar green\nproperty uchar blue\n";
+  h += "element face 0\nproperty list uint8 int32 vertex_index\nend_header\n";
+  return h;
+}
+
+tmc2_status tmc2gpu_frame_to_ply(tmc2gpu_ctx* ctx, const tmc2_frame_out* frame, uint32_t format, void* dst, uint64_t dst_capacity,
+                                 uint64_t* file_bytes) {
+  if (!ctx || !frame || !file_bytes || !frame->_handle || (format != TMC2_PLY_ASCII && format != TMC2_PLY_BINARY_LE))
+    return TMC2_ERR_INVALID_ARG;
+  *file_bytes = 0;
+  Err& err = ctx->err;
+  err = Err();
+  Batch* b = static_cast<Batch*>(frame->_handle);
+  bool known = false;
+  for (auto& v : ctx->slots) for (auto& s : v) known |= s.get() == b;
+  if (!known || !b->busy || !b->counts_ready) { ctx->last_error = "frame_to_ply: frame was not handed out by this context (or already released)"; return TMC2_ERR_STATE; }
+  // which frame of the batch: by its buffer (device slab or offset inside the pinned output area)
+  uint32_t local = b->F;
+  for (uint32_t k = 0; k < b->F; ++k) {
+    const void* p = frame->memory_space == 1 ? static_cast<const void*>(b->d_pos.as<uint8_t>() + (size_t)k * b->cap * 6)
+                                              : static_cast<const void*>(b->h_out.as<uint8_t>() + b->out_pos_off[k]);
+    if (p == static_cast<const void*>(frame->positions) && b->counts[k] == frame->point_count) { local = k; break; }   // empty frames share an offset
+  }
+  if (local == b->F) { ctx->last_error = "frame_to_ply: not a frame of this context"; return TMC2_ERR_STATE; }
+  auto body = [&]() -> tmc2_status {
+    const uint64_t n = frame->point_count;
+    const bool colours = b->params.attribute_count != 0;
+    const std::string head = ply_header(format, n, colours);
+    const uint16_t* dpos = reinterpret_cast<const uint16_t*>(b->d_pos.as<uint8_t>() + (size_t)local * b->cap * 6);
+    const uint8_t* drgb = colours ? b->d_rgb.as<uint8_t>() + (size_t)local * b->cap * 3 : nullptr;
+    CU(cudaSetDevice(b->device));
+    cudaStream_t s = b->stream;                       // idle: the GOF of a handed-out frame is complete, the slot is still taken
+    const uint64_t nb = ply_blocks(n);
+    uint64_t body_bytes = n * (colours ? 15u : 12u);
+    unsigned long long* d_offs = nullptr;
+    if (format == TMC2_PLY_ASCII && n) {
+      // [block sums u32 x nb, padded][block offsets u64 x nb][total u64]
+      const size_t sums_bytes = (nb * 4 + 7) / 8 * 8;
+      CU(b->d_ply_sums.ensure(sums_bytes + nb * 8 + 8));
+      CU(b->h_ply.ensure(8));
+      uint32_t* d_sums = b->d_ply_sums.as<uint32_t>();
+      d_offs = reinterpret_cast<unsigned long long*>(b->d_ply_sums.as<uint8_t>() + sums_bytes);
+      CU((cudaError_t)launch_ply_measure(dpos, drgb, n, d_sums, s));
+      CU((cudaError_t)launch_ply_scan(d_sums, n, d_offs, d_offs + nb, s));
+      CU(cudaMemcpyAsync(b->h_ply.p, d_offs + nb, 8, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      body_bytes = *static_cast<const unsigned long long*>(b->h_ply.p);
+    }
+    *file_bytes = head.size() + body_bytes;
+    if (!dst) return TMC2_OK;                         // size query
+    if (dst_capacity < *file_bytes) {
+      err.st = TMC2_ERR_CAPACITY;
+      err.msg = fmt("frame_to_ply: the file has %llu bytes, the destination %llu", (unsigned long long)*file_bytes, (unsigned long long)dst_capacity);
+      return err.st;
+    }
+    cudaPointerAttributes at{};
+    const bool dst_on_device = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    if (dst_on_device && at.device != b->device) {
+      err.st = TMC2_ERR_INVALID_ARG; err.msg = "frame_to_ply: device destination is not on the frame's device";
+      return err.st;
+    }
+    uint8_t* out_body = static_cast<uint8_t*>(dst) + head.size();
+    if (dst_on_device) {
+      CU(cudaMemcpyAsync(dst, head.data(), head.size(), cudaMemcpyHostToDevice, s));
+      CU((cudaError_t)launch_ply_write(dpos, drgb, n, d_offs, out_body, format == TMC2_PLY_ASCII, s));
+    } else {
+      memcpy(dst, head.data(), head.size());
+      if (n) {
+        CU(b->d_ply.ensure(body_bytes + 16));
+        CU((cudaError_t)launch_ply_write(dpos, drgb, n, d_offs, b->d_ply.as<uint8_t>(), format == TMC2_PLY_ASCII, s));
+        CU(cudaMemcpyAsync(out_body, b->d_ply.p, body_bytes, cudaMemcpyDeviceToHost, s));
+      }
+    }
+    CU(cudaStreamSynchronize(s));
+    return TMC2_OK;
+  };
+  if (body()) return ctx->fail();
   return TMC2_OK;
 }
 
