@@ -322,16 +322,24 @@ def main():
     # a kernel-only step repeats the rank's GOF list until it holds at least `inner` GOFs (strong scaling at N = 8 leaves a
     # rank two GOFs of ~1 ms in total: far too short to time)
     inner = max(1, -(-32 // len(sizes))) if mode == "strong" else 1
+    # every resident GOF keeps ONE stream for all of its launches (two launches of the same resident on different streams
+    # would not be ordered with respect to each other)
+    stream_of, nth = {}, 0
+    for sz in sorted(residents, reverse=True):
+        for r in residents[sz]:
+            stream_of[id(r)] = tstreams[nth % n_res]
+            nth += 1
     plan = []                                            # (resident, stream) of one kernel-only step
     k = 0
     for _ in range(inner):
         for sz in sizes:
             rs = residents[sz]
-            plan.append((rs[k % len(rs)], tstreams[k % n_res]))
+            r = rs[k % len(rs)]
+            plan.append((r, stream_of[id(r)]))
             k += 1
     for rs in residents.values():                        # every resident once (buffers, tables), then the usual warm-up
         for r in rs:
-            r.reconstruct(tstream.cuda_stream)
+            r.reconstruct(stream_of[id(r)].cuda_stream)
     for _ in range(max(1, min(args.warmup, 3))):
         for r, t in plan[:3 * n_res]:
             r.reconstruct(t.cuda_stream)
